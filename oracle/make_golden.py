@@ -1,0 +1,133 @@
+"""Generate tests/golden/*.npz from the LIVE, UNMODIFIED reference.  Build-container only.
+
+    python -m oracle.make_golden
+
+The reference has no tests or golden vectors; these fixtures are outputs of
+the reference's own modules (imported from /root/reference through oracle/ref_shim.py) on
+seeded inputs, seeded reference-layout weights (oracle.selfc_oracle.make_state_dict) and an
+injected eps.  They pin oracle/selfc_oracle.py, which in turn is what the CUDA path is
+checked against on the GPU box (where /root/reference does not exist).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import ref_shim, selfc_oracle as so  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def sd_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.numpy().tobytes())
+    return h.hexdigest()
+
+
+def case_net(ref, name, b, t, hh, ww, wseed, xseed, gain=1.0):
+    sd = so.make_state_dict(wseed, gain)
+    net = ref.build_net(t)
+    net.load_state_dict(sd, strict=True)          # the reference's own strict load
+    x = so.make_frames(b, t, hh, ww, xseed)
+    h, w = hh // 4, ww // 4
+    eps = so.make_eps(b, t, h, w, xseed + 7)       # regenerated from the seed by the tests (not stored)
+    with torch.no_grad():
+        # per-stage capture: SelfCInvNet calls op.forward(...) directly (:456,:487), which bypasses
+        # forward hooks, so the instances' forward attributes are wrapped instead.
+        stages = {}
+
+        def tap(op, key):
+            orig = op.forward
+
+            def wrapped(*a, **k):
+                o = orig(*a, **k)
+                stages[key + ("_rev" if (len(a) > 1 and a[1]) or k.get("rev") else "")] = o.clone()
+                return o
+            op.forward = wrapped
+        for i, op in enumerate(net.operations):
+            tap(op, f"op{i}")
+        out, loss_c = net(x)
+        from models.modules.Quantization import Quantization   # reference module
+        lr = Quantization()(out[:, :3])
+        ref.inject_eps(net, eps)
+        up_stages = {}
+
+        def grab(key):
+            def hook(m, a, o):          # must return None: a returned tensor would REPLACE the output
+                up_stages[key] = o.clone()
+            return hook
+        hooks = [net.stp_net.other_stp_modules.register_forward_hook(grab("feat")),
+                 net.stp_net.global_m1.register_forward_hook(grab("ga1")),
+                 net.stp_net.local_m1.register_forward_hook(grab("lm1"))]
+        hr, hf = net(x=lr, rev=True)
+        for hk in hooks:
+            hk.remove()
+        params = net.stp_net.parameters            # [B,720,T,h,w] (attribute shadowing)
+        params = params.transpose(1, 2).reshape(b * t, 720, h, w)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        meta=np.array([b, t, hh, ww, wseed, xseed], dtype=np.int64), gain=np.float32(gain),
+        sd_sha256=np.array(sd_digest(sd)),
+        x=x.numpy(), eps_seed=np.int64(xseed + 7), eps_sum=np.float64(eps.double().sum().item()),
+        down_fa=stages["op0"].numpy(), down_blk1=stages["op1"].numpy(), down_out=out.numpy(),
+        loss_c=np.float32(loss_c.item()),
+        lr=lr.numpy(),
+        stp_lm1=up_stages["lm1"].numpy(), stp_ga1=up_stages["ga1"].numpy(), stp_feat=up_stages["feat"].numpy(),
+        params_sub=params[:, ::16].contiguous().numpy(),
+        hf=hf.numpy(), up_after_blk8=stages["op8_rev"].numpy(),
+        up_after_blk1=stages["op1_rev"].numpy(), hr=hr.numpy())
+    print(name, "down", tuple(out.shape), "hr", tuple(hr.shape),
+          "lr range", float(out[:, :3].min()), float(out[:, :3].max()),
+          "hr err vs x", float((hr - x).abs().max()))
+
+
+def case_fa(ref):
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(3, 3, 16, 24, generator=g)
+    z = torch.randn(3, 51, 4, 6, generator=g)
+    fa = ref.arch.FrequencyAnalyzer(3)
+    with torch.no_grad():
+        np.savez_compressed(os.path.join(OUT, "fa.npz"), x=x.numpy(), fwd=fa(x).numpy(),
+                            z=z.numpy(), rev=fa(z, rev=True).numpy())
+
+
+def case_metrics(ref):
+    import data.util as dutil                      # reference modules
+    import utils.util as uutil
+    from models.Guassian import Guassian_downsample
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand(4, 3, 40, 56, generator=g)
+    bb = (a + 0.05 * torch.randn(4, 3, 40, 56, generator=g)).clamp(0, 1)
+    ya, yb = dutil.rgb_to_ycbcr(a), dutil.rgb_to_ycbcr(bb)
+    # calculate_psnr / calculate_ssim hard-code .cuda(0) (utils/util.py:206-207,602-603): the
+    # arithmetic they wrap is called directly instead - ssim() as-is, psnr by its one-line formula.
+    ssims = [float(uutil.ssim(ya[i:i + 1], yb[i:i + 1], data_range=1.0)) for i in range(4)]
+    psnrs = [20.0 * torch.log10(1.0 / torch.sqrt(torch.mean((ya[i] - yb[i]) ** 2.0))).item() for i in range(4)]
+    lr_ref = Guassian_downsample(a.transpose(0, 1)).transpose(0, 1)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), a=a.numpy(), b=bb.numpy(), ya=ya.numpy(),
+                        ssim=np.array(ssims), psnr=np.array(psnrs), lr_ref=lr_ref.numpy())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    ref = ref_shim.load_reference()
+    case_fa(ref)
+    case_metrics(ref)
+    case_net(ref, "net_t3", b=2, t=3, hh=32, ww=48, wseed=0, xseed=11)
+    case_net(ref, "net_t7", b=1, t=7, hh=32, ww=40, wseed=1, xseed=12)
+    # partial 8x16 output tiles, non-integral 32x32 pooling windows (h=10, w=18), larger weights
+    case_net(ref, "net_t2_gain", b=2, t=2, hh=40, ww=72, wseed=2, xseed=13, gain=1.5)
+
+
+if __name__ == "__main__":
+    main()
