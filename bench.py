@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the SelfC-large 4x rescaling hot path (BASELINE.json: "1080p 4x rescale frames/s (down+up)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32] [--frames F]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One step = one synthetic UVG-shape 1080p group of F frames (default 100 = 15 GOPs of 7, the last one padded with
+copies of the final frame as models/SelfC_model.py:204-209 does) taken through down -> 8-bit quantise -> up on each
+GPU.  Groups are independent units: rank r works on its own group, no data-path collective (scaling = weak).
+
+`value`  : frames/s with the group resident in HBM (fp32 NCHW), CUDA-event timed, max over ranks.
+`e2e`    : the same through the public engine call with HOST (pinned) frames: H2D of the group and D2H of the LR codes
+           and the reconstructed HR frames inside the timed region.
+`roofline`: the dominant kernel class (the (1,3,3) dense-block convolutions), from a separately instrumented step
+           (CUDA events around every launch on the launching stream, selfc_prof_*).
+`cpu_baseline` / `--impl reference`: the CPU restatement of the reference's PyTorch path (oracle/, pinned to the
+           reference's own outputs) on the box's host cores, on a bounded crop of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+HR_H, HR_W, GOP = 1080, 1920, 7
+METRIC = "1080p 4x rescale frames/s (down+up)"
+FLOP_PER_LR_PX = 10_885_760          # algorithmic conv/linear FLOPs per LR pixel-frame, down + up
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("SELFC_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--frames", type=int, default=100, help="frames per 1080p group (one step = one group per GPU)")
+    ap.add_argument("--gops-per-launch", type=int, default=1)
+    ap.add_argument("--height", type=int, default=HR_H)
+    ap.add_argument("--width", type=int, default=HR_W)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def make_group(frames: int, hh: int, ww: int, seed: int, device) -> torch.Tensor:
+    """Smooth synthetic 8-bit video [frames,3,hh,ww] fp32 in [0,1] generated on the device (SURVEY 8d inputs)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    base = torch.rand(1, 3, max(hh // 16, 2), max(ww // 16, 2), generator=g, device=device)
+    up = torch.nn.functional.interpolate(base, size=(hh, ww), mode="bicubic", align_corners=False)
+    drift = torch.linspace(0, 0.1, frames, device=device).reshape(frames, 1, 1, 1)
+    out = torch.empty(frames, 3, hh, ww, device=device)
+    for f0 in range(0, frames, 10):
+        f1 = min(frames, f0 + 10)
+        noise = torch.randn(f1 - f0, 3, hh, ww, generator=g, device=device) * 0.02
+        out[f0:f1] = torch.round((up + drift[f0:f1] + noise).clamp_(0, 1) * 255.0) / 255.0
+    return out
+
+
+def gop_slices(frames: int):
+    """GOP decomposition of a group: full GOPs of 7, then a padded tail (models/SelfC_model.py:196-209)."""
+    idx = []
+    for g0 in range(0, frames, GOP):
+        ids = list(range(g0, min(frames, g0 + GOP)))
+        real = len(ids)
+        ids += [frames - 1] * (GOP - real)
+        idx.append((ids, real))
+    return idx
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_fps(hh: int, ww: int, steps: int, warmup: int, crop=(272, 480)):
+    """The reference's CPU path (oracle port, all host threads) on a bounded crop of the 1080p workload: 7 frames of
+    crop[0] x crop[1] per step; frames/s in 1080p-frame equivalents = 7 * crop_area / frame_area / seconds."""
+    from oracle import selfc_oracle as so
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ch, cw = min(crop[0], hh), min(crop[1], ww)
+    sd = so.make_state_dict(0)
+    x = so.make_frames(1, GOP, ch, cw, 1234)
+    eps = so.make_eps(1, GOP, ch // 4, cw // 4, 42)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            so.rescale(sd, x, eps, GOP)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    frames_eq = GOP * (ch * cw) / float(hh * ww)
+    sample = f"{GOP} frames of a {ch}x{cw} crop of the {hh}x{ww} clip per step ({frames_eq:.4f} frame-equivalents), fp32, torch CPU ops"
+    return frames_eq / sec, sec * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fps, ms, cores, sample = cpu_reference_fps(args.height, args.width, max(1, args.steps), max(0, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"SelfC-large 4x rescaling, synthetic {args.height}x{args.width} clips (CPU sample)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from selfc_b200.engine import Engine, launch_count
+    from oracle import selfc_oracle as so   # only for the seeded reference-layout weights and the cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    hh, ww, frames = args.height, args.width, args.frames
+    h, w = hh // 4, ww // 4
+    eng = Engine(dev, args.mode)
+    eng.load_state(so.make_state_dict(0))
+    group = make_group(frames, hh, ww, 1234 + rank, dev)
+    gops = gop_slices(frames)
+    gpl = max(1, args.gops_per_launch)
+    lr_out = torch.empty(frames, 3, h, w, dtype=torch.uint8, device=dev)
+    hr_out = torch.empty(frames, 3, hh, ww, dtype=torch.float32, device=dev)
+
+    def step_resident(step_idx: int):
+        """one group, frames already in HBM"""
+        for g0 in range(0, len(gops), gpl):
+            chunk = gops[g0:g0 + gpl]
+            ids = [i for ids, _ in chunk for i in ids]
+            full = all(real == GOP for _, real in chunk)
+            x = group[ids[0]:ids[-1] + 1] if full else group[ids]
+            lr_u8, rec = eng.rescale(x, GOP, seed=42, offset=step_idx * len(gops) + g0)
+            if full:
+                lr_out[ids[0]:ids[-1] + 1] = lr_u8
+                hr_out[ids[0]:ids[-1] + 1] = rec
+            else:
+                pos = 0
+                for gids, real in chunk:
+                    lr_out[gids[0]:gids[0] + real] = lr_u8[pos:pos + real]
+                    hr_out[gids[0]:gids[0] + real] = rec[pos:pos + real]
+                    pos += GOP
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput --------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    ev1.record()
+    barrier()
+    launches = launch_count() - n0
+    clocks = sampler.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * frames * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public call with host buffers ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.empty(group.shape, dtype=torch.float32).pin_memory()
+        host_in.copy_(group)
+        host_lr = torch.empty(lr_out.shape, dtype=torch.uint8).pin_memory()
+        host_hr = torch.empty(hr_out.shape, dtype=torch.float32).pin_memory()
+
+        def step_e2e(step_idx: int):
+            dgroup = host_in.to(dev, non_blocking=True)
+            for g0, (ids, real) in enumerate(gops):
+                x = dgroup[ids[0]:ids[0] + GOP] if real == GOP else dgroup[ids]
+                lr_u8, rec = eng.rescale(x, GOP, seed=42, offset=step_idx * len(gops) + g0)
+                host_lr[ids[0]:ids[0] + real].copy_(lr_u8[:real], non_blocking=True)
+                host_hr[ids[0]:ids[0] + real].copy_(rec[:real], non_blocking=True)
+            torch.cuda.synchronize()
+
+        e_steps = max(1, min(args.steps, 3))
+        step_e2e(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            step_e2e(1 + i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * frames * e_steps / float(dt.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_lr.numel() + host_hr.numel() * 4),
+               "steps": e_steps, "timing": "host wall clock around pinned H2D + rescale + D2H, max over ranks"}
+
+    # ---- roofline of the dominant kernel class (instrumented step, outside the timed regions) ---------------------
+    roofline = None
+    prof = None
+    if rank == 0:
+        eng.prof_enable(True)
+        ids, _ = gops[0]
+        eng.rescale(group[ids[0]:ids[0] + GOP] if frames >= GOP else group[ids], GOP, seed=1, offset=0)
+        torch.cuda.synchronize()
+        prof = eng.prof_read()
+        eng.prof_enable(False)
+        hbm, tf_burst, tf_sust, src = peaks()
+        tot_ms = sum(v["ms"] for v in prof.values())
+        c = prof["conv3x3"]
+        ach = c["work"] / (c["ms"] / 1e3) / 1e12 if c["ms"] > 0 else 0.0
+        roofline = {"kernel": "conv3x3 dense-block convolution (all launches of one 7-frame GOP, down+up)",
+                    "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
+                    "traffic": None, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches": c["launches"],
+                    "share_of_step": c["ms"] / tot_ms if tot_ms else None,
+                    "classes": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                                    "share": round(v["ms"] / tot_ms, 4) if tot_ms else None} for k, v in prof.items()}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        fps, ms_cpu, cores, sample = cpu_reference_fps(hh, ww, steps=2, warmup=1)
+        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+
+    whole_tflops = value * (h * w) * FLOP_PER_LR_PX / 1e12
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"SelfC-large 4x rescaling (down + 8-bit quantise + up), synthetic UVG-shape {hh}x{ww} "
+                                   f"{frames}-frame group per GPU per step = {len(gops)} GOPs of {GOP} (tail padded), {args.mode} mode",
+                       "frames_per_step_per_gpu": frames, "gops_per_launch": gpl, "weights": "seeded random, reference state_dict layout",
+                       "l2": "inputs larger than L2 (one group = %.2f GB fp32)" % (group.numel() * 4 / 1e9)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "algorithmic_tflops": whole_tflops}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

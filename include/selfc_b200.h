@@ -1,0 +1,105 @@
+/* selfc_b200 C-ABI -- the drop-in boundary of the SelfC-large 4x rescaling hot path on B200 (sm_100a).
+ *
+ * Plain C symbols, device pointers and sizes only: no torch / C++ types cross this boundary.
+ * The reference (tianyuan168326/SelfC) has no native code; each entry point below replaces a
+ * stretch of stock-PyTorch ops in the reference's Python.  Citations are relative to
+ * /root/reference/codes.  The host-side mirror of the reference's operator interface
+ * (selfc_b200/arch.py: SelfCInvNet.forward(x, rev)) binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SELFC_E_* code; selfc_last_error() gives the
+ *     text for the calling thread.  Nothing throws, nothing synchronises the device.
+ *   - all pointers are DEVICE pointers (16-byte aligned) unless the name says host; `stream` is a
+ *     cudaStream_t passed as void* (the caller's current torch stream).
+ *   - frames are the reference's layouts: [B*T, C, H, W] fp32 NCHW; H, W multiples of 4; h=H/4, w=W/4.
+ *   - the library allocates nothing persistent except the packed weight cache inside a selfc_ctx; all
+ *     activations live in a caller-provided workspace (selfc_workspace_bytes).
+ */
+#ifndef SELFC_B200_H
+#define SELFC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SELFC_OK 0
+#define SELFC_E_ARG (-1)       /* bad shape / null pointer / misaligned pointer */
+#define SELFC_E_STATE (-2)     /* weights not loaded, wrong device, workspace too small */
+#define SELFC_E_CUDA (-3)      /* a CUDA runtime / driver call or a launch failed */
+#define SELFC_E_UNSUPPORTED (-4)
+
+/* precision modes (new knob, supplied out of band; SURVEY 8b "Config") */
+#define SELFC_MODE_FP32 0      /* fp32 storage, fp32 FMA convolutions: the <=1e-3 numerics gate */
+#define SELFC_MODE_BF16 1      /* bf16 activations, tcgen05 kind::f16 implicit-GEMM, fp32 accumulate/state */
+
+#define SELFC_NUM_PARAMS 354   /* state_dict tensors of SelfCInvNet (vid4 YAML) */
+
+typedef struct selfc_ctx selfc_ctx;
+
+int selfc_version(void);
+const char* selfc_last_error(void);
+
+/* ---- context: packed-weight cache for one device --------------------------------------------------- */
+int selfc_ctx_create(selfc_ctx** out, int device, int mode);
+int selfc_ctx_destroy(selfc_ctx* ctx);
+int selfc_ctx_mode(const selfc_ctx* ctx);
+/* Re-pack the reference-layout parameters (models/modules/SelfC_GMM_arch_inv.py:433-448 registration order,
+ * SURVEY A.8; `params[i]` = device pointer to the i-th fp32 tensor) into kernel layout.  Called after
+ * load_state_dict / .to(); replaces base_model.py:87-107's implicit "weights are just nn.Parameters". */
+int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* params_host_array_of_dev_ptrs, int n_params, void* stream);
+
+size_t selfc_workspace_bytes(const selfc_ctx* ctx, int B, int T, int h, int w);
+
+/* ---- the path: SelfCInvNet.forward (SelfC_GMM_arch_inv.py:450-490) ---------------------------------- */
+/* rev=False (:454-469): FrequencyAnalyzer + 8 InvBlockExp.  out51 [B*T,51,h,w] fp32 (may be NULL);
+ * lr_u8 [B*T,3,h,w] = Quantization of out51[:, :3] (Quantization.py:4-17, models/SelfC_model.py:217-222)
+ * as 8-bit codes, lr_q the same on the 1/255 fp32 grid (either may be NULL). */
+int selfc_down(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_u8, float* lr_q,
+               int B, int T, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+/* rev=True (:470-490): STPNet prior + soft-GMM sample + 8 inverse couplings + FrequencyAnalyzer reverse.
+ * lr [B*T,3,h,w] fp32.  eps: NULL -> counter-based Philox4x32-10 noise keyed (seed, offset) and indexed by
+ * the reference's eps linear index in [B,48,5,T,h,w] (:412-415); non-NULL -> injected noise in that layout.
+ * hr [B*T,3,H,W]; hf [B*T,48,h,w] (recon_hf, may be NULL). */
+int selfc_up(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset,
+             float* hr, float* hf, int B, int T, int H, int W,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- components (each is one row of SURVEY 8a; used by the parity tests) ---------------------------- */
+/* a1 FrequencyAnalyzer.forward(rev=False) :62-78 -> [N,51,h,w]; a10 rev=True :79-82 -> [N,3,H,W] */
+int selfc_fa_fwd(const float* x, float* out51, int N, int H, int W, void* stream);
+int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream);
+/* a4 Quantization.py:4-17 on [n] floats */
+int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* stream);
+/* a3 D2DTInput.forward (Subnet_constructor.py:115-133) for the dense block stored at parameter index
+ * `first_param` (its conv1.weight); x [B*T,Cin,h,w] -> y [B*T,Cout,h,w], both fp32 NCHW. */
+int selfc_d2dt(selfc_ctx* ctx, int first_param, const float* x, float* y, int B, int T, int h, int w,
+               void* workspace, size_t workspace_bytes, void* stream);
+/* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
+ * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
+int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,
+                     int B, int T, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+/* a7 sampler (:383-394): params [B*T,720,h,w] (channel hf*15+k*3+j), eps as in selfc_up -> v [B*T,48,h,w] */
+int selfc_gmm_sample(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* v,
+                     int B, int T, int h, int w, void* stream);
+/* the noise selfc_up would draw for (seed, offset), in the reference layout [B,48,5,T,h,w] */
+int selfc_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, int h, int w, void* stream);
+
+/* Optional per-launch timing for the roofline report: while enabled, every launch of selfc_down / selfc_up is
+ * bracketed by CUDA events on the caller's stream.  Classes: 0 (1,3,3) dense-block convs [work = FLOPs],
+ * 1 (3,1,1) conv5 + coupling [FLOPs], 2 GlobalAgg [bytes], 3 GMM head [FLOPs], 4 sampler [bytes], 5 layout [bytes].
+ * selfc_prof_read synchronises on the recorded events, sums ms / algorithmic work / launches per class, and clears. */
+#define SELFC_PROF_CLASSES 6
+int selfc_prof_enable(selfc_ctx* ctx, int on);
+int selfc_prof_read(selfc_ctx* ctx, int ncls, double* ms, double* work, uint64_t* launches);
+
+/* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
+uint64_t selfc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELFC_B200_H */

@@ -369,3 +369,40 @@ def gaussian_downsample(x: torch.Tensor) -> torch.Tensor:
     v = F.pad(x.reshape(-1, 1, hh, ww), [14, 14, 14, 14], mode="reflect")
     v = F.conv2d(v, gaussian_kernel_13()[None, None], stride=4)[:, :, 2:-2, 2:-2]
     return v.reshape(n, c, v.shape[2], v.shape[3])
+
+
+# --------------------------------------------------------------------------------------
+# counter-based noise of the CUDA path (selfc_b200/csrc/common.cuh: philox_normal) - numpy restatement
+# --------------------------------------------------------------------------------------
+def philox4x32_10(c, k):
+    """Philox4x32-10 (Salmon et al., SC'11): c uint32[...,4] counters, k uint32[...,2] keys -> uint32[...,4]."""
+    c = [c[..., i].astype(np.uint64) for i in range(4)]
+    k0 = k[..., 0].astype(np.uint64)
+    k1 = k[..., 1].astype(np.uint64)
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[0]
+        p1 = M1 * c[2]
+        n0 = ((p1 >> np.uint64(32)) ^ c[1] ^ k0) & MASK
+        n1 = p1 & MASK
+        n2 = ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & MASK
+        n3 = p0 & MASK
+        c = [n0, n1, n2, n3]
+        k0 = (k0 + W0) & MASK
+        k1 = (k1 + W1) & MASK
+    return np.stack(c, -1).astype(np.uint32)
+
+
+def philox_normal(idx: np.ndarray, seed: int, offset: int) -> np.ndarray:
+    """eps element `idx` of stream (seed, offset): counter (idx_lo, idx_hi, off_lo, off_hi), key (seed_lo, seed_hi),
+    Box-Muller cosine branch on the first two output words, in float32 like the device code."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    ctr = np.stack([idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32),
+                    np.full_like(idx, offset & 0xFFFFFFFF), np.full_like(idx, (offset >> 32) & 0xFFFFFFFF)], -1).astype(np.uint32)
+    key = np.stack([np.full_like(idx, seed & 0xFFFFFFFF), np.full_like(idx, (seed >> 32) & 0xFFFFFFFF)], -1).astype(np.uint32)
+    r = philox4x32_10(ctr, key)
+    scale = np.float32(2.3283064365386963e-10)
+    u1 = (r[..., 0].astype(np.float32) + np.float32(1.0)) * scale
+    u2 = r[..., 1].astype(np.float32) * scale
+    rad = np.sqrt(np.float32(-2.0) * np.log(u1).astype(np.float32)).astype(np.float32)
+    return (rad * np.cos(np.float64(np.pi) * (np.float32(2.0) * u2).astype(np.float64)).astype(np.float32)).astype(np.float32)

@@ -1,0 +1,116 @@
+// Shared declarations for the selfc_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/selfc_b200.h"
+
+namespace selfc {
+
+constexpr int kHF = 48;         // 3 * 4 * 4 high-frequency channels
+constexpr int kGmmK = 5;
+constexpr int kGrowth = 32;     // D2DTInput gc
+constexpr int kZPitch = 52;     // latent state [M][52] fp32: ch 0..2 = x1 (LR part), 3 = pad, 4..51 = x2 (HF part)
+constexpr int kZHf = 4;
+constexpr int kStpC = 64;
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+uint64_t& launch_counter();
+
+#define SELFC_CHECK_ARG(cond, ...)            \
+  do {                                        \
+    if (!(cond)) {                            \
+      selfc::set_error(__VA_ARGS__);          \
+      return SELFC_E_ARG;                     \
+    }                                         \
+  } while (0)
+
+#define SELFC_CUDA(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      selfc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SELFC_E_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define SELFC_LAUNCH_CHECK(name)                                                           \
+  do {                                                                                     \
+    selfc::launch_counter()++;                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) {                                                              \
+      selfc::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));          \
+      return SELFC_E_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define SELFC_TRY(expr)        \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- element helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+// 4 consecutive elements -> float4
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// ---- Philox4x32-10 counter RNG (keyed on the reference's eps linear index; SURVEY 7.2 "RNG") ---------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0;
+    uint64_t p1 = (uint64_t)M1 * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// One N(0,1) draw for eps element `idx` of stream (seed, offset): Box-Muller on two Philox words.
+__device__ __forceinline__ float philox_normal(uint64_t idx, uint64_t seed, uint64_t offset) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
+                (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  float u1 = ((float)r[0] + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  float u2 = (float)r[1] * 2.3283064365386963e-10f;            // [0, 1]
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+}  // namespace selfc

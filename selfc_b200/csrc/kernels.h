@@ -1,0 +1,76 @@
+// Host-side launcher declarations shared by the translation units of libselfc_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace selfc {
+
+// ---- layout.cu ------------------------------------------------------------------------------------------
+int launch_fa_fwd_nchw(const float* x, float* out51, int N, int h, int w, cudaStream_t st);
+template <typename T>
+int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, int N, int h, int w, cudaStream_t st);
+int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w, cudaStream_t st);
+int launch_quantize(const float* x, uint8_t* q8, float* qf, size_t n, cudaStream_t st);
+int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q, long long M, long long hw, cudaStream_t st);
+int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st);
+template <typename T>
+int launch_nchw_to_dense(const float* x, T* dst, int pitch, int off, int C, int cpad, long long M, long long hw, cudaStream_t st);
+template <typename T>
+int launch_dense_to_nchw(const T* src, int pitch, int off, float* y, int C, long long M, long long hw, cudaStream_t st);
+
+// ---- conv_simt.cu: fp32-FMA implicit GEMM (strict-fp32 mode and the small GEMMs of both modes) --------------
+enum TapMode { TAP_POINT = 0, TAP_SPATIAL = 1, TAP_TEMPORAL = 2, TAP_TMIX = 3 };
+enum Epilogue { EPI_STORE = 0, EPI_COUPLE_Y1 = 1, EPI_COUPLE_S = 2, EPI_COUPLE_Y2 = 3, EPI_GA = 4 };
+
+template <typename T>
+struct ConvArgs {
+  // input: pixel-major buffer, channels [0,cin) consumed (cin % 4 == 0)
+  const T* in = nullptr;
+  int in_pitch = 0, cin = 0;
+  // packed weights [taps*cin][np] fp32 (np % 32 == 0) + bias [np]
+  const float* w = nullptr;
+  const float* bias = nullptr;
+  int np = 0, cout = 0;
+  int taps = 1, tap_mode = TAP_POINT, in_lrelu = 0;
+  int BT = 0, Tn = 1, h = 0, w_ = 0;
+  // TAP_TMIX: temporal mixing matrix [B][T][T] (GlobalAgg), column sums [B][T]
+  const float* wmat = nullptr;
+  const float* wsum = nullptr;
+  // epilogue
+  int epi = EPI_STORE, act = 0, rev = 0;
+  T* outT = nullptr;
+  int outT_pitch = 0, outT_off = 0;
+  float* outF = nullptr;
+  int outF_pitch = 0, outF_off = 0;
+  float* z = nullptr;       // latent state [M][52]
+  float* sbuf = nullptr;    // coupling log-scale s [M][48]
+  T* copyA = nullptr;       // typed copies of the coupling result into conv-input slots
+  int copyA_pitch = 0;
+  T* copyB = nullptr;
+  int copyB_pitch = 0;
+  int copy_pad = 0;         // Y1: zero-fill channels [3, copy_pad)
+  const T* resid = nullptr; // EPI_GA residual
+  int resid_pitch = 0;
+};
+
+template <typename T>
+int launch_conv_simt(const ConvArgs<T>& a, cudaStream_t st);
+
+// reference conv weight [cout][cin_ref][taps...] -> [taps*cin_buf][np]; buffer channel c maps to reference
+// channel c (c < xreal), nothing (xreal <= c < xpad), or c - xpad + xreal (growth channels)
+int launch_pack_conv_simt(const float* wref, const float* bref, float* wpk, float* bpk, int cout, int cin_ref, int taps,
+                          int cin_buf, int xreal, int xpad, int np, cudaStream_t st);
+
+// ---- stp.cu: GlobalAgg statistics, GMM sampler -----------------------------------------------------------------
+int launch_ga_wmap(const float* fcw, float* wmap, int h, int w, cudaStream_t st);
+template <typename T>
+int launch_ga_stat(const T* x, int pitch, const float* wmap, float* partial, int nsplit, int BT, int hw, cudaStream_t st);
+int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const float* p2w, const float* p2b, const float* p3w,
+                      const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st);
+// params: pixel-major [M][720] fp32 (ppitch floats per pixel) or NCHW [BT,720,h,w] (params_nchw)
+int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, uint64_t seed, uint64_t offset, float* v,
+                      bool v_nchw, int vpitch, int voff, int B, int T, int h, int w, cudaStream_t st);
+int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, long long n, cudaStream_t st);
+
+}  // namespace selfc

@@ -1,0 +1,276 @@
+// Memory-bound layout kernels of the rescaling path: FrequencyAnalyzer forward/reverse, the LR split +
+// 8-bit quantisation, and the NCHW <-> pixel-major ("dense buffer") conversions at the boundary.
+//
+// Reference behaviour restated (not copied): models/modules/SelfC_GMM_arch_inv.py:46-82 (FrequencyAnalyzer,
+// PixelUnshuffle), models/modules/Quantization.py:4-17, models/SelfC_model.py:217-222.
+//
+// Internal layout: latent state z [M][52] fp32, M = B*T*h*w pixel-major; ch 0..2 = LR part x1, 3 = pad,
+// 4..51 = HF part x2 (in the FORWARD channel order (sy*4+sx)*3+c while going down, and whatever the
+// couplings produce while going up -- the reverse FrequencyAnalyzer reads it as c*16+sy*4+sx).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace selfc {
+
+// ------------------------------------------------------------------------------------------------------
+// FrequencyAnalyzer forward: one thread per LR pixel, 12 x 16-byte loads (4 rows x 3 colours).
+// OUT_NCHW: write [N,51,h,w] (standalone component); else write z [M][52] (+ optional T copy of the 48 HF
+// channels into the F dense buffer, channel offset 0).
+// ------------------------------------------------------------------------------------------------------
+template <bool OUT_NCHW, typename T>
+__global__ void __launch_bounds__(256) fa_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                     T* __restrict__ fbuf, int fpitch, int N, int h, int w) {
+  const long long M = (long long)N * h * w;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int j = (int)(m % w);
+  const int i = (int)((m / w) % h);
+  const int n = (int)(m / ((long long)w * h));
+  const int W = 4 * w, H = 4 * h;
+  float v[3][16];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* src = x + (((long long)n * 3 + c) * H + 4 * i) * W + 4 * j;
+#pragma unroll
+    for (int sy = 0; sy < 4; ++sy) {
+      float4 r = __ldg(reinterpret_cast<const float4*>(src + (long long)sy * W));
+      v[c][sy * 4 + 0] = r.x; v[c][sy * 4 + 1] = r.y; v[c][sy * 4 + 2] = r.z; v[c][sy * 4 + 3] = r.w;
+    }
+  }
+  float lf[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // sequential row-major accumulation then /16: the order adaptive_avg_pool2d uses (bit-exact, oracle fa_forward)
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc = acc + v[c][q];
+    lf[c] = acc / 16.0f;
+  }
+  if (OUT_NCHW) {
+    const long long hw = (long long)h * w;
+    float* o = out + (long long)n * 51 * hw + (long long)i * w + j;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * hw] = lf[c];
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[(3 + q * 3 + c) * hw] = v[c][q] - lf[c];
+  } else {
+    float row[kZPitch];
+    row[0] = lf[0]; row[1] = lf[1]; row[2] = lf[2]; row[3] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) row[kZHf + q * 3 + c] = v[c][q] - lf[c];
+    float* o = out + m * kZPitch;
+#pragma unroll
+    for (int k = 0; k < kZPitch; k += 4) store4(o + k, make_float4(row[k], row[k + 1], row[k + 2], row[k + 3]));
+    if (fbuf != nullptr) {
+      T* f = fbuf + m * fpitch;
+#pragma unroll
+      for (int k = 0; k < kHF; k += 4)
+        store4(f + k, make_float4(row[kZHf + k], row[kZHf + k + 1], row[kZHf + k + 2], row[kZHf + k + 3]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// FrequencyAnalyzer reverse: y[n,c,4i+sy,4j+sx] = lf[c] + hf[c*16+sy*4+sx]  (nn.PixelShuffle order).
+// ------------------------------------------------------------------------------------------------------
+template <bool IN_NCHW>
+__global__ void __launch_bounds__(256) fa_rev_kernel(const float* __restrict__ z, float* __restrict__ y, int N, int h, int w) {
+  const long long M = (long long)N * h * w;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int j = (int)(m % w);
+  const int i = (int)((m / w) % h);
+  const int n = (int)(m / ((long long)w * h));
+  const int W = 4 * w, H = 4 * h;
+  float lf[3], hf[kHF];
+  if (IN_NCHW) {
+    const long long hw = (long long)h * w;
+    const float* src = z + (long long)n * 51 * hw + (long long)i * w + j;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) lf[c] = __ldg(src + c * hw);
+#pragma unroll
+    for (int k = 0; k < kHF; ++k) hf[k] = __ldg(src + (3 + k) * hw);
+  } else {
+    const float* src = z + m * kZPitch;
+    float4 a = load4(src);
+    lf[0] = a.x; lf[1] = a.y; lf[2] = a.z;
+#pragma unroll
+    for (int k = 0; k < kHF; k += 4) {
+      float4 r = load4(src + kZHf + k);
+      hf[k] = r.x; hf[k + 1] = r.y; hf[k + 2] = r.z; hf[k + 3] = r.w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float* dst = y + (((long long)n * 3 + c) * H + 4 * i) * W + 4 * j;
+#pragma unroll
+    for (int sy = 0; sy < 4; ++sy) {
+      float4 r = make_float4(lf[c] + hf[c * 16 + sy * 4 + 0], lf[c] + hf[c * 16 + sy * 4 + 1],
+                             lf[c] + hf[c * 16 + sy * 4 + 2], lf[c] + hf[c * 16 + sy * 4 + 3]);
+      *reinterpret_cast<float4*>(dst + (long long)sy * W) = r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Quantisation (Quantization.py:9-12): round-half-even of clamp(x,0,1)*255.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float quant_code(float v) {
+  v = fminf(fmaxf(v, 0.f), 1.f);
+  return rintf(v * 255.0f);
+}
+
+__global__ void quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ q8, float* __restrict__ qf, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float c = quant_code(x[i]);
+  if (q8) q8[i] = (uint8_t)c;
+  if (qf) qf[i] = c / 255.0f;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Export of the forward result: z [M][52] -> out51 [N,51,h,w] (+ LR quantised to u8 / fp32 grid).
+// 128 pixels per block staged through shared memory so both sides are coalesced.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) export_down_kernel(const float* __restrict__ z, float* __restrict__ out51,
+                                                          uint8_t* __restrict__ lr_u8, float* __restrict__ lr_q,
+                                                          long long M, long long hw) {
+  __shared__ float tile[128 * (kZPitch + 1)];
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int cnt = (int)min((long long)128, M - m0);
+  for (int e = threadIdx.x; e < cnt * kZPitch; e += 128) {
+    int p = e / kZPitch, c = e % kZPitch;
+    tile[p * (kZPitch + 1) + c] = z[m0 * kZPitch + e];
+  }
+  __syncthreads();
+  const int p = threadIdx.x;
+  if (p >= cnt) return;
+  const long long m = m0 + p;
+  const long long n = m / hw, pix = m % hw;
+  const float* r = tile + p * (kZPitch + 1);
+  if (out51) {
+    float* o = out51 + n * 51 * hw + pix;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * hw] = r[c];
+#pragma unroll 8
+    for (int k = 0; k < kHF; ++k) o[(3 + k) * hw] = r[kZHf + k];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float code = quant_code(r[c]);
+    if (lr_u8) lr_u8[(n * 3 + c) * hw + pix] = (uint8_t)code;
+    if (lr_q) lr_q[(n * 3 + c) * hw + pix] = code / 255.0f;
+  }
+}
+
+// hf part of z -> [N,48,h,w]
+__global__ void __launch_bounds__(128) export_hf_kernel(const float* __restrict__ z, float* __restrict__ hf, long long M, long long hw) {
+  __shared__ float tile[128 * (kHF + 1)];
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int cnt = (int)min((long long)128, M - m0);
+  for (int e = threadIdx.x; e < cnt * kHF; e += 128) {
+    int p = e / kHF, c = e % kHF;
+    tile[p * (kHF + 1) + c] = z[(m0 + p) * kZPitch + kZHf + c];
+  }
+  __syncthreads();
+  const int p = threadIdx.x;
+  if (p >= cnt) return;
+  const long long m = m0 + p;
+  const long long n = m / hw, pix = m % hw;
+  float* o = hf + n * kHF * hw + pix;
+#pragma unroll 8
+  for (int k = 0; k < kHF; ++k) o[k * hw] = tile[p * (kHF + 1) + k];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// NCHW [N,C,h,w] fp32 -> pixel-major T buffer [M][pitch] at channel offset `off`, zero-filling channels
+// [C, cpad).  Used for the LR ingest of the reverse pass (x1 into z and the X slots of G/H/local_m1) and by
+// the component entry points.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_dense_kernel(const float* __restrict__ x, T* __restrict__ dst, int pitch, int off, int C, int cpad,
+                                     long long M, long long hw) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long n = m / hw, pix = m % hw;
+  T* d = dst + m * pitch + off;
+  for (int c = 0; c < cpad; ++c) d[c] = from_f<T>(c < C ? __ldg(x + (n * C + c) * hw + pix) : 0.f);
+}
+
+template <typename T>
+__global__ void dense_to_nchw_kernel(const T* __restrict__ src, int pitch, int off, float* __restrict__ y, int C, long long M, long long hw) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long n = m / hw, pix = m % hw;
+  const T* s = src + m * pitch + off;
+  for (int c = 0; c < C; ++c) y[(n * C + c) * hw + pix] = to_f(s[c]);
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------
+int launch_fa_fwd_nchw(const float* x, float* out51, int N, int h, int w, cudaStream_t st) {
+  long long M = (long long)N * h * w;
+  fa_fwd_kernel<true, float><<<cdiv(M, 256), 256, 0, st>>>(x, out51, nullptr, 0, N, h, w);
+  SELFC_LAUNCH_CHECK("fa_fwd_kernel<nchw>");
+  return 0;
+}
+
+template <typename T>
+int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, int N, int h, int w, cudaStream_t st) {
+  long long M = (long long)N * h * w;
+  fa_fwd_kernel<false, T><<<cdiv(M, 256), 256, 0, st>>>(x, z, fbuf, fpitch, N, h, w);
+  SELFC_LAUNCH_CHECK("fa_fwd_kernel<z>");
+  return 0;
+}
+template int launch_fa_fwd_z<float>(const float*, float*, float*, int, int, int, int, cudaStream_t);
+template int launch_fa_fwd_z<__nv_bfloat16>(const float*, float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+
+int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w, cudaStream_t st) {
+  long long M = (long long)N * h * w;
+  if (z_is_nchw) fa_rev_kernel<true><<<cdiv(M, 256), 256, 0, st>>>(z, y, N, h, w);
+  else fa_rev_kernel<false><<<cdiv(M, 256), 256, 0, st>>>(z, y, N, h, w);
+  SELFC_LAUNCH_CHECK("fa_rev_kernel");
+  return 0;
+}
+
+int launch_quantize(const float* x, uint8_t* q8, float* qf, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  quantize_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(x, q8, qf, n);
+  SELFC_LAUNCH_CHECK("quantize_kernel");
+  return 0;
+}
+
+int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q, long long M, long long hw, cudaStream_t st) {
+  export_down_kernel<<<cdiv(M, 128), 128, 0, st>>>(z, out51, lr_u8, lr_q, M, hw);
+  SELFC_LAUNCH_CHECK("export_down_kernel");
+  return 0;
+}
+
+int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st) {
+  export_hf_kernel<<<cdiv(M, 128), 128, 0, st>>>(z, hf, M, hw);
+  SELFC_LAUNCH_CHECK("export_hf_kernel");
+  return 0;
+}
+
+template <typename T>
+int launch_nchw_to_dense(const float* x, T* dst, int pitch, int off, int C, int cpad, long long M, long long hw, cudaStream_t st) {
+  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, dst, pitch, off, C, cpad, M, hw);
+  SELFC_LAUNCH_CHECK("nchw_to_dense_kernel");
+  return 0;
+}
+template int launch_nchw_to_dense<float>(const float*, float*, int, int, int, int, long long, long long, cudaStream_t);
+template int launch_nchw_to_dense<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, int, int, long long, long long, cudaStream_t);
+
+template <typename T>
+int launch_dense_to_nchw(const T* src, int pitch, int off, float* y, int C, long long M, long long hw, cudaStream_t st) {
+  dense_to_nchw_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(src, pitch, off, y, C, M, hw);
+  SELFC_LAUNCH_CHECK("dense_to_nchw_kernel");
+  return 0;
+}
+template int launch_dense_to_nchw<float>(const float*, int, int, float*, int, long long, long long, cudaStream_t);
+template int launch_dense_to_nchw<__nv_bfloat16>(const __nv_bfloat16*, int, int, float*, int, long long, long long, cudaStream_t);
+
+}  // namespace selfc

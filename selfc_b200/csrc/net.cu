@@ -1,0 +1,640 @@
+// libselfc_b200: context (packed-weight cache), workspace layout, orchestration of the rescaling path and the
+// C-ABI declared in include/selfc_b200.h.
+//
+// Orchestration restates SelfCInvNet.forward (models/modules/SelfC_GMM_arch_inv.py:450-490), InvBlockExp.forward
+// (:21-33), D2DTInput.forward (Subnet_constructor.py:115-133) and STPNet.forward (:358-394) as a fixed launch
+// sequence over pixel-major buffers; nothing here is a translation of reference code.
+#include <mutex>
+#include <new>
+#include <string.h>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "conv_tc.h"
+
+namespace selfc {
+
+// ---- per-thread error text + launch counter --------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+uint64_t& launch_counter() { return g_launches; }
+
+// ---- parameter index map (module registration order of the reference) ------------------------
+constexpr int P_INV0 = 0;           // operations.{1..8}.{F,G,H}.conv{1..5}.{weight,bias}: 8 * 3 * 10
+constexpr int P_LOCAL1 = 240;       // stp_net.local_m1 (10)
+constexpr int P_LOCAL2 = 250;       // stp_net.local_m2 (10)
+constexpr int P_GLOBAL1 = 260;      // stp_net.global_m1 (8: fc, proj1, proj2, proj3)
+constexpr int P_GLOBAL2 = 268;
+constexpr int P_OTHER = 276;        // 4 x (D2DT 10, GlobalAgg 8)
+constexpr int P_TAIL = 348;         // tail_gmm.{1,3,5}.{weight,bias}
+static_assert(P_TAIL + 6 == SELFC_NUM_PARAMS, "parameter map");
+
+struct DenseW {            // one D2DTInput in kernel layout
+  int cin = 0, cout = 0, xpad = 0;
+  float* w[5] = {};        // SIMT fp32 [taps*cin_buf][np]
+  float* b[5] = {};
+  int np[5] = {};
+  TcConvW tc[5];           // tcgen05 bf16 images (BF16 mode)
+};
+struct GaW {
+  float *fcw = nullptr, *fcb = nullptr, *p2w = nullptr, *p2b = nullptr, *p3w = nullptr, *p3b = nullptr;
+  float *p1w = nullptr, *p1b = nullptr;   // packed [64][64] (k-major rows), bias [64]
+};
+struct ProfRec {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cls = 0;
+  double work = 0.0;
+};
+struct HeadW {
+  float* w[3] = {};
+  float* b[3] = {};
+  int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 720}, np[3] = {128, 256, 736};
+};
+
+}  // namespace selfc
+
+using namespace selfc;
+
+struct selfc_ctx {
+  int device = 0, mode = SELFC_MODE_FP32;
+  bool loaded = false;
+  int xpad3 = 4;            // X-slot width of the 3-channel dense blocks (G, H, local_m1)
+  DenseW inv[8][3];         // [block][F,G,H]
+  DenseW stp[6];            // local_m1, local_m2, other 0,2,4,6
+  GaW ga[6];
+  HeadW head;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::mutex mu;
+  // optional per-launch timing (bench.py's roofline leg): CUDA events around every launch, by kernel class
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+};
+
+namespace selfc {
+
+// ---- per-launch profiler ----------------------------------------------------------------------------------
+static void prof_begin(const selfc_ctx* cctx, cudaStream_t st, int cls, double work) {
+  selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
+  if (!ctx->prof_on) return;
+  ProfRec r;
+  r.cls = cls;
+  r.work = work;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  ctx->prof.push_back(r);
+}
+static void prof_end(const selfc_ctx* cctx, cudaStream_t st) {
+  selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
+  if (!ctx->prof_on || ctx->prof.empty()) return;
+  cudaEventRecord(ctx->prof.back().b, st);
+}
+#define PROF(ctx, st, cls, work, call) \
+  do {                                 \
+    prof_begin(ctx, st, cls, work);    \
+    int rc_p = (call);                 \
+    prof_end(ctx, st);                 \
+    if (rc_p != 0) return rc_p;        \
+  } while (0)
+
+// ---- workspace layout -------------------------------------------------------------------------------------
+struct Workspace {
+  size_t total = 0;
+  size_t z, sbuf, fbuf, gbuf, hbuf, stpbuf, feat, h1, h2, params, wmap, partial, wmat, wsum;
+  int nsplit = 1;
+  int fpitch = 176, gpitch = 0, spitch = 192;
+};
+
+static Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w) {
+  Workspace ws;
+  const size_t M = (size_t)B * T * h * w;
+  const size_t es = ctx->mode == SELFC_MODE_BF16 ? 2 : 4;
+  const size_t guard = 4096;   // conv_tc halo boxes may touch a few rows past a buffer's end only through TMA (bounds-checked); keep slack anyway
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes + guard, 1024);
+    return o;
+  };
+  ws.gpitch = ctx->xpad3 + 4 * kGrowth;
+  ws.z = take(M * kZPitch * 4);
+  ws.sbuf = take(M * kHF * 4);
+  ws.fbuf = take(M * ws.fpitch * es);
+  ws.gbuf = take(M * ws.gpitch * es);
+  ws.hbuf = take(M * ws.gpitch * es);
+  ws.stpbuf = take(M * ws.spitch * es);
+  ws.feat = take(M * kStpC * es);
+  ws.h1 = take(M * 128 * es);
+  ws.h2 = take(M * 256 * es);
+  ws.params = take(M * 720 * 4);
+  ws.nsplit = (int)((size_t)h * w / 2048);
+  if (ws.nsplit < 1) ws.nsplit = 1;
+  if (ws.nsplit > 32) ws.nsplit = 32;
+  ws.wmap = take((size_t)h * w * 4);
+  ws.partial = take((size_t)B * T * ws.nsplit * 64 * 4);
+  ws.wmat = take((size_t)B * T * T * 4);
+  ws.wsum = take((size_t)B * T * 4);
+  ws.total = off;
+  return ws;
+}
+
+struct Dims {
+  int B, T, h, w;
+  long long M() const { return (long long)B * T * h * w; }
+  long long hw() const { return (long long)h * w; }
+};
+
+// ---- dense block: conv1..4 in place, then conv5 with the given epilogue ---------------------------------------
+template <typename T>
+static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pitch, const Dims& d, cudaStream_t st) {
+  for (int k = 0; k < 4; ++k) {
+    const int cin = W.xpad + kGrowth * k;
+    const double flops = 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;   // algorithmic (unpadded) FLOPs
+    if (ctx->mode == SELFC_MODE_BF16 && W.tc[k].img != nullptr) {
+      PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), pitch, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
+      continue;
+    }
+    ConvArgs<T> a;
+    a.in = buf; a.in_pitch = pitch; a.cin = cin;
+    a.w = W.w[k]; a.bias = W.b[k]; a.np = W.np[k]; a.cout = kGrowth;
+    a.taps = 9; a.tap_mode = TAP_SPATIAL;
+    a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
+    a.epi = EPI_STORE; a.act = 1;
+    a.outT = buf; a.outT_pitch = pitch; a.outT_off = cin;
+    PROF(ctx, st, 0, flops, launch_conv_simt<T>(a, st));
+  }
+  return 0;
+}
+
+template <typename T>
+static ConvArgs<T> conv5_args(const DenseW& W, const T* buf, int pitch, const Dims& d) {
+  ConvArgs<T> a;
+  a.in = buf; a.in_pitch = pitch; a.cin = W.xpad + 4 * kGrowth;
+  a.w = W.w[4]; a.bias = W.b[4]; a.np = W.np[4]; a.cout = W.cout;
+  a.taps = 3; a.tap_mode = TAP_TEMPORAL;
+  a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
+  return a;
+}
+
+static double conv5_flops(const DenseW& W, const Dims& d) { return 2.0 * (double)d.M() * 3.0 * (W.cin + 4 * kGrowth) * W.cout; }
+
+// InvBlockExp (SelfC_GMM_arch_inv.py:21-33) on the latent state z, forward or reverse
+template <typename T>
+static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
+  float* z = reinterpret_cast<float*>(wsp + ws.z);
+  float* sbuf = reinterpret_cast<float*>(wsp + ws.sbuf);
+  T* fbuf = reinterpret_cast<T*>(wsp + ws.fbuf);
+  T* gbuf = reinterpret_cast<T*>(wsp + ws.gbuf);
+  T* hbuf = reinterpret_cast<T*>(wsp + ws.hbuf);
+  const DenseW& F = ctx->inv[blk][0];
+  const DenseW& G = ctx->inv[blk][1];
+  const DenseW& H = ctx->inv[blk][2];
+  auto do_F = [&]() -> int {
+    SELFC_TRY(run_dense_convs<T>(ctx, F, fbuf, ws.fpitch, d, st));
+    ConvArgs<T> a = conv5_args<T>(F, fbuf, ws.fpitch, d);
+    a.epi = EPI_COUPLE_Y1; a.rev = rev ? 1 : 0; a.z = z;
+    a.copyA = gbuf; a.copyA_pitch = ws.gpitch; a.copyB = hbuf; a.copyB_pitch = ws.gpitch; a.copy_pad = ctx->xpad3;
+    PROF(ctx, st, 1, conv5_flops(F, d), launch_conv_simt<T>(a, st));
+    return 0;
+  };
+  auto do_HG = [&]() -> int {
+    SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st));
+    ConvArgs<T> a = conv5_args<T>(H, hbuf, ws.gpitch, d);
+    a.epi = EPI_COUPLE_S; a.sbuf = sbuf;
+    PROF(ctx, st, 1, conv5_flops(H, d), launch_conv_simt<T>(a, st));
+    SELFC_TRY(run_dense_convs<T>(ctx, G, gbuf, ws.gpitch, d, st));
+    ConvArgs<T> g = conv5_args<T>(G, gbuf, ws.gpitch, d);
+    g.epi = EPI_COUPLE_Y2; g.rev = rev ? 1 : 0; g.z = z; g.sbuf = sbuf;
+    g.copyA = fbuf; g.copyA_pitch = ws.fpitch;
+    PROF(ctx, st, 1, conv5_flops(G, d), launch_conv_simt<T>(g, st));
+    return 0;
+  };
+  if (!rev) {
+    SELFC_TRY(do_F());
+    SELFC_TRY(do_HG());
+  } else {
+    SELFC_TRY(do_HG());
+    SELFC_TRY(do_F());
+  }
+  return 0;
+}
+
+// GlobalAgg (SelfC_GMM_arch_inv.py:265-285): x = feat [M][64]; result -> outT (pitch/off) and/or outF
+template <typename T>
+static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* outT, int outT_pitch, float* outF, int outF_pitch,
+                          float* wmat_copy, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
+  float* wmap = reinterpret_cast<float*>(wsp + ws.wmap);
+  float* partial = reinterpret_cast<float*>(wsp + ws.partial);
+  float* wmat = reinterpret_cast<float*>(wsp + ws.wmat);
+  float* wsum = reinterpret_cast<float*>(wsp + ws.wsum);
+  const double px_bytes = (double)d.M() * kStpC * sizeof(T);
+  PROF(ctx, st, 2, 0.0, launch_ga_wmap(g.fcw, wmap, d.h, d.w, st));
+  PROF(ctx, st, 2, px_bytes, launch_ga_stat<T>(feat, kStpC, wmap, partial, ws.nsplit, d.B * d.T, (int)d.hw(), st));
+  PROF(ctx, st, 2, 0.0, launch_ga_weights(partial, ws.nsplit, g.fcb, g.p2w, g.p2b, g.p3w, g.p3b, wmat, wsum, d.B, d.T, st));
+  if (wmat_copy) SELFC_CUDA(cudaMemcpyAsync(wmat_copy, wmat, (size_t)d.B * d.T * d.T * 4, cudaMemcpyDeviceToDevice, st));
+  ConvArgs<T> a;
+  a.in = feat; a.in_pitch = kStpC; a.cin = kStpC;
+  a.w = g.p1w; a.bias = g.p1b; a.np = 64; a.cout = 64;
+  a.taps = 1; a.tap_mode = TAP_TMIX;
+  a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
+  a.wmat = wmat; a.wsum = wsum;
+  a.epi = EPI_GA; a.resid = feat; a.resid_pitch = kStpC;
+  a.outT = outT; a.outT_pitch = outT_pitch; a.outT_off = 0;
+  a.outF = outF; a.outF_pitch = outF_pitch; a.outF_off = 0;
+  PROF(ctx, st, 2, 2.0 * px_bytes, launch_conv_simt<T>(a, st));
+  return 0;
+}
+
+template <typename T>
+static int down_impl(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_u8, float* lr_q, const Dims& d, char* wsp,
+                     const Workspace& ws, cudaStream_t st) {
+  float* z = reinterpret_cast<float*>(wsp + ws.z);
+  T* fbuf = reinterpret_cast<T*>(wsp + ws.fbuf);
+  PROF(ctx, st, 5, (double)d.M() * (16 * 3 * 4 + 51 * 4), launch_fa_fwd_z<T>(hr, z, fbuf, ws.fpitch, d.B * d.T, d.h, d.w, st));
+  for (int blk = 0; blk < 8; ++blk) SELFC_TRY(run_invblock<T>(ctx, blk, false, wsp, ws, d, st));
+  PROF(ctx, st, 5, (double)d.M() * (51 * 4 + (out51 ? 51 * 4 : 0) + 3), launch_export_down(z, out51, lr_u8, lr_q, d.M(), d.hw(), st));
+  return 0;
+}
+
+template <typename T>
+static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, float* hf,
+                   const Dims& d, char* wsp, const Workspace& ws, cudaStream_t st) {
+  float* z = reinterpret_cast<float*>(wsp + ws.z);
+  T* gbuf = reinterpret_cast<T*>(wsp + ws.gbuf);
+  T* hbuf = reinterpret_cast<T*>(wsp + ws.hbuf);
+  T* stpbuf = reinterpret_cast<T*>(wsp + ws.stpbuf);
+  T* feat = reinterpret_cast<T*>(wsp + ws.feat);
+  T* h1 = reinterpret_cast<T*>(wsp + ws.h1);
+  T* h2 = reinterpret_cast<T*>(wsp + ws.h2);
+  float* params = reinterpret_cast<float*>(wsp + ws.params);
+  const long long M = d.M(), hw = d.hw();
+  const int xp = ctx->xpad3;
+  // LR ingest: x1 of the reversed block 8, and the X slot of local_m1
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<float>(lr, z, kZPitch, 0, 3, 4, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, gbuf, ws.gpitch, 0, 3, xp, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, hbuf, ws.gpitch, 0, 3, xp, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, stpbuf, ws.gpitch, 0, 3, xp, M, hw, st));
+  // STPNet.forward (:366-374)
+  for (int i = 0; i < 6; ++i) {
+    const DenseW& W = ctx->stp[i];
+    const int pitch = i == 0 ? ws.gpitch : ws.spitch;
+    SELFC_TRY(run_dense_convs<T>(ctx, W, stpbuf, pitch, d, st));
+    ConvArgs<T> a = conv5_args<T>(W, stpbuf, pitch, d);
+    a.epi = EPI_STORE; a.act = 0; a.outT = feat; a.outT_pitch = kStpC; a.outT_off = 0;
+    PROF(ctx, st, 1, conv5_flops(W, d), launch_conv_simt<T>(a, st));
+    SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, nullptr, 0, nullptr, wsp, ws, d, st));
+  }
+  // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
+  {
+    ConvArgs<T> a;
+    a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
+    a.taps = 1; a.tap_mode = TAP_POINT; a.epi = EPI_STORE;
+    a.in = stpbuf; a.in_pitch = ws.spitch; a.cin = 64; a.in_lrelu = 1;
+    a.w = ctx->head.w[0]; a.bias = ctx->head.b[0]; a.np = ctx->head.np[0]; a.cout = 128;
+    a.act = 1; a.outT = h1; a.outT_pitch = 128;
+    PROF(ctx, st, 3, 2.0 * M * 64 * 128, launch_conv_simt<T>(a, st));
+    a.in = h1; a.in_pitch = 128; a.cin = 128; a.in_lrelu = 0;
+    a.w = ctx->head.w[1]; a.bias = ctx->head.b[1]; a.np = ctx->head.np[1]; a.cout = 256;
+    a.outT = h2; a.outT_pitch = 256;
+    PROF(ctx, st, 3, 2.0 * M * 128 * 256, launch_conv_simt<T>(a, st));
+    a.in = h2; a.in_pitch = 256; a.cin = 256;
+    a.w = ctx->head.w[2]; a.bias = ctx->head.b[2]; a.np = ctx->head.np[2]; a.cout = 720;
+    a.act = 0; a.outT = nullptr; a.outF = params; a.outF_pitch = 720;
+    PROF(ctx, st, 3, 2.0 * M * 256 * 720, launch_conv_simt<T>(a, st));
+  }
+  PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample(params, false, eps, seed, offset, z, false, kZPitch, kZHf, d.B, d.T, d.h, d.w, st));
+  if (hf) PROF(ctx, st, 5, (double)M * 48 * 8, launch_export_hf(z, hf, M, hw, st));
+  for (int blk = 7; blk >= 0; --blk) SELFC_TRY(run_invblock<T>(ctx, blk, true, wsp, ws, d, st));
+  PROF(ctx, st, 5, (double)M * (51 * 4 + 48 * 4), launch_fa_rev(z, false, hr, d.B * d.T, d.h, d.w, st));
+  return 0;
+}
+
+// ---- weight packing ---------------------------------------------------------------------------------------
+struct ArenaPlan {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+static void plan_dense(ArenaPlan& pl, int cin, int cout, int xpad, size_t woff[5], size_t boff[5], int np[5]) {
+  for (int k = 0; k < 5; ++k) {
+    const int taps = k < 4 ? 9 : 3;
+    const int cin_buf = xpad + kGrowth * k;
+    np[k] = k < 4 ? 32 : (int)align_up(cout, 32);
+    woff[k] = pl.take((size_t)taps * cin_buf * np[k] * 4);
+    boff[k] = pl.take((size_t)np[k] * 4);
+  }
+  (void)cin;
+}
+
+template <typename T>
+static int d2dt_impl(selfc_ctx* ctx, const DenseW& W, const float* x, float* y, const Dims& d, char* wsp, const Workspace& ws,
+                     cudaStream_t st) {
+  T* buf = reinterpret_cast<T*>(wsp + ws.stpbuf);
+  float* tmp = reinterpret_cast<float*>(wsp + ws.params);
+  const int pitch = W.xpad + 4 * kGrowth;
+  SELFC_TRY(launch_nchw_to_dense<T>(x, buf, pitch, 0, W.cin, W.xpad, d.M(), d.hw(), st));
+  SELFC_TRY(run_dense_convs<T>(ctx, W, buf, pitch, d, st));
+  ConvArgs<T> a = conv5_args<T>(W, buf, pitch, d);
+  a.epi = EPI_STORE; a.outF = tmp; a.outF_pitch = 64;
+  SELFC_TRY(launch_conv_simt<T>(a, st));
+  return launch_dense_to_nchw<float>(tmp, 64, 0, y, W.cout, d.M(), d.hw(), st);
+}
+
+template <typename T>
+static int ga_impl(selfc_ctx* ctx, const GaW& g, const float* x, float* y, float* wmat_out, const Dims& d, char* wsp,
+                   const Workspace& ws, cudaStream_t st) {
+  T* feat = reinterpret_cast<T*>(wsp + ws.feat);
+  float* tmp = reinterpret_cast<float*>(wsp + ws.params);
+  SELFC_TRY(launch_nchw_to_dense<T>(x, feat, kStpC, 0, kStpC, kStpC, d.M(), d.hw(), st));
+  SELFC_TRY(run_global_agg<T>(ctx, g, feat, nullptr, 0, tmp, 64, wmat_out, wsp, ws, d, st));
+  return launch_dense_to_nchw<float>(tmp, 64, 0, y, kStpC, d.M(), d.hw(), st);
+}
+
+}  // namespace selfc
+
+// =============================================================================================================
+// C-ABI
+// =============================================================================================================
+extern "C" {
+
+int selfc_version(void) { return 100; }
+const char* selfc_last_error(void) { return g_err; }
+uint64_t selfc_launch_count(void) { return g_launches; }
+
+int selfc_ctx_create(selfc_ctx** out, int device, int mode) {
+  SELFC_CHECK_ARG(out != nullptr, "selfc_ctx_create: null out");
+  SELFC_CHECK_ARG(mode == SELFC_MODE_FP32 || mode == SELFC_MODE_BF16, "selfc_ctx_create: unknown mode %d", mode);
+  int ndev = 0;
+  SELFC_CUDA(cudaGetDeviceCount(&ndev));
+  SELFC_CHECK_ARG(device >= 0 && device < ndev, "selfc_ctx_create: device %d of %d", device, ndev);
+  cudaDeviceProp prop;
+  SELFC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("selfc_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return SELFC_E_UNSUPPORTED;
+  }
+  selfc_ctx* c = new (std::nothrow) selfc_ctx();
+  SELFC_CHECK_ARG(c != nullptr, "out of host memory");
+  c->device = device;
+  c->mode = mode;
+  c->xpad3 = mode == SELFC_MODE_BF16 ? 16 : 4;
+  *out = c;
+  return 0;
+}
+
+int selfc_ctx_destroy(selfc_ctx* ctx) {
+  if (!ctx) return 0;
+  if (ctx->arena) cudaFree(ctx->arena);
+  for (int b = 0; b < 8; ++b)
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 5; ++k) free_tc_weights(ctx->inv[b][j].tc[k]);
+  for (int i = 0; i < 6; ++i)
+    for (int k = 0; k < 5; ++k) free_tc_weights(ctx->stp[i].tc[k]);
+  delete ctx;
+  return 0;
+}
+
+int selfc_ctx_mode(const selfc_ctx* ctx) { return ctx ? ctx->mode : SELFC_E_ARG; }
+
+int selfc_prof_enable(selfc_ctx* ctx, int on) {
+  SELFC_CHECK_ARG(ctx != nullptr, "null context");
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  ctx->prof_on = on != 0;
+  return 0;
+}
+
+int selfc_prof_read(selfc_ctx* ctx, int ncls, double* ms, double* work, uint64_t* launches) {
+  SELFC_CHECK_ARG(ctx && ms && work && launches && ncls >= 1, "prof_read: bad argument");
+  for (int i = 0; i < ncls; ++i) { ms[i] = 0.0; work[i] = 0.0; launches[i] = 0; }
+  for (auto& r : ctx->prof) {
+    SELFC_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    SELFC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    if (r.cls >= 0 && r.cls < ncls) { ms[r.cls] += t; work[r.cls] += r.work; launches[r.cls] += 1; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  return 0;
+}
+
+int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, void* stream) {
+  SELFC_CHECK_ARG(ctx && p, "selfc_ctx_load_weights: null argument");
+  SELFC_CHECK_ARG(n_params == SELFC_NUM_PARAMS, "selfc_ctx_load_weights: expected %d tensors, got %d", SELFC_NUM_PARAMS, n_params);
+  for (int i = 0; i < n_params; ++i) SELFC_CHECK_ARG(p[i] != nullptr, "selfc_ctx_load_weights: tensor %d is null", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  SELFC_CUDA(cudaSetDevice(ctx->device));
+  const int xp3 = ctx->xpad3;
+
+  // plan the arena
+  ArenaPlan pl;
+  struct DensePlan { size_t w[5], b[5]; int np[5]; int cin, cout, xpad, first; };
+  std::vector<DensePlan> dp;
+  auto add_dense = [&](int first, int cin, int cout) {
+    DensePlan d;
+    d.cin = cin; d.cout = cout; d.first = first;
+    d.xpad = cin == 3 ? xp3 : cin;
+    plan_dense(pl, cin, cout, d.xpad, d.w, d.b, d.np);
+    dp.push_back(d);
+  };
+  for (int b = 0; b < 8; ++b) {
+    add_dense(P_INV0 + b * 30 + 0, kHF, 3);     // F
+    add_dense(P_INV0 + b * 30 + 10, 3, kHF);    // G
+    add_dense(P_INV0 + b * 30 + 20, 3, kHF);    // H
+  }
+  add_dense(P_LOCAL1, 3, kStpC);
+  add_dense(P_LOCAL2, kStpC, kStpC);
+  for (int i = 0; i < 4; ++i) add_dense(P_OTHER + i * 18, kStpC, kStpC);
+  const int ga_first[6] = {P_GLOBAL1, P_GLOBAL2, P_OTHER + 10, P_OTHER + 28, P_OTHER + 46, P_OTHER + 64};
+  size_t ga_off[6][8];
+  const size_t ga_sz[8] = {1024, 1, 64 * 64, 64, 64 * 64, 64, 64 * 64, 64};   // fc.w fc.b p1.w p1.b p2.w p2.b p3.w p3.b
+  for (int g = 0; g < 6; ++g)
+    for (int j = 0; j < 8; ++j) ga_off[g][j] = pl.take(ga_sz[j] * 4);
+  size_t head_w[3], head_b[3];
+  for (int j = 0; j < 3; ++j) {
+    head_w[j] = pl.take((size_t)ctx->head.cin[j] * ctx->head.np[j] * 4);
+    head_b[j] = pl.take((size_t)ctx->head.np[j] * 4);
+  }
+  if (ctx->arena_bytes < pl.off) {
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    SELFC_CUDA(cudaMalloc(&ctx->arena, pl.off));
+    ctx->arena_bytes = pl.off;
+  }
+  char* A = ctx->arena;
+  auto fp = [&](size_t off) { return reinterpret_cast<float*>(A + off); };
+
+  // dense blocks
+  for (size_t i = 0; i < dp.size(); ++i) {
+    const DensePlan& d = dp[i];
+    DenseW* W = i < 24 ? &ctx->inv[i / 3][i % 3] : &ctx->stp[i - 24];
+    W->cin = d.cin; W->cout = d.cout; W->xpad = d.xpad;
+    for (int k = 0; k < 5; ++k) {
+      const int taps = k < 4 ? 9 : 3;
+      const int cin_ref = d.cin + kGrowth * k;
+      const int cin_buf = d.xpad + kGrowth * k;
+      const int cout = k < 4 ? kGrowth : d.cout;
+      W->w[k] = fp(d.w[k]); W->b[k] = fp(d.b[k]); W->np[k] = d.np[k];
+      SELFC_TRY(launch_pack_conv_simt(p[d.first + 2 * k], p[d.first + 2 * k + 1], W->w[k], W->b[k], cout, cin_ref, taps, cin_buf,
+                                      d.cin, d.xpad, d.np[k], st));
+      if (ctx->mode == SELFC_MODE_BF16 && k < 4)
+        SELFC_TRY(pack_tc_weights(W->tc[k], p[d.first + 2 * k], p[d.first + 2 * k + 1], cin_ref, cin_buf, d.cin, d.xpad, st));
+    }
+  }
+  // GlobalAgg
+  for (int g = 0; g < 6; ++g) {
+    GaW& G = ctx->ga[g];
+    const int f = ga_first[g];
+    float* dst[8];
+    for (int j = 0; j < 8; ++j) dst[j] = fp(ga_off[g][j]);
+    G.fcw = dst[0]; G.fcb = dst[1]; G.p1w = dst[2]; G.p1b = dst[3]; G.p2w = dst[4]; G.p2b = dst[5]; G.p3w = dst[6]; G.p3b = dst[7];
+    SELFC_CUDA(cudaMemcpyAsync(G.fcw, p[f + 0], 1024 * 4, cudaMemcpyDeviceToDevice, st));
+    SELFC_CUDA(cudaMemcpyAsync(G.fcb, p[f + 1], 4, cudaMemcpyDeviceToDevice, st));
+    SELFC_TRY(launch_pack_conv_simt(p[f + 2], p[f + 3], G.p1w, G.p1b, 64, 64, 1, 64, 64, 64, 64, st));
+    SELFC_CUDA(cudaMemcpyAsync(G.p2w, p[f + 4], 64 * 64 * 4, cudaMemcpyDeviceToDevice, st));
+    SELFC_CUDA(cudaMemcpyAsync(G.p2b, p[f + 5], 64 * 4, cudaMemcpyDeviceToDevice, st));
+    SELFC_CUDA(cudaMemcpyAsync(G.p3w, p[f + 6], 64 * 64 * 4, cudaMemcpyDeviceToDevice, st));
+    SELFC_CUDA(cudaMemcpyAsync(G.p3b, p[f + 7], 64 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  // GMM head
+  for (int j = 0; j < 3; ++j) {
+    ctx->head.w[j] = fp(head_w[j]);
+    ctx->head.b[j] = fp(head_b[j]);
+    const int cin = ctx->head.cin[j], cout = ctx->head.cout[j];
+    SELFC_TRY(launch_pack_conv_simt(p[P_TAIL + 2 * j], p[P_TAIL + 2 * j + 1], ctx->head.w[j], ctx->head.b[j], cout, cin, 1, cin, cin,
+                                    cin, ctx->head.np[j], st));
+  }
+  ctx->loaded = true;
+  return 0;
+}
+
+size_t selfc_workspace_bytes(const selfc_ctx* ctx, int B, int T, int h, int w) {
+  if (!ctx || B < 0 || T < 1 || h < 1 || w < 1) return 0;
+  return make_workspace(ctx, B, T, h, w).total;
+}
+
+static int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws) {
+  SELFC_CHECK_ARG(ctx != nullptr, "null context");
+  if (!ctx->loaded) {
+    set_error("weights not loaded: call selfc_ctx_load_weights first");
+    return SELFC_E_STATE;
+  }
+  SELFC_CHECK_ARG(B >= 1 && T >= 1 && T <= 32, "B=%d T=%d: need B >= 1 and 1 <= T <= 32", B, T);
+  SELFC_CHECK_ARG(H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0, "H=%d W=%d must be positive multiples of 4", H, W);
+  SELFC_CHECK_ARG((long long)B * T * (H / 4) * (W / 4) < (1ll << 31) / 8, "clip batch too large for 32-bit tile indices");
+  *ws = make_workspace(ctx, B, T, H / 4, W / 4);
+  SELFC_CHECK_ARG(workspace != nullptr && aligned16(workspace), "workspace null or misaligned");
+  if (workspace_bytes < ws->total) {
+    set_error("workspace too small: %zu < %zu bytes", workspace_bytes, ws->total);
+    return SELFC_E_STATE;
+  }
+  SELFC_CUDA(cudaSetDevice(ctx->device));
+  return 0;
+}
+
+int selfc_down(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_u8, float* lr_q, int B, int T, int H, int W,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, H, W, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(hr && aligned16(hr), "hr null or not 16-byte aligned");
+  Dims d{B, T, H / 4, W / 4};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->mode == SELFC_MODE_BF16)
+    return down_impl<__nv_bfloat16>(ctx, hr, out51, lr_u8, lr_q, d, (char*)workspace, ws, st);
+  return down_impl<float>(ctx, hr, out51, lr_u8, lr_q, d, (char*)workspace, ws, st);
+}
+
+int selfc_up(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, float* hf, int B, int T,
+             int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, H, W, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(lr && hr && aligned16(hr), "lr/hr null or hr not 16-byte aligned");
+  Dims d{B, T, H / 4, W / 4};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->mode == SELFC_MODE_BF16)
+    return up_impl<__nv_bfloat16>(ctx, lr, eps, seed, offset, hr, hf, d, (char*)workspace, ws, st);
+  return up_impl<float>(ctx, lr, eps, seed, offset, hr, hf, d, (char*)workspace, ws, st);
+}
+
+int selfc_fa_fwd(const float* x, float* out51, int N, int H, int W, void* stream) {
+  SELFC_CHECK_ARG(x && out51 && aligned16(x), "fa_fwd: null or misaligned pointer");
+  SELFC_CHECK_ARG(N >= 0 && H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0, "fa_fwd: N=%d H=%d W=%d", N, H, W);
+  if (N == 0) return 0;
+  return launch_fa_fwd_nchw(x, out51, N, H / 4, W / 4, (cudaStream_t)stream);
+}
+
+int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream) {
+  SELFC_CHECK_ARG(z51 && y && aligned16(y), "fa_rev: null or misaligned pointer");
+  SELFC_CHECK_ARG(N >= 0 && h >= 1 && w >= 1, "fa_rev: N=%d h=%d w=%d", N, h, w);
+  if (N == 0) return 0;
+  return launch_fa_rev(z51, true, y, N, h, w, (cudaStream_t)stream);
+}
+
+int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* stream) {
+  SELFC_CHECK_ARG(x || n == 0, "quantize: null input");
+  return launch_quantize(x, q_u8, q_f32, n, (cudaStream_t)stream);
+}
+
+int selfc_d2dt(selfc_ctx* ctx, int first_param, const float* x, float* y, int B, int T, int h, int w, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(x && y, "d2dt: null pointer");
+  const DenseW* W = nullptr;
+  if (first_param >= 0 && first_param < 240 && first_param % 10 == 0) W = &ctx->inv[first_param / 30][(first_param % 30) / 10];
+  else if (first_param == P_LOCAL1) W = &ctx->stp[0];
+  else if (first_param == P_LOCAL2) W = &ctx->stp[1];
+  else
+    for (int i = 0; i < 4; ++i)
+      if (first_param == P_OTHER + 18 * i) W = &ctx->stp[2 + i];
+  SELFC_CHECK_ARG(W != nullptr, "d2dt: parameter index %d is not the conv1.weight of a dense block", first_param);
+  Dims d{B, T, h, w};
+  if (ctx->mode == SELFC_MODE_BF16) return d2dt_impl<__nv_bfloat16>(ctx, *W, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
+  return d2dt_impl<float>(ctx, *W, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
+}
+
+int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out, int B, int T, int h, int w,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(x && y, "global_agg: null pointer");
+  const int ga_first[6] = {P_GLOBAL1, P_GLOBAL2, P_OTHER + 10, P_OTHER + 28, P_OTHER + 46, P_OTHER + 64};
+  const GaW* g = nullptr;
+  for (int i = 0; i < 6; ++i)
+    if (first_param == ga_first[i]) g = &ctx->ga[i];
+  SELFC_CHECK_ARG(g != nullptr, "global_agg: parameter index %d is not the fc.weight of a GlobalAgg", first_param);
+  Dims d{B, T, h, w};
+  if (ctx->mode == SELFC_MODE_BF16) return ga_impl<__nv_bfloat16>(ctx, *g, x, y, wmat_out, d, (char*)workspace, ws, (cudaStream_t)stream);
+  return ga_impl<float>(ctx, *g, x, y, wmat_out, d, (char*)workspace, ws, (cudaStream_t)stream);
+}
+
+int selfc_gmm_sample(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* v, int B, int T, int h, int w,
+                     void* stream) {
+  SELFC_CHECK_ARG(params && v, "gmm_sample: null pointer");
+  SELFC_CHECK_ARG(B >= 0 && T >= 1 && h >= 1 && w >= 1, "gmm_sample: bad shape");
+  return launch_gmm_sample(params, true, eps, seed, offset, v, true, 0, 0, B, T, h, w, (cudaStream_t)stream);
+}
+
+int selfc_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, int h, int w, void* stream) {
+  SELFC_CHECK_ARG(eps, "export_eps: null pointer");
+  return launch_export_eps(eps, seed, offset, (long long)B * kHF * kGmmK * T * h * w, (cudaStream_t)stream);
+}
+
+}  // extern "C"

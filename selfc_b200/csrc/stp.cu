@@ -1,0 +1,225 @@
+// STPNet pieces that are not convolutions: GlobalAgg statistics (pooled descriptor -> T x T mixing matrix) and
+// the soft-GMM sampler with counter-based noise.
+//
+// Reference behaviour restated (not copied): models/modules/SelfC_GMM_arch_inv.py:257-285 (GlobalAgg),
+// :383-394 + :412-417 (sampler / reparametrize).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace selfc {
+
+// ------------------------------------------------------------------------------------------------------
+// fc(adaptive_avg_pool2d(x,(32,32))) is linear in x: d[n,ch] = fcb + sum_pix wmap[pix] * x[n,pix,ch] with
+// wmap[y,x] = sum over the pooling bins (i,j) that contain (y,x) of fcw[i*32+j] / (|bin_i| * |bin_j|).
+// Bins follow PyTorch: rows floor(i*h/32) .. ceil((i+1)*h/32)-1 (they overlap when h/32 is not integral).
+// ------------------------------------------------------------------------------------------------------
+__global__ void ga_wmap_kernel(const float* __restrict__ fcw, float* __restrict__ wmap, int h, int w) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= h * w) return;
+  const int y = p / w, x = p % w;
+  float acc = 0.f;
+  for (int i = 0; i < 32; ++i) {
+    const int ys = (i * h) / 32, ye = ((i + 1) * h + 31) / 32;
+    if (y < ys || y >= ye) continue;
+    for (int j = 0; j < 32; ++j) {
+      const int xs = (j * w) / 32, xe = ((j + 1) * w + 31) / 32;
+      if (x < xs || x >= xe) continue;
+      acc += __ldg(fcw + i * 32 + j) / (float)((ye - ys) * (xe - xs));
+    }
+  }
+  wmap[p] = acc;
+}
+
+// partial[n][split][64] = sum over this split's pixels of wmap[p] * x[n,p,ch]   (deterministic two-stage sum)
+template <typename T>
+__global__ void __launch_bounds__(256) ga_stat_kernel(const T* __restrict__ x, int pitch, const float* __restrict__ wmap,
+                                                      float* __restrict__ partial, int nsplit, int hw) {
+  __shared__ float red[16][64 + 4];
+  const int split = blockIdx.x, n = blockIdx.y;
+  const int ch = (threadIdx.x & 15) * 4;
+  const int lane = threadIdx.x >> 4;
+  const int per = (hw + nsplit - 1) / nsplit;
+  const int p0 = split * per, p1 = min(hw, p0 + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = p0 + lane; p < p1; p += 16) {
+    const float wv = __ldg(wmap + p);
+    const float4 r = load4(x + ((long long)n * hw + p) * pitch + ch);
+    acc.x += wv * r.x; acc.y += wv * r.y; acc.z += wv * r.z; acc.w += wv * r.w;
+  }
+  red[lane][ch] = acc.x; red[lane][ch + 1] = acc.y; red[lane][ch + 2] = acc.z; red[lane][ch + 3] = acc.w;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) s += red[l][threadIdx.x];
+    partial[((long long)n * nsplit + split) * 64 + threadIdx.x] = s;
+  }
+}
+
+// one CTA per clip: d -> q,k -> A = q k^T / 64 -> row softmax -> W [T][T], column sums
+__global__ void __launch_bounds__(64) ga_weights_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ fcb,
+                                                        const float* __restrict__ p2w, const float* __restrict__ p2b,
+                                                        const float* __restrict__ p3w, const float* __restrict__ p3b,
+                                                        float* __restrict__ wmat, float* __restrict__ wsum, int T) {
+  constexpr int MAXT = 32;
+  __shared__ float d[MAXT][64], q[MAXT][64], k[MAXT][64], A[MAXT][MAXT];
+  const int b = blockIdx.x, c = threadIdx.x;
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[(((long long)b * T + t) * nsplit + sp) * 64 + c];
+    d[t][c] = s + fcb[0];
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    float sq = p2b[c], sk = p3b[c];
+    for (int i = 0; i < 64; ++i) {
+      sq += p2w[c * 64 + i] * d[t][i];
+      sk += p3w[c * 64 + i] * d[t][i];
+    }
+    q[t][c] = sq;
+    k[t][c] = sk;
+  }
+  __syncthreads();
+  for (int e = c; e < T * T; e += 64) {
+    const int t = e / T, u = e % T;
+    float s = 0.f;
+    for (int i = 0; i < 64; ++i) s += q[t][i] * k[u][i];
+    A[t][u] = s / 64.0f;
+  }
+  __syncthreads();
+  if (c < T) {
+    const int t = c;
+    float mx = -INFINITY;
+    for (int u = 0; u < T; ++u) mx = fmaxf(mx, A[t][u]);
+    float sum = 0.f;
+    for (int u = 0; u < T; ++u) { A[t][u] = expf(A[t][u] - mx); sum += A[t][u]; }
+    for (int u = 0; u < T; ++u) {
+      A[t][u] = A[t][u] / sum;
+      wmat[((long long)b * T + t) * T + u] = A[t][u];
+    }
+  }
+  __syncthreads();
+  if (c < T) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += A[t][c];
+    wsum[(long long)b * T + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Soft-GMM sampler: one warp per LR pixel.  Channel ch = hf*15 + k*3 + j (j: 0 logit, 1 log-scale, 2 mean);
+// the softmax runs over the 48 hf channels for each k; v[hf] = sum_k pi * (eps*exp(clamp(ls,-7,7)) + mu).
+// eps is read from `eps` (reference layout [B,48,5,T,h,w]) or generated by Philox at that linear index.
+// ------------------------------------------------------------------------------------------------------
+template <bool P_NCHW, bool V_NCHW>
+__global__ void __launch_bounds__(128) gmm_sample_kernel(const float* __restrict__ params, const float* __restrict__ eps, uint64_t seed,
+                                                         uint64_t offset, float* __restrict__ v, int vpitch, int voff, int T, int h,
+                                                         int w, long long M) {
+  __shared__ __align__(16) float sp[4][720];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const long long hw = (long long)h * w;
+  const long long n = m / hw, pix = m - n * hw;
+  const int t = (int)(n % T);
+  const long long b = n / T;
+  float* P = sp[warp];
+  if (P_NCHW) {
+    for (int c = lane; c < 720; c += 32) P[c] = __ldg(params + (n * 720 + c) * hw + pix);
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(params + m * 720);
+    for (int c = lane; c < 180; c += 32) reinterpret_cast<float4*>(P)[c] = __ldg(src + c);
+  }
+  __syncwarp();
+  // each lane owns hf = lane and (lane < 16) hf = lane + 32
+  const int hf0 = lane, hf1 = lane + 32;
+  const bool has1 = hf1 < kHF;
+  float out0 = 0.f, out1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < kGmmK; ++k) {
+    const float l0 = P[hf0 * 15 + k * 3], l1 = has1 ? P[hf1 * 15 + k * 3] : -INFINITY;
+    float mx = fmaxf(l0, l1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e0 = expf(l0 - mx), e1 = has1 ? expf(l1 - mx) : 0.f;
+    float sum = e0 + e1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    {
+      const float ls = fminf(fmaxf(P[hf0 * 15 + k * 3 + 1], -7.f), 7.f);
+      const float mu = P[hf0 * 15 + k * 3 + 2];
+      const uint64_t idx = (uint64_t)(((((b * kHF + hf0) * kGmmK + k) * T + t) * hw) + pix);
+      const float ep = eps ? __ldg(eps + idx) : philox_normal(idx, seed, offset);
+      out0 += (e0 / sum) * (ep * expf(ls) + mu);
+    }
+    if (has1) {
+      const float ls = fminf(fmaxf(P[hf1 * 15 + k * 3 + 1], -7.f), 7.f);
+      const float mu = P[hf1 * 15 + k * 3 + 2];
+      const uint64_t idx = (uint64_t)(((((b * kHF + hf1) * kGmmK + k) * T + t) * hw) + pix);
+      const float ep = eps ? __ldg(eps + idx) : philox_normal(idx, seed, offset);
+      out1 += (e1 / sum) * (ep * expf(ls) + mu);
+    }
+  }
+  if (V_NCHW) {
+    v[(n * kHF + hf0) * hw + pix] = out0;
+    if (has1) v[(n * kHF + hf1) * hw + pix] = out1;
+  } else {
+    v[m * vpitch + voff + hf0] = out0;
+    if (has1) v[m * vpitch + voff + hf1] = out1;
+  }
+}
+
+__global__ void export_eps_kernel(float* __restrict__ eps, uint64_t seed, uint64_t offset, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) eps[i] = philox_normal((uint64_t)i, seed, offset);
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------
+int launch_ga_wmap(const float* fcw, float* wmap, int h, int w, cudaStream_t st) {
+  ga_wmap_kernel<<<cdiv((long long)h * w, 128), 128, 0, st>>>(fcw, wmap, h, w);
+  SELFC_LAUNCH_CHECK("ga_wmap_kernel");
+  return 0;
+}
+
+template <typename T>
+int launch_ga_stat(const T* x, int pitch, const float* wmap, float* partial, int nsplit, int BT, int hw, cudaStream_t st) {
+  ga_stat_kernel<T><<<dim3(nsplit, BT), 256, 0, st>>>(x, pitch, wmap, partial, nsplit, hw);
+  SELFC_LAUNCH_CHECK("ga_stat_kernel");
+  return 0;
+}
+template int launch_ga_stat<float>(const float*, int, const float*, float*, int, int, int, cudaStream_t);
+template int launch_ga_stat<__nv_bfloat16>(const __nv_bfloat16*, int, const float*, float*, int, int, int, cudaStream_t);
+
+int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const float* p2w, const float* p2b, const float* p3w,
+                      const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st) {
+  SELFC_CHECK_ARG(T >= 1 && T <= 32, "GlobalAgg: temporal length %d outside [1,32]", T);
+  ga_weights_kernel<<<B, 64, 0, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
+  SELFC_LAUNCH_CHECK("ga_weights_kernel");
+  return 0;
+}
+
+int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, uint64_t seed, uint64_t offset, float* v,
+                      bool v_nchw, int vpitch, int voff, int B, int T, int h, int w, cudaStream_t st) {
+  const long long M = (long long)B * T * h * w;
+  if (M == 0) return 0;
+  const int grid = cdiv(M, 4);
+  if (params_nchw && v_nchw)
+    gmm_sample_kernel<true, true><<<grid, 128, 0, st>>>(params, eps, seed, offset, v, vpitch, voff, T, h, w, M);
+  else if (!params_nchw && !v_nchw)
+    gmm_sample_kernel<false, false><<<grid, 128, 0, st>>>(params, eps, seed, offset, v, vpitch, voff, T, h, w, M);
+  else if (!params_nchw && v_nchw)
+    gmm_sample_kernel<false, true><<<grid, 128, 0, st>>>(params, eps, seed, offset, v, vpitch, voff, T, h, w, M);
+  else
+    gmm_sample_kernel<true, false><<<grid, 128, 0, st>>>(params, eps, seed, offset, v, vpitch, voff, T, h, w, M);
+  SELFC_LAUNCH_CHECK("gmm_sample_kernel");
+  return 0;
+}
+
+int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, long long n, cudaStream_t st) {
+  if (n == 0) return 0;
+  export_eps_kernel<<<cdiv(n, 256), 256, 0, st>>>(eps, seed, offset, n);
+  SELFC_LAUNCH_CHECK("export_eps_kernel");
+  return 0;
+}
+
+}  // namespace selfc

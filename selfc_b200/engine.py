@@ -1,0 +1,286 @@
+"""Host-side driver of libselfc_b200: owns a selfc_ctx (packed-weight cache) and the activation workspace for one
+device, and exposes the path as tensor-in / tensor-out calls.  PyTorch is used for device memory and streams only.
+
+There is no CPU path: every call requires CUDA tensors and the built sm_100a library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MODE_BF16, MODE_FP32, NUM_PARAMS
+
+HF_DIM = 48
+GMM_K = 5
+
+
+def param_names() -> Sequence[str]:
+    """state_dict keys of SelfCInvNet in the canonical order the C-ABI expects."""
+    names = []
+
+    def d2dt(prefix):
+        for k in range(1, 6):
+            names.append(f"{prefix}.conv{k}.weight")
+            names.append(f"{prefix}.conv{k}.bias")
+
+    def gagg(prefix):
+        for m in ("fc", "proj1", "proj2", "proj3"):
+            names.append(f"{prefix}.{m}.weight")
+            names.append(f"{prefix}.{m}.bias")
+
+    for blk in range(1, 9):
+        for sub in "FGH":
+            d2dt(f"operations.{blk}.{sub}")
+    d2dt("stp_net.local_m1")
+    d2dt("stp_net.local_m2")
+    gagg("stp_net.global_m1")
+    gagg("stp_net.global_m2")
+    for i in range(4):
+        d2dt(f"stp_net.other_stp_modules.{2 * i}")
+        gagg(f"stp_net.other_stp_modules.{2 * i + 1}")
+    for idx in (1, 3, 5):
+        names.append(f"stp_net.tail_gmm.{idx}.weight")
+        names.append(f"stp_net.tail_gmm.{idx}.bias")
+    assert len(names) == NUM_PARAMS
+    return names
+
+
+PARAM_NAMES = tuple(param_names())
+PARAM_INDEX = {n: i for i, n in enumerate(PARAM_NAMES)}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def parse_mode(mode) -> int:
+    if mode in (MODE_FP32, "fp32", "float32", None):
+        return MODE_FP32
+    if mode in (MODE_BF16, "bf16", "bfloat16"):
+        return MODE_BF16
+    raise ValueError(f"unknown selfc_b200 precision mode {mode!r} (use 'fp32' or 'bf16')")
+
+
+class Engine:
+    """One selfc_ctx + workspace on one CUDA device."""
+
+    def __init__(self, device: torch.device, mode="fp32"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("selfc_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self.mode = parse_mode(mode)
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self._L.selfc_ctx_create(C.byref(h), self.device.index, self.mode), "ctx_create")
+        self._ctx = h
+        self._ws: Optional[torch.Tensor] = None
+        self._weights_key = None
+        self._keep = None   # keeps fp32 contiguous copies of the parameters alive while packing
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._L.selfc_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ----------------------------------------------------------------------------------------
+    def load_state(self, state: Dict[str, torch.Tensor]) -> None:
+        """(Re)pack weights from a reference-layout state_dict (keys may carry a 'module.' prefix)."""
+        tensors = []
+        for name in PARAM_NAMES:
+            t = state.get(name)
+            if t is None:
+                t = state.get("module." + name)
+            if t is None:
+                raise KeyError(f"state_dict is missing {name}")
+            t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            tensors.append(t)
+        arr = (C.c_void_p * NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_ctx_load_weights(self._ctx, arr, NUM_PARAMS, _stream(self.device)), "load_weights")
+        self._keep = tensors
+
+    def sync_params(self, named_params: Sequence[Tuple[str, torch.Tensor]]) -> None:
+        """Re-pack iff any parameter's storage or version changed since the last call."""
+        key = tuple((p.data_ptr(), p._version) for _, p in named_params)
+        if key != self._weights_key:
+            self.load_state({n: p for n, p in named_params})
+            self._weights_key = key
+
+    # ---- workspace ---------------------------------------------------------------------------------------
+    def _workspace(self, B: int, T: int, h: int, w: int) -> torch.Tensor:
+        need = int(self._L.selfc_workspace_bytes(self._ctx, B, T, h, w))
+        if need == 0:
+            raise RuntimeError(f"selfc_b200: bad clip shape B={B} T={T} h={h} w={w}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _clip_dims(x: torch.Tensor, T: int) -> Tuple[int, int, int]:
+        bt, _, hh, ww = x.shape
+        if T is None or T < 1 or bt % T != 0:
+            raise ValueError(f"batch of {bt} frames is not a multiple of the clip length T={T} (GlobalVar.set_Temporal_LEN)")
+        return bt // T, hh, ww
+
+    def _check_in(self, x: torch.Tensor, what: str) -> torch.Tensor:
+        if not x.is_cuda or x.device != self.device:
+            raise RuntimeError(f"selfc_b200: {what} must live on {self.device} (got {x.device}); there is no CPU path")
+        return x.to(torch.float32).contiguous()
+
+    # ---- the path ----------------------------------------------------------------------------------------
+    def down(self, hr: torch.Tensor, T: int, want_out51: bool = True, want_u8: bool = True, want_q: bool = True):
+        """SelfCInvNet.forward(rev=False) + Quantization.  hr [B*T,3,H,W] -> (out51|None, lr_u8|None, lr_q|None)."""
+        hr = self._check_in(hr, "hr")
+        B, H, W = self._clip_dims(hr, T)
+        if hr.shape[1] != 3 or H % 4 or W % 4:
+            raise ValueError(f"expected [B*T,3,H,W] with H,W multiples of 4, got {tuple(hr.shape)}")
+        h, w = H // 4, W // 4
+        ws = self._workspace(B, T, h, w)
+        out51 = torch.empty((B * T, 51, h, w), dtype=torch.float32, device=self.device) if want_out51 else None
+        lr_u8 = torch.empty((B * T, 3, h, w), dtype=torch.uint8, device=self.device) if want_u8 else None
+        lr_q = torch.empty((B * T, 3, h, w), dtype=torch.float32, device=self.device) if want_q else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_down(self._ctx, _ptr(hr), _ptr(out51), _ptr(lr_u8), _ptr(lr_q), B, T, H, W,
+                                          _ptr(ws), ws.numel(), _stream(self.device)), "down")
+        return out51, lr_u8, lr_q
+
+    def up(self, lr: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
+           want_hf: bool = True):
+        """SelfCInvNet.forward(rev=True).  lr [B*T,3,h,w] -> (hr [B*T,3,4h,4w], recon_hf [B*T,48,h,w]|None)."""
+        lr = self._check_in(lr, "lr")
+        B, h, w = self._clip_dims(lr, T)
+        if lr.shape[1] != 3:
+            raise ValueError(f"expected [B*T,3,h,w], got {tuple(lr.shape)}")
+        if eps is not None:
+            eps = self._check_in(eps, "eps")
+            if tuple(eps.shape) != (B, HF_DIM, GMM_K, T, h, w):
+                raise ValueError(f"eps must be [B,48,5,T,h,w]={(B, HF_DIM, GMM_K, T, h, w)}, got {tuple(eps.shape)}")
+        ws = self._workspace(B, T, h, w)
+        hr = torch.empty((B * T, 3, 4 * h, 4 * w), dtype=torch.float32, device=self.device)
+        hf = torch.empty((B * T, HF_DIM, h, w), dtype=torch.float32, device=self.device) if want_hf else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_up(self._ctx, _ptr(lr), _ptr(eps), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1),
+                                        _ptr(hr), _ptr(hf), B, T, 4 * h, 4 * w, _ptr(ws), ws.numel(),
+                                        _stream(self.device)), "up")
+        return hr, hf
+
+    def rescale(self, hr: torch.Tensor, T: int, seed: int = 0, offset: int = 0, eps: Optional[torch.Tensor] = None):
+        """down -> 8-bit quantise -> up (models/SelfC_model.py:213-233, one pass).  Returns (lr_u8, hr_rec)."""
+        _, lr_u8, lr_q = self.down(hr, T, want_out51=False)
+        rec, _ = self.up(lr_q, T, eps=eps, seed=seed, offset=offset, want_hf=False)
+        return lr_u8, rec
+
+    # ---- per-launch timing (bench.py roofline leg) ---------------------------------------------------------------
+    PROF_CLASSES = ("conv3x3", "conv5_coupling", "global_agg", "gmm_head", "sampler", "layout")
+
+    def prof_enable(self, on: bool = True) -> None:
+        _lib.check(self._L.selfc_prof_enable(self._ctx, 1 if on else 0), "prof_enable")
+
+    def prof_read(self):
+        n = len(self.PROF_CLASSES)
+        ms = (C.c_double * n)()
+        work = (C.c_double * n)()
+        cnt = (C.c_uint64 * n)()
+        _lib.check(self._L.selfc_prof_read(self._ctx, n, ms, work, cnt), "prof_read")
+        return {name: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, name in enumerate(self.PROF_CLASSES)}
+
+    # ---- components (parity tests) --------------------------------------------------------------------------
+    def d2dt(self, prefix: str, x: torch.Tensor, T: int) -> torch.Tensor:
+        first = PARAM_INDEX[prefix + ".conv1.weight"]
+        cout = {"F": 3, "G": 48, "H": 48}.get(prefix.rsplit(".", 1)[-1], 64)
+        x = self._check_in(x, "x")
+        B, h, w = self._clip_dims(x, T)
+        ws = self._workspace(B, T, h, w)
+        y = torch.empty((B * T, cout, h, w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_d2dt(self._ctx, first, _ptr(x), _ptr(y), B, T, h, w, _ptr(ws), ws.numel(),
+                                          _stream(self.device)), "d2dt")
+        return y
+
+    def global_agg(self, prefix: str, x: torch.Tensor, T: int):
+        first = PARAM_INDEX[prefix + ".fc.weight"]
+        x = self._check_in(x, "x")
+        B, h, w = self._clip_dims(x, T)
+        ws = self._workspace(B, T, h, w)
+        y = torch.empty_like(x)
+        wmat = torch.empty((B, T, T), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_global_agg(self._ctx, first, _ptr(x), _ptr(y), _ptr(wmat), B, T, h, w, _ptr(ws),
+                                                ws.numel(), _stream(self.device)), "global_agg")
+        return y, wmat
+
+
+# ---- context-free components -----------------------------------------------------------------------------------
+def _dev_check(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("selfc_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    return x.to(torch.float32).contiguous()
+
+
+def fa_forward(x: torch.Tensor) -> torch.Tensor:
+    x = _dev_check(x)
+    n, c, hh, ww = x.shape
+    out = torch.empty((n, 51, hh // 4, ww // 4), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().selfc_fa_fwd(_ptr(x), _ptr(out), n, hh, ww, _stream(x.device)), "fa_fwd")
+    return out
+
+
+def fa_reverse(z: torch.Tensor) -> torch.Tensor:
+    z = _dev_check(z)
+    n, c, h, w = z.shape
+    if c != 51:
+        raise ValueError("fa_reverse expects 51 channels")
+    y = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().selfc_fa_rev(_ptr(z), _ptr(y), n, h, w, _stream(z.device)), "fa_rev")
+    return y
+
+
+def quantize(x: torch.Tensor):
+    x = _dev_check(x)
+    q8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    qf = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().selfc_quantize(_ptr(x), _ptr(q8), _ptr(qf), x.numel(), _stream(x.device)), "quantize")
+    return q8, qf
+
+
+def gmm_sample(params: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0):
+    params = _dev_check(params)
+    bt, c, h, w = params.shape
+    if c != 720 or bt % T:
+        raise ValueError("gmm_sample expects [B*T,720,h,w]")
+    if eps is not None:
+        eps = _dev_check(eps)
+    v = torch.empty((bt, HF_DIM, h, w), dtype=torch.float32, device=params.device)
+    with torch.cuda.device(params.device):
+        _lib.check(_lib.lib().selfc_gmm_sample(_ptr(params), _ptr(eps), seed, offset, _ptr(v), bt // T, T, h, w,
+                                               _stream(params.device)), "gmm_sample")
+    return v
+
+
+def export_eps(B: int, T: int, h: int, w: int, seed: int, offset: int, device) -> torch.Tensor:
+    eps = torch.empty((B, HF_DIM, GMM_K, T, h, w), dtype=torch.float32, device=device)
+    with torch.cuda.device(eps.device):
+        _lib.check(_lib.lib().selfc_export_eps(_ptr(eps), seed, offset, B, T, h, w, _stream(eps.device)), "export_eps")
+    return eps
+
+
+def launch_count() -> int:
+    return int(_lib.lib().selfc_launch_count())

@@ -1,0 +1,97 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/selfc_b200.h
+declares (no compute calls without a GPU), the module tree has the reference's state_dict layout, the options loader
+behaves like the reference's, and the product path refuses to run without CUDA (no fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import selfc_oracle as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "selfc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(selfc_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from selfc_b200 import _lib, build
+    build.build()
+    L = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/selfc_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in selfc_b200/_lib.py"
+    assert L.selfc_version() >= 100
+    assert L.selfc_last_error() is not None
+
+
+def test_module_layout_is_the_reference_state_dict():
+    from selfc_b200 import networks, options
+    from selfc_b200.engine import PARAM_NAMES
+    opt = options.dict_to_nonedict(options.parse(os.path.join(ROOT, "selfc_b200", "configs", "selfc_large_synthetic.yml"), is_train=False))
+    assert opt["network_G"]["no_such_key"] is None and opt["is_train"] is False
+    assert opt["datasets"]["test_1"]["phase"] == "test" and opt["datasets"]["test_1"]["data_type"] == "img"
+    net = networks.define_G(opt)
+    sd = net.state_dict()
+    shapes = so.param_shapes()
+    assert list(sd.keys()) == list(shapes.keys()) == list(PARAM_NAMES)
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+    assert sum(v.numel() for v in sd.values()) == 3_365_038
+    # strict load of a reference-layout checkpoint, with and without DataParallel's 'module.' prefix stripped by the caller
+    net.load_state_dict(so.make_state_dict(0), strict=True)
+    assert len(list(net.buffers())) == 0
+
+
+def test_unsupported_variants_fail_loudly():
+    from selfc_b200 import networks, options
+    opt = options.dict_to_nonedict(options.parse(os.path.join(ROOT, "selfc_b200", "configs", "selfc_large_synthetic.yml"), is_train=False))
+    opt["model"] = "IRN"
+    with pytest.raises(NotImplementedError):
+        networks.define_G(opt)
+    opt["model"] = "SelfC_GMM"
+    opt["network_G"]["global_module"] = "nolocal"     # the typo in two reference YAMLs
+    with pytest.raises(NotImplementedError):
+        networks.define_G(opt)
+
+
+def test_no_cpu_fallback():
+    from selfc_b200 import networks, options
+    from selfc_b200.global_var import GlobalVar
+    opt = options.dict_to_nonedict(options.parse(os.path.join(ROOT, "selfc_b200", "configs", "selfc_large_synthetic.yml"), is_train=False))
+    net = networks.define_G(opt)
+    GlobalVar.set_Temporal_LEN(1)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        net(torch.zeros(1, 3, 8, 8))
+    from selfc_b200 import engine
+    with pytest.raises(RuntimeError, match="no CPU"):
+        engine.fa_forward(torch.zeros(1, 3, 8, 8))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "selfc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/codes"), reason="reference mount absent (GPU box)")
+def test_same_seed_same_initial_weights_as_reference():
+    """torch.manual_seed(s); define_G(opt) draws the same default-init weights as the reference."""
+    from oracle import ref_shim
+    from selfc_b200 import networks, options
+    ref = ref_shim.load_reference()
+    torch.manual_seed(3)
+    rnet = ref.build_net(7)
+    opt = options.dict_to_nonedict(options.parse(ref_shim.VID4_YAML, is_train=False))   # the UNMODIFIED reference YAML
+    torch.manual_seed(3)
+    mine = networks.define_G(opt)
+    a, b = rnet.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)

@@ -1,0 +1,253 @@
+"""GPU parity tests: the sm_100a kernels (through the C-ABI) against the CPU oracle on the same seeded inputs,
+against the committed golden fixtures, and through size-independent properties at the benchmark's full size.
+
+Tolerances (BASELINE.json north_star): LR uint8 within +-1 LSB on >= 99.99 % of pixels; HR max-abs <= 1e-3 in fp32
+mode, <= 2e-2 in bf16 mode.  Integer / index work (FrequencyAnalyzer, quantisation) is bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import selfc_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+HR_TOL_FP32 = 1e-3
+HR_TOL_BF16 = 2e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _engine(dev, sd, mode="fp32"):
+    from selfc_b200.engine import Engine
+    eng = Engine(dev, mode)
+    eng.load_state(sd)
+    return eng
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+# ------------------------------------------------------------------------------------------------ a1 / a10 / a4
+def test_fa_golden_bit_exact(dev, golden_dir):
+    from selfc_b200 import engine
+    g = np.load(os.path.join(golden_dir, "fa.npz"))
+    assert torch.equal(engine.fa_forward(_t(g["x"]).to(dev)).cpu(), _t(g["fwd"]))
+    assert torch.equal(engine.fa_reverse(_t(g["z"]).to(dev)).cpu(), _t(g["rev"]))
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 4), (2, 8, 12), (3, 36, 52), (7, 144, 176)])
+def test_fa_vs_oracle_bit_exact(dev, shape):
+    from selfc_b200 import engine
+    n, hh, ww = shape
+    gen = torch.Generator().manual_seed(hh * 131 + ww)
+    x = torch.rand(n, 3, hh, ww, generator=gen)
+    z = torch.randn(n, 51, hh // 4, ww // 4, generator=gen)
+    assert torch.equal(engine.fa_forward(x.to(dev)).cpu(), so.fa_forward(x))
+    assert torch.equal(engine.fa_reverse(z.to(dev)).cpu(), so.fa_reverse(z))
+
+
+def test_quantize_bit_exact(dev):
+    from selfc_b200 import engine
+    k = torch.arange(0, 256, dtype=torch.float32)
+    x = torch.cat([k / 255.0, (k + 0.5) / 255.0, (k + 0.49999) / 255.0, torch.tensor([-1.0, -0.0, 1.0, 1.5, 2e-3]),
+                   torch.rand(10007, generator=torch.Generator().manual_seed(1)) * 1.2 - 0.1])
+    q8, qf = engine.quantize(x.to(dev))
+    assert torch.equal(q8.cpu(), so.quantize_u8(x))
+    assert torch.equal(qf.cpu(), so.quantize(x))
+
+
+# ------------------------------------------------------------------------------------------------ a3 / a6 / a7
+@pytest.mark.parametrize("prefix,cin", [("operations.1.F", 48), ("operations.3.G", 3), ("operations.8.H", 3),
+                                        ("stp_net.local_m1", 3), ("stp_net.local_m2", 64),
+                                        ("stp_net.other_stp_modules.4", 64)])
+def test_dense_block_vs_oracle(dev, prefix, cin):
+    sd = so.make_state_dict(5)
+    eng = _engine(dev, sd)
+    b, t, h, w = 2, 3, 13, 21     # ragged: not a multiple of any tile
+    x = torch.randn(b * t, cin, h, w, generator=torch.Generator().manual_seed(7)) * 0.5
+    with torch.no_grad():
+        ref = so.d2dt(sd, prefix, x, t)
+    got = eng.d2dt(prefix, x.to(dev), t).cpu()
+    torch.testing.assert_close(got, ref, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("h,w,t", [(10, 18, 2), (32, 32, 3), (45, 67, 7)])
+def test_global_agg_vs_oracle(dev, h, w, t):
+    sd = so.make_state_dict(6, gain=2.0)
+    eng = _engine(dev, sd)
+    b = 2
+    x = torch.randn(b * t, 64, h, w, generator=torch.Generator().manual_seed(h))
+    with torch.no_grad():
+        ref = so.global_agg(sd, "stp_net.global_m2", x, t)
+        wref = so.global_agg_weights(sd, "stp_net.global_m2", x, t)
+    got, wmat = eng.global_agg("stp_net.global_m2", x.to(dev), t)
+    torch.testing.assert_close(wmat.cpu(), wref, rtol=0, atol=1e-6)
+    torch.testing.assert_close(got.cpu(), ref, rtol=0, atol=2e-5)
+
+
+def test_gmm_sample_vs_oracle(dev):
+    from selfc_b200 import engine
+    b, t, h, w = 2, 3, 5, 9
+    gen = torch.Generator().manual_seed(3)
+    params = torch.randn(b * t, 720, h, w, generator=gen) * 3.0      # exercises the +-7 clamp
+    eps = so.make_eps(b, t, h, w, 17)
+    ref = so.gmm_sample(params, eps, t)
+    got = engine.gmm_sample(params.to(dev), t, eps=eps.to(dev)).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-4)
+    # counter-based noise: export the stream, feed it to the oracle
+    eps2 = engine.export_eps(b, t, h, w, seed=42, offset=3, device=dev)
+    got2 = engine.gmm_sample(params.to(dev), t, seed=42, offset=3).cpu()
+    torch.testing.assert_close(got2, so.gmm_sample(params, eps2.cpu(), t), rtol=1e-5, atol=1e-4)
+
+
+def test_philox_stream(dev):
+    from selfc_b200 import engine
+    a = engine.export_eps(1, 7, 16, 24, seed=42, offset=0, device=dev).cpu()
+    b = engine.export_eps(1, 7, 16, 24, seed=42, offset=0, device=dev).cpu()
+    c = engine.export_eps(1, 7, 16, 24, seed=42, offset=1, device=dev).cpu()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1.0) < 5e-3
+    # keyed on the linear index: a bigger batch's first clip draws the same numbers (GPU-count invariance)
+    big = engine.export_eps(2, 7, 16, 24, seed=42, offset=0, device=dev).cpu()
+    assert torch.equal(big[0], a[0])
+    ref = so.philox_normal(np.arange(4096, dtype=np.uint64), seed=42, offset=0)
+    np.testing.assert_allclose(a.reshape(-1)[:4096].numpy(), ref, rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ a2 / a9 / a11
+@pytest.mark.parametrize("name", ["net_t3", "net_t7", "net_t2_gain"])
+def test_network_vs_golden_and_oracle(dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    b, t, hh, ww, wseed, xseed = [int(v) for v in g["meta"]]
+    sd = so.make_state_dict(wseed, float(g["gain"]))
+    eng = _engine(dev, sd)
+    x = _t(g["x"])
+    out51, lr_u8, lr_q = eng.down(x.to(dev), t)
+    torch.testing.assert_close(out51.cpu(), _t(g["down_out"]), rtol=0, atol=1e-4)
+    ref_u8 = so.quantize_u8(_t(g["down_out"])[:, :3])
+    diff = (lr_u8.cpu().int() - ref_u8.int()).abs()
+    assert diff.max().item() <= 1 and (diff == 0).float().mean().item() >= 0.9999
+    assert torch.equal(lr_q.cpu(), lr_u8.cpu().float() / 255.0)
+    # up, from the REFERENCE's quantised LR so both sides see identical inputs
+    eps = so.make_eps(b, t, hh // 4, ww // 4, int(g["eps_seed"]))
+    hr, hf = eng.up(_t(g["lr"]).to(dev), t, eps=eps.to(dev))
+    torch.testing.assert_close(hf.cpu(), _t(g["hf"]), rtol=0, atol=5e-4)
+    torch.testing.assert_close(hr.cpu(), _t(g["hr"]), rtol=0, atol=HR_TOL_FP32)
+
+
+def test_vid4_shape_clip_vs_oracle(dev):
+    """configs[0]/[1]: one 7-frame 576x704 clip, fp32 mode, against the oracle at full size."""
+    b, t, hh, ww = 1, 7, 576, 704
+    sd = so.make_state_dict(0)
+    eng = _engine(dev, sd)
+    x = so.make_frames(b, t, hh, ww, 1234)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 99)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        z = so.net_down(sd, x, t)
+        lr = so.quantize(z[:, :3])
+        hr_ref, hf_ref = so.net_up(sd, lr, eps, t)
+    out51, lr_u8, lr_q = eng.down(x.to(dev), t)
+    torch.testing.assert_close(out51.cpu(), z, rtol=0, atol=2e-4)
+    diff = (lr_u8.cpu().int() - so.quantize_u8(z[:, :3]).int()).abs()
+    assert diff.max().item() <= 1 and (diff == 0).float().mean().item() >= 0.9999
+    hr, hf = eng.up(lr.to(dev), t, eps=eps.to(dev))
+    torch.testing.assert_close(hf.cpu(), hf_ref, rtol=0, atol=5e-4)
+    assert (hr.cpu() - hr_ref).abs().max().item() <= HR_TOL_FP32
+    # per-clip metrics within 0.01 dB / 1e-4 (test_rescaling.py:109-123)
+    ya, yb, y0 = so.rgb_to_y(hr.cpu()), so.rgb_to_y(hr_ref), so.rgb_to_y(x)
+    p_got, p_ref = np.mean(so.psnr_frames(ya, y0)), np.mean(so.psnr_frames(yb, y0))
+    s_got, s_ref = np.mean(so.ssim_frames(ya, y0)), np.mean(so.ssim_frames(yb, y0))
+    assert abs(p_got - p_ref) <= 0.01 and abs(s_got - s_ref) <= 1e-4
+
+
+def test_bf16_mode_vs_oracle(dev):
+    """bf16 mode (tcgen05 convolutions, bf16 activations, fp32 state): HR within 2e-2, LR within +-1 LSB."""
+    b, t, hh, ww = 2, 7, 96, 160
+    sd = so.make_state_dict(0)
+    eng = _engine(dev, sd, "bf16")
+    x = so.make_frames(b, t, hh, ww, 77)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 5)
+    with torch.no_grad():
+        z = so.net_down(sd, x, t)
+        lr = so.quantize(z[:, :3])
+        hr_ref, hf_ref = so.net_up(sd, lr, eps, t)
+    out51, lr_u8, _ = eng.down(x.to(dev), t)
+    diff = (lr_u8.cpu().int() - so.quantize_u8(z[:, :3]).int()).abs()
+    assert diff.max().item() <= 1 and (diff <= 1).float().mean().item() >= 0.9999
+    hr, hf = eng.up(lr.to(dev), t, eps=eps.to(dev))
+    assert (hr.cpu() - hr_ref).abs().max().item() <= HR_TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------------ boundary (8b)
+def test_drop_in_module_matches_oracle(dev):
+    from selfc_b200 import networks, options
+    from selfc_b200.global_var import GlobalVar
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    opt = options.dict_to_nonedict(options.parse(os.path.join(here, "selfc_b200", "configs", "selfc_large_synthetic.yml"),
+                                                 is_train=False))
+    net = networks.define_G(opt)
+    sd = so.make_state_dict(4)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    b, t, hh, ww = 1, 3, 24, 40
+    GlobalVar.set_Temporal_LEN(t)
+    x = so.make_frames(b, t, hh, ww, 21)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 8)
+    with torch.no_grad():
+        out, loss_c = net(x=x.to(dev))
+        assert out.shape == (b * t, 51, hh // 4, ww // 4) and float(loss_c) == 0.0
+        z = so.net_down(sd, x, t)
+        torch.testing.assert_close(out.cpu(), z, rtol=0, atol=1e-4)
+        lr = so.quantize(z[:, :3])
+        net.inject_eps(eps.to(dev))
+        hr, hf = net(x=lr.to(dev), rev=True)
+        hr_ref, hf_ref = so.net_up(sd, lr, eps, t)
+        torch.testing.assert_close(hf.cpu(), hf_ref, rtol=0, atol=5e-4)
+        torch.testing.assert_close(hr.cpu(), hr_ref, rtol=0, atol=HR_TOL_FP32)
+        assert net.stp_net.gmm_v.shape == (b, 48, t, hh // 4, ww // 4)
+    with pytest.raises(RuntimeError):
+        net.cpu()(x=x)                      # no CPU fallback
+
+
+def test_errors_are_loud(dev):
+    from selfc_b200.engine import Engine
+    eng = Engine(dev, "fp32")
+    with pytest.raises(RuntimeError, match="weights not loaded"):
+        eng.down(torch.zeros(1, 3, 8, 8, device=dev), 1)
+    eng.load_state(so.make_state_dict(0))
+    with pytest.raises(ValueError):
+        eng.down(torch.zeros(3, 3, 8, 8, device=dev), 2)      # B*T not a multiple of T
+    with pytest.raises(ValueError):
+        eng.down(torch.zeros(2, 3, 10, 8, device=dev), 2)     # H not a multiple of 4
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_1080p_properties(dev):
+    """BASELINE.json configs[2] size (one 7-frame 1080p GOP): properties that need no oracle run."""
+    b, t, hh, ww = 1, 7, 1080, 1920
+    sd = so.make_state_dict(0)
+    eng = _engine(dev, sd)
+    x = so.make_frames(b, t, hh, ww, 4321).to(dev)
+    out51, lr_u8, lr_q = eng.down(x, t)
+    # LR codes are exactly the quantisation of the returned latent
+    assert torch.equal(lr_u8, torch.round(out51[:, :3].clamp(0, 1) * 255.0).to(torch.uint8))
+    # determinism + seed/offset sensitivity + batch invariance of the noise stream
+    hr1, _ = eng.up(lr_q, t, seed=7, offset=0)
+    hr2, _ = eng.up(lr_q, t, seed=7, offset=0)
+    hr3, _ = eng.up(lr_q, t, seed=7, offset=1)
+    assert torch.equal(hr1, hr2) and not torch.equal(hr1, hr3)
+    assert torch.isfinite(hr1).all()
+    # the first frame's top-left corner depends only on its own GOP: a 2-GOP batch reproduces it
+    x2 = torch.cat([x, x.flip(0)], 0)
+    _, lr2_u8, lr2_q = eng.down(x2, t, want_out51=False)
+    assert torch.equal(lr2_u8[:t], lr_u8)
