@@ -78,6 +78,10 @@ int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* 
  * `first_param` (its conv1.weight); x [B*T,Cin,h,w] -> y [B*T,Cout,h,w], both fp32 NCHW. */
 int selfc_d2dt(selfc_ctx* ctx, int first_param, const float* x, float* y, int B, int T, int h, int w,
                void* workspace, size_t workspace_bytes, void* stream);
+/* one (1,3,3) conv of that dense block (Subnet_constructor.py:102-105,126-129), k = 0..3 for conv1..conv4:
+ * x [B*T, Cin+32k, h, w] (the concatenated input) -> y [B*T,32,h,w] = LeakyReLU_0.2(conv(x) + bias) */
+int selfc_conv3x3(selfc_ctx* ctx, int first_param, int k, const float* x, float* y, int B, int T, int h, int w,
+                  void* workspace, size_t workspace_bytes, void* stream);
 /* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
  * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
 int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "conv3x3_tc" 2>&1 | tail -40 > gpurun_out/r2_tc.log
+tail -25 gpurun_out/r2_tc.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "bf16 or dense_block" 2>&1 | tail -20 > gpurun_out/r2_bf16.log
+tail -8 gpurun_out/r2_bf16.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -4
+timeout 600 python bench.py --mode bf16 --frames 14 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_bf16.json 2> gpurun_out/r2_bench_bf16.err; tail -c 2500 gpurun_out/r2_bench_bf16.json; tail -3 gpurun_out/r2_bench_bf16.err

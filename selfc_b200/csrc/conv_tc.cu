@@ -1,8 +1,430 @@
+// (1,3,3) dense-block convolution as a tcgen05 / TMEM / TMA implicit GEMM (BF16 mode).
+//
+// What it computes (Subnet_constructor.py:102-105,126-129): for conv_k of a D2DTInput block stored in a pixel-major
+// bf16 dense buffer [M][pitch],  out[:, cin:cin+32] = lrelu_0.2( conv3x3(buf[:, 0:cin]) + bias ),  zero padding.
+//
+// Mapping to the hardware
+//   * GEMM view: D[pixels, 32] = sum over 9 taps, cin channels of A_tap[pixels, ch] * W_tap[ch, 32].
+//   * Tile = 8 output rows x 30 output columns.  The TMA loads the (8+2) x (30+2) halo ONCE per 16-channel slice
+//     as two 8-channel planes [10][32][8ch] (one cp.async.bulk.tensor.4d each; out-of-image coordinates are
+//     zero-filled by the TMA = the conv's zero padding).  A plane is exactly the no-swizzle K-major UMMA core-
+//     matrix layout with rows = halo pixels in flattened order (16 B per pixel per plane), so the A operand of tap
+//     (ky,kx) is the SAME shared-memory tile with the descriptor start address advanced by (ky*32+kx)*16 bytes:
+//     nine taps re-use one load.  M = 128 consecutive flattened positions; two M-blocks cover the 8x32 positions
+//     (the 2 halo columns per row are computed and discarded: 240/256 useful).
+//   * The whole conv's weights (<= 92 KB bf16) stay resident in shared memory for the life of the persistent CTA,
+//     pre-packed on the host side of the ABI as the exact B-operand core-matrix image.
+//   * Accumulators: 2 M-blocks x 32 fp32 columns in TMEM, double-buffered across tiles (128 columns) so the
+//     epilogue of tile i (tcgen05.ld -> +bias -> LeakyReLU -> bf16 -> global, written in place into the dense
+//     buffer: the concat is address arithmetic) overlaps the MMAs of tile i+1.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
+//     warps 2..5 = epilogue (one TMEM lane quarter each).  8-stage mbarrier ring between TMA and MMA.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "conv_tc.h"
+
 namespace selfc {
-int pack_tc_weights(TcConvW&, const float*, const float*, int, int, int, int, cudaStream_t) { return 0; }
-void free_tc_weights(TcConvW& w) { if (w.img) cudaFree(w.img); if (w.bias) cudaFree(w.bias); w.img = nullptr; w.bias = nullptr; }
-int launch_conv3x3_tc(const TcConvW&, __nv_bfloat16*, int, int, int, int, int, int, cudaStream_t) {
-  set_error("conv3x3_tc not built"); return SELFC_E_UNSUPPORTED; }
+namespace tc {
+
+constexpr int WT = 32;                    // tile pitch (30 valid columns + 2 halo)
+constexpr int VALID_W = WT - 2;
+constexpr int ROWS = 8;                   // output rows per tile
+constexpr int HT = ROWS + 2;
+constexpr int PLANE_BYTES = HT * WT * 16; // one 8-channel plane of the halo tile
+constexpr int STAGE_BYTES = 2 * PLANE_BYTES;   // 16 channels = one UMMA K step
+constexpr int NSTAGE = 8;
+constexpr int MBLK = 2;                   // 2 x 128 flattened positions per tile
+constexpr int NOUT = 32;
+constexpr int ACC_COLS = MBLK * NOUT;     // TMEM columns per accumulator buffer
+constexpr int TMEM_COLS = 2 * ACC_COLS;   // double buffered
+constexpr int MAX_CIN = 160;
+constexpr int WTILE_BYTES = NOUT * 16 * 2;   // one (tap, k-step) B tile: 32 x 16 bf16
+constexpr int THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+struct SmemLayout {
+  // offsets from the 1024-aligned dynamic smem base
+  static constexpr int A_OFF = 0;                                   // NSTAGE stages
+  static constexpr int A_PAD = 1024;                                // garbage rows of the last M-block read 32 B past a plane
+  static constexpr int BAR_OFF = A_OFF + NSTAGE * STAGE_BYTES + A_PAD;
+  static constexpr int W_OFF = BAR_OFF + 256;
+  static int total(int cin) { return W_OFF + 9 * (cin / 16) * WTILE_BYTES + 1024; }
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) {
+      if (err) atomicExch(err, code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14), LBO>>4 [16,30) = byte distance between the two 8-element K core matrices,
+// SBO>>4 [32,46) = byte distance between 8-row groups, version=1 [46,48), layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A,B K-major, N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+struct Params {
+  const void* wimg;
+  const float* bias;
+  __nv_bfloat16* buf;
+  int pitch, out_off, N, h, w, nchunk;   // nchunk = cin / 16
+  int tiles_x, tiles_y, ntiles;
+  int* err;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16-byte aligned: round up to 1024 by hand
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base + SmemLayout::A_OFF;
+  const uint32_t bar_base = base + SmemLayout::BAR_OFF;
+  const uint32_t w_base = base + SmemLayout::W_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * NSTAGE);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + 3 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 5);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + SmemLayout::BAR_OFF + 8 * (2 * NSTAGE + 5));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int nchunk = p.nchunk;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t wbytes = 9u * nchunk * WTILE_BYTES;
+      mbar_expect_tx(w_bar, wbytes);
+      for (int tap = 0; tap < 9; ++tap)
+        bulk_g2s(w_base + tap * nchunk * WTILE_BYTES, (const uint8_t*)p.wimg + (size_t)tap * nchunk * WTILE_BYTES,
+                 (uint32_t)nchunk * WTILE_BYTES, w_bar);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int n = tile / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * VALID_W - 1, y0 = ty * ROWS - 1;
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(empty_bar(s), ph ^ 1u, p.err, 1);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const uint32_t dst = a_base + s * STAGE_BYTES;
+          tma_load_4d(dst, &tmap, full_bar(s), c * 16, x0, y0, n);
+          tma_load_4d(dst + PLANE_BYTES, &tmap, full_bar(s), c * 16 + 8, x0, y0, n);
+          if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      mbar_wait(w_bar, 0, p.err, 2);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u, p.err, 3);
+        tc_fence_after();
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(full_bar(s), ph, p.err, 4);
+          tc_fence_after();
+          const uint32_t a_stage = a_base + s * STAGE_BYTES;
+#pragma unroll
+          for (int mb = 0; mb < MBLK; ++mb) {
+            const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS + mb * NOUT);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ky = tap / 3, kx = tap % 3;
+              const uint64_t ad = umma_desc(a_stage + (uint32_t)(mb * 128 + ky * WT + kx) * 16u, PLANE_BYTES, 128);
+              const uint64_t bd = umma_desc(w_base + (uint32_t)(tap * nchunk + c) * WTILE_BYTES, 512, 128);
+              umma_bf16(d, ad, bd, kIdesc, (c > 0 || tap > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(s));      // frees the stage when these MMAs have read it
+          if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    float bias[NOUT];
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) bias[j] = __ldg(p.bias + j);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int n = tile / (p.tiles_x * p.tiles_y);
+      mbar_wait(tfull_bar(acc), use & 1u, p.err, 5);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < MBLK; ++mb) {
+        uint32_t r[NOUT];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mb * NOUT);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // flattened halo-tile position of this accumulator row
+        const int f = WT + 1 + mb * 128 + q * 32 + lane;
+        const int fy = f / WT, fx = f % WT;
+        const int y = ty * ROWS + fy - 1, x = tx * VALID_W + fx - 1;
+        if (fx >= 1 && fx <= VALID_W && fy <= ROWS && y < p.h && x < p.w) {
+          __nv_bfloat16* o = p.buf + ((size_t)((size_t)n * p.h + y) * p.w + x) * p.pitch + p.out_off;
+#pragma unroll
+          for (int j = 0; j < NOUT; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = lrelu02(__uint_as_float(r[j + e]) + bias[j + e]);
+            uint4 pk;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[4], v[5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(v[6], v[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&b0);
+            pk.y = *reinterpret_cast<uint32_t*>(&b1);
+            pk.z = *reinterpret_cast<uint32_t*>(&b2);
+            pk.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---- weight image ------------------------------------------------------------------------------------------
+// wref [32][cin_ref][3][3] fp32 -> bf16 image [tap][kstep][kcore(2)][ngroup(4)][n%8][k%8]
+__global__ void pack_tc_kernel(const float* __restrict__ wref, __nv_bfloat16* __restrict__ img, int cin_ref, int cin_buf, int xreal,
+                               int xpad) {
+  const int nchunk = cin_buf / 16;
+  const int total = 9 * cin_buf * NOUT;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = idx % NOUT;
+  const int c = (idx / NOUT) % cin_buf;
+  const int tap = idx / (NOUT * cin_buf);
+  const int cref = c < xreal ? c : (c < xpad ? -1 : c - xpad + xreal);
+  float v = 0.f;
+  if (cref >= 0 && cref < cin_ref) v = wref[((size_t)n * cin_ref + cref) * 9 + tap];
+  const int ks = c / 16, kk = c % 16;
+  const size_t off = (size_t)(tap * nchunk + ks) * (WTILE_BYTES / 2) + (size_t)((kk / 8) * 4 + n / 8) * 64 + (n % 8) * 8 + (kk % 8);
+  img[off] = __float2bfloat16_rn(v);
+}
+
+}  // namespace tc
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int* g_err_flag[64] = {};
+
+static int* err_flag_for_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!g_err_flag[dev]) {
+    if (cudaMalloc(&g_err_flag[dev], sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(g_err_flag[dev], 0, sizeof(int));
+  }
+  return g_err_flag[dev];
+}
+
+int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st) {
+  SELFC_CHECK_ARG(cin_buf % 16 == 0 && cin_buf <= tc::MAX_CIN, "conv3x3_tc: cin %d must be a multiple of 16 and <= %d", cin_buf,
+                  tc::MAX_CIN);
+  const size_t bytes = (size_t)9 * (cin_buf / 16) * tc::WTILE_BYTES;
+  if (w.img == nullptr || w.img_bytes != bytes) {
+    free_tc_weights(w);
+    SELFC_CUDA(cudaMalloc(&w.img, bytes));
+    SELFC_CUDA(cudaMalloc(&w.bias, tc::NOUT * sizeof(float)));
+    w.img_bytes = bytes;
+  }
+  w.cin_buf = cin_buf;
+  const int total = 9 * cin_buf * tc::NOUT;
+  tc::pack_tc_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, reinterpret_cast<__nv_bfloat16*>(w.img), cin_ref, cin_buf, xreal, xpad);
+  SELFC_LAUNCH_CHECK("pack_tc_kernel");
+  SELFC_CUDA(cudaMemcpyAsync(w.bias, bref, tc::NOUT * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+void free_tc_weights(TcConvW& w) {
+  if (w.img) cudaFree(w.img);
+  if (w.bias) cudaFree(w.bias);
+  w.img = nullptr;
+  w.bias = nullptr;
+  w.img_bytes = 0;
+}
+
+int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, int out_off, int N, int h, int wd, cudaStream_t st) {
+  SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
+  SELFC_CHECK_ARG(pitch % 8 == 0 && out_off % 8 == 0 && aligned16(buf), "conv3x3_tc: pitch/out_off/buffer alignment");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SELFC_E_CUDA;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {(cuuint64_t)pitch, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N};
+  const cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)wd * pitch * 2, (cuuint64_t)h * wd * pitch * 2};
+  const cuuint32_t box[4] = {8, (cuuint32_t)tc::WT, (cuuint32_t)tc::HT, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (pitch %d, %dx%dx%d)", (int)r, pitch, N, h, wd);
+    return SELFC_E_CUDA;
+  }
+  tc::Params p;
+  p.wimg = w.img;
+  p.bias = w.bias;
+  p.buf = buf;
+  p.pitch = pitch;
+  p.out_off = out_off;
+  p.N = N;
+  p.h = h;
+  p.w = wd;
+  p.nchunk = cin / 16;
+  p.tiles_x = cdiv(wd, tc::VALID_W);
+  p.tiles_y = cdiv(h, tc::ROWS);
+  p.ntiles = p.tiles_x * p.tiles_y * N;
+  p.err = err_flag_for_device();
+  if (p.ntiles == 0) return 0;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int smem = tc::SmemLayout::total(cin);
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    SELFC_CUDA(cudaFuncSetAttribute(tc::conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout::total(tc::MAX_CIN)));
+    smem_set = tc::SmemLayout::total(tc::MAX_CIN);
+  }
+  const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
+  tc::conv3x3_tc_kernel<<<grid, tc::THREADS, smem, st>>>(tmap, p);
+  SELFC_LAUNCH_CHECK("conv3x3_tc_kernel");
+  return 0;
+}
+
+}  // namespace selfc

@@ -17,6 +17,9 @@ int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaS
 template <typename T>
 int launch_nchw_to_dense(const float* x, T* dst, int pitch, int off, int C, int cpad, long long M, long long hw, cudaStream_t st);
 template <typename T>
+int launch_nchw_slice_to_dense(const float* x, int ctot, int c0, T* dst, int pitch, int off, int C, int cpad, long long M,
+                               long long hw, cudaStream_t st);
+template <typename T>
 int launch_dense_to_nchw(const T* src, int pitch, int off, float* y, int C, long long M, long long hw, cudaStream_t st);
 
 // ---- conv_simt.cu: fp32-FMA implicit GEMM (strict-fp32 mode and the small GEMMs of both modes) --------------

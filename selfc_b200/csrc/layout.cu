@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(128) export_hf_kernel(const float* __restrict_
 // the component entry points.
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void nchw_to_dense_kernel(const float* __restrict__ x, T* __restrict__ dst, int pitch, int off, int C, int cpad,
-                                     long long M, long long hw) {
+__global__ void nchw_to_dense_kernel(const float* __restrict__ x, int ctot, int c0, T* __restrict__ dst, int pitch, int off, int C,
+                                     int cpad, long long M, long long hw) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const long long n = m / hw, pix = m % hw;
   T* d = dst + m * pitch + off;
-  for (int c = 0; c < cpad; ++c) d[c] = from_f<T>(c < C ? __ldg(x + (n * C + c) * hw + pix) : 0.f);
+  for (int c = 0; c < cpad; ++c) d[c] = from_f<T>(c < C ? __ldg(x + (n * ctot + c0 + c) * hw + pix) : 0.f);
 }
 
 template <typename T>
@@ -257,10 +257,20 @@ int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaS
 
 template <typename T>
 int launch_nchw_to_dense(const float* x, T* dst, int pitch, int off, int C, int cpad, long long M, long long hw, cudaStream_t st) {
-  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, dst, pitch, off, C, cpad, M, hw);
+  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, C, 0, dst, pitch, off, C, cpad, M, hw);
   SELFC_LAUNCH_CHECK("nchw_to_dense_kernel");
   return 0;
 }
+template <typename T>
+int launch_nchw_slice_to_dense(const float* x, int ctot, int c0, T* dst, int pitch, int off, int C, int cpad, long long M,
+                               long long hw, cudaStream_t st) {
+  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, ctot, c0, dst, pitch, off, C, cpad, M, hw);
+  SELFC_LAUNCH_CHECK("nchw_to_dense_kernel");
+  return 0;
+}
+template int launch_nchw_slice_to_dense<float>(const float*, int, int, float*, int, int, int, int, long long, long long, cudaStream_t);
+template int launch_nchw_slice_to_dense<__nv_bfloat16>(const float*, int, int, __nv_bfloat16*, int, int, int, int, long long, long long,
+                                                       cudaStream_t);
 template int launch_nchw_to_dense<float>(const float*, float*, int, int, int, int, long long, long long, cudaStream_t);
 template int launch_nchw_to_dense<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, int, int, long long, long long, cudaStream_t);
 

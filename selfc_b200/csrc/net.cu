@@ -154,8 +154,9 @@ struct Dims {
 
 // ---- dense block: conv1..4 in place, then conv5 with the given epilogue ---------------------------------------
 template <typename T>
-static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pitch, const Dims& d, cudaStream_t st) {
-  for (int k = 0; k < 4; ++k) {
+static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pitch, const Dims& d, cudaStream_t st, int k_first = 0,
+                           int k_last = 3) {
+  for (int k = k_first; k <= k_last; ++k) {
     const int cin = W.xpad + kGrowth * k;
     const double flops = 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;   // algorithmic (unpadded) FLOPs
     if (ctx->mode == SELFC_MODE_BF16 && W.tc[k].img != nullptr) {
@@ -350,6 +351,18 @@ static int d2dt_impl(selfc_ctx* ctx, const DenseW& W, const float* x, float* y, 
   a.epi = EPI_STORE; a.outF = tmp; a.outF_pitch = 64;
   SELFC_TRY(launch_conv_simt<T>(a, st));
   return launch_dense_to_nchw<float>(tmp, 64, 0, y, W.cout, d.M(), d.hw(), st);
+}
+
+template <typename T>
+static int conv3x3_impl(selfc_ctx* ctx, const DenseW& W, int k, const float* x, float* y, const Dims& d, char* wsp, const Workspace& ws,
+                        cudaStream_t st) {
+  T* buf = reinterpret_cast<T*>(wsp + ws.stpbuf);
+  const int pitch = W.xpad + 4 * kGrowth;
+  const int cref = W.cin + kGrowth * k;
+  SELFC_TRY(launch_nchw_slice_to_dense<T>(x, cref, 0, buf, pitch, 0, W.cin, W.xpad, d.M(), d.hw(), st));
+  if (k > 0) SELFC_TRY(launch_nchw_slice_to_dense<T>(x, cref, W.cin, buf, pitch, W.xpad, kGrowth * k, kGrowth * k, d.M(), d.hw(), st));
+  SELFC_TRY(run_dense_convs<T>(ctx, W, buf, pitch, d, st, k, k));
+  return launch_dense_to_nchw<T>(buf, pitch, W.xpad + kGrowth * k, y, kGrowth, d.M(), d.hw(), st);
 }
 
 template <typename T>
@@ -592,18 +605,33 @@ int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* 
   return launch_quantize(x, q_u8, q_f32, n, (cudaStream_t)stream);
 }
 
+static const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
+  if (first_param >= 0 && first_param < 240 && first_param % 10 == 0) return &ctx->inv[first_param / 30][(first_param % 30) / 10];
+  if (first_param == P_LOCAL1) return &ctx->stp[0];
+  if (first_param == P_LOCAL2) return &ctx->stp[1];
+  for (int i = 0; i < 4; ++i)
+    if (first_param == P_OTHER + 18 * i) return &ctx->stp[2 + i];
+  return nullptr;
+}
+
+int selfc_conv3x3(selfc_ctx* ctx, int first_param, int k, const float* x, float* y, int B, int T, int h, int w, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(x && y && k >= 0 && k < 4, "conv3x3: null pointer or conv index %d outside 0..3", k);
+  const DenseW* W = find_dense(ctx, first_param);
+  SELFC_CHECK_ARG(W != nullptr, "conv3x3: parameter index %d is not the conv1.weight of a dense block", first_param);
+  Dims d{B, T, h, w};
+  if (ctx->mode == SELFC_MODE_BF16) return conv3x3_impl<__nv_bfloat16>(ctx, *W, k, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
+  return conv3x3_impl<float>(ctx, *W, k, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
+}
+
 int selfc_d2dt(selfc_ctx* ctx, int first_param, const float* x, float* y, int B, int T, int h, int w, void* workspace,
                size_t workspace_bytes, void* stream) {
   Workspace ws;
   SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
   SELFC_CHECK_ARG(x && y, "d2dt: null pointer");
-  const DenseW* W = nullptr;
-  if (first_param >= 0 && first_param < 240 && first_param % 10 == 0) W = &ctx->inv[first_param / 30][(first_param % 30) / 10];
-  else if (first_param == P_LOCAL1) W = &ctx->stp[0];
-  else if (first_param == P_LOCAL2) W = &ctx->stp[1];
-  else
-    for (int i = 0; i < 4; ++i)
-      if (first_param == P_OTHER + 18 * i) W = &ctx->stp[2 + i];
+  const DenseW* W = find_dense(ctx, first_param);
   SELFC_CHECK_ARG(W != nullptr, "d2dt: parameter index %d is not the conv1.weight of a dense block", first_param);
   Dims d{B, T, h, w};
   if (ctx->mode == SELFC_MODE_BF16) return d2dt_impl<__nv_bfloat16>(ctx, *W, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);

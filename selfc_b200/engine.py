@@ -212,6 +212,18 @@ class Engine:
                                           _stream(self.device)), "d2dt")
         return y
 
+    def conv3x3(self, prefix: str, k: int, x: torch.Tensor, T: int) -> torch.Tensor:
+        """conv{k+1} of the dense block `prefix` on its concatenated input x [B*T,Cin+32k,h,w] -> [B*T,32,h,w]."""
+        first = PARAM_INDEX[prefix + ".conv1.weight"]
+        x = self._check_in(x, "x")
+        B, h, w = self._clip_dims(x, T)
+        ws = self._workspace(B, T, h, w)
+        y = torch.empty((B * T, 32, h, w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_conv3x3(self._ctx, first, k, _ptr(x), _ptr(y), B, T, h, w, _ptr(ws), ws.numel(),
+                                             _stream(self.device)), "conv3x3")
+        return y
+
     def global_agg(self, prefix: str, x: torch.Tensor, T: int):
         first = PARAM_INDEX[prefix + ".fc.weight"]
         x = self._check_in(x, "x")

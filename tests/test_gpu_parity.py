@@ -251,3 +251,24 @@ def test_1080p_properties(dev):
     x2 = torch.cat([x, x.flip(0)], 0)
     _, lr2_u8, lr2_q = eng.down(x2, t, want_out51=False)
     assert torch.equal(lr2_u8[:t], lr_u8)
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 conv (bf16 mode)
+def _bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("prefix,cin,k", [("operations.2.F", 48, 0), ("operations.2.F", 48, 3), ("operations.5.G", 3, 0),
+                                          ("operations.5.H", 3, 1), ("stp_net.local_m2", 64, 3), ("stp_net.local_m1", 3, 2)])
+@pytest.mark.parametrize("shape", [(1, 2, 13, 21), (2, 3, 40, 70)])
+def test_conv3x3_tc_vs_oracle(dev, prefix, cin, k, shape):
+    """One (1,3,3) conv through the tcgen05 kernel vs conv3d on bf16-rounded operands (fp32 accumulate)."""
+    import torch.nn.functional as F
+    sd = so.make_state_dict(9)
+    eng = _engine(dev, sd, "bf16")
+    b, t, h, w = shape
+    x = torch.randn(b * t, cin + 32 * k, h, w, generator=torch.Generator().manual_seed(cin + k)) * 0.7
+    wgt, bias = sd[f"{prefix}.conv{k + 1}.weight"], sd[f"{prefix}.conv{k + 1}.bias"]
+    ref = F.leaky_relu(F.conv2d(_bf16r(x), _bf16r(wgt)[:, :, 0], bias, padding=1), 0.2)
+    got = eng.conv3x3(prefix, k, x.to(dev), t).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-2, atol=3e-3)
