@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "conv_tc.h"
+#include "tc_ptx.cuh"
 
 namespace selfc {
 namespace tc {
@@ -41,7 +42,6 @@ constexpr int TMEM_COLS = 2 * ACC_COLS;   // double buffered
 constexpr int MAX_CIN = 160;
 constexpr int WTILE_BYTES = NOUT * 16 * 2;   // one (tap, k-step) B tile: 32 x 16 bf16
 constexpr int THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 struct SmemLayout {
   // offsets from the 1024-aligned dynamic smem base
@@ -52,70 +52,6 @@ struct SmemLayout {
   static int total(int cin) { return W_OFF + 9 * (cin / 16) * WTILE_BYTES + 1024; }
 };
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SPIN_LIMIT) {
-      if (err) atomicExch(err, code);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14), LBO>>4 [16,30) = byte distance between the two 8-element K core matrices,
-// SBO>>4 [32,46) = byte distance between 8-row groups, version=1 [46,48), layout_type=0 [61,64)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         ((uint64_t)1 << 46);
-}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
 // A,B K-major, N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -320,11 +256,8 @@ __global__ void pack_tc_kernel(const float* __restrict__ wref, __nv_bfloat16* __
 }  // namespace tc
 
 // ---- host side ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
+namespace tc {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -338,7 +271,7 @@ static EncodeTiledFn get_encode_fn() {
 
 static int* g_err_flag[64] = {};
 
-static int* err_flag_for_device() {
+int* err_flag_for_device() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
@@ -348,6 +281,17 @@ static int* err_flag_for_device() {
   }
   return g_err_flag[dev];
 }
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+}  // namespace tc
 
 int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st) {
   SELFC_CHECK_ARG(cin_buf % 16 == 0 && cin_buf <= tc::MAX_CIN, "conv3x3_tc: cin %d must be a multiple of 16 and <= %d", cin_buf,
@@ -378,7 +322,7 @@ void free_tc_weights(TcConvW& w) {
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, int out_off, int N, int h, int wd, cudaStream_t st) {
   SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
   SELFC_CHECK_ARG(pitch % 8 == 0 && out_off % 8 == 0 && aligned16(buf), "conv3x3_tc: pitch/out_off/buffer alignment");
-  EncodeTiledFn encode = get_encode_fn();
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return SELFC_E_CUDA;
@@ -407,14 +351,9 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, 
   p.tiles_x = cdiv(wd, tc::VALID_W);
   p.tiles_y = cdiv(h, tc::ROWS);
   p.ntiles = p.tiles_x * p.tiles_y * N;
-  p.err = err_flag_for_device();
+  p.err = tc::err_flag_for_device();
   if (p.ntiles == 0) return 0;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = tc::num_sms();
   const int smem = tc::SmemLayout::total(cin);
   static int smem_set = 0;
   if (smem_set < smem) {

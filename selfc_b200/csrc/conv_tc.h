@@ -20,4 +20,41 @@ void free_tc_weights(TcConvW& w);
 // conv_k of a dense block, in place: reads channels [0,cin) of buf, writes lrelu(conv+bias) to [out_off,out_off+32)
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, int out_off, int N, int h, int wd, cudaStream_t st);
 
+// ---- temporal_tc.cu: (3,1,1) conv5 + coupling epilogues, GlobalAgg apply ---------------------------------------
+struct TcTempW {
+  void* img = nullptr;      // device, bf16 B-operand image [tap][kstep][...]
+  float* bias = nullptr;    // device, [64]
+  size_t img_bytes = 0;
+  int cin_buf = 0, npad = 0, taps = 0, cout = 0;
+};
+
+struct TcTempArgs {
+  const __nv_bfloat16* in = nullptr;
+  int in_pitch = 0, B = 0, T = 0, hw = 0;
+  int epi = 0, rev = 0, act = 0;
+  __nv_bfloat16* outT = nullptr;
+  int outT_pitch = 0, outT_off = 0;
+  float* outF = nullptr;
+  int outF_pitch = 0;
+  float* z = nullptr;
+  float* sbuf = nullptr;
+  __nv_bfloat16* copyA = nullptr;
+  int copyA_pitch = 0;
+  __nv_bfloat16* copyB = nullptr;
+  int copyB_pitch = 0;
+  int copy_pad = 0;
+  const float* wmat = nullptr;
+  const float* wsum = nullptr;
+  const __nv_bfloat16* resid = nullptr;
+  int resid_pitch = 0;
+  __nv_bfloat16* outAct = nullptr;   // EPI_GA: optional LeakyReLU'd copy (input of the GMM head)
+  int outAct_pitch = 0;
+};
+
+int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int cout, int cin_ref, int taps, int cin_buf, int xreal,
+                          int xpad, cudaStream_t st);
+void free_temporal_weights(TcTempW& w);
+bool temporal_tc_supported(const TcTempW& w, int T);
+int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st);
+
 }  // namespace selfc

@@ -6,6 +6,7 @@
 // sequence over pixel-major buffers; nothing here is a translation of reference code.
 #include <mutex>
 #include <new>
+#include <type_traits>
 #include <string.h>
 #include <vector>
 
@@ -42,10 +43,12 @@ struct DenseW {            // one D2DTInput in kernel layout
   float* b[5] = {};
   int np[5] = {};
   TcConvW tc[5];           // tcgen05 bf16 images (BF16 mode)
+  TcTempW t5;              // conv5 image (BF16 mode)
 };
 struct GaW {
   float *fcw = nullptr, *fcb = nullptr, *p2w = nullptr, *p2b = nullptr, *p3w = nullptr, *p3b = nullptr;
   float *p1w = nullptr, *p1b = nullptr;   // packed [64][64] (k-major rows), bias [64]
+  TcTempW tp;                             // proj1 image (BF16 mode)
 };
 struct ProfRec {
   cudaEvent_t a = nullptr, b = nullptr;
@@ -187,6 +190,25 @@ static ConvArgs<T> conv5_args(const DenseW& W, const T* buf, int pitch, const Di
 
 static double conv5_flops(const DenseW& W, const Dims& d) { return 2.0 * (double)d.M() * 3.0 * (W.cin + 4 * kGrowth) * W.cout; }
 
+// conv5 / GlobalAgg-apply dispatch: tcgen05 kernel in BF16 mode when T accumulators fit TMEM, fp32-FMA kernel otherwise
+template <typename T>
+static int launch_temporal(const selfc_ctx* ctx, const TcTempW& tw, const ConvArgs<T>& a, const Dims& d, cudaStream_t st) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (ctx->mode == SELFC_MODE_BF16 && temporal_tc_supported(tw, d.T)) {
+      TcTempArgs t;
+      t.in = a.in; t.in_pitch = a.in_pitch; t.B = d.B; t.T = d.T; t.hw = (int)d.hw();
+      t.epi = a.epi; t.rev = a.rev; t.act = a.act;
+      t.outT = a.outT; t.outT_pitch = a.outT_pitch; t.outT_off = a.outT_off;
+      t.outF = a.outF; t.outF_pitch = a.outF_pitch;
+      t.z = a.z; t.sbuf = a.sbuf;
+      t.copyA = a.copyA; t.copyA_pitch = a.copyA_pitch; t.copyB = a.copyB; t.copyB_pitch = a.copyB_pitch; t.copy_pad = a.copy_pad;
+      t.wmat = a.wmat; t.wsum = a.wsum; t.resid = a.resid; t.resid_pitch = a.resid_pitch;
+      return launch_temporal_tc(tw, t, st);
+    }
+  }
+  return launch_conv_simt<T>(a, st);
+}
+
 // InvBlockExp (SelfC_GMM_arch_inv.py:21-33) on the latent state z, forward or reverse
 template <typename T>
 static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
@@ -203,19 +225,19 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
     ConvArgs<T> a = conv5_args<T>(F, fbuf, ws.fpitch, d);
     a.epi = EPI_COUPLE_Y1; a.rev = rev ? 1 : 0; a.z = z;
     a.copyA = gbuf; a.copyA_pitch = ws.gpitch; a.copyB = hbuf; a.copyB_pitch = ws.gpitch; a.copy_pad = ctx->xpad3;
-    PROF(ctx, st, 1, conv5_flops(F, d), launch_conv_simt<T>(a, st));
+    PROF(ctx, st, 1, conv5_flops(F, d), launch_temporal<T>(ctx, F.t5, a, d, st));
     return 0;
   };
   auto do_HG = [&]() -> int {
     SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st));
     ConvArgs<T> a = conv5_args<T>(H, hbuf, ws.gpitch, d);
     a.epi = EPI_COUPLE_S; a.sbuf = sbuf;
-    PROF(ctx, st, 1, conv5_flops(H, d), launch_conv_simt<T>(a, st));
+    PROF(ctx, st, 1, conv5_flops(H, d), launch_temporal<T>(ctx, H.t5, a, d, st));
     SELFC_TRY(run_dense_convs<T>(ctx, G, gbuf, ws.gpitch, d, st));
     ConvArgs<T> g = conv5_args<T>(G, gbuf, ws.gpitch, d);
     g.epi = EPI_COUPLE_Y2; g.rev = rev ? 1 : 0; g.z = z; g.sbuf = sbuf;
     g.copyA = fbuf; g.copyA_pitch = ws.fpitch;
-    PROF(ctx, st, 1, conv5_flops(G, d), launch_conv_simt<T>(g, st));
+    PROF(ctx, st, 1, conv5_flops(G, d), launch_temporal<T>(ctx, G.t5, g, d, st));
     return 0;
   };
   if (!rev) {
@@ -250,7 +272,7 @@ static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* 
   a.epi = EPI_GA; a.resid = feat; a.resid_pitch = kStpC;
   a.outT = outT; a.outT_pitch = outT_pitch; a.outT_off = 0;
   a.outF = outF; a.outF_pitch = outF_pitch; a.outF_off = 0;
-  PROF(ctx, st, 2, 2.0 * px_bytes, launch_conv_simt<T>(a, st));
+  PROF(ctx, st, 2, 2.0 * px_bytes, launch_temporal<T>(ctx, g.tp, a, d, st));
   return 0;
 }
 
@@ -290,7 +312,7 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
     SELFC_TRY(run_dense_convs<T>(ctx, W, stpbuf, pitch, d, st));
     ConvArgs<T> a = conv5_args<T>(W, stpbuf, pitch, d);
     a.epi = EPI_STORE; a.act = 0; a.outT = feat; a.outT_pitch = kStpC; a.outT_off = 0;
-    PROF(ctx, st, 1, conv5_flops(W, d), launch_conv_simt<T>(a, st));
+    PROF(ctx, st, 1, conv5_flops(W, d), launch_temporal<T>(ctx, W.t5, a, d, st));
     SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, nullptr, 0, nullptr, wsp, ws, d, st));
   }
   // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
@@ -349,7 +371,7 @@ static int d2dt_impl(selfc_ctx* ctx, const DenseW& W, const float* x, float* y, 
   SELFC_TRY(run_dense_convs<T>(ctx, W, buf, pitch, d, st));
   ConvArgs<T> a = conv5_args<T>(W, buf, pitch, d);
   a.epi = EPI_STORE; a.outF = tmp; a.outF_pitch = 64;
-  SELFC_TRY(launch_conv_simt<T>(a, st));
+  SELFC_TRY(launch_temporal<T>(ctx, W.t5, a, d, st));
   return launch_dense_to_nchw<float>(tmp, 64, 0, y, W.cout, d.M(), d.hw(), st);
 }
 
@@ -412,9 +434,15 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   for (int b = 0; b < 8; ++b)
     for (int j = 0; j < 3; ++j)
+    {
       for (int k = 0; k < 5; ++k) free_tc_weights(ctx->inv[b][j].tc[k]);
-  for (int i = 0; i < 6; ++i)
+      free_temporal_weights(ctx->inv[b][j].t5);
+    }
+  for (int i = 0; i < 6; ++i) {
     for (int k = 0; k < 5; ++k) free_tc_weights(ctx->stp[i].tc[k]);
+    free_temporal_weights(ctx->stp[i].t5);
+    free_temporal_weights(ctx->ga[i].tp);
+  }
   delete ctx;
   return 0;
 }
@@ -509,6 +537,8 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
                                       d.cin, d.xpad, d.np[k], st));
       if (ctx->mode == SELFC_MODE_BF16 && k < 4)
         SELFC_TRY(pack_tc_weights(W->tc[k], p[d.first + 2 * k], p[d.first + 2 * k + 1], cin_ref, cin_buf, d.cin, d.xpad, st));
+      if (ctx->mode == SELFC_MODE_BF16 && k == 4)
+        SELFC_TRY(pack_temporal_weights(W->t5, p[d.first + 8], p[d.first + 9], d.cout, cin_ref, 3, cin_buf, d.cin, d.xpad, st));
     }
   }
   // GlobalAgg
@@ -521,6 +551,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     SELFC_CUDA(cudaMemcpyAsync(G.fcw, p[f + 0], 1024 * 4, cudaMemcpyDeviceToDevice, st));
     SELFC_CUDA(cudaMemcpyAsync(G.fcb, p[f + 1], 4, cudaMemcpyDeviceToDevice, st));
     SELFC_TRY(launch_pack_conv_simt(p[f + 2], p[f + 3], G.p1w, G.p1b, 64, 64, 1, 64, 64, 64, 64, st));
+    if (ctx->mode == SELFC_MODE_BF16) SELFC_TRY(pack_temporal_weights(G.tp, p[f + 2], p[f + 3], 64, 64, 1, 64, 64, 64, st));
     SELFC_CUDA(cudaMemcpyAsync(G.p2w, p[f + 4], 64 * 64 * 4, cudaMemcpyDeviceToDevice, st));
     SELFC_CUDA(cudaMemcpyAsync(G.p2b, p[f + 5], 64 * 4, cudaMemcpyDeviceToDevice, st));
     SELFC_CUDA(cudaMemcpyAsync(G.p3w, p[f + 6], 64 * 64 * 4, cudaMemcpyDeviceToDevice, st));

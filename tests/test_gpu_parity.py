@@ -272,3 +272,31 @@ def test_conv3x3_tc_vs_oracle(dev, prefix, cin, k, shape):
     ref = F.leaky_relu(F.conv2d(_bf16r(x), _bf16r(wgt)[:, :, 0], bias, padding=1), 0.2)
     got = eng.conv3x3(prefix, k, x.to(dev), t).cpu()
     torch.testing.assert_close(got, ref, rtol=1e-2, atol=3e-3)
+
+
+@pytest.mark.parametrize("prefix,cin", [("operations.1.F", 48), ("operations.3.G", 3), ("stp_net.local_m2", 64)])
+@pytest.mark.parametrize("t,h,w", [(1, 9, 14), (3, 13, 21), (7, 24, 40), (9, 8, 8)])
+def test_dense_block_bf16_vs_oracle(dev, prefix, cin, t, h, w):
+    """Whole D2DTInput in bf16 mode (tcgen05 conv1-4 + tcgen05 temporal conv5; T=9 exceeds TMEM and takes the FMA kernel)."""
+    sd = so.make_state_dict(5)
+    eng = _engine(dev, sd, "bf16")
+    b = 2
+    x = _bf16r(torch.randn(b * t, cin, h, w, generator=torch.Generator().manual_seed(7)) * 0.5)
+    with torch.no_grad():
+        ref = so.d2dt(sd, prefix, x, t)
+    got = eng.d2dt(prefix, x.to(dev), t).cpu()
+    torch.testing.assert_close(got, ref, rtol=2e-2, atol=6e-3)
+
+
+@pytest.mark.parametrize("h,w,t", [(10, 18, 2), (45, 67, 7)])
+def test_global_agg_bf16_vs_oracle(dev, h, w, t):
+    sd = so.make_state_dict(6, gain=2.0)
+    eng = _engine(dev, sd, "bf16")
+    b = 2
+    x = _bf16r(torch.randn(b * t, 64, h, w, generator=torch.Generator().manual_seed(h)))
+    with torch.no_grad():
+        ref = so.global_agg(sd, "stp_net.global_m2", x, t)
+        wref = so.global_agg_weights(sd, "stp_net.global_m2", x, t)
+    got, wmat = eng.global_agg("stp_net.global_m2", x.to(dev), t)
+    torch.testing.assert_close(wmat.cpu(), wref, rtol=0, atol=1e-5)
+    torch.testing.assert_close(got.cpu(), ref, rtol=2e-2, atol=2e-2)
