@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
           const float4 ov = make_float4(v[0], v[1], v[2], v[3]);
           if (a.outT) store4(a.outT + m * a.outT_pitch + a.outT_off + n0, ov);
           if (a.outF) store4(a.outF + m * a.outF_pitch + a.outF_off + n0, ov);
+          if (a.outAct)
+            store4(a.outAct + m * a.outAct_pitch + n0, make_float4(lrelu02(v[0]), lrelu02(v[1]), lrelu02(v[2]), lrelu02(v[3])));
         }
       } break;
     }

@@ -35,7 +35,8 @@ struct TcTempArgs {
   __nv_bfloat16* outT = nullptr;
   int outT_pitch = 0, outT_off = 0;
   float* outF = nullptr;
-  int outF_pitch = 0;
+  int outF_pitch = 0, outF_off = 0;
+  long long m_limit = 0;             // > 0: rows >= m_limit do not exist (pointwise mode over pseudo-frames)
   float* z = nullptr;
   float* sbuf = nullptr;
   __nv_bfloat16* copyA = nullptr;

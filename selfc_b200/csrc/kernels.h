@@ -55,6 +55,8 @@ struct ConvArgs {
   int copy_pad = 0;         // Y1: zero-fill channels [3, copy_pad)
   const T* resid = nullptr; // EPI_GA residual
   int resid_pitch = 0;
+  T* outAct = nullptr;      // EPI_GA: optional LeakyReLU'd copy of the result (input of the GMM head)
+  int outAct_pitch = 0;
 };
 
 template <typename T>

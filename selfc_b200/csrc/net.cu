@@ -59,6 +59,7 @@ struct HeadW {
   float* w[3] = {};
   float* b[3] = {};
   int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 720}, np[3] = {128, 256, 736};
+  TcTempW t[5];            // BF16 mode: 64->128, 128->256, 256->240 x3 as tcgen05 pointwise GEMMs
 };
 
 }  // namespace selfc
@@ -111,7 +112,7 @@ static void prof_end(const selfc_ctx* cctx, cudaStream_t st) {
 // ---- workspace layout -------------------------------------------------------------------------------------
 struct Workspace {
   size_t total = 0;
-  size_t z, sbuf, fbuf, gbuf, hbuf, stpbuf, feat, h1, h2, params, wmap, partial, wmat, wsum;
+  size_t z, sbuf, fbuf, gbuf, hbuf, stpbuf, feat, fact, h1, h2, params, wmap, partial, wmat, wsum;
   int nsplit = 1;
   int fpitch = 176, gpitch = 0, spitch = 192;
 };
@@ -135,6 +136,7 @@ static Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w
   ws.hbuf = take(M * ws.gpitch * es);
   ws.stpbuf = take(M * ws.spitch * es);
   ws.feat = take(M * kStpC * es);
+  ws.fact = take(M * kStpC * es);
   ws.h1 = take(M * 128 * es);
   ws.h2 = take(M * 256 * es);
   ws.params = take(M * 720 * 4);
@@ -203,6 +205,7 @@ static int launch_temporal(const selfc_ctx* ctx, const TcTempW& tw, const ConvAr
       t.z = a.z; t.sbuf = a.sbuf;
       t.copyA = a.copyA; t.copyA_pitch = a.copyA_pitch; t.copyB = a.copyB; t.copyB_pitch = a.copyB_pitch; t.copy_pad = a.copy_pad;
       t.wmat = a.wmat; t.wsum = a.wsum; t.resid = a.resid; t.resid_pitch = a.resid_pitch;
+      t.outAct = a.outAct; t.outAct_pitch = a.outAct_pitch;
       return launch_temporal_tc(tw, t, st);
     }
   }
@@ -253,7 +256,7 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
 // GlobalAgg (SelfC_GMM_arch_inv.py:265-285): x = feat [M][64]; result -> outT (pitch/off) and/or outF
 template <typename T>
 static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* outT, int outT_pitch, float* outF, int outF_pitch,
-                          float* wmat_copy, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
+                          float* wmat_copy, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st, T* outAct = nullptr) {
   float* wmap = reinterpret_cast<float*>(wsp + ws.wmap);
   float* partial = reinterpret_cast<float*>(wsp + ws.partial);
   float* wmat = reinterpret_cast<float*>(wsp + ws.wmat);
@@ -272,6 +275,7 @@ static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* 
   a.epi = EPI_GA; a.resid = feat; a.resid_pitch = kStpC;
   a.outT = outT; a.outT_pitch = outT_pitch; a.outT_off = 0;
   a.outF = outF; a.outF_pitch = outF_pitch; a.outF_off = 0;
+  a.outAct = outAct; a.outAct_pitch = kStpC;
   PROF(ctx, st, 2, 2.0 * px_bytes, launch_temporal<T>(ctx, g.tp, a, d, st));
   return 0;
 }
@@ -295,6 +299,7 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   T* hbuf = reinterpret_cast<T*>(wsp + ws.hbuf);
   T* stpbuf = reinterpret_cast<T*>(wsp + ws.stpbuf);
   T* feat = reinterpret_cast<T*>(wsp + ws.feat);
+  T* fact = reinterpret_cast<T*>(wsp + ws.fact);
   T* h1 = reinterpret_cast<T*>(wsp + ws.h1);
   T* h2 = reinterpret_cast<T*>(wsp + ws.h2);
   float* params = reinterpret_cast<float*>(wsp + ws.params);
@@ -313,10 +318,30 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
     ConvArgs<T> a = conv5_args<T>(W, stpbuf, pitch, d);
     a.epi = EPI_STORE; a.act = 0; a.outT = feat; a.outT_pitch = kStpC; a.outT_off = 0;
     PROF(ctx, st, 1, conv5_flops(W, d), launch_temporal<T>(ctx, W.t5, a, d, st));
-    SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, nullptr, 0, nullptr, wsp, ws, d, st));
+    SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, nullptr, 0, nullptr, wsp, ws, d, st,
+                                i == 5 ? fact : nullptr));
   }
   // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
-  {
+  bool head_done = false;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (ctx->mode == SELFC_MODE_BF16 && ctx->head.t[0].img != nullptr) {
+      // pointwise GEMMs over all M pixels, viewed as 2 pseudo-frames of ceil(M/2) rows (two accumulators in flight)
+      auto pointwise = [&](const TcTempW& w, const __nv_bfloat16* in, int in_pitch, __nv_bfloat16* outT, int outT_pitch, float* outF,
+                           int outF_pitch, int outF_off, int act) -> int {
+        TcTempArgs t;
+        t.in = in; t.in_pitch = in_pitch; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
+        t.epi = EPI_STORE; t.act = act;
+        t.outT = outT; t.outT_pitch = outT_pitch; t.outF = outF; t.outF_pitch = outF_pitch; t.outF_off = outF_off;
+        return launch_temporal_tc(w, t, st);
+      };
+      PROF(ctx, st, 3, 2.0 * M * 64 * 128, pointwise(ctx->head.t[0], fact, kStpC, h1, 128, nullptr, 0, 0, 1));
+      PROF(ctx, st, 3, 2.0 * M * 128 * 256, pointwise(ctx->head.t[1], h1, 128, h2, 256, nullptr, 0, 0, 1));
+      for (int j = 0; j < 3; ++j)
+        PROF(ctx, st, 3, 2.0 * M * 256 * 240, pointwise(ctx->head.t[2 + j], h2, 256, nullptr, 0, params, 720, 240 * j, 0));
+      head_done = true;
+    }
+  }
+  if (!head_done) {
     ConvArgs<T> a;
     a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
     a.taps = 1; a.tap_mode = TAP_POINT; a.epi = EPI_STORE;
@@ -443,6 +468,7 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
     free_temporal_weights(ctx->stp[i].t5);
     free_temporal_weights(ctx->ga[i].tp);
   }
+  for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.t[j]);
   delete ctx;
   return 0;
 }
@@ -564,6 +590,13 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     const int cin = ctx->head.cin[j], cout = ctx->head.cout[j];
     SELFC_TRY(launch_pack_conv_simt(p[P_TAIL + 2 * j], p[P_TAIL + 2 * j + 1], ctx->head.w[j], ctx->head.b[j], cout, cin, 1, cin, cin,
                                     cin, ctx->head.np[j], st));
+  }
+  if (ctx->mode == SELFC_MODE_BF16) {
+    SELFC_TRY(pack_temporal_weights(ctx->head.t[0], p[P_TAIL + 0], p[P_TAIL + 1], 128, 64, 1, 64, 64, 64, st));
+    SELFC_TRY(pack_temporal_weights(ctx->head.t[1], p[P_TAIL + 2], p[P_TAIL + 3], 256, 128, 1, 128, 128, 128, st));
+    for (int j = 0; j < 3; ++j)
+      SELFC_TRY(pack_temporal_weights(ctx->head.t[2 + j], p[P_TAIL + 4] + (size_t)240 * j * 256, p[P_TAIL + 5] + 240 * j, 240, 256, 1,
+                                      256, 256, 256, st));
   }
   ctx->loaded = true;
   return 0;

@@ -32,17 +32,19 @@ constexpr int NST = 4;
 constexpr int TMAX = 8;
 constexpr int THREADS = 192;
 constexpr int BAR_BYTES = 512;
+constexpr int BIAS_BYTES = 1024;   // up to 256 fp32
 
 struct Params {
   const void* wimg;
   const float* bias;
   int T, B, hw, nchunk, npad, taps, cout;
   int tiles_p, ntiles, tmem_cols;
+  long long m_limit;   // rows (pixels) that really exist in the buffer
   int epi, rev, act;
   __nv_bfloat16* outT;
   int outT_pitch, outT_off;
   float* outF;
-  int outF_pitch;
+  int outF_pitch, outF_off;
   float* z;
   float* sbuf;
   __nv_bfloat16* copyA;
@@ -78,6 +80,7 @@ __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float* v) {
     v[2 * i + 1] = __high2float(b);
   }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   const uint32_t a_base = base;
   const uint32_t bar_base = base + NST * stage_bytes;
   const uint32_t bias_off = NST * stage_bytes + BAR_BYTES;
-  const uint32_t w_base = base + bias_off + 256;
+  const uint32_t w_base = base + bias_off + BIAS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
   const uint32_t w_bar = bar_base + 8u * (2 * NST);
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  if (threadIdx.x >= 64 && threadIdx.x - 64 < p.npad) sbias[threadIdx.x - 64] = __ldg(p.bias + threadIdx.x - 64);
+  for (int i = threadIdx.x; i < p.npad; i += THREADS) sbias[i] = __ldg(p.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -196,6 +199,22 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       const int b = tile / p.tiles_p;
       const int pix = (tile - b * p.tiles_p) * MT + row;
       const bool valid = pix < p.hw;
+      // the epilogue's operands (latent state, log-scale, residual) are pulled into L2 while the MMAs of this tile run
+      if (pix < p.hw) {
+        for (int t = 0; t < T; ++t) {
+          const size_t m = ((size_t)b * T + t) * p.hw + pix;
+          if (p.epi == EPI_COUPLE_Y1) {
+            prefetch_l2(p.z + m * kZPitch);
+          } else if (p.epi == EPI_COUPLE_Y2) {
+            prefetch_l2(p.z + m * kZPitch);
+            prefetch_l2(p.z + m * kZPitch + 32);
+            prefetch_l2(p.sbuf + m * kHF);
+            prefetch_l2(p.sbuf + m * kHF + 32);
+          } else if (p.epi == EPI_GA) {
+            prefetch_l2(p.resid + m * p.resid_pitch);
+          }
+        }
+      }
       mbar_wait(tfull_bar, (uint32_t)it & 1u, p.err, 15);
       tc_fence_after();
       if (p.epi == EPI_GA) {
@@ -250,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
           uint32_t r[16];
           tmem_ld16(lane_addr + (uint32_t)(t * npad + n0), r);
           tmem_ld_wait();
-          if (!valid) continue;
+          if (!valid || (long long)m >= p.m_limit) continue;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
@@ -271,9 +290,14 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                 }
               }
               if (p.outF) {
-                float* o = p.outF + m * p.outF_pitch + n0;
-                for (int j = 0; j < 16; ++j)
-                  if (n0 + j < p.cout) o[j] = v[j];
+                float* o = p.outF + m * p.outF_pitch + p.outF_off + n0;
+                if (n0 + 16 <= p.cout && ((p.outF_pitch | p.outF_off) & 3) == 0) {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4) store4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                } else {
+                  for (int j = 0; j < 16; ++j)
+                    if (n0 + j < p.cout) o[j] = v[j];
+                }
               }
             } break;
             case EPI_COUPLE_Y1: {
@@ -369,13 +393,13 @@ __global__ void pack_temporal_kernel(const float* __restrict__ wref, const float
 
 int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int cout, int cin_ref, int taps, int cin_buf, int xreal,
                           int xpad, cudaStream_t st) {
-  SELFC_CHECK_ARG(cin_buf % 16 == 0 && cout >= 1 && cout <= 64, "temporal_tc: cin %d / cout %d unsupported", cin_buf, cout);
+  SELFC_CHECK_ARG(cin_buf % 16 == 0 && cout >= 1 && cout <= 256, "temporal_tc: cin %d / cout %d unsupported", cin_buf, cout);
   const int npad = (cout + 15) & ~15;
   const size_t bytes = (size_t)taps * (cin_buf / 16) * npad * 32;
   if (w.img == nullptr || w.img_bytes != bytes) {
     free_temporal_weights(w);
     SELFC_CUDA(cudaMalloc(&w.img, bytes));
-    SELFC_CUDA(cudaMalloc(&w.bias, 64 * sizeof(float)));
+    SELFC_CUDA(cudaMalloc(&w.bias, 256 * sizeof(float)));
     w.img_bytes = bytes;
   }
   w.cin_buf = cin_buf; w.npad = npad; w.taps = taps; w.cout = cout;
@@ -405,6 +429,7 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
     return SELFC_E_CUDA;
   }
   const int BT = a.B * a.T;
+  SELFC_CHECK_ARG(a.epi != EPI_GA || w.npad <= 64, "temporal_tc: GlobalAgg epilogue needs N <= 64");
   CUtensorMap tmap;
   const cuuint64_t gdim[3] = {(cuuint64_t)a.in_pitch, (cuuint64_t)a.hw, (cuuint64_t)BT};
   const cuuint64_t gstr[2] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.hw * a.in_pitch * 2};
@@ -428,14 +453,15 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   p.tmem_cols = pw;
   p.epi = a.epi; p.rev = a.rev; p.act = a.act;
   p.outT = a.outT; p.outT_pitch = a.outT_pitch; p.outT_off = a.outT_off;
-  p.outF = a.outF; p.outF_pitch = a.outF_pitch;
+  p.outF = a.outF; p.outF_pitch = a.outF_pitch; p.outF_off = a.outF_off;
+  p.m_limit = a.m_limit > 0 ? a.m_limit : (long long)BT * a.hw;
   p.z = a.z; p.sbuf = a.sbuf;
   p.copyA = a.copyA; p.copyA_pitch = a.copyA_pitch; p.copyB = a.copyB; p.copyB_pitch = a.copyB_pitch; p.copy_pad = a.copy_pad;
   p.wmat = a.wmat; p.wsum = a.wsum; p.resid = a.resid; p.resid_pitch = a.resid_pitch;
   p.outAct = a.outAct; p.outAct_pitch = a.outAct_pitch;
   p.err = tc::err_flag_for_device();
   if (p.ntiles == 0) return 0;
-  const int smem = tc5::NST * a.T * tc5::FRAME_BYTES + tc5::BAR_BYTES + 256 + (int)w.img_bytes + 1024;
+  const int smem = tc5::NST * a.T * tc5::FRAME_BYTES + tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes + 1024;
   static int smem_set = 0;
   if (smem_set < smem) {
     SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -170,9 +170,10 @@ def test_vid4_shape_clip_vs_oracle(dev):
     assert abs(p_got - p_ref) <= 0.01 and abs(s_got - s_ref) <= 1e-4
 
 
-def test_bf16_mode_vs_oracle(dev):
-    """bf16 mode (tcgen05 convolutions, bf16 activations, fp32 state): HR within 2e-2, LR within +-1 LSB."""
-    b, t, hh, ww = 2, 7, 96, 160
+@pytest.mark.parametrize("b,t,hh,ww", [(2, 7, 96, 160), (1, 1, 20, 28), (1, 3, 36, 44), (1, 9, 16, 16)])
+def test_bf16_mode_vs_oracle(dev, b, t, hh, ww):
+    """bf16 mode (tcgen05 convolutions, bf16 activations, fp32 state): HR within 2e-2, LR within +-1 LSB.
+    Shapes cover an odd pixel count (pointwise pseudo-frame split) and T=9 (temporal FMA fallback)."""
     sd = so.make_state_dict(0)
     eng = _engine(dev, sd, "bf16")
     x = so.make_frames(b, t, hh, ww, 77)
