@@ -13,8 +13,12 @@ namespace selfc {
 constexpr int kHF = 48;         // 3 * 4 * 4 high-frequency channels
 constexpr int kGmmK = 5;
 constexpr int kGrowth = 32;     // D2DTInput gc
-constexpr int kZPitch = 52;     // latent state [M][52] fp32: ch 0..2 = x1 (LR part), 3 = pad, 4..51 = x2 (HF part)
-constexpr int kZHf = 4;
+// Latent state z: PLANAR quads [13][M][4] fp32 -- quad 0 = (x1_0, x1_1, x1_2, 0) the LR part, quad 1+q = x2[4q..4q+3]
+// the HF part.  One thread per pixel then reads / writes 16 bytes per quad with consecutive lanes on consecutive
+// addresses (coalesced), which is what every epilogue and layout kernel does.  The coupling log-scale s is [12][M][4].
+constexpr int kZQuads = 13;
+constexpr int kSQuads = 12;
+__host__ __device__ __forceinline__ size_t quad_off(size_t M, int quad, size_t m) { return ((size_t)quad * M + m) * 4; }
 constexpr int kStpC = 64;
 
 // ---- error plumbing ---------------------------------------------------------------------------------

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
         if (n0 < a.copy_pad || n0 < 4) {
           float y[4] = {0.f, 0.f, 0.f, 0.f};
           if (n0 == 0) {
-            float* zp = a.z + m * kZPitch;
+            float* zp = a.z + quad_off(M, 0, m);
             const float4 x1 = load4(zp);
             y[0] = a.rev ? x1.x - v[0] : x1.x + v[0];
             y[1] = a.rev ? x1.y - v[1] : x1.y + v[1];
@@ -186,14 +186,14 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
           float s[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) s[j] = (1.0f / (1.0f + expf(-v[j]))) * 2.0f - 1.0f;
-          store4(a.sbuf + m * kHF + n0, make_float4(s[0], s[1], s[2], s[3]));
+          store4(a.sbuf + quad_off(M, n0 / 4, m), make_float4(s[0], s[1], s[2], s[3]));
         }
       } break;
       case EPI_COUPLE_Y2: {   // y2 = x2*exp(s) + G(y1)  |  y2 = (x2 - G(x1)) / exp(s)   (:27, :30)
         if (n0 < kHF) {
-          float* zp = a.z + m * kZPitch + kZHf + n0;
+          float* zp = a.z + quad_off(M, 1 + n0 / 4, m);
           const float4 x2 = load4(zp);
-          const float4 s4 = load4(a.sbuf + m * kHF + n0);
+          const float4 s4 = load4(a.sbuf + quad_off(M, n0 / 4, m));
           const float xr[4] = {x2.x, x2.y, x2.z, x2.w};
           const float sr[4] = {s4.x, s4.y, s4.z, s4.w};
           float y[4];

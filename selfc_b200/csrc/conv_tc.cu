@@ -20,6 +20,7 @@
 //   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
 //     warps 2..5 = epilogue (one TMEM lane quarter each).  8-stage mbarrier ring between TMA and MMA.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv_tc.h"
@@ -33,8 +34,10 @@ constexpr int VALID_W = WT - 2;
 constexpr int ROWS = 8;                   // output rows per tile
 constexpr int HT = ROWS + 2;
 constexpr int PLANE_BYTES = HT * WT * 16; // one 8-channel plane of the halo tile
-constexpr int STAGE_BYTES = 2 * PLANE_BYTES;   // 16 channels = one UMMA K step
-constexpr int NSTAGE = 8;
+constexpr int KSTEP_BYTES = 2 * PLANE_BYTES;   // 16 channels = one UMMA K step = two planes
+constexpr int MAX_KPS = 4;                // K steps per pipeline stage (fewer, larger stages amortise the per-stage
+                                          // barrier wait / fence / commit of the single issuing warp: measured ~400-570 cycles)
+constexpr int NSTAGE = 8;                 // barrier slots (upper bound on stages)
 constexpr int MBLK = 2;                   // 2 x 128 flattened positions per tile
 constexpr int NOUT = 32;
 constexpr int ACC_COLS = MBLK * NOUT;     // TMEM columns per accumulator buffer
@@ -44,12 +47,11 @@ constexpr int WTILE_BYTES = NOUT * 16 * 2;   // one (tap, k-step) B tile: 32 x 1
 constexpr int THREADS = 192;
 
 struct SmemLayout {
-  // offsets from the 1024-aligned dynamic smem base
-  static constexpr int A_OFF = 0;                                   // NSTAGE stages
-  static constexpr int A_PAD = 1024;                                // garbage rows of the last M-block read 32 B past a plane
-  static constexpr int BAR_OFF = A_OFF + NSTAGE * STAGE_BYTES + A_PAD;
-  static constexpr int W_OFF = BAR_OFF + 256;
-  static int total(int cin) { return W_OFF + 9 * (cin / 16) * WTILE_BYTES + 1024; }
+  // offsets from the 1024-aligned dynamic smem base: [A stages][pad][barriers][weights]
+  static constexpr int A_PAD = 1024;      // garbage rows of the last M-block read a little past the tile
+  static constexpr int BAR_BYTES = 256;
+  __host__ __device__ static int bar_off(int nst, int stage_bytes) { return nst * stage_bytes + A_PAD; }
+  static int total(int cin, int nst, int stage_bytes) { return bar_off(nst, stage_bytes) + BAR_BYTES + 9 * (cin / 16) * WTILE_BYTES + 1024; }
 };
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
@@ -60,7 +62,8 @@ struct Params {
   const void* wimg;
   const float* bias;
   __nv_bfloat16* buf;
-  int pitch, out_off, N, h, w, nchunk;   // nchunk = cin / 16
+  int pitch, out_off, N, h, w, nchunk;   // nchunk = cin / 16 (K steps)
+  int nst, kps;                          // pipeline stages; K steps (16 channels) per stage
   int tiles_x, tiles_y, ntiles;
   int* err;
 };
@@ -68,10 +71,13 @@ struct Params {
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to 1024 by hand
+  const int STAGE = p.kps * KSTEP_BYTES;
+  const int NST = p.nst;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = base + SmemLayout::A_OFF;
-  const uint32_t bar_base = base + SmemLayout::BAR_OFF;
-  const uint32_t w_base = base + SmemLayout::W_OFF;
+  const uint32_t a_base = base;
+  const int bar_off = SmemLayout::bar_off(NST, STAGE);
+  const uint32_t bar_base = base + bar_off;
+  const uint32_t w_base = bar_base + SmemLayout::BAR_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
   const uint32_t w_bar = bar_base + 8u * (2 * NSTAGE);
@@ -79,9 +85,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc_kernel(const __grid_con
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + 3 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 5);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + SmemLayout::BAR_OFF + 8 * (2 * NSTAGE + 5));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bar_off + 8 * (2 * NSTAGE + 5));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -106,6 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
 
   const int nchunk = p.nchunk;
   if (warp == 0) {
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc_kernel(const __grid_con
       for (int tap = 0; tap < 9; ++tap)
         bulk_g2s(w_base + tap * nchunk * WTILE_BYTES, (const uint8_t*)p.wimg + (size_t)tap * nchunk * WTILE_BYTES,
                  (uint32_t)nchunk * WTILE_BYTES, w_bar);
+      pdl_wait();      // weights are static; activations come from the previous kernel in the stream
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -123,19 +131,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc_kernel(const __grid_con
         const int ty = (tile / p.tiles_x) % p.tiles_y;
         const int n = tile / (p.tiles_x * p.tiles_y);
         const int x0 = tx * VALID_W - 1, y0 = ty * ROWS - 1;
-        for (int c = 0; c < nchunk; ++c) {
+        for (int c0 = 0; c0 < nchunk; c0 += p.kps) {
+          const int nk = nchunk - c0 < p.kps ? nchunk - c0 : p.kps;
           mbar_wait(empty_bar(s), ph ^ 1u, p.err, 1);
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          const uint32_t dst = a_base + s * STAGE_BYTES;
-          tma_load_4d(dst, &tmap, full_bar(s), c * 16, x0, y0, n);
-          tma_load_4d(dst + PLANE_BYTES, &tmap, full_bar(s), c * 16 + 8, x0, y0, n);
-          if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+          mbar_expect_tx(full_bar(s), (uint32_t)nk * KSTEP_BYTES);
+          const uint32_t dst = a_base + s * STAGE;
+          for (int pl = 0; pl < 2 * nk; ++pl) tma_load_4d(dst + pl * PLANE_BYTES, &tmap, full_bar(s), c0 * 16 + pl * 8, x0, y0, n);
+          if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
+    {
       mbar_wait(w_bar, 0, p.err, 2);
       int s = 0;
       uint32_t ph = 0;
@@ -145,30 +153,40 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc_kernel(const __grid_con
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u, p.err, 3);
         tc_fence_after();
-        for (int c = 0; c < nchunk; ++c) {
+        const uint32_t hi = desc_hi(128, 0);
+        const uint32_t b_tap = (uint32_t)nchunk * (WTILE_BYTES >> 4);
+        for (int c0 = 0; c0 < nchunk; c0 += p.kps) {
+          const int nk = nchunk - c0 < p.kps ? nchunk - c0 : p.kps;
           mbar_wait(full_bar(s), ph, p.err, 4);
           tc_fence_after();
-          const uint32_t a_stage = a_base + s * STAGE_BYTES;
+          const uint32_t a_stage = a_base + s * STAGE;
+          for (int ks = 0; ks < nk; ++ks) {
+            // descriptor low words advance by constants (16-byte units): one halo pixel = 1, one weight tile = 64
+            const uint32_t a_lo = desc_lo(a_stage + (uint32_t)ks * KSTEP_BYTES, PLANE_BYTES);
+            const uint32_t b_lo = desc_lo(w_base + (uint32_t)(c0 + ks) * WTILE_BYTES, 512);
+            const bool first = (c0 + ks) == 0;
 #pragma unroll
-          for (int mb = 0; mb < MBLK; ++mb) {
-            const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS + mb * NOUT);
+            for (int mb = 0; mb < MBLK; ++mb) {
+              const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS + mb * NOUT);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int ky = tap / 3, kx = tap % 3;
-              const uint64_t ad = umma_desc(a_stage + (uint32_t)(mb * 128 + ky * WT + kx) * 16u, PLANE_BYTES, 128);
-              const uint64_t bd = umma_desc(w_base + (uint32_t)(tap * nchunk + c) * WTILE_BYTES, 512, 128);
-              umma_bf16(d, ad, bd, kIdesc, (c > 0 || tap > 0) ? 1u : 0u);
+              for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap % 3;
+                const uint64_t ad = desc_join(a_lo + (uint32_t)(mb * 128 + ky * WT + kx), hi);
+                const uint64_t bd = desc_join(b_lo + (uint32_t)tap * b_tap, hi);
+                umma_bf16_elect(d, ad, bd, kIdesc, (!first || tap > 0) ? 1u : 0u);
+              }
             }
           }
-          umma_commit(empty_bar(s));      // frees the stage when these MMAs have read it
-          if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+          umma_commit_elect(empty_bar(s));      // frees the stage when these MMAs have read it
+          if (++s == NST) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+        umma_commit_elect(tfull_bar(acc));      // accumulator complete -> epilogue
       }
     }
   } else {
     // ===================== epilogue warps 2..5 =====================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
+    pdl_wait();
     float bias[NOUT];
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) bias[j] = __ldg(p.bias + j);
@@ -282,6 +300,46 @@ int* err_flag_for_device() {
   return g_err_flag[dev];
 }
 
+static long long* g_dbg_dev = nullptr;
+static long long g_dbg_tags[4096];
+static int g_dbg_n = 0;
+bool debug_slots() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SELFC_TC_DBG");
+    on = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
+long long* debug_next_slot(long long tag) {
+  if (!g_dbg_dev) {
+    if (cudaMalloc(&g_dbg_dev, 4096 * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
+    cudaMemset(g_dbg_dev, 0, 4096 * 16 * sizeof(long long));
+  }
+  if (g_dbg_n >= 4096) return nullptr;
+  g_dbg_tags[g_dbg_n] = tag;
+  return g_dbg_dev + 16 * (g_dbg_n++);
+}
+int debug_read(long long* out, int cap) {
+  cudaDeviceSynchronize();
+  int n = g_dbg_n < cap ? g_dbg_n : cap;
+  for (int i = 0; i < n; ++i) {
+    out[17 * i] = g_dbg_tags[i];
+    cudaMemcpy(out + 17 * i + 1, g_dbg_dev + 16 * i, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  }
+  g_dbg_n = 0;
+  return n;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SELFC_NO_PDL");
+    on = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return on == 1;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -330,10 +388,11 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, 
   CUtensorMap tmap;
   const cuuint64_t gdim[4] = {(cuuint64_t)pitch, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N};
   const cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)wd * pitch * 2, (cuuint64_t)h * wd * pitch * 2};
-  const cuuint32_t box[4] = {8, (cuuint32_t)tc::WT, (cuuint32_t)tc::HT, 1};
+  const cuuint32_t box[4] = {8u, (cuuint32_t)tc::WT, (cuuint32_t)tc::HT, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (pitch %d, %dx%dx%d)", (int)r, pitch, N, h, wd);
     return SELFC_E_CUDA;
@@ -354,14 +413,34 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, 
   p.err = tc::err_flag_for_device();
   if (p.ntiles == 0) return 0;
   const int num_sms = tc::num_sms();
-  const int smem = tc::SmemLayout::total(cin);
-  static int smem_set = 0;
-  if (smem_set < smem) {
-    SELFC_CUDA(cudaFuncSetAttribute(tc::conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout::total(tc::MAX_CIN)));
-    smem_set = tc::SmemLayout::total(tc::MAX_CIN);
+  // stage size: as many K steps per stage as leave >= 3 stages next to the resident weights
+  static int kps_env = -1;
+  if (kps_env < 0) {
+    const char* e = getenv("SELFC_TC_KPS");
+    kps_env = e ? atoi(e) : 0;
+  }
+  const int nchunk = cin / 16;
+  int kps = kps_env > 0 ? kps_env : tc::MAX_KPS;
+  if (kps > tc::MAX_KPS) kps = tc::MAX_KPS;
+  if (kps > nchunk) kps = nchunk;
+  int nst = 0;
+  for (;; --kps) {
+    const int stage = kps * tc::KSTEP_BYTES;
+    nst = (227 * 1024 - tc::SmemLayout::total(cin, 0, stage)) / stage;
+    if (nst >= 3 || kps == 1) break;
+  }
+  if (nst > tc::NSTAGE) nst = tc::NSTAGE;
+  SELFC_CHECK_ARG(nst >= 2, "conv3x3_tc: no room for the A pipeline (cin %d)", cin);
+  p.nst = nst;
+  p.kps = kps;
+  const int smem = tc::SmemLayout::total(cin, nst, kps * tc::KSTEP_BYTES);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SELFC_CUDA(cudaFuncSetAttribute(tc::conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
   }
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
-  tc::conv3x3_tc_kernel<<<grid, tc::THREADS, smem, st>>>(tmap, p);
+  SELFC_CUDA(tc::launch_pdl(tc::conv3x3_tc_kernel, grid, tc::THREADS, smem, st, tmap, p));
   SELFC_LAUNCH_CHECK("conv3x3_tc_kernel");
   return 0;
 }

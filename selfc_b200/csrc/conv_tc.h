@@ -35,7 +35,7 @@ struct TcTempArgs {
   __nv_bfloat16* outT = nullptr;
   int outT_pitch = 0, outT_off = 0;
   float* outF = nullptr;
-  int outF_pitch = 0, outF_off = 0;
+  int outF_pitch = 0, outF_off = 0, outF_planar = 0;
   long long m_limit = 0;             // > 0: rows >= m_limit do not exist (pointwise mode over pseudo-frames)
   float* z = nullptr;
   float* sbuf = nullptr;
@@ -48,6 +48,7 @@ struct TcTempArgs {
   const float* wsum = nullptr;
   const __nv_bfloat16* resid = nullptr;
   int resid_pitch = 0;
+  void* dbg = nullptr;               // optional device buffer of 16 x int64: per-role barrier wait cycles of CTA 0
   __nv_bfloat16* outAct = nullptr;   // EPI_GA: optional LeakyReLU'd copy (input of the GMM head)
   int outAct_pitch = 0;
 };

@@ -76,6 +76,10 @@ int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const 
 // params: pixel-major [M][720] fp32 (ppitch floats per pixel) or NCHW [BT,720,h,w] (params_nchw)
 int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, uint64_t seed, uint64_t offset, float* v,
                       bool v_nchw, int vpitch, int voff, int B, int T, int h, int w, cudaStream_t st);
+// params as planar quads [180][M][4] in the permuted channel order n' = j*240 + k*48 + hf (tcgen05 head); v -> planar z
+int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* z, int B, int T, int h,
+                             int w, cudaStream_t st);
+int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, cudaStream_t st);
 int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, long long n, cudaStream_t st);
 
 }  // namespace selfc

@@ -4,8 +4,8 @@
 // Reference behaviour restated (not copied): models/modules/SelfC_GMM_arch_inv.py:46-82 (FrequencyAnalyzer,
 // PixelUnshuffle), models/modules/Quantization.py:4-17, models/SelfC_model.py:217-222.
 //
-// Internal layout: latent state z [M][52] fp32, M = B*T*h*w pixel-major; ch 0..2 = LR part x1, 3 = pad,
-// 4..51 = HF part x2 (in the FORWARD channel order (sy*4+sx)*3+c while going down, and whatever the
+// Internal layout: latent state z as planar quads [13][M][4] fp32, M = B*T*h*w (common.cuh); quad 0 = LR part x1,
+// quads 1..12 = HF part x2 (in the FORWARD channel order (sy*4+sx)*3+c while going down, and whatever the
 // couplings produce while going up -- the reverse FrequencyAnalyzer reads it as c*16+sy*4+sx).
 #include "common.cuh"
 #include "kernels.h"
@@ -56,20 +56,20 @@ __global__ void __launch_bounds__(256) fa_fwd_kernel(const float* __restrict__ x
 #pragma unroll
       for (int c = 0; c < 3; ++c) o[(3 + q * 3 + c) * hw] = v[c][q] - lf[c];
   } else {
-    float row[kZPitch];
+    float row[4 * kZQuads];
     row[0] = lf[0]; row[1] = lf[1]; row[2] = lf[2]; row[3] = 0.f;
 #pragma unroll
     for (int q = 0; q < 16; ++q)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) row[kZHf + q * 3 + c] = v[c][q] - lf[c];
-    float* o = out + m * kZPitch;
+      for (int c = 0; c < 3; ++c) row[4 + q * 3 + c] = v[c][q] - lf[c];
 #pragma unroll
-    for (int k = 0; k < kZPitch; k += 4) store4(o + k, make_float4(row[k], row[k + 1], row[k + 2], row[k + 3]));
+    for (int k = 0; k < kZQuads; ++k)
+      store4(out + quad_off(M, k, m), make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]));
     if (fbuf != nullptr) {
       T* f = fbuf + m * fpitch;
 #pragma unroll
       for (int k = 0; k < kHF; k += 4)
-        store4(f + k, make_float4(row[kZHf + k], row[kZHf + k + 1], row[kZHf + k + 2], row[kZHf + k + 3]));
+        store4(f + k, make_float4(row[4 + k], row[4 + k + 1], row[4 + k + 2], row[4 + k + 3]));
     }
   }
 }
@@ -95,12 +95,11 @@ __global__ void __launch_bounds__(256) fa_rev_kernel(const float* __restrict__ z
 #pragma unroll
     for (int k = 0; k < kHF; ++k) hf[k] = __ldg(src + (3 + k) * hw);
   } else {
-    const float* src = z + m * kZPitch;
-    float4 a = load4(src);
+    float4 a = load4(z + quad_off(M, 0, m));
     lf[0] = a.x; lf[1] = a.y; lf[2] = a.z;
 #pragma unroll
     for (int k = 0; k < kHF; k += 4) {
-      float4 r = load4(src + kZHf + k);
+      float4 r = load4(z + quad_off(M, 1 + k / 4, m));
       hf[k] = r.x; hf[k + 1] = r.y; hf[k + 2] = r.z; hf[k + 3] = r.w;
     }
   }
@@ -133,57 +132,46 @@ __global__ void quantize_kernel(const float* __restrict__ x, uint8_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Export of the forward result: z [M][52] -> out51 [N,51,h,w] (+ LR quantised to u8 / fp32 grid).
-// 128 pixels per block staged through shared memory so both sides are coalesced.
+// Export of the forward result: planar z -> out51 [N,51,h,w] (+ LR quantised to u8 / fp32 grid).  One thread per
+// pixel: both the planar reads and the NCHW writes are coalesced across the warp.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) export_down_kernel(const float* __restrict__ z, float* __restrict__ out51,
+__global__ void __launch_bounds__(256) export_down_kernel(const float* __restrict__ z, float* __restrict__ out51,
                                                           uint8_t* __restrict__ lr_u8, float* __restrict__ lr_q,
                                                           long long M, long long hw) {
-  __shared__ float tile[128 * (kZPitch + 1)];
-  const long long m0 = (long long)blockIdx.x * 128;
-  const int cnt = (int)min((long long)128, M - m0);
-  for (int e = threadIdx.x; e < cnt * kZPitch; e += 128) {
-    int p = e / kZPitch, c = e % kZPitch;
-    tile[p * (kZPitch + 1) + c] = z[m0 * kZPitch + e];
-  }
-  __syncthreads();
-  const int p = threadIdx.x;
-  if (p >= cnt) return;
-  const long long m = m0 + p;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
   const long long n = m / hw, pix = m % hw;
-  const float* r = tile + p * (kZPitch + 1);
+  const float4 x1 = load4(z + quad_off(M, 0, m));
+  const float lr[3] = {x1.x, x1.y, x1.z};
   if (out51) {
     float* o = out51 + n * 51 * hw + pix;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) o[c * hw] = r[c];
-#pragma unroll 8
-    for (int k = 0; k < kHF; ++k) o[(3 + k) * hw] = r[kZHf + k];
+    for (int c = 0; c < 3; ++c) o[c * hw] = lr[c];
+#pragma unroll
+    for (int q = 0; q < kSQuads; ++q) {
+      const float4 r = load4(z + quad_off(M, 1 + q, m));
+      o[(3 + 4 * q) * hw] = r.x; o[(4 + 4 * q) * hw] = r.y; o[(5 + 4 * q) * hw] = r.z; o[(6 + 4 * q) * hw] = r.w;
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float code = quant_code(r[c]);
+    float code = quant_code(lr[c]);
     if (lr_u8) lr_u8[(n * 3 + c) * hw + pix] = (uint8_t)code;
     if (lr_q) lr_q[(n * 3 + c) * hw + pix] = code / 255.0f;
   }
 }
 
 // hf part of z -> [N,48,h,w]
-__global__ void __launch_bounds__(128) export_hf_kernel(const float* __restrict__ z, float* __restrict__ hf, long long M, long long hw) {
-  __shared__ float tile[128 * (kHF + 1)];
-  const long long m0 = (long long)blockIdx.x * 128;
-  const int cnt = (int)min((long long)128, M - m0);
-  for (int e = threadIdx.x; e < cnt * kHF; e += 128) {
-    int p = e / kHF, c = e % kHF;
-    tile[p * (kHF + 1) + c] = z[(m0 + p) * kZPitch + kZHf + c];
-  }
-  __syncthreads();
-  const int p = threadIdx.x;
-  if (p >= cnt) return;
-  const long long m = m0 + p;
+__global__ void __launch_bounds__(256) export_hf_kernel(const float* __restrict__ z, float* __restrict__ hf, long long M, long long hw) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
   const long long n = m / hw, pix = m % hw;
   float* o = hf + n * kHF * hw + pix;
-#pragma unroll 8
-  for (int k = 0; k < kHF; ++k) o[k * hw] = tile[p * (kHF + 1) + k];
+#pragma unroll
+  for (int q = 0; q < kSQuads; ++q) {
+    const float4 r = load4(z + quad_off(M, 1 + q, m));
+    o[(4 * q) * hw] = r.x; o[(4 * q + 1) * hw] = r.y; o[(4 * q + 2) * hw] = r.z; o[(4 * q + 3) * hw] = r.w;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -244,13 +232,13 @@ int launch_quantize(const float* x, uint8_t* q8, float* qf, size_t n, cudaStream
 }
 
 int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q, long long M, long long hw, cudaStream_t st) {
-  export_down_kernel<<<cdiv(M, 128), 128, 0, st>>>(z, out51, lr_u8, lr_q, M, hw);
+  export_down_kernel<<<cdiv(M, 256), 256, 0, st>>>(z, out51, lr_u8, lr_q, M, hw);
   SELFC_LAUNCH_CHECK("export_down_kernel");
   return 0;
 }
 
 int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st) {
-  export_hf_kernel<<<cdiv(M, 128), 128, 0, st>>>(z, hf, M, hw);
+  export_hf_kernel<<<cdiv(M, 256), 256, 0, st>>>(z, hf, M, hw);
   SELFC_LAUNCH_CHECK("export_hf_kernel");
   return 0;
 }

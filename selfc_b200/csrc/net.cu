@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "conv_tc.h"
+#include "tc_ptx.cuh"
 
 namespace selfc {
 
@@ -129,7 +130,7 @@ static Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w
     return o;
   };
   ws.gpitch = ctx->xpad3 + 4 * kGrowth;
-  ws.z = take(M * kZPitch * 4);
+  ws.z = take(M * kZQuads * 16);
   ws.sbuf = take(M * kHF * 4);
   ws.fbuf = take(M * ws.fpitch * es);
   ws.gbuf = take(M * ws.gpitch * es);
@@ -306,7 +307,7 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   const long long M = d.M(), hw = d.hw();
   const int xp = ctx->xpad3;
   // LR ingest: x1 of the reversed block 8, and the X slot of local_m1
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<float>(lr, z, kZPitch, 0, 3, 4, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<float>(lr, z, 4, 0, 3, 4, M, hw, st));
   PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, gbuf, ws.gpitch, 0, 3, xp, M, hw, st));
   PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, hbuf, ws.gpitch, 0, 3, xp, M, hw, st));
   PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, stpbuf, ws.gpitch, 0, 3, xp, M, hw, st));
@@ -332,6 +333,7 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
         t.in = in; t.in_pitch = in_pitch; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
         t.epi = EPI_STORE; t.act = act;
         t.outT = outT; t.outT_pitch = outT_pitch; t.outF = outF; t.outF_pitch = outF_pitch; t.outF_off = outF_off;
+        t.outF_planar = outF != nullptr ? 1 : 0;     // GMM parameters as planar quads for the thread-per-pixel sampler
         return launch_temporal_tc(w, t, st);
       };
       PROF(ctx, st, 3, 2.0 * M * 64 * 128, pointwise(ctx->head.t[0], fact, kStpC, h1, 128, nullptr, 0, 0, 1));
@@ -358,7 +360,10 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
     a.act = 0; a.outT = nullptr; a.outF = params; a.outF_pitch = 720;
     PROF(ctx, st, 3, 2.0 * M * 256 * 720, launch_conv_simt<T>(a, st));
   }
-  PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample(params, false, eps, seed, offset, z, false, kZPitch, kZHf, d.B, d.T, d.h, d.w, st));
+  if (head_done)
+    PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample_planar(params, eps, seed, offset, z, d.B, d.T, d.h, d.w, st));
+  else
+    PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample(params, false, eps, seed, offset, z, false, /*planar z*/ -1, 0, d.B, d.T, d.h, d.w, st));
   if (hf) PROF(ctx, st, 5, (double)M * 48 * 8, launch_export_hf(z, hf, M, hw, st));
   for (int blk = 7; blk >= 0; --blk) SELFC_TRY(run_invblock<T>(ctx, blk, true, wsp, ws, d, st));
   PROF(ctx, st, 5, (double)M * (51 * 4 + 48 * 4), launch_fa_rev(z, false, hr, d.B * d.T, d.h, d.w, st));
@@ -430,6 +435,8 @@ static int ga_impl(selfc_ctx* ctx, const GaW& g, const float* x, float* y, float
 extern "C" {
 
 int selfc_version(void) { return 100; }
+/* debug only (SELFC_TC_DBG=1): barrier-wait cycle counters of the tcgen05 temporal kernel, 17 int64 per launch */
+int selfc_debug_read(long long* out, int cap) { return selfc::tc::debug_read(out, cap); }
 const char* selfc_last_error(void) { return g_err; }
 uint64_t selfc_launch_count(void) { return g_launches; }
 
@@ -539,6 +546,8 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     head_w[j] = pl.take((size_t)ctx->head.cin[j] * ctx->head.np[j] * 4);
     head_b[j] = pl.take((size_t)ctx->head.np[j] * 4);
   }
+  const size_t head_perm_w = pl.take((size_t)720 * 256 * 4);
+  const size_t head_perm_b = pl.take(720 * 4);
   if (ctx->arena_bytes < pl.off) {
     if (ctx->arena) cudaFree(ctx->arena);
     ctx->arena = nullptr;
@@ -594,9 +603,11 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
   if (ctx->mode == SELFC_MODE_BF16) {
     SELFC_TRY(pack_temporal_weights(ctx->head.t[0], p[P_TAIL + 0], p[P_TAIL + 1], 128, 64, 1, 64, 64, 64, st));
     SELFC_TRY(pack_temporal_weights(ctx->head.t[1], p[P_TAIL + 2], p[P_TAIL + 3], 256, 128, 1, 128, 128, 128, st));
+    float* wperm = fp(head_perm_w);
+    float* bperm = fp(head_perm_b);
+    SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, st));
     for (int j = 0; j < 3; ++j)
-      SELFC_TRY(pack_temporal_weights(ctx->head.t[2 + j], p[P_TAIL + 4] + (size_t)240 * j * 256, p[P_TAIL + 5] + 240 * j, 240, 256, 1,
-                                      256, 256, 256, st));
+      SELFC_TRY(pack_temporal_weights(ctx->head.t[2 + j], wperm + (size_t)240 * j * 256, bperm + 240 * j, 240, 256, 1, 256, 256, 256, st));
   }
   ctx->loaded = true;
   return 0;

@@ -163,10 +163,72 @@ __global__ void __launch_bounds__(128) gmm_sample_kernel(const float* __restrict
   if (V_NCHW) {
     v[(n * kHF + hf0) * hw + pix] = out0;
     if (has1) v[(n * kHF + hf1) * hw + pix] = out1;
+  } else if (vpitch < 0) {      // planar latent state: quad 1 + hf/4
+    v[quad_off((size_t)M, 1 + hf0 / 4, (size_t)m) + (hf0 & 3)] = out0;
+    if (has1) v[quad_off((size_t)M, 1 + hf1 / 4, (size_t)m) + (hf1 & 3)] = out1;
   } else {
     v[m * vpitch + voff + hf0] = out0;
     if (has1) v[m * vpitch + voff + hf1] = out1;
   }
+}
+
+// Thread-per-pixel sampler over planar parameters (all loads coalesced): quad (j*60 + k*12 + i) holds channels
+// j*240 + k*48 + 4i .. +3 of the permuted head output.
+__global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __restrict__ params, const float* __restrict__ eps,
+                                                                uint64_t seed, uint64_t offset, float* __restrict__ z, int T,
+                                                                long long hw, long long M) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long n = m / hw, pix = m - n * hw;
+  const int t = (int)(n % T);
+  const long long b = n / T;
+  float mx[kGmmK], inv[kGmmK];
+#pragma unroll
+  for (int k = 0; k < kGmmK; ++k) {
+    float mk = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const float4 l = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + i, (size_t)m)));
+      mk = fmaxf(fmaxf(fmaxf(mk, l.x), fmaxf(l.y, l.z)), l.w);
+    }
+    float sk = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const float4 l = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + i, (size_t)m)));
+      sk += expf(l.x - mk) + expf(l.y - mk) + expf(l.z - mk) + expf(l.w - mk);
+    }
+    mx[k] = mk;
+    inv[k] = 1.0f / sk;
+  }
+  for (int i = 0; i < 12; ++i) {
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kGmmK; ++k) {
+      const float4 l4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + i, (size_t)m)));
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 60 + k * 12 + i, (size_t)m)));
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 120 + k * 12 + i, (size_t)m)));
+      const float lg[4] = {l4.x, l4.y, l4.z, l4.w}, ls[4] = {s4.x, s4.y, s4.z, s4.w}, mu[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int hf = 4 * i + e;
+        const uint64_t idx = (uint64_t)(((((b * kHF + hf) * kGmmK + k) * T + t) * hw) + pix);
+        const float ep = eps ? __ldg(eps + idx) : philox_normal(idx, seed, offset);
+        const float pi = expf(lg[e] - mx[k]) * inv[k];
+        out[e] += pi * (ep * expf(fminf(fmaxf(ls[e], -7.f), 7.f)) + mu[e]);
+      }
+    }
+    store4(z + quad_off((size_t)M, 1 + i, (size_t)m), make_float4(out[0], out[1], out[2], out[3]));
+  }
+}
+
+// tail_gmm.5 rows hf*15+k*3+j  ->  j*240 + k*48 + hf  (so each tcgen05 pass emits one parameter kind, hf contiguous)
+__global__ void permute_gmm_rows_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wp,
+                                        float* __restrict__ bp) {
+  const int np = blockIdx.x;                      // permuted row
+  const int j = np / 240, k = (np % 240) / 48, hf = np % 48;
+  const int src = hf * 15 + k * 3 + j;
+  for (int c = threadIdx.x; c < 256; c += blockDim.x) wp[np * 256 + c] = w[src * 256 + c];
+  if (threadIdx.x == 0) bp[np] = b[src];
 }
 
 __global__ void export_eps_kernel(float* __restrict__ eps, uint64_t seed, uint64_t offset, long long n) {
@@ -212,6 +274,21 @@ int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, u
   else
     gmm_sample_kernel<true, false><<<grid, 128, 0, st>>>(params, eps, seed, offset, v, vpitch, voff, T, h, w, M);
   SELFC_LAUNCH_CHECK("gmm_sample_kernel");
+  return 0;
+}
+
+int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* z, int B, int T, int h,
+                             int w, cudaStream_t st) {
+  const long long M = (long long)B * T * h * w;
+  if (M == 0) return 0;
+  gmm_sample_planar_kernel<<<cdiv(M, 128), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
+  SELFC_LAUNCH_CHECK("gmm_sample_planar_kernel");
+  return 0;
+}
+
+int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, cudaStream_t st) {
+  permute_gmm_rows_kernel<<<720, 128, 0, st>>>(w, b, wp, bp);
+  SELFC_LAUNCH_CHECK("permute_gmm_rows_kernel");
   return 0;
 }
 

@@ -67,6 +67,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Whole-warp variants: every lane executes the (warp-uniform) control flow and address arithmetic, so the compiler
+// keeps descriptors in uniform registers; one elected lane issues.  (Issuing from inside `if (lane == 0)` makes the
+// region divergent and costs several R2UR moves per MMA -- measured ~165 cycles per issue.)
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14), LBO>>4 [16,30) = byte distance between the two 8-element K core matrices,
 // SBO>>4 [32,46) = byte distance between 8-row groups, version=1 [46,48), layout_type=0 [61,64)
@@ -86,6 +106,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// Descriptor halves, so that the per-MMA work of the single issuing thread is one 32-bit add per operand:
+//   lo = start>>4 [0,14) | LBO>>4 [16,30)      hi = SBO>>4 [0,14) | version 1 [14,16) | base_offset [17,20) | layout [29,32)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return (sbo_bytes >> 4) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// K-major SWIZZLE_128B descriptor: rows of 128 bytes (64 bf16), 8-row swizzle atoms of 1024 bytes (SBO), the tile
+// base 1024-byte aligned; a K step of 16 elements advances the start address by 32 bytes inside the row.
+// `base_offset` [49,52) is for a start address that is not aligned to the 1024-byte atom (row phase).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t base_offset = 0) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)(base_offset & 7u) << 49) | ((uint64_t)2 << 61);
 }
 // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, A,B K-major, N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
@@ -112,12 +150,38 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Programmatic dependent launch: let the next kernel in the stream start its prologue (barrier init, TMEM alloc,
+// weight loads) while this one drains; `pdl_wait` must precede the first access to data the previous kernel wrote.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// host: launch with the programmatic-stream-serialization attribute (SELFC_NO_PDL=1 turns it off)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
 int* err_flag_for_device();
 int num_sms();
+// debug: per-launch slots of 16 int64 (device) + a host-side tag per slot; enabled by SELFC_TC_DBG=1
+bool debug_slots();
+long long* debug_next_slot(long long tag);
+int debug_read(long long* out, int cap);
 
 }  // namespace tc
 }  // namespace selfc

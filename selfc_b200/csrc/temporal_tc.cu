@@ -15,6 +15,7 @@
 // arithmetic on the fp32 latent state, and release each frame's accumulator as soon as it is drained so the next
 // tile's MMAs chase the epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv_tc.h"
@@ -27,8 +28,9 @@ namespace tc5 {
 using namespace tc;
 
 constexpr int MT = 128;
-constexpr int FRAME_BYTES = 2 * MT * 16;   // one frame tile of one 16-channel slice
-constexpr int NST = 4;
+// channels per pipeline stage = one swizzled row per pixel: KC = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B
+constexpr int KC_DEFAULT = 64;
+constexpr int NST_MAX = 8;
 constexpr int TMAX = 8;
 constexpr int THREADS = 192;
 constexpr int BAR_BYTES = 512;
@@ -37,14 +39,16 @@ constexpr int BIAS_BYTES = 1024;   // up to 256 fp32
 struct Params {
   const void* wimg;
   const float* bias;
-  int T, B, hw, nchunk, npad, taps, cout;
+  int T, B, hw, nks, npad, taps, cout, nst;   // nks = K steps of 16 channels; nst = pipeline stages
+  int fps;                                    // frames per pipeline stage (1 or 2)
+  int epi_quads;                              // 16-byte quads of epilogue operands staged per pixel-frame (Y2: 24, Y1: 1)
   int tiles_p, ntiles, tmem_cols;
   long long m_limit;   // rows (pixels) that really exist in the buffer
   int epi, rev, act;
   __nv_bfloat16* outT;
   int outT_pitch, outT_off;
   float* outF;
-  int outF_pitch, outF_off;
+  int outF_pitch, outF_off, outF_planar;   // outF_planar: write quads [C/4][m_limit][4] instead of [M][pitch]
   float* z;
   float* sbuf;
   __nv_bfloat16* copyA;
@@ -59,7 +63,44 @@ struct Params {
   __nv_bfloat16* outAct;
   int outAct_pitch;
   int* err;
+  long long* dbg;   // optional: CTA 0 writes cycles waited per barrier site [16] + totals
 };
+
+// Stage the coupling operands of the frame `ahead` frames after (tile, t) -- in this CTA's processing order -- into the
+// calling thread's own shared-memory slots with cp.async, and commit one group (always, so group counting is uniform).
+// Y2: quads 0..11 = x2 (latent state quads 1..12), 12..23 = log-scale s.  Y1: quad 0 = x1.
+__device__ __forceinline__ void stage_epilogue_operands(const Params& p, int tile, int t, int ahead, int row, size_t Mtot, uint32_t slot) {
+  int t2 = t + ahead, tile2 = tile;
+  while (t2 >= p.T) { t2 -= p.T; tile2 += (int)gridDim.x; }
+  if (tile2 < p.ntiles) {
+    const int b = tile2 / p.tiles_p;
+    const int pix = (tile2 - b * p.tiles_p) * MT + row;
+    if (pix < p.hw) {
+      const size_t m = ((size_t)b * p.T + t2) * p.hw + pix;
+      if (p.epi == EPI_COUPLE_Y2) {
+#pragma unroll
+        for (int qd = 0; qd < kSQuads; ++qd) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + (uint32_t)(qd * MT) * 16u), "l"(p.z + quad_off(Mtot, 1 + qd, m)) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + (uint32_t)((kSQuads + qd) * MT) * 16u), "l"(p.sbuf + quad_off(Mtot, qd, m)) : "memory");
+        }
+      } else {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(p.z + quad_off(Mtot, 0, m)) : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// barrier wait; with -DSELFC_TC_TIMING the cycles spent waiting are accumulated for the debug counters
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, int* err, int code, long long& acc) {
+#ifdef SELFC_TC_TIMING
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err, code);
+  acc += clock64() - t0;
+#else
+  mbar_wait(bar, parity, err, code);
+#endif
+}
 
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -69,6 +110,15 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* o, const float* v) {
   uint4 pk;
   pk.x = pack_bf2(v[0], v[1]); pk.y = pack_bf2(v[2], v[3]); pk.z = pack_bf2(v[4], v[5]); pk.w = pack_bf2(v[6], v[7]);
   *reinterpret_cast<uint4*>(o) = pk;
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4 r, float* v) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] = __low2float(b);
+    v[2 * i + 1] = __high2float(b);
+  }
 }
 __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float* v) {
   const uint4 r = *reinterpret_cast<const uint4*>(p);
@@ -80,6 +130,12 @@ __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float* v) {
     v[2 * i + 1] = __high2float(b);
   }
 }
+// streaming 16-byte load that the compiler may hoist above later stores (the buffers never alias within a launch)
+__device__ __forceinline__ float4 ld_nc4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -88,30 +144,48 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+
+template <int KC>
 __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  constexpr int FRAME_BYTES = MT * KC * 2;          // one frame tile of one KC-channel slice
+  const int FPS = p.fps;
+  const int STAGE_BYTES = FPS * FRAME_BYTES;
+  constexpr int KSTEPS = KC / 16;                   // UMMA K steps per stage
+  constexpr uint32_t SBO = 8 * KC * 2;              // 8-row swizzle atom
+  constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int T = p.T;
-  const uint32_t stage_bytes = (uint32_t)T * FRAME_BYTES;
+  const int NST = p.nst;
   const uint32_t a_base = base;
-  const uint32_t bar_base = base + NST * stage_bytes;
-  const uint32_t bias_off = NST * stage_bytes + BAR_BYTES;
+  const uint32_t bar_base = base + NST * STAGE_BYTES;
+  const uint32_t bias_off = NST * STAGE_BYTES + BAR_BYTES;
   const uint32_t w_base = base + bias_off + BIAS_BYTES;
+  // epilogue operand staging (double buffered, each thread owns its 16-byte slots): [2][epi_quads][128 px][16 B]
+  const uint32_t epi_base = w_base + (uint32_t)p.taps * p.nks * p.npad * 32u;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
-  const uint32_t w_bar = bar_base + 8u * (2 * NST);
-  const uint32_t tfull_bar = bar_base + 8u * (2 * NST + 1);
-  auto tempty_bar = [&](int t) { return bar_base + 8u * (2 * NST + 2 + t); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * NST + 2 + TMAX);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + NST * stage_bytes + 8 * (2 * NST + 2 + TMAX));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NST_MAX + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * NST_MAX);
+  const uint32_t tfull_bar = bar_base + 8u * (2 * NST_MAX + 1);
+  auto tempty_bar = [&](int t) { return bar_base + 8u * (2 * NST_MAX + 2 + t); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NST_MAX + 2 + TMAX);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + NST * STAGE_BYTES + 8 * (2 * NST_MAX + 2 + TMAX));
   float* sbias = reinterpret_cast<float*>(gen_base + bias_off);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < NST; ++s) {
+    for (int s = 0; s < NST_MAX; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -127,73 +201,103 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
 
-  const int nchunk = p.nchunk, npad = p.npad, taps = p.taps;
+  const int nks = p.nks, npad = p.npad, taps = p.taps;
+  const int nchunk = (nks + KSTEPS - 1) / KSTEPS;   // KC-channel slices
   const uint32_t wtile = (uint32_t)npad * 32u;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      const uint32_t wbytes = (uint32_t)taps * nchunk * wtile;
+      const uint32_t wbytes = (uint32_t)taps * nks * wtile;
       mbar_expect_tx(w_bar, wbytes);
       for (int tap = 0; tap < taps; ++tap)
-        bulk_g2s(w_base + tap * nchunk * wtile, (const uint8_t*)p.wimg + (size_t)tap * nchunk * wtile, (uint32_t)nchunk * wtile, w_bar);
+        bulk_g2s(w_base + tap * nks * wtile, (const uint8_t*)p.wimg + (size_t)tap * nks * wtile, (uint32_t)nks * wtile, w_bar);
+      pdl_wait();      // weights are static; activations come from the previous kernel in the stream
       int s = 0;
       uint32_t ph = 0;
+      long long w_prod = 0;
+      const long long t_start = clock64();
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int b = tile / p.tiles_p;
         const int p0 = (tile - b * p.tiles_p) * MT;
         for (int c = 0; c < nchunk; ++c) {
-          mbar_wait(empty_bar(s), ph ^ 1u, p.err, 11);
-          mbar_expect_tx(full_bar(s), stage_bytes);
-          const uint32_t dst = a_base + s * stage_bytes;
-          for (int t = 0; t < T; ++t) {
-            tma_load_3d(dst + t * FRAME_BYTES, &tmap, full_bar(s), c * 16, p0, b * T + t);
-            tma_load_3d(dst + t * FRAME_BYTES + MT * 16, &tmap, full_bar(s), c * 16 + 8, p0, b * T + t);
+          for (int t0 = 0; t0 < T; t0 += FPS) {
+            const int nf = T - t0 < FPS ? T - t0 : FPS;
+            timed_wait(empty_bar(s), ph ^ 1u, p.err, 11, w_prod);
+            mbar_expect_tx(full_bar(s), (uint32_t)nf * FRAME_BYTES);
+            for (int f = 0; f < nf; ++f)
+              tma_load_3d(a_base + s * STAGE_BYTES + f * FRAME_BYTES, &tmap, full_bar(s), c * KC, p0, b * T + t0 + f);
+            if (++s == NST) { s = 0; ph ^= 1u; }
           }
-          if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = w_prod; p.dbg[1] = clock64() - t_start; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
       const uint32_t idesc = umma_idesc_bf16(128, npad);
+      long long w_full = 0, w_tempty = 0;
+      const long long t_start = clock64();
       mbar_wait(w_bar, 0, p.err, 12);
+      const long long t_w = clock64() - t_start;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        uint32_t started = 0;                   // bit t: accumulator of output frame t already holds a partial sum
         for (int c = 0; c < nchunk; ++c) {
-          mbar_wait(full_bar(s), ph, p.err, 14);
-          tc_fence_after();
-          const uint32_t a_stage = a_base + s * stage_bytes;
-          for (int to = 0; to < T; ++to) {
-            if (c == 0) {
-              mbar_wait(tempty_bar(to), ((uint32_t)it & 1u) ^ 1u, p.err, 13);
-              tc_fence_after();
-            }
-            bool first = (c == 0);
+          const int ksn = nks - KSTEPS * c < KSTEPS ? nks - KSTEPS * c : KSTEPS;
+          for (int t0 = 0; t0 < T; t0 += FPS) {
+            const int nf = T - t0 < FPS ? T - t0 : FPS;
+            timed_wait(full_bar(s), ph, p.err, 14, w_full);
+            tc_fence_after();
+           for (int f = 0; f < nf; ++f) {
+            const int ti = t0 + f;
+            const uint32_t a_stage = a_base + s * STAGE_BYTES + f * FRAME_BYTES;
             for (int tap = 0; tap < taps; ++tap) {
-              const int ti = taps == 3 ? to + tap - 1 : to;
-              if (ti < 0 || ti >= T) continue;
-              const uint64_t ad = umma_desc(a_stage + (uint32_t)ti * FRAME_BYTES, MT * 16, 128);
-              const uint64_t bd = umma_desc(w_base + (uint32_t)(tap * nchunk + c) * wtile, (uint32_t)npad * 16u, 128);
-              umma_bf16(tmem_base + (uint32_t)(to * npad), ad, bd, idesc, first ? 0u : 1u);
-              first = false;
+              const int to = taps == 3 ? ti - tap + 1 : ti;     // out[to] += W[tap] . in[to + tap - 1]
+              if (to < 0 || to >= T) continue;
+              if (!(started >> to & 1u)) {
+                timed_wait(tempty_bar(to), ((uint32_t)it & 1u) ^ 1u, p.err, 13, w_tempty);
+                tc_fence_after();
+              }
+              const uint32_t a_lo = desc_lo(a_stage, 16);
+              const uint32_t b_lo = desc_lo(w_base + (uint32_t)(tap * nks + KSTEPS * c) * wtile, (uint32_t)npad * 16u);
+              const uint32_t dcol = tmem_base + (uint32_t)(to * npad);
+              for (int ks = 0; ks < ksn; ++ks) {
+                // A: +32 bytes per K step inside the 128-byte swizzled row; B: next 16-channel weight tile
+                const uint64_t ad = desc_join(a_lo + 2u * (uint32_t)ks, desc_hi(SBO, LAYOUT));
+                const uint64_t bd = desc_join(b_lo + (uint32_t)ks * (wtile >> 4), desc_hi(128, 0));
+                umma_bf16_elect(dcol, ad, bd, idesc, (started >> to & 1u) ? 1u : 0u);
+                started |= 1u << to;
+              }
             }
+           }
+            umma_commit_elect(empty_bar(s));
+            if (++s == NST) { s = 0; ph ^= 1u; }
           }
-          umma_commit(empty_bar(s));
-          if (++s == NST) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull_bar);
+        umma_commit_elect(tfull_bar);
       }
+      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - t_start; p.dbg[5] = t_w; }
     }
   } else {
     // ===================== epilogue warps 2..5 =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    pdl_wait();
+    const size_t Mtot = (size_t)p.B * T * p.hw;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    long long w_tfull = 0, w_cp = 0;
+    const long long t_start_e = clock64();
+    uint32_t gframe = 0;     // frames processed so far by this CTA: staging buffer = gframe & 1
+    if (p.epi_quads) {
+      stage_epilogue_operands(p, (int)blockIdx.x, 0, 0, row, Mtot, epi_base + (uint32_t)row * 16u);
+      stage_epilogue_operands(p, (int)blockIdx.x, 0, 1, row, Mtot, epi_base + (uint32_t)(p.epi_quads * MT + row) * 16u);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_p;
@@ -203,19 +307,12 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       if (pix < p.hw) {
         for (int t = 0; t < T; ++t) {
           const size_t m = ((size_t)b * T + t) * p.hw + pix;
-          if (p.epi == EPI_COUPLE_Y1) {
-            prefetch_l2(p.z + m * kZPitch);
-          } else if (p.epi == EPI_COUPLE_Y2) {
-            prefetch_l2(p.z + m * kZPitch);
-            prefetch_l2(p.z + m * kZPitch + 32);
-            prefetch_l2(p.sbuf + m * kHF);
-            prefetch_l2(p.sbuf + m * kHF + 32);
-          } else if (p.epi == EPI_GA) {
+          if (p.epi == EPI_GA) {
             prefetch_l2(p.resid + m * p.resid_pitch);
           }
         }
       }
-      mbar_wait(tfull_bar, (uint32_t)it & 1u, p.err, 15);
+      timed_wait(tfull_bar, (uint32_t)it & 1u, p.err, 15, w_tfull);
       tc_fence_after();
       if (p.epi == EPI_GA) {
         // out[t'] = x[t'] + bias * colsum(W)[t'] + sum_t W[b,t,t'] * D_t
@@ -227,10 +324,16 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
             if (t < T) tmem_ld8(lane_addr + (uint32_t)(t * npad + n0), d[t]);
           tmem_ld_wait();
           if (valid) {
-            for (int tp = 0; tp < T; ++tp) {
+            uint4 rs[TMAX];
+#pragma unroll
+            for (int tp = 0; tp < TMAX; ++tp)
+              if (tp < T) rs[tp] = *reinterpret_cast<const uint4*>(p.resid + (((size_t)b * T + tp) * p.hw + pix) * p.resid_pitch + n0);
+#pragma unroll
+            for (int tp = 0; tp < TMAX; ++tp) {
+              if (tp >= T) continue;
               const size_t m = ((size_t)b * T + tp) * p.hw + pix;
               float v[8];
-              load_bf16x8(p.resid + m * p.resid_pitch + n0, v);
+              unpack_bf16x8(rs[tp], v);
               const float ws = __ldg(p.wsum + b * T + tp);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] += sbias[n0 + j] * ws;
@@ -262,14 +365,31 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
           for (int t = 0; t < T; ++t) mbar_arrive(tempty_bar(t));
         continue;
       }
-      for (int t = 0; t < T; ++t) {
+      for (int t = 0; t < T; ++t, ++gframe) {
         const size_t m = ((size_t)b * T + t) * p.hw + pix;
         const int ncols = p.epi == EPI_COUPLE_Y1 ? 16 : (p.epi == EPI_STORE ? ((p.cout + 15) & ~15) : kHF);
+        const bool live = valid && (long long)m < p.m_limit;
+        const uint32_t ebuf = epi_base + (uint32_t)((gframe & 1) * p.epi_quads * MT + row) * 16u;
+        if (p.epi_quads) {
+          const long long t0 = clock64();
+          asm volatile("cp.async.wait_group 1;" ::: "memory");   // this frame's operands have landed
+          w_cp += clock64() - t0;
+        }
         for (int n0 = 0; n0 < ncols; n0 += 16) {
+          float4 x2q[4], sq[4];
+          if (live && p.epi == EPI_COUPLE_Y2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x2q[j] = lds4(ebuf + (uint32_t)((n0 / 4 + j) * MT) * 16u);
+              sq[j] = lds4(ebuf + (uint32_t)((kSQuads + n0 / 4 + j) * MT) * 16u);
+            }
+          } else if (live && p.epi == EPI_COUPLE_Y1) {
+            x2q[0] = lds4(ebuf);
+          }
           uint32_t r[16];
           tmem_ld16(lane_addr + (uint32_t)(t * npad + n0), r);
           tmem_ld_wait();
-          if (!valid || (long long)m >= p.m_limit) continue;
+          if (!live) continue;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
@@ -289,7 +409,11 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                     if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
                 }
               }
-              if (p.outF) {
+              if (p.outF && p.outF_planar) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  store4(p.outF + quad_off((size_t)p.m_limit, (p.outF_off + n0 + j) / 4, m), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+              } else if (p.outF) {
                 float* o = p.outF + m * p.outF_pitch + p.outF_off + n0;
                 if (n0 + 16 <= p.cout && ((p.outF_pitch | p.outF_off) & 3) == 0) {
 #pragma unroll
@@ -301,8 +425,8 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
               }
             } break;
             case EPI_COUPLE_Y1: {
-              float* zp = p.z + m * kZPitch;
-              const float4 x1 = load4(zp);
+              float* zp = p.z + quad_off(Mtot, 0, m);
+              const float4 x1 = x2q[0];
               float y[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) y[j] = 0.f;
@@ -320,29 +444,27 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
               }
             } break;
             case EPI_COUPLE_S: {
-              float* sp = p.sbuf + m * kHF + n0;
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 float s[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) s[e] = (1.0f / (1.0f + expf(-v[j + e]))) * 2.0f - 1.0f;
-                store4(sp + j, make_float4(s[0], s[1], s[2], s[3]));
+                for (int e = 0; e < 4; ++e) s[e] = __fdividef(2.0f, 1.0f + __expf(-v[j + e])) - 1.0f;   // 2*sigmoid(h)-1, ~1e-6 rel
+                store4(p.sbuf + quad_off(Mtot, (n0 + j) / 4, m), make_float4(s[0], s[1], s[2], s[3]));
               }
             } break;
             case EPI_COUPLE_Y2: {
-              float* zp = p.z + m * kZPitch + kZHf + n0;
-              const float* sp = p.sbuf + m * kHF + n0;
               float y[16];
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
-                const float4 x2 = load4(zp + j);
-                const float4 s4 = load4(sp + j);
+                float* zp = p.z + quad_off(Mtot, 1 + (n0 + j) / 4, m) - j;
+                const float4 x2 = x2q[j / 4];
+                const float4 s4 = sq[j / 4];
                 const float xr[4] = {x2.x, x2.y, x2.z, x2.w};
                 const float sr[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float ex = expf(sr[e]);
-                  y[j + e] = p.rev ? (xr[e] - v[j + e]) / ex : xr[e] * ex + v[j + e];
+                  // s in (-1,1): exp via ex2.approx (rel 2^-21); the reverse divides by multiplying with exp(-s)
+                  y[j + e] = p.rev ? (xr[e] - v[j + e]) * __expf(-sr[e]) : fmaf(xr[e], __expf(sr[e]), v[j + e]);
                 }
                 store4(zp + j, make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]));
               }
@@ -357,8 +479,11 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(t));
+        if (p.epi_quads) stage_epilogue_operands(p, tile, t, 2, row, Mtot, ebuf);
       }
     }
+    if (p.epi_quads) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[6] = w_tfull; p.dbg[7] = w_cp; p.dbg[8] = clock64() - t_start_e; p.dbg[9] = it; }
   }
 
   tc_fence_before();
@@ -433,10 +558,18 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   CUtensorMap tmap;
   const cuuint64_t gdim[3] = {(cuuint64_t)a.in_pitch, (cuuint64_t)a.hw, (cuuint64_t)BT};
   const cuuint64_t gstr[2] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.hw * a.in_pitch * 2};
-  const cuuint32_t box[3] = {8, (cuuint32_t)tc5::MT, 1};
+  static int kc = 0;     // SELFC_TC_KC = 64 | 32 | 16 selects the swizzle width of the A operand (experiment knob)
+  if (!kc) {
+    const char* e = getenv("SELFC_TC_KC");
+    kc = e ? atoi(e) : tc5::KC_DEFAULT;
+    if (kc != 64 && kc != 32 && kc != 16) kc = tc5::KC_DEFAULT;
+  }
+  const cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)tc5::MT, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (temporal) failed with CUresult %d", (int)r);
@@ -445,7 +578,7 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   tc5::Params p;
   memset(&p, 0, sizeof(p));
   p.wimg = w.img; p.bias = w.bias;
-  p.T = a.T; p.B = a.B; p.hw = a.hw; p.nchunk = w.cin_buf / 16; p.npad = w.npad; p.taps = w.taps; p.cout = w.cout;
+  p.T = a.T; p.B = a.B; p.hw = a.hw; p.nks = w.cin_buf / 16; p.npad = w.npad; p.taps = w.taps; p.cout = w.cout;
   p.tiles_p = cdiv(a.hw, tc5::MT);
   p.ntiles = p.tiles_p * a.B;
   int cols = a.T * w.npad, pw = 32;
@@ -453,24 +586,43 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   p.tmem_cols = pw;
   p.epi = a.epi; p.rev = a.rev; p.act = a.act;
   p.outT = a.outT; p.outT_pitch = a.outT_pitch; p.outT_off = a.outT_off;
-  p.outF = a.outF; p.outF_pitch = a.outF_pitch; p.outF_off = a.outF_off;
+  p.outF = a.outF; p.outF_pitch = a.outF_pitch; p.outF_off = a.outF_off; p.outF_planar = a.outF_planar;
   p.m_limit = a.m_limit > 0 ? a.m_limit : (long long)BT * a.hw;
   p.z = a.z; p.sbuf = a.sbuf;
   p.copyA = a.copyA; p.copyA_pitch = a.copyA_pitch; p.copyB = a.copyB; p.copyB_pitch = a.copyB_pitch; p.copy_pad = a.copy_pad;
   p.wmat = a.wmat; p.wsum = a.wsum; p.resid = a.resid; p.resid_pitch = a.resid_pitch;
   p.outAct = a.outAct; p.outAct_pitch = a.outAct_pitch;
   p.err = tc::err_flag_for_device();
+  p.dbg = reinterpret_cast<long long*>(a.dbg);
+  if (!p.dbg && tc::debug_slots()) {          // SELFC_TC_DBG=1: every launch records CTA 0's barrier-wait cycles
+    long long* slot = tc::debug_next_slot(a.epi * 1000000 + w.npad * 1000 + w.cin_buf / 16);
+    p.dbg = slot;
+  }
   if (p.ntiles == 0) return 0;
-  const int smem = tc5::NST * a.T * tc5::FRAME_BYTES + tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes + 1024;
+  p.epi_quads = a.epi == EPI_COUPLE_Y2 ? 2 * kSQuads : (a.epi == EPI_COUPLE_Y1 ? 1 : 0);
+  const int fixed = tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes + 2 * p.epi_quads * tc5::MT * 16 + 1024;
+  int fps = a.T >= 2 ? 2 : 1;
+  if ((227 * 1024 - fixed) / (fps * tc5::MT * kc * 2) < 3) fps = 1;
+  p.fps = fps;
+  const int stage_bytes = fps * tc5::MT * kc * 2;
+  int nst = (227 * 1024 - fixed) / stage_bytes;
+  if (nst > tc5::NST_MAX) nst = tc5::NST_MAX;
+  SELFC_CHECK_ARG(nst >= 2, "temporal_tc: weights of %zu bytes leave no room for the A pipeline", w.img_bytes);
+  p.nst = nst;
+  const int smem = nst * stage_bytes + fixed;
   static int smem_set = 0;
   if (smem_set < smem) {
-    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set = 227 * 1024;
   }
   SELFC_CHECK_ARG(smem <= 227 * 1024, "temporal_tc: %d bytes of shared memory needed", smem);
   const int nsm = tc::num_sms();
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
-  tc5::temporal_tc_kernel<<<grid, tc5::THREADS, smem, st>>>(tmap, p);
+  if (kc == 64) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<64>, grid, tc5::THREADS, smem, st, tmap, p));
+  else if (kc == 32) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<32>, grid, tc5::THREADS, smem, st, tmap, p));
+  else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<16>, grid, tc5::THREADS, smem, st, tmap, p));
   SELFC_LAUNCH_CHECK("temporal_tc_kernel");
   return 0;
 }
