@@ -74,6 +74,9 @@ int selfc_fa_fwd(const float* x, float* out51, int N, int H, int W, void* stream
 int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream);
 /* a4 Quantization.py:4-17 on [n] floats */
 int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* stream);
+/* caller-side neighbour of the path: LR_ref of `distortion: sr_bd`, models/Guassian.py:7-52 as called at
+ * models/SelfC_model.py:128-129.  x [N,C,H,W] -> y [N,C,H/4,W/4]; k13 = the 13x13 taps (device, 169 floats). */
+int selfc_gaussian_down(const float* x, const float* k13, float* y, int N, int C, int H, int W, void* stream);
 /* a3 D2DTInput.forward (Subnet_constructor.py:115-133) for the dense block stored at parameter index
  * `first_param` (its conv1.weight); x [B*T,Cin,h,w] -> y [B*T,Cout,h,w], both fp32 NCHW. */
 int selfc_d2dt(selfc_ctx* ctx, int first_param, const float* x, float* y, int B, int T, int h, int w,

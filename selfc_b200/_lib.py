@@ -27,6 +27,7 @@ SIGNATURES = {
     "selfc_fa_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa_rev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_quantize": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "selfc_gaussian_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "selfc_d2dt": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_conv3x3": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_global_agg": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),

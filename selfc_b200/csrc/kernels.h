@@ -14,6 +14,7 @@ int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w,
 int launch_quantize(const float* x, uint8_t* q8, float* qf, size_t n, cudaStream_t st);
 int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q, long long M, long long hw, cudaStream_t st);
 int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st);
+int launch_gaussian_down(const float* x, const float* k13, float* y, int NC, int H, int W, cudaStream_t st);
 template <typename T>
 int launch_nchw_to_dense(const float* x, T* dst, int pitch, int off, int C, int cpad, long long M, long long hw, cudaStream_t st);
 template <typename T>

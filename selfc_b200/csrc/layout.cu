@@ -198,6 +198,43 @@ __global__ void dense_to_nchw_kernel(const T* __restrict__ src, int pitch, int o
   for (int c = 0; c < C; ++c) y[(n * C + c) * hw + pix] = to_f(s[c]);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// LR_ref of `distortion: sr_bd` (models/Guassian.py:7-52): reflect-pad 14, 13x13 Gaussian (sigma 1.6, the taps of
+// scipy.ndimage.gaussian_filter on a dirac, passed in), stride 4, crop 2 px of the padded result on each side
+// => out[i,j] = sum_{u,v<13} k[u,v] * x[reflect(4i+u-6), reflect(4j+v-6)].
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int p, int n) {
+  if (p < 0) p = -p;
+  if (p >= n) p = 2 * n - 2 - p;
+  return p;
+}
+__global__ void __launch_bounds__(256) gaussian_down_kernel(const float* __restrict__ x, const float* __restrict__ k13,
+                                                            float* __restrict__ y, int NC, int H, int W) {
+  __shared__ float ks[169];
+  for (int i = threadIdx.x; i < 169; i += blockDim.x) ks[i] = k13[i];
+  __syncthreads();
+  const int h = H / 4, w = W / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)NC * h * w) return;
+  const int j = (int)(idx % w), i = (int)((idx / w) % h);
+  const long long nc = idx / ((long long)w * h);
+  const float* src = x + nc * H * W;
+  float acc = 0.f;
+  for (int u = 0; u < 13; ++u) {
+    const int yy = reflect_idx(4 * i + u - 6, H);
+    for (int v = 0; v < 13; ++v) acc += ks[u * 13 + v] * __ldg(src + (long long)yy * W + reflect_idx(4 * j + v - 6, W));
+  }
+  y[idx] = acc;
+}
+
+int launch_gaussian_down(const float* x, const float* k13, float* y, int NC, int H, int W, cudaStream_t st) {
+  const long long n = (long long)NC * (H / 4) * (W / 4);
+  if (n == 0) return 0;
+  gaussian_down_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, k13, y, NC, H, W);
+  SELFC_LAUNCH_CHECK("gaussian_down_kernel");
+  return 0;
+}
+
 // ---- launchers ----------------------------------------------------------------------------------------
 int launch_fa_fwd_nchw(const float* x, float* out51, int N, int h, int w, cudaStream_t st) {
   long long M = (long long)N * h * w;

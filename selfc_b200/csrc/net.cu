@@ -675,6 +675,12 @@ int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream) 
   return launch_fa_rev(z51, true, y, N, h, w, (cudaStream_t)stream);
 }
 
+int selfc_gaussian_down(const float* x, const float* k13, float* y, int N, int C, int H, int W, void* stream) {
+  SELFC_CHECK_ARG(x && k13 && y, "gaussian_down: null pointer");
+  SELFC_CHECK_ARG(N >= 0 && C >= 1 && H >= 16 && W >= 16 && H % 4 == 0 && W % 4 == 0, "gaussian_down: N=%d C=%d H=%d W=%d", N, C, H, W);
+  return launch_gaussian_down(x, k13, y, N * C, H, W, (cudaStream_t)stream);
+}
+
 int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* stream) {
   SELFC_CHECK_ARG(x || n == 0, "quantize: null input");
   return launch_quantize(x, q_u8, q_f32, n, (cudaStream_t)stream);

@@ -185,6 +185,43 @@ class Engine:
         rec, _ = self.up(lr_q, T, eps=eps, seed=seed, offset=offset, want_hf=False)
         return lr_u8, rec
 
+    def rescale_host(self, frames_host: torch.Tensor, lr_host: torch.Tensor, hr_host: torch.Tensor, T: int = 7,
+                     seed: int = 0, offset0: int = 0) -> None:
+        """A whole clip held in (pinned) HOST memory -> LR codes and reconstructed HR frames in HOST memory.
+
+        frames_host [n,3,H,W] fp32; lr_host [n,3,H/4,W/4] uint8; hr_host [n,3,H,W] fp32.  The clip is cut into GOPs of T
+        frames (tail padded with copies of the last frame, models/SelfC_model.py:204-209); the H2D copy of GOP i+1 and the
+        D2H copy of GOP i-1 run on side streams while GOP i computes.  Returns after everything has landed in host memory."""
+        from .sharding import gop_indices
+        n, _, H, W = frames_host.shape
+        dev = self.device
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_in, s_out = self._s_in, self._s_out
+        cur = torch.cuda.current_stream(dev)
+        bufs = [torch.empty((T, 3, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+        ev_free = [None, None]
+        s_in.wait_stream(cur)
+        for i, (ids, real) in enumerate(gop_indices(n, T)):
+            buf = bufs[i & 1]
+            with torch.cuda.stream(s_in):
+                if ev_free[i & 1] is not None:
+                    s_in.wait_event(ev_free[i & 1])             # the previous user of this buffer has finished reading it
+                buf[:real].copy_(frames_host[ids[0]:ids[0] + real], non_blocking=True)
+                if real < T:
+                    buf[real:] = buf[real - 1:real]
+                ev_in = s_in.record_event()
+            cur.wait_event(ev_in)
+            lr_u8, rec = self.rescale(buf, T, seed=seed, offset=offset0 + i)
+            ev_free[i & 1] = cur.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_free[i & 1])
+                lr_host[ids[0]:ids[0] + real].copy_(lr_u8[:real], non_blocking=True)
+                hr_host[ids[0]:ids[0] + real].copy_(rec[:real], non_blocking=True)
+                lr_u8.record_stream(s_out)
+                rec.record_stream(s_out)
+        s_out.synchronize()
+
     # ---- per-launch timing (bench.py roofline leg) ---------------------------------------------------------------
     PROF_CLASSES = ("conv3x3", "conv5_coupling", "global_agg", "gmm_head", "sampler", "layout")
 
@@ -271,6 +308,33 @@ def quantize(x: torch.Tensor):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().selfc_quantize(_ptr(x), _ptr(q8), _ptr(qf), x.numel(), _stream(x.device)), "quantize")
     return q8, qf
+
+
+_GAUSS13 = {}
+
+
+def gaussian_kernel_13(sigma: float = 1.6) -> torch.Tensor:
+    """The 13x13 taps the reference builds with scipy.ndimage.gaussian_filter on a dirac (models/Guassian.py:16-22):
+    a separable, 4-sigma-truncated, normalised Gaussian (truncate=4 -> radius 6 at sigma 1.6)."""
+    import math
+    g = [math.exp(-0.5 * (i / sigma) ** 2) for i in range(-6, 7)]
+    ssum = sum(g)
+    g = torch.tensor([v / ssum for v in g], dtype=torch.float64)
+    return torch.outer(g, g).to(torch.float32)
+
+
+def gaussian_downsample(x: torch.Tensor) -> torch.Tensor:
+    """LR_ref for `distortion: sr_bd`: [N,C,H,W] -> [N,C,H/4,W/4] (models/Guassian.py:7-52)."""
+    x = _dev_check(x)
+    n, c, hh, ww = x.shape
+    key = x.device
+    if key not in _GAUSS13:
+        _GAUSS13[key] = gaussian_kernel_13().to(x.device).contiguous()
+    y = torch.empty((n, c, hh // 4, ww // 4), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().selfc_gaussian_down(_ptr(x), _ptr(_GAUSS13[key]), _ptr(y), n, c, hh, ww, _stream(x.device)),
+                   "gaussian_down")
+    return y
 
 
 def gmm_sample(params: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0):

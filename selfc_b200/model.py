@@ -1,0 +1,146 @@
+"""Host-side mirror of the reference's model wrapper for the rescaling path: `create_model(opt)` /
+`SelfCModel` (models/__init__.py:5-15, models/SelfC_model.py:27-319, models/base_model.py:77-107), inference half.
+
+Same call sequence as test_rescaling.py uses -- feed_data(data) -> test() -> get_current_visuals() -- and the same
+checkpoint handling (state_dict file, optional 'module.' prefix, strict load).  Differences, on purpose:
+  * test() runs the network ONCE per GOP; the reference's extra padded pass whose result is discarded
+    (SelfC_model.py:203-243) is not reproduced;
+  * no DataParallel wrapper: one process per GPU (the wrapper's `.module` attribute is provided for compatibility);
+  * training (optimize_parameters) is not implemented in this round (row a13).
+"""
+from __future__ import annotations
+
+import logging
+from collections import OrderedDict
+
+import torch
+
+from . import engine as _engine
+from . import networks
+from .global_var import GlobalVar
+from .sharding import GOP
+
+logger = logging.getLogger("base")
+
+
+class _ModuleHandle:
+    """`model.netG.module` compatibility with code written against the DataParallel wrapper."""
+
+    def __init__(self, net):
+        self.module = net
+
+    def __getattr__(self, k):
+        return getattr(self.module, k)
+
+    def __call__(self, *a, **k):
+        return self.module(*a, **k)
+
+
+class SelfCModel:
+    def __init__(self, opt):
+        self.opt = opt
+        if not torch.cuda.is_available():
+            raise RuntimeError("selfc_b200.model.SelfCModel needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.is_train = bool(opt["is_train"])
+        if self.is_train:
+            raise NotImplementedError("selfc_b200 implements the inference half of SelfCModel (test/feed_data) in this round")
+        net = networks.define_G(opt).to(self.device)
+        self.netG = _ModuleHandle(net)
+        self.load()
+        net.eval()
+        self.gop = GOP
+
+    # ---- checkpoint handling: base_model.py:77-107 ----------------------------------------------------------
+    def load(self):
+        path = (self.opt["path"] or {}).get("pretrain_model_G") if self.opt["path"] else None
+        if path:
+            logger.info("Loading model for G [%s] ...", path)
+            self.load_network(path, self.netG.module, bool(self.opt["path"].get("strict_load", True)))
+
+    @staticmethod
+    def load_network(load_path, network, strict=True):
+        load_net = torch.load(load_path, map_location="cpu")
+        clean = OrderedDict()
+        for k, v in load_net.items():
+            if "Quantization_H265_Suggrogate" in k:
+                continue
+            clean[k[7:] if k.startswith("module.") else k] = v
+        network.load_state_dict(clean, strict=strict)
+
+    def save_network(self, save_path):
+        sd = OrderedDict((k, v.detach().cpu()) for k, v in self.netG.module.state_dict().items())
+        torch.save(sd, save_path)
+
+    # ---- feed_data: SelfC_model.py:93-132 -----------------------------------------------------------------
+    def feed_data(self, data):
+        real = data["GT"]                                   # [B,3,t,H,W]
+        t_len = GlobalVar.get_Temporal_LEN()
+        clip_length = real.size(2)
+        if clip_length < t_len:                             # pad short clips with copies of the last frame
+            pads = real[:, :, -1:].expand(-1, -1, t_len - clip_length, -1, -1)
+            real = torch.cat([real, pads], dim=2)
+        real = real.to(self.device, non_blocking=True)
+        self.real_H = real.transpose(1, 2).reshape(-1, 3, real.size(3), real.size(4)).contiguous()
+        dist = self.opt["distortion"]
+        if "LQ" in data:
+            lq = data["LQ"].to(self.device)
+            self.ref_L = lq.transpose(1, 2).reshape(-1, 3, lq.size(3), lq.size(4))
+        elif dist == "sr_bd":
+            self.ref_L = _engine.gaussian_downsample(self.real_H)
+        elif dist == "pytorch_bicubic":
+            self.ref_L = torch.nn.functional.interpolate(self.real_H, scale_factor=1.0 / self.opt["scale"], mode="area")
+        else:
+            raise NotImplementedError(f"distortion {dist!r} is not on the rescaling path (only sr_bd / pytorch_bicubic)")
+        return clip_length
+
+    # ---- test: SelfC_model.py:185-250 -----------------------------------------------------------------------
+    def test(self):
+        net = self.netG.module
+        t = GlobalVar.get_Temporal_LEN()
+        bt, c, hh, ww = self.real_H.shape
+        b = bt // t
+        clips = self.real_H.reshape(b, t, c, hh, ww)
+        saved_t = t
+        forw_L, forw_H, fake_H, sample_H = [], [], [], []
+        with torch.no_grad():
+            for g0 in range(0, t, self.gop):
+                ids = list(range(g0, min(t, g0 + self.gop)))
+                real = len(ids)
+                ids += [t - 1] * (self.gop - real)
+                x = clips[:, ids].reshape(b * self.gop, c, hh, ww)
+                GlobalVar.set_Temporal_LEN(self.gop)
+                out, _ = net(x=x)
+                lr = net_quantize(out[:, :3])
+                hr, hf = net(x=lr, rev=True)
+                for lst, ten, cc in ((forw_L, lr, 3), (forw_H, out[:, 3:], 48), (fake_H, hr[:, :3], 3), (sample_H, hf, 48)):
+                    v = ten.reshape(b, self.gop, cc, ten.shape[-2], ten.shape[-1])[:, :real]
+                    lst.append(v)
+        GlobalVar.set_Temporal_LEN(saved_t)
+        cat = lambda lst: torch.cat(lst, dim=1).reshape(-1, *lst[0].shape[2:])
+        self.forw_L, self.forw_H, self.fake_H, self.sample_H = cat(forw_L), cat(forw_H), cat(fake_H), cat(sample_H)
+
+    def get_current_visuals(self):
+        out = OrderedDict()
+        out["SR"] = self.fake_H.detach()
+        out["LR_ref"] = self.ref_L.detach()
+        out["LR"] = self.forw_L.detach()
+        out["GT"] = self.real_H.detach()
+        out["forw_H"] = self.forw_H.detach()
+        return out
+
+
+def net_quantize(x: torch.Tensor) -> torch.Tensor:
+    """Quantization() of the reference (Quantization.py:19-26) on the CUDA path."""
+    return _engine.quantize(x.contiguous())[1]
+
+
+def create_model(opt):
+    """models/__init__.py:5-15, rescaling branch."""
+    model = opt["model"]
+    if model in ("SelfC_GMM",):
+        m = SelfCModel(opt)
+    else:
+        raise NotImplementedError(f"Model [{model}] not recognized by selfc_b200 (only SelfC_GMM).")
+    logger.info("Model [%s] is created.", m.__class__.__name__)
+    return m

@@ -301,3 +301,65 @@ def test_global_agg_bf16_vs_oracle(dev, h, w, t):
     got, wmat = eng.global_agg("stp_net.global_m2", x.to(dev), t)
     torch.testing.assert_close(wmat.cpu(), wref, rtol=0, atol=1e-5)
     torch.testing.assert_close(got.cpu(), ref, rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ callers (a12, f1)
+def test_gaussian_lr_ref_vs_oracle(dev):
+    from selfc_b200 import engine
+    x = torch.rand(5, 3, 40, 56, generator=torch.Generator().manual_seed(2))
+    got = engine.gaussian_downsample(x.to(dev)).cpu()
+    torch.testing.assert_close(got, so.gaussian_downsample(x), rtol=0, atol=2e-6)
+
+
+def test_model_wrapper_matches_oracle(dev, tmp_path):
+    """create_model(opt) -> feed_data -> test -> get_current_visuals, the call sequence of test_rescaling.py:65-110,
+    with a checkpoint file in the reference's format (DataParallel 'module.' prefix)."""
+    from selfc_b200 import engine, model, options
+    from selfc_b200.global_var import GlobalVar
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sd = so.make_state_dict(12)
+    ckpt = tmp_path / "selfc_large_synthetic.pth"
+    torch.save({"module." + k: v for k, v in sd.items()}, ckpt)
+    opt = options.parse(os.path.join(here, "selfc_b200", "configs", "selfc_large_synthetic.yml"), is_train=False)
+    opt["path"]["pretrain_model_G"] = str(ckpt)
+    opt = options.dict_to_nonedict(opt)
+    b, t, hh, ww = 2, 7, 32, 48
+    GlobalVar.set_Temporal_LEN(t)
+    m = model.create_model(opt)
+    frames = so.make_frames(b, t, hh, ww, 31)                            # [b*t,3,H,W]
+    gt = frames.reshape(b, t, 3, hh, ww).transpose(1, 2).contiguous()    # dataset layout [B,3,T,H,W]
+    m.netG.module.set_noise(seed=5, offset=9)
+    assert m.feed_data({"GT": gt}) == t
+    m.test()
+    vis = m.get_current_visuals()
+    assert set(vis) == {"SR", "LR_ref", "LR", "GT", "forw_H"}
+    eps = engine.export_eps(b, t, hh // 4, ww // 4, seed=5, offset=9, device=dev).cpu()
+    with torch.no_grad():
+        z = so.net_down(sd, frames, t)
+        lr = so.quantize(z[:, :3])
+        hr_ref, _ = so.net_up(sd, lr, eps, t)
+    assert torch.equal(vis["GT"].cpu(), frames)
+    torch.testing.assert_close(vis["LR_ref"].cpu(), so.gaussian_downsample(frames), rtol=0, atol=2e-6)
+    d = (torch.round(vis["LR"].cpu() * 255) - torch.round(lr * 255)).abs()
+    assert d.max().item() <= 1 and (d == 0).float().mean().item() >= 0.9999
+    torch.testing.assert_close(vis["forw_H"].cpu(), z[:, 3:], rtol=0, atol=1e-4)
+    # the wrapper quantised its own LR; feed the oracle the same codes for the HR comparison
+    hr_ref2, _ = so.net_up(sd, vis["LR"].cpu(), eps, t)
+    torch.testing.assert_close(vis["SR"].cpu(), hr_ref2, rtol=0, atol=HR_TOL_FP32)
+
+
+def test_rescale_host_pipeline_matches_per_gop_calls(dev):
+    """The overlapped host-buffer API gives bit-identical results to plain per-GOP calls (incl. the padded tail GOP)."""
+    sd = so.make_state_dict(0)
+    eng = _engine(dev, sd, "bf16")
+    n, hh, ww = 16, 32, 48            # 2 full GOPs + a 2-frame tail
+    frames = so.make_frames(1, n, hh, ww, 3)
+    host_in = frames.pin_memory()
+    lr_h = torch.empty(n, 3, hh // 4, ww // 4, dtype=torch.uint8).pin_memory()
+    hr_h = torch.empty(n, 3, hh, ww).pin_memory()
+    eng.rescale_host(host_in, lr_h, hr_h, 7, seed=3, offset0=10)
+    from selfc_b200.sharding import gop_indices
+    for i, (ids, real) in enumerate(gop_indices(n, 7)):
+        lr_u8, rec = eng.rescale(frames[ids].to(dev), 7, seed=3, offset=10 + i)
+        assert torch.equal(lr_h[ids[0]:ids[0] + real], lr_u8[:real].cpu())
+        assert torch.equal(hr_h[ids[0]:ids[0] + real], rec[:real].cpu())

@@ -1,0 +1,56 @@
+"""Host logic of the multi-GPU path, on CPU: GOP decomposition, contiguous partitioning, and the metric gather under a
+world_size-2 gloo process group (the N>1 path has no data-path collective)."""
+import os
+
+import torch
+import torch.multiprocessing as mp
+
+from selfc_b200 import sharding
+
+
+def test_gop_indices_pad_like_the_reference():
+    g = sharding.gop_indices(100)
+    assert len(g) == 15 and all(len(ids) == 7 for ids, _ in g)
+    assert [r for _, r in g] == [7] * 14 + [2]
+    assert g[-1][0] == [98, 99, 99, 99, 99, 99, 99]
+    assert sharding.gop_indices(7) == [([0, 1, 2, 3, 4, 5, 6], 7)]
+    assert sharding.gop_indices(3)[0] == ([0, 1, 2, 2, 2, 2, 2], 3)
+
+
+def test_partition_covers_every_unit_once():
+    for n in (0, 1, 7, 15, 120, 121):
+        for world in (1, 2, 3, 4, 8):
+            parts = [sharding.partition(n, world, r) for r in range(world)]
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    units = sharding.partition(15, world, rank)                 # 15 GOPs of a 100-frame group
+    local = torch.tensor([[float(u), 2.0 * u, 10.0 + u, 0.5 * u] for u in units])   # 4 metrics per unit
+    allm = sharding.gather_metrics(local)
+    q.put((rank, allm.tolist(), list(units)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_metric_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [[float(u), 2.0 * u, 10.0 + u, 0.5 * u] for u in range(15)]
+    for rank, allm, units in res:
+        assert allm == expect                                   # every rank sees all rows, in unit order
+    assert sorted(u for _, _, units in res for u in units) == list(range(15))
