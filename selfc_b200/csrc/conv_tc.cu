@@ -370,6 +370,9 @@ int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_re
 }
 
 void free_tc_weights(TcConvW& w) {
+  if (w.img2) cudaFree(w.img2);
+  w.img2 = nullptr;
+  w.img2_bytes = 0;
   if (w.img) cudaFree(w.img);
   if (w.bias) cudaFree(w.bias);
   w.img = nullptr;

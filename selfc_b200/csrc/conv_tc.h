@@ -13,10 +13,16 @@ struct TcConvW {
   float* bias = nullptr;    // device, [32]
   size_t img_bytes = 0;
   int cin_buf = 0;          // input channels consumed from the dense buffer (multiple of 16)
+  void* img2 = nullptr;     // device, bf16: A-operand image of conv_tc2.cu (weights in M, kx stacked)
+  size_t img2_bytes = 0;
 };
 
 int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st);
 void free_tc_weights(TcConvW& w);
+// conv_tc2.cu: weights-as-A formulation (default; SELFC_TC_CONV2=0 selects the pixels-as-M kernel of conv_tc.cu)
+bool conv3x3_tc2_enabled();
+int pack_tc2_weights(TcConvW& w, const float* wref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st);
+int launch_conv3x3_tc2(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, int out_off, int N, int h, int wd, cudaStream_t st);
 // conv_k of a dense block, in place: reads channels [0,cin) of buf, writes lrelu(conv+bias) to [out_off,out_off+32)
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, int out_off, int N, int h, int wd, cudaStream_t st);
 

@@ -166,7 +166,10 @@ static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pi
     const int cin = W.xpad + kGrowth * k;
     const double flops = 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;   // algorithmic (unpadded) FLOPs
     if (ctx->mode == SELFC_MODE_BF16 && W.tc[k].img != nullptr) {
-      PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), pitch, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
+      if (conv3x3_tc2_enabled() && W.tc[k].img2 != nullptr)
+        PROF(ctx, st, 0, flops, launch_conv3x3_tc2(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), pitch, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
+      else
+        PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), pitch, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
       continue;
     }
     ConvArgs<T> a;
@@ -570,8 +573,10 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
       W->w[k] = fp(d.w[k]); W->b[k] = fp(d.b[k]); W->np[k] = d.np[k];
       SELFC_TRY(launch_pack_conv_simt(p[d.first + 2 * k], p[d.first + 2 * k + 1], W->w[k], W->b[k], cout, cin_ref, taps, cin_buf,
                                       d.cin, d.xpad, d.np[k], st));
-      if (ctx->mode == SELFC_MODE_BF16 && k < 4)
+      if (ctx->mode == SELFC_MODE_BF16 && k < 4) {
         SELFC_TRY(pack_tc_weights(W->tc[k], p[d.first + 2 * k], p[d.first + 2 * k + 1], cin_ref, cin_buf, d.cin, d.xpad, st));
+        SELFC_TRY(pack_tc2_weights(W->tc[k], p[d.first + 2 * k], cin_ref, cin_buf, d.cin, d.xpad, st));
+      }
       if (ctx->mode == SELFC_MODE_BF16 && k == 4)
         SELFC_TRY(pack_temporal_weights(W->t5, p[d.first + 8], p[d.first + 9], d.cout, cin_ref, 3, cin_buf, d.cin, d.xpad, st));
     }
