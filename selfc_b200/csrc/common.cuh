@@ -21,6 +21,18 @@ constexpr int kSQuads = 12;
 __host__ __device__ __forceinline__ size_t quad_off(size_t M, int quad, size_t m) { return ((size_t)quad * M + m) * 4; }
 constexpr int kStpC = 64;
 
+// Dense-block buffers ("dense buffers") hold the concatenation [X | x1 | x2 | x3 | x4] of a D2DTInput.
+//   pixel-major (fp32 mode):  element (m, c) at  m * pitch + c
+//   slab-planar (bf16 mode):  16-channel slabs [pitch/16][M][16]: element (m, c) at ((c >> 4) * M + m) * 16 + (c & 15)
+// In the slab layout every access of every kernel is contiguous along the pixel index: a conv tile row of 32 pixels of
+// one K-step is one 1 KB run, a conv reads exactly the slabs it consumes (no over-fetch of the channels it does not),
+// and an epilogue's 32 output channels are two 32-byte stores per pixel with consecutive lanes on consecutive addresses.
+// `slabM` = M selects the slab layout, 0 the pixel-major one.  Groups of 4/8/16 channels starting at a multiple of
+// their size never straddle a slab.
+__host__ __device__ __forceinline__ size_t dense_off(long long m, int c, int pitch, long long slabM) {
+  return slabM ? ((size_t)(c >> 4) * (size_t)slabM + (size_t)m) * 16 + (size_t)(c & 15) : (size_t)m * pitch + c;
+}
+
 // ---- error plumbing ---------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 uint64_t& launch_counter();

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
           const float* wm = a.wmat + ((long long)lb * a.Tn) * a.Tn + lt;   // W[b][tt][t'], t' = lt
           for (int tt = 0; tt < a.Tn; ++tt) {
             const float wv = __ldg(wm + tt * a.Tn);
-            float4 r = load4(a.in + (lm + (long long)(tt - lt) * hw) * a.in_pitch + c);
+            float4 r = load4(a.in + dense_off(lm + (long long)(tt - lt) * hw, c, a.in_pitch, a.in_slabM));
             v.x += wv * r.x; v.y += wv * r.y; v.z += wv * r.z; v.w += wv * r.w;
           }
         } else {
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
             ok = (unsigned)(lt + dt) < (unsigned)a.Tn;
             src = lm + (long long)dt * hw;
           }
-          if (ok) v = load4(a.in + src * a.in_pitch + c);
+          if (ok) v = load4(a.in + dense_off(src, c, a.in_pitch, a.in_slabM));
         }
         if (a.in_lrelu) { v.x = lrelu02(v.x); v.y = lrelu02(v.y); v.z = lrelu02(v.z); v.w = lrelu02(v.w); }
       }
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
           for (int j = 0; j < 4; ++j) v[j] = lrelu02(v[j]);
         }
         if (a.outT) {
-          T* o = a.outT + m * a.outT_pitch + a.outT_off + n0;
+          T* o = a.outT + dense_off(m, a.outT_off + n0, a.outT_pitch, a.outT_slabM);
           if (n0 + 4 <= a.cout) store4(o, make_float4(v[0], v[1], v[2], v[3]));
           else
             for (int j = 0; j < 4; ++j)
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
           }
           if (n0 < a.copy_pad) {
             const float4 yv = make_float4(y[0], y[1], y[2], 0.f);
-            if (a.copyA) store4(a.copyA + m * a.copyA_pitch + n0, yv);
-            if (a.copyB) store4(a.copyB + m * a.copyB_pitch + n0, yv);
+            if (a.copyA) store4(a.copyA + dense_off(m, n0, a.copyA_pitch, a.copy_slabM), yv);
+            if (a.copyB) store4(a.copyB + dense_off(m, n0, a.copyB_pitch, a.copy_slabM), yv);
           }
         }
       } break;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
           }
           const float4 yv = make_float4(y[0], y[1], y[2], y[3]);
           store4(zp, yv);
-          if (a.copyA) store4(a.copyA + m * a.copyA_pitch + n0, yv);
+          if (a.copyA) store4(a.copyA + dense_off(m, n0, a.copyA_pitch, a.copy_slabM), yv);
         }
       } break;
       case EPI_GA: {          // out = x + proj1(mix) + bias * colsum(W)   (:266, :278-285 by linearity)
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[j] = rr[j] + acc[i][j] + bias[j] * ws;
           const float4 ov = make_float4(v[0], v[1], v[2], v[3]);
-          if (a.outT) store4(a.outT + m * a.outT_pitch + a.outT_off + n0, ov);
+          if (a.outT) store4(a.outT + dense_off(m, a.outT_off + n0, a.outT_pitch, a.outT_slabM), ov);
           if (a.outF) store4(a.outF + m * a.outF_pitch + a.outF_off + n0, ov);
           if (a.outAct)
             store4(a.outAct + m * a.outAct_pitch + n0, make_float4(lrelu02(v[0]), lrelu02(v[1]), lrelu02(v[2]), lrelu02(v[3])));

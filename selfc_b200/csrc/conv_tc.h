@@ -7,24 +7,19 @@
 namespace selfc {
 
 // One (1,3,3) convolution's weights as the exact shared-memory image the UMMA B-operand descriptors read
-// (see conv_tc.cu), plus its fp32 bias.
+// (see conv_tc3.cu), plus its fp32 bias.
 struct TcConvW {
   void* img = nullptr;      // device, bf16
   float* bias = nullptr;    // device, [32]
   size_t img_bytes = 0;
   int cin_buf = 0;          // input channels consumed from the dense buffer (multiple of 16)
-  void* img2 = nullptr;     // device, bf16: A-operand image of conv_tc2.cu (weights in M, kx stacked)
-  size_t img2_bytes = 0;
 };
 
 int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st);
 void free_tc_weights(TcConvW& w);
-// conv_tc2.cu: weights-as-A formulation (default; SELFC_TC_CONV2=0 selects the pixels-as-M kernel of conv_tc.cu)
-bool conv3x3_tc2_enabled();
-int pack_tc2_weights(TcConvW& w, const float* wref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st);
-int launch_conv3x3_tc2(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, int out_off, int N, int h, int wd, cudaStream_t st);
-// conv_k of a dense block, in place: reads channels [0,cin) of buf, writes lrelu(conv+bias) to [out_off,out_off+32)
-int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, int pitch, int cin, int out_off, int N, int h, int wd, cudaStream_t st);
+// conv_k of a dense block, in place on the slab-planar buffer (slabM = N*h*wd pixels per 16-channel slab): reads
+// channels [0,cin), writes lrelu(conv+bias) to [out_off,out_off+32)   (conv_tc3.cu)
+int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st);
 
 // ---- temporal_tc.cu: (3,1,1) conv5 + coupling epilogues, GlobalAgg apply ---------------------------------------
 struct TcTempW {
@@ -37,9 +32,11 @@ struct TcTempW {
 struct TcTempArgs {
   const __nv_bfloat16* in = nullptr;
   int in_pitch = 0, B = 0, T = 0, hw = 0;
+  long long in_slabM = 0;            // != 0: `in` is a slab-planar dense buffer (common.cuh) of in_slabM pixels per slab
   int epi = 0, rev = 0, act = 0;
   __nv_bfloat16* outT = nullptr;
   int outT_pitch = 0, outT_off = 0;
+  long long outT_slabM = 0, copy_slabM = 0;
   float* outF = nullptr;
   int outF_pitch = 0, outF_off = 0, outF_planar = 0;
   long long m_limit = 0;             // > 0: rows >= m_limit do not exist (pointwise mode over pseudo-frames)

@@ -1,0 +1,438 @@
+// (1,3,3) dense-block convolution conv1..4 of D2DTInput (Subnet_constructor.py:102-105,126-129) as a tcgen05 / TMEM /
+// TMA implicit GEMM over the slab-planar dense buffer (common.cuh), BF16 mode.
+//
+// Formulation: PIXELS are the M dimension (one TMEM lane = one pixel, so the epilogue is thread-per-pixel), the three
+// kx taps are STACKED IN N:
+//     D[p][kx*32 + n] += sum_c X[p + ky*32][c] * W[ky,kx][n][c]        M = 128 halo positions, N = 96, K = 16
+// for ky = 0..2, where p runs over the flattened (rows x 32) halo tile; the ky shift is a start-address offset of 32
+// rows in the A descriptor, the kx shift is applied when the accumulator is read back:
+//     out[r][x][n] = sum_kx D[(r, x + kx)][kx*32 + n]                     -> two warp shuffles (lane = x)
+// So one activation tile load feeds all nine taps, the tile is read from shared memory once per ky (3x, not 9x), and an
+// MMA moves 4 KB (A) + 3 KB (B) of shared memory for 48 cycles of math (the N = 32 formulation moved 5 KB for 16).
+//
+// Data movement: a pipeline stage is `kps` K-steps; ONE 5-D TMA box {16 ch, 32 x, 10 y, 1 frame, kps slabs} brings the
+// (8+2) x 32 halo of an 8 x 30 output tile, every tile row of a K-step being one contiguous 1 KB run of the slab
+// (SWIZZLE_32B rows of 32 bytes; out-of-image rows / columns / slabs are zero-filled by the TMA = the conv padding).
+// DRAM traffic is algorithmic: the conv reads exactly the cin/16 slabs it consumes.
+//
+// Per CTA (persistent, 192 threads): warp 0 TMA producer, warp 1 MMA issuer (whole warp, elected lane), warps 2..5
+// epilogue (TMEM lane quarter q = tile row q of the M-block, lane = x): tcgen05.ld -> shuffle-add the kx partials ->
+// + bias -> LeakyReLU(0.2) -> bf16 -> two 32-byte stores into the output slabs.  Accumulators are double-buffered across
+// tiles (2 tiles x 2 M-blocks x 128 columns), the whole conv's weights stay resident in shared memory.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "conv_tc.h"
+#include "tc_ptx.cuh"
+
+namespace selfc {
+namespace tc3 {
+
+using namespace tc;
+
+constexpr int WT = 32;                        // tile pitch (30 valid columns + 2 halo)
+constexpr int VALID_W = WT - 2;
+constexpr int ROWS = 8;                       // output rows per tile = 2 M-blocks of 4 rows x 32 positions
+constexpr int HT = ROWS + 2;
+constexpr int HALO_POS = HT * WT;             // 320 halo positions = rows of the activation tile
+constexpr int MBLK = 2;
+constexpr int NOUT = 32;
+constexpr int NB = 3 * NOUT;                  // MMA N: kx-major, 96
+constexpr int SUB_BYTES = HALO_POS * 32;      // one K-step sub-tile: 320 rows x 16 bf16, SWIZZLE_32B
+constexpr int WTILE_BYTES = NB * 16 * 2;      // one (ky, K-step) B tile: 96 x 16 bf16 = 3 KB
+constexpr int ACC_STRIDE = 128;               // TMEM columns reserved per accumulator (96 used)
+constexpr int TMEM_COLS = 512;                // 2 tiles x 2 M-blocks x 128
+constexpr int MAX_CIN = 160;
+constexpr int THREADS = 192;
+constexpr int NSTAGE_MAX = 8;
+constexpr int BAR_BYTES = 256;
+
+struct Params {
+  const void* wimg;
+  const float* bias;
+  __nv_bfloat16* buf;
+  long long slabM;       // pixels per slab (= N*h*w)
+  int out_slab, N, h, w, nks, kps;
+  int tiles_x, tiles_y, ntiles;
+  int nst;
+  int* err;
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int NST = p.nst;
+  const int KPS = p.kps;
+  const int STAGE = KPS * SUB_BYTES;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  // [activation stages][barriers][weights]
+  const uint32_t a_base = base;
+  const int bar_off = NST * STAGE;
+  const uint32_t bar_base = base + bar_off;
+  const uint32_t w_base = base + bar_off + BAR_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE_MAX + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * NSTAGE_MAX);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE_MAX + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE_MAX + 3 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE_MAX + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bar_off + 8 * (2 * NSTAGE_MAX + 5));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSTAGE_MAX; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+
+  const int nks = p.nks;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t wbytes = 3u * nks * WTILE_BYTES;
+      mbar_expect_tx(w_bar, wbytes);
+      for (int ky = 0; ky < 3; ++ky)
+        bulk_g2s(w_base + ky * nks * WTILE_BYTES, (const uint8_t*)p.wimg + (size_t)ky * nks * WTILE_BYTES, (uint32_t)nks * WTILE_BYTES,
+                 w_bar);
+      pdl_wait();      // weights are static; activations come from the previous kernel in the stream
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int n = tile / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * VALID_W - 1, y0 = ty * ROWS - 1;
+        for (int c0 = 0; c0 < nks; c0 += KPS) {
+          mbar_wait(empty_bar(s), ph ^ 1u, p.err, 31);
+          mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
+          tma_load_5d(a_base + s * STAGE, &tmap, full_bar(s), 0, x0, y0, n, c0);
+          if (++s == NST) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
+    mbar_wait(w_bar, 0, p.err, 32);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    const uint32_t hi_a = desc_hi(256, 6);            // activations: SWIZZLE_32B rows, 8-row atoms of 256 bytes
+    const uint32_t hi_b = desc_hi(128, 0);            // weights: no-swizzle core matrices, 8-row groups 128 bytes apart
+    const uint32_t b_ky = (uint32_t)nks * (WTILE_BYTES >> 4);
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u, p.err, 33);
+      tc_fence_after();
+      for (int c0 = 0; c0 < nks; c0 += KPS) {
+        const int nk = nks - c0 < KPS ? nks - c0 : KPS;
+        mbar_wait(full_bar(s), ph, p.err, 34);
+        tc_fence_after();
+        const uint32_t a_stage = a_base + s * STAGE;
+        for (int ks = 0; ks < nk; ++ks) {
+          const uint32_t a_lo = desc_lo(a_stage + (uint32_t)ks * SUB_BYTES, 16);
+          // B (weights): (ky, K-step) tiles of 3 KB; the two 8-element K core matrices are 12 row-groups apart
+          const uint32_t b_lo = desc_lo(w_base + (uint32_t)(c0 + ks) * WTILE_BYTES, (NB / 8) * 128);
+#pragma unroll
+          for (int mb = 0; mb < MBLK; ++mb) {
+            const uint32_t d = tmem_base + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              // A rows = flattened halo positions: M-block mb starts at tile row 4*mb, the ky tap one tile row further
+              const uint64_t ad = desc_join(a_lo + (uint32_t)((mb * 128 + ky * WT) * 2), hi_a);
+              const uint64_t bd = desc_join(b_lo + (uint32_t)ky * b_ky, hi_b);
+              umma_bf16_elect(d, ad, bd, idesc, ((c0 + ks) > 0 || ky > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit_elect(empty_bar(s));
+        if (++s == NST) { s = 0; ph ^= 1u; }
+      }
+      umma_commit_elect(tfull_bar(acc));
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;               // TMEM lane quarter = tile row within the M-block; lane = x within the tile
+    pdl_wait();
+    float bias[NOUT];
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) bias[j] = __ldg(p.bias + j);
+    const size_t slab_elems = (size_t)p.slabM * 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int n = tile / (p.tiles_x * p.tiles_y);
+      const int x = tx * VALID_W + lane;
+      mbar_wait(tfull_bar(acc), use & 1u, p.err, 35);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < MBLK; ++mb) {
+        const int y = ty * ROWS + mb * 4 + q;
+        const bool ok = lane < VALID_W && x < p.w && y < p.h;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
+        __nv_bfloat16* o = p.buf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)n * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
+#pragma unroll
+        for (int n0 = 0; n0 < NOUT; n0 += 16) {
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16(trow + (uint32_t)n0, r0);
+          tmem_ld16(trow + (uint32_t)(NOUT + n0), r1);
+          tmem_ld16(trow + (uint32_t)(2 * NOUT + n0), r2);
+          tmem_ld_wait();
+          if (mb == MBLK - 1 && n0 == NOUT - 16) {
+            // both accumulators of this tile are in registers: the next-but-one tile's MMAs may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[j]), 1);
+            const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 2);
+            v[j] = lrelu02(__uint_as_float(r0[j]) + a1 + a2 + bias[n0 + j]);
+          }
+          if (ok) {
+            uint4 lo, hi;
+            lo.x = pack_bf2(v[0], v[1]); lo.y = pack_bf2(v[2], v[3]); lo.z = pack_bf2(v[4], v[5]); lo.w = pack_bf2(v[6], v[7]);
+            hi.x = pack_bf2(v[8], v[9]); hi.y = pack_bf2(v[10], v[11]); hi.z = pack_bf2(v[12], v[13]); hi.w = pack_bf2(v[14], v[15]);
+            __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems;
+            *reinterpret_cast<uint4*>(os) = lo;
+            *reinterpret_cast<uint4*>(os + 8) = hi;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
+  }
+}
+
+// wref [32][cin_ref][3][3] fp32 -> bf16 B-operand image [ky][kstep][kcore(2)][ngroup(12)][r%8][k%8], row r = kx*32 + n
+__global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* __restrict__ img, int cin_ref, int cin_buf, int xreal,
+                                int xpad) {
+  const int nks = cin_buf / 16;
+  const int total = 3 * cin_buf * NB;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int r = idx % NB;
+  const int c = (idx / NB) % cin_buf;
+  const int ky = idx / (NB * cin_buf);
+  const int kx = r / 32, n = r % 32;
+  const int cref = c < xreal ? c : (c < xpad ? -1 : c - xpad + xreal);
+  float v = 0.f;
+  if (cref >= 0 && cref < cin_ref) v = wref[((size_t)n * cin_ref + cref) * 9 + ky * 3 + kx];
+  const int ks = c / 16, kk = c % 16;
+  const size_t off = (size_t)(ky * nks + ks) * (WTILE_BYTES / 2) + (size_t)((kk / 8) * (NB / 8) + r / 8) * 64 + (r % 8) * 8 + (kk % 8);
+  img[off] = __float2bfloat16_rn(v);
+}
+
+}  // namespace tc3
+
+// ---- host-side helpers shared by the tcgen05 kernels -----------------------------------------------------------
+namespace tc {
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int* g_err_flag[64] = {};
+
+int* err_flag_for_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!g_err_flag[dev]) {
+    if (cudaMalloc(&g_err_flag[dev], sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(g_err_flag[dev], 0, sizeof(int));
+  }
+  return g_err_flag[dev];
+}
+
+static long long* g_dbg_dev = nullptr;
+static long long g_dbg_tags[4096];
+static int g_dbg_n = 0;
+bool debug_slots() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SELFC_TC_DBG");
+    on = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
+long long* debug_next_slot(long long tag) {
+  if (!g_dbg_dev) {
+    if (cudaMalloc(&g_dbg_dev, 4096 * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
+    cudaMemset(g_dbg_dev, 0, 4096 * 16 * sizeof(long long));
+  }
+  if (g_dbg_n >= 4096) return nullptr;
+  g_dbg_tags[g_dbg_n] = tag;
+  return g_dbg_dev + 16 * (g_dbg_n++);
+}
+int debug_read(long long* out, int cap) {
+  cudaDeviceSynchronize();
+  int n = g_dbg_n < cap ? g_dbg_n : cap;
+  for (int i = 0; i < n; ++i) {
+    out[17 * i] = g_dbg_tags[i];
+    cudaMemcpy(out + 17 * i + 1, g_dbg_dev + 16 * i, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  }
+  g_dbg_n = 0;
+  return n;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SELFC_NO_PDL");
+    on = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return on == 1;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+}  // namespace tc
+
+int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st) {
+  SELFC_CHECK_ARG(cin_buf % 16 == 0 && cin_buf <= tc3::MAX_CIN, "conv3x3_tc: cin %d must be a multiple of 16 and <= %d", cin_buf,
+                  tc3::MAX_CIN);
+  const size_t bytes = (size_t)3 * (cin_buf / 16) * tc3::WTILE_BYTES;
+  if (w.img == nullptr || w.img_bytes != bytes) {
+    free_tc_weights(w);
+    SELFC_CUDA(cudaMalloc(&w.img, bytes));
+    SELFC_CUDA(cudaMalloc(&w.bias, tc3::NOUT * sizeof(float)));
+    w.img_bytes = bytes;
+  }
+  w.cin_buf = cin_buf;
+  const int total = 3 * cin_buf * tc3::NB;
+  tc3::pack_tc3_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, reinterpret_cast<__nv_bfloat16*>(w.img), cin_ref, cin_buf, xreal, xpad);
+  SELFC_LAUNCH_CHECK("pack_tc3_kernel");
+  SELFC_CUDA(cudaMemcpyAsync(w.bias, bref, tc3::NOUT * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+void free_tc_weights(TcConvW& w) {
+  if (w.img) cudaFree(w.img);
+  if (w.bias) cudaFree(w.bias);
+  w.img = nullptr;
+  w.bias = nullptr;
+  w.img_bytes = 0;
+}
+
+int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st) {
+  SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
+  SELFC_CHECK_ARG(out_off % 16 == 0 && aligned16(buf) && slabM == (long long)N * h * wd, "conv3x3_tc: slab layout / alignment");
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SELFC_E_CUDA;
+  }
+  static int kps_pref = 0;     // SELFC_TC3_KPS: K-steps (16-channel slabs) per pipeline stage / TMA box
+  if (!kps_pref) {
+    const char* e = getenv("SELFC_TC3_KPS");
+    kps_pref = e ? atoi(e) : 2;
+    if (kps_pref < 1 || kps_pref > 4) kps_pref = 2;
+  }
+  const int nks = cin / 16;
+  int kps = kps_pref < nks ? kps_pref : nks;
+  const int fixed = tc3::BAR_BYTES + (int)w.img_bytes + 1024;
+  while (kps > 1 && (227 * 1024 - fixed) / (kps * tc3::SUB_BYTES) < 3) --kps;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {16, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
+  const cuuint64_t gstr[4] = {32, (cuuint64_t)wd * 32, (cuuint64_t)h * wd * 32, (cuuint64_t)slabM * 32};
+  const cuuint32_t box[5] = {16, (cuuint32_t)tc3::WT, (cuuint32_t)tc3::HT, 1, (cuuint32_t)kps};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (%dx%dx%d, %d slabs)", (int)r, N, h, wd, nks);
+    return SELFC_E_CUDA;
+  }
+  tc3::Params p;
+  memset(&p, 0, sizeof(p));
+  p.wimg = w.img;
+  p.bias = w.bias;
+  p.buf = buf;
+  p.slabM = slabM;
+  p.out_slab = out_off / 16;
+  p.N = N;
+  p.h = h;
+  p.w = wd;
+  p.nks = nks;
+  p.kps = kps;
+  p.tiles_x = cdiv(wd, tc3::VALID_W);
+  p.tiles_y = cdiv(h, tc3::ROWS);
+  p.ntiles = p.tiles_x * p.tiles_y * N;
+  p.err = tc::err_flag_for_device();
+  if (p.ntiles == 0) return 0;
+  const int stage = kps * tc3::SUB_BYTES;
+  int nst = (227 * 1024 - fixed) / stage;
+  if (nst > tc3::NSTAGE_MAX) nst = tc3::NSTAGE_MAX;
+  SELFC_CHECK_ARG(nst >= 2, "conv3x3_tc: no room for the activation pipeline (cin %d)", cin);
+  p.nst = nst;
+  const int smem = fixed + nst * stage;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int nsm = tc::num_sms();
+  const int grid = p.ntiles < nsm ? p.ntiles : nsm;
+  SELFC_CUDA(tc::launch_pdl(tc3::conv3x3_tc3_kernel, grid, tc3::THREADS, smem, st, tmap, p));
+  SELFC_LAUNCH_CHECK("conv3x3_tc3_kernel");
+  return 0;
+}
+
+}  // namespace selfc

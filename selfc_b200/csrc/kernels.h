@@ -9,19 +9,20 @@ namespace selfc {
 // ---- layout.cu ------------------------------------------------------------------------------------------
 int launch_fa_fwd_nchw(const float* x, float* out51, int N, int h, int w, cudaStream_t st);
 template <typename T>
-int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, int N, int h, int w, cudaStream_t st);
+int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, long long fslabM, int N, int h, int w, cudaStream_t st);
 int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w, cudaStream_t st);
 int launch_quantize(const float* x, uint8_t* q8, float* qf, size_t n, cudaStream_t st);
 int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q, long long M, long long hw, cudaStream_t st);
 int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st);
 int launch_gaussian_down(const float* x, const float* k13, float* y, int NC, int H, int W, cudaStream_t st);
 template <typename T>
-int launch_nchw_to_dense(const float* x, T* dst, int pitch, int off, int C, int cpad, long long M, long long hw, cudaStream_t st);
+int launch_nchw_to_dense(const float* x, T* dst, int pitch, long long slabM, int off, int C, int cpad, long long M, long long hw,
+                         cudaStream_t st);
 template <typename T>
-int launch_nchw_slice_to_dense(const float* x, int ctot, int c0, T* dst, int pitch, int off, int C, int cpad, long long M,
-                               long long hw, cudaStream_t st);
+int launch_nchw_slice_to_dense(const float* x, int ctot, int c0, T* dst, int pitch, long long slabM, int off, int C, int cpad,
+                               long long M, long long hw, cudaStream_t st);
 template <typename T>
-int launch_dense_to_nchw(const T* src, int pitch, int off, float* y, int C, long long M, long long hw, cudaStream_t st);
+int launch_dense_to_nchw(const T* src, int pitch, long long slabM, int off, float* y, int C, long long M, long long hw, cudaStream_t st);
 
 // ---- conv_simt.cu: fp32-FMA implicit GEMM (strict-fp32 mode and the small GEMMs of both modes) --------------
 enum TapMode { TAP_POINT = 0, TAP_SPATIAL = 1, TAP_TEMPORAL = 2, TAP_TMIX = 3 };
@@ -29,9 +30,10 @@ enum Epilogue { EPI_STORE = 0, EPI_COUPLE_Y1 = 1, EPI_COUPLE_S = 2, EPI_COUPLE_Y
 
 template <typename T>
 struct ConvArgs {
-  // input: pixel-major buffer, channels [0,cin) consumed (cin % 4 == 0)
+  // input: dense buffer (common.cuh: pixel-major, or slab-planar when in_slabM != 0), channels [0,cin) consumed (cin % 4 == 0)
   const T* in = nullptr;
   int in_pitch = 0, cin = 0;
+  long long in_slabM = 0;
   // packed weights [taps*cin][np] fp32 (np % 32 == 0) + bias [np]
   const float* w = nullptr;
   const float* bias = nullptr;
@@ -45,6 +47,7 @@ struct ConvArgs {
   int epi = EPI_STORE, act = 0, rev = 0;
   T* outT = nullptr;
   int outT_pitch = 0, outT_off = 0;
+  long long outT_slabM = 0;
   float* outF = nullptr;
   int outF_pitch = 0, outF_off = 0;
   float* z = nullptr;       // latent state [M][52]
@@ -54,6 +57,7 @@ struct ConvArgs {
   T* copyB = nullptr;
   int copyB_pitch = 0;
   int copy_pad = 0;         // Y1: zero-fill channels [3, copy_pad)
+  long long copy_slabM = 0; // layout of the copyA / copyB dense buffers
   const T* resid = nullptr; // EPI_GA residual
   int resid_pitch = 0;
   T* outAct = nullptr;      // EPI_GA: optional LeakyReLU'd copy of the result (input of the GMM head)

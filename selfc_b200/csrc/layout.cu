@@ -19,7 +19,7 @@ namespace selfc {
 // ------------------------------------------------------------------------------------------------------
 template <bool OUT_NCHW, typename T>
 __global__ void __launch_bounds__(256) fa_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                     T* __restrict__ fbuf, int fpitch, int N, int h, int w) {
+                                                     T* __restrict__ fbuf, int fpitch, long long fslabM, int N, int h, int w) {
   const long long M = (long long)N * h * w;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
@@ -66,10 +66,9 @@ __global__ void __launch_bounds__(256) fa_fwd_kernel(const float* __restrict__ x
     for (int k = 0; k < kZQuads; ++k)
       store4(out + quad_off(M, k, m), make_float4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]));
     if (fbuf != nullptr) {
-      T* f = fbuf + m * fpitch;
 #pragma unroll
       for (int k = 0; k < kHF; k += 4)
-        store4(f + k, make_float4(row[4 + k], row[4 + k + 1], row[4 + k + 2], row[4 + k + 3]));
+        store4(fbuf + dense_off(m, k, fpitch, fslabM), make_float4(row[4 + k], row[4 + k + 1], row[4 + k + 2], row[4 + k + 3]));
     }
   }
 }
@@ -180,22 +179,22 @@ __global__ void __launch_bounds__(256) export_hf_kernel(const float* __restrict_
 // the component entry points.
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void nchw_to_dense_kernel(const float* __restrict__ x, int ctot, int c0, T* __restrict__ dst, int pitch, int off, int C,
-                                     int cpad, long long M, long long hw) {
+__global__ void nchw_to_dense_kernel(const float* __restrict__ x, int ctot, int c0, T* __restrict__ dst, int pitch, long long slabM,
+                                     int off, int C, int cpad, long long M, long long hw) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const long long n = m / hw, pix = m % hw;
-  T* d = dst + m * pitch + off;
-  for (int c = 0; c < cpad; ++c) d[c] = from_f<T>(c < C ? __ldg(x + (n * ctot + c0 + c) * hw + pix) : 0.f);
+  for (int c = 0; c < cpad; ++c)
+    dst[dense_off(m, off + c, pitch, slabM)] = from_f<T>(c < C ? __ldg(x + (n * ctot + c0 + c) * hw + pix) : 0.f);
 }
 
 template <typename T>
-__global__ void dense_to_nchw_kernel(const T* __restrict__ src, int pitch, int off, float* __restrict__ y, int C, long long M, long long hw) {
+__global__ void dense_to_nchw_kernel(const T* __restrict__ src, int pitch, long long slabM, int off, float* __restrict__ y, int C,
+                                     long long M, long long hw) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const long long n = m / hw, pix = m % hw;
-  const T* s = src + m * pitch + off;
-  for (int c = 0; c < C; ++c) y[(n * C + c) * hw + pix] = to_f(s[c]);
+  for (int c = 0; c < C; ++c) y[(n * C + c) * hw + pix] = to_f(src[dense_off(m, off + c, pitch, slabM)]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -238,20 +237,20 @@ int launch_gaussian_down(const float* x, const float* k13, float* y, int NC, int
 // ---- launchers ----------------------------------------------------------------------------------------
 int launch_fa_fwd_nchw(const float* x, float* out51, int N, int h, int w, cudaStream_t st) {
   long long M = (long long)N * h * w;
-  fa_fwd_kernel<true, float><<<cdiv(M, 256), 256, 0, st>>>(x, out51, nullptr, 0, N, h, w);
+  fa_fwd_kernel<true, float><<<cdiv(M, 256), 256, 0, st>>>(x, out51, nullptr, 0, 0, N, h, w);
   SELFC_LAUNCH_CHECK("fa_fwd_kernel<nchw>");
   return 0;
 }
 
 template <typename T>
-int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, int N, int h, int w, cudaStream_t st) {
+int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, long long fslabM, int N, int h, int w, cudaStream_t st) {
   long long M = (long long)N * h * w;
-  fa_fwd_kernel<false, T><<<cdiv(M, 256), 256, 0, st>>>(x, z, fbuf, fpitch, N, h, w);
+  fa_fwd_kernel<false, T><<<cdiv(M, 256), 256, 0, st>>>(x, z, fbuf, fpitch, fslabM, N, h, w);
   SELFC_LAUNCH_CHECK("fa_fwd_kernel<z>");
   return 0;
 }
-template int launch_fa_fwd_z<float>(const float*, float*, float*, int, int, int, int, cudaStream_t);
-template int launch_fa_fwd_z<__nv_bfloat16>(const float*, float*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+template int launch_fa_fwd_z<float>(const float*, float*, float*, int, long long, int, int, int, cudaStream_t);
+template int launch_fa_fwd_z<__nv_bfloat16>(const float*, float*, __nv_bfloat16*, int, long long, int, int, int, cudaStream_t);
 
 int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w, cudaStream_t st) {
   long long M = (long long)N * h * w;
@@ -281,31 +280,34 @@ int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaS
 }
 
 template <typename T>
-int launch_nchw_to_dense(const float* x, T* dst, int pitch, int off, int C, int cpad, long long M, long long hw, cudaStream_t st) {
-  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, C, 0, dst, pitch, off, C, cpad, M, hw);
+int launch_nchw_to_dense(const float* x, T* dst, int pitch, long long slabM, int off, int C, int cpad, long long M, long long hw,
+                         cudaStream_t st) {
+  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, C, 0, dst, pitch, slabM, off, C, cpad, M, hw);
   SELFC_LAUNCH_CHECK("nchw_to_dense_kernel");
   return 0;
 }
 template <typename T>
-int launch_nchw_slice_to_dense(const float* x, int ctot, int c0, T* dst, int pitch, int off, int C, int cpad, long long M,
-                               long long hw, cudaStream_t st) {
-  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, ctot, c0, dst, pitch, off, C, cpad, M, hw);
+int launch_nchw_slice_to_dense(const float* x, int ctot, int c0, T* dst, int pitch, long long slabM, int off, int C, int cpad,
+                               long long M, long long hw, cudaStream_t st) {
+  nchw_to_dense_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(x, ctot, c0, dst, pitch, slabM, off, C, cpad, M, hw);
   SELFC_LAUNCH_CHECK("nchw_to_dense_kernel");
   return 0;
 }
-template int launch_nchw_slice_to_dense<float>(const float*, int, int, float*, int, int, int, int, long long, long long, cudaStream_t);
-template int launch_nchw_slice_to_dense<__nv_bfloat16>(const float*, int, int, __nv_bfloat16*, int, int, int, int, long long, long long,
-                                                       cudaStream_t);
-template int launch_nchw_to_dense<float>(const float*, float*, int, int, int, int, long long, long long, cudaStream_t);
-template int launch_nchw_to_dense<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, int, int, long long, long long, cudaStream_t);
+template int launch_nchw_slice_to_dense<float>(const float*, int, int, float*, int, long long, int, int, int, long long, long long,
+                                               cudaStream_t);
+template int launch_nchw_slice_to_dense<__nv_bfloat16>(const float*, int, int, __nv_bfloat16*, int, long long, int, int, int, long long,
+                                                       long long, cudaStream_t);
+template int launch_nchw_to_dense<float>(const float*, float*, int, long long, int, int, int, long long, long long, cudaStream_t);
+template int launch_nchw_to_dense<__nv_bfloat16>(const float*, __nv_bfloat16*, int, long long, int, int, int, long long, long long,
+                                                 cudaStream_t);
 
 template <typename T>
-int launch_dense_to_nchw(const T* src, int pitch, int off, float* y, int C, long long M, long long hw, cudaStream_t st) {
-  dense_to_nchw_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(src, pitch, off, y, C, M, hw);
+int launch_dense_to_nchw(const T* src, int pitch, long long slabM, int off, float* y, int C, long long M, long long hw, cudaStream_t st) {
+  dense_to_nchw_kernel<T><<<cdiv(M, 256), 256, 0, st>>>(src, pitch, slabM, off, y, C, M, hw);
   SELFC_LAUNCH_CHECK("dense_to_nchw_kernel");
   return 0;
 }
-template int launch_dense_to_nchw<float>(const float*, int, int, float*, int, long long, long long, cudaStream_t);
-template int launch_dense_to_nchw<__nv_bfloat16>(const __nv_bfloat16*, int, int, float*, int, long long, long long, cudaStream_t);
+template int launch_dense_to_nchw<float>(const float*, int, long long, int, float*, int, long long, long long, cudaStream_t);
+template int launch_dense_to_nchw<__nv_bfloat16>(const __nv_bfloat16*, int, long long, int, float*, int, long long, long long, cudaStream_t);
 
 }  // namespace selfc

@@ -158,36 +158,37 @@ struct Dims {
   long long hw() const { return (long long)h * w; }
 };
 
+// layout of the dense-block buffers (common.cuh): slab-planar in BF16 mode, pixel-major in FP32 mode
+static long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->mode == SELFC_MODE_BF16 ? d.M() : 0; }
+
 // ---- dense block: conv1..4 in place, then conv5 with the given epilogue ---------------------------------------
 template <typename T>
 static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pitch, const Dims& d, cudaStream_t st, int k_first = 0,
                            int k_last = 3) {
+  const long long slabM = dense_slab(ctx, d);
   for (int k = k_first; k <= k_last; ++k) {
     const int cin = W.xpad + kGrowth * k;
     const double flops = 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;   // algorithmic (unpadded) FLOPs
     if (ctx->mode == SELFC_MODE_BF16 && W.tc[k].img != nullptr) {
-      if (conv3x3_tc2_enabled() && W.tc[k].img2 != nullptr)
-        PROF(ctx, st, 0, flops, launch_conv3x3_tc2(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), pitch, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
-      else
-        PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), pitch, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
+      PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), slabM, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
       continue;
     }
     ConvArgs<T> a;
-    a.in = buf; a.in_pitch = pitch; a.cin = cin;
+    a.in = buf; a.in_pitch = pitch; a.cin = cin; a.in_slabM = slabM;
     a.w = W.w[k]; a.bias = W.b[k]; a.np = W.np[k]; a.cout = kGrowth;
     a.taps = 9; a.tap_mode = TAP_SPATIAL;
     a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
     a.epi = EPI_STORE; a.act = 1;
-    a.outT = buf; a.outT_pitch = pitch; a.outT_off = cin;
+    a.outT = buf; a.outT_pitch = pitch; a.outT_off = cin; a.outT_slabM = slabM;
     PROF(ctx, st, 0, flops, launch_conv_simt<T>(a, st));
   }
   return 0;
 }
 
 template <typename T>
-static ConvArgs<T> conv5_args(const DenseW& W, const T* buf, int pitch, const Dims& d) {
+static ConvArgs<T> conv5_args(const selfc_ctx* ctx, const DenseW& W, const T* buf, int pitch, const Dims& d) {
   ConvArgs<T> a;
-  a.in = buf; a.in_pitch = pitch; a.cin = W.xpad + 4 * kGrowth;
+  a.in = buf; a.in_pitch = pitch; a.cin = W.xpad + 4 * kGrowth; a.in_slabM = dense_slab(ctx, d);
   a.w = W.w[4]; a.bias = W.b[4]; a.np = W.np[4]; a.cout = W.cout;
   a.taps = 3; a.tap_mode = TAP_TEMPORAL;
   a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
@@ -202,9 +203,9 @@ static int launch_temporal(const selfc_ctx* ctx, const TcTempW& tw, const ConvAr
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     if (ctx->mode == SELFC_MODE_BF16 && temporal_tc_supported(tw, d.T)) {
       TcTempArgs t;
-      t.in = a.in; t.in_pitch = a.in_pitch; t.B = d.B; t.T = d.T; t.hw = (int)d.hw();
+      t.in = a.in; t.in_pitch = a.in_pitch; t.B = d.B; t.T = d.T; t.hw = (int)d.hw(); t.in_slabM = a.in_slabM;
       t.epi = a.epi; t.rev = a.rev; t.act = a.act;
-      t.outT = a.outT; t.outT_pitch = a.outT_pitch; t.outT_off = a.outT_off;
+      t.outT = a.outT; t.outT_pitch = a.outT_pitch; t.outT_off = a.outT_off; t.outT_slabM = a.outT_slabM; t.copy_slabM = a.copy_slabM;
       t.outF = a.outF; t.outF_pitch = a.outF_pitch;
       t.z = a.z; t.sbuf = a.sbuf;
       t.copyA = a.copyA; t.copyA_pitch = a.copyA_pitch; t.copyB = a.copyB; t.copyB_pitch = a.copyB_pitch; t.copy_pad = a.copy_pad;
@@ -229,21 +230,22 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
   const DenseW& H = ctx->inv[blk][2];
   auto do_F = [&]() -> int {
     SELFC_TRY(run_dense_convs<T>(ctx, F, fbuf, ws.fpitch, d, st));
-    ConvArgs<T> a = conv5_args<T>(F, fbuf, ws.fpitch, d);
+    ConvArgs<T> a = conv5_args<T>(ctx, F, fbuf, ws.fpitch, d);
     a.epi = EPI_COUPLE_Y1; a.rev = rev ? 1 : 0; a.z = z;
     a.copyA = gbuf; a.copyA_pitch = ws.gpitch; a.copyB = hbuf; a.copyB_pitch = ws.gpitch; a.copy_pad = ctx->xpad3;
+    a.copy_slabM = dense_slab(ctx, d);
     PROF(ctx, st, 1, conv5_flops(F, d), launch_temporal<T>(ctx, F.t5, a, d, st));
     return 0;
   };
   auto do_HG = [&]() -> int {
     SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st));
-    ConvArgs<T> a = conv5_args<T>(H, hbuf, ws.gpitch, d);
+    ConvArgs<T> a = conv5_args<T>(ctx, H, hbuf, ws.gpitch, d);
     a.epi = EPI_COUPLE_S; a.sbuf = sbuf;
     PROF(ctx, st, 1, conv5_flops(H, d), launch_temporal<T>(ctx, H.t5, a, d, st));
     SELFC_TRY(run_dense_convs<T>(ctx, G, gbuf, ws.gpitch, d, st));
-    ConvArgs<T> g = conv5_args<T>(G, gbuf, ws.gpitch, d);
+    ConvArgs<T> g = conv5_args<T>(ctx, G, gbuf, ws.gpitch, d);
     g.epi = EPI_COUPLE_Y2; g.rev = rev ? 1 : 0; g.z = z; g.sbuf = sbuf;
-    g.copyA = fbuf; g.copyA_pitch = ws.fpitch;
+    g.copyA = fbuf; g.copyA_pitch = ws.fpitch; g.copy_slabM = dense_slab(ctx, d);
     PROF(ctx, st, 1, conv5_flops(G, d), launch_temporal<T>(ctx, G.t5, g, d, st));
     return 0;
   };
@@ -259,8 +261,8 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
 
 // GlobalAgg (SelfC_GMM_arch_inv.py:265-285): x = feat [M][64]; result -> outT (pitch/off) and/or outF
 template <typename T>
-static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* outT, int outT_pitch, float* outF, int outF_pitch,
-                          float* wmat_copy, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st, T* outAct = nullptr) {
+static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* outT, int outT_pitch, long long outT_slabM, float* outF,
+                          int outF_pitch, float* wmat_copy, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st, T* outAct = nullptr) {
   float* wmap = reinterpret_cast<float*>(wsp + ws.wmap);
   float* partial = reinterpret_cast<float*>(wsp + ws.partial);
   float* wmat = reinterpret_cast<float*>(wsp + ws.wmat);
@@ -277,7 +279,7 @@ static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* 
   a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
   a.wmat = wmat; a.wsum = wsum;
   a.epi = EPI_GA; a.resid = feat; a.resid_pitch = kStpC;
-  a.outT = outT; a.outT_pitch = outT_pitch; a.outT_off = 0;
+  a.outT = outT; a.outT_pitch = outT_pitch; a.outT_off = 0; a.outT_slabM = outT_slabM;
   a.outF = outF; a.outF_pitch = outF_pitch; a.outF_off = 0;
   a.outAct = outAct; a.outAct_pitch = kStpC;
   PROF(ctx, st, 2, 2.0 * px_bytes, launch_temporal<T>(ctx, g.tp, a, d, st));
@@ -289,7 +291,7 @@ static int down_impl(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_
                      const Workspace& ws, cudaStream_t st) {
   float* z = reinterpret_cast<float*>(wsp + ws.z);
   T* fbuf = reinterpret_cast<T*>(wsp + ws.fbuf);
-  PROF(ctx, st, 5, (double)d.M() * (16 * 3 * 4 + 51 * 4), launch_fa_fwd_z<T>(hr, z, fbuf, ws.fpitch, d.B * d.T, d.h, d.w, st));
+  PROF(ctx, st, 5, (double)d.M() * (16 * 3 * 4 + 51 * 4), launch_fa_fwd_z<T>(hr, z, fbuf, ws.fpitch, dense_slab(ctx, d), d.B * d.T, d.h, d.w, st));
   for (int blk = 0; blk < 8; ++blk) SELFC_TRY(run_invblock<T>(ctx, blk, false, wsp, ws, d, st));
   PROF(ctx, st, 5, (double)d.M() * (51 * 4 + (out51 ? 51 * 4 : 0) + 3), launch_export_down(z, out51, lr_u8, lr_q, d.M(), d.hw(), st));
   return 0;
@@ -309,20 +311,21 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   float* params = reinterpret_cast<float*>(wsp + ws.params);
   const long long M = d.M(), hw = d.hw();
   const int xp = ctx->xpad3;
+  const long long slabM = dense_slab(ctx, d);
   // LR ingest: x1 of the reversed block 8, and the X slot of local_m1
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<float>(lr, z, 4, 0, 3, 4, M, hw, st));
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, gbuf, ws.gpitch, 0, 3, xp, M, hw, st));
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, hbuf, ws.gpitch, 0, 3, xp, M, hw, st));
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, stpbuf, ws.gpitch, 0, 3, xp, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<float>(lr, z, 4, 0, 0, 3, 4, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, gbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, hbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
+  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, stpbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
   // STPNet.forward (:366-374)
   for (int i = 0; i < 6; ++i) {
     const DenseW& W = ctx->stp[i];
     const int pitch = i == 0 ? ws.gpitch : ws.spitch;
     SELFC_TRY(run_dense_convs<T>(ctx, W, stpbuf, pitch, d, st));
-    ConvArgs<T> a = conv5_args<T>(W, stpbuf, pitch, d);
+    ConvArgs<T> a = conv5_args<T>(ctx, W, stpbuf, pitch, d);
     a.epi = EPI_STORE; a.act = 0; a.outT = feat; a.outT_pitch = kStpC; a.outT_off = 0;
     PROF(ctx, st, 1, conv5_flops(W, d), launch_temporal<T>(ctx, W.t5, a, d, st));
-    SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, nullptr, 0, nullptr, wsp, ws, d, st,
+    SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, slabM, nullptr, 0, nullptr, wsp, ws, d, st,
                                 i == 5 ? fact : nullptr));
   }
   // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
@@ -350,11 +353,11 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
     ConvArgs<T> a;
     a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
     a.taps = 1; a.tap_mode = TAP_POINT; a.epi = EPI_STORE;
-    a.in = stpbuf; a.in_pitch = ws.spitch; a.cin = 64; a.in_lrelu = 1;
+    a.in = stpbuf; a.in_pitch = ws.spitch; a.cin = 64; a.in_lrelu = 1; a.in_slabM = slabM;
     a.w = ctx->head.w[0]; a.bias = ctx->head.b[0]; a.np = ctx->head.np[0]; a.cout = 128;
     a.act = 1; a.outT = h1; a.outT_pitch = 128;
     PROF(ctx, st, 3, 2.0 * M * 64 * 128, launch_conv_simt<T>(a, st));
-    a.in = h1; a.in_pitch = 128; a.cin = 128; a.in_lrelu = 0;
+    a.in = h1; a.in_pitch = 128; a.cin = 128; a.in_lrelu = 0; a.in_slabM = 0;
     a.w = ctx->head.w[1]; a.bias = ctx->head.b[1]; a.np = ctx->head.np[1]; a.cout = 256;
     a.outT = h2; a.outT_pitch = 256;
     PROF(ctx, st, 3, 2.0 * M * 128 * 256, launch_conv_simt<T>(a, st));
@@ -400,12 +403,12 @@ static int d2dt_impl(selfc_ctx* ctx, const DenseW& W, const float* x, float* y, 
   T* buf = reinterpret_cast<T*>(wsp + ws.stpbuf);
   float* tmp = reinterpret_cast<float*>(wsp + ws.params);
   const int pitch = W.xpad + 4 * kGrowth;
-  SELFC_TRY(launch_nchw_to_dense<T>(x, buf, pitch, 0, W.cin, W.xpad, d.M(), d.hw(), st));
+  SELFC_TRY(launch_nchw_to_dense<T>(x, buf, pitch, dense_slab(ctx, d), 0, W.cin, W.xpad, d.M(), d.hw(), st));
   SELFC_TRY(run_dense_convs<T>(ctx, W, buf, pitch, d, st));
-  ConvArgs<T> a = conv5_args<T>(W, buf, pitch, d);
+  ConvArgs<T> a = conv5_args<T>(ctx, W, buf, pitch, d);
   a.epi = EPI_STORE; a.outF = tmp; a.outF_pitch = 64;
   SELFC_TRY(launch_temporal<T>(ctx, W.t5, a, d, st));
-  return launch_dense_to_nchw<float>(tmp, 64, 0, y, W.cout, d.M(), d.hw(), st);
+  return launch_dense_to_nchw<float>(tmp, 64, 0, 0, y, W.cout, d.M(), d.hw(), st);
 }
 
 template <typename T>
@@ -414,10 +417,12 @@ static int conv3x3_impl(selfc_ctx* ctx, const DenseW& W, int k, const float* x, 
   T* buf = reinterpret_cast<T*>(wsp + ws.stpbuf);
   const int pitch = W.xpad + 4 * kGrowth;
   const int cref = W.cin + kGrowth * k;
-  SELFC_TRY(launch_nchw_slice_to_dense<T>(x, cref, 0, buf, pitch, 0, W.cin, W.xpad, d.M(), d.hw(), st));
-  if (k > 0) SELFC_TRY(launch_nchw_slice_to_dense<T>(x, cref, W.cin, buf, pitch, W.xpad, kGrowth * k, kGrowth * k, d.M(), d.hw(), st));
+  const long long slabM = dense_slab(ctx, d);
+  SELFC_TRY(launch_nchw_slice_to_dense<T>(x, cref, 0, buf, pitch, slabM, 0, W.cin, W.xpad, d.M(), d.hw(), st));
+  if (k > 0)
+    SELFC_TRY(launch_nchw_slice_to_dense<T>(x, cref, W.cin, buf, pitch, slabM, W.xpad, kGrowth * k, kGrowth * k, d.M(), d.hw(), st));
   SELFC_TRY(run_dense_convs<T>(ctx, W, buf, pitch, d, st, k, k));
-  return launch_dense_to_nchw<T>(buf, pitch, W.xpad + kGrowth * k, y, kGrowth, d.M(), d.hw(), st);
+  return launch_dense_to_nchw<T>(buf, pitch, slabM, W.xpad + kGrowth * k, y, kGrowth, d.M(), d.hw(), st);
 }
 
 template <typename T>
@@ -425,9 +430,9 @@ static int ga_impl(selfc_ctx* ctx, const GaW& g, const float* x, float* y, float
                    const Workspace& ws, cudaStream_t st) {
   T* feat = reinterpret_cast<T*>(wsp + ws.feat);
   float* tmp = reinterpret_cast<float*>(wsp + ws.params);
-  SELFC_TRY(launch_nchw_to_dense<T>(x, feat, kStpC, 0, kStpC, kStpC, d.M(), d.hw(), st));
-  SELFC_TRY(run_global_agg<T>(ctx, g, feat, nullptr, 0, tmp, 64, wmat_out, wsp, ws, d, st));
-  return launch_dense_to_nchw<float>(tmp, 64, 0, y, kStpC, d.M(), d.hw(), st);
+  SELFC_TRY(launch_nchw_to_dense<T>(x, feat, kStpC, 0, 0, kStpC, kStpC, d.M(), d.hw(), st));
+  SELFC_TRY(run_global_agg<T>(ctx, g, feat, nullptr, 0, 0, tmp, 64, wmat_out, wsp, ws, d, st));
+  return launch_dense_to_nchw<float>(tmp, 64, 0, 0, y, kStpC, d.M(), d.hw(), st);
 }
 
 }  // namespace selfc
@@ -575,7 +580,6 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
                                       d.cin, d.xpad, d.np[k], st));
       if (ctx->mode == SELFC_MODE_BF16 && k < 4) {
         SELFC_TRY(pack_tc_weights(W->tc[k], p[d.first + 2 * k], p[d.first + 2 * k + 1], cin_ref, cin_buf, d.cin, d.xpad, st));
-        SELFC_TRY(pack_tc2_weights(W->tc[k], p[d.first + 2 * k], cin_ref, cin_buf, d.cin, d.xpad, st));
       }
       if (ctx->mode == SELFC_MODE_BF16 && k == 4)
         SELFC_TRY(pack_temporal_weights(W->t5, p[d.first + 8], p[d.first + 9], d.cout, cin_ref, 3, cin_buf, d.cin, d.xpad, st));

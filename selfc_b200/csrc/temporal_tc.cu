@@ -45,8 +45,10 @@ struct Params {
   int tiles_p, ntiles, tmem_cols;
   long long m_limit;   // rows (pixels) that really exist in the buffer
   int epi, rev, act;
+  int in_slab;                                // input is a slab-planar dense buffer (common.cuh): 4-D TMA, SWIZZLE_32B sub-tiles
   __nv_bfloat16* outT;
   int outT_pitch, outT_off;
+  long long outT_slabM, copy_slabM;           // layouts of outT and of copyA / copyB (0 = pixel-major)
   float* outF;
   int outF_pitch, outF_off, outF_planar;   // outF_planar: write quads [C/4][m_limit][4] instead of [M][pitch]
   float* z;
@@ -227,8 +229,10 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
             const int nf = T - t0 < FPS ? T - t0 : FPS;
             timed_wait(empty_bar(s), ph ^ 1u, p.err, 11, w_prod);
             mbar_expect_tx(full_bar(s), (uint32_t)nf * FRAME_BYTES);
-            for (int f = 0; f < nf; ++f)
-              tma_load_3d(a_base + s * STAGE_BYTES + f * FRAME_BYTES, &tmap, full_bar(s), c * KC, p0, b * T + t0 + f);
+            for (int f = 0; f < nf; ++f) {
+              if (p.in_slab) tma_load_4d(a_base + s * STAGE_BYTES + f * FRAME_BYTES, &tmap, full_bar(s), 0, p0, b * T + t0 + f, c * KSTEPS);
+              else tma_load_3d(a_base + s * STAGE_BYTES + f * FRAME_BYTES, &tmap, full_bar(s), c * KC, p0, b * T + t0 + f);
+            }
             if (++s == NST) { s = 0; ph ^= 1u; }
           }
         }
@@ -239,6 +243,10 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
     {
       // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
       const uint32_t idesc = umma_idesc_bf16(128, npad);
+      // pixel-major input: one swizzled row of KC channels per pixel, a K step advances 32 bytes inside the row;
+      // slab input: KSTEPS sub-tiles of [128 px][16 ch] (SWIZZLE_32B, 4 KB each), a K step advances one sub-tile
+      const uint32_t hi_a = p.in_slab ? desc_hi(256, 6) : desc_hi(SBO, LAYOUT);
+      const uint32_t a_kinc = p.in_slab ? (uint32_t)(MT * 32 >> 4) : 2u;
       long long w_full = 0, w_tempty = 0;
       const long long t_start = clock64();
       mbar_wait(w_bar, 0, p.err, 12);
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
               const uint32_t dcol = tmem_base + (uint32_t)(to * npad);
               for (int ks = 0; ks < ksn; ++ks) {
                 // A: +32 bytes per K step inside the 128-byte swizzled row; B: next 16-channel weight tile
-                const uint64_t ad = desc_join(a_lo + 2u * (uint32_t)ks, desc_hi(SBO, LAYOUT));
+                const uint64_t ad = desc_join(a_lo + a_kinc * (uint32_t)ks, hi_a);
                 const uint64_t bd = desc_join(b_lo + (uint32_t)ks * (wtile >> 4), desc_hi(128, 0));
                 umma_bf16_elect(dcol, ad, bd, idesc, (started >> to & 1u) ? 1u : 0u);
                 started |= 1u << to;
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                   for (int j = 0; j < 8; ++j) v[j] = fmaf(wv, __uint_as_float(d[t][j]), v[j]);
                 }
               }
-              if (p.outT) store_bf16x8(p.outT + m * p.outT_pitch + p.outT_off + n0, v);
+              if (p.outT) store_bf16x8(p.outT + dense_off((long long)m, p.outT_off + n0, p.outT_pitch, p.outT_slabM), v);
               if (p.outF) {
                 float* o = p.outF + m * p.outF_pitch + n0;
                 store4(o, make_float4(v[0], v[1], v[2], v[3]));
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                 for (int j = 0; j < 16; ++j) v[j] = lrelu02(v[j]);
               }
               if (p.outT) {
-                __nv_bfloat16* o = p.outT + m * p.outT_pitch + p.outT_off + n0;
+                __nv_bfloat16* o = p.outT + dense_off((long long)m, p.outT_off + n0, p.outT_pitch, p.outT_slabM);
                 if (n0 + 16 <= p.cout) {
                   store_bf16x8(o, v);
                   store_bf16x8(o + 8, v + 8);
@@ -435,12 +443,14 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
               y[2] = p.rev ? x1.z - v[2] : x1.z + v[2];
               store4(zp, make_float4(y[0], y[1], y[2], 0.f));
               if (p.copyA) {
-                store_bf16x8(p.copyA + m * p.copyA_pitch, y);
-                if (p.copy_pad > 8) store_bf16x8(p.copyA + m * p.copyA_pitch + 8, y + 8);
+                __nv_bfloat16* o = p.copyA + dense_off((long long)m, 0, p.copyA_pitch, p.copy_slabM);
+                store_bf16x8(o, y);
+                if (p.copy_pad > 8) store_bf16x8(o + 8, y + 8);
               }
               if (p.copyB) {
-                store_bf16x8(p.copyB + m * p.copyB_pitch, y);
-                if (p.copy_pad > 8) store_bf16x8(p.copyB + m * p.copyB_pitch + 8, y + 8);
+                __nv_bfloat16* o = p.copyB + dense_off((long long)m, 0, p.copyB_pitch, p.copy_slabM);
+                store_bf16x8(o, y);
+                if (p.copy_pad > 8) store_bf16x8(o + 8, y + 8);
               }
             } break;
             case EPI_COUPLE_S: {
@@ -469,8 +479,9 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                 store4(zp + j, make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]));
               }
               if (p.copyA) {
-                store_bf16x8(p.copyA + m * p.copyA_pitch + n0, y);
-                store_bf16x8(p.copyA + m * p.copyA_pitch + n0 + 8, y + 8);
+                __nv_bfloat16* o = p.copyA + dense_off((long long)m, n0, p.copyA_pitch, p.copy_slabM);
+                store_bf16x8(o, y);
+                store_bf16x8(o + 8, y + 8);
               }
             } break;
             default: break;
@@ -556,21 +567,33 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   const int BT = a.B * a.T;
   SELFC_CHECK_ARG(a.epi != EPI_GA || w.npad <= 64, "temporal_tc: GlobalAgg epilogue needs N <= 64");
   CUtensorMap tmap;
-  const cuuint64_t gdim[3] = {(cuuint64_t)a.in_pitch, (cuuint64_t)a.hw, (cuuint64_t)BT};
-  const cuuint64_t gstr[2] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.hw * a.in_pitch * 2};
   static int kc = 0;     // SELFC_TC_KC = 64 | 32 | 16 selects the swizzle width of the A operand (experiment knob)
   if (!kc) {
     const char* e = getenv("SELFC_TC_KC");
     kc = e ? atoi(e) : tc5::KC_DEFAULT;
     if (kc != 64 && kc != 32 && kc != 16) kc = tc5::KC_DEFAULT;
   }
-  const cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)tc5::MT, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (a.in_slabM) {
+    // slab-planar dense buffer [cin/16][M][16]: box = 128 pixels of one frame x kc/16 slabs, each slab's rows one 4 KB run
+    SELFC_CHECK_ARG(a.in_slabM == (long long)BT * a.hw, "temporal_tc: slab stride %lld != B*T*hw", a.in_slabM);
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)a.hw, (cuuint64_t)BT, (cuuint64_t)(w.cin_buf / 16)};
+    const cuuint64_t gstr[3] = {32, (cuuint64_t)a.hw * 32, (cuuint64_t)a.in_slabM * 32};
+    const cuuint32_t box[4] = {16, (cuuint32_t)tc5::MT, 1, (cuuint32_t)(kc / 16)};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.in_pitch, (cuuint64_t)a.hw, (cuuint64_t)BT};
+    const cuuint64_t gstr[2] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.hw * a.in_pitch * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)tc5::MT, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE,
+               kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (temporal) failed with CUresult %d", (int)r);
     return SELFC_E_CUDA;
@@ -585,7 +608,9 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   p.epi = a.epi; p.rev = a.rev; p.act = a.act;
+  p.in_slab = a.in_slabM ? 1 : 0;
   p.outT = a.outT; p.outT_pitch = a.outT_pitch; p.outT_off = a.outT_off;
+  p.outT_slabM = a.outT_slabM; p.copy_slabM = a.copy_slabM;
   p.outF = a.outF; p.outF_pitch = a.outF_pitch; p.outF_off = a.outF_off; p.outF_planar = a.outF_planar;
   p.m_limit = a.m_limit > 0 ? a.m_limit : (long long)BT * a.hw;
   p.z = a.z; p.sbuf = a.sbuf;
