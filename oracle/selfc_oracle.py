@@ -393,16 +393,30 @@ def philox4x32_10(c, k):
     return np.stack(c, -1).astype(np.uint32)
 
 
-def philox_normal(idx: np.ndarray, seed: int, offset: int) -> np.ndarray:
-    """eps element `idx` of stream (seed, offset): counter (idx_lo, idx_hi, off_lo, off_hi), key (seed_lo, seed_hi),
-    Box-Muller cosine branch on the first two output words, in float32 like the device code."""
-    idx = np.asarray(idx, dtype=np.uint64)
-    ctr = np.stack([idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32),
-                    np.full_like(idx, offset & 0xFFFFFFFF), np.full_like(idx, (offset >> 32) & 0xFFFFFFFF)], -1).astype(np.uint32)
-    key = np.stack([np.full_like(idx, seed & 0xFFFFFFFF), np.full_like(idx, (seed >> 32) & 0xFFFFFFFF)], -1).astype(np.uint32)
+def philox_normal4(g: np.ndarray, seed: int, offset: int) -> np.ndarray:
+    """The four normals of Philox call `g` of stream (seed, offset) (common.cuh: philox_normal4): counter
+    (g_lo, g_hi, off_lo, off_hi), key (seed_lo, seed_hi); Box-Muller on words (0,1) -> [cos, sin] and (2,3) -> [cos, sin],
+    in float32 like the device code.  Returns float32[..., 4]."""
+    g = np.asarray(g, dtype=np.uint64)
+    ctr = np.stack([g & np.uint64(0xFFFFFFFF), g >> np.uint64(32),
+                    np.full_like(g, offset & 0xFFFFFFFF), np.full_like(g, (offset >> 32) & 0xFFFFFFFF)], -1).astype(np.uint32)
+    key = np.stack([np.full_like(g, seed & 0xFFFFFFFF), np.full_like(g, (seed >> 32) & 0xFFFFFFFF)], -1).astype(np.uint32)
     r = philox4x32_10(ctr, key)
     scale = np.float32(2.3283064365386963e-10)
-    u1 = (r[..., 0].astype(np.float32) + np.float32(1.0)) * scale
-    u2 = r[..., 1].astype(np.float32) * scale
-    rad = np.sqrt(np.float32(-2.0) * np.log(u1).astype(np.float32)).astype(np.float32)
-    return (rad * np.cos(np.float64(np.pi) * (np.float32(2.0) * u2).astype(np.float64)).astype(np.float32)).astype(np.float32)
+    out = []
+    for h in range(2):
+        u1 = (r[..., 2 * h].astype(np.float32) + np.float32(1.0)) * scale
+        u2 = r[..., 2 * h + 1].astype(np.float32) * scale
+        rad = np.sqrt(np.float32(-2.0) * np.log(u1).astype(np.float32)).astype(np.float32)
+        ang = np.float64(np.pi) * (np.float32(2.0) * u2).astype(np.float64)
+        out.append((rad * np.cos(ang).astype(np.float32)).astype(np.float32))
+        out.append((rad * np.sin(ang).astype(np.float32)).astype(np.float32))
+    return np.stack(out, -1)
+
+
+def philox_eps(b: int, t: int, h: int, w: int, seed: int, offset: int) -> np.ndarray:
+    """The device noise tensor eps [b,48,5,t,h,w]: Philox call g = linear index of (b, hf//4, k, t, pixel) in [b,12,5,t,h*w]
+    gives hf = 4*(hf//4) + 0..3 (DESIGN.md "Noise")."""
+    g = np.arange(b * 12 * 5 * t * h * w, dtype=np.uint64)
+    n4 = philox_normal4(g, seed, offset).reshape(b, 12, 5, t, h, w, 4)
+    return np.ascontiguousarray(np.moveaxis(n4, -1, 2)).reshape(b, 48, 5, t, h, w)

@@ -119,14 +119,35 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// One N(0,1) draw for eps element `idx` of stream (seed, offset): Box-Muller on two Philox words.
-__device__ __forceinline__ float philox_normal(uint64_t idx, uint64_t seed, uint64_t offset) {
+// Noise stream (DESIGN.md "Noise"): the reference's eps tensor is [B,48,5,T,h,w] (SelfC_GMM_arch_inv.py:412-415).  One
+// Philox4x32-10 call, counter = the linear index g of (b, hf/4, k, t, pixel) in [B,12,5,T,h*w], yields the FOUR normals
+// of hf = 4*(hf/4) + 0..3: Box-Muller on words (0,1) -> cos, sin branches, on words (2,3) -> cos, sin branches.
+// So a thread-per-pixel sampler pays one Philox per (k, hf-quad), and the values depend only on (seed, offset) and
+// the element's coordinates, never on tiling, launch shape or GPU count.
+__device__ __forceinline__ void philox_normal4(uint64_t g, uint64_t seed, uint64_t offset, float out[4]) {
   uint32_t r[4];
-  philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
+  philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
                 (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  float u1 = ((float)r[0] + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
-  float u2 = (float)r[1] * 2.3283064365386963e-10f;            // [0, 1]
-  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+    const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;        // [0, 1]
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    out[2 * h] = rad * cs;
+    out[2 * h + 1] = rad * sn;
+  }
+}
+__host__ __device__ __forceinline__ uint64_t eps_group(long long b, int hfq, int k, int t, long long pix, int T, long long hw) {
+  return (uint64_t)(((((b * (kHF / 4) + hfq) * kGmmK + k) * T + t) * hw) + pix);
+}
+// single element eps[b, hf, k, t, pix] (the non-hot callers)
+__device__ __forceinline__ float philox_eps(long long b, int hf, int k, int t, long long pix, int T, long long hw, uint64_t seed,
+                                            uint64_t offset) {
+  float n4[4];
+  philox_normal4(eps_group(b, hf >> 2, k, t, pix, T, hw), seed, offset, n4);
+  return n4[hf & 3];
 }
 
 }  // namespace selfc

@@ -85,6 +85,6 @@ int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, u
 int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* z, int B, int T, int h,
                              int w, cudaStream_t st);
 int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, cudaStream_t st);
-int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, long long n, cudaStream_t st);
+int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, long long hw, cudaStream_t st);
 
 }  // namespace selfc

@@ -752,7 +752,8 @@ int selfc_gmm_sample(const float* params, const float* eps, uint64_t seed, uint6
 
 int selfc_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, int h, int w, void* stream) {
   SELFC_CHECK_ARG(eps, "export_eps: null pointer");
-  return launch_export_eps(eps, seed, offset, (long long)B * kHF * kGmmK * T * h * w, (cudaStream_t)stream);
+  SELFC_CHECK_ARG(B >= 0 && T >= 1 && h >= 1 && w >= 1, "export_eps: bad shape");
+  return launch_export_eps(eps, seed, offset, B, T, (long long)h * w, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -149,14 +149,14 @@ __global__ void __launch_bounds__(128) gmm_sample_kernel(const float* __restrict
       const float ls = fminf(fmaxf(P[hf0 * 15 + k * 3 + 1], -7.f), 7.f);
       const float mu = P[hf0 * 15 + k * 3 + 2];
       const uint64_t idx = (uint64_t)(((((b * kHF + hf0) * kGmmK + k) * T + t) * hw) + pix);
-      const float ep = eps ? __ldg(eps + idx) : philox_normal(idx, seed, offset);
+      const float ep = eps ? __ldg(eps + idx) : philox_eps(b, hf0, k, t, pix, T, hw, seed, offset);
       out0 += (e0 / sum) * (ep * expf(ls) + mu);
     }
     if (has1) {
       const float ls = fminf(fmaxf(P[hf1 * 15 + k * 3 + 1], -7.f), 7.f);
       const float mu = P[hf1 * 15 + k * 3 + 2];
       const uint64_t idx = (uint64_t)(((((b * kHF + hf1) * kGmmK + k) * T + t) * hw) + pix);
-      const float ep = eps ? __ldg(eps + idx) : philox_normal(idx, seed, offset);
+      const float ep = eps ? __ldg(eps + idx) : philox_eps(b, hf1, k, t, pix, T, hw, seed, offset);
       out1 += (e1 / sum) * (ep * expf(ls) + mu);
     }
   }
@@ -208,11 +208,16 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
       const float4 s4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 60 + k * 12 + i, (size_t)m)));
       const float4 m4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 120 + k * 12 + i, (size_t)m)));
       const float lg[4] = {l4.x, l4.y, l4.z, l4.w}, ls[4] = {s4.x, s4.y, s4.z, s4.w}, mu[4] = {m4.x, m4.y, m4.z, m4.w};
+      float ep4[4];
+      if (eps) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ep4[e] = __ldg(eps + (uint64_t)(((((b * kHF + 4 * i + e) * kGmmK + k) * T + t) * hw) + pix));
+      } else {
+        philox_normal4(eps_group(b, i, k, t, pix, T, hw), seed, offset, ep4);   // one Philox call per (k, hf quad)
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int hf = 4 * i + e;
-        const uint64_t idx = (uint64_t)(((((b * kHF + hf) * kGmmK + k) * T + t) * hw) + pix);
-        const float ep = eps ? __ldg(eps + idx) : philox_normal(idx, seed, offset);
+        const float ep = ep4[e];
         const float pi = expf(lg[e] - mx[k]) * inv[k];
         out[e] += pi * (ep * expf(fminf(fmaxf(ls[e], -7.f), 7.f)) + mu[e]);
       }
@@ -231,9 +236,18 @@ __global__ void permute_gmm_rows_kernel(const float* __restrict__ w, const float
   if (threadIdx.x == 0) bp[np] = b[src];
 }
 
-__global__ void export_eps_kernel(float* __restrict__ eps, uint64_t seed, uint64_t offset, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) eps[i] = philox_normal((uint64_t)i, seed, offset);
+// eps [B,48,5,T,h,w]: thread i of [B,12,5,T,hw] writes the four hf of its quad
+__global__ void export_eps_kernel(float* __restrict__ eps, uint64_t seed, uint64_t offset, int T, long long hw, long long ngroups) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups) return;
+  float n4[4];
+  philox_normal4((uint64_t)g, seed, offset, n4);
+  const long long inner = (long long)kGmmK * T * hw;          // elements per hf channel of one clip
+  const long long bq = g / inner, rest = g - bq * inner;      // bq = b*12 + hf/4
+  const long long b = bq / (kHF / 4);
+  const int hfq = (int)(bq - b * (kHF / 4));
+#pragma unroll
+  for (int e = 0; e < 4; ++e) eps[(b * kHF + hfq * 4 + e) * inner + rest] = n4[e];
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------
@@ -292,9 +306,10 @@ int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp
   return 0;
 }
 
-int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, long long n, cudaStream_t st) {
+int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, long long hw, cudaStream_t st) {
+  const long long n = (long long)B * (kHF / 4) * kGmmK * T * hw;
   if (n == 0) return 0;
-  export_eps_kernel<<<cdiv(n, 256), 256, 0, st>>>(eps, seed, offset, n);
+  export_eps_kernel<<<cdiv(n, 256), 256, 0, st>>>(eps, seed, offset, T, hw, n);
   SELFC_LAUNCH_CHECK("export_eps_kernel");
   return 0;
 }

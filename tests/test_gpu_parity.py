@@ -119,8 +119,11 @@ def test_philox_stream(dev):
     # keyed on the linear index: a bigger batch's first clip draws the same numbers (GPU-count invariance)
     big = engine.export_eps(2, 7, 16, 24, seed=42, offset=0, device=dev).cpu()
     assert torch.equal(big[0], a[0])
-    ref = so.philox_normal(np.arange(4096, dtype=np.uint64), seed=42, offset=0)
-    np.testing.assert_allclose(a.reshape(-1)[:4096].numpy(), ref, rtol=0, atol=2e-6)
+    # the numpy restatement of the stream (one Philox call -> the four hf of a quad), every element
+    ref = so.philox_eps(1, 7, 16, 24, seed=42, offset=0)
+    np.testing.assert_allclose(a.numpy(), ref, rtol=0, atol=2e-6)
+    ref1 = so.philox_eps(2, 7, 16, 24, seed=42, offset=0)
+    np.testing.assert_allclose(big.numpy(), ref1, rtol=0, atol=2e-6)
 
 
 # ------------------------------------------------------------------------------------------------ a2 / a9 / a11
