@@ -17,6 +17,8 @@ STAMP = os.path.join(HERE, ".libselfc_b200.stamp")
 SOURCES = ["layout.cu", "conv_simt.cu", "conv_tc3.cu", "temporal_tc.cu", "stp.cu", "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# debugging builds only (e.g. SELFC_B200_NVCC_EXTRA="-DSELFC_TC_TIMING"); part of the digest, so switching it rebuilds
+NVCC_FLAGS += [f for f in os.environ.get("SELFC_B200_NVCC_EXTRA", "").split() if f]
 
 
 def _nvcc() -> str:

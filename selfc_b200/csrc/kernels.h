@@ -76,6 +76,9 @@ int launch_pack_conv_simt(const float* wref, const float* bref, float* wpk, floa
 int launch_ga_wmap(const float* fcw, float* wmap, int h, int w, cudaStream_t st);
 template <typename T>
 int launch_ga_stat(const T* x, int pitch, const float* wmap, float* partial, int nsplit, int BT, int hw, cudaStream_t st);
+// BF16 mode GlobalAgg apply: out = x + sum_t W[b,t,t'] * P[t], P = proj1(x) + bias (pixel-major [M][64] bf16)
+int launch_ga_mix(const __nv_bfloat16* P, const __nv_bfloat16* x, const float* wmat, __nv_bfloat16* outT, int outT_pitch,
+                  long long outT_slabM, float* outF, int outF_pitch, __nv_bfloat16* outAct, int B, int T, long long hw, cudaStream_t st);
 int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const float* p2w, const float* p2b, const float* p3w,
                       const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st);
 // params: pixel-major [M][720] fp32 (ppitch floats per pixel) or NCHW [BT,720,h,w] (params_nchw)

@@ -211,7 +211,8 @@ static int launch_temporal(const selfc_ctx* ctx, const TcTempW& tw, const ConvAr
       t.copyA = a.copyA; t.copyA_pitch = a.copyA_pitch; t.copyB = a.copyB; t.copyB_pitch = a.copyB_pitch; t.copy_pad = a.copy_pad;
       t.wmat = a.wmat; t.wsum = a.wsum; t.resid = a.resid; t.resid_pitch = a.resid_pitch;
       t.outAct = a.outAct; t.outAct_pitch = a.outAct_pitch;
-      return launch_temporal_tc(tw, t, st);
+      const int rc = launch_temporal_tc(tw, t, st);
+      if (rc != SELFC_E_UNSUPPORTED) return rc;      // shared memory cannot hold the frame ring: fp32-FMA kernel below
     }
   }
   return launch_conv_simt<T>(a, st);
@@ -272,6 +273,18 @@ static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* 
   PROF(ctx, st, 2, px_bytes, launch_ga_stat<T>(feat, kStpC, wmap, partial, ws.nsplit, d.B * d.T, (int)d.hw(), st));
   PROF(ctx, st, 2, 0.0, launch_ga_weights(partial, ws.nsplit, g.fcb, g.p2w, g.p2b, g.p3w, g.p3b, wmat, wsum, d.B, d.T, st));
   if (wmat_copy) SELFC_CUDA(cudaMemcpyAsync(wmat_copy, wmat, (size_t)d.B * d.T * d.T * 4, cudaMemcpyDeviceToDevice, st));
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (ctx->mode == SELFC_MODE_BF16 && g.tp.img != nullptr) {
+      // P = proj1(x) + bias as a tcgen05 pointwise GEMM over all M pixels (two pseudo-frames), then the T x T mix at full occupancy
+      __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(wsp + ws.h1);
+      TcTempArgs t;
+      t.in = feat; t.in_pitch = kStpC; t.B = 1; t.T = 2; t.hw = (int)((d.M() + 1) / 2); t.m_limit = d.M();
+      t.epi = EPI_STORE; t.act = 0; t.outT = P; t.outT_pitch = kStpC;
+      PROF(ctx, st, 2, 2.0 * px_bytes, launch_temporal_tc(g.tp, t, st));
+      PROF(ctx, st, 2, 3.0 * px_bytes, launch_ga_mix(P, feat, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch, outAct, d.B, d.T, d.hw(), st));
+      return 0;
+    }
+  }
   ConvArgs<T> a;
   a.in = feat; a.in_pitch = kStpC; a.cin = kStpC;
   a.w = g.p1w; a.bias = g.p1b; a.np = 64; a.cout = 64;

@@ -107,6 +107,148 @@ __global__ void __launch_bounds__(64) ga_weights_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// GlobalAgg apply (BF16 mode): out[b,t',.] = x[b,t',.] + sum_t W[b,t,t'] * P[b,t,.]  with P = proj1(x) + bias computed by
+// the tcgen05 pointwise GEMM (SelfC_GMM_arch_inv.py:266,278-285).  49 FMAs per output element are nothing for the GPU
+// as a whole but were 205 us when done by the four epilogue warps per SM of the GEMM kernel; here they run at full
+// occupancy: one thread per (pixel, 8-channel group), 16-byte loads / stores, consecutive lanes on consecutive addresses.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ga_mix_kernel(const __nv_bfloat16* __restrict__ P, const __nv_bfloat16* __restrict__ x,
+                                                     const float* __restrict__ wmat, __nv_bfloat16* __restrict__ outT, int outT_pitch,
+                                                     long long outT_slabM, float* __restrict__ outF, int outF_pitch,
+                                                     __nv_bfloat16* __restrict__ outAct, int T, long long hw, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = idx >> 3;
+  const int c0 = (int)(idx & 7) * 8;
+  if (m >= M) return;
+  const long long n = m / hw, pix = m - n * hw;
+  const int tq = (int)(n % T);
+  const long long b = n / T;
+  auto unpack = [](const uint4 r, float* v) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h);
+      v[2 * i + 1] = __high2float(h);
+    }
+  };
+  auto pack = [](const float* v) {
+    uint4 r;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+    return r;
+  };
+  float acc[8];
+  unpack(__ldg(reinterpret_cast<const uint4*>(x + m * kStpC + c0)), acc);
+  const float* wm = wmat + b * T * T + tq;          // W[b][t][t' = tq]
+  for (int t = 0; t < T; ++t) {
+    const float wv = __ldg(wm + t * T);
+    float pv[8];
+    unpack(__ldg(reinterpret_cast<const uint4*>(P + ((b * T + t) * hw + pix) * kStpC + c0)), pv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv, pv[j], acc[j]);
+  }
+  if (outT) *reinterpret_cast<uint4*>(outT + dense_off(m, c0, outT_pitch, outT_slabM)) = pack(acc);
+  if (outF) {
+    float* o = outF + m * outF_pitch + c0;
+    store4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    store4(o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+  }
+  if (outAct) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = lrelu02(acc[j]);
+    *reinterpret_cast<uint4*>(outAct + m * kStpC + c0) = pack(acc);
+  }
+}
+
+// T <= 8: one thread per (clip, pixel, 8-channel group) produces ALL T output frames, so every P element is read from
+// DRAM exactly once (the per-output-frame kernel above re-reads each P value T times from frames that are 16 MB apart).
+__global__ void __launch_bounds__(256) ga_mix_allframes_kernel(const __nv_bfloat16* __restrict__ P, const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ wmat, __nv_bfloat16* __restrict__ outT,
+                                                               int outT_pitch, long long outT_slabM, float* __restrict__ outF,
+                                                               int outF_pitch, __nv_bfloat16* __restrict__ outAct, int T, long long hw,
+                                                               long long Bhw) {
+  constexpr int TM = 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long bp = idx >> 3;                  // b * hw + pix
+  const int c0 = (int)(idx & 7) * 8;
+  if (bp >= Bhw) return;
+  const long long b = bp / hw, pix = bp - b * hw;
+  auto unpack = [](const uint4 r, float* v) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h);
+      v[2 * i + 1] = __high2float(h);
+    }
+  };
+  auto pack = [](const float* v) {
+    uint4 r;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+    return r;
+  };
+  float pv[TM][8];
+  uint4 xr[TM];
+#pragma unroll
+  for (int t = 0; t < TM; ++t) {
+    if (t < T) {
+      const long long m = (b * T + t) * hw + pix;
+      unpack(__ldg(reinterpret_cast<const uint4*>(P + m * kStpC + c0)), pv[t]);
+      xr[t] = __ldg(reinterpret_cast<const uint4*>(x + m * kStpC + c0));
+    }
+  }
+  const float* wm = wmat + b * T * T;               // W[b][t][t']
+#pragma unroll
+  for (int tq = 0; tq < TM; ++tq) {
+    if (tq >= T) continue;
+    const long long m = (b * T + tq) * hw + pix;
+    float acc[8];
+    unpack(xr[tq], acc);
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+      if (t < T) {
+        const float wv = __ldg(wm + t * T + tq);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv, pv[t][j], acc[j]);
+      }
+    }
+    if (outT) *reinterpret_cast<uint4*>(outT + dense_off(m, c0, outT_pitch, outT_slabM)) = pack(acc);
+    if (outF) {
+      float* o = outF + m * outF_pitch + c0;
+      store4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      store4(o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
+    if (outAct) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = lrelu02(acc[j]);
+      *reinterpret_cast<uint4*>(outAct + m * kStpC + c0) = pack(acc);
+    }
+  }
+}
+
+int launch_ga_mix(const __nv_bfloat16* P, const __nv_bfloat16* x, const float* wmat, __nv_bfloat16* outT, int outT_pitch,
+                  long long outT_slabM, float* outF, int outF_pitch, __nv_bfloat16* outAct, int B, int T, long long hw, cudaStream_t st) {
+  const long long M = (long long)B * T * hw;
+  if (M == 0) return 0;
+  SELFC_CHECK_ARG(outF == nullptr || outF_pitch % 4 == 0, "ga_mix: outF pitch");
+  if (T <= 8) {
+    ga_mix_allframes_kernel<<<cdiv((long long)B * hw * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch,
+                                                                             outAct, T, hw, (long long)B * hw);
+    SELFC_LAUNCH_CHECK("ga_mix_allframes_kernel");
+    return 0;
+  }
+  ga_mix_kernel<<<cdiv(M * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch, outAct, T, hw, M);
+  SELFC_LAUNCH_CHECK("ga_mix_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Soft-GMM sampler: one warp per LR pixel.  Channel ch = hf*15 + k*3 + j (j: 0 logit, 1 log-scale, 2 mean);
 // the softmax runs over the 48 hf channels for each k; v[hf] = sum_k pi * (eps*exp(clamp(ls,-7,7)) + mu).
 // eps is read from `eps` (reference layout [B,48,5,T,h,w]) or generated by Philox at that linear index.

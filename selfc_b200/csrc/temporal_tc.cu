@@ -6,14 +6,16 @@
 //   coupling                   SelfC_GMM_arch_inv.py:21-33      y1 = x1 +/- F, s = 2*sigmoid(H)-1, y2 = x2*e^s + G | (x2-G)/e^s
 //   GlobalAgg apply            SelfC_GMM_arch_inv.py:266,278-285 out[t'] = x[t'] + sum_t W[b,t,t'] * proj1(x[t])
 //
-// Mapping: a CTA owns 128 consecutive pixels of ALL T frames of one clip.  Per 16-channel K slice the TMA brings the
-// T frame tiles ([2 planes][128 px][8 ch], the no-swizzle K-major core-matrix layout) into one pipeline stage ONCE;
-// frame t's tile is the A operand of up to three MMAs (output frames t-1, t, t+1), so the temporal taps re-use the
-// load.  Each output frame has its own fp32 accumulator (N columns) in TMEM: T*N <= 512 columns.  Clip-end zero
-// padding = the corresponding MMA is simply not issued.  Weights stay resident in shared memory.
-// Epilogue warps read the accumulators frame by frame (tcgen05.ld), apply bias and the fused coupling / residual
-// arithmetic on the fp32 latent state, and release each frame's accumulator as soon as it is drained so the next
-// tile's MMAs chase the epilogue.
+// Mapping: a CTA owns 128 consecutive pixels of ALL T frames of one clip and walks the INPUT frames in order.  The tile
+// of input frame f (one ring stage per K chunk, loaded once, released as soon as its MMAs are committed) is the A operand
+// of up to three MMAs per K step issued back to back -- out[f-1] (tap 2), out[f] (tap 1), out[f+1] (tap 0).  Output
+// frames live in ROLLING TMEM accumulators (4 x N columns): out[f-1] is complete when frame f has been consumed, so its
+// epilogue runs while the MMAs of the following frames are issued, across tile boundaries too, and T is not limited by
+// TMEM.  Clip-end zero padding = the corresponding MMAs are simply not issued.  Weights stay resident in shared memory.
+// Input: a slab-planar dense buffer (common.cuh; one 4-D TMA box of 128 px x kps slabs per stage, SWIZZLE_32B sub-tiles
+// of 4 KB) or a pixel-major buffer (GMM head; 3-D box of 128 px x 64 ch, SWIZZLE_128B rows).
+// Epilogue warps read the accumulator of the finished pass (tcgen05.ld), apply bias and the fused coupling arithmetic on
+// the fp32 latent state, and release the accumulator.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -28,10 +30,8 @@ namespace tc5 {
 using namespace tc;
 
 constexpr int MT = 128;
-// channels per pipeline stage = one swizzled row per pixel: KC = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B
-constexpr int KC_DEFAULT = 64;
-constexpr int NST_MAX = 8;
-constexpr int TMAX = 8;
+constexpr int NST_MAX = 14;      // ring slots
+constexpr int NACC_MAX = 4;      // rolling accumulators
 constexpr int THREADS = 192;
 constexpr int BAR_BYTES = 512;
 constexpr int BIAS_BYTES = 1024;   // up to 256 fp32
@@ -39,8 +39,8 @@ constexpr int BIAS_BYTES = 1024;   // up to 256 fp32
 struct Params {
   const void* wimg;
   const float* bias;
-  int T, B, hw, nks, npad, taps, cout, nst;   // nks = K steps of 16 channels; nst = pipeline stages
-  int fps;                                    // frames per pipeline stage (1 or 2)
+  int T, B, hw, nks, npad, taps, cout, nst;   // nks = K steps of 16 channels; nst = ring slots
+  int kps, nchunk, nacc;                      // K steps per stage, stages per frame, rolling accumulators
   int epi_quads;                              // 16-byte quads of epilogue operands staged per pixel-frame (Y2: 24, Y1: 1)
   int tiles_p, ntiles, tmem_cols;
   long long m_limit;   // rows (pixels) that really exist in the buffer
@@ -155,19 +155,17 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 
-template <int KC>
+template <int TAPS>
 __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  constexpr int FRAME_BYTES = MT * KC * 2;          // one frame tile of one KC-channel slice
-  const int FPS = p.fps;
-  const int STAGE_BYTES = FPS * FRAME_BYTES;
-  constexpr int KSTEPS = KC / 16;                   // UMMA K steps per stage
-  constexpr uint32_t SBO = 8 * KC * 2;              // 8-row swizzle atom
-  constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int T = p.T;
   const int NST = p.nst;
+  const int KPS = p.kps;
+  const int NC = p.nchunk;
+  const int NACC = p.nacc;
+  const int STAGE_BYTES = KPS * MT * 32;            // KPS K-steps of [128 px][16 ch]
   const uint32_t a_base = base;
   const uint32_t bar_base = base + NST * STAGE_BYTES;
   const uint32_t bias_off = NST * STAGE_BYTES + BAR_BYTES;
@@ -177,10 +175,10 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NST_MAX + s); };
   const uint32_t w_bar = bar_base + 8u * (2 * NST_MAX);
-  const uint32_t tfull_bar = bar_base + 8u * (2 * NST_MAX + 1);
-  auto tempty_bar = [&](int t) { return bar_base + 8u * (2 * NST_MAX + 2 + t); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * NST_MAX + 2 + TMAX);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + NST * STAGE_BYTES + 8 * (2 * NST_MAX + 2 + TMAX));
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NST_MAX + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NST_MAX + 1 + NACC_MAX + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NST_MAX + 1 + 2 * NACC_MAX);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + NST * STAGE_BYTES + 8 * (2 * NST_MAX + 1 + 2 * NACC_MAX));
   float* sbias = reinterpret_cast<float*>(gen_base + bias_off);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
@@ -192,8 +190,10 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(w_bar, 1);
-    mbar_init(tfull_bar, 1);
-    for (int t = 0; t < TMAX; ++t) mbar_init(tempty_bar(t), 4);
+    for (int a = 0; a < NACC_MAX; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -205,13 +205,13 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_launch_dependents();
 
-  const int nks = p.nks, npad = p.npad, taps = p.taps;
-  const int nchunk = (nks + KSTEPS - 1) / KSTEPS;   // KC-channel slices
+  const int nks = p.nks, npad = p.npad;
+  constexpr int taps = TAPS;
   const uint32_t wtile = (uint32_t)npad * 32u;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
+      // ===================== TMA producer: stages in (tile, frame, chunk) order =====================
       const uint32_t wbytes = (uint32_t)taps * nks * wtile;
       mbar_expect_tx(w_bar, wbytes);
       for (int tap = 0; tap < taps; ++tap)
@@ -224,15 +224,12 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int b = tile / p.tiles_p;
         const int p0 = (tile - b * p.tiles_p) * MT;
-        for (int c = 0; c < nchunk; ++c) {
-          for (int t0 = 0; t0 < T; t0 += FPS) {
-            const int nf = T - t0 < FPS ? T - t0 : FPS;
+        for (int f = 0; f < T; ++f) {
+          for (int c = 0; c < NC; ++c) {
             timed_wait(empty_bar(s), ph ^ 1u, p.err, 11, w_prod);
-            mbar_expect_tx(full_bar(s), (uint32_t)nf * FRAME_BYTES);
-            for (int f = 0; f < nf; ++f) {
-              if (p.in_slab) tma_load_4d(a_base + s * STAGE_BYTES + f * FRAME_BYTES, &tmap, full_bar(s), 0, p0, b * T + t0 + f, c * KSTEPS);
-              else tma_load_3d(a_base + s * STAGE_BYTES + f * FRAME_BYTES, &tmap, full_bar(s), c * KC, p0, b * T + t0 + f);
-            }
+            mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);
+            if (p.in_slab) tma_load_4d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), 0, p0, b * T + f, c * KPS);
+            else tma_load_3d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), c * KPS * 16, p0, b * T + f);
             if (++s == NST) { s = 0; ph ^= 1u; }
           }
         }
@@ -243,52 +240,70 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
     {
       // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
       const uint32_t idesc = umma_idesc_bf16(128, npad);
-      // pixel-major input: one swizzled row of KC channels per pixel, a K step advances 32 bytes inside the row;
-      // slab input: KSTEPS sub-tiles of [128 px][16 ch] (SWIZZLE_32B, 4 KB each), a K step advances one sub-tile
-      const uint32_t hi_a = p.in_slab ? desc_hi(256, 6) : desc_hi(SBO, LAYOUT);
+      // pixel-major input: one SWIZZLE_128B row of 64 channels per pixel, a K step advances 32 bytes inside the row;
+      // slab input: KPS sub-tiles of [128 px][16 ch] (SWIZZLE_32B, 4 KB each), a K step advances one sub-tile
+      const uint32_t hi_a = p.in_slab ? desc_hi(256, 6) : desc_hi(1024, 2);
       const uint32_t a_kinc = p.in_slab ? (uint32_t)(MT * 32 >> 4) : 2u;
       long long w_full = 0, w_tempty = 0;
       const long long t_start = clock64();
       mbar_wait(w_bar, 0, p.err, 12);
       const long long t_w = clock64() - t_start;
-      int s = 0;
+      int gbase = 0;            // output frames of earlier tiles: output o of this tile uses accumulator (gbase + o) & (NACC-1)
+      int s = 0;                // stage ring position (plain FIFO: every stage is consumed once)
       uint32_t ph = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        uint32_t started = 0;                   // bit t: accumulator of output frame t already holds a partial sum
-        for (int c = 0; c < nchunk; ++c) {
-          const int ksn = nks - KSTEPS * c < KSTEPS ? nks - KSTEPS * c : KSTEPS;
-          for (int t0 = 0; t0 < T; t0 += FPS) {
-            const int nf = T - t0 < FPS ? T - t0 : FPS;
+      const uint32_t amask = (uint32_t)(NACC - 1);          // NACC is 2 or 4
+      const uint32_t hi_b = desc_hi(128, 0);
+      const uint32_t b_lbo = ((uint32_t)npad * 16u >> 4) << 16;
+      const uint32_t wstep = wtile >> 4;                    // descriptor units per 16-channel weight tile
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, gbase += T) {
+        // INPUT-frame-major: the tile of input frame fi feeds the outputs fi-1, fi, fi+1 (taps 2, 1, 0) back to back with
+        // the same A descriptor, then is released.  Output fi-1 is complete once frame fi has been consumed.
+        for (int fi = 0; fi < T; ++fi) {
+          // per tap: output frame, accumulator column, whether the accumulator already holds a partial sum.  Everything
+          // the K loop needs is computed here so that the issue loop is a handful of uniform-datapath instructions per MMA
+          // (a runtime modulo inside it cost ~100 cycles per MMA, 3x the tensor-core time of these small-N MMAs).
+          uint32_t dcol[TAPS], bdesc0[TAPS], started[TAPS];
+          bool valid[TAPS];
+#pragma unroll
+          for (int j = 0; j < TAPS; ++j) {
+            const int tap = TAPS - 1 - j;                                  // issue order: taps 2, 1, 0 -> outputs fi-1, fi, fi+1
+            const int o = TAPS == 3 ? fi - tap + 1 : fi;                   // out[o] += W[tap] . in[o + tap - 1]
+            valid[j] = o >= 0 && o < T;
+            dcol[j] = tmem_base + (((uint32_t)(gbase + o)) & amask) * (uint32_t)npad;
+            bdesc0[j] = (((w_base + (uint32_t)(tap * nks) * wtile) & 0x3FFFFu) >> 4) | b_lbo;
+            // first contribution to out[o] comes from frame max(o-1, 0) (frame o for a pointwise conv)
+            started[j] = TAPS == 3 ? (fi != (o > 0 ? o - 1 : 0) ? 1u : 0u) : 0u;
+            if (valid[j] && !started[j]) {
+              const int g = gbase + o;
+              timed_wait(tempty_bar((int)((uint32_t)g & amask)), (((uint32_t)g / (uint32_t)NACC) & 1u) ^ 1u, p.err, 13, w_tempty);
+            }
+          }
+          tc_fence_after();
+          uint32_t kk = 0;                                                // K step within the frame
+          for (int c = 0; c < NC; ++c) {
             timed_wait(full_bar(s), ph, p.err, 14, w_full);
             tc_fence_after();
-           for (int f = 0; f < nf; ++f) {
-            const int ti = t0 + f;
-            const uint32_t a_stage = a_base + s * STAGE_BYTES + f * FRAME_BYTES;
-            for (int tap = 0; tap < taps; ++tap) {
-              const int to = taps == 3 ? ti - tap + 1 : ti;     // out[to] += W[tap] . in[to + tap - 1]
-              if (to < 0 || to >= T) continue;
-              if (!(started >> to & 1u)) {
-                timed_wait(tempty_bar(to), ((uint32_t)it & 1u) ^ 1u, p.err, 13, w_tempty);
-                tc_fence_after();
-              }
-              const uint32_t a_lo = desc_lo(a_stage, 16);
-              const uint32_t b_lo = desc_lo(w_base + (uint32_t)(tap * nks + KSTEPS * c) * wtile, (uint32_t)npad * 16u);
-              const uint32_t dcol = tmem_base + (uint32_t)(to * npad);
-              for (int ks = 0; ks < ksn; ++ks) {
-                // A: +32 bytes per K step inside the 128-byte swizzled row; B: next 16-channel weight tile
-                const uint64_t ad = desc_join(a_lo + a_kinc * (uint32_t)ks, hi_a);
-                const uint64_t bd = desc_join(b_lo + (uint32_t)ks * (wtile >> 4), desc_hi(128, 0));
-                umma_bf16_elect(dcol, ad, bd, idesc, (started >> to & 1u) ? 1u : 0u);
-                started |= 1u << to;
+            const int ksn = nks - KPS * c < KPS ? nks - KPS * c : KPS;
+            const uint32_t a_lo = desc_lo(a_base + s * STAGE_BYTES, 16);
+            for (int ks = 0; ks < ksn; ++ks, ++kk) {
+              const uint64_t ad = desc_join(a_lo + a_kinc * (uint32_t)ks, hi_a);
+#pragma unroll
+              for (int j = 0; j < TAPS; ++j) {
+                if (!valid[j]) continue;
+                umma_bf16_elect(dcol[j], ad, desc_join(bdesc0[j] + kk * wstep, hi_b), idesc, started[j] | (kk > 0 ? 1u : 0u));
               }
             }
-           }
             umma_commit_elect(empty_bar(s));
             if (++s == NST) { s = 0; ph ^= 1u; }
           }
+          // outputs completed by this frame
+          if (TAPS == 3) {
+            if (fi >= 1) umma_commit_elect(tfull_bar((int)((uint32_t)(gbase + fi - 1) & amask)));
+            if (fi == T - 1) umma_commit_elect(tfull_bar((int)((uint32_t)(gbase + fi) & amask)));
+          } else {
+            umma_commit_elect(tfull_bar((int)((uint32_t)(gbase + fi) & amask)));
+          }
         }
-        umma_commit_elect(tfull_bar);
       }
       if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - t_start; p.dbg[5] = t_w; }
     }
@@ -311,70 +326,12 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       const int b = tile / p.tiles_p;
       const int pix = (tile - b * p.tiles_p) * MT + row;
       const bool valid = pix < p.hw;
-      // the epilogue's operands (latent state, log-scale, residual) are pulled into L2 while the MMAs of this tile run
-      if (pix < p.hw) {
-        for (int t = 0; t < T; ++t) {
-          const size_t m = ((size_t)b * T + t) * p.hw + pix;
-          if (p.epi == EPI_GA) {
-            prefetch_l2(p.resid + m * p.resid_pitch);
-          }
-        }
-      }
-      timed_wait(tfull_bar, (uint32_t)it & 1u, p.err, 15, w_tfull);
-      tc_fence_after();
-      if (p.epi == EPI_GA) {
-        // out[t'] = x[t'] + bias * colsum(W)[t'] + sum_t W[b,t,t'] * D_t
-        const float* wm = p.wmat + (size_t)b * T * T;
-        for (int n0 = 0; n0 < p.cout; n0 += 8) {
-          uint32_t d[TMAX][8];
-#pragma unroll
-          for (int t = 0; t < TMAX; ++t)
-            if (t < T) tmem_ld8(lane_addr + (uint32_t)(t * npad + n0), d[t]);
-          tmem_ld_wait();
-          if (valid) {
-            uint4 rs[TMAX];
-#pragma unroll
-            for (int tp = 0; tp < TMAX; ++tp)
-              if (tp < T) rs[tp] = *reinterpret_cast<const uint4*>(p.resid + (((size_t)b * T + tp) * p.hw + pix) * p.resid_pitch + n0);
-#pragma unroll
-            for (int tp = 0; tp < TMAX; ++tp) {
-              if (tp >= T) continue;
-              const size_t m = ((size_t)b * T + tp) * p.hw + pix;
-              float v[8];
-              unpack_bf16x8(rs[tp], v);
-              const float ws = __ldg(p.wsum + b * T + tp);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += sbias[n0 + j] * ws;
-#pragma unroll
-              for (int t = 0; t < TMAX; ++t) {
-                if (t < T) {
-                  const float wv = __ldg(wm + t * T + tp);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = fmaf(wv, __uint_as_float(d[t][j]), v[j]);
-                }
-              }
-              if (p.outT) store_bf16x8(p.outT + dense_off((long long)m, p.outT_off + n0, p.outT_pitch, p.outT_slabM), v);
-              if (p.outF) {
-                float* o = p.outF + m * p.outF_pitch + n0;
-                store4(o, make_float4(v[0], v[1], v[2], v[3]));
-                store4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
-              }
-              if (p.outAct) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = lrelu02(v[j]);
-                store_bf16x8(p.outAct + m * p.outAct_pitch + n0, v);
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0)
-          for (int t = 0; t < T; ++t) mbar_arrive(tempty_bar(t));
-        continue;
-      }
       for (int t = 0; t < T; ++t, ++gframe) {
         const size_t m = ((size_t)b * T + t) * p.hw + pix;
+        const int aslot = (int)(gframe & (uint32_t)(NACC - 1));     // rolling accumulator of this output frame (NACC = 2 or 4)
+        const uint32_t acol = lane_addr + (uint32_t)(aslot * npad);
+        timed_wait(tfull_bar(aslot), (gframe / (uint32_t)NACC) & 1u, p.err, 15, w_tfull);
+        tc_fence_after();
         const int ncols = p.epi == EPI_COUPLE_Y1 ? 16 : (p.epi == EPI_STORE ? ((p.cout + 15) & ~15) : kHF);
         const bool live = valid && (long long)m < p.m_limit;
         const uint32_t ebuf = epi_base + (uint32_t)((gframe & 1) * p.epi_quads * MT + row) * 16u;
@@ -395,12 +352,13 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
             x2q[0] = lds4(ebuf);
           }
           uint32_t r[16];
-          tmem_ld16(lane_addr + (uint32_t)(t * npad + n0), r);
+          tmem_ld16(acol + (uint32_t)n0, r);
           tmem_ld_wait();
           if (!live) continue;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
+
           switch (p.epi) {
             case EPI_STORE: {
               if (p.act) {
@@ -489,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(t));
+        if (lane == 0) mbar_arrive(tempty_bar(aslot));
         if (p.epi_quads) stage_epilogue_operands(p, tile, t, 2, row, Mtot, ebuf);
       }
     }
@@ -554,32 +512,39 @@ void free_temporal_weights(TcTempW& w) {
   w.img_bytes = 0;
 }
 
-bool temporal_tc_supported(const TcTempW& w, int T) { return w.img != nullptr && T >= 1 && T <= tc5::TMAX && T * w.npad <= 512; }
+bool temporal_tc_supported(const TcTempW& w, int T) { return w.img != nullptr && T >= 1 && T <= 32; }
 
 int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
-  SELFC_CHECK_ARG(temporal_tc_supported(w, a.T), "temporal_tc: T=%d x N=%d does not fit TMEM", a.T, w.npad);
+  SELFC_CHECK_ARG(temporal_tc_supported(w, a.T), "temporal_tc: weights not packed or T=%d outside [1,32]", a.T);
   SELFC_CHECK_ARG(a.in_pitch % 8 == 0 && aligned16(a.in), "temporal_tc: input pitch/alignment");
+  SELFC_CHECK_ARG(a.epi != EPI_GA, "temporal_tc: the GlobalAgg mix is a separate kernel (stp.cu: ga_mix)");
   tc::EncodeTiledFn encode = tc::get_encode_fn();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return SELFC_E_CUDA;
   }
   const int BT = a.B * a.T;
-  SELFC_CHECK_ARG(a.epi != EPI_GA || w.npad <= 64, "temporal_tc: GlobalAgg epilogue needs N <= 64");
-  CUtensorMap tmap;
-  static int kc = 0;     // SELFC_TC_KC = 64 | 32 | 16 selects the swizzle width of the A operand (experiment knob)
-  if (!kc) {
-    const char* e = getenv("SELFC_TC_KC");
-    kc = e ? atoi(e) : tc5::KC_DEFAULT;
-    if (kc != 64 && kc != 32 && kc != 16) kc = tc5::KC_DEFAULT;
+  const int nks = w.cin_buf / 16;
+  // K steps per ring stage: slab input -> the split of nks with the least padding (a stage is kps sub-tiles of 4 KB);
+  // pixel-major input -> one SWIZZLE_128B row of 64 channels per pixel
+  int kps = 4;
+  if (a.in_slabM) {
+    int best_waste = 1 << 30;
+    for (int k = 4; k >= 2; --k) {
+      const int waste = cdiv(nks, k) * k - nks;
+      if (waste < best_waste) { best_waste = waste; kps = k; }
+    }
+    if (nks < kps) kps = nks;
   }
+  const int nchunk = cdiv(nks, kps);
+  CUtensorMap tmap;
   CUresult r;
   if (a.in_slabM) {
-    // slab-planar dense buffer [cin/16][M][16]: box = 128 pixels of one frame x kc/16 slabs, each slab's rows one 4 KB run
+    // slab-planar dense buffer [cin/16][M][16]: box = 128 pixels of one frame x kps slabs, each slab's rows one 4 KB run
     SELFC_CHECK_ARG(a.in_slabM == (long long)BT * a.hw, "temporal_tc: slab stride %lld != B*T*hw", a.in_slabM);
-    const cuuint64_t gdim[4] = {16, (cuuint64_t)a.hw, (cuuint64_t)BT, (cuuint64_t)(w.cin_buf / 16)};
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)a.hw, (cuuint64_t)BT, (cuuint64_t)nks};
     const cuuint64_t gstr[3] = {32, (cuuint64_t)a.hw * 32, (cuuint64_t)a.in_slabM * 32};
-    const cuuint32_t box[4] = {16, (cuuint32_t)tc5::MT, 1, (cuuint32_t)(kc / 16)};
+    const cuuint32_t box[4] = {16, (cuuint32_t)tc5::MT, 1, (cuuint32_t)kps};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -587,12 +552,11 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   } else {
     const cuuint64_t gdim[3] = {(cuuint64_t)a.in_pitch, (cuuint64_t)a.hw, (cuuint64_t)BT};
     const cuuint64_t gstr[2] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.hw * a.in_pitch * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)tc5::MT, 1};
+    const cuuint32_t box[3] = {64, (cuuint32_t)tc5::MT, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE,
-               kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
-               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (temporal) failed with CUresult %d", (int)r);
@@ -601,10 +565,19 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   tc5::Params p;
   memset(&p, 0, sizeof(p));
   p.wimg = w.img; p.bias = w.bias;
-  p.T = a.T; p.B = a.B; p.hw = a.hw; p.nks = w.cin_buf / 16; p.npad = w.npad; p.taps = w.taps; p.cout = w.cout;
+  p.T = a.T; p.B = a.B; p.hw = a.hw; p.nks = nks; p.npad = w.npad; p.taps = w.taps; p.cout = w.cout;
+  p.kps = kps; p.nchunk = nchunk;
   p.tiles_p = cdiv(a.hw, tc5::MT);
   p.ntiles = p.tiles_p * a.B;
-  int cols = a.T * w.npad, pw = 32;
+  // taps == 3: the outputs fi-1, fi, fi+1 are being accumulated while the epilogue drains a fourth one
+  const int nacc = 512 / w.npad >= 4 ? 4 : (512 / w.npad >= 2 ? 2 : 0);     // power of two: slot = index & (nacc-1)
+  SELFC_CHECK_ARG(w.taps == 3 || w.taps == 1, "temporal_tc: %d taps", w.taps);
+  if (nacc < (w.taps == 3 ? 4 : 2)) {
+    set_error("temporal_tc: N=%d leaves no room for %d rolling accumulators", w.npad, w.taps == 3 ? 4 : 2);
+    return SELFC_E_UNSUPPORTED;
+  }
+  p.nacc = nacc;
+  int cols = nacc * w.npad, pw = 32;
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   p.epi = a.epi; p.rev = a.rev; p.act = a.act;
@@ -626,28 +599,27 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   if (p.ntiles == 0) return 0;
   p.epi_quads = a.epi == EPI_COUPLE_Y2 ? 2 * kSQuads : (a.epi == EPI_COUPLE_Y1 ? 1 : 0);
   const int fixed = tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes + 2 * p.epi_quads * tc5::MT * 16 + 1024;
-  int fps = a.T >= 2 ? 2 : 1;
-  if ((227 * 1024 - fixed) / (fps * tc5::MT * kc * 2) < 3) fps = 1;
-  p.fps = fps;
-  const int stage_bytes = fps * tc5::MT * kc * 2;
+  const int stage_bytes = kps * tc5::MT * 32;
   int nst = (227 * 1024 - fixed) / stage_bytes;
   if (nst > tc5::NST_MAX) nst = tc5::NST_MAX;
-  SELFC_CHECK_ARG(nst >= 2, "temporal_tc: weights of %zu bytes leave no room for the A pipeline", w.img_bytes);
+  if (nst < 2) {
+    set_error("temporal_tc: no room for two %d-byte stages next to %zu bytes of weights", stage_bytes, w.img_bytes);
+    return SELFC_E_UNSUPPORTED;
+  }
   p.nst = nst;
   const int smem = nst * stage_bytes + fixed;
-  static int smem_set = 0;
-  if (smem_set < smem) {
-    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
+  static bool smem_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !smem_set[dev]) {
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set[dev] = true;
   }
-  SELFC_CHECK_ARG(smem <= 227 * 1024, "temporal_tc: %d bytes of shared memory needed", smem);
   const int nsm = tc::num_sms();
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
-  if (kc == 64) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<64>, grid, tc5::THREADS, smem, st, tmap, p));
-  else if (kc == 32) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<32>, grid, tc5::THREADS, smem, st, tmap, p));
-  else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<16>, grid, tc5::THREADS, smem, st, tmap, p));
+  if (w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3>, grid, tc5::THREADS, smem, st, tmap, p));
+  else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1>, grid, tc5::THREADS, smem, st, tmap, p));
   SELFC_LAUNCH_CHECK("temporal_tc_kernel");
   return 0;
 }
