@@ -273,9 +273,15 @@ def run_ours(args):
         tot_ms = sum(v["ms"] for v in prof.values())
         c = prof["conv3x3"]
         ach = c["work"] / (c["ms"] / 1e3) / 1e12 if c["ms"] > 0 else 0.0
-        roofline = {"kernel": "conv3x3 dense-block convolution (all launches of one 7-frame GOP, down+up)",
+        # DRAM bytes per launch of the same kernel class from the committed `ncu` capture (profiles/; null when absent)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_conv3x3_ncu_traffic.json")
+        if os.path.exists(tp) and (hh, ww) == (HR_H, HR_W):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roofline = {"kernel": "conv3x3_tc3_kernel: (1,3,3) dense-block convolution, tcgen05 implicit GEMM "
+                              "(all 216 launches of one 7-frame GOP, down+up)",
                     "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
-                    "traffic": None, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "traffic": traffic, "peak_source": f"of {src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches": c["launches"],
                     "share_of_step": c["ms"] / tot_ms if tot_ms else None,
                     "classes": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],

@@ -54,6 +54,13 @@ struct TcTempArgs {
   void* dbg = nullptr;               // optional device buffer of 16 x int64: per-role barrier wait cycles of CTA 0
   __nv_bfloat16* outAct = nullptr;   // EPI_GA: optional LeakyReLU'd copy (input of the GMM head)
   int outAct_pitch = 0;
+  // EPI_GMM (fused GMM head + sampler): this launch's accumulator columns are [logit | log-scale | mean] x 48 hf of mixture
+  // component gmm_k; v[hf] (+)= softmax_hf(logit) * (eps * exp(clamp(ls)) + mean) goes to quads 1..12 of z (stored for
+  // gmm_k == 0, accumulated otherwise).  eps: injected [B,48,5,T,h,w] or null -> Philox stream (seed, offset).
+  int gmm_k = 0, gmm_T = 1;
+  long long gmm_hw = 0;
+  const float* eps = nullptr;
+  uint64_t seed = 0, offset = 0;
 };
 
 int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int cout, int cin_ref, int taps, int cin_buf, int xreal,

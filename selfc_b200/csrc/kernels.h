@@ -15,6 +15,9 @@ int launch_quantize(const float* x, uint8_t* q8, float* qf, size_t n, cudaStream
 int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q, long long M, long long hw, cudaStream_t st);
 int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st);
 int launch_gaussian_down(const float* x, const float* k13, float* y, int NC, int H, int W, cudaStream_t st);
+// BF16 mode: lr [N,3,h,w] -> quad 0 of z + the X slab (16 channels) of up to three slab-planar dense buffers, one pass
+int launch_lr_ingest_slab(const float* lr, float* z, __nv_bfloat16* d0, __nv_bfloat16* d1, __nv_bfloat16* d2, long long M, long long hw,
+                          cudaStream_t st);
 template <typename T>
 int launch_nchw_to_dense(const float* x, T* dst, int pitch, long long slabM, int off, int C, int cpad, long long M, long long hw,
                          cudaStream_t st);
@@ -26,7 +29,7 @@ int launch_dense_to_nchw(const T* src, int pitch, long long slabM, int off, floa
 
 // ---- conv_simt.cu: fp32-FMA implicit GEMM (strict-fp32 mode and the small GEMMs of both modes) --------------
 enum TapMode { TAP_POINT = 0, TAP_SPATIAL = 1, TAP_TEMPORAL = 2, TAP_TMIX = 3 };
-enum Epilogue { EPI_STORE = 0, EPI_COUPLE_Y1 = 1, EPI_COUPLE_S = 2, EPI_COUPLE_Y2 = 3, EPI_GA = 4 };
+enum Epilogue { EPI_STORE = 0, EPI_COUPLE_Y1 = 1, EPI_COUPLE_S = 2, EPI_COUPLE_Y2 = 3, EPI_GA = 4, EPI_GMM = 5 };
 
 template <typename T>
 struct ConvArgs {
@@ -87,7 +90,8 @@ int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, u
 // params as planar quads [180][M][4] in the permuted channel order n' = j*240 + k*48 + hf (tcgen05 head); v -> planar z
 int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* z, int B, int T, int h,
                              int w, cudaStream_t st);
-int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, cudaStream_t st);
+// by_component: rows k*144 + j*48 + hf (fused head + sampler, one GEMM per mixture component); else j*240 + k*48 + hf
+int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, bool by_component, cudaStream_t st);
 int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, long long hw, cudaStream_t st);
 
 }  // namespace selfc

@@ -61,6 +61,7 @@ struct HeadW {
   float* b[3] = {};
   int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 720}, np[3] = {128, 256, 736};
   TcTempW t[5];            // BF16 mode: 64->128, 128->256, 256->240 x3 as tcgen05 pointwise GEMMs
+  TcTempW g[5];            // BF16 mode: 256->144 per mixture component (fused head + sampler)
 };
 
 }  // namespace selfc
@@ -141,9 +142,9 @@ static Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w
   ws.h1 = take(M * 128 * es);
   ws.h2 = take(M * 256 * es);
   ws.params = take(M * 720 * 4);
-  ws.nsplit = (int)((size_t)h * w / 2048);
+  ws.nsplit = (int)((size_t)h * w / 512);     // ga_stat: enough CTAs (nsplit x B*T) to cover the DRAM latency
   if (ws.nsplit < 1) ws.nsplit = 1;
-  if (ws.nsplit > 32) ws.nsplit = 32;
+  if (ws.nsplit > 128) ws.nsplit = 128;
   ws.wmap = take((size_t)h * w * 4);
   ws.partial = take((size_t)B * T * ws.nsplit * 64 * 4);
   ws.wmat = take((size_t)B * T * T * 4);
@@ -326,10 +327,19 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   const int xp = ctx->xpad3;
   const long long slabM = dense_slab(ctx, d);
   // LR ingest: x1 of the reversed block 8, and the X slot of local_m1
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<float>(lr, z, 4, 0, 0, 3, 4, M, hw, st));
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, gbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, hbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
-  PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, stpbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
+  bool ingested = false;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (slabM != 0 && xp == 16) {
+      PROF(ctx, st, 5, (double)M * (12 + 16 + 3 * 32), launch_lr_ingest_slab(lr, z, gbuf, hbuf, stpbuf, M, hw, st));
+      ingested = true;
+    }
+  }
+  if (!ingested) {
+    PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<float>(lr, z, 4, 0, 0, 3, 4, M, hw, st));
+    PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, gbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
+    PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, hbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
+    PROF(ctx, st, 5, (double)M * 28, launch_nchw_to_dense<T>(lr, stpbuf, ws.gpitch, slabM, 0, 3, xp, M, hw, st));
+  }
   // STPNet.forward (:366-374)
   for (int i = 0; i < 6; ++i) {
     const DenseW& W = ctx->stp[i];
@@ -342,7 +352,7 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
                                 i == 5 ? fact : nullptr));
   }
   // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
-  bool head_done = false;
+  bool head_done = false, sampled = false;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     if (ctx->mode == SELFC_MODE_BF16 && ctx->head.t[0].img != nullptr) {
       // pointwise GEMMs over all M pixels, viewed as 2 pseudo-frames of ceil(M/2) rows (two accumulators in flight)
@@ -357,8 +367,29 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
       };
       PROF(ctx, st, 3, 2.0 * M * 64 * 128, pointwise(ctx->head.t[0], fact, kStpC, h1, 128, nullptr, 0, 0, 1));
       PROF(ctx, st, 3, 2.0 * M * 128 * 256, pointwise(ctx->head.t[1], h1, 128, h2, 256, nullptr, 0, 0, 1));
-      for (int j = 0; j < 3; ++j)
-        PROF(ctx, st, 3, 2.0 * M * 256 * 240, pointwise(ctx->head.t[2 + j], h2, 256, nullptr, 0, params, 720, 240 * j, 0));
+      // SELFC_GMM_FUSED=1: head GEMM with the sampler fused into its epilogue, one launch per mixture component (the
+      // 720-channel tensor never exists: 2.6 GB less workspace traffic at 1080p).  Parity-tested, but OFF by default: the
+      // Philox / Box-Muller / exp work then runs on the GEMM's four epilogue warps per SM and is latency-bound there
+      // (5 x 0.61 ms vs 3 x 0.245 ms GEMM + 0.98 ms full-occupancy sampler, measured).
+      static int fused = -1;
+      if (fused < 0) {
+        const char* e = getenv("SELFC_GMM_FUSED");
+        fused = (e && atoi(e) != 0) ? 1 : 0;
+      }
+      if (fused && ctx->head.g[0].img != nullptr) {
+        // 256 -> 720 and the soft-GMM draw, one launch per mixture component: the 720-channel tensor never exists
+        for (int k = 0; k < kGmmK; ++k) {
+          TcTempArgs t;
+          t.in = h2; t.in_pitch = 256; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
+          t.epi = EPI_GMM; t.z = z;
+          t.gmm_k = k; t.gmm_T = d.T; t.gmm_hw = hw; t.eps = eps; t.seed = seed; t.offset = offset;
+          PROF(ctx, st, k == 0 ? 3 : 4, k == 0 ? 2.0 * M * 256 * 720 : (double)M * (720 + 48) * 4, launch_temporal_tc(ctx->head.g[k], t, st));
+        }
+        sampled = true;
+      } else {
+        for (int j = 0; j < 3; ++j)
+          PROF(ctx, st, 3, 2.0 * M * 256 * 240, pointwise(ctx->head.t[2 + j], h2, 256, nullptr, 0, params, 720, 240 * j, 0));
+      }
       head_done = true;
     }
   }
@@ -379,7 +410,8 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
     a.act = 0; a.outT = nullptr; a.outF = params; a.outF_pitch = 720;
     PROF(ctx, st, 3, 2.0 * M * 256 * 720, launch_conv_simt<T>(a, st));
   }
-  if (head_done)
+  if (sampled) {
+  } else if (head_done)
     PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample_planar(params, eps, seed, offset, z, d.B, d.T, d.h, d.w, st));
   else
     PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample(params, false, eps, seed, offset, z, false, /*planar z*/ -1, 0, d.B, d.T, d.h, d.w, st));
@@ -497,6 +529,7 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
     free_temporal_weights(ctx->ga[i].tp);
   }
   for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.t[j]);
+  for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.g[j]);
   delete ctx;
   return 0;
 }
@@ -627,9 +660,12 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     SELFC_TRY(pack_temporal_weights(ctx->head.t[1], p[P_TAIL + 2], p[P_TAIL + 3], 256, 128, 1, 128, 128, 128, st));
     float* wperm = fp(head_perm_w);
     float* bperm = fp(head_perm_b);
-    SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, st));
+    SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, false, st));
     for (int j = 0; j < 3; ++j)
       SELFC_TRY(pack_temporal_weights(ctx->head.t[2 + j], wperm + (size_t)240 * j * 256, bperm + 240 * j, 240, 256, 1, 256, 256, 256, st));
+    SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, true, st));
+    for (int k = 0; k < kGmmK; ++k)
+      SELFC_TRY(pack_temporal_weights(ctx->head.g[k], wperm + (size_t)144 * k * 256, bperm + 144 * k, 144, 256, 1, 256, 256, 256, st));
   }
   ctx->loaded = true;
   return 0;

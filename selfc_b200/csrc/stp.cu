@@ -56,53 +56,72 @@ __global__ void __launch_bounds__(256) ga_stat_kernel(const T* __restrict__ x, i
   }
 }
 
-// one CTA per clip: d -> q,k -> A = q k^T / 64 -> row softmax -> W [T][T], column sums
-__global__ void __launch_bounds__(64) ga_weights_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ fcb,
-                                                        const float* __restrict__ p2w, const float* __restrict__ p2b,
-                                                        const float* __restrict__ p3w, const float* __restrict__ p3b,
-                                                        float* __restrict__ wmat, float* __restrict__ wsum, int T) {
+// one CTA per clip, one warp-pair (64 threads) per frame: d -> q,k -> A = q k^T / 64 -> row softmax -> W [T][T], column sums
+__global__ void __launch_bounds__(1024) ga_weights_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ fcb,
+                                                          const float* __restrict__ p2w, const float* __restrict__ p2b,
+                                                          const float* __restrict__ p3w, const float* __restrict__ p3b,
+                                                          float* __restrict__ wmat, float* __restrict__ wsum, int T) {
   constexpr int MAXT = 32;
-  __shared__ float d[MAXT][64], q[MAXT][64], k[MAXT][64], A[MAXT][MAXT];
-  const int b = blockIdx.x, c = threadIdx.x;
-  for (int t = 0; t < T; ++t) {
+  extern __shared__ float sm[];
+  float* d = sm;                      // [T][64]
+  float* q = d + T * 64;              // [T][65]  (padded: the q.k products read rows with stride 65)
+  float* k = q + T * 65;              // [T][65]
+  float* A = k + T * 65;              // [T][MAXT]
+  const int b = blockIdx.x;
+  const int nfr = blockDim.x / 64;    // frames handled concurrently
+  const int c = threadIdx.x & 63, f0 = threadIdx.x >> 6;
+  for (int t = f0; t < T; t += nfr) {
     float s = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) s += partial[(((long long)b * T + t) * nsplit + sp) * 64 + c];
-    d[t][c] = s + fcb[0];
-  }
-  __syncthreads();
-  for (int t = 0; t < T; ++t) {
-    float sq = p2b[c], sk = p3b[c];
-    for (int i = 0; i < 64; ++i) {
-      sq += p2w[c * 64 + i] * d[t][i];
-      sk += p3w[c * 64 + i] * d[t][i];
+    const float* pp = partial + (((long long)b * T + t) * nsplit) * 64 + c;
+    int sp = 0;
+    for (; sp + 16 <= nsplit; sp += 16) {        // 16 independent loads in flight, summed in a fixed order (deterministic)
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = __ldg(pp + (long long)(sp + u) * 64);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += v[u];
     }
-    q[t][c] = sq;
-    k[t][c] = sk;
+    for (; sp < nsplit; ++sp) s += __ldg(pp + (long long)sp * 64);
+    d[t * 64 + c] = s + fcb[0];
   }
   __syncthreads();
-  for (int e = c; e < T * T; e += 64) {
+  for (int t = f0; t < T; t += nfr) {
+    float sq = p2b[c], sk = p3b[c];
+    const float* w2 = p2w + c * 64;
+    const float* w3 = p3w + c * 64;
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) {
+      const float dv = d[t * 64 + i];
+      sq += __ldg(w2 + i) * dv;
+      sk += __ldg(w3 + i) * dv;
+    }
+    q[t * 65 + c] = sq;
+    k[t * 65 + c] = sk;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
     const int t = e / T, u = e % T;
     float s = 0.f;
-    for (int i = 0; i < 64; ++i) s += q[t][i] * k[u][i];
-    A[t][u] = s / 64.0f;
+    for (int i = 0; i < 64; ++i) s += q[t * 65 + i] * k[u * 65 + i];
+    A[t * MAXT + u] = s / 64.0f;
   }
   __syncthreads();
-  if (c < T) {
-    const int t = c;
+  if (threadIdx.x < T) {
+    const int t = threadIdx.x;
     float mx = -INFINITY;
-    for (int u = 0; u < T; ++u) mx = fmaxf(mx, A[t][u]);
+    for (int u = 0; u < T; ++u) mx = fmaxf(mx, A[t * MAXT + u]);
     float sum = 0.f;
-    for (int u = 0; u < T; ++u) { A[t][u] = expf(A[t][u] - mx); sum += A[t][u]; }
+    for (int u = 0; u < T; ++u) { A[t * MAXT + u] = expf(A[t * MAXT + u] - mx); sum += A[t * MAXT + u]; }
     for (int u = 0; u < T; ++u) {
-      A[t][u] = A[t][u] / sum;
-      wmat[((long long)b * T + t) * T + u] = A[t][u];
+      A[t * MAXT + u] = A[t * MAXT + u] / sum;
+      wmat[((long long)b * T + t) * T + u] = A[t * MAXT + u];
     }
   }
   __syncthreads();
-  if (c < T) {
+  if (threadIdx.x < T) {
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s += A[t][c];
-    wsum[(long long)b * T + c] = s;
+    for (int t = 0; t < T; ++t) s += A[t * MAXT + threadIdx.x];
+    wsum[(long long)b * T + threadIdx.x] = s;
   }
 }
 
@@ -163,71 +182,64 @@ __global__ void __launch_bounds__(256) ga_mix_kernel(const __nv_bfloat16* __rest
   }
 }
 
-// T <= 8: one thread per (clip, pixel, 8-channel group) produces ALL T output frames, so every P element is read from
+// T <= 8: one thread per (clip, pixel, 4-channel group) produces ALL T output frames, so every P element is read from
 // DRAM exactly once (the per-output-frame kernel above re-reads each P value T times from frames that are 16 MB apart).
-__global__ void __launch_bounds__(256) ga_mix_allframes_kernel(const __nv_bfloat16* __restrict__ P, const __nv_bfloat16* __restrict__ x,
-                                                               const float* __restrict__ wmat, __nv_bfloat16* __restrict__ outT,
-                                                               int outT_pitch, long long outT_slabM, float* __restrict__ outF,
-                                                               int outF_pitch, __nv_bfloat16* __restrict__ outAct, int T, long long hw,
-                                                               long long Bhw) {
+// 4 channels per thread keep the register count low enough for 4 CTAs per SM (the loads of 2*T frames are all in flight).
+__global__ void __launch_bounds__(256, 4) ga_mix_allframes_kernel(const __nv_bfloat16* __restrict__ P, const __nv_bfloat16* __restrict__ x,
+                                                                  const float* __restrict__ wmat, __nv_bfloat16* __restrict__ outT,
+                                                                  int outT_pitch, long long outT_slabM, float* __restrict__ outF,
+                                                                  int outF_pitch, __nv_bfloat16* __restrict__ outAct, int T, long long hw,
+                                                                  long long Bhw) {
   constexpr int TM = 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long bp = idx >> 3;                  // b * hw + pix
-  const int c0 = (int)(idx & 7) * 8;
+  const long long bp = idx >> 4;                  // b * hw + pix
+  const int c0 = (int)(idx & 15) * 4;
   if (bp >= Bhw) return;
   const long long b = bp / hw, pix = bp - b * hw;
-  auto unpack = [](const uint4 r, float* v) {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-      v[2 * i] = __low2float(h);
-      v[2 * i + 1] = __high2float(h);
-    }
+  auto unpack = [](const uint2 r, float* v) {
+    __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&r.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    v[0] = __low2float(h0); v[1] = __high2float(h0); v[2] = __low2float(h1); v[3] = __high2float(h1);
   };
   auto pack = [](const float* v) {
-    uint4 r;
+    uint2 r;
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
     r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
-    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
     return r;
   };
-  float pv[TM][8];
-  uint4 xr[TM];
+  uint2 pr[TM], xr[TM];
 #pragma unroll
   for (int t = 0; t < TM; ++t) {
     if (t < T) {
       const long long m = (b * T + t) * hw + pix;
-      unpack(__ldg(reinterpret_cast<const uint4*>(P + m * kStpC + c0)), pv[t]);
-      xr[t] = __ldg(reinterpret_cast<const uint4*>(x + m * kStpC + c0));
+      pr[t] = __ldg(reinterpret_cast<const uint2*>(P + m * kStpC + c0));
+      xr[t] = __ldg(reinterpret_cast<const uint2*>(x + m * kStpC + c0));
     }
   }
+  float pv[TM][4];
+#pragma unroll
+  for (int t = 0; t < TM; ++t)
+    if (t < T) unpack(pr[t], pv[t]);
   const float* wm = wmat + b * T * T;               // W[b][t][t']
 #pragma unroll
   for (int tq = 0; tq < TM; ++tq) {
     if (tq >= T) continue;
     const long long m = (b * T + tq) * hw + pix;
-    float acc[8];
+    float acc[4];
     unpack(xr[tq], acc);
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
       if (t < T) {
         const float wv = __ldg(wm + t * T + tq);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv, pv[t][j], acc[j]);
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv, pv[t][j], acc[j]);
       }
     }
-    if (outT) *reinterpret_cast<uint4*>(outT + dense_off(m, c0, outT_pitch, outT_slabM)) = pack(acc);
-    if (outF) {
-      float* o = outF + m * outF_pitch + c0;
-      store4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
-      store4(o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
-    }
+    if (outT) *reinterpret_cast<uint2*>(outT + dense_off(m, c0, outT_pitch, outT_slabM)) = pack(acc);
+    if (outF) store4(outF + m * outF_pitch + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
     if (outAct) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = lrelu02(acc[j]);
-      *reinterpret_cast<uint4*>(outAct + m * kStpC + c0) = pack(acc);
+      for (int j = 0; j < 4; ++j) acc[j] = lrelu02(acc[j]);
+      *reinterpret_cast<uint2*>(outAct + m * kStpC + c0) = pack(acc);
     }
   }
 }
@@ -238,7 +250,7 @@ int launch_ga_mix(const __nv_bfloat16* P, const __nv_bfloat16* x, const float* w
   if (M == 0) return 0;
   SELFC_CHECK_ARG(outF == nullptr || outF_pitch % 4 == 0, "ga_mix: outF pitch");
   if (T <= 8) {
-    ga_mix_allframes_kernel<<<cdiv((long long)B * hw * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch,
+    ga_mix_allframes_kernel<<<cdiv((long long)B * hw * 16, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch,
                                                                              outAct, T, hw, (long long)B * hw);
     SELFC_LAUNCH_CHECK("ga_mix_allframes_kernel");
     return 0;
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       const float4 l = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + i, (size_t)m)));
-      sk += expf(l.x - mk) + expf(l.y - mk) + expf(l.z - mk) + expf(l.w - mk);
+      sk += __expf(l.x - mk) + __expf(l.y - mk) + __expf(l.z - mk) + __expf(l.w - mk);
     }
     mx[k] = mk;
     inv[k] = 1.0f / sk;
@@ -360,8 +372,9 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float ep = ep4[e];
-        const float pi = expf(lg[e] - mx[k]) * inv[k];
-        out[e] += pi * (ep * expf(fminf(fmaxf(ls[e], -7.f), 7.f)) + mu[e]);
+        // ex2.approx based exp: relative error ~2^-21 on arguments in [-7, 7] / (-inf, 0]
+        const float pi = __expf(lg[e] - mx[k]) * inv[k];
+        out[e] += pi * (ep * __expf(fminf(fmaxf(ls[e], -7.f), 7.f)) + mu[e]);
       }
     }
     store4(z + quad_off((size_t)M, 1 + i, (size_t)m), make_float4(out[0], out[1], out[2], out[3]));
@@ -370,9 +383,11 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
 
 // tail_gmm.5 rows hf*15+k*3+j  ->  j*240 + k*48 + hf  (so each tcgen05 pass emits one parameter kind, hf contiguous)
 __global__ void permute_gmm_rows_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wp,
-                                        float* __restrict__ bp) {
+                                        float* __restrict__ bp, int by_component) {
   const int np = blockIdx.x;                      // permuted row
-  const int j = np / 240, k = (np % 240) / 48, hf = np % 48;
+  const int hf = np % 48;
+  const int j = by_component ? (np % 144) / 48 : np / 240;
+  const int k = by_component ? np / 144 : (np % 240) / 48;
   const int src = hf * 15 + k * 3 + j;
   for (int c = threadIdx.x; c < 256; c += blockDim.x) wp[np * 256 + c] = w[src * 256 + c];
   if (threadIdx.x == 0) bp[np] = b[src];
@@ -411,7 +426,9 @@ template int launch_ga_stat<__nv_bfloat16>(const __nv_bfloat16*, int, const floa
 int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const float* p2w, const float* p2b, const float* p3w,
                       const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st) {
   SELFC_CHECK_ARG(T >= 1 && T <= 32, "GlobalAgg: temporal length %d outside [1,32]", T);
-  ga_weights_kernel<<<B, 64, 0, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
+  const int threads = 64 * (T < 16 ? T : 16);
+  const size_t smem = (size_t)(T * 64 + 2 * T * 65 + T * 32) * sizeof(float);
+  ga_weights_kernel<<<B, threads, smem, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
   SELFC_LAUNCH_CHECK("ga_weights_kernel");
   return 0;
 }
@@ -442,8 +459,8 @@ int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t see
   return 0;
 }
 
-int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, cudaStream_t st) {
-  permute_gmm_rows_kernel<<<720, 128, 0, st>>>(w, b, wp, bp);
+int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, bool by_component, cudaStream_t st) {
+  permute_gmm_rows_kernel<<<720, 128, 0, st>>>(w, b, wp, bp, by_component ? 1 : 0);
   SELFC_LAUNCH_CHECK("permute_gmm_rows_kernel");
   return 0;
 }

@@ -64,6 +64,10 @@ struct Params {
   int resid_pitch;
   __nv_bfloat16* outAct;
   int outAct_pitch;
+  int gmm_k, gmm_T;     // EPI_GMM: mixture component of this launch, frames per clip (eps index)
+  long long gmm_hw;     //          pixels per frame
+  const float* eps;     //          injected noise [B,48,5,T,h,w] or null
+  uint64_t seed, offset;
   int* err;
   long long* dbg;   // optional: CTA 0 writes cycles waited per barrier site [16] + totals
 };
@@ -334,6 +338,75 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
         tc_fence_after();
         const int ncols = p.epi == EPI_COUPLE_Y1 ? 16 : (p.epi == EPI_STORE ? ((p.cout + 15) & ~15) : kHF);
         const bool live = valid && (long long)m < p.m_limit;
+        if (p.epi == EPI_GMM) {
+          // ---- fused GMM head + sampler (SelfC_GMM_arch_inv.py:383-394): columns [0,48) logits, [48,96) log-scales,
+          // [96,144) means of component k; softmax over the 48 hf channels
+          float pi[kHF];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c3 = 0; c3 < 3; ++c3) {
+            uint32_t r[16];
+            tmem_ld16(acol + (uint32_t)(16 * c3), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pi[16 * c3 + j] = __uint_as_float(r[j]) + sbias[16 * c3 + j];
+              mx = fmaxf(mx, pi[16 * c3 + j]);
+            }
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < kHF; ++j) {
+            pi[j] = __expf(pi[j] - mx);
+            sum += pi[j];
+          }
+          const float inv = 1.0f / sum;
+          const size_t Mreal = (size_t)p.m_limit;
+          const long long n = live ? (long long)m / p.gmm_hw : 0;
+          const long long gpix = (long long)m - n * p.gmm_hw;
+          const int gt = (int)(n % p.gmm_T);
+          const long long gb = n / p.gmm_T;
+#pragma unroll
+          for (int c3 = 0; c3 < 3; ++c3) {
+            uint32_t rl[16], rm[16];
+            tmem_ld16(acol + (uint32_t)(kHF + 16 * c3), rl);
+            tmem_ld16(acol + (uint32_t)(2 * kHF + 16 * c3), rm);
+            tmem_ld_wait();
+            if (c3 == 2) {                       // the whole accumulator is in registers: hand it back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(aslot));
+            }
+            if (!live) continue;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int hfq = 4 * c3 + q4;
+              float ep4[4];
+              if (p.eps) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  ep4[e] = __ldg(p.eps + (uint64_t)(((((gb * kHF + 4 * hfq + e) * kGmmK + p.gmm_k) * p.gmm_T + gt) * p.gmm_hw) + gpix));
+              } else {
+                philox_normal4(eps_group(gb, hfq, p.gmm_k, gt, gpix, p.gmm_T, p.gmm_hw), p.seed, p.offset, ep4);
+              }
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int hf = 4 * hfq + e, cc = 4 * q4 + e;
+                const float ls = fminf(fmaxf(__uint_as_float(rl[cc]) + sbias[kHF + hf], -7.f), 7.f);
+                const float mu = __uint_as_float(rm[cc]) + sbias[2 * kHF + hf];
+                o[e] = pi[hf] * inv * fmaf(ep4[e], __expf(ls), mu);
+              }
+              float* zq = p.z + quad_off(Mreal, 1 + hfq, m);
+              if (p.gmm_k > 0) {
+                const float4 old = ld_nc4(zq);
+                o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+              }
+              store4(zq, make_float4(o[0], o[1], o[2], o[3]));
+            }
+          }
+          continue;
+        }
         const uint32_t ebuf = epi_base + (uint32_t)((gframe & 1) * p.epi_quads * MT + row) * 16u;
         if (p.epi_quads) {
           const long long t0 = clock64();
@@ -590,6 +663,9 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   p.copyA = a.copyA; p.copyA_pitch = a.copyA_pitch; p.copyB = a.copyB; p.copyB_pitch = a.copyB_pitch; p.copy_pad = a.copy_pad;
   p.wmat = a.wmat; p.wsum = a.wsum; p.resid = a.resid; p.resid_pitch = a.resid_pitch;
   p.outAct = a.outAct; p.outAct_pitch = a.outAct_pitch;
+  p.gmm_k = a.gmm_k; p.gmm_T = a.gmm_T; p.gmm_hw = a.gmm_hw; p.eps = a.eps; p.seed = a.seed; p.offset = a.offset;
+  SELFC_CHECK_ARG(a.epi != EPI_GMM || (w.npad == 3 * kHF && a.z != nullptr && a.gmm_hw > 0 && a.gmm_T >= 1 && a.gmm_k >= 0 && a.gmm_k < kGmmK),
+                  "temporal_tc: GMM epilogue needs N = 144, the latent state and the clip shape");
   p.err = tc::err_flag_for_device();
   p.dbg = reinterpret_cast<long long*>(a.dbg);
   if (!p.dbg && tc::debug_slots()) {          // SELFC_TC_DBG=1: every launch records CTA 0's barrier-wait cycles
