@@ -50,9 +50,15 @@ constexpr int NSTAGE_MAX = 8;
 constexpr int BAR_BYTES = 256;
 
 struct Params {
+  // up to two independent problems of identical shape in one launch (G and H of an InvBlockExp read the same y1 and
+  // differ only in weights and buffer): CTA parity selects the problem, each gets half of the grid
   const void* wimg;
+  const void* wimg2;
   const float* bias;
+  const float* bias2;
   __nv_bfloat16* buf;
+  __nv_bfloat16* buf2;
+  int nprob;             // 1 or 2
   long long slabM;       // pixels per slab (= N*h*w)
   int out_slab, N, h, w, nks, kps;
   int tiles_x, tiles_y, ntiles;
@@ -72,8 +78,16 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                  const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int prob = p.nprob == 2 ? (int)(blockIdx.x & 1u) : 0;
+  const int rank = p.nprob == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // this CTA walks tiles rank, rank + nctas, ...
+  const int nctas = p.nprob == 2 ? (int)((gridDim.x + 1 - prob) >> 1) : (int)gridDim.x;
+  const CUtensorMap* tmap = prob ? &tmap_b : &tmap_a;
+  const void* wimg = prob ? p.wimg2 : p.wimg;
+  const float* biasp = prob ? p.bias2 : p.bias;
+  __nv_bfloat16* obuf = prob ? p.buf2 : p.buf;
   const int NST = p.nst;
   const int KPS = p.kps;
   const int STAGE = KPS * SUB_BYTES;
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
       mbar_init(tempty_bar(a), 4);
     }
     fence_barrier_init();
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)TMEM_COLS);
   tc_fence_before();
@@ -122,12 +136,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
       const uint32_t wbytes = 3u * nks * WTILE_BYTES;
       mbar_expect_tx(w_bar, wbytes);
       for (int ky = 0; ky < 3; ++ky)
-        bulk_g2s(w_base + ky * nks * WTILE_BYTES, (const uint8_t*)p.wimg + (size_t)ky * nks * WTILE_BYTES, (uint32_t)nks * WTILE_BYTES,
+        bulk_g2s(w_base + ky * nks * WTILE_BYTES, (const uint8_t*)wimg + (size_t)ky * nks * WTILE_BYTES, (uint32_t)nks * WTILE_BYTES,
                  w_bar);
       pdl_wait();      // weights are static; activations come from the previous kernel in the stream
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int tile = rank; tile < p.ntiles; tile += nctas) {
         const int tx = tile % p.tiles_x;
         const int ty = (tile / p.tiles_x) % p.tiles_y;
         const int n = tile / (p.tiles_x * p.tiles_y);
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
         for (int c0 = 0; c0 < nks; c0 += KPS) {
           mbar_wait(empty_bar(s), ph ^ 1u, p.err, 31);
           mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
-          tma_load_5d(a_base + s * STAGE, &tmap, full_bar(s), 0, x0, y0, n, c0);
+          tma_load_5d(a_base + s * STAGE, tmap, full_bar(s), 0, x0, y0, n, c0);
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
@@ -150,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
     const uint32_t hi_a = desc_hi(256, 6);            // activations: SWIZZLE_32B rows, 8-row atoms of 256 bytes
     const uint32_t hi_b = desc_hi(128, 0);            // weights: no-swizzle core matrices, 8-row groups 128 bytes apart
     const uint32_t b_ky = (uint32_t)nks * (WTILE_BYTES >> 4);
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = rank; tile < p.ntiles; tile += nctas, ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u, p.err, 33);
@@ -189,10 +203,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
     pdl_wait();
     float bias[NOUT];
 #pragma unroll
-    for (int j = 0; j < NOUT; ++j) bias[j] = __ldg(p.bias + j);
+    for (int j = 0; j < NOUT; ++j) bias[j] = __ldg(biasp + j);
     const size_t slab_elems = (size_t)p.slabM * 16;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = rank; tile < p.ntiles; tile += nctas, ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       const int tx = tile % p.tiles_x;
@@ -206,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
         const int y = ty * ROWS + mb * 4 + q;
         const bool ok = lane < VALID_W && x < p.w && y < p.h;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
-        __nv_bfloat16* o = p.buf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)n * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
+        __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)n * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
 #pragma unroll
         for (int n0 = 0; n0 < NOUT; n0 += 16) {
           uint32_t r0[16], r1[16], r2[16];
@@ -373,9 +387,13 @@ void free_tc_weights(TcConvW& w) {
   w.img_bytes = 0;
 }
 
-int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st) {
+int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
+                      const TcConvW* w2, __nv_bfloat16* buf2) {
   SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
   SELFC_CHECK_ARG(out_off % 16 == 0 && aligned16(buf) && slabM == (long long)N * h * wd, "conv3x3_tc: slab layout / alignment");
+  const bool dual = w2 != nullptr;
+  SELFC_CHECK_ARG(!dual || (w2->img != nullptr && w2->cin_buf == cin && buf2 != nullptr && aligned16(buf2) && buf2 != buf),
+                  "conv3x3_tc: the second problem must have the same shape and its own buffer");
   tc::EncodeTiledFn encode = tc::get_encode_fn();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -389,15 +407,18 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   }
   const int nks = cin / 16;
   int kps = kps_pref < nks ? kps_pref : nks;
-  const int fixed = tc3::BAR_BYTES + (int)w.img_bytes + 1024;
+  const int fixed = tc3::BAR_BYTES + (int)w.img_bytes + 1024;      // both problems' weights have the same size
   while (kps > 1 && (227 * 1024 - fixed) / (kps * tc3::SUB_BYTES) < 3) --kps;
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap2;
   const cuuint64_t gdim[5] = {16, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
   const cuuint64_t gstr[4] = {32, (cuuint64_t)wd * 32, (cuuint64_t)h * wd * 32, (cuuint64_t)slabM * 32};
   const cuuint32_t box[5] = {16, (cuuint32_t)tc3::WT, (cuuint32_t)tc3::HT, 1, (cuuint32_t)kps};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS)
+    r = encode(&tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dual ? buf2 : buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (%dx%dx%d, %d slabs)", (int)r, N, h, wd, nks);
     return SELFC_E_CUDA;
@@ -407,6 +428,10 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   p.wimg = w.img;
   p.bias = w.bias;
   p.buf = buf;
+  p.nprob = dual ? 2 : 1;
+  p.wimg2 = dual ? w2->img : w.img;
+  p.bias2 = dual ? w2->bias : w.bias;
+  p.buf2 = dual ? buf2 : buf;
   p.slabM = slabM;
   p.out_slab = out_off / 16;
   p.N = N;
@@ -431,8 +456,9 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
     attr_set = true;
   }
   const int nsm = tc::num_sms();
-  const int grid = p.ntiles < nsm ? p.ntiles : nsm;
-  SELFC_CUDA(tc::launch_pdl(tc3::conv3x3_tc3_kernel, grid, tc3::THREADS, smem, st, tmap, p));
+  int grid = p.nprob * p.ntiles < nsm ? p.nprob * p.ntiles : nsm;
+  if (dual && (grid & 1)) --grid;                   // CTA parity selects the problem: both halves get the same CTA count
+  SELFC_CUDA(tc::launch_pdl(tc3::conv3x3_tc3_kernel, grid, tc3::THREADS, smem, st, tmap, tmap2, p));
   SELFC_LAUNCH_CHECK("conv3x3_tc3_kernel");
   return 0;
 }

@@ -165,12 +165,18 @@ static long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->m
 // ---- dense block: conv1..4 in place, then conv5 with the given epilogue ---------------------------------------
 template <typename T>
 static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pitch, const Dims& d, cudaStream_t st, int k_first = 0,
-                           int k_last = 3) {
+                           int k_last = 3, const DenseW* W2 = nullptr, T* buf2 = nullptr) {
   const long long slabM = dense_slab(ctx, d);
   for (int k = k_first; k <= k_last; ++k) {
     const int cin = W.xpad + kGrowth * k;
     const double flops = 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;   // algorithmic (unpadded) FLOPs
     if (ctx->mode == SELFC_MODE_BF16 && W.tc[k].img != nullptr) {
+      if (W2 != nullptr && W2->tc[k].img != nullptr) {
+        // two dense blocks of the same shape (G and H of a coupling) side by side: one launch per layer for both
+        PROF(ctx, st, 0, 2.0 * flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), slabM, cin, /*out_off=*/cin, d.B * d.T,
+                                                        d.h, d.w, st, &W2->tc[k], reinterpret_cast<__nv_bfloat16*>(buf2)));
+        continue;
+      }
       PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), slabM, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
       continue;
     }
@@ -240,11 +246,19 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
     return 0;
   };
   auto do_HG = [&]() -> int {
-    SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st));
+    // H and G read the same X slab (y1 / x1) and have the same shape: in BF16 mode their conv1..4 share launches
+    static int dual_on = -1;     // SELFC_DUAL_GH=0: separate launches for H and G (A/B)
+    if (dual_on < 0) {
+      const char* e = getenv("SELFC_DUAL_GH");
+      dual_on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const bool dual = dual_on && ctx->mode == SELFC_MODE_BF16 && H.tc[0].img != nullptr && G.tc[0].img != nullptr;
+    if (dual) SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st, 0, 3, &G, gbuf));
+    else SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st));
     ConvArgs<T> a = conv5_args<T>(ctx, H, hbuf, ws.gpitch, d);
     a.epi = EPI_COUPLE_S; a.sbuf = sbuf;
     PROF(ctx, st, 1, conv5_flops(H, d), launch_temporal<T>(ctx, H.t5, a, d, st));
-    SELFC_TRY(run_dense_convs<T>(ctx, G, gbuf, ws.gpitch, d, st));
+    if (!dual) SELFC_TRY(run_dense_convs<T>(ctx, G, gbuf, ws.gpitch, d, st));
     ConvArgs<T> g = conv5_args<T>(ctx, G, gbuf, ws.gpitch, d);
     g.epi = EPI_COUPLE_Y2; g.rev = rev ? 1 : 0; g.z = z; g.sbuf = sbuf;
     g.copyA = fbuf; g.copyA_pitch = ws.fpitch; g.copy_slabM = dense_slab(ctx, d);
