@@ -35,6 +35,9 @@ struct TcTempArgs {
   const __nv_bfloat16* in = nullptr;
   int in_pitch = 0, B = 0, T = 0, hw = 0;
   long long in_slabM = 0;            // != 0: `in` is a slab-planar dense buffer (common.cuh) of in_slabM pixels per slab
+  // EPI_COUPLE_HG: H(y1) and G(y1) of a coupling in ONE launch -- `in` is H's dense buffer, `in2` G's (same shape); the
+  // accumulator holds [H | G] (48 + 48 columns), s = 2*sigmoid(H)-1 never leaves the SM
+  const __nv_bfloat16* in2 = nullptr;
   int epi = 0, rev = 0, act = 0;
   __nv_bfloat16* outT = nullptr;
   int outT_pitch = 0, outT_off = 0;
@@ -69,6 +72,7 @@ int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int 
                           int xpad, cudaStream_t st);
 void free_temporal_weights(TcTempW& w);
 bool temporal_tc_supported(const TcTempW& w, int T);
-int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st);
+// w2: weights of the second conv of an EPI_COUPLE_HG launch (G), same shape as w (H)
+int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, const TcTempW* w2 = nullptr);
 
 }  // namespace selfc

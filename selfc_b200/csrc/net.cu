@@ -255,6 +255,25 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
     const bool dual = dual_on && ctx->mode == SELFC_MODE_BF16 && H.tc[0].img != nullptr && G.tc[0].img != nullptr;
     if (dual) SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st, 0, 3, &G, gbuf));
     else SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st));
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      static int fuse_hg = -1;     // SELFC_FUSE_HG=0: separate conv5 launches for H (-> s) and G (A/B)
+      if (fuse_hg < 0) {
+        const char* e = getenv("SELFC_FUSE_HG");
+        fuse_hg = (e && atoi(e) == 0) ? 0 : 1;
+      }
+      if (dual && fuse_hg && temporal_tc_supported(H.t5, d.T) && temporal_tc_supported(G.t5, d.T)) {
+        // conv5 of H and of G in ONE launch: s = 2*sigmoid(H(y1))-1 is consumed from the accumulator, never written to HBM
+        TcTempArgs t;
+        t.in = hbuf; t.in2 = gbuf; t.in_pitch = ws.gpitch; t.B = d.B; t.T = d.T; t.hw = (int)d.hw(); t.in_slabM = dense_slab(ctx, d);
+        t.epi = EPI_COUPLE_HG; t.rev = rev ? 1 : 0; t.z = z;
+        t.copyA = fbuf; t.copyA_pitch = ws.fpitch; t.copy_slabM = dense_slab(ctx, d);
+        prof_begin(ctx, st, 1, conv5_flops(H, d) + conv5_flops(G, d));
+        const int rc = launch_temporal_tc(H.t5, t, st, &G.t5);
+        prof_end(ctx, st);
+        if (rc == 0) return 0;
+        if (rc != SELFC_E_UNSUPPORTED) return rc;
+      }
+    }
     ConvArgs<T> a = conv5_args<T>(ctx, H, hbuf, ws.gpitch, d);
     a.epi = EPI_COUPLE_S; a.sbuf = sbuf;
     PROF(ctx, st, 1, conv5_flops(H, d), launch_temporal<T>(ctx, H.t5, a, d, st));

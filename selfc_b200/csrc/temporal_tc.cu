@@ -39,6 +39,10 @@ constexpr int BIAS_BYTES = 1024;   // up to 256 fp32
 struct Params {
   const void* wimg;
   const float* bias;
+  const void* wimg2;                          // EPI_COUPLE_HG: second conv (G); its chunks follow the first conv's in a frame
+  const float* bias2;
+  int nc_split;                               // chunks per frame that belong to the first conv / tensor map (== nchunk: single conv)
+  int nhalf;                                  // columns of one conv inside the accumulator (npad: single conv; npad/2: HG)
   int T, B, hw, nks, npad, taps, cout, nst;   // nks = K steps of 16 channels; nst = ring slots
   int kps, nchunk, nacc;                      // K steps per stage, stages per frame, rolling accumulators
   int epi_quads;                              // 16-byte quads of epilogue operands staged per pixel-frame (Y2: 24, Y1: 1)
@@ -83,7 +87,11 @@ __device__ __forceinline__ void stage_epilogue_operands(const Params& p, int til
     const int pix = (tile2 - b * p.tiles_p) * MT + row;
     if (pix < p.hw) {
       const size_t m = ((size_t)b * p.T + t2) * p.hw + pix;
-      if (p.epi == EPI_COUPLE_Y2) {
+      if (p.epi == EPI_COUPLE_HG) {
+#pragma unroll
+        for (int qd = 0; qd < kSQuads; ++qd)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + (uint32_t)(qd * MT) * 16u), "l"(p.z + quad_off(Mtot, 1 + qd, m)) : "memory");
+      } else if (p.epi == EPI_COUPLE_Y2) {
 #pragma unroll
         for (int qd = 0; qd < kSQuads; ++qd) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + (uint32_t)(qd * MT) * 16u), "l"(p.z + quad_off(Mtot, 1 + qd, m)) : "memory");
@@ -160,7 +168,8 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
 }
 
 template <int TAPS>
-__global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                  const __grid_constant__ CUtensorMap tmap2, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   const uint32_t bias_off = NST * STAGE_BYTES + BAR_BYTES;
   const uint32_t w_base = base + bias_off + BIAS_BYTES;
   // epilogue operand staging (double buffered, each thread owns its 16-byte slots): [2][epi_quads][128 px][16 B]
-  const uint32_t epi_base = w_base + (uint32_t)p.taps * p.nks * p.npad * 32u;
+  const uint32_t epi_base = w_base + (uint32_t)p.taps * p.nks * p.nhalf * 32u * (p.nc_split < p.nchunk ? 2u : 1u);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NST_MAX + s); };
   const uint32_t w_bar = bar_base + 8u * (2 * NST_MAX);
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  for (int i = threadIdx.x; i < p.npad; i += THREADS) sbias[i] = __ldg(p.bias + i);
+  for (int i = threadIdx.x; i < p.npad; i += THREADS) sbias[i] = i < p.nhalf ? __ldg(p.bias + i) : __ldg(p.bias2 + (i - p.nhalf));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -211,15 +220,20 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
 
   const int nks = p.nks, npad = p.npad;
   constexpr int taps = TAPS;
-  const uint32_t wtile = (uint32_t)npad * 32u;
+  const int nconv = p.nhalf;                          // N of one MMA (== npad unless two convs share the accumulator)
+  const uint32_t wtile = (uint32_t)nconv * 32u;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer: stages in (tile, frame, chunk) order =====================
       const uint32_t wbytes = (uint32_t)taps * nks * wtile;
-      mbar_expect_tx(w_bar, wbytes);
-      for (int tap = 0; tap < taps; ++tap)
+      const bool two = p.nc_split < NC;
+      mbar_expect_tx(w_bar, two ? 2u * wbytes : wbytes);
+      for (int tap = 0; tap < taps; ++tap) {
         bulk_g2s(w_base + tap * nks * wtile, (const uint8_t*)p.wimg + (size_t)tap * nks * wtile, (uint32_t)nks * wtile, w_bar);
+        if (two)
+          bulk_g2s(w_base + wbytes + tap * nks * wtile, (const uint8_t*)p.wimg2 + (size_t)tap * nks * wtile, (uint32_t)nks * wtile, w_bar);
+      }
       pdl_wait();      // weights are static; activations come from the previous kernel in the stream
       int s = 0;
       uint32_t ph = 0;
@@ -232,7 +246,8 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
           for (int c = 0; c < NC; ++c) {
             timed_wait(empty_bar(s), ph ^ 1u, p.err, 11, w_prod);
             mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);
-            if (p.in_slab) tma_load_4d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), 0, p0, b * T + f, c * KPS);
+            if (c >= p.nc_split) tma_load_4d(a_base + s * STAGE_BYTES, &tmap2, full_bar(s), 0, p0, b * T + f, (c - p.nc_split) * KPS);
+            else if (p.in_slab) tma_load_4d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), 0, p0, b * T + f, c * KPS);
             else tma_load_3d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), c * KPS * 16, p0, b * T + f);
             if (++s == NST) { s = 0; ph ^= 1u; }
           }
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   } else if (warp == 1) {
     {
       // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
-      const uint32_t idesc = umma_idesc_bf16(128, npad);
+      const uint32_t idesc = umma_idesc_bf16(128, nconv);
       // pixel-major input: one SWIZZLE_128B row of 64 channels per pixel, a K step advances 32 bytes inside the row;
       // slab input: KPS sub-tiles of [128 px][16 ch] (SWIZZLE_32B, 4 KB each), a K step advances one sub-tile
       const uint32_t hi_a = p.in_slab ? desc_hi(256, 6) : desc_hi(1024, 2);
@@ -257,7 +272,8 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       uint32_t ph = 0;
       const uint32_t amask = (uint32_t)(NACC - 1);          // NACC is 2 or 4
       const uint32_t hi_b = desc_hi(128, 0);
-      const uint32_t b_lbo = ((uint32_t)npad * 16u >> 4) << 16;
+      const uint32_t b_lbo = ((uint32_t)nconv * 16u >> 4) << 16;
+      const uint32_t wconv = (uint32_t)taps * nks * wtile;    // bytes of one conv's weight image
       const uint32_t wstep = wtile >> 4;                    // descriptor units per 16-channel weight tile
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, gbase += T) {
         // INPUT-frame-major: the tile of input frame fi feeds the outputs fi-1, fi, fi+1 (taps 2, 1, 0) back to back with
@@ -283,18 +299,22 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
             }
           }
           tc_fence_after();
-          uint32_t kk = 0;                                                // K step within the frame
+          uint32_t kk = 0;                                                // K step of the current conv within the frame
+          uint32_t cvoff_d = 0, cvoff_b = 0;                              // second conv: accumulator column / weight image offsets
           for (int c = 0; c < NC; ++c) {
+            if (c == p.nc_split) { kk = 0; cvoff_d = (uint32_t)nconv; cvoff_b = wconv >> 4; }
+            const int lc = c >= p.nc_split ? c - p.nc_split : c;
             timed_wait(full_bar(s), ph, p.err, 14, w_full);
             tc_fence_after();
-            const int ksn = nks - KPS * c < KPS ? nks - KPS * c : KPS;
+            const int ksn = nks - KPS * lc < KPS ? nks - KPS * lc : KPS;
             const uint32_t a_lo = desc_lo(a_base + s * STAGE_BYTES, 16);
             for (int ks = 0; ks < ksn; ++ks, ++kk) {
               const uint64_t ad = desc_join(a_lo + a_kinc * (uint32_t)ks, hi_a);
 #pragma unroll
               for (int j = 0; j < TAPS; ++j) {
                 if (!valid[j]) continue;
-                umma_bf16_elect(dcol[j], ad, desc_join(bdesc0[j] + kk * wstep, hi_b), idesc, started[j] | (kk > 0 ? 1u : 0u));
+                umma_bf16_elect(dcol[j] + cvoff_d, ad, desc_join(bdesc0[j] + cvoff_b + kk * wstep, hi_b), idesc,
+                                started[j] | (kk > 0 ? 1u : 0u));
               }
             }
             umma_commit_elect(empty_bar(s));
@@ -415,7 +435,10 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
         }
         for (int n0 = 0; n0 < ncols; n0 += 16) {
           float4 x2q[4], sq[4];
-          if (live && p.epi == EPI_COUPLE_Y2) {
+          if (live && p.epi == EPI_COUPLE_HG) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x2q[j] = lds4(ebuf + (uint32_t)((n0 / 4 + j) * MT) * 16u);
+          } else if (live && p.epi == EPI_COUPLE_Y2) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               x2q[j] = lds4(ebuf + (uint32_t)((n0 / 4 + j) * MT) * 16u);
@@ -424,8 +447,9 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
           } else if (live && p.epi == EPI_COUPLE_Y1) {
             x2q[0] = lds4(ebuf);
           }
-          uint32_t r[16];
+          uint32_t r[16], rg[16];
           tmem_ld16(acol + (uint32_t)n0, r);
+          if (p.epi == EPI_COUPLE_HG) tmem_ld16(acol + (uint32_t)(kHF + n0), rg);     // warp-uniform: G's columns of the accumulator
           tmem_ld_wait();
           if (!live) continue;
           float v[16];
@@ -482,6 +506,28 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                 __nv_bfloat16* o = p.copyB + dense_off((long long)m, 0, p.copyB_pitch, p.copy_slabM);
                 store_bf16x8(o, y);
                 if (p.copy_pad > 8) store_bf16x8(o + 8, y + 8);
+              }
+            } break;
+            case EPI_COUPLE_HG: {
+              // columns [n0, n0+16) hold H (v = h + bias), columns [48+n0, ...) hold G: s = 2*sigmoid(h)-1 stays in registers
+              float y[16];
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float* zp = p.z + quad_off(Mtot, 1 + (n0 + j) / 4, m) - j;
+                const float4 x2 = x2q[j / 4];
+                const float xr[4] = {x2.x, x2.y, x2.z, x2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float sv = __fdividef(2.0f, 1.0f + __expf(-v[j + e])) - 1.0f;
+                  const float g = __uint_as_float(rg[j + e]) + sbias[kHF + n0 + j + e];
+                  y[j + e] = p.rev ? (xr[e] - g) * __expf(-sv) : fmaf(xr[e], __expf(sv), g);
+                }
+                store4(zp + j, make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]));
+              }
+              if (p.copyA) {
+                __nv_bfloat16* o = p.copyA + dense_off((long long)m, n0, p.copyA_pitch, p.copy_slabM);
+                store_bf16x8(o, y);
+                store_bf16x8(o + 8, y + 8);
               }
             } break;
             case EPI_COUPLE_S: {
@@ -587,8 +633,13 @@ void free_temporal_weights(TcTempW& w) {
 
 bool temporal_tc_supported(const TcTempW& w, int T) { return w.img != nullptr && T >= 1 && T <= 32; }
 
-int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
+int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, const TcTempW* w2) {
   SELFC_CHECK_ARG(temporal_tc_supported(w, a.T), "temporal_tc: weights not packed or T=%d outside [1,32]", a.T);
+  const bool hg = a.epi == EPI_COUPLE_HG;
+  SELFC_CHECK_ARG(!hg || (w2 != nullptr && w2->img != nullptr && w2->cin_buf == w.cin_buf && w2->npad == w.npad && w.npad == kHF &&
+                          w.taps == 3 && a.in2 != nullptr && a.in_slabM != 0 && aligned16(a.in2)),
+                  "temporal_tc: the fused H+G epilogue needs two 48-output temporal convs over slab-planar buffers of the same shape");
+  const int npad_acc = hg ? 2 * w.npad : w.npad;       // accumulator columns per output frame
   SELFC_CHECK_ARG(a.in_pitch % 8 == 0 && aligned16(a.in), "temporal_tc: input pitch/alignment");
   SELFC_CHECK_ARG(a.epi != EPI_GA, "temporal_tc: the GlobalAgg mix is a separate kernel (stp.cu: ga_mix)");
   tc::EncodeTiledFn encode = tc::get_encode_fn();
@@ -609,8 +660,10 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
     }
     if (nks < kps) kps = nks;
   }
-  const int nchunk = cdiv(nks, kps);
-  CUtensorMap tmap;
+  if (hg && nks % kps != 0) return SELFC_E_UNSUPPORTED;      // the second conv's chunks must start on a stage boundary
+  const int nchunk1 = cdiv(nks, kps);
+  const int nchunk = hg ? 2 * nchunk1 : nchunk1;
+  CUtensorMap tmap, tmap2;
   CUresult r;
   if (a.in_slabM) {
     // slab-planar dense buffer [cin/16][M][16]: box = 128 pixels of one frame x kps slabs, each slab's rows one 4 KB run
@@ -622,6 +675,10 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
     r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+      r = encode(&tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(hg ? a.in2 : a.in), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t gdim[3] = {(cuuint64_t)a.in_pitch, (cuuint64_t)a.hw, (cuuint64_t)BT};
     const cuuint64_t gstr[2] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.hw * a.in_pitch * 2};
@@ -630,6 +687,7 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
     r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    tmap2 = tmap;
   }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (temporal) failed with CUresult %d", (int)r);
@@ -638,19 +696,21 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   tc5::Params p;
   memset(&p, 0, sizeof(p));
   p.wimg = w.img; p.bias = w.bias;
-  p.T = a.T; p.B = a.B; p.hw = a.hw; p.nks = nks; p.npad = w.npad; p.taps = w.taps; p.cout = w.cout;
-  p.kps = kps; p.nchunk = nchunk;
+  p.wimg2 = hg ? w2->img : w.img; p.bias2 = hg ? w2->bias : w.bias;
+  p.T = a.T; p.B = a.B; p.hw = a.hw; p.nks = nks; p.npad = npad_acc; p.taps = w.taps; p.cout = w.cout;
+  p.nhalf = w.npad;
+  p.kps = kps; p.nchunk = nchunk; p.nc_split = nchunk1;
   p.tiles_p = cdiv(a.hw, tc5::MT);
   p.ntiles = p.tiles_p * a.B;
   // taps == 3: the outputs fi-1, fi, fi+1 are being accumulated while the epilogue drains a fourth one
-  const int nacc = 512 / w.npad >= 4 ? 4 : (512 / w.npad >= 2 ? 2 : 0);     // power of two: slot = index & (nacc-1)
+  const int nacc = 512 / npad_acc >= 4 ? 4 : (512 / npad_acc >= 2 ? 2 : 0);     // power of two: slot = index & (nacc-1)
   SELFC_CHECK_ARG(w.taps == 3 || w.taps == 1, "temporal_tc: %d taps", w.taps);
   if (nacc < (w.taps == 3 ? 4 : 2)) {
-    set_error("temporal_tc: N=%d leaves no room for %d rolling accumulators", w.npad, w.taps == 3 ? 4 : 2);
+    set_error("temporal_tc: N=%d leaves no room for %d rolling accumulators", npad_acc, w.taps == 3 ? 4 : 2);
     return SELFC_E_UNSUPPORTED;
   }
   p.nacc = nacc;
-  int cols = nacc * w.npad, pw = 32;
+  int cols = nacc * npad_acc, pw = 32;
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   p.epi = a.epi; p.rev = a.rev; p.act = a.act;
@@ -673,8 +733,8 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
     p.dbg = slot;
   }
   if (p.ntiles == 0) return 0;
-  p.epi_quads = a.epi == EPI_COUPLE_Y2 ? 2 * kSQuads : (a.epi == EPI_COUPLE_Y1 ? 1 : 0);
-  const int fixed = tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes + 2 * p.epi_quads * tc5::MT * 16 + 1024;
+  p.epi_quads = a.epi == EPI_COUPLE_Y2 ? 2 * kSQuads : (a.epi == EPI_COUPLE_HG ? kSQuads : (a.epi == EPI_COUPLE_Y1 ? 1 : 0));
+  const int fixed = tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes * (hg ? 2 : 1) + 2 * p.epi_quads * tc5::MT * 16 + 1024;
   const int stage_bytes = kps * tc5::MT * 32;
   int nst = (227 * 1024 - fixed) / stage_bytes;
   if (nst > tc5::NST_MAX) nst = tc5::NST_MAX;
@@ -694,8 +754,8 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st) {
   }
   const int nsm = tc::num_sms();
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
-  if (w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3>, grid, tc5::THREADS, smem, st, tmap, p));
-  else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1>, grid, tc5::THREADS, smem, st, tmap, p));
+  if (w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
+  else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
   SELFC_LAUNCH_CHECK("temporal_tc_kernel");
   return 0;
 }

@@ -102,6 +102,12 @@ def test_gmm_sample_vs_oracle(dev):
     eps = so.make_eps(b, t, h, w, 17)
     ref = so.gmm_sample(params, eps, t)
     got = engine.gmm_sample(params.to(dev), t, eps=eps.to(dev)).cpu()
+    if not torch.allclose(got, ref, rtol=1e-5, atol=1e-4):       # diagnose against a float64 evaluation: which side is off?
+        ref64 = so.gmm_sample(params.double(), eps.double(), t)
+        got_b = engine.gmm_sample(params.to(dev), t, eps=eps.to(dev)).cpu()
+        print("gmm_sample mismatch: |gpu-f64| %.3e  |cpu32-f64| %.3e  |gpu-gpu_again| %.3e  cpu32 deterministic %s" % (
+            (got.double() - ref64).abs().max().item(), (ref.double() - ref64).abs().max().item(),
+            (got - got_b).abs().max().item(), torch.equal(ref, so.gmm_sample(params, eps, t))))
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-4)
     # counter-based noise: export the stream, feed it to the oracle
     eps2 = engine.export_eps(b, t, h, w, seed=42, offset=3, device=dev)
