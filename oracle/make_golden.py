@@ -117,6 +117,42 @@ def case_metrics(ref):
                         ssim=np.array(ssims), psnr=np.array(psnrs), lr_ref=lr_ref.numpy())
 
 
+def case_train(ref, name, b, t, hh, ww, wseed, xseed):
+    """One training step's losses and gradients from the reference's own modules (SelfC_model.py:148-170 restated with
+    netG, Quantization, ReconstructionLoss and Guassian_downsample imported from the reference; SelfCModel itself needs
+    a CUDA device).  Stored: the loss terms, every parameter's gradient norm, a few whole gradients."""
+    from models.modules.Quantization import Quantization
+    from models.modules.loss import ReconstructionLoss
+    from models.Guassian import Guassian_downsample
+    sd = so.make_state_dict(wseed)
+    net = ref.build_net(t)
+    net.load_state_dict(sd, strict=True)
+    net.train()
+    x = so.make_frames(b, t, hh, ww, xseed)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, xseed + 7)
+    ref_l = Guassian_downsample(x.transpose(0, 1)).transpose(0, 1)          # distortion: sr_bd (SelfC_model.py:127-128)
+    out, loss_c = net(x=x, rev=False)
+    lr_pre = out[:, :3]
+    l_forw = 1.0 * ReconstructionLoss(losstype="l2")(lr_pre, ref_l.detach())
+    lr_q = Quantization()(lr_pre)
+    ref.inject_eps(net, eps)
+    hr, _ = net(x=lr_q, rev=True)
+    l_back = 1.0 * ReconstructionLoss(losstype="l1")(x, hr[:, :3])
+    loss = (l_forw + l_back + loss_c.mean() * 0) * 144 * 144 * 3
+    loss.backward()
+    names = [k for k, _ in net.named_parameters()]
+    norms = np.array([float(p.grad.double().norm()) for _, p in net.named_parameters()])
+    keep = ["operations.1.F.conv1.weight", "operations.8.G.conv5.bias", "operations.4.H.conv3.weight",
+            "stp_net.global_m1.fc.weight", "stp_net.global_m2.proj2.weight", "stp_net.tail_gmm.5.bias",
+            "stp_net.local_m1.conv5.weight"]
+    grads = {"grad__" + k.replace(".", "__"): dict(net.named_parameters())[k].grad.numpy() for k in keep}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                        meta=np.array([b, t, hh, ww, wseed, xseed], dtype=np.int64), eps_seed=np.int64(xseed + 7),
+                        names=np.array(names), grad_norms=norms, loss=np.float64(loss.item()),
+                        l_forw=np.float64(l_forw.item()), l_back=np.float64(l_back.item()), ref_l=ref_l.numpy(), **grads)
+    print(name, "loss", loss.item(), "l_forw", l_forw.item(), "l_back", l_back.item(), "global grad norm", float(np.sqrt((norms ** 2).sum())))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -127,6 +163,7 @@ def main():
     case_net(ref, "net_t7", b=1, t=7, hh=32, ww=40, wseed=1, xseed=12)
     # partial 8x16 output tiles, non-integral 32x32 pooling windows (h=10, w=18), larger weights
     case_net(ref, "net_t2_gain", b=2, t=2, hh=40, ww=72, wseed=2, xseed=13, gain=1.5)
+    case_train(ref, "train_t3", b=2, t=3, hh=32, ww=48, wseed=4, xseed=21)
 
 
 if __name__ == "__main__":

@@ -372,6 +372,37 @@ def gaussian_downsample(x: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------
+# a13 training step (models/SelfC_model.py:148-183, models/modules/loss.py:5-21, Quantization.py:4-17) -- the autograd
+# reference for the backward kernels of the next round; pinned by tests/golden/train_t3.npz
+# --------------------------------------------------------------------------------------
+def quantize_ste(x: torch.Tensor) -> torch.Tensor:
+    """Quant.forward / backward (Quantization.py:4-17): clamp + round to the 1/255 grid, gradient = identity everywhere
+    (the clamp sits inside the autograd.Function, so the straight-through estimator also passes outside [0,1])."""
+    return x + (quantize(x) - x).detach()
+
+
+def train_losses(sd, x: torch.Tensor, ref_l: torch.Tensor, eps: torch.Tensor, t: int):
+    """optimize_parameters' forward (SelfC_model.py:152-170) with the training YAML's settings (l2 forward fit, l1
+    = Charbonnier eps 1e-6 backward reconstruction, lambda 1/1, loss_c = 0): returns (loss, l_forw_fit, l_back_rec)."""
+    out = net_down(sd, x, t)
+    lr_pre = out[:, :3]
+    l_forw = ((lr_pre - ref_l.detach()) ** 2).mean()
+    hr, _ = net_up(sd, quantize_ste(lr_pre), eps, t)
+    d = x - hr[:, :3]
+    l_back = torch.sqrt(d * d + 1e-6).mean()
+    loss = (l_forw + l_back + 0.0) * 144 * 144 * 3
+    return loss, l_forw, l_back
+
+
+def train_grads(sd, x: torch.Tensor, ref_l: torch.Tensor, eps: torch.Tensor, t: int):
+    """loss.backward() of the step above: {name: grad} for every parameter, plus the three loss values."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    loss, l_forw, l_back = train_losses(leaf, x, ref_l, eps, t)
+    loss.backward()
+    return {k: v.grad for k, v in leaf.items()}, float(loss.detach()), float(l_forw.detach()), float(l_back.detach())
+
+
+# --------------------------------------------------------------------------------------
 # counter-based noise of the CUDA path (selfc_b200/csrc/common.cuh: philox_normal) - numpy restatement
 # --------------------------------------------------------------------------------------
 def philox4x32_10(c, k):
