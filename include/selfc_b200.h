@@ -85,6 +85,12 @@ int selfc_d2dt(selfc_ctx* ctx, int first_param, const float* x, float* y, int B,
  * x [B*T, Cin+32k, h, w] (the concatenated input) -> y [B*T,32,h,w] = LeakyReLU_0.2(conv(x) + bias) */
 int selfc_conv3x3(selfc_ctx* ctx, int first_param, int k, const float* x, float* y, int B, int T, int h, int w,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* a13 (training step, models/SelfC_model.py:148-183) building block: backward of D2DTInput (Subnet_constructor.py:115-133)
+ * for the dense block at `first_param`.  x [B*T,Cin,h,w], gy [B*T,Cout,h,w] -> gx [B*T,Cin,h,w]; gparams[10] (conv1.weight,
+ * conv1.bias, ..., conv5.bias in the reference layouts, device fp32) are ACCUMULATED into; a NULL weight entry skips that
+ * conv's weight and bias gradient.  FP32 mode only.  The forward activations are recomputed, not stored. */
+int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gy, float* gx, float* const* gparams,
+                        int B, int T, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
 /* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
  * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
 int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,

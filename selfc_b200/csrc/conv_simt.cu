@@ -163,6 +163,11 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) 
               if (n0 + j < a.cout) o[j] = v[j];
         }
       } break;
+      case EPI_ACCUM: {       // outF[m][off + n] += v   (dgrad of the training step: gradients of a concat sum up)
+        float* o = a.outF + m * a.outF_pitch + a.outF_off + n0;
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < a.cout) o[j] += v[j];
+      } break;
       case EPI_COUPLE_Y1: {   // y1 = x1 +/- F(x2)   (SelfC_GMM_arch_inv.py:25, :31)
         if (n0 < a.copy_pad || n0 < 4) {
           float y[4] = {0.f, 0.f, 0.f, 0.f};
@@ -232,7 +237,7 @@ int launch_conv_simt(const ConvArgs<T>& a, cudaStream_t st) {
   const long long M = (long long)a.BT * a.h * a.w_;
   if (M == 0) return 0;
   dim3 grid(cdiv(M, SM_TILE_M), a.np / SM_TILE_N);
-  if (a.epi != EPI_STORE && a.epi != EPI_GA) {
+  if (a.epi != EPI_STORE && a.epi != EPI_GA && a.epi != EPI_ACCUM) {
     // coupling epilogues only consume the first channels: skip all-padding column tiles
     int need = (a.epi == EPI_COUPLE_Y1) ? (a.copy_pad > 4 ? a.copy_pad : 4) : kHF;
     grid.y = cdiv(need, SM_TILE_N);

@@ -29,7 +29,7 @@ int launch_dense_to_nchw(const T* src, int pitch, long long slabM, int off, floa
 
 // ---- conv_simt.cu: fp32-FMA implicit GEMM (strict-fp32 mode and the small GEMMs of both modes) --------------
 enum TapMode { TAP_POINT = 0, TAP_SPATIAL = 1, TAP_TEMPORAL = 2, TAP_TMIX = 3 };
-enum Epilogue { EPI_STORE = 0, EPI_COUPLE_Y1 = 1, EPI_COUPLE_S = 2, EPI_COUPLE_Y2 = 3, EPI_GA = 4, EPI_GMM = 5, EPI_COUPLE_HG = 6 };
+enum Epilogue { EPI_STORE = 0, EPI_COUPLE_Y1 = 1, EPI_COUPLE_S = 2, EPI_COUPLE_Y2 = 3, EPI_GA = 4, EPI_GMM = 5, EPI_COUPLE_HG = 6, EPI_ACCUM = 7 };
 
 template <typename T>
 struct ConvArgs {

@@ -14,6 +14,7 @@
 #include "kernels.h"
 #include "conv_tc.h"
 #include "tc_ptx.cuh"
+#include "net_ctx.h"
 
 namespace selfc {
 
@@ -38,51 +39,9 @@ constexpr int P_OTHER = 276;        // 4 x (D2DT 10, GlobalAgg 8)
 constexpr int P_TAIL = 348;         // tail_gmm.{1,3,5}.{weight,bias}
 static_assert(P_TAIL + 6 == SELFC_NUM_PARAMS, "parameter map");
 
-struct DenseW {            // one D2DTInput in kernel layout
-  int cin = 0, cout = 0, xpad = 0;
-  float* w[5] = {};        // SIMT fp32 [taps*cin_buf][np]
-  float* b[5] = {};
-  int np[5] = {};
-  TcConvW tc[5];           // tcgen05 bf16 images (BF16 mode)
-  TcTempW t5;              // conv5 image (BF16 mode)
-};
-struct GaW {
-  float *fcw = nullptr, *fcb = nullptr, *p2w = nullptr, *p2b = nullptr, *p3w = nullptr, *p3b = nullptr;
-  float *p1w = nullptr, *p1b = nullptr;   // packed [64][64] (k-major rows), bias [64]
-  TcTempW tp;                             // proj1 image (BF16 mode)
-};
-struct ProfRec {
-  cudaEvent_t a = nullptr, b = nullptr;
-  int cls = 0;
-  double work = 0.0;
-};
-struct HeadW {
-  float* w[3] = {};
-  float* b[3] = {};
-  int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 720}, np[3] = {128, 256, 736};
-  TcTempW t[5];            // BF16 mode: 64->128, 128->256, 256->240 x3 as tcgen05 pointwise GEMMs
-  TcTempW g[5];            // BF16 mode: 256->144 per mixture component (fused head + sampler)
-};
-
 }  // namespace selfc
 
 using namespace selfc;
-
-struct selfc_ctx {
-  int device = 0, mode = SELFC_MODE_FP32;
-  bool loaded = false;
-  int xpad3 = 4;            // X-slot width of the 3-channel dense blocks (G, H, local_m1)
-  DenseW inv[8][3];         // [block][F,G,H]
-  DenseW stp[6];            // local_m1, local_m2, other 0,2,4,6
-  GaW ga[6];
-  HeadW head;
-  char* arena = nullptr;
-  size_t arena_bytes = 0;
-  std::mutex mu;
-  // optional per-launch timing (bench.py's roofline leg): CUDA events around every launch, by kernel class
-  bool prof_on = false;
-  std::vector<ProfRec> prof;
-};
 
 namespace selfc {
 
@@ -111,15 +70,7 @@ static void prof_end(const selfc_ctx* cctx, cudaStream_t st) {
     if (rc_p != 0) return rc_p;        \
   } while (0)
 
-// ---- workspace layout -------------------------------------------------------------------------------------
-struct Workspace {
-  size_t total = 0;
-  size_t z, sbuf, fbuf, gbuf, hbuf, stpbuf, feat, fact, h1, h2, params, wmap, partial, wmat, wsum;
-  int nsplit = 1;
-  int fpitch = 176, gpitch = 0, spitch = 192;
-};
-
-static Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w) {
+Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w) {
   Workspace ws;
   const size_t M = (size_t)B * T * h * w;
   const size_t es = ctx->mode == SELFC_MODE_BF16 ? 2 : 4;
@@ -152,15 +103,6 @@ static Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w
   ws.total = off;
   return ws;
 }
-
-struct Dims {
-  int B, T, h, w;
-  long long M() const { return (long long)B * T * h * w; }
-  long long hw() const { return (long long)h * w; }
-};
-
-// layout of the dense-block buffers (common.cuh): slab-planar in BF16 mode, pixel-major in FP32 mode
-static long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->mode == SELFC_MODE_BF16 ? d.M() : 0; }
 
 // ---- dense block: conv1..4 in place, then conv5 with the given epilogue ---------------------------------------
 template <typename T>
@@ -515,6 +457,43 @@ static int ga_impl(selfc_ctx* ctx, const GaW& g, const float* x, float* y, float
 
 }  // namespace selfc
 
+namespace selfc {
+int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws) {
+  SELFC_CHECK_ARG(ctx != nullptr, "null context");
+  if (!ctx->loaded) {
+    set_error("weights not loaded: call selfc_ctx_load_weights first");
+    return SELFC_E_STATE;
+  }
+  SELFC_CHECK_ARG(B >= 1 && T >= 1 && T <= 32, "B=%d T=%d: need B >= 1 and 1 <= T <= 32", B, T);
+  SELFC_CHECK_ARG(H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0, "H=%d W=%d must be positive multiples of 4", H, W);
+  SELFC_CHECK_ARG((long long)B * T * (H / 4) * (W / 4) < (1ll << 31) / 8, "clip batch too large for 32-bit tile indices");
+  *ws = make_workspace(ctx, B, T, H / 4, W / 4);
+  SELFC_CHECK_ARG(workspace != nullptr && aligned16(workspace), "workspace null or misaligned");
+  if (workspace_bytes < ws->total) {
+    set_error("workspace too small: %zu < %zu bytes", workspace_bytes, ws->total);
+    return SELFC_E_STATE;
+  }
+  SELFC_CUDA(cudaSetDevice(ctx->device));
+  return 0;
+}
+
+}  // namespace selfc
+
+namespace selfc {
+const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
+  if (first_param >= 0 && first_param < 240 && first_param % 10 == 0) return &ctx->inv[first_param / 30][(first_param % 30) / 10];
+  if (first_param == P_LOCAL1) return &ctx->stp[0];
+  if (first_param == P_LOCAL2) return &ctx->stp[1];
+  for (int i = 0; i < 4; ++i)
+    if (first_param == P_OTHER + 18 * i) return &ctx->stp[2 + i];
+  return nullptr;
+}
+
+int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st) {
+  return run_dense_convs<float>(ctx, W, buf, pitch, d, st);
+}
+}  // namespace selfc
+
 // =============================================================================================================
 // C-ABI
 // =============================================================================================================
@@ -709,25 +688,6 @@ size_t selfc_workspace_bytes(const selfc_ctx* ctx, int B, int T, int h, int w) {
   return make_workspace(ctx, B, T, h, w).total;
 }
 
-static int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws) {
-  SELFC_CHECK_ARG(ctx != nullptr, "null context");
-  if (!ctx->loaded) {
-    set_error("weights not loaded: call selfc_ctx_load_weights first");
-    return SELFC_E_STATE;
-  }
-  SELFC_CHECK_ARG(B >= 1 && T >= 1 && T <= 32, "B=%d T=%d: need B >= 1 and 1 <= T <= 32", B, T);
-  SELFC_CHECK_ARG(H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0, "H=%d W=%d must be positive multiples of 4", H, W);
-  SELFC_CHECK_ARG((long long)B * T * (H / 4) * (W / 4) < (1ll << 31) / 8, "clip batch too large for 32-bit tile indices");
-  *ws = make_workspace(ctx, B, T, H / 4, W / 4);
-  SELFC_CHECK_ARG(workspace != nullptr && aligned16(workspace), "workspace null or misaligned");
-  if (workspace_bytes < ws->total) {
-    set_error("workspace too small: %zu < %zu bytes", workspace_bytes, ws->total);
-    return SELFC_E_STATE;
-  }
-  SELFC_CUDA(cudaSetDevice(ctx->device));
-  return 0;
-}
-
 int selfc_down(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_u8, float* lr_q, int B, int T, int H, int W,
                void* workspace, size_t workspace_bytes, void* stream) {
   Workspace ws;
@@ -775,15 +735,6 @@ int selfc_gaussian_down(const float* x, const float* k13, float* y, int N, int C
 int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* stream) {
   SELFC_CHECK_ARG(x || n == 0, "quantize: null input");
   return launch_quantize(x, q_u8, q_f32, n, (cudaStream_t)stream);
-}
-
-static const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
-  if (first_param >= 0 && first_param < 240 && first_param % 10 == 0) return &ctx->inv[first_param / 30][(first_param % 30) / 10];
-  if (first_param == P_LOCAL1) return &ctx->stp[0];
-  if (first_param == P_LOCAL2) return &ctx->stp[1];
-  for (int i = 0; i < 4; ++i)
-    if (first_param == P_OTHER + 18 * i) return &ctx->stp[2 + i];
-  return nullptr;
 }
 
 int selfc_conv3x3(selfc_ctx* ctx, int first_param, int k, const float* x, float* y, int B, int T, int h, int w, void* workspace,

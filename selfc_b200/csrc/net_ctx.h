@@ -1,0 +1,89 @@
+// Context, workspace layout and a few host helpers shared by net.cu (inference orchestration + C-ABI) and train.cu
+// (backward kernels of the training step).
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "conv_tc.h"
+
+namespace selfc {
+
+struct DenseW {            // one D2DTInput in kernel layout
+  int cin = 0, cout = 0, xpad = 0;
+  float* w[5] = {};        // SIMT fp32 [taps*cin_buf][np]
+  float* b[5] = {};
+  int np[5] = {};
+  TcConvW tc[5];           // tcgen05 bf16 images (BF16 mode)
+  TcTempW t5;              // conv5 image (BF16 mode)
+};
+struct GaW {
+  float *fcw = nullptr, *fcb = nullptr, *p2w = nullptr, *p2b = nullptr, *p3w = nullptr, *p3b = nullptr;
+  float *p1w = nullptr, *p1b = nullptr;   // packed [64][64] (k-major rows), bias [64]
+  TcTempW tp;                             // proj1 image (BF16 mode)
+};
+struct ProfRec {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cls = 0;
+  double work = 0.0;
+};
+struct HeadW {
+  float* w[3] = {};
+  float* b[3] = {};
+  int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 720}, np[3] = {128, 256, 736};
+  TcTempW t[5];            // BF16 mode: 64->128, 128->256, 256->240 x3 as tcgen05 pointwise GEMMs
+  TcTempW g[5];            // BF16 mode: 256->144 per mixture component (fused head + sampler)
+};
+
+}  // namespace selfc
+
+using selfc::DenseW;
+using selfc::GaW;
+using selfc::HeadW;
+using selfc::ProfRec;
+
+struct selfc_ctx {
+  int device = 0, mode = SELFC_MODE_FP32;
+  bool loaded = false;
+  int xpad3 = 4;            // X-slot width of the 3-channel dense blocks (G, H, local_m1)
+  DenseW inv[8][3];         // [block][F,G,H]
+  DenseW stp[6];            // local_m1, local_m2, other 0,2,4,6
+  GaW ga[6];
+  HeadW head;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::mutex mu;
+  // optional per-launch timing (bench.py's roofline leg): CUDA events around every launch, by kernel class
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+};
+
+namespace selfc {
+
+// ---- workspace layout -------------------------------------------------------------------------------------
+struct Workspace {
+  size_t total = 0;
+  size_t z, sbuf, fbuf, gbuf, hbuf, stpbuf, feat, fact, h1, h2, params, wmap, partial, wmat, wsum;
+  int nsplit = 1;
+  int fpitch = 176, gpitch = 0, spitch = 192;
+};
+
+Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w);
+
+struct Dims {
+  int B, T, h, w;
+  long long M() const { return (long long)B * T * h * w; }
+  long long hw() const { return (long long)h * w; }
+};
+
+// layout of the dense-block buffers (common.cuh): slab-planar in BF16 mode, pixel-major in FP32 mode
+inline long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->mode == SELFC_MODE_BF16 ? d.M() : 0; }
+
+
+// fp32-mode forward pieces re-used by the training step (net.cu)
+int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st);
+int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws);
+const DenseW* find_dense(selfc_ctx* ctx, int first_param);
+
+}  // namespace selfc

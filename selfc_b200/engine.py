@@ -112,6 +112,7 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self._L.selfc_ctx_load_weights(self._ctx, arr, NUM_PARAMS, _stream(self.device)), "load_weights")
         self._keep = tensors
+        self._shapes = {name: tuple(t.shape) for name, t in zip(PARAM_NAMES, tensors)}
 
     def sync_params(self, named_params: Sequence[Tuple[str, torch.Tensor]]) -> None:
         """Re-pack iff any parameter's storage or version changed since the last call."""
@@ -248,6 +249,23 @@ class Engine:
             _lib.check(self._L.selfc_d2dt(self._ctx, first, _ptr(x), _ptr(y), B, T, h, w, _ptr(ws), ws.numel(),
                                           _stream(self.device)), "d2dt")
         return y
+
+    def d2dt_backward(self, prefix: str, x: torch.Tensor, gy: torch.Tensor, T: int):
+        """Backward of the dense block `prefix` (training step building block, fp32 mode): x [B*T,Cin,h,w], gy [B*T,Cout,h,w]
+        -> (gx, {parameter name: gradient}) with the gradients in the reference's parameter layouts."""
+        first = PARAM_INDEX[prefix + ".conv1.weight"]
+        x = self._check_in(x, "x")
+        gy = self._check_in(gy, "gy")
+        B, h, w = self._clip_dims(x, T)
+        ws = self._workspace(B, T, h, w)
+        gx = torch.empty_like(x)
+        names = PARAM_NAMES[first:first + 10]
+        grads = [torch.zeros(self._shapes[n], dtype=torch.float32, device=self.device) for n in names]
+        ptrs = (C.c_void_p * 10)(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_d2dt_backward(self._ctx, first, _ptr(x), _ptr(gy), _ptr(gx), ptrs, B, T, h, w, _ptr(ws), ws.numel(),
+                                                   _stream(self.device)), "d2dt_backward")
+        return gx, dict(zip(names, grads))
 
     def conv3x3(self, prefix: str, k: int, x: torch.Tensor, T: int) -> torch.Tensor:
         """conv{k+1} of the dense block `prefix` on its concatenated input x [B*T,Cin+32k,h,w] -> [B*T,32,h,w]."""

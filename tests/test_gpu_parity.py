@@ -395,3 +395,26 @@ def test_rescale_host_pipeline_matches_per_gop_calls(dev):
         lr_u8, rec = eng.rescale(frames[ids].to(dev), 7, seed=3, offset=10 + i)
         assert torch.equal(lr_h[ids[0]:ids[0] + real], lr_u8[:real].cpu())
         assert torch.equal(hr_h[ids[0]:ids[0] + real], rec[:real].cpu())
+
+
+# ------------------------------------------------------------------------------------------------ a13 building blocks (training step)
+@pytest.mark.parametrize("prefix,cin,cout", [("operations.2.F", 48, 3), ("operations.6.G", 3, 48), ("stp_net.local_m2", 64, 64)])
+def test_d2dt_backward_vs_autograd(dev, prefix, cin, cout):
+    """Backward of one dense block (dgrad = the forward implicit GEMM on flipped weights, wgrad = pixel reduction) against
+    torch autograd on the oracle's D2DTInput: input gradient and all ten parameter gradients."""
+    sd = so.make_state_dict(8)
+    eng = _engine(dev, sd)
+    b, t, h, w = 2, 3, 11, 14
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(b * t, cin, h, w, generator=gen) * 0.5
+    gy = torch.randn(b * t, cout, h, w, generator=gen)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(prefix + ".")}
+    xr = x.clone().requires_grad_(True)
+    y = so.d2dt(leaf, prefix, xr, t)
+    y.backward(gy)
+    gx, grads = eng.d2dt_backward(prefix, x.to(dev), gy.to(dev), t)
+    torch.testing.assert_close(gx.cpu(), xr.grad, rtol=1e-4, atol=1e-4)
+    for name, gval in grads.items():
+        ref = leaf[name].grad
+        tol = 2e-4 * float(ref.abs().max()) + 1e-5
+        torch.testing.assert_close(gval.cpu(), ref, rtol=0, atol=tol)
