@@ -91,6 +91,12 @@ int selfc_conv3x3(selfc_ctx* ctx, int first_param, int k, const float* x, float*
  * conv's weight and bias gradient.  FP32 mode only.  The forward activations are recomputed, not stored. */
 int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gy, float* gx, float* const* gparams,
                         int B, int T, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+/* a13 building block: backward of InvBlockExp (SelfC_GMM_arch_inv.py:21-33) number blk (0..7) in the forward (rev = 0) or
+ * reverse (rev = 1) direction.  z_in [B*T,51,h,w]: the block's input (its forward is recomputed); gz [B*T,51,h,w]: gradient
+ * w.r.t. the block's output on entry, overwritten with the gradient w.r.t. its input; gparams[30] (F, G, H x conv1..5 weight,
+ * bias; reference layouts) are accumulated into.  FP32 mode only. */
+int selfc_invblock_backward(selfc_ctx* ctx, int blk, int rev, const float* z_in, float* gz, float* const* gparams,
+                            int B, int T, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
 /* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
  * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
 int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,

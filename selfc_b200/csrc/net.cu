@@ -489,6 +489,9 @@ const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
   return nullptr;
 }
 
+int invblock_f32(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
+  return run_invblock<float>(ctx, blk, rev, wsp, ws, d, st);
+}
 int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st) {
   return run_dense_convs<float>(ctx, W, buf, pitch, d, st);
 }

@@ -83,6 +83,10 @@ inline long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->m
 
 // fp32-mode forward pieces re-used by the training step (net.cu)
 int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st);
+// InvBlockExp forward / reverse on the latent state in the workspace (ws.z), leaving the F / G / H dense buffers and the
+// log-scale (ws.sbuf) behind; the X slot of the first dense block must already hold its input (x2 for F when !rev, x1 for
+// G and H when rev)
+int invblock_f32(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st);
 int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws);
 const DenseW* find_dense(selfc_ctx* ctx, int first_param);
 

@@ -218,6 +218,198 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const float* buf
   return 0;
 }
 
+
+// ====================================================================================================================
+// InvBlockExp backward (SelfC_GMM_arch_inv.py:21-33), both directions.  State and its gradient are planar quads
+// [13][M][4] (common.cuh); the block's forward is RECOMPUTED from its saved input state (invblock_f32), which leaves the
+// three dense buffers and the log-scale s in the workspace.
+//   forward dir:  y1 = x1 + F(x2);  s = 2*sigmoid(H(y1))-1;  y2 = x2*e^s + G(y1)
+//   reverse dir:  s = 2*sigmoid(H(x1))-1;  y2 = (x2 - G(x1))*e^-s;  y1 = x1 - F(y2)
+// ====================================================================================================================
+__global__ void quads_to_dense_kernel(const float* __restrict__ z, int q0, int nq, float* __restrict__ dst, int pitch, int off, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * nq) return;
+  const long long m = idx / nq;
+  const int j = (int)(idx - m * nq);
+  store4(dst + m * pitch + off + 4 * j, load4(z + quad_off((size_t)M, q0 + j, (size_t)m)));
+}
+
+// forward dir, step 1: gyG = gy2, gyH = gy2*x2*e^s*(1-s^2)/2, gz[x2 part] = gy2*e^s
+__global__ void cpl_fwd_pre_kernel(float* __restrict__ gz, const float* __restrict__ zin, const float* __restrict__ sbuf,
+                                   float* __restrict__ gyG, float* __restrict__ gyH, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * kSQuads) return;
+  const long long m = idx / kSQuads;
+  const int q = (int)(idx - m * kSQuads);
+  const float4 g = load4(gz + quad_off((size_t)M, 1 + q, (size_t)m));
+  const float4 x = load4(zin + quad_off((size_t)M, 1 + q, (size_t)m));
+  const float4 s = load4(sbuf + quad_off((size_t)M, q, (size_t)m));
+  const float gg[4] = {g.x, g.y, g.z, g.w}, xx[4] = {x.x, x.y, x.z, x.w}, ss[4] = {s.x, s.y, s.z, s.w};
+  float oG[4], oH[4], oX[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float ex = expf(ss[e]);
+    oG[e] = gg[e];
+    oH[e] = gg[e] * xx[e] * ex * (1.0f - ss[e] * ss[e]) * 0.5f;
+    oX[e] = gg[e] * ex;
+  }
+  store4(gyG + m * kHF + 4 * q, make_float4(oG[0], oG[1], oG[2], oG[3]));
+  store4(gyH + m * kHF + 4 * q, make_float4(oH[0], oH[1], oH[2], oH[3]));
+  store4(gz + quad_off((size_t)M, 1 + q, (size_t)m), make_float4(oX[0], oX[1], oX[2], oX[3]));
+}
+
+// acc[m][0:4] (+)= src[m][0:4]  (first channels of a dense-buffer gradient); init: overwrite instead of add
+__global__ void take4_kernel(float* __restrict__ acc, const float* __restrict__ src, int pitch, int init, float sign, long long M) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float4 v = load4(src + m * pitch);
+  float4 a = init ? make_float4(0.f, 0.f, 0.f, 0.f) : load4(acc + m * 4);
+  a.x += sign * v.x; a.y += sign * v.y; a.z += sign * v.z; a.w = 0.f;
+  store4(acc + m * 4, a);
+}
+
+// gz quad 0 += acc (xyz);  optionally also out4[m] = sign * gz quad 0 (the 4-channel gradient fed to F's backward)
+__global__ void cpl_quad0_kernel(float* __restrict__ gz, const float* __restrict__ acc, float* __restrict__ out4, float sign, long long M) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float4 g = load4(gz + quad_off((size_t)M, 0, (size_t)m));
+  if (acc) {
+    const float4 a = load4(acc + m * 4);
+    g.x += a.x; g.y += a.y; g.z += a.z;
+  }
+  g.w = 0.f;
+  store4(gz + quad_off((size_t)M, 0, (size_t)m), g);
+  if (out4) store4(out4 + m * 4, make_float4(sign * g.x, sign * g.y, sign * g.z, 0.f));
+}
+
+// gz[x2 part] += gX[m][0:48]   (forward dir, after F's backward)
+__global__ void cpl_add_hf_kernel(float* __restrict__ gz, const float* __restrict__ gX, int pitch, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * kSQuads) return;
+  const long long m = idx / kSQuads;
+  const int q = (int)(idx - m * kSQuads);
+  float4 g = load4(gz + quad_off((size_t)M, 1 + q, (size_t)m));
+  const float4 a = load4(gX + m * pitch + 4 * q);
+  g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+  store4(gz + quad_off((size_t)M, 1 + q, (size_t)m), g);
+}
+
+// reverse dir: t = gy2 + gXF;  gz[x2 part] = t*e^-s;  gyG = -t*e^-s;  gyH = -t*y2*(1-s^2)/2
+__global__ void cpl_rev_pre_kernel(float* __restrict__ gz, const float* __restrict__ gXF, int pitchF, const float* __restrict__ zout,
+                                   const float* __restrict__ sbuf, float* __restrict__ gyG, float* __restrict__ gyH, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * kSQuads) return;
+  const long long m = idx / kSQuads;
+  const int q = (int)(idx - m * kSQuads);
+  const float4 g = load4(gz + quad_off((size_t)M, 1 + q, (size_t)m));
+  const float4 f = load4(gXF + m * pitchF + 4 * q);
+  const float4 y = load4(zout + quad_off((size_t)M, 1 + q, (size_t)m));
+  const float4 s = load4(sbuf + quad_off((size_t)M, q, (size_t)m));
+  const float tt[4] = {g.x + f.x, g.y + f.y, g.z + f.z, g.w + f.w}, yy[4] = {y.x, y.y, y.z, y.w}, ss[4] = {s.x, s.y, s.z, s.w};
+  float oG[4], oH[4], oX[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float ex = expf(-ss[e]);
+    oX[e] = tt[e] * ex;
+    oG[e] = -tt[e] * ex;
+    oH[e] = -tt[e] * yy[e] * (1.0f - ss[e] * ss[e]) * 0.5f;
+  }
+  store4(gyG + m * kHF + 4 * q, make_float4(oG[0], oG[1], oG[2], oG[3]));
+  store4(gyH + m * kHF + 4 * q, make_float4(oH[0], oH[1], oH[2], oH[3]));
+  store4(gz + quad_off((size_t)M, 1 + q, (size_t)m), make_float4(oX[0], oX[1], oX[2], oX[3]));
+}
+
+static float* train_scratch() {              // dgrad weights + weight-gradient scratch of dense_block_backward (per device)
+  static float* scratch_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!scratch_dev[dev] && cudaMalloc(&scratch_dev[dev], (size_t)(9 * 64 * 192 + (9 * 192 + 1) * 64 + 256) * sizeof(float)) != cudaSuccess)
+    return nullptr;
+  return scratch_dev[dev];
+}
+
+// zin: the block's saved input state (planar); gz: gradient w.r.t. the block's OUTPUT state on entry, w.r.t. its INPUT state
+// on return; gparams: 30 gradients (F, G, H x conv1..5 weight/bias), accumulated into.  Scratch inside the workspace: the STP
+// regions (params, h1, h2), which are idle while a coupling block runs.
+int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin, float* gz, float* const* gparams, char* wsp,
+                      const Workspace& ws, const Dims& d, cudaStream_t st) {
+  const long long M = d.M();
+  float* z = reinterpret_cast<float*>(wsp + ws.z);
+  float* sbuf = reinterpret_cast<float*>(wsp + ws.sbuf);
+  float* fbuf = reinterpret_cast<float*>(wsp + ws.fbuf);
+  float* gbuf = reinterpret_cast<float*>(wsp + ws.gbuf);
+  float* hbuf = reinterpret_cast<float*>(wsp + ws.hbuf);
+  float* gdense = reinterpret_cast<float*>(wsp + ws.params);                 // [M][<=192] gradient of a dense buffer
+  float* gyG = reinterpret_cast<float*>(wsp + ws.h2);                        // [M][48]
+  float* gyH = gyG + (size_t)M * kHF;                                        // [M][48]
+  float* gyF = reinterpret_cast<float*>(wsp + ws.h1);                        // [M][4]
+  float* acc = gyF + (size_t)M * 4;                                          // [M][4]
+  float* scratch = train_scratch();
+  SELFC_CHECK_ARG(scratch != nullptr, "out of device memory (training scratch)");
+  const DenseW& F = ctx->inv[blk][0];
+  const DenseW& G = ctx->inv[blk][1];
+  const DenseW& H = ctx->inv[blk][2];
+  float* const* gF = gparams ? gparams : nullptr;
+  float* const* gG = gparams ? gparams + 10 : nullptr;
+  float* const* gH = gparams ? gparams + 20 : nullptr;
+  const int nb = cdiv(M, 256), nbq = cdiv(M * kSQuads, 256);
+  // recompute the block's forward from its input state
+  SELFC_CUDA(cudaMemcpyAsync(z, zin, (size_t)M * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
+  if (!rev) {
+    quads_to_dense_kernel<<<nbq, 256, 0, st>>>(zin, 1, kSQuads, fbuf, ws.fpitch, 0, M);
+    SELFC_LAUNCH_CHECK("quads_to_dense_kernel");
+  } else {
+    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, gbuf, ws.gpitch, 0, M);
+    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, hbuf, ws.gpitch, 0, M);
+    SELFC_LAUNCH_CHECK("quads_to_dense_kernel");
+  }
+  SELFC_TRY(invblock_f32(ctx, blk, rev, wsp, ws, d, st));
+  // the block's last epilogue has already put the NEXT block's input into an X slot (y2 into F's, or y1 into G's and H's):
+  // restore this block's own inputs, which the weight gradients need
+  if (!rev) {
+    quads_to_dense_kernel<<<nbq, 256, 0, st>>>(zin, 1, kSQuads, fbuf, ws.fpitch, 0, M);
+  } else {
+    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, gbuf, ws.gpitch, 0, M);
+    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, hbuf, ws.gpitch, 0, M);
+  }
+  SELFC_LAUNCH_CHECK("quads_to_dense_kernel");
+  if (!rev) {
+    cpl_fwd_pre_kernel<<<nbq, 256, 0, st>>>(gz, zin, sbuf, gyG, gyH, M);
+    SELFC_LAUNCH_CHECK("cpl_fwd_pre_kernel");
+    SELFC_TRY(dense_block_backward(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 1, 1.0f, M);
+    SELFC_TRY(dense_block_backward(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 0, 1.0f, M);
+    cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, acc, gyF, 1.0f, M);             // gx1 = gy1 + G^T + H^T; F's output gradient = the same
+    SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
+    SELFC_TRY(dense_block_backward(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
+    cpl_add_hf_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, M);
+    SELFC_LAUNCH_CHECK("cpl_add_hf_kernel");
+  } else {
+    cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, nullptr, gyF, -1.0f, M);        // y1 = x1 - F(y2): F's output gradient = -gy1
+    SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
+    SELFC_TRY(dense_block_backward(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
+    cpl_rev_pre_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, z, sbuf, gyG, gyH, M);
+    SELFC_LAUNCH_CHECK("cpl_rev_pre_kernel");
+    SELFC_TRY(dense_block_backward(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 1, 1.0f, M);
+    SELFC_TRY(dense_block_backward(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 0, 1.0f, M);
+    cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, acc, nullptr, 1.0f, M);
+    SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
+  }
+  return 0;
+}
+
+// NCHW [N,51,h,w] -> planar quads (test boundary)
+static int nchw51_to_quads(const float* x51, float* z, const Dims& d, cudaStream_t st) {
+  SELFC_TRY(launch_nchw_slice_to_dense<float>(x51, 51, 0, z, 4, 0, 0, 3, 4, d.M(), d.hw(), st));
+  for (int q = 0; q < kSQuads; ++q)
+    SELFC_TRY(launch_nchw_slice_to_dense<float>(x51, 51, 3 + 4 * q, z + quad_off((size_t)d.M(), 1 + q, 0), 4, 0, 0, 4, 4, d.M(), d.hw(), st));
+  return 0;
+}
+
 }  // namespace selfc
 
 using namespace selfc;
@@ -241,12 +433,8 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
   float* buf = reinterpret_cast<float*>(wsp + ws.stpbuf);
   float* gbuf = reinterpret_cast<float*>(wsp + ws.params);           // M * 720 floats >= M * pitch
   float* gyd = reinterpret_cast<float*>(wsp + ws.h2);                // M * 256 floats
-  static float* scratch_dev[64] = {};                                // dgrad weights + weight-gradient scratch (<= 0.9 MB)
-  int dev = 0;
-  cudaGetDevice(&dev);
-  SELFC_CHECK_ARG(dev >= 0 && dev < 64, "device index");
-  if (!scratch_dev[dev]) SELFC_CUDA(cudaMalloc(&scratch_dev[dev], (size_t)(9 * 64 * 192 + (9 * 192 + 1) * 64 + 256) * sizeof(float)));
-  float* scratch = scratch_dev[dev];
+  float* scratch = train_scratch();                                  // dgrad weights + weight-gradient scratch (<= 0.9 MB)
+  SELFC_CHECK_ARG(scratch != nullptr, "out of device memory (training scratch)");
   const int pitch = W->xpad + 4 * kGrowth;
   SELFC_CHECK_ARG(dense_bwd_scratch_floats(*W) <= (size_t)(9 * 64 * 192 + (9 * 192 + 1) * 64 + 256), "d2dt_backward: scratch size");
   const int cout4 = (W->cout + 3) & ~3;
@@ -258,4 +446,25 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
   return launch_dense_to_nchw<float>(gbuf, pitch, 0, 0, gx, W->cin, d.M(), d.hw(), st);
 }
 
+
+/* a13 building block: backward of InvBlockExp (SelfC_GMM_arch_inv.py:21-33) number blk (0..7), forward (rev = 0) or reverse
+ * (rev = 1) direction.  z_in [B*T,51,h,w]: the block's input; gz [B*T,51,h,w]: gradient w.r.t. the block's output on entry,
+ * overwritten with the gradient w.r.t. its input; gparams[30] (F, G, H x conv1..5 weight, bias) accumulated into. */
+int selfc_invblock_backward(selfc_ctx* ctx, int blk, int rev, const float* z_in, float* gz, float* const* gparams, int B, int T, int h,
+                            int w, void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(z_in && gz && blk >= 0 && blk < 8, "invblock_backward: null pointer or block index");
+  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32, "invblock_backward: the training step runs in FP32 mode");
+  Dims d{B, T, h, w};
+  cudaStream_t st = (cudaStream_t)stream;
+  char* wsp = (char*)workspace;
+  // test boundary: planar copies of the two NCHW tensors live in the STP dense buffer / feature regions
+  float* zin_p = reinterpret_cast<float*>(wsp + ws.stpbuf);                  // M * 192 floats >= M * 52
+  float* gz_p = zin_p + (size_t)d.M() * 4 * kZQuads;
+  SELFC_TRY(nchw51_to_quads(z_in, zin_p, d, st));
+  SELFC_TRY(nchw51_to_quads(gz, gz_p, d, st));
+  SELFC_TRY(invblock_backward(ctx, blk, rev != 0, zin_p, gz_p, gparams, wsp, ws, d, st));
+  return launch_export_down(gz_p, gz, nullptr, nullptr, d.M(), d.hw(), st);
+}
 }  // extern "C"

@@ -267,6 +267,22 @@ class Engine:
                                                    _stream(self.device)), "d2dt_backward")
         return gx, dict(zip(names, grads))
 
+    def invblock_backward(self, blk: int, rev: bool, z_in: torch.Tensor, gz: torch.Tensor, T: int):
+        """Backward of InvBlockExp `operations.{blk+1}` in the forward / reverse direction (fp32 mode): z_in, gz [B*T,51,h,w]
+        -> (gradient w.r.t. z_in, {parameter name: gradient})."""
+        z_in = self._check_in(z_in, "z_in")
+        gz = self._check_in(gz, "gz").clone()
+        B, h, w = self._clip_dims(z_in, T)
+        ws = self._workspace(B, T, h, w)
+        first = PARAM_INDEX[f"operations.{blk + 1}.F.conv1.weight"]
+        names = PARAM_NAMES[first:first + 30]
+        grads = [torch.zeros(self._shapes[n], dtype=torch.float32, device=self.device) for n in names]
+        ptrs = (C.c_void_p * 30)(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_invblock_backward(self._ctx, blk, 1 if rev else 0, _ptr(z_in), _ptr(gz), ptrs, B, T, h, w, _ptr(ws),
+                                                       ws.numel(), _stream(self.device)), "invblock_backward")
+        return gz, dict(zip(names, grads))
+
     def conv3x3(self, prefix: str, k: int, x: torch.Tensor, T: int) -> torch.Tensor:
         """conv{k+1} of the dense block `prefix` on its concatenated input x [B*T,Cin+32k,h,w] -> [B*T,32,h,w]."""
         first = PARAM_INDEX[prefix + ".conv1.weight"]
