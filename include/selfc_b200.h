@@ -97,6 +97,14 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
  * bias; reference layouts) are accumulated into.  FP32 mode only. */
 int selfc_invblock_backward(selfc_ctx* ctx, int blk, int rev, const float* z_in, float* gz, float* const* gparams,
                             int B, int T, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+/* extra device memory ("tape": gradient state, saved block inputs, scratch) the training-step entry points need */
+size_t selfc_train_tape_bytes(int B, int T, int h, int w);
+/* a13 building block: backward of the GMM head (tail_gmm, SelfC_GMM_arch_inv.py:336-344) + soft-GMM sampler (:383-394).
+ * feat [B*T,64,h,w]: the STP feature; gv [B*T,48,h,w]: gradient w.r.t. the sampled HF latents; eps as in selfc_up (NULL: the
+ * Philox stream seed/offset); gfeat [B*T,64,h,w] out; gparams[6]: tail_gmm.{1,3,5}.{weight,bias}, accumulated into. */
+int selfc_head_sampler_backward(selfc_ctx* ctx, const float* feat, const float* gv, const float* eps, uint64_t seed,
+                                uint64_t offset, float* gfeat, float* const* gparams, int B, int T, int h, int w,
+                                void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes, void* stream);
 /* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
  * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
 int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,

@@ -15,6 +15,8 @@
 
 namespace selfc {
 
+constexpr size_t kTrainScratchFloats = 768 * 1024;   // dgrad weights (<= 720 x 256) + weight-gradient scratch (<= 257 x 736), per device
+
 // ---- dgrad weights: wd[(tap' * cout4 + n)][c] = w[((taps-1-tap') * cin_buf + c)][n]   (w = forward pack [taps*cin_buf][np]) ----
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, int taps, int cin_buf, int np, int cout,
                                   int cout4, int npd) {
@@ -324,7 +326,7 @@ static float* train_scratch() {              // dgrad weights + weight-gradient 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
-  if (!scratch_dev[dev] && cudaMalloc(&scratch_dev[dev], (size_t)(9 * 64 * 192 + (9 * 192 + 1) * 64 + 256) * sizeof(float)) != cudaSuccess)
+  if (!scratch_dev[dev] && cudaMalloc(&scratch_dev[dev], kTrainScratchFloats * sizeof(float)) != cudaSuccess)
     return nullptr;
   return scratch_dev[dev];
 }
@@ -402,6 +404,210 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
   return 0;
 }
 
+// ====================================================================================================================
+// Extra device memory of the training step ("tape"): gradient state, saved block inputs, STP stage outputs, scratch.
+// ====================================================================================================================
+struct Tape {
+  size_t total = 0;
+  size_t gz;            // [13][M][4] gradient of the latent state
+  size_t zsave;         // 18 x [13][M][4]: state before FA^-1 ... (see train_grads)
+  size_t ga;            // 7 x [M][64]: input of STP stage i (i = 0: LR in 4 channels of the first slot) and the final feature
+  size_t sa, sb;        // [M][256] scratch each
+  size_t sc;            // [M][64] scratch
+  size_t small;         // per-clip scratch of the GlobalAgg backward
+};
+static Tape make_tape(int B, int T, int h, int w) {
+  Tape t;
+  const size_t M = (size_t)B * T * h * w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes + 256, 1024); return o; };
+  t.gz = take(M * kZQuads * 16);
+  t.zsave = take(18 * M * kZQuads * 16);
+  t.ga = take(7 * M * 64 * 4);
+  t.sa = take(M * 256 * 4);
+  t.sb = take(M * 256 * 4);
+  t.sc = take(M * 64 * 4);
+  t.small = take((size_t)B * 64 * 1024 + (size_t)h * w * 4 + 65536);
+  t.total = off;
+  return t;
+}
+
+// g[m][c] *= (y[m][c] > 0 ? 1 : 0.2) over a whole [M][C] array (C % 4 == 0); y is the activation's OUTPUT (same sign as its input)
+__global__ void lrelu_bwd_full_kernel(float* __restrict__ g, const float* __restrict__ y, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 gv = load4(g + 4 * i);
+  const float4 yv = load4(y + 4 * i);
+  gv.x *= yv.x > 0.f ? 1.f : 0.2f; gv.y *= yv.y > 0.f ? 1.f : 0.2f; gv.z *= yv.z > 0.f ? 1.f : 0.2f; gv.w *= yv.w > 0.f ? 1.f : 0.2f;
+  store4(g + 4 * i, gv);
+}
+__global__ void lrelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = load4(x + 4 * i);
+  store4(y + 4 * i, make_float4(lrelu02(v.x), lrelu02(v.y), lrelu02(v.z), lrelu02(v.w)));
+}
+
+// Backward of a pointwise (1x1x1) conv y = W.x + b:  g_in = W^T g (stored or accumulated),  dW += g (x) in,  db += sum g.
+// wf: forward pack [cin][np]; gw / gb: reference layouts [cout][cin] / [cout], accumulated into.
+static int pointwise_backward(const float* wf, int cin, int np, int cout, const float* in, int in_pitch, const float* g, int g_pitch,
+                              float* gin, int gin_pitch, bool accumulate, float* gw, float* gb, float* scratch, float* zero_bias,
+                              const Dims& d, cudaStream_t st) {
+  const long long M = d.M();
+  const int cout4 = (cout + 3) & ~3;
+  const int npd = (cin + 31) & ~31;
+  float* wd = scratch;
+  float* dw = scratch + (size_t)cout4 * npd;
+  if (gw != nullptr) {
+    SELFC_CUDA(cudaMemsetAsync(dw, 0, (size_t)(cin + 1) * np * sizeof(float), st));
+    int splits = (int)(M / 2048);
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+    dim3 grid(2 * cdiv(cout, 32), cdiv(cin, 32), splits);
+    wgrad_kernel<<<grid, 256, 0, st>>>(in, in_pitch, cin, g, g_pitch, 0, cout, dw, np, 1, TAP_POINT, d.B * d.T, d.T, d.h, d.w);
+    SELFC_LAUNCH_CHECK("wgrad_kernel");
+    const long long total = (long long)cout * cin;
+    wgrad_unpack_kernel<<<cdiv(total, 256), 256, 0, st>>>(dw, gw, gb, cout, cin, 1, cin, cin, cin, np);
+    SELFC_LAUNCH_CHECK("wgrad_unpack_kernel");
+  }
+  if (gin != nullptr) {
+    pack_dgrad_kernel<<<cdiv((long long)cout4 * npd, 256), 256, 0, st>>>(wf, wd, 1, cin, np, cout, cout4, npd);
+    SELFC_LAUNCH_CHECK("pack_dgrad_kernel");
+    ConvArgs<float> a;
+    a.in = g; a.in_pitch = g_pitch; a.cin = cout4;
+    a.w = wd; a.bias = zero_bias; a.np = npd; a.cout = cin;
+    a.taps = 1; a.tap_mode = TAP_POINT;
+    a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
+    a.epi = accumulate ? EPI_ACCUM : EPI_STORE; a.outF = gin; a.outF_pitch = gin_pitch; a.outF_off = 0;
+    SELFC_TRY(launch_conv_simt<float>(a, st));
+  }
+  return 0;
+}
+
+// ---- soft-GMM sampler backward (SelfC_GMM_arch_inv.py:383-394), one warp per pixel, IN PLACE on the parameters ----
+// params [M][720] (channel hf*15 + k*3 + j; j: 0 logit, 1 log-scale, 2 mean) is overwritten with its gradient:
+//   g_mu = gv*pi,  g_ls = gv*pi*eps*exp(ls) inside the clamp (0 outside),  g_logit = pi*(a - sum_hf pi*a) with a = gv*(eps*exp(ls)+mu)
+__global__ void __launch_bounds__(128) gmm_sample_bwd_kernel(float* __restrict__ params, const float* __restrict__ eps, uint64_t seed,
+                                                             uint64_t offset, const float* __restrict__ gz, int T, long long hw, long long M) {
+  __shared__ __align__(16) float sp[4][720];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const long long n = m / hw, pix = m - n * hw;
+  const int t = (int)(n % T);
+  const long long b = n / T;
+  float* P = sp[warp];
+  float4* dst = reinterpret_cast<float4*>(params + m * 720);
+  for (int c = lane; c < 180; c += 32) reinterpret_cast<float4*>(P)[c] = dst[c];
+  __syncwarp();
+  const int hf0 = lane, hf1 = lane + 32;
+  const bool has1 = hf1 < kHF;
+  const float gv0 = gz[quad_off((size_t)M, 1 + hf0 / 4, (size_t)m) + (hf0 & 3)];
+  const float gv1 = has1 ? gz[quad_off((size_t)M, 1 + hf1 / 4, (size_t)m) + (hf1 & 3)] : 0.f;
+#pragma unroll
+  for (int k = 0; k < kGmmK; ++k) {
+    const float l0 = P[hf0 * 15 + k * 3], l1 = has1 ? P[hf1 * 15 + k * 3] : -INFINITY;
+    float mx = fmaxf(l0, l1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e0 = expf(l0 - mx), e1 = has1 ? expf(l1 - mx) : 0.f;
+    float sum = e0 + e1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float pi0 = e0 / sum, pi1 = e1 / sum;
+    float a0, a1 = 0.f, gls0, gls1 = 0.f;
+    {
+      const float lsr = P[hf0 * 15 + k * 3 + 1];
+      const float sd = expf(fminf(fmaxf(lsr, -7.f), 7.f));
+      const float ep = eps ? __ldg(eps + (uint64_t)(((((b * kHF + hf0) * kGmmK + k) * T + t) * hw) + pix))
+                           : philox_eps(b, hf0, k, t, pix, T, hw, seed, offset);
+      a0 = gv0 * fmaf(ep, sd, P[hf0 * 15 + k * 3 + 2]);
+      gls0 = (lsr >= -7.f && lsr <= 7.f) ? gv0 * pi0 * ep * sd : 0.f;
+    }
+    if (has1) {
+      const float lsr = P[hf1 * 15 + k * 3 + 1];
+      const float sd = expf(fminf(fmaxf(lsr, -7.f), 7.f));
+      const float ep = eps ? __ldg(eps + (uint64_t)(((((b * kHF + hf1) * kGmmK + k) * T + t) * hw) + pix))
+                           : philox_eps(b, hf1, k, t, pix, T, hw, seed, offset);
+      a1 = gv1 * fmaf(ep, sd, P[hf1 * 15 + k * 3 + 2]);
+      gls1 = (lsr >= -7.f && lsr <= 7.f) ? gv1 * pi1 * ep * sd : 0.f;
+    }
+    float dot = pi0 * a0 + pi1 * a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    __syncwarp();
+    P[hf0 * 15 + k * 3] = pi0 * (a0 - dot);
+    P[hf0 * 15 + k * 3 + 1] = gls0;
+    P[hf0 * 15 + k * 3 + 2] = gv0 * pi0;
+    if (has1) {
+      P[hf1 * 15 + k * 3] = pi1 * (a1 - dot);
+      P[hf1 * 15 + k * 3 + 1] = gls1;
+      P[hf1 * 15 + k * 3 + 2] = gv1 * pi1;
+    }
+  }
+  __syncwarp();
+  for (int c = lane; c < 180; c += 32) dst[c] = reinterpret_cast<float4*>(P)[c];
+}
+
+static float* train_zero_bias() {
+  static float* zb[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!zb[dev]) {
+    if (cudaMalloc(&zb[dev], 1024 * sizeof(float)) != cudaSuccess) return nullptr;
+    cudaMemset(zb[dev], 0, 1024 * sizeof(float));
+  }
+  return zb[dev];
+}
+
+// GMM head + sampler backward.  feat [M][64]: the STP feature (before the head's first LeakyReLU); gz: gradient state whose HF
+// quads hold g_v; gfeat [M][64] receives the feature gradient (overwritten); gparams[6]: tail_gmm.{1,3,5}.{weight,bias}.
+int head_sampler_backward(const selfc_ctx* ctx, const float* feat, const float* eps, uint64_t seed, uint64_t offset, const float* gz,
+                          float* gfeat, float* const* gparams, char* wsp, const Workspace& ws, char* tp, const Tape& tape, const Dims& d,
+                          cudaStream_t st) {
+  const long long M = d.M();
+  float* h1 = reinterpret_cast<float*>(wsp + ws.h1);
+  float* h2 = reinterpret_cast<float*>(wsp + ws.h2);
+  float* params = reinterpret_cast<float*>(wsp + ws.params);
+  float* fact = reinterpret_cast<float*>(tp + tape.sc);           // [M][64]
+  float* gh2 = reinterpret_cast<float*>(tp + tape.sa);            // [M][256]
+  float* gh1 = reinterpret_cast<float*>(tp + tape.sb);            // [M][128]
+  float* scratch = train_scratch();
+  float* zb = train_zero_bias();
+  SELFC_CHECK_ARG(scratch && zb, "out of device memory (training scratch)");
+  const HeadW& hd = ctx->head;
+  // recompute the head: fact = lrelu(feat); h1 = lrelu(W1 fact + b1); h2 = lrelu(W2 h1 + b2); params = W3 h2 + b3
+  lrelu_fwd_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(feat, fact, M * 16);
+  SELFC_LAUNCH_CHECK("lrelu_fwd_kernel");
+  ConvArgs<float> a;
+  a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
+  a.taps = 1; a.tap_mode = TAP_POINT; a.epi = EPI_STORE;
+  a.in = fact; a.in_pitch = 64; a.cin = 64; a.w = hd.w[0]; a.bias = hd.b[0]; a.np = hd.np[0]; a.cout = 128; a.act = 1; a.outF = h1; a.outF_pitch = 128;
+  SELFC_TRY(launch_conv_simt<float>(a, st));
+  a.in = h1; a.in_pitch = 128; a.cin = 128; a.w = hd.w[1]; a.bias = hd.b[1]; a.np = hd.np[1]; a.cout = 256; a.outF = h2; a.outF_pitch = 256;
+  SELFC_TRY(launch_conv_simt<float>(a, st));
+  a.in = h2; a.in_pitch = 256; a.cin = 256; a.w = hd.w[2]; a.bias = hd.b[2]; a.np = hd.np[2]; a.cout = 720; a.act = 0; a.outF = params; a.outF_pitch = 720;
+  SELFC_TRY(launch_conv_simt<float>(a, st));
+  // sampler backward, in place: params <- d loss / d params
+  gmm_sample_bwd_kernel<<<cdiv(M, 4), 128, 0, st>>>(params, eps, seed, offset, gz, d.T, d.hw(), M);
+  SELFC_LAUNCH_CHECK("gmm_sample_bwd_kernel");
+  // 256 -> 720
+  SELFC_TRY(pointwise_backward(hd.w[2], 256, hd.np[2], 720, h2, 256, params, 720, gh2, 256, false, gparams ? gparams[4] : nullptr,
+                               gparams ? gparams[5] : nullptr, scratch, zb, d, st));
+  lrelu_bwd_full_kernel<<<cdiv(M * 64, 256), 256, 0, st>>>(gh2, h2, M * 64);
+  // 128 -> 256
+  SELFC_TRY(pointwise_backward(hd.w[1], 128, hd.np[1], 256, h1, 128, gh2, 256, gh1, 128, false, gparams ? gparams[2] : nullptr,
+                               gparams ? gparams[3] : nullptr, scratch, zb, d, st));
+  lrelu_bwd_full_kernel<<<cdiv(M * 32, 256), 256, 0, st>>>(gh1, h1, M * 32);
+  // 64 -> 128
+  SELFC_TRY(pointwise_backward(hd.w[0], 64, hd.np[0], 128, fact, 64, gh1, 128, gfeat, 64, false, gparams ? gparams[0] : nullptr,
+                               gparams ? gparams[1] : nullptr, scratch, zb, d, st));
+  lrelu_bwd_full_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(gfeat, fact, M * 16);
+  SELFC_LAUNCH_CHECK("lrelu_bwd_full_kernel");
+  return 0;
+}
+
 // NCHW [N,51,h,w] -> planar quads (test boundary)
 static int nchw51_to_quads(const float* x51, float* z, const Dims& d, cudaStream_t st) {
   SELFC_TRY(launch_nchw_slice_to_dense<float>(x51, 51, 0, z, 4, 0, 0, 3, 4, d.M(), d.hw(), st));
@@ -436,7 +642,7 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
   float* scratch = train_scratch();                                  // dgrad weights + weight-gradient scratch (<= 0.9 MB)
   SELFC_CHECK_ARG(scratch != nullptr, "out of device memory (training scratch)");
   const int pitch = W->xpad + 4 * kGrowth;
-  SELFC_CHECK_ARG(dense_bwd_scratch_floats(*W) <= (size_t)(9 * 64 * 192 + (9 * 192 + 1) * 64 + 256), "d2dt_backward: scratch size");
+  SELFC_CHECK_ARG(dense_bwd_scratch_floats(*W) <= kTrainScratchFloats, "d2dt_backward: scratch size");
   const int cout4 = (W->cout + 3) & ~3;
   // recompute the forward activations, then walk the block backwards
   SELFC_TRY(to_dense(x, buf, pitch, W->cin, W->xpad, d, st));
@@ -466,5 +672,35 @@ int selfc_invblock_backward(selfc_ctx* ctx, int blk, int rev, const float* z_in,
   SELFC_TRY(nchw51_to_quads(gz, gz_p, d, st));
   SELFC_TRY(invblock_backward(ctx, blk, rev != 0, zin_p, gz_p, gparams, wsp, ws, d, st));
   return launch_export_down(gz_p, gz, nullptr, nullptr, d.M(), d.hw(), st);
+}
+
+size_t selfc_train_tape_bytes(int B, int T, int h, int w) {
+  if (B < 1 || T < 1 || h < 1 || w < 1) return 0;
+  return make_tape(B, T, h, w).total;
+}
+
+/* a13 building block: backward of the GMM head (tail_gmm, :336-344) + soft-GMM sampler (:383-394).  feat [B*T,64,h,w]: the STP
+ * feature; gv [B*T,48,h,w]: gradient w.r.t. the sampled HF latents; eps as in selfc_up (NULL: Philox stream seed/offset);
+ * gfeat [B*T,64,h,w] out; gparams[6]: tail_gmm.{1,3,5}.{weight,bias} gradients, accumulated into. */
+int selfc_head_sampler_backward(selfc_ctx* ctx, const float* feat, const float* gv, const float* eps, uint64_t seed, uint64_t offset,
+                                float* gfeat, float* const* gparams, int B, int T, int h, int w, void* workspace, size_t workspace_bytes,
+                                void* tape, size_t tape_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(feat && gv && gfeat && tape, "head_sampler_backward: null pointer");
+  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32, "head_sampler_backward: the training step runs in FP32 mode");
+  const Tape tl = make_tape(B, T, h, w);
+  SELFC_CHECK_ARG(tape_bytes >= tl.total && aligned16(tape), "head_sampler_backward: tape too small (%zu < %zu)", tape_bytes, tl.total);
+  Dims d{B, T, h, w};
+  cudaStream_t st = (cudaStream_t)stream;
+  char* tp = (char*)tape;
+  float* featd = reinterpret_cast<float*>(tp + tl.ga) + (size_t)6 * d.M() * 64;
+  float* gz = reinterpret_cast<float*>(tp + tl.gz);
+  float* gfd = reinterpret_cast<float*>(tp + tl.ga);               // slot 0 as the output scratch
+  SELFC_TRY(launch_nchw_to_dense<float>(feat, featd, 64, 0, 0, 64, 64, d.M(), d.hw(), st));
+  for (int q = 0; q < kSQuads; ++q)
+    SELFC_TRY(launch_nchw_slice_to_dense<float>(gv, kHF, 4 * q, gz + quad_off((size_t)d.M(), 1 + q, 0), 4, 0, 0, 4, 4, d.M(), d.hw(), st));
+  SELFC_TRY(head_sampler_backward(ctx, featd, eps, seed, offset, gz, gfd, gparams, (char*)workspace, ws, tp, tl, d, st));
+  return launch_dense_to_nchw<float>(gfd, 64, 0, 0, gfeat, 64, d.M(), d.hw(), st);
 }
 }  // extern "C"

@@ -283,6 +283,35 @@ class Engine:
                                                        ws.numel(), _stream(self.device)), "invblock_backward")
         return gz, dict(zip(names, grads))
 
+    def _tape(self, B: int, T: int, h: int, w: int) -> torch.Tensor:
+        n = int(self._L.selfc_train_tape_bytes(B, T, h, w))
+        t = getattr(self, "_tape_buf", None)
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._tape_buf = t
+        return t
+
+    def head_sampler_backward(self, feat: torch.Tensor, gv: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0,
+                              offset: int = 0):
+        """Backward of tail_gmm + the soft-GMM sampler (fp32 mode): feat [B*T,64,h,w], gv [B*T,48,h,w] -> (gfeat, grads)."""
+        feat = self._check_in(feat, "feat")
+        gv = self._check_in(gv, "gv")
+        if eps is not None:
+            eps = _dev_check(eps)
+        B, h, w = self._clip_dims(feat, T)
+        ws = self._workspace(B, T, h, w)
+        tape = self._tape(B, T, h, w)
+        first = PARAM_INDEX["stp_net.tail_gmm.1.weight"]
+        names = PARAM_NAMES[first:first + 6]
+        grads = [torch.zeros(self._shapes[n], dtype=torch.float32, device=self.device) for n in names]
+        ptrs = (C.c_void_p * 6)(*[g.data_ptr() for g in grads])
+        gfeat = torch.empty_like(feat)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_head_sampler_backward(self._ctx, _ptr(feat), _ptr(gv), _ptr(eps), seed, offset, _ptr(gfeat), ptrs,
+                                                           B, T, h, w, _ptr(ws), ws.numel(), _ptr(tape), tape.numel(),
+                                                           _stream(self.device)), "head_sampler_backward")
+        return gfeat, dict(zip(names, grads))
+
     def conv3x3(self, prefix: str, k: int, x: torch.Tensor, T: int) -> torch.Tensor:
         """conv{k+1} of the dense block `prefix` on its concatenated input x [B*T,Cin+32k,h,w] -> [B*T,32,h,w]."""
         first = PARAM_INDEX[prefix + ".conv1.weight"]

@@ -441,3 +441,24 @@ def test_invblock_backward_vs_autograd(dev, rev):
         ref = leaf[name].grad
         tol = 3e-4 * float(ref.abs().max()) + 1e-5
         torch.testing.assert_close(gval.cpu(), ref, rtol=0, atol=tol)
+
+
+def test_head_sampler_backward_vs_autograd(dev):
+    """Backward of tail_gmm (three 1x1 convs + LeakyReLUs) and the soft-GMM sampler (softmax over hf, clamp, exp, injected
+    eps) against autograd on the oracle."""
+    sd = so.make_state_dict(12, gain=2.0)
+    eng = _engine(dev, sd)
+    b, t, h, w = 2, 3, 7, 10
+    gen = torch.Generator().manual_seed(9)
+    feat = torch.randn(b * t, 64, h, w, generator=gen)
+    gv = torch.randn(b * t, 48, h, w, generator=gen)
+    eps = so.make_eps(b, t, h, w, 33)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("stp_net.tail_gmm.")}
+    fr = feat.clone().requires_grad_(True)
+    v = so.gmm_sample(so.gmm_head(leaf, fr), eps, t)
+    v.backward(gv)
+    gfeat, grads = eng.head_sampler_backward(feat.to(dev), gv.to(dev), t, eps=eps.to(dev))
+    torch.testing.assert_close(gfeat.cpu(), fr.grad, rtol=0, atol=3e-4 * float(fr.grad.abs().max()) + 1e-6)
+    for name, gval in grads.items():
+        ref = leaf[name].grad
+        torch.testing.assert_close(gval.cpu(), ref, rtol=0, atol=3e-4 * float(ref.abs().max()) + 1e-6)
