@@ -105,6 +105,12 @@ size_t selfc_train_tape_bytes(int B, int T, int h, int w);
 int selfc_head_sampler_backward(selfc_ctx* ctx, const float* feat, const float* gv, const float* eps, uint64_t seed,
                                 uint64_t offset, float* gfeat, float* const* gparams, int B, int T, int h, int w,
                                 void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes, void* stream);
+/* a13 building block: backward of GlobalAgg (SelfC_GMM_arch_inv.py:265-285) whose fc.weight is parameter `first_param`.
+ * x, gout [B*T,64,h,w] -> gx; gparams[8] (fc.weight, fc.bias, proj1.weight, proj1.bias, proj2.weight, proj2.bias,
+ * proj3.weight, proj3.bias; reference layouts) are accumulated into.  FP32 mode, T <= 16. */
+int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gout, float* gx,
+                              float* const* gparams, int B, int T, int h, int w, void* workspace, size_t workspace_bytes,
+                              void* tape, size_t tape_bytes, void* stream);
 /* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
  * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
 int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,

@@ -492,6 +492,12 @@ const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
 int invblock_f32(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
   return run_invblock<float>(ctx, blk, rev, wsp, ws, d, st);
 }
+const GaW* find_ga(selfc_ctx* ctx, int first_param) {
+  const int ga_first[6] = {P_GLOBAL1, P_GLOBAL2, P_OTHER + 10, P_OTHER + 28, P_OTHER + 46, P_OTHER + 64};
+  for (int i = 0; i < 6; ++i)
+    if (first_param == ga_first[i]) return &ctx->ga[i];
+  return nullptr;
+}
 int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st) {
   return run_dense_convs<float>(ctx, W, buf, pitch, d, st);
 }

@@ -89,5 +89,6 @@ int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch
 int invblock_f32(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st);
 int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws);
 const DenseW* find_dense(selfc_ctx* ctx, int first_param);
+const GaW* find_ga(selfc_ctx* ctx, int first_param);
 
 }  // namespace selfc

@@ -427,7 +427,7 @@ static Tape make_tape(int B, int T, int h, int w) {
   t.sa = take(M * 256 * 4);
   t.sb = take(M * 256 * 4);
   t.sc = take(M * 64 * 4);
-  t.small = take((size_t)B * 64 * 1024 + (size_t)h * w * 4 + 65536);
+  t.small = take(((size_t)B * T * 128 + (size_t)B * T * T + (size_t)h * w + 1024) * 4);
   t.total = off;
   return t;
 }
@@ -608,6 +608,255 @@ int head_sampler_backward(const selfc_ctx* ctx, const float* feat, const float* 
   return 0;
 }
 
+// ====================================================================================================================
+// GlobalAgg backward (SelfC_GMM_arch_inv.py:265-285).  Forward (as computed here): d = fc(pool(x)) = fcb + sum_pix wmap*x,
+// q = P2 d + b2, k = P3 d + b3, W = softmax_rows(q k^T / 64), Xmix[t'] = sum_t W[t,t'] x[t],
+// out[t'] = x[t'] + P1 Xmix[t'] + b1 * sum_t W[t,t'].
+// ====================================================================================================================
+// out[b,t'] = (base ? base : 0) + sum_t W[b,t,t'] in[b,t]   (transpose: out[b,t] = sum_t' W[b,t,t'] in[b,t'])
+__global__ void ga_mix_f32_kernel(const float* __restrict__ in, const float* __restrict__ wmat, int transpose, const float* __restrict__ base,
+                                  float* __restrict__ out, int T, long long hw, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = idx >> 4;
+  const int c = (int)(idx & 15) * 4;
+  if (m >= M) return;
+  const long long n = m / hw, pix = m - n * hw;
+  const int to = (int)(n % T);
+  const long long b = n / T;
+  float4 acc = base ? load4(base + m * 64 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* wm = wmat + b * T * T;
+  for (int t = 0; t < T; ++t) {
+    const float wv = transpose ? __ldg(wm + to * T + t) : __ldg(wm + t * T + to);
+    const float4 v = load4(in + ((b * T + t) * hw + pix) * 64 + c);
+    acc.x = fmaf(wv, v.x, acc.x); acc.y = fmaf(wv, v.y, acc.y); acc.z = fmaf(wv, v.z, acc.z); acc.w = fmaf(wv, v.w, acc.w);
+  }
+  store4(out + m * 64 + c, acc);
+}
+
+// S[n][ch] = sum_pix g[n,pix,ch]   (one block per frame, 256 threads = 4 pixel lanes x 64 channels)
+__global__ void __launch_bounds__(256) frame_channel_sum_kernel(const float* __restrict__ g, float* __restrict__ S, long long hw) {
+  __shared__ float red[4][64];
+  const int n = blockIdx.x, ch = threadIdx.x & 63, lane = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (long long p = lane; p < hw; p += 4) acc += g[((long long)n * hw + p) * 64 + ch];
+  red[lane][ch] = acc;
+  __syncthreads();
+  if (lane == 0) S[n * 64 + ch] = red[0][ch] + red[1][ch] + red[2][ch] + red[3][ch];
+}
+
+// R[b][t][u] = sum_{pix,ch} a[b,t,pix,ch] * c[b,u,pix,ch]   (one block per (b,t,u))
+__global__ void __launch_bounds__(256) pair_dot_kernel(const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ R, int T,
+                                                       long long hw) {
+  __shared__ float red[256];
+  const int u = blockIdx.x % T, t = (blockIdx.x / T) % T, b = blockIdx.x / (T * T);
+  const float4* pa = reinterpret_cast<const float4*>(a + ((long long)(b * T + t) * hw) * 64);
+  const float4* pc = reinterpret_cast<const float4*>(c + ((long long)(b * T + u) * hw) * 64);
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < hw * 16; i += 256) {
+    const float4 x = pa[i], y = pc[i];
+    acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) R[blockIdx.x] = red[0];
+}
+
+// per clip: recompute d, q, k, W; gW = R + b1 . S; softmax backward; gq, gk; gd; gradients of proj2 / proj3 / fc.bias
+__global__ void __launch_bounds__(64) ga_small_bwd_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ fcb,
+                                                          const float* __restrict__ p2w, const float* __restrict__ p2b,
+                                                          const float* __restrict__ p3w, const float* __restrict__ p3b,
+                                                          const float* __restrict__ b1, const float* __restrict__ R,
+                                                          const float* __restrict__ S, float* __restrict__ gd, float* __restrict__ gp2w,
+                                                          float* __restrict__ gp2b, float* __restrict__ gp3w, float* __restrict__ gp3b,
+                                                          float* __restrict__ gfcb, int T) {
+  constexpr int MAXT = 32;
+  extern __shared__ float sm[];
+  float* d = sm;                 // [T][64]
+  float* q = d + T * 64;         // [T][64]
+  float* k = q + T * 64;         // [T][64]
+  float* gq = k + T * 64;        // [T][64]
+  float* gk = gq + T * 64;       // [T][64]
+  float* W = gk + T * 64;        // [T][MAXT]
+  float* gA = W + T * MAXT;      // [T][MAXT]
+  const int b = blockIdx.x, c = threadIdx.x;
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[(((long long)b * T + t) * nsplit + sp) * 64 + c];
+    d[t * 64 + c] = s + fcb[0];
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    float sq = p2b[c], sk = p3b[c];
+    for (int i = 0; i < 64; ++i) {
+      sq += p2w[c * 64 + i] * d[t * 64 + i];
+      sk += p3w[c * 64 + i] * d[t * 64 + i];
+    }
+    q[t * 64 + c] = sq;
+    k[t * 64 + c] = sk;
+  }
+  __syncthreads();
+  for (int e = c; e < T * T; e += 64) {
+    const int t = e / T, u = e % T;
+    float s = 0.f;
+    for (int i = 0; i < 64; ++i) s += q[t * 64 + i] * k[u * 64 + i];
+    W[t * MAXT + u] = s / 64.0f;
+    float gw = R[((long long)b * T + t) * T + u];
+    for (int i = 0; i < 64; ++i) gw += b1[i] * S[((long long)b * T + u) * 64 + i];
+    gA[t * MAXT + u] = gw;                    // holds gW until the softmax backward below
+  }
+  __syncthreads();
+  if (c < T) {
+    const int t = c;
+    float mx = -INFINITY;
+    for (int u = 0; u < T; ++u) mx = fmaxf(mx, W[t * MAXT + u]);
+    float sum = 0.f;
+    for (int u = 0; u < T; ++u) { W[t * MAXT + u] = expf(W[t * MAXT + u] - mx); sum += W[t * MAXT + u]; }
+    float dot = 0.f;
+    for (int u = 0; u < T; ++u) { W[t * MAXT + u] /= sum; dot += W[t * MAXT + u] * gA[t * MAXT + u]; }
+    for (int u = 0; u < T; ++u) gA[t * MAXT + u] = W[t * MAXT + u] * (gA[t * MAXT + u] - dot) / 64.0f;   // d loss / d (q.k), 1/64 folded in
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    float a = 0.f, bb = 0.f;
+    for (int u = 0; u < T; ++u) {
+      a += gA[t * MAXT + u] * k[u * 64 + c];       // gq[t][c]
+      bb += gA[u * MAXT + t] * q[u * 64 + c];      // gk[t][c]
+    }
+    gq[t * 64 + c] = a;
+    gk[t * 64 + c] = bb;
+  }
+  __syncthreads();
+  float sfc = 0.f;
+  for (int t = 0; t < T; ++t) {
+    float g = 0.f;                                  // gd[t][i = c]
+    for (int o = 0; o < 64; ++o) g += p2w[o * 64 + c] * gq[t * 64 + o] + p3w[o * 64 + c] * gk[t * 64 + o];
+    gd[((long long)b * T + t) * 64 + c] = g;
+    sfc += g;
+  }
+  // parameter gradients (row c of proj2 / proj3)
+  if (gp2w) {
+    float sb2 = 0.f, sb3 = 0.f;
+    for (int t = 0; t < T; ++t) { sb2 += gq[t * 64 + c]; sb3 += gk[t * 64 + c]; }
+    atomicAdd(gp2b + c, sb2);
+    atomicAdd(gp3b + c, sb3);
+    for (int i = 0; i < 64; ++i) {
+      float a2 = 0.f, a3 = 0.f;
+      for (int t = 0; t < T; ++t) { a2 += gq[t * 64 + c] * d[t * 64 + i]; a3 += gk[t * 64 + c] * d[t * 64 + i]; }
+      atomicAdd(gp2w + c * 64 + i, a2);
+      atomicAdd(gp3w + c * 64 + i, a3);
+    }
+    // fc.bias: sum of gd over frames and channels
+    __shared__ float red[64];
+    red[c] = sfc;
+    __syncthreads();
+    if (c == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 64; ++i) s += red[i];
+      atomicAdd(gfcb, s);
+    }
+  }
+}
+
+// descriptor path: gx[n,pix,:] += wmap[pix] * gd[n,:];  gwmap[pix] += sum_ch gd[n,ch] * x[n,pix,ch]
+__global__ void ga_desc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wmap, const float* __restrict__ gd,
+                                   float* __restrict__ gx, float* __restrict__ gwmap, long long hw, long long M) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long n = m / hw, pix = m - n * hw;
+  const float wv = wmap[pix];
+  float dot = 0.f;
+  for (int c = 0; c < 64; c += 4) {
+    const float4 g = load4(gd + n * 64 + c);
+    const float4 xv = load4(x + m * 64 + c);
+    float4 o = load4(gx + m * 64 + c);
+    o.x += wv * g.x; o.y += wv * g.y; o.z += wv * g.z; o.w += wv * g.w;
+    store4(gx + m * 64 + c, o);
+    dot += g.x * xv.x + g.y * xv.y + g.z * xv.z + g.w * xv.w;
+  }
+  atomicAdd(gwmap + pix, dot);
+}
+
+// adjoint of ga_wmap_kernel: gfcw[i*32+j] += sum over the pixels of pooling bin (i,j) of gwmap / |bin|
+__global__ void ga_wmap_bwd_kernel(const float* __restrict__ gwmap, float* __restrict__ gfcw, int h, int w) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 1024) return;
+  const int i = e / 32, j = e % 32;
+  const int ys = (i * h) / 32, ye = ((i + 1) * h + 31) / 32;
+  const int xs = (j * w) / 32, xe = ((j + 1) * w + 31) / 32;
+  float acc = 0.f;
+  for (int y = ys; y < ye; ++y)
+    for (int x = xs; x < xe; ++x) acc += gwmap[y * w + x];
+  gfcw[e] += acc / (float)((ye - ys) * (xe - xs));
+}
+
+__global__ void ga_bias1_kernel(const float* __restrict__ S, const float* __restrict__ wsum, float* __restrict__ gb1, int BT) {
+  const int c = threadIdx.x;
+  float acc = 0.f;
+  for (int n = 0; n < BT; ++n) acc += wsum[n] * S[n * 64 + c];
+  gb1[c] += acc;
+}
+
+// x, gout: [M][64]; gx [M][64] out; gparams[8]: fc.weight, fc.bias, proj1.weight, proj1.bias, proj2.weight, proj2.bias, proj3.weight, proj3.bias
+int ga_backward(const selfc_ctx* ctx, const GaW& g, const float* x, const float* gout, float* gx, float* const* gparams, char* wsp,
+                const Workspace& ws, char* tp, const Tape& tape, const Dims& d, cudaStream_t st) {
+  const long long M = d.M(), hw = d.hw();
+  const int T = d.T, BT = d.B * d.T;
+  float* wmap = reinterpret_cast<float*>(wsp + ws.wmap);
+  float* partial = reinterpret_cast<float*>(wsp + ws.partial);
+  float* wmat = reinterpret_cast<float*>(wsp + ws.wmat);
+  float* wsum = reinterpret_cast<float*>(wsp + ws.wsum);
+  float* xmix = reinterpret_cast<float*>(tp + tape.sc);          // [M][64]
+  float* gxmix = reinterpret_cast<float*>(tp + tape.sa);         // [M][64]
+  float* small = reinterpret_cast<float*>(tp + tape.small);
+  auto up64 = [](size_t n) { return (n + 63) & ~(size_t)63; };   // keep every sub-buffer 16-byte aligned
+  float* S = small;                                  // [BT][64]
+  float* R = S + (size_t)BT * 64;                    // [B][T][T]
+  float* gd = R + up64((size_t)d.B * T * T);         // [BT][64]
+  float* gwmap = gd + (size_t)BT * 64;               // [hw]
+  float* gb1w = gwmap + up64((size_t)hw);            // [64] scratch for the wsum-weighted bias gradient
+  float* scratch = train_scratch();
+  float* zb = train_zero_bias();
+  SELFC_CHECK_ARG(scratch && zb, "out of device memory (training scratch)");
+  // recompute the forward's small quantities
+  SELFC_TRY(launch_ga_wmap(g.fcw, wmap, d.h, d.w, st));
+  SELFC_TRY(launch_ga_stat<float>(x, kStpC, wmap, partial, ws.nsplit, BT, (int)hw, st));
+  SELFC_TRY(launch_ga_weights(partial, ws.nsplit, g.fcb, g.p2w, g.p2b, g.p3w, g.p3b, wmat, wsum, d.B, T, st));
+  const int nb16 = cdiv(M * 16, 256);
+  ga_mix_f32_kernel<<<nb16, 256, 0, st>>>(x, wmat, 0, nullptr, xmix, T, hw, M);
+  SELFC_LAUNCH_CHECK("ga_mix_f32_kernel");
+  // proj1: weight gradient from (Xmix, gout); gXmix = P1^T gout.  Its plain bias gradient is NOT the right one (the bias is
+  // scaled by colsum(W) per frame), so it goes to a scratch and the weighted sum is formed from the per-frame sums S below.
+  SELFC_CUDA(cudaMemsetAsync(gb1w, 0, 64 * sizeof(float), st));
+  SELFC_TRY(pointwise_backward(g.p1w, 64, 64, 64, xmix, 64, gout, 64, gxmix, 64, false, gparams ? gparams[2] : nullptr, gb1w, scratch, zb, d, st));
+  frame_channel_sum_kernel<<<BT, 256, 0, st>>>(gout, S, hw);
+  SELFC_LAUNCH_CHECK("frame_channel_sum_kernel");
+  // gx = gout + sum_t' W[t,t'] gXmix[t']
+  ga_mix_f32_kernel<<<nb16, 256, 0, st>>>(gxmix, wmat, 1, gout, gx, T, hw, M);
+  SELFC_LAUNCH_CHECK("ga_mix_f32_kernel");
+  pair_dot_kernel<<<d.B * T * T, 256, 0, st>>>(x, gxmix, R, T, hw);
+  SELFC_LAUNCH_CHECK("pair_dot_kernel");
+  SELFC_CUDA(cudaMemsetAsync(gwmap, 0, (size_t)hw * sizeof(float), st));
+  const size_t smem = (size_t)(5 * T * 64 + 2 * T * 32) * sizeof(float);
+  ga_small_bwd_kernel<<<d.B, 64, smem, st>>>(partial, ws.nsplit, g.fcb, g.p2w, g.p2b, g.p3w, g.p3b, g.p1b, R, S, gd,
+                                             gparams ? gparams[4] : nullptr, gparams ? gparams[5] : nullptr, gparams ? gparams[6] : nullptr,
+                                             gparams ? gparams[7] : nullptr, gparams ? gparams[1] : nullptr, T);
+  SELFC_LAUNCH_CHECK("ga_small_bwd_kernel");
+  ga_desc_bwd_kernel<<<cdiv(M, 256), 256, 0, st>>>(x, wmap, gd, gx, gwmap, hw, M);
+  SELFC_LAUNCH_CHECK("ga_desc_bwd_kernel");
+  if (gparams) {
+    ga_wmap_bwd_kernel<<<4, 256, 0, st>>>(gwmap, gparams[0], d.h, d.w);
+    SELFC_LAUNCH_CHECK("ga_wmap_bwd_kernel");
+    // proj1.bias: sum_{b,t'} wsum[b,t'] * S[b,t',ch]
+    ga_bias1_kernel<<<1, 64, 0, st>>>(S, wsum, gparams[3], BT);
+    SELFC_LAUNCH_CHECK("ga_bias1_kernel");
+  }
+  return 0;
+}
+
 // NCHW [N,51,h,w] -> planar quads (test boundary)
 static int nchw51_to_quads(const float* x51, float* z, const Dims& d, cudaStream_t st) {
   SELFC_TRY(launch_nchw_slice_to_dense<float>(x51, 51, 0, z, 4, 0, 0, 3, 4, d.M(), d.hw(), st));
@@ -702,5 +951,29 @@ int selfc_head_sampler_backward(selfc_ctx* ctx, const float* feat, const float* 
     SELFC_TRY(launch_nchw_slice_to_dense<float>(gv, kHF, 4 * q, gz + quad_off((size_t)d.M(), 1 + q, 0), 4, 0, 0, 4, 4, d.M(), d.hw(), st));
   SELFC_TRY(head_sampler_backward(ctx, featd, eps, seed, offset, gz, gfd, gparams, (char*)workspace, ws, tp, tl, d, st));
   return launch_dense_to_nchw<float>(gfd, 64, 0, 0, gfeat, 64, d.M(), d.hw(), st);
+}
+
+/* a13 building block: backward of GlobalAgg (:265-285) whose fc.weight is parameter `first_param`.  x, gout [B*T,64,h,w] -> gx;
+ * gparams[8] (fc.weight, fc.bias, proj1.weight, proj1.bias, proj2.weight, proj2.bias, proj3.weight, proj3.bias) accumulated into. */
+int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gout, float* gx, float* const* gparams, int B,
+                              int T, int h, int w, void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(x && gout && gx && tape, "global_agg_backward: null pointer");
+  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32 && T <= 16, "global_agg_backward: FP32 mode and T <= 16 only");
+  const GaW* g = find_ga(ctx, first_param);
+  SELFC_CHECK_ARG(g != nullptr, "global_agg_backward: parameter index %d is not the fc.weight of a GlobalAgg", first_param);
+  const Tape tl = make_tape(B, T, h, w);
+  SELFC_CHECK_ARG(tape_bytes >= tl.total && aligned16(tape), "global_agg_backward: tape too small (%zu < %zu)", tape_bytes, tl.total);
+  Dims d{B, T, h, w};
+  cudaStream_t st = (cudaStream_t)stream;
+  char* tp = (char*)tape;
+  float* xd = reinterpret_cast<float*>(tp + tl.ga);
+  float* gd = xd + (size_t)d.M() * 64;
+  float* gxd = gd + (size_t)d.M() * 64;
+  SELFC_TRY(launch_nchw_to_dense<float>(x, xd, 64, 0, 0, 64, 64, d.M(), d.hw(), st));
+  SELFC_TRY(launch_nchw_to_dense<float>(gout, gd, 64, 0, 0, 64, 64, d.M(), d.hw(), st));
+  SELFC_TRY(ga_backward(ctx, *g, xd, gd, gxd, gparams, (char*)workspace, ws, tp, tl, d, st));
+  return launch_dense_to_nchw<float>(gxd, 64, 0, 0, gx, 64, d.M(), d.hw(), st);
 }
 }  // extern "C"

@@ -312,6 +312,23 @@ class Engine:
                                                            _stream(self.device)), "head_sampler_backward")
         return gfeat, dict(zip(names, grads))
 
+    def global_agg_backward(self, prefix: str, x: torch.Tensor, gout: torch.Tensor, T: int):
+        """Backward of GlobalAgg `prefix` (fp32 mode): x, gout [B*T,64,h,w] -> (gx, grads of its eight parameters)."""
+        x = self._check_in(x, "x")
+        gout = self._check_in(gout, "gout")
+        B, h, w = self._clip_dims(x, T)
+        ws = self._workspace(B, T, h, w)
+        tape = self._tape(B, T, h, w)
+        first = PARAM_INDEX[prefix + ".fc.weight"]
+        names = PARAM_NAMES[first:first + 8]
+        grads = [torch.zeros(self._shapes[n], dtype=torch.float32, device=self.device) for n in names]
+        ptrs = (C.c_void_p * 8)(*[g.data_ptr() for g in grads])
+        gx = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_global_agg_backward(self._ctx, first, _ptr(x), _ptr(gout), _ptr(gx), ptrs, B, T, h, w, _ptr(ws),
+                                                         ws.numel(), _ptr(tape), tape.numel(), _stream(self.device)), "global_agg_backward")
+        return gx, dict(zip(names, grads))
+
     def conv3x3(self, prefix: str, k: int, x: torch.Tensor, T: int) -> torch.Tensor:
         """conv{k+1} of the dense block `prefix` on its concatenated input x [B*T,Cin+32k,h,w] -> [B*T,32,h,w]."""
         first = PARAM_INDEX[prefix + ".conv1.weight"]

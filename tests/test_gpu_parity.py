@@ -462,3 +462,25 @@ def test_head_sampler_backward_vs_autograd(dev):
     for name, gval in grads.items():
         ref = leaf[name].grad
         torch.testing.assert_close(gval.cpu(), ref, rtol=0, atol=3e-4 * float(ref.abs().max()) + 1e-6)
+
+
+@pytest.mark.parametrize("h,w,t", [(10, 18, 2), (33, 40, 7)])
+def test_global_agg_backward_vs_autograd(dev, h, w, t):
+    """Backward of GlobalAgg (pooled descriptor -> T x T softmax mixing -> proj1 mix + residual) against autograd on the
+    oracle: input gradient and the eight parameter gradients (fc through the overlapping adaptive-pool bins)."""
+    sd = so.make_state_dict(6, gain=2.0)
+    eng = _engine(dev, sd)
+    b = 2
+    prefix = "stp_net.global_m2"
+    gen = torch.Generator().manual_seed(h)
+    x = torch.randn(b * t, 64, h, w, generator=gen)
+    gout = torch.randn(b * t, 64, h, w, generator=gen)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(prefix + ".")}
+    xr = x.clone().requires_grad_(True)
+    so.global_agg(leaf, prefix, xr, t).backward(gout)
+    gx, grads = eng.global_agg_backward(prefix, x.to(dev), gout.to(dev), t)
+    torch.testing.assert_close(gx.cpu(), xr.grad, rtol=0, atol=3e-4 * float(xr.grad.abs().max()) + 1e-6)
+    for name, gval in grads.items():
+        ref = leaf[name].grad
+        # proj3.bias shifts every logit of a softmax row equally: its exact gradient is 0 and both sides return fp32 noise (~1e-6)
+        torch.testing.assert_close(gval.cpu(), ref, rtol=0, atol=5e-4 * float(ref.abs().max()) + 2e-5)
