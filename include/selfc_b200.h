@@ -111,6 +111,15 @@ int selfc_head_sampler_backward(selfc_ctx* ctx, const float* feat, const float* 
 int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gout, float* gx,
                               float* const* gparams, int B, int T, int h, int w, void* workspace, size_t workspace_bytes,
                               void* tape, size_t tape_bytes, void* stream);
+/* a13 SelfCModel.optimize_parameters' forward + backward (models/SelfC_model.py:148-170, models/modules/loss.py:5-21,
+ * Quantization.py:4-17 with its straight-through gradient; losses of train_rescaling_selfc_large.yml: l2 forward fit against
+ * ref_l, Charbonnier reconstruction, total x 144*144*3).  hr [B*T,3,H,W], ref_l [B*T,3,H/4,W/4], eps as in selfc_up.
+ * grads[354]: device fp32 buffers in the reference parameter layouts (state_dict order), ACCUMULATED into -- zero them for a
+ * plain step; losses: 3 device floats (total, l_forw_fit, l_back_rec).  Block inputs are kept on the tape and every block's
+ * forward is recomputed in the backward pass.  FP32 mode (fp32-FMA kernels), T <= 16. */
+int selfc_train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset,
+                      float* const* grads, int n_grads, float* losses, int B, int T, int H, int W, void* workspace,
+                      size_t workspace_bytes, void* tape, size_t tape_bytes, void* stream);
 /* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
  * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
 int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,

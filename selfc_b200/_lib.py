@@ -32,6 +32,7 @@ SIGNATURES = {
     "selfc_d2dt_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_invblock_backward": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_train_tape_bytes": (_sz, [_i, _i, _i, _i]),
+    "selfc_train_grads": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "selfc_global_agg_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "selfc_head_sampler_backward": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "selfc_conv3x3": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),

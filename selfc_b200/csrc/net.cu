@@ -29,15 +29,6 @@ void set_error(const char* fmt, ...) {
 }
 uint64_t& launch_counter() { return g_launches; }
 
-// ---- parameter index map (module registration order of the reference) ------------------------
-constexpr int P_INV0 = 0;           // operations.{1..8}.{F,G,H}.conv{1..5}.{weight,bias}: 8 * 3 * 10
-constexpr int P_LOCAL1 = 240;       // stp_net.local_m1 (10)
-constexpr int P_LOCAL2 = 250;       // stp_net.local_m2 (10)
-constexpr int P_GLOBAL1 = 260;      // stp_net.global_m1 (8: fc, proj1, proj2, proj3)
-constexpr int P_GLOBAL2 = 268;
-constexpr int P_OTHER = 276;        // 4 x (D2DT 10, GlobalAgg 8)
-constexpr int P_TAIL = 348;         // tail_gmm.{1,3,5}.{weight,bias}
-static_assert(P_TAIL + 6 == SELFC_NUM_PARAMS, "parameter map");
 
 }  // namespace selfc
 
@@ -288,7 +279,7 @@ static int down_impl(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_
 
 template <typename T>
 static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, float* hf,
-                   const Dims& d, char* wsp, const Workspace& ws, cudaStream_t st) {
+                   const Dims& d, char* wsp, const Workspace& ws, cudaStream_t st, const TrainHooks* hooks = nullptr) {
   float* z = reinterpret_cast<float*>(wsp + ws.z);
   T* gbuf = reinterpret_cast<T*>(wsp + ws.gbuf);
   T* hbuf = reinterpret_cast<T*>(wsp + ws.hbuf);
@@ -323,7 +314,9 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
     ConvArgs<T> a = conv5_args<T>(ctx, W, stpbuf, pitch, d);
     a.epi = EPI_STORE; a.act = 0; a.outT = feat; a.outT_pitch = kStpC; a.outT_off = 0;
     PROF(ctx, st, 1, conv5_flops(W, d), launch_temporal<T>(ctx, W.t5, a, d, st));
-    SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, slabM, nullptr, 0, nullptr, wsp, ws, d, st,
+    // training: every GlobalAgg output (= input of the next STP stage / the final feature) is also kept as fp32 [M][64]
+    float* ga_keep = hooks && hooks->ga_save ? hooks->ga_save + (size_t)(i + 1) * d.M() * kStpC : nullptr;
+    SELFC_TRY(run_global_agg<T>(ctx, ctx->ga[i], feat, stpbuf, ws.spitch, slabM, ga_keep, ga_keep ? kStpC : 0, nullptr, wsp, ws, d, st,
                                 i == 5 ? fact : nullptr));
   }
   // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
@@ -391,7 +384,11 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   else
     PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample(params, false, eps, seed, offset, z, false, /*planar z*/ -1, 0, d.B, d.T, d.h, d.w, st));
   if (hf) PROF(ctx, st, 5, (double)M * 48 * 8, launch_export_hf(z, hf, M, hw, st));
-  for (int blk = 7; blk >= 0; --blk) SELFC_TRY(run_invblock<T>(ctx, blk, true, wsp, ws, d, st));
+  for (int blk = 7; blk >= 0; --blk) {
+    if (hooks && hooks->z_save)      // training: the state each reverse block starts from
+      SELFC_CUDA(cudaMemcpyAsync(hooks->z_save + (size_t)blk * d.M() * kZQuads * 4, z, (size_t)d.M() * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
+    SELFC_TRY(run_invblock<T>(ctx, blk, true, wsp, ws, d, st));
+  }
   PROF(ctx, st, 5, (double)M * (51 * 4 + 48 * 4), launch_fa_rev(z, false, hr, d.B * d.T, d.h, d.w, st));
   return 0;
 }
@@ -491,6 +488,18 @@ const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
 
 int invblock_f32(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
   return run_invblock<float>(ctx, blk, rev, wsp, ws, d, st);
+}
+int up_f32_hooked(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, const Dims& d, char* wsp,
+                  const Workspace& ws, cudaStream_t st, const TrainHooks* hooks) {
+  return up_impl<float>(ctx, lr, eps, seed, offset, hr, nullptr, d, wsp, ws, st, hooks);
+}
+// one STP stage's dense block in FP32 mode: conv1..4 + conv5 on the buffer whose X slot is already filled -> feat [M][64]
+int stp_dense_f32(const selfc_ctx* ctx, int i, float* stpbuf, int pitch, float* feat, const Dims& d, cudaStream_t st) {
+  const DenseW& W = ctx->stp[i];
+  SELFC_TRY(run_dense_convs<float>(ctx, W, stpbuf, pitch, d, st));
+  ConvArgs<float> a = conv5_args<float>(ctx, W, stpbuf, pitch, d);
+  a.epi = EPI_STORE; a.act = 0; a.outF = feat; a.outF_pitch = kStpC; a.outF_off = 0;
+  return launch_conv_simt<float>(a, st);
 }
 const GaW* find_ga(selfc_ctx* ctx, int first_param) {
   const int ga_first[6] = {P_GLOBAL1, P_GLOBAL2, P_OTHER + 10, P_OTHER + 28, P_OTHER + 46, P_OTHER + 64};

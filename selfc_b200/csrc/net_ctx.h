@@ -10,6 +10,16 @@
 
 namespace selfc {
 
+// ---- parameter index map (module registration order of the reference) ------------------------
+constexpr int P_INV0 = 0;           // operations.{1..8}.{F,G,H}.conv{1..5}.{weight,bias}: 8 * 3 * 10
+constexpr int P_LOCAL1 = 240;       // stp_net.local_m1 (10)
+constexpr int P_LOCAL2 = 250;       // stp_net.local_m2 (10)
+constexpr int P_GLOBAL1 = 260;      // stp_net.global_m1 (8: fc, proj1, proj2, proj3)
+constexpr int P_GLOBAL2 = 268;
+constexpr int P_OTHER = 276;        // 4 x (D2DT 10, GlobalAgg 8)
+constexpr int P_TAIL = 348;         // tail_gmm.{1,3,5}.{weight,bias}
+static_assert(P_TAIL + 6 == SELFC_NUM_PARAMS, "parameter map");
+
 struct DenseW {            // one D2DTInput in kernel layout
   int cin = 0, cout = 0, xpad = 0;
   float* w[5] = {};        // SIMT fp32 [taps*cin_buf][np]
@@ -80,6 +90,16 @@ struct Dims {
 // layout of the dense-block buffers (common.cuh): slab-planar in BF16 mode, pixel-major in FP32 mode
 inline long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->mode == SELFC_MODE_BF16 ? d.M() : 0; }
 
+
+// what the training step asks the reverse pass to keep (fp32, device): ga_save = 7 x [M][64] (slot i+1 <- output of
+// GlobalAgg i), z_save = 8 x planar state (slot blk <- the state reverse block blk starts from)
+struct TrainHooks {
+  float* ga_save = nullptr;
+  float* z_save = nullptr;
+};
+int up_f32_hooked(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, const Dims& d, char* wsp,
+                  const Workspace& ws, cudaStream_t st, const TrainHooks* hooks);
+int stp_dense_f32(const selfc_ctx* ctx, int i, float* stpbuf, int pitch, float* feat, const Dims& d, cudaStream_t st);
 
 // fp32-mode forward pieces re-used by the training step (net.cu)
 int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st);

@@ -414,6 +414,10 @@ struct Tape {
   size_t ga;            // 7 x [M][64]: input of STP stage i (i = 0: LR in 4 channels of the first slot) and the final feature
   size_t sa, sb;        // [M][256] scratch each
   size_t sc;            // [M][64] scratch
+  size_t gcur, gnext, feat;   // [M][64] each: running feature gradient, its successor, a recomputed STP stage output
+  size_t rec;           // [B*T,3,H,W] reconstruction (NCHW), lrq: [B*T,3,h,w] quantised LR (NCHW), glr: [M][4]
+  size_t lrq, glr;
+  size_t loss;          // 4 floats: sum of squared LR errors, sum of Charbonnier terms
   size_t small;         // per-clip scratch of the GlobalAgg backward
 };
 static Tape make_tape(int B, int T, int h, int w) {
@@ -427,6 +431,13 @@ static Tape make_tape(int B, int T, int h, int w) {
   t.sa = take(M * 256 * 4);
   t.sb = take(M * 256 * 4);
   t.sc = take(M * 64 * 4);
+  t.gcur = take(M * 64 * 4);
+  t.gnext = take(M * 64 * 4);
+  t.feat = take(M * 64 * 4);
+  t.rec = take(M * 48 * 4);
+  t.lrq = take(M * 3 * 4);
+  t.glr = take(M * 4 * 4);
+  t.loss = take(64);
   t.small = take(((size_t)B * T * 128 + (size_t)B * T * T + (size_t)h * w + 1024) * 4);
   t.total = off;
   return t;
@@ -857,6 +868,175 @@ int ga_backward(const selfc_ctx* ctx, const GaW& g, const float* x, const float*
   return 0;
 }
 
+// ====================================================================================================================
+// The training step's forward + backward (models/SelfC_model.py:148-170): losses and all 354 parameter gradients.
+// ====================================================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// l_forw_fit = mean((LR_pre - ref_L)^2) (loss.py:12-13): accumulates the sum into loss[0] and writes the LR part of the state
+// gradient: gz quad 0 = (gq0 from the reverse pass, straight through the quantiser) + glr (from the STP's first block) +
+// 2*(lr_pre - ref)*gscale; the HF part of the downscaling output does not enter the loss: gz quads 1..12 = 0.
+__global__ void loss_forw_kernel(const float* __restrict__ zout, const float* __restrict__ ref_l, const float* __restrict__ glr,
+                                 float* __restrict__ gz, float* __restrict__ loss, float gscale, long long hw, long long M) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float part = 0.f;
+  if (m < M) {
+    const long long n = m / hw, pix = m - n * hw;
+    const float4 lr = load4(zout + quad_off((size_t)M, 0, (size_t)m));
+    float4 g = load4(gz + quad_off((size_t)M, 0, (size_t)m));
+    const float4 gs = load4(glr + m * 4);
+    const float d0 = lr.x - ref_l[(n * 3 + 0) * hw + pix], d1 = lr.y - ref_l[(n * 3 + 1) * hw + pix], d2 = lr.z - ref_l[(n * 3 + 2) * hw + pix];
+    part = d0 * d0 + d1 * d1 + d2 * d2;
+    g.x += gs.x + 2.f * d0 * gscale; g.y += gs.y + 2.f * d1 * gscale; g.z += gs.z + 2.f * d2 * gscale; g.w = 0.f;
+    store4(gz + quad_off((size_t)M, 0, (size_t)m), g);
+    for (int q = 1; q < kZQuads; ++q) store4(gz + quad_off((size_t)M, q, (size_t)m), make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss, part);
+}
+
+// l_back_rec = mean(sqrt((x - rec)^2 + 1e-6)) (loss.py:15-17) and the backward of the reverse FrequencyAnalyzer
+// (rec[c,4i+sy,4j+sx] = lf[c] + hf[c*16+sy*4+sx], SelfC_GMM_arch_inv.py:79-82): one thread per LR pixel writes the whole
+// gradient state: quad 0 = sum over the 4x4 block, HF quads = the per-pixel gradients in the reverse (c*16+sy*4+sx) order.
+__global__ void loss_back_fa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ rec, float* __restrict__ gz,
+                                        float* __restrict__ loss, float gscale, int N, int h, int w) {
+  const long long M = (long long)N * h * w;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float part = 0.f;
+  if (m < M) {
+    const int j = (int)(m % w);
+    const int i = (int)((m / w) % h);
+    const int n = (int)(m / ((long long)w * h));
+    const int W = 4 * w, H = 4 * h;
+    float glf[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long base = (((long long)n * 3 + c) * H + 4 * i) * W + 4 * j;
+#pragma unroll
+      for (int sy = 0; sy < 4; ++sy) {
+        const float4 xv = load4(x + base + (long long)sy * W);
+        const float4 rv = load4(rec + base + (long long)sy * W);
+        const float dd[4] = {xv.x - rv.x, xv.y - rv.y, xv.z - rv.z, xv.w - rv.w};
+        float g4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float r = sqrtf(dd[e] * dd[e] + 1e-6f);
+          part += r;
+          g4[e] = -dd[e] / r * gscale;
+          glf[c] += g4[e];
+        }
+        store4(gz + quad_off((size_t)M, 1 + (c * 16 + sy * 4) / 4, (size_t)m), make_float4(g4[0], g4[1], g4[2], g4[3]));
+      }
+    }
+    store4(gz + quad_off((size_t)M, 0, (size_t)m), make_float4(glf[0], glf[1], glf[2], 0.f));
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss + 1, part);
+}
+
+// dst[m][doff + c] = src[m][soff + c], c < ncol (ncol % 4 == 0)
+__global__ void copy_cols_kernel(float* __restrict__ dst, int dpitch, int doff, const float* __restrict__ src, int spitch, int soff, int ncol,
+                                 long long M) {
+  const int per = ncol / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * per) return;
+  const long long m = idx / per;
+  const int c = (int)(idx - m * per) * 4;
+  store4(dst + m * dpitch + doff + c, load4(src + m * spitch + soff + c));
+}
+
+// losses[0..2] = (total, l_forw_fit, l_back_rec) from the accumulated sums
+__global__ void loss_finish_kernel(const float* __restrict__ acc, float* __restrict__ out, float n_lr, float n_hr) {
+  const float lf = acc[0] / n_lr, lb = acc[1] / n_hr;
+  out[0] = (lf + lb) * (144.0f * 144.0f * 3.0f);
+  out[1] = lf;
+  out[2] = lb;
+}
+
+int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset, float* const* grads,
+                float* losses, const Dims& d, char* wsp, const Workspace& ws, char* tp, const Tape& tape, cudaStream_t st) {
+  const long long M = d.M(), hw = d.hw();
+  const int BT = d.B * d.T;
+  const size_t state_f = (size_t)M * kZQuads * 4;       // floats per planar state
+  float* z = reinterpret_cast<float*>(wsp + ws.z);
+  float* fbuf = reinterpret_cast<float*>(wsp + ws.fbuf);
+  float* stpbuf = reinterpret_cast<float*>(wsp + ws.stpbuf);
+  float* gdense = reinterpret_cast<float*>(wsp + ws.params);
+  float* gz = reinterpret_cast<float*>(tp + tape.gz);
+  float* zs_dn = reinterpret_cast<float*>(tp + tape.zsave);             // slots 0..7: input of forward block blk; slot 8: the output
+  float* zs_up = zs_dn + 9 * state_f;                                   // slots 0..7: input of reverse block blk
+  float* ga_save = reinterpret_cast<float*>(tp + tape.ga);
+  float* gcur = reinterpret_cast<float*>(tp + tape.gcur);
+  float* gnext = reinterpret_cast<float*>(tp + tape.gnext);
+  float* feat = reinterpret_cast<float*>(tp + tape.feat);
+  float* rec = reinterpret_cast<float*>(tp + tape.rec);
+  float* lrq = reinterpret_cast<float*>(tp + tape.lrq);
+  float* glr = reinterpret_cast<float*>(tp + tape.glr);
+  float* lacc = reinterpret_cast<float*>(tp + tape.loss);
+  float* scratch = train_scratch();
+  SELFC_CHECK_ARG(scratch != nullptr, "out of device memory (training scratch)");
+  const float kScale = 144.0f * 144.0f * 3.0f;
+  const float n_lr = (float)((double)M * 3.0), n_hr = (float)((double)M * 48.0);
+  SELFC_CUDA(cudaMemsetAsync(lacc, 0, 64, st));
+
+  // ---- forward: downscale (states kept), quantise, upscale (states and STP stage outputs kept) ----
+  SELFC_TRY(launch_fa_fwd_z<float>(hr, z, fbuf, ws.fpitch, 0, BT, d.h, d.w, st));
+  for (int blk = 0; blk < 8; ++blk) {
+    SELFC_CUDA(cudaMemcpyAsync(zs_dn + blk * state_f, z, state_f * 4, cudaMemcpyDeviceToDevice, st));
+    SELFC_TRY(invblock_f32(ctx, blk, false, wsp, ws, d, st));
+  }
+  SELFC_CUDA(cudaMemcpyAsync(zs_dn + 8 * state_f, z, state_f * 4, cudaMemcpyDeviceToDevice, st));
+  SELFC_TRY(launch_export_down(z, nullptr, nullptr, lrq, M, hw, st));            // Quantization.forward
+  TrainHooks hooks;
+  hooks.ga_save = ga_save;
+  hooks.z_save = zs_up;
+  SELFC_TRY(up_f32_hooked(ctx, lrq, eps, seed, offset, rec, d, wsp, ws, st, &hooks));
+
+  // ---- backward ----
+  loss_back_fa_bwd_kernel<<<cdiv(M, 128), 128, 0, st>>>(hr, rec, gz, lacc, kScale / n_hr, BT, d.h, d.w);
+  SELFC_LAUNCH_CHECK("loss_back_fa_bwd_kernel");
+  for (int blk = 0; blk < 8; ++blk)            // the reverse pass ran blocks 7..0, so their backward runs 0..7
+    SELFC_TRY(invblock_backward(ctx, blk, true, zs_up + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
+  // gz now holds d loss / d [LR_q | v]; the HF part goes through the sampler and the GMM head into the STP
+  SELFC_TRY(head_sampler_backward(ctx, ga_save + (size_t)6 * M * kStpC, eps, seed, offset, gz, gcur, grads ? grads + P_TAIL : nullptr, wsp, ws,
+                                  tp, tape, d, st));
+  const int stp_first[6] = {P_LOCAL1, P_LOCAL2, P_OTHER, P_OTHER + 18, P_OTHER + 36, P_OTHER + 54};
+  const int ga_first[6] = {P_GLOBAL1, P_GLOBAL2, P_OTHER + 10, P_OTHER + 28, P_OTHER + 46, P_OTHER + 64};
+  for (int i = 5; i >= 0; --i) {
+    const DenseW& W = ctx->stp[i];
+    const int pitch = W.xpad + 4 * kGrowth;
+    // recompute stage i: X slot <- its input (LR for the first stage), dense block -> feat
+    if (i == 0) SELFC_TRY(launch_nchw_to_dense<float>(lrq, stpbuf, pitch, 0, 0, 3, W.xpad, M, hw, st));
+    else {
+      copy_cols_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(stpbuf, pitch, 0, ga_save + (size_t)i * M * kStpC, kStpC, 0, kStpC, M);
+      SELFC_LAUNCH_CHECK("copy_cols_kernel");
+    }
+    SELFC_TRY(stp_dense_f32(ctx, i, stpbuf, pitch, feat, d, st));
+    SELFC_TRY(ga_backward(ctx, ctx->ga[i], feat, gcur, gnext, grads ? grads + ga_first[i] : nullptr, wsp, ws, tp, tape, d, st));
+    SELFC_TRY(dense_block_backward(ctx, W, stpbuf, pitch, gnext, kStpC, gdense, scratch, grads ? grads + stp_first[i] : nullptr, d, st));
+    if (i > 0) {
+      copy_cols_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(gcur, kStpC, 0, gdense, pitch, 0, kStpC, M);
+    } else {
+      copy_cols_kernel<<<cdiv(M, 256), 256, 0, st>>>(glr, 4, 0, gdense, pitch, 0, 4, M);
+    }
+    SELFC_LAUNCH_CHECK("copy_cols_kernel");
+  }
+  // straight-through quantiser + forward-fit loss: gradient of the downscaling output
+  loss_forw_kernel<<<cdiv(M, 128), 128, 0, st>>>(zs_dn + 8 * state_f, ref_l, glr, gz, lacc, kScale / n_lr, hw, M);
+  SELFC_LAUNCH_CHECK("loss_forw_kernel");
+  for (int blk = 7; blk >= 0; --blk)
+    SELFC_TRY(invblock_backward(ctx, blk, false, zs_dn + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
+  if (losses) {
+    loss_finish_kernel<<<1, 1, 0, st>>>(lacc, losses, n_lr, n_hr);
+    SELFC_LAUNCH_CHECK("loss_finish_kernel");
+  }
+  return 0;
+}
+
 // NCHW [N,51,h,w] -> planar quads (test boundary)
 static int nchw51_to_quads(const float* x51, float* z, const Dims& d, cudaStream_t st) {
   SELFC_TRY(launch_nchw_slice_to_dense<float>(x51, 51, 0, z, 4, 0, 0, 3, 4, d.M(), d.hw(), st));
@@ -975,5 +1155,23 @@ int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, c
   SELFC_TRY(launch_nchw_to_dense<float>(gout, gd, 64, 0, 0, 64, 64, d.M(), d.hw(), st));
   SELFC_TRY(ga_backward(ctx, *g, xd, gd, gxd, gparams, (char*)workspace, ws, tp, tl, d, st));
   return launch_dense_to_nchw<float>(gxd, 64, 0, 0, gx, 64, d.M(), d.hw(), st);
+}
+
+/* a13: forward + backward of one training step (models/SelfC_model.py:148-170 with the training YAML's losses: l2 forward fit
+ * against ref_l, Charbonnier reconstruction, x 144*144*3; Quantization with its straight-through gradient).  hr [B*T,3,H,W],
+ * ref_l [B*T,3,H/4,W/4]; eps as in selfc_up.  grads[354]: device fp32 buffers in the reference parameter layouts, ACCUMULATED
+ * into (zero them for a plain step); losses: 3 device floats (total, l_forw_fit, l_back_rec).  FP32 mode, T <= 16. */
+int selfc_train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset,
+                      float* const* grads, int n_grads, float* losses, int B, int T, int H, int W, void* workspace, size_t workspace_bytes,
+                      void* tape, size_t tape_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, H, W, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(hr && ref_l && tape && aligned16(hr), "train_grads: null or misaligned pointer");
+  SELFC_CHECK_ARG(grads == nullptr || n_grads == SELFC_NUM_PARAMS, "train_grads: expected %d gradient buffers", SELFC_NUM_PARAMS);
+  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32 && T <= 16, "train_grads: FP32 mode and T <= 16 only");
+  const Tape tl = make_tape(B, T, H / 4, W / 4);
+  SELFC_CHECK_ARG(tape_bytes >= tl.total && aligned16(tape), "train_grads: tape too small (%zu < %zu)", tape_bytes, tl.total);
+  Dims d{B, T, H / 4, W / 4};
+  return train_grads(ctx, hr, ref_l, eps, seed, offset, grads, losses, d, (char*)workspace, ws, (char*)tape, tl, (cudaStream_t)stream);
 }
 }  // extern "C"

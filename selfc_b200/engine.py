@@ -329,6 +329,28 @@ class Engine:
                                                          ws.numel(), _ptr(tape), tape.numel(), _stream(self.device)), "global_agg_backward")
         return gx, dict(zip(names, grads))
 
+    def train_grads(self, hr: torch.Tensor, ref_l: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0,
+                    offset: int = 0, grads: Optional[Sequence[torch.Tensor]] = None):
+        """Forward + backward of one training step (SelfC_model.py:148-170; fp32 mode): hr [B*T,3,H,W], ref_l [B*T,3,H/4,W/4]
+        -> ({parameter name: gradient}, losses tensor [total, l_forw_fit, l_back_rec]).  `grads` (354 fp32 device tensors in
+        PARAM_NAMES order) are accumulated into when given, otherwise fresh zero tensors are used."""
+        hr = self._check_in(hr, "hr")
+        ref_l = self._check_in(ref_l, "ref_l")
+        if eps is not None:
+            eps = _dev_check(eps)
+        B, H, W = self._clip_dims(hr, T)
+        ws = self._workspace(B, T, H // 4, W // 4)
+        tape = self._tape(B, T, H // 4, W // 4)
+        if grads is None:
+            grads = [torch.zeros(self._shapes[n], dtype=torch.float32, device=self.device) for n in PARAM_NAMES]
+        ptrs = (C.c_void_p * NUM_PARAMS)(*[g.data_ptr() for g in grads])
+        losses = torch.zeros(3, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_train_grads(self._ctx, _ptr(hr), _ptr(ref_l), _ptr(eps), seed, offset, ptrs, NUM_PARAMS, _ptr(losses),
+                                                 B, T, H, W, _ptr(ws), ws.numel(), _ptr(tape), tape.numel(), _stream(self.device)),
+                       "train_grads")
+        return dict(zip(PARAM_NAMES, grads)), losses
+
     def conv3x3(self, prefix: str, k: int, x: torch.Tensor, T: int) -> torch.Tensor:
         """conv{k+1} of the dense block `prefix` on its concatenated input x [B*T,Cin+32k,h,w] -> [B*T,32,h,w]."""
         first = PARAM_INDEX[prefix + ".conv1.weight"]
