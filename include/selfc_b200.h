@@ -120,6 +120,13 @@ int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, c
 int selfc_train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset,
                       float* const* grads, int n_grads, float* losses, int B, int T, int H, int W, void* workspace,
                       size_t workspace_bytes, void* tape, size_t tape_bytes, void* stream);
+/* a13 optimiser step (models/SelfC_model.py:66-68 Adam, :172-176 clip_grad_norm_ + step) on a flat gradient buffer.
+ * params[n_tensors]: DEVICE array of device pointers to the parameter tensors; offsets[n_tensors+1]: DEVICE array of the
+ * tensors' element offsets inside grad / m / v (flat fp32, `total` elements); gscale multiplies the gradient first (1/world
+ * after a SUM all-reduce); max_norm <= 0 disables clipping; step >= 1 (bias correction); sqnorm_scratch: one device float. */
+int selfc_adam_step(float* const* params, const long long* offsets, int n_tensors, long long total, const float* grad,
+                    float* m, float* v, float* sqnorm_scratch, float gscale, float max_norm, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, void* stream);
 /* a6 GlobalAgg.forward (:265-285) for the module whose fc.weight is parameter `first_param`;
  * x,y [B*T,64,h,w]; wmat_out (may be NULL) receives the [B,T,T] mixing matrix. */
 int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, float* wmat_out,

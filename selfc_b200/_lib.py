@@ -32,6 +32,8 @@ SIGNATURES = {
     "selfc_d2dt_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_invblock_backward": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_train_tape_bytes": (_sz, [_i, _i, _i, _i]),
+    "selfc_adam_step": (_i, [_vp, _vp, _i, C.c_longlong, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                            C.c_float, C.c_float, _i, _vp]),
     "selfc_train_grads": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "selfc_global_agg_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "selfc_head_sampler_backward": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),

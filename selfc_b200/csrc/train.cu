@@ -1037,6 +1037,46 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
   return 0;
 }
 
+// ====================================================================================================================
+// Optimiser step on a FLAT gradient buffer (one NCCL all-reduce, one norm): clip_grad_norm_(params, max_norm) followed by
+// torch.optim.Adam (SelfC_model.py:66-68,172-176): the parameters themselves stay separate tensors (reference layout).
+// ====================================================================================================================
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += g[i] * g[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// offsets[n_tensors + 1]: element offsets of the tensors inside the flat buffers; params[t]: device pointer of tensor t
+__global__ void __launch_bounds__(256) adam_kernel(float* const* __restrict__ params, const long long* __restrict__ offsets, int n_tensors,
+                                                   const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+                                                   const float* __restrict__ sqnorm, float gscale, float max_norm, float lr, float b1,
+                                                   float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= offsets[n_tensors]) return;
+  int lo = 0, hi = n_tensors - 1;               // the tensor that holds flat element i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (offsets[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  float* p = params[lo] + (i - offsets[lo]);
+  float coef = gscale;
+  if (max_norm > 0.f) {
+    const float total = sqrtf(sqnorm[0]) * gscale;                     // norm of the (already averaged) gradient
+    coef *= fminf(1.0f, max_norm / (total + 1e-6f));                    // torch.nn.utils.clip_grad_norm_
+  }
+  float g = grad[i] * coef;
+  const float pv = *p;
+  if (wd != 0.f) g = fmaf(wd, pv, g);
+  const float mi = b1 * m[i] + (1.0f - b1) * g;
+  const float vi = b2 * v[i] + (1.0f - b2) * g * g;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  *p = pv - (lr / bc1) * (mi / denom);
+}
+
 // NCHW [N,51,h,w] -> planar quads (test boundary)
 static int nchw51_to_quads(const float* x51, float* z, const Dims& d, cudaStream_t st) {
   SELFC_TRY(launch_nchw_slice_to_dense<float>(x51, 51, 0, z, 4, 0, 0, 3, 4, d.M(), d.hw(), st));
@@ -1173,5 +1213,28 @@ int selfc_train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const
   SELFC_CHECK_ARG(tape_bytes >= tl.total && aligned16(tape), "train_grads: tape too small (%zu < %zu)", tape_bytes, tl.total);
   Dims d{B, T, H / 4, W / 4};
   return train_grads(ctx, hr, ref_l, eps, seed, offset, grads, losses, d, (char*)workspace, ws, (char*)tape, tl, (cudaStream_t)stream);
+}
+
+/* a13 optimiser step (SelfC_model.py:66-68,172-176): gradient clipping by global norm + Adam, on a flat gradient buffer.
+ * params[n_tensors]: DEVICE array of device pointers to the parameter tensors; offsets[n_tensors+1]: DEVICE array of element
+ * offsets of those tensors inside grad / m / v (flat fp32 buffers of offsets[n_tensors] elements, given as total);
+ * gscale multiplies the gradient first (1/world after a SUM all-reduce); max_norm <= 0 disables clipping; step >= 1.
+ * sqnorm_scratch: one device float. */
+int selfc_adam_step(float* const* params, const long long* offsets, int n_tensors, long long total, const float* grad, float* m,
+                    float* v, float* sqnorm_scratch, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, void* stream) {
+  SELFC_CHECK_ARG(params && offsets && grad && m && v && sqnorm_scratch && n_tensors >= 1 && total >= 1 && step >= 1, "adam_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SELFC_CUDA(cudaMemsetAsync(sqnorm_scratch, 0, sizeof(float), st));
+  if (max_norm > 0.f) {
+    sqnorm_kernel<<<296, 256, 0, st>>>(grad, total, sqnorm_scratch);
+    SELFC_LAUNCH_CHECK("sqnorm_kernel");
+  }
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  adam_kernel<<<cdiv(total, 256), 256, 0, st>>>(params, offsets, n_tensors, grad, m, v, sqnorm_scratch, gscale, max_norm, lr, beta1, beta2, eps,
+                                               weight_decay, bc1, bc2_sqrt);
+  SELFC_LAUNCH_CHECK("adam_kernel");
+  return 0;
 }
 }  // extern "C"

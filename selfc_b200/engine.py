@@ -114,6 +114,11 @@ class Engine:
         self._keep = tensors
         self._shapes = {name: tuple(t.shape) for name, t in zip(PARAM_NAMES, tensors)}
 
+    def invalidate(self) -> None:
+        """Forget the packed-weight cache key: the next sync_params re-packs (used after an in-place optimiser step, which
+        writes the parameters through raw pointers and therefore does not bump their version counters)."""
+        self._weights_key = None
+
     def sync_params(self, named_params: Sequence[Tuple[str, torch.Tensor]]) -> None:
         """Re-pack iff any parameter's storage or version changed since the last call."""
         key = tuple((p.data_ptr(), p._version) for _, p in named_params)

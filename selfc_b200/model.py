@@ -6,7 +6,8 @@ checkpoint handling (state_dict file, optional 'module.' prefix, strict load).  
   * test() runs the network ONCE per GOP; the reference's extra padded pass whose result is discarded
     (SelfC_model.py:203-243, SURVEY F7) is not reproduced;
   * no DataParallel wrapper: one process per GPU (the wrapper's `.module` attribute is provided for compatibility);
-  * training (optimize_parameters) is not implemented in this round (row a13).
+  * training: optimize_parameters (SelfC_model.py:148-183) runs forward + backward + clip + Adam through the C-ABI
+    (selfc_b200/train.py), fp32 mode; the gradient all-reduce replaces DistributedDataParallel.
 """
 from __future__ import annotations
 
@@ -43,13 +44,22 @@ class SelfCModel:
             raise RuntimeError("selfc_b200.model.SelfCModel needs a CUDA device (sm_100a); there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.is_train = bool(opt["is_train"])
-        if self.is_train:
-            raise NotImplementedError("selfc_b200 implements the inference half of SelfCModel (test/feed_data) in this round")
         net = networks.define_G(opt).to(self.device)
         self.netG = _ModuleHandle(net)
         self.load()
-        net.eval()
         self.gop = GOP
+        self.log_dict = OrderedDict()
+        if self.is_train:
+            net.train()
+            to = opt["train"]
+            from .train import Trainer
+            self.train_opt = to
+            self.trainer = Trainer(net, self.device, lr=float(to["lr_G"]), betas=(float(to["beta1"]), float(to["beta2"])),
+                                   weight_decay=float(to["weight_decay_G"] or 0.0),
+                                   max_norm=float(to["gradient_clipping"]) if to["gradient_clipping"] else None)
+            self.cur_lr = float(to["lr_G"])
+        else:
+            net.eval()
 
     # ---- checkpoint handling: base_model.py:77-107 ----------------------------------------------------------
     def load(self):
@@ -93,6 +103,43 @@ class SelfCModel:
         else:
             raise NotImplementedError(f"distortion {dist!r} is not on the rescaling path (only sr_bd / pytorch_bicubic)")
         return clip_length
+
+    # ---- optimize_parameters: SelfC_model.py:148-183 ---------------------------------------------------------
+    def optimize_parameters(self, step):
+        """zero_grad, forward (down, quantise, up), the two losses x 144*144*3, backward, gradient clipping, Adam."""
+        if not self.is_train:
+            raise RuntimeError("optimize_parameters needs is_train (a training options file)")
+        to = self.train_opt
+        for key, want in (("pixel_criterion_forw", "l2"), ("pixel_criterion_back", "l1")):
+            if (to[key] or want) != want:
+                raise NotImplementedError(f"{key}={to[key]!r}: the CUDA training step implements the SelfC-large YAML's losses (l2 / l1)")
+        if float(to["lambda_fit_forw"] or 1) != 1.0 or float(to["lambda_rec_back"] or 1) != 1.0:
+            raise NotImplementedError("lambda_fit_forw / lambda_rec_back other than 1 are not implemented")
+        t = GlobalVar.get_Temporal_LEN()
+        net = self.netG.module
+        losses = self.trainer.step(self.real_H, self.ref_L.contiguous(), t, eps=net._eps_override, seed=net.noise_seed,
+                                   offset=net.noise_offset, lr=self.cur_lr)
+        net.noise_offset += 1
+        total, l_forw, l_back = [float(v) for v in losses.cpu()]
+        self.log_dict["l_forw_fit"] = l_forw
+        self.log_dict["l_back_rec"] = l_back
+        self.log_dict["loss_c"] = 0.0
+        self.log_dict["loss"] = total
+
+    def update_learning_rate(self, cur_iter, warmup_iter=-1):
+        """base_model.py:40-58 with the MultiStepLR scheme of the training YAML."""
+        from .train import multistep_lr
+        to = self.train_opt
+        lr = multistep_lr(float(to["lr_G"]), int(cur_iter), to["lr_steps"] or [], float(to["lr_gamma"] or 1.0))
+        if warmup_iter and warmup_iter > 0 and cur_iter < warmup_iter:
+            lr = lr / warmup_iter * cur_iter
+        self.cur_lr = lr
+
+    def get_current_learning_rate(self):
+        return self.cur_lr
+
+    def get_current_log(self):
+        return self.log_dict
 
     # ---- test: SelfC_model.py:185-250 -----------------------------------------------------------------------
     def test(self):

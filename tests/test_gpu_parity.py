@@ -513,3 +513,49 @@ def test_train_step_gradients_vs_reference_fixture_and_oracle(dev, golden_dir):
         # largest gradient (the gradient norms above are held to 0.5 % against the reference's own numbers)
         tol = 5e-3 * float(ref.abs().max()) + 1e-5 * gmax
         torch.testing.assert_close(grads[n].cpu(), ref, rtol=0, atol=tol, msg=lambda m, n=n: f"{n}: {m}")
+
+
+def _make_net(dev, sd):
+    from selfc_b200 import networks, options
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    opt = options.dict_to_nonedict(options.parse(os.path.join(here, "selfc_b200", "configs", "selfc_large_synthetic.yml"), is_train=False))
+    net = networks.define_G(opt)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev)
+
+
+def test_optimizer_step_matches_torch_adam_with_clipping(dev, golden_dir):
+    """clip_grad_norm_(10) + Adam(1e-4, wd 1e-14) through selfc_adam_step on the flat gradient against torch.optim.Adam on the
+    oracle's autograd gradients: every parameter after one step, and after a second step on the updated weights."""
+    from selfc_b200.train import Trainer
+    from selfc_b200.global_var import GlobalVar
+    g = np.load(os.path.join(golden_dir, "train_t3.npz"))
+    b, t, hh, ww, wseed, xseed = [int(v) for v in g["meta"]]
+    sd = so.make_state_dict(wseed)
+    x = so.make_frames(b, t, hh, ww, xseed)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, int(g["eps_seed"]))
+    ref_l = _t(g["ref_l"])
+    GlobalVar.set_Temporal_LEN(t)
+    net = _make_net(dev, sd)
+    tr = Trainer(net, dev, lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-14, max_norm=10.0)
+    # CPU reference: the same two steps with torch
+    ref_p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(ref_p.values()), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-14)
+    for it in range(2):
+        losses = tr.step(x.to(dev), ref_l.to(dev), t, eps=eps.to(dev))
+        opt.zero_grad()
+        loss, _, _ = so.train_losses(ref_p, x, ref_l, eps, t)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(ref_p.values()), 10.0)
+        opt.step()
+        assert abs(losses[0].item() - loss.item()) <= 2e-4 * abs(loss.item())
+        own = dict(net.named_parameters())
+        n_bad = n_all = 0
+        for k, v in ref_p.items():
+            # Adam's first steps move every weight by ~lr * sign(g): compare the UPDATE to 2 % of lr; where the gradient is at
+            # fp32-noise level its sign (hence an update of +-lr) is arbitrary on both sides -- allow 0.2 % such elements over the whole model
+            diff = (own[k].detach().cpu() - v.detach()).abs()
+            assert diff.max().item() <= (it + 1) * 2.1e-4, f"{k} step {it}: max |diff| {diff.max().item():.3e}"
+            n_bad += int((diff > (it + 1) * 2e-6).sum().item())
+            n_all += diff.numel()
+        assert n_bad <= 2e-3 * n_all, f"step {it}: {n_bad} of {n_all} elements differ by more than 2 % of lr"
