@@ -22,6 +22,22 @@ def multistep_lr(base_lr: float, step: int, milestones: Sequence[int], gamma: fl
     return base_lr * (gamma ** sum(1 for m in (milestones or []) if step >= m))
 
 
+def all_reduce_sum(flat: torch.Tensor) -> float:
+    """SUM all-reduce of a flat gradient buffer over the default process group (NCCL on the GPU box, gloo in the CPU tests);
+    returns the scale (1/world) that turns the sum into the data-parallel mean.  No-op without a process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
+def shard_batch(n_clips: int, world: int, rank: int) -> range:
+    """Per-rank slice of a global batch of clips (data/__init__.py:13-14: batch_size // world per rank)."""
+    per = n_clips // world
+    return range(rank * per, (rank + 1) * per)
+
+
 class Trainer:
     """Flat gradient / Adam-moment buffers over the network's parameters (which stay separate tensors in the reference
     layout, so `state_dict()` is unchanged) and the step itself."""
@@ -63,11 +79,7 @@ class Trainer:
 
     def all_reduce(self) -> float:
         """SUM all-reduce of the flat gradient over the data-parallel group; returns the 1/world scale for the optimiser."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
-            return 1.0 / dist.get_world_size()
-        return 1.0
+        return all_reduce_sum(self.flat_grad)
 
     def apply(self, gscale: float = 1.0, lr: Optional[float] = None):
         """clip_grad_norm_(max_norm) + Adam step, in place on the parameters."""

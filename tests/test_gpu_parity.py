@@ -559,3 +559,38 @@ def test_optimizer_step_matches_torch_adam_with_clipping(dev, golden_dir):
             n_bad += int((diff > (it + 1) * 2e-6).sum().item())
             n_all += diff.numel()
         assert n_bad <= 2e-3 * n_all, f"step {it}: {n_bad} of {n_all} elements differ by more than 2 % of lr"
+
+
+def test_model_optimize_parameters_matches_oracle_step(dev):
+    """SelfCModel (training options) -> feed_data -> optimize_parameters: the logged losses are the oracle's, the weights
+    move as torch.optim.Adam would move them, update_learning_rate follows the MultiStepLR milestones."""
+    from selfc_b200 import model as smodel, options
+    from selfc_b200.global_var import GlobalVar
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    opt = options.dict_to_nonedict(options.parse(os.path.join(here, "selfc_b200", "configs", "selfc_large_train_synthetic.yml"),
+                                                 is_train=True))
+    torch.manual_seed(10)
+    m = smodel.create_model(opt)
+    net = m.netG.module
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    b, t, hh, ww = 1, 3, 32, 48
+    GlobalVar.set_Temporal_LEN(t)
+    x = so.make_frames(b, t, hh, ww, 77)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 3)
+    net.inject_eps(eps.to(dev))
+    m.feed_data({"GT": x.reshape(b, t, 3, hh, ww).transpose(1, 2)})
+    m.optimize_parameters(1)
+    ref_p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, l_forw, l_back = so.train_losses(ref_p, x, so.gaussian_downsample(x), eps, t)
+    log = m.get_current_log()
+    assert abs(log["loss"] - loss.item()) <= 2e-4 * abs(loss.item())
+    assert abs(log["l_forw_fit"] - l_forw.item()) <= 1e-5 and abs(log["l_back_rec"] - l_back.item()) <= 1e-5
+    moved = max(float((p.detach().cpu() - sd[k]).abs().max()) for k, p in net.named_parameters())
+    assert 0.5e-4 <= moved <= 1.05e-4                           # Adam's first step: |update| <= lr
+    # the next forward uses the updated weights (packed images were invalidated)
+    out, _ = net(x=x.to(dev))
+    with torch.no_grad():
+        ref_out = so.net_down({k: p.detach().cpu() for k, p in net.named_parameters()}, x, t)
+    torch.testing.assert_close(out.cpu(), ref_out, rtol=0, atol=2e-4)
+    m.update_learning_rate(100000)
+    assert m.get_current_learning_rate() == 5e-5

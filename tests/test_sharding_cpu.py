@@ -54,3 +54,43 @@ def test_metric_gather_world2_gloo():
     for rank, allm, units in res:
         assert allm == expect                                   # every rank sees all rows, in unit order
     assert sorted(u for _, _, units in res for u in units) == list(range(15))
+
+
+# ---- training step (row a13): the gradient all-reduce and the per-rank batch split, world_size 2, gloo ------------------------
+def _grad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from selfc_b200 import train
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)          # this rank's flat gradient
+    scale = train.all_reduce_sum(flat)
+    q.put((rank, scale, (flat * scale).tolist()[:5], list(train.shard_batch(8, world, rank))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, scale, head, clips in res:
+        assert scale == 0.5
+        assert head == [0.0, 1.5, 3.0, 4.5, 6.0]                        # mean of g and 2g
+        assert clips == list(range(4 * rank, 4 * rank + 4))
+
+
+def test_multistep_lr_and_single_process_allreduce():
+    from selfc_b200 import train
+    assert train.multistep_lr(1e-4, 0, [100000, 200000, 300000], 0.5) == 1e-4
+    assert train.multistep_lr(1e-4, 100000, [100000, 200000, 300000], 0.5) == 5e-5
+    assert train.multistep_lr(1e-4, 350000, [100000, 200000, 300000], 0.5) == 1.25e-5
+    g = torch.ones(4)
+    assert train.all_reduce_sum(g) == 1.0 and torch.equal(g, torch.ones(4))
