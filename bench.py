@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--width", type=int, default=HR_W)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="rescale", choices=["rescale", "train"],
+                    help="rescale: the headline metric (default); train: BASELINE.json configs[3], one training step on synthetic "
+                         "Vimeo90K-shape septuplets per rank with the flat-gradient NCCL all-reduce")
+    ap.add_argument("--septuplets", type=int, default=1, help="--workload train: septuplets (7x256x448) per rank per step")
     return ap.parse_args()
 
 
@@ -309,8 +313,78 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE.json configs[3]: SelfC-large training step (forward, backward, gradient all-reduce, clip, Adam) on synthetic
+    Vimeo90K-shape septuplets, fp32 mode (fp32-FMA kernels; the tensor-core backward is the next round's work)."""
+    import torch.distributed as dist
+    from selfc_b200 import networks, options, engine as _eng
+    from selfc_b200.global_var import GlobalVar
+    from selfc_b200.train import Trainer
+    from oracle import selfc_oracle as so
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    t, hh, ww, b = GOP, 256, 448, max(1, args.septuplets)
+    opt = options.dict_to_nonedict(options.parse(os.path.join(ROOT, "selfc_b200", "configs", "selfc_large_train_synthetic.yml"), is_train=True))
+    net = networks.define_G(opt)
+    net.load_state_dict(so.make_state_dict(0), strict=True)
+    net = net.to(dev)
+    GlobalVar.set_Temporal_LEN(t)
+    tr = Trainer(net, dev, lr=1e-4, weight_decay=1e-14, max_norm=10.0)
+    x = make_group(b * t, hh, ww, 1234 + rank, dev)
+    ref_l = _eng.gaussian_downsample(x)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    losses = None
+    for i in range(args.warmup):
+        losses = tr.step(x, ref_l, t, seed=42, offset=i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        losses = tr.step(x, ref_l, t, seed=42, offset=args.warmup + i)
+    ev1.record()
+    barrier()
+    launches = _eng.launch_count() - n0
+    clocks = sampler.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    if rank == 0:
+        flop = 3.0 * FLOP_PER_LR_PX * (hh // 4) * (ww // 4) * t * b * world      # SURVEY 8d: training ~ 3x forward
+        line = {"metric": "training step septuplets/s (7x256x448 HR, fwd+bwd+allreduce+Adam)", "value": world * b * args.steps / (ms_total / 1e3),
+                "unit": "septuplets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"SelfC-large training step, {b} synthetic Vimeo90K-shape septuplet(s) per GPU per step, fp32 mode "
+                                       "(fp32-FMA kernels, recompute-based backward), one NCCL all-reduce of the flat 3.37M-element gradient",
+                           "septuplets_per_step_per_gpu": b, "weights": "seeded random, reference state_dict layout"},
+                "clocks": clocks, "gpu_launches": int(launches), "loss": float(losses[0].item()),
+                "algorithmic_tflops": flop * args.steps / (ms_total / 1e3) / 1e12}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if args.workload == "train":
+        run_train(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
