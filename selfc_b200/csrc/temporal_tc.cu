@@ -167,7 +167,7 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 
-template <int TAPS>
+template <int TAPS, bool GMM>
 __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                   const __grid_constant__ CUtensorMap tmap2, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
         tc_fence_after();
         const int ncols = p.epi == EPI_COUPLE_Y1 ? 16 : (p.epi == EPI_STORE ? ((p.cout + 15) & ~15) : kHF);
         const bool live = valid && (long long)m < p.m_limit;
-        if (p.epi == EPI_GMM) {
+        if (GMM) {                                    // its own instantiation: 48 softmax weights live in registers
           // ---- fused GMM head + sampler (SelfC_GMM_arch_inv.py:383-394): columns [0,48) logits, [48,96) log-scales,
           // [96,144) means of component k; softmax over the 48 hf channels
           float pi[kHF];
@@ -435,28 +435,28 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
         }
         for (int n0 = 0; n0 < ncols; n0 += 16) {
           float4 x2q[4], sq[4];
-          if (live && p.epi == EPI_COUPLE_HG) {
+          if (TAPS == 3 && live && p.epi == EPI_COUPLE_HG) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x2q[j] = lds4(ebuf + (uint32_t)((n0 / 4 + j) * MT) * 16u);
-          } else if (live && p.epi == EPI_COUPLE_Y2) {
+          } else if (TAPS == 3 && live && p.epi == EPI_COUPLE_Y2) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               x2q[j] = lds4(ebuf + (uint32_t)((n0 / 4 + j) * MT) * 16u);
               sq[j] = lds4(ebuf + (uint32_t)((kSQuads + n0 / 4 + j) * MT) * 16u);
             }
-          } else if (live && p.epi == EPI_COUPLE_Y1) {
+          } else if (TAPS == 3 && live && p.epi == EPI_COUPLE_Y1) {
             x2q[0] = lds4(ebuf);
           }
           uint32_t r[16], rg[16];
           tmem_ld16(acol + (uint32_t)n0, r);
-          if (p.epi == EPI_COUPLE_HG) tmem_ld16(acol + (uint32_t)(kHF + n0), rg);     // warp-uniform: G's columns of the accumulator
+          if (TAPS == 3 && p.epi == EPI_COUPLE_HG) tmem_ld16(acol + (uint32_t)(kHF + n0), rg);     // warp-uniform: G's columns of the accumulator
           tmem_ld_wait();
           if (!live) continue;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
 
-          switch (p.epi) {
+          switch (TAPS == 1 ? EPI_STORE : p.epi) {     // the pointwise instantiation only stores (the coupling epilogues belong to conv5)
             case EPI_STORE: {
               if (p.act) {
 #pragma unroll
@@ -748,14 +748,17 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !smem_set[dev]) {
-    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
   }
   const int nsm = tc::num_sms();
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
-  if (w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
-  else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
+  SELFC_CHECK_ARG(a.epi != EPI_GMM || w.taps == 1, "temporal_tc: the GMM epilogue belongs to a pointwise conv");
+  if (w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3, false>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
+  else if (a.epi == EPI_GMM) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1, true>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
+  else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1, false>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
   SELFC_LAUNCH_CHECK("temporal_tc_kernel");
   return 0;
 }
