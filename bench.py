@@ -171,7 +171,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from selfc_b200.engine import Engine, launch_count
-    from oracle import selfc_oracle as so   # only for the seeded reference-layout weights and the cpu_baseline leg
+    from selfc_b200.synthetic import seeded_state_dict, synthetic_net
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,7 +185,7 @@ def run_ours(args):
     hh, ww, frames = args.height, args.width, args.frames
     h, w = hh // 4, ww // 4
     eng = Engine(dev, args.mode)
-    eng.load_state(so.make_state_dict(0))
+    eng.load_state(seeded_state_dict(synthetic_net()[0], 0))
     group = make_group(frames, hh, ww, 1234 + rank, dev)
     gops = gop_slices(frames)
     gpl = max(1, args.gops_per_launch)
@@ -317,10 +317,10 @@ def run_train(args):
     """BASELINE.json configs[3]: SelfC-large training step (forward, backward, gradient all-reduce, clip, Adam) on synthetic
     Vimeo90K-shape septuplets, fp32 mode (fp32-FMA kernels; the tensor-core backward is the next round's work)."""
     import torch.distributed as dist
-    from selfc_b200 import networks, options, engine as _eng
+    from selfc_b200 import engine as _eng
     from selfc_b200.global_var import GlobalVar
+    from selfc_b200.synthetic import seeded_state_dict, synthetic_net
     from selfc_b200.train import Trainer
-    from oracle import selfc_oracle as so
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -331,9 +331,8 @@ def run_train(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     t, hh, ww, b = GOP, 256, 448, max(1, args.septuplets)
-    opt = options.dict_to_nonedict(options.parse(os.path.join(ROOT, "selfc_b200", "configs", "selfc_large_train_synthetic.yml"), is_train=True))
-    net = networks.define_G(opt)
-    net.load_state_dict(so.make_state_dict(0), strict=True)
+    net, _ = synthetic_net(train=True)
+    net.load_state_dict(seeded_state_dict(net, 0), strict=True)
     net = net.to(dev)
     GlobalVar.set_Temporal_LEN(t)
     tr = Trainer(net, dev, lr=1e-4, weight_decay=1e-14, max_norm=10.0)

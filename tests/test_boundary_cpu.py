@@ -95,3 +95,15 @@ def test_same_seed_same_initial_weights_as_reference():
     a, b = rnet.state_dict(), mine.state_dict()
     assert list(a.keys()) == list(b.keys())
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_packaged_seeded_weights_equal_the_oracle_recipe():
+    """bench.py's product arm draws its weights from selfc_b200.synthetic (no oracle import on that path); the recipe is the
+    oracle's, tensor for tensor."""
+    import torch
+    from oracle import selfc_oracle as so
+    from selfc_b200.synthetic import seeded_state_dict, synthetic_net
+    net, _ = synthetic_net()
+    a, b = seeded_state_dict(net, 0), so.make_state_dict(0)
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
