@@ -262,6 +262,26 @@ def run_ours(args):
         e2e = {"value": world * frames * e_steps / float(dt.item()), "unit": "frames/s",
                "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_lr.numel() + host_hr.numel() * 4),
                "steps": e_steps, "timing": "host wall clock around Engine.rescale_host (pinned H2D + rescale + D2H, copies overlapped on side streams), max over ranks"}
+        del host_in, host_hr
+        # the same through the 8-bit interface: decoded uint8 frames in, uint8 LR + HR frames out
+        img_dev = eng.frames_to_u8(group)
+        host_img = torch.empty(img_dev.shape, dtype=torch.uint8).pin_memory()
+        host_img.copy_(img_dev)
+        del img_dev
+        host_lr8 = torch.empty((frames, h, w, 3), dtype=torch.uint8).pin_memory()
+        host_hr8 = torch.empty((frames, hh, ww, 3), dtype=torch.uint8).pin_memory()
+        eng.rescale_host_u8(host_img, host_lr8, host_hr8, GOP, seed=42, offset0=0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            eng.rescale_host_u8(host_img, host_lr8, host_hr8, GOP, seed=42, offset0=(1 + i) * len(gops))
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e["u8_frames"] = {"value": world * frames * e_steps / float(dt.item()), "unit": "frames/s",
+                            "h2d_bytes_per_step": int(host_img.numel()), "d2h_bytes_per_step": int(host_lr8.numel() + host_hr8.numel()),
+                            "what": "Engine.rescale_host_u8: cv2-layout uint8 frames in and out, conversions fused into the FrequencyAnalyzer kernels"}
 
     # ---- roofline of the dominant kernel class (instrumented step, outside the timed regions) ---------------------
     roofline = None

@@ -68,6 +68,26 @@ int selfc_up(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, u
              float* hr, float* hf, int B, int T, int H, int W,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- 8-bit frames at the boundary --------------------------------------------------------
+ * Images are what cv2.imread / cv2.imwrite hold: [n][H][W][3] bytes, channel order B,G,R.  Ingest replaces
+ * read_img1's astype(float32)/255 (data/util.py:103-115) + the dataset's BGR->RGB, HWC->CHW
+ * (data/LQGTVID_dataset.py:150-154); egress replaces tensor2img's clamp(0,1), *255, round-half-even, RGB->BGR,
+ * CHW->HWC (utils/util.py:104-133) before save_img (:181-182).  Both are bit-exact with those CPU conversions and,
+ * on the HR side, fused into the FrequencyAnalyzer kernels (no fp32 frame ever exists in HBM). */
+/* hr_img [B*T][H][W][3] -> lr_img [B*T][h][w][3] (may be NULL), lr_q [B*T,3,h,w] fp32 on the 1/255 grid (may be NULL) */
+int selfc_down_u8(selfc_ctx* ctx, const uint8_t* hr_img, uint8_t* lr_img, float* lr_q, int B, int T, int H, int W,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* lr_img [B*T][h][w][3] (the stored LR video) -> hr_img [B*T][H][W][3]; eps/seed/offset as selfc_up */
+int selfc_up_u8(selfc_ctx* ctx, const uint8_t* lr_img, const float* eps, uint64_t seed, uint64_t offset, uint8_t* hr_img,
+                int B, int T, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+/* both halves in one call (models/SelfC_model.py:213-233 on 8-bit frames); lr_img may be NULL */
+int selfc_rescale_u8(selfc_ctx* ctx, const uint8_t* hr_img, const float* eps, uint64_t seed, uint64_t offset,
+                     uint8_t* lr_img, uint8_t* hr_out_img, int B, int T, int H, int W,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* stand-alone conversions, any H and W: img [N][H][W][3] BGR bytes <-> x [N,3,H,W] RGB fp32 */
+int selfc_frames_from_u8(const uint8_t* img, float* x, int N, int H, int W, void* stream);
+int selfc_frames_to_u8(const float* x, uint8_t* img, int N, int H, int W, void* stream);
+
 /* ---- components (each is one row of SURVEY 8a; used by the parity tests) ---------------------------- */
 /* a1 FrequencyAnalyzer.forward(rev=False) :62-78 -> [N,51,h,w]; a10 rev=True :79-82 -> [N,3,H,W] */
 int selfc_fa_fwd(const float* x, float* out51, int N, int H, int W, void* stream);

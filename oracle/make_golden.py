@@ -117,6 +117,35 @@ def case_metrics(ref):
                         ssim=np.array(ssims), psnr=np.array(psnrs), lr_ref=lr_ref.numpy())
 
 
+def case_u8(ref):
+    """8-bit ingest/egress: the reference's own read_img1 on a PNG written by cv2, the dataset's two conversion lines
+    (LQGTVID_dataset.py:150-154, applied here verbatim because the class needs a directory tree), and tensor2img."""
+    import tempfile
+    import cv2
+    import data.util as dutil                      # reference modules
+    import utils.util as uutil
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, size=(2, 12, 16, 3), dtype=np.uint8)
+    img[0, 0, :, 0] = np.arange(16) * 17            # every 17th code incl. 0 and 255
+    xs = []
+    with tempfile.TemporaryDirectory() as td:
+        for i in range(2):
+            path = os.path.join(td, f"{i}.png")
+            cv2.imwrite(path, img[i])
+            im = dutil.read_img1(None, path)
+            if im.shape[2] == 3:
+                im = im[:, :, [2, 1, 0]]
+            xs.append(torch.from_numpy(np.ascontiguousarray(np.transpose(im, (2, 0, 1)))).float())
+    from_ref = torch.stack(xs)
+    g = torch.Generator().manual_seed(10)
+    y = torch.rand(3, 3, 8, 12, generator=g) * 1.3 - 0.15          # values outside [0,1] on both sides
+    ties = (torch.arange(0, 96, dtype=torch.float32) * 2.5 + 0.5) / 255.0   # k+0.5 ties, even and odd k
+    y[0, 0].view(-1)[:96] = ties
+    y[1, 1].view(-1)[:96] = torch.arange(0, 96, dtype=torch.float32) / 255.0 * 2.6
+    to_ref = np.stack([uutil.tensor2img(y[i]) for i in range(3)])
+    np.savez_compressed(os.path.join(OUT, "u8.npz"), img=img, from_ref=from_ref.numpy(), y=y.numpy(), to_ref=to_ref)
+
+
 def case_train(ref, name, b, t, hh, ww, wseed, xseed):
     """One training step's losses and gradients from the reference's own modules (SelfC_model.py:148-170 restated with
     netG, Quantization, ReconstructionLoss and Guassian_downsample imported from the reference; SelfCModel itself needs
@@ -159,6 +188,7 @@ def main():
     ref = ref_shim.load_reference()
     case_fa(ref)
     case_metrics(ref)
+    case_u8(ref)
     case_net(ref, "net_t3", b=2, t=3, hh=32, ww=48, wseed=0, xseed=11)
     case_net(ref, "net_t7", b=1, t=7, hh=32, ww=40, wseed=1, xseed=12)
     # partial 8x16 output tiles, non-integral 32x32 pooling windows (h=10, w=18), larger weights

@@ -296,6 +296,31 @@ def net_up(sd, lr: torch.Tensor, eps: torch.Tensor, t: int, return_stages: bool 
     return hr, hf
 
 
+def frames_from_u8(img: np.ndarray) -> torch.Tensor:
+    """Decoded 8-bit frames ``[n,H,W,3]`` (cv2 order B,G,R) -> ``[n,3,H,W]`` RGB fp32 in [0,1].
+
+    read_img1's ``astype(np.float32) / 255.`` (data/util.py:103-115) followed by the dataset's ``[:, :, [2, 1, 0]]`` and
+    ``np.transpose(..., (2, 0, 1))`` (data/LQGTVID_dataset.py:150-154), per frame."""
+    x = img.astype(np.float32) / 255.
+    x = x[..., [2, 1, 0]]
+    return torch.from_numpy(np.ascontiguousarray(np.transpose(x, (0, 3, 1, 2)))).float()
+
+
+def frames_to_u8(x: torch.Tensor) -> np.ndarray:
+    """``[n,3,H,W]`` RGB fp32 -> 8-bit frames ``[n,H,W,3]`` (B,G,R): tensor2img per frame (utils/util.py:104-133):
+    clamp to [0,1], (t-0)/(1-0), channel flip, CHW->HWC, ``(img * 255.0).round()`` (numpy: half to even), astype(uint8)."""
+    t = x.float().clamp(0, 1)
+    t = (t - 0) / (1 - 0)
+    a = np.transpose(t.numpy()[:, [2, 1, 0]], (0, 2, 3, 1))
+    return (a * 255.0).round().astype(np.uint8)
+
+
+def rescale_u8(sd, img: np.ndarray, eps: torch.Tensor, t: int):
+    """rescale() on 8-bit frames: (LR frames, reconstructed HR frames), both uint8 [n,·,·,3] BGR."""
+    lr, hr = rescale(sd, frames_from_u8(img), eps, t)
+    return frames_to_u8(lr), frames_to_u8(hr)
+
+
 def rescale(sd, x: torch.Tensor, eps: torch.Tensor, t: int):
     """down -> 8-bit quantise -> up: one 'step' of the benchmark (models/SelfC_model.py:213-233)."""
     z = net_down(sd, x, t)

@@ -24,6 +24,11 @@ SIGNATURES = {
     "selfc_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "selfc_down": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_up": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "selfc_down_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "selfc_up_u8": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "selfc_rescale_u8": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "selfc_frames_from_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "selfc_frames_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa_rev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_quantize": (_i, [_vp, _vp, _vp, _sz, _vp]),

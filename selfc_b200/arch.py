@@ -167,6 +167,21 @@ class SelfCInvNet(nn.Module):
         eng.sync_params(self._named)
         return eng
 
+    @property
+    def engine(self) -> "_engine.Engine":
+        """The C-ABI engine holding this module's current weights on its device (8-bit frame calls)."""
+        return self._engine_for(next(self.parameters()).device)
+
+    def rescale_u8(self, frames_bgr: torch.Tensor):
+        """uint8 [B*T,H,W,3] (cv2 layout) -> (LR frames, reconstructed HR frames), uint8, the same layout: what the test loop's
+        read_img1 -> forward -> Quantization -> forward(rev=True) -> tensor2img chain produces (models/SelfC_model.py:213-233)."""
+        t = GlobalVar.get_Temporal_LEN()
+        if t is None:
+            raise RuntimeError("GlobalVar.set_Temporal_LEN(T) must be called before rescale_u8")
+        out = self.engine.rescale_u8(frames_bgr, t, seed=self.noise_seed, offset=self.noise_offset, eps=self._eps_override)
+        self.noise_offset += 1
+        return out
+
     def _apply(self, fn, *a, **k):   # .to()/.cuda()/.half(): parameter storage changes -> rebuild the name list
         self._named = None
         return super()._apply(fn, *a, **k)

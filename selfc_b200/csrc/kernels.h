@@ -11,6 +11,12 @@ int launch_fa_fwd_nchw(const float* x, float* out51, int N, int h, int w, cudaSt
 template <typename T>
 int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, long long fslabM, int N, int h, int w, cudaStream_t st);
 int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w, cudaStream_t st);
+// 8-bit frames in cv2 layout [N][H][W][3] (B,G,R): fused into the FrequencyAnalyzer kernels (HR side) and stand-alone
+template <typename T>
+int launch_fa_fwd_z_u8(const uint8_t* x, float* z, T* fbuf, int fpitch, long long fslabM, int N, int h, int w, cudaStream_t st);
+int launch_fa_rev_u8(const float* z, uint8_t* y, int N, int h, int w, cudaStream_t st);
+int launch_frames_from_u8(const uint8_t* img, float* x, long long N, long long HW, cudaStream_t st);
+int launch_frames_to_u8(const float* x, uint8_t* img, long long N, long long HW, cudaStream_t st);
 int launch_quantize(const float* x, uint8_t* q8, float* qf, size_t n, cudaStream_t st);
 int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q, long long M, long long hw, cudaStream_t st);
 int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st);

@@ -17,8 +17,11 @@ namespace selfc {
 // OUT_NCHW: write [N,51,h,w] (standalone component); else write z [M][52] (+ optional T copy of the 48 HF
 // channels into the F dense buffer, channel offset 0).
 // ------------------------------------------------------------------------------------------------------
-template <bool OUT_NCHW, typename T>
-__global__ void __launch_bounds__(256) fa_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+// IN_U8: x is a decoded 8-bit frame stack [N][H][W][3] in cv2 order (B,G,R); value = float(byte)/255.0f, the
+// conversion read_img1 + the dataset's BGR->RGB / HWC->CHW make on the CPU (data/util.py:103-115,
+// data/LQGTVID_dataset.py:150-154), done in the load instead.
+template <bool OUT_NCHW, typename T, bool IN_U8 = false>
+__global__ void __launch_bounds__(256) fa_fwd_kernel(const void* __restrict__ xin, float* __restrict__ out,
                                                      T* __restrict__ fbuf, int fpitch, long long fslabM, int N, int h, int w) {
   const long long M = (long long)N * h * w;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,13 +31,29 @@ __global__ void __launch_bounds__(256) fa_fwd_kernel(const float* __restrict__ x
   const int n = (int)(m / ((long long)w * h));
   const int W = 4 * w, H = 4 * h;
   float v[3][16];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float* src = x + (((long long)n * 3 + c) * H + 4 * i) * W + 4 * j;
+  if (IN_U8) {
+    // 4 rows x 12 bytes (4 pixels x BGR); 12-byte aligned because W % 4 == 0
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(xin) + (((long long)n * H + 4 * i) * W + 4 * j) * 3;
 #pragma unroll
     for (int sy = 0; sy < 4; ++sy) {
-      float4 r = __ldg(reinterpret_cast<const float4*>(src + (long long)sy * W));
-      v[c][sy * 4 + 0] = r.x; v[c][sy * 4 + 1] = r.y; v[c][sy * 4 + 2] = r.z; v[c][sy * 4 + 3] = r.w;
+      const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (long long)sy * W * 3);
+      uint32_t wds[3] = {__ldg(r), __ldg(r + 1), __ldg(r + 2)};
+#pragma unroll
+      for (int b = 0; b < 12; ++b) {
+        const uint32_t byte = (wds[b >> 2] >> (8 * (b & 3))) & 0xffu;
+        v[2 - b % 3][sy * 4 + b / 3] = (float)byte / 255.0f;
+      }
+    }
+  } else {
+    const float* x = reinterpret_cast<const float*>(xin);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* src = x + (((long long)n * 3 + c) * H + 4 * i) * W + 4 * j;
+#pragma unroll
+      for (int sy = 0; sy < 4; ++sy) {
+        float4 r = __ldg(reinterpret_cast<const float4*>(src + (long long)sy * W));
+        v[c][sy * 4 + 0] = r.x; v[c][sy * 4 + 1] = r.y; v[c][sy * 4 + 2] = r.z; v[c][sy * 4 + 3] = r.w;
+      }
     }
   }
   float lf[3];
@@ -76,8 +95,15 @@ __global__ void __launch_bounds__(256) fa_fwd_kernel(const float* __restrict__ x
 // ------------------------------------------------------------------------------------------------------
 // FrequencyAnalyzer reverse: y[n,c,4i+sy,4j+sx] = lf[c] + hf[c*16+sy*4+sx]  (nn.PixelShuffle order).
 // ------------------------------------------------------------------------------------------------------
-template <bool IN_NCHW>
-__global__ void __launch_bounds__(256) fa_rev_kernel(const float* __restrict__ z, float* __restrict__ y, int N, int h, int w) {
+// OUT_U8: write the frames as 8-bit [N][H][W][3] in cv2 order (B,G,R): round-half-even of clamp(v,0,1)*255, the
+// conversion tensor2img makes on the CPU before save_img (utils/util.py:104-133,181-182).
+__device__ __forceinline__ uint32_t img_code(float v) {
+  v = fminf(fmaxf(v, 0.f), 1.f);
+  return (uint32_t)rintf(v * 255.0f);
+}
+
+template <bool IN_NCHW, bool OUT_U8 = false>
+__global__ void __launch_bounds__(256) fa_rev_kernel(const float* __restrict__ z, void* __restrict__ yout, int N, int h, int w) {
   const long long M = (long long)N * h * w;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
@@ -102,6 +128,22 @@ __global__ void __launch_bounds__(256) fa_rev_kernel(const float* __restrict__ z
       hf[k] = r.x; hf[k + 1] = r.y; hf[k + 2] = r.z; hf[k + 3] = r.w;
     }
   }
+  if (OUT_U8) {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(yout) + (((long long)n * H + 4 * i) * W + 4 * j) * 3;
+#pragma unroll
+    for (int sy = 0; sy < 4; ++sy) {
+      uint32_t wds[3] = {0u, 0u, 0u};
+#pragma unroll
+      for (int b = 0; b < 12; ++b) {
+        const int c = 2 - b % 3, sx = b / 3;
+        wds[b >> 2] |= img_code(lf[c] + hf[c * 16 + sy * 4 + sx]) << (8 * (b & 3));
+      }
+      uint32_t* r = reinterpret_cast<uint32_t*>(dst + (long long)sy * W * 3);
+      r[0] = wds[0]; r[1] = wds[1]; r[2] = wds[2];
+    }
+    return;
+  }
+  float* y = reinterpret_cast<float*>(yout);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float* dst = y + (((long long)n * 3 + c) * H + 4 * i) * W + 4 * j;
@@ -112,6 +154,33 @@ __global__ void __launch_bounds__(256) fa_rev_kernel(const float* __restrict__ z
       *reinterpret_cast<float4*>(dst + (long long)sy * W) = r;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Stand-alone 8-bit frame conversions (any H, W): [N][H][W][3] BGR bytes <-> [N][3][H][W] RGB fp32.  One thread per
+// pixel; the LR side of the path uses them (LR is 1/16 of the HR pixels), the HR side is fused into the
+// FrequencyAnalyzer kernels above.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frames_from_u8_kernel(const uint8_t* __restrict__ img, float* __restrict__ x, long long N, long long HW) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N * HW) return;
+  const long long n = p / HW, q = p - n * HW;
+  const uint8_t* s = img + p * 3;
+  float* d = x + n * 3 * HW + q;
+  d[0] = (float)s[2] / 255.0f;
+  d[HW] = (float)s[1] / 255.0f;
+  d[2 * HW] = (float)s[0] / 255.0f;
+}
+
+__global__ void __launch_bounds__(256) frames_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, long long N, long long HW) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N * HW) return;
+  const long long n = p / HW, q = p - n * HW;
+  const float* s = x + n * 3 * HW + q;
+  uint8_t* d = img + p * 3;
+  d[0] = (uint8_t)img_code(s[2 * HW]);
+  d[1] = (uint8_t)img_code(s[HW]);
+  d[2] = (uint8_t)img_code(s[0]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -279,6 +348,36 @@ int launch_fa_fwd_z(const float* x, float* z, T* fbuf, int fpitch, long long fsl
   long long M = (long long)N * h * w;
   fa_fwd_kernel<false, T><<<cdiv(M, 256), 256, 0, st>>>(x, z, fbuf, fpitch, fslabM, N, h, w);
   SELFC_LAUNCH_CHECK("fa_fwd_kernel<z>");
+  return 0;
+}
+template <typename T>
+int launch_fa_fwd_z_u8(const uint8_t* x, float* z, T* fbuf, int fpitch, long long fslabM, int N, int h, int w, cudaStream_t st) {
+  long long M = (long long)N * h * w;
+  fa_fwd_kernel<false, T, true><<<cdiv(M, 256), 256, 0, st>>>(x, z, fbuf, fpitch, fslabM, N, h, w);
+  SELFC_LAUNCH_CHECK("fa_fwd_kernel<z,u8>");
+  return 0;
+}
+template int launch_fa_fwd_z_u8<float>(const uint8_t*, float*, float*, int, long long, int, int, int, cudaStream_t);
+template int launch_fa_fwd_z_u8<__nv_bfloat16>(const uint8_t*, float*, __nv_bfloat16*, int, long long, int, int, int, cudaStream_t);
+
+int launch_fa_rev_u8(const float* z, uint8_t* y, int N, int h, int w, cudaStream_t st) {
+  long long M = (long long)N * h * w;
+  fa_rev_kernel<false, true><<<cdiv(M, 256), 256, 0, st>>>(z, y, N, h, w);
+  SELFC_LAUNCH_CHECK("fa_rev_kernel<u8>");
+  return 0;
+}
+
+int launch_frames_from_u8(const uint8_t* img, float* x, long long N, long long HW, cudaStream_t st) {
+  if (N * HW == 0) return 0;
+  frames_from_u8_kernel<<<cdiv(N * HW, 256), 256, 0, st>>>(img, x, N, HW);
+  SELFC_LAUNCH_CHECK("frames_from_u8_kernel");
+  return 0;
+}
+
+int launch_frames_to_u8(const float* x, uint8_t* img, long long N, long long HW, cudaStream_t st) {
+  if (N * HW == 0) return 0;
+  frames_to_u8_kernel<<<cdiv(N * HW, 256), 256, 0, st>>>(x, img, N, HW);
+  SELFC_LAUNCH_CHECK("frames_to_u8_kernel");
   return 0;
 }
 template int launch_fa_fwd_z<float>(const float*, float*, float*, int, long long, int, int, int, cudaStream_t);

@@ -91,6 +91,7 @@ Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w) {
   ws.partial = take((size_t)B * T * ws.nsplit * 64 * 4);
   ws.wmat = take((size_t)B * T * T * 4);
   ws.wsum = take((size_t)B * T * 4);
+  ws.lrq = take(M * 3 * 4);                   // 8-bit entry points: the LR frames as fp32 NCHW between the two halves
   ws.total = off;
   return ws;
 }
@@ -268,10 +269,13 @@ static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* 
 
 template <typename T>
 static int down_impl(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_u8, float* lr_q, const Dims& d, char* wsp,
-                     const Workspace& ws, cudaStream_t st) {
+                     const Workspace& ws, cudaStream_t st, const uint8_t* hr_img = nullptr) {
   float* z = reinterpret_cast<float*>(wsp + ws.z);
   T* fbuf = reinterpret_cast<T*>(wsp + ws.fbuf);
-  PROF(ctx, st, 5, (double)d.M() * (16 * 3 * 4 + 51 * 4), launch_fa_fwd_z<T>(hr, z, fbuf, ws.fpitch, dense_slab(ctx, d), d.B * d.T, d.h, d.w, st));
+  if (hr_img != nullptr)
+    PROF(ctx, st, 5, (double)d.M() * (16 * 3 + 51 * 4), launch_fa_fwd_z_u8<T>(hr_img, z, fbuf, ws.fpitch, dense_slab(ctx, d), d.B * d.T, d.h, d.w, st));
+  else
+    PROF(ctx, st, 5, (double)d.M() * (16 * 3 * 4 + 51 * 4), launch_fa_fwd_z<T>(hr, z, fbuf, ws.fpitch, dense_slab(ctx, d), d.B * d.T, d.h, d.w, st));
   for (int blk = 0; blk < 8; ++blk) SELFC_TRY(run_invblock<T>(ctx, blk, false, wsp, ws, d, st));
   PROF(ctx, st, 5, (double)d.M() * (51 * 4 + (out51 ? 51 * 4 : 0) + 3), launch_export_down(z, out51, lr_u8, lr_q, d.M(), d.hw(), st));
   return 0;
@@ -279,7 +283,8 @@ static int down_impl(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_
 
 template <typename T>
 static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, float* hf,
-                   const Dims& d, char* wsp, const Workspace& ws, cudaStream_t st, const TrainHooks* hooks = nullptr) {
+                   const Dims& d, char* wsp, const Workspace& ws, cudaStream_t st, const TrainHooks* hooks = nullptr,
+                   uint8_t* hr_img = nullptr) {
   float* z = reinterpret_cast<float*>(wsp + ws.z);
   T* gbuf = reinterpret_cast<T*>(wsp + ws.gbuf);
   T* hbuf = reinterpret_cast<T*>(wsp + ws.hbuf);
@@ -389,7 +394,10 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
       SELFC_CUDA(cudaMemcpyAsync(hooks->z_save + (size_t)blk * d.M() * kZQuads * 4, z, (size_t)d.M() * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
     SELFC_TRY(run_invblock<T>(ctx, blk, true, wsp, ws, d, st));
   }
-  PROF(ctx, st, 5, (double)M * (51 * 4 + 48 * 4), launch_fa_rev(z, false, hr, d.B * d.T, d.h, d.w, st));
+  if (hr_img != nullptr)
+    PROF(ctx, st, 5, (double)M * (51 * 4 + 48), launch_fa_rev_u8(z, hr_img, d.B * d.T, d.h, d.w, st));
+  else
+    PROF(ctx, st, 5, (double)M * (51 * 4 + 48 * 4), launch_fa_rev(z, false, hr, d.B * d.T, d.h, d.w, st));
   return 0;
 }
 
@@ -728,6 +736,65 @@ int selfc_up(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, u
   if (ctx->mode == SELFC_MODE_BF16)
     return up_impl<__nv_bfloat16>(ctx, lr, eps, seed, offset, hr, hf, d, (char*)workspace, ws, st);
   return up_impl<float>(ctx, lr, eps, seed, offset, hr, hf, d, (char*)workspace, ws, st);
+}
+
+// ---- 8-bit frames at the boundary (decoded PNG / raw video planes in cv2 layout [n][H][W][3], B,G,R) ----------------
+int selfc_down_u8(selfc_ctx* ctx, const uint8_t* hr_img, uint8_t* lr_img, float* lr_q, int B, int T, int H, int W, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, H, W, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(hr_img && ((uintptr_t)hr_img & 3) == 0, "hr_img null or not 4-byte aligned");
+  Dims d{B, T, H / 4, W / 4};
+  cudaStream_t st = (cudaStream_t)stream;
+  float* q = lr_q ? lr_q : reinterpret_cast<float*>((char*)workspace + ws.lrq);
+  if (ctx->mode == SELFC_MODE_BF16)
+    SELFC_TRY(down_impl<__nv_bfloat16>(ctx, nullptr, nullptr, nullptr, q, d, (char*)workspace, ws, st, hr_img));
+  else
+    SELFC_TRY(down_impl<float>(ctx, nullptr, nullptr, nullptr, q, d, (char*)workspace, ws, st, hr_img));
+  if (lr_img) SELFC_TRY(launch_frames_to_u8(q, lr_img, (long long)B * T, d.hw(), st));
+  return 0;
+}
+
+int selfc_up_u8(selfc_ctx* ctx, const uint8_t* lr_img, const float* eps, uint64_t seed, uint64_t offset, uint8_t* hr_img, int B, int T,
+                int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, H, W, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(lr_img && hr_img && ((uintptr_t)hr_img & 3) == 0, "lr_img/hr_img null or hr_img not 4-byte aligned");
+  Dims d{B, T, H / 4, W / 4};
+  cudaStream_t st = (cudaStream_t)stream;
+  float* q = reinterpret_cast<float*>((char*)workspace + ws.lrq);
+  SELFC_TRY(launch_frames_from_u8(lr_img, q, (long long)B * T, d.hw(), st));
+  if (ctx->mode == SELFC_MODE_BF16)
+    return up_impl<__nv_bfloat16>(ctx, q, eps, seed, offset, nullptr, nullptr, d, (char*)workspace, ws, st, nullptr, hr_img);
+  return up_impl<float>(ctx, q, eps, seed, offset, nullptr, nullptr, d, (char*)workspace, ws, st, nullptr, hr_img);
+}
+
+int selfc_rescale_u8(selfc_ctx* ctx, const uint8_t* hr_img, const float* eps, uint64_t seed, uint64_t offset, uint8_t* lr_img,
+                     uint8_t* hr_out_img, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  SELFC_TRY(check_run(ctx, B, T, H, W, workspace, workspace_bytes, &ws));
+  SELFC_CHECK_ARG(hr_img && hr_out_img && ((uintptr_t)hr_img & 3) == 0 && ((uintptr_t)hr_out_img & 3) == 0,
+                  "hr_img/hr_out_img null or not 4-byte aligned");
+  Dims d{B, T, H / 4, W / 4};
+  cudaStream_t st = (cudaStream_t)stream;
+  char* wsp = (char*)workspace;
+  float* q = reinterpret_cast<float*>(wsp + ws.lrq);
+  const bool bf = ctx->mode == SELFC_MODE_BF16;
+  SELFC_TRY(bf ? down_impl<__nv_bfloat16>(ctx, nullptr, nullptr, nullptr, q, d, wsp, ws, st, hr_img)
+               : down_impl<float>(ctx, nullptr, nullptr, nullptr, q, d, wsp, ws, st, hr_img));
+  if (lr_img) SELFC_TRY(launch_frames_to_u8(q, lr_img, (long long)B * T, d.hw(), st));
+  return bf ? up_impl<__nv_bfloat16>(ctx, q, eps, seed, offset, nullptr, nullptr, d, wsp, ws, st, nullptr, hr_out_img)
+            : up_impl<float>(ctx, q, eps, seed, offset, nullptr, nullptr, d, wsp, ws, st, nullptr, hr_out_img);
+}
+
+int selfc_frames_from_u8(const uint8_t* img, float* x, int N, int H, int W, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && (N == 0 || (img && x)), "frames_from_u8: null pointer or N=%d H=%d W=%d", N, H, W);
+  return launch_frames_from_u8(img, x, N, (long long)H * W, (cudaStream_t)stream);
+}
+
+int selfc_frames_to_u8(const float* x, uint8_t* img, int N, int H, int W, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && (N == 0 || (img && x)), "frames_to_u8: null pointer or N=%d H=%d W=%d", N, H, W);
+  return launch_frames_to_u8(x, img, N, (long long)H * W, (cudaStream_t)stream);
 }
 
 int selfc_fa_fwd(const float* x, float* out51, int N, int H, int W, void* stream) {

@@ -74,7 +74,7 @@ namespace selfc {
 // ---- workspace layout -------------------------------------------------------------------------------------
 struct Workspace {
   size_t total = 0;
-  size_t z, sbuf, fbuf, gbuf, hbuf, stpbuf, feat, fact, h1, h2, params, wmap, partial, wmat, wsum;
+  size_t z, sbuf, fbuf, gbuf, hbuf, stpbuf, feat, fact, h1, h2, params, wmap, partial, wmat, wsum, lrq;
   int nsplit = 1;
   int fpitch = 176, gpitch = 0, spitch = 192;
 };

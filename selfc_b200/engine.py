@@ -191,6 +191,122 @@ class Engine:
         rec, _ = self.up(lr_q, T, eps=eps, seed=seed, offset=offset, want_hf=False)
         return lr_u8, rec
 
+    # ---- 8-bit frames: cv2 layout [n,H,W,3], B,G,R -------------------------------------------
+    def _check_img(self, x: torch.Tensor, what: str) -> torch.Tensor:
+        if not x.is_cuda or x.device != self.device:
+            raise RuntimeError(f"selfc_b200: {what} must live on {self.device} (got {x.device}); there is no CPU path")
+        if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3:
+            raise ValueError(f"{what} must be uint8 [n,H,W,3] (cv2 layout, BGR), got {x.dtype} {tuple(x.shape)}")
+        return x.contiguous()
+
+    def _img_dims(self, x: torch.Tensor, T: int, mult: int) -> Tuple[int, int, int]:
+        n, hh, ww, _ = x.shape
+        if T is None or T < 1 or n % T != 0:
+            raise ValueError(f"batch of {n} frames is not a multiple of the clip length T={T} (GlobalVar.set_Temporal_LEN)")
+        if hh % mult or ww % mult:
+            raise ValueError(f"expected H,W multiples of {mult}, got {tuple(x.shape)}")
+        return n // T, hh, ww
+
+    def frames_from_u8(self, img: torch.Tensor) -> torch.Tensor:
+        """read_img1 + BGR->RGB + HWC->CHW (data/util.py:103-115, LQGTVID_dataset.py:150-154): uint8 [n,H,W,3] -> fp32 [n,3,H,W]."""
+        img = self._check_img(img, "img")
+        n, hh, ww, _ = img.shape
+        x = torch.empty((n, 3, hh, ww), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_frames_from_u8(_ptr(img), _ptr(x), n, hh, ww, _stream(self.device)), "frames_from_u8")
+        return x
+
+    def frames_to_u8(self, x: torch.Tensor) -> torch.Tensor:
+        """tensor2img per frame (utils/util.py:104-133): fp32 [n,3,H,W] RGB -> uint8 [n,H,W,3] BGR."""
+        x = self._check_in(x, "x")
+        n, c, hh, ww = x.shape
+        if c != 3:
+            raise ValueError(f"expected [n,3,H,W], got {tuple(x.shape)}")
+        img = torch.empty((n, hh, ww, 3), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_frames_to_u8(_ptr(x), _ptr(img), n, hh, ww, _stream(self.device)), "frames_to_u8")
+        return img
+
+    def down_u8(self, hr_img: torch.Tensor, T: int, want_q: bool = False):
+        """8-bit HR frames -> 8-bit LR frames (+ the LR on the 1/255 fp32 grid, NCHW, when want_q)."""
+        hr_img = self._check_img(hr_img, "hr_img")
+        B, H, W = self._img_dims(hr_img, T, 4)
+        ws = self._workspace(B, T, H // 4, W // 4)
+        lr_img = torch.empty((B * T, H // 4, W // 4, 3), dtype=torch.uint8, device=self.device)
+        lr_q = torch.empty((B * T, 3, H // 4, W // 4), dtype=torch.float32, device=self.device) if want_q else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_down_u8(self._ctx, _ptr(hr_img), _ptr(lr_img), _ptr(lr_q), B, T, H, W, _ptr(ws), ws.numel(),
+                                             _stream(self.device)), "down_u8")
+        return (lr_img, lr_q) if want_q else lr_img
+
+    def up_u8(self, lr_img: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0) -> torch.Tensor:
+        """8-bit LR frames (the stored LR video) -> 8-bit reconstructed HR frames."""
+        lr_img = self._check_img(lr_img, "lr_img")
+        B, h, w = self._img_dims(lr_img, T, 1)
+        if eps is not None:
+            eps = self._check_in(eps, "eps")
+            if tuple(eps.shape) != (B, HF_DIM, GMM_K, T, h, w):
+                raise ValueError(f"eps must be [B,48,5,T,h,w]={(B, HF_DIM, GMM_K, T, h, w)}, got {tuple(eps.shape)}")
+        ws = self._workspace(B, T, h, w)
+        hr_img = torch.empty((B * T, 4 * h, 4 * w, 3), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_up_u8(self._ctx, _ptr(lr_img), _ptr(eps), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), _ptr(hr_img),
+                                           B, T, 4 * h, 4 * w, _ptr(ws), ws.numel(), _stream(self.device)), "up_u8")
+        return hr_img
+
+    def rescale_u8(self, hr_img: torch.Tensor, T: int, seed: int = 0, offset: int = 0, eps: Optional[torch.Tensor] = None,
+                   lr_out: Optional[torch.Tensor] = None, hr_out: Optional[torch.Tensor] = None):
+        """8-bit frames in, 8-bit LR and reconstructed HR frames out, one call.  Returns (lr_img, hr_rec_img)."""
+        hr_img = self._check_img(hr_img, "hr_img")
+        B, H, W = self._img_dims(hr_img, T, 4)
+        h, w = H // 4, W // 4
+        if eps is not None:
+            eps = self._check_in(eps, "eps")
+            if tuple(eps.shape) != (B, HF_DIM, GMM_K, T, h, w):
+                raise ValueError(f"eps must be [B,48,5,T,h,w]={(B, HF_DIM, GMM_K, T, h, w)}, got {tuple(eps.shape)}")
+        ws = self._workspace(B, T, h, w)
+        lr_img = lr_out if lr_out is not None else torch.empty((B * T, h, w, 3), dtype=torch.uint8, device=self.device)
+        rec = hr_out if hr_out is not None else torch.empty((B * T, H, W, 3), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.selfc_rescale_u8(self._ctx, _ptr(hr_img), _ptr(eps), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1),
+                                                _ptr(lr_img), _ptr(rec), B, T, H, W, _ptr(ws), ws.numel(), _stream(self.device)),
+                       "rescale_u8")
+        return lr_img, rec
+
+    def rescale_host_u8(self, frames_host: torch.Tensor, lr_host: torch.Tensor, hr_host: torch.Tensor, T: int = 7,
+                        seed: int = 0, offset0: int = 0) -> None:
+        """rescale_host on 8-bit frames: frames_host [n,H,W,3], lr_host [n,H/4,W/4,3], hr_host [n,H,W,3], all uint8 in (pinned)
+        HOST memory, cv2 layout.  A quarter of the PCIe bytes of the fp32 interface, and no fp32 frame in HBM on either side."""
+        from .sharding import gop_indices
+        n, H, W, _ = frames_host.shape
+        dev = self.device
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_in, s_out = self._s_in, self._s_out
+        cur = torch.cuda.current_stream(dev)
+        bufs = [torch.empty((T, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+        ev_free = [None, None]
+        s_in.wait_stream(cur)
+        for i, (ids, real) in enumerate(gop_indices(n, T)):
+            buf = bufs[i & 1]
+            with torch.cuda.stream(s_in):
+                if ev_free[i & 1] is not None:
+                    s_in.wait_event(ev_free[i & 1])
+                buf[:real].copy_(frames_host[ids[0]:ids[0] + real], non_blocking=True)
+                if real < T:
+                    buf[real:] = buf[real - 1:real]
+                ev_in = s_in.record_event()
+            cur.wait_event(ev_in)
+            lr_img, rec = self.rescale_u8(buf, T, seed=seed, offset=offset0 + i)
+            ev_free[i & 1] = cur.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_free[i & 1])
+                lr_host[ids[0]:ids[0] + real].copy_(lr_img[:real], non_blocking=True)
+                hr_host[ids[0]:ids[0] + real].copy_(rec[:real], non_blocking=True)
+                lr_img.record_stream(s_out)
+                rec.record_stream(s_out)
+        s_out.synchronize()
+
     def rescale_host(self, frames_host: torch.Tensor, lr_host: torch.Tensor, hr_host: torch.Tensor, T: int = 7,
                      seed: int = 0, offset0: int = 0) -> None:
         """A whole clip held in (pinned) HOST memory -> LR codes and reconstructed HR frames in HOST memory.

@@ -397,6 +397,121 @@ def test_rescale_host_pipeline_matches_per_gop_calls(dev):
         assert torch.equal(hr_h[ids[0]:ids[0] + real], rec[:real].cpu())
 
 
+# ------------------------------------------------------------------------------------------------ f2: 8-bit frames at the boundary
+def test_u8_frame_conversions_bit_exact(dev, golden_dir):
+    """Stand-alone ingest/egress kernels against the reference's helpers (fixture) and the oracle (odd sizes, ties, out of range)."""
+    eng = _engine(dev, so.make_state_dict(0))
+    g = np.load(os.path.join(golden_dir, "u8.npz"))
+    assert np.array_equal(eng.frames_from_u8(torch.from_numpy(g["img"]).to(dev)).cpu().numpy(), g["from_ref"])
+    assert np.array_equal(eng.frames_to_u8(_t(g["y"]).to(dev)).cpu().numpy(), g["to_ref"])
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, size=(3, 37, 53, 3), dtype=np.uint8)
+    assert np.array_equal(eng.frames_from_u8(torch.from_numpy(img).to(dev)).cpu().numpy(), so.frames_from_u8(img).numpy())
+    y = torch.randn(3, 3, 37, 53, generator=torch.Generator().manual_seed(5)) * 0.5 + 0.5
+    y.view(-1)[:512] = (torch.arange(512, dtype=torch.float32) * 0.5) / 255.0        # every half code: all the ties
+    assert np.array_equal(eng.frames_to_u8(y.to(dev)).cpu().numpy(), so.frames_to_u8(y))
+    assert eng.frames_to_u8(torch.zeros(0, 3, 8, 8, device=dev)).shape == (0, 8, 8, 3)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_u8_path_equals_fp32_interface_on_converted_frames(dev, mode):
+    """The fused 8-bit entry points are the fp32 entry points composed with the CPU conversions, bit for bit:
+    down_u8(img) == to_u8(down(from_u8(img))), up_u8(lr_img) == to_u8(up(from_u8(lr_img))), and the one-call rescale_u8."""
+    sd = so.make_state_dict(0)
+    eng = _engine(dev, sd, mode)
+    b, t, hh, ww = 2, 3, 40, 72
+    rng = np.random.default_rng(6)
+    base = so.make_frames(b, t, hh, ww, 8)
+    img = so.frames_to_u8(base)                                  # a plausible 8-bit clip
+    img[0, :2, :8] = rng.integers(0, 256, size=(2, 8, 3), dtype=np.uint8)
+    x = so.frames_from_u8(img)
+    img_d = torch.from_numpy(img).to(dev)
+    _, lr_u8, lr_q = eng.down(x.to(dev), t, want_out51=False)
+    lr_img, lr_q2 = eng.down_u8(img_d, t, want_q=True)
+    assert torch.equal(lr_q2, lr_q)
+    assert np.array_equal(lr_img.cpu().numpy(), so.frames_to_u8(lr_q.cpu()))
+    assert np.array_equal(lr_img.cpu().numpy(), np.transpose(lr_u8.cpu().numpy()[:, [2, 1, 0]], (0, 2, 3, 1)))
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 15).to(dev)
+    hr, _ = eng.up(lr_q, t, eps=eps, want_hf=False)
+    hr_img = eng.up_u8(lr_img, t, eps=eps)
+    assert np.array_equal(hr_img.cpu().numpy(), so.frames_to_u8(hr.cpu()))
+    lr_img2, hr_img2 = eng.rescale_u8(img_d, t, eps=eps)
+    assert torch.equal(lr_img2, lr_img) and torch.equal(hr_img2, hr_img)
+    # Philox noise path too
+    hr_p, _ = eng.up(lr_q, t, seed=5, offset=2, want_hf=False)
+    assert np.array_equal(eng.up_u8(lr_img, t, seed=5, offset=2).cpu().numpy(), so.frames_to_u8(hr_p.cpu()))
+
+
+def test_u8_rescale_vs_oracle(dev):
+    """8-bit frames through the whole path against the oracle's rescale_u8 (fp32 mode): LR codes within 1 LSB on >= 99.99 %,
+    HR codes within 1 (HR tolerance 1e-3 is < half a code, so only rounding ties can differ)."""
+    sd = so.make_state_dict(1)
+    eng = _engine(dev, sd)
+    b, t, hh, ww = 1, 3, 32, 48
+    img = so.frames_to_u8(so.make_frames(b, t, hh, ww, 21))
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 22)
+    lr_ref, hr_ref = so.rescale_u8(sd, img, eps, t)
+    lr_img = eng.down_u8(torch.from_numpy(img).to(dev), t)
+    dl = np.abs(lr_img.cpu().numpy().astype(int) - lr_ref.astype(int))
+    assert dl.max() <= 1 and (dl != 0).sum() <= max(1, int(1e-4 * dl.size))      # 864 codes: at most one rounding tie
+    # up from the ORACLE's LR frames so both sides start from identical codes
+    hr_img = eng.up_u8(torch.from_numpy(lr_ref).to(dev), t, eps=eps.to(dev))
+    dh = np.abs(hr_img.cpu().numpy().astype(int) - hr_ref.astype(int))
+    assert dh.max() <= 1 and (dh == 0).mean() >= 0.99
+
+
+def test_rescale_host_u8_pipeline_matches_per_gop_calls(dev):
+    sd = so.make_state_dict(0)
+    eng = _engine(dev, sd, "bf16")
+    n, hh, ww = 16, 32, 48
+    img = torch.from_numpy(so.frames_to_u8(so.make_frames(1, n, hh, ww, 3)))
+    host_in = img.pin_memory()
+    lr_h = torch.empty(n, hh // 4, ww // 4, 3, dtype=torch.uint8).pin_memory()
+    hr_h = torch.empty(n, hh, ww, 3, dtype=torch.uint8).pin_memory()
+    eng.rescale_host_u8(host_in, lr_h, hr_h, 7, seed=3, offset0=10)
+    from selfc_b200.sharding import gop_indices
+    for i, (ids, real) in enumerate(gop_indices(n, 7)):
+        lr_img, rec = eng.rescale_u8(img[ids].to(dev), 7, seed=3, offset=10 + i)
+        assert torch.equal(lr_h[ids[0]:ids[0] + real], lr_img[:real].cpu())
+        assert torch.equal(hr_h[ids[0]:ids[0] + real], rec[:real].cpu())
+
+
+def test_module_rescale_u8_matches_forward_chain(dev):
+    """SelfCInvNet.rescale_u8 == read_img1-style conversion -> forward -> Quantization -> forward(rev) -> tensor2img, bit for bit."""
+    from selfc_b200 import networks, options
+    from selfc_b200.global_var import GlobalVar
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    opt = options.dict_to_nonedict(options.parse(os.path.join(here, "selfc_b200", "configs", "selfc_large_synthetic.yml"),
+                                                 is_train=False))
+    net = networks.define_G(opt)
+    sd = so.make_state_dict(2)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    t = 3
+    GlobalVar.set_Temporal_LEN(t)
+    img = so.frames_to_u8(so.make_frames(1, t, 32, 48, 31))
+    net.set_noise(9, 4)
+    lr_img, hr_img = net.rescale_u8(torch.from_numpy(img).to(dev))
+    net.set_noise(9, 4)
+    out, _ = net(so.frames_from_u8(img).to(dev))
+    lr = so.quantize(out[:, :3].cpu())
+    hr, _ = net(lr.to(dev), rev=True)
+    assert np.array_equal(lr_img.cpu().numpy(), so.frames_to_u8(lr))
+    assert np.array_equal(hr_img.cpu().numpy(), so.frames_to_u8(hr.cpu()))
+
+
+def test_u8_errors_are_loud(dev):
+    eng = _engine(dev, so.make_state_dict(0))
+    with pytest.raises(ValueError):
+        eng.down_u8(torch.zeros(3, 30, 48, 3, dtype=torch.uint8, device=dev), 3)      # H not a multiple of 4
+    with pytest.raises(ValueError):
+        eng.down_u8(torch.zeros(3, 3, 32, 48, dtype=torch.uint8, device=dev), 3)      # NCHW instead of cv2 layout
+    with pytest.raises(ValueError):
+        eng.up_u8(torch.zeros(4, 8, 12, 3, dtype=torch.uint8, device=dev), 3)         # not a multiple of T
+    with pytest.raises(RuntimeError):
+        eng.down_u8(torch.zeros(3, 32, 48, 3, dtype=torch.uint8), 3)                  # host tensor: no CPU path
+
+
 # ------------------------------------------------------------------------------------------------ a13 building blocks (training step)
 @pytest.mark.parametrize("prefix,cin,cout", [("operations.2.F", 48, 3), ("operations.6.G", 3, 48), ("stp_net.local_m2", 64, 64)])
 def test_d2dt_backward_vs_autograd(dev, prefix, cin, cout):
