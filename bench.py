@@ -305,7 +305,12 @@ def run_ours(args):
         roofline = {"kernel": "conv3x3_tc3_kernel: (1,3,3) dense-block convolution, tcgen05 implicit GEMM "
                               "(all 216 launches of one 7-frame GOP, down+up)",
                     "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
-                    "traffic": traffic, "peak_source": f"of {src} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "traffic": traffic,
+                    "hbm_view": ({"achieved_gbs": traffic / (c["ms"] / max(1, c["launches"]) / 1e3) / 1e9, "peak_gbs": hbm,
+                                  "frac": traffic / (c["ms"] / max(1, c["launches"]) / 1e3) / 1e9 / hbm,
+                                  "note": "the same launches against the HBM roof: cold-cache DRAM bytes per launch (ncu) / in-stream launch time; "
+                                          "the class sits at about the same fraction of both roofs"} if traffic and c["ms"] > 0 else None),
+                    "peak_source": f"of {src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches": c["launches"],
                     "share_of_step": c["ms"] / tot_ms if tot_ms else None,
                     "classes": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],

@@ -10,6 +10,7 @@ namespace selfc {
 // (see conv_tc3.cu), plus its fp32 bias.
 struct TcConvW {
   void* img = nullptr;      // device, bf16
+  void* img_pair = nullptr; // device, bf16: the same rows split in two halves for the CTA-pair kernel
   float* bias = nullptr;    // device, [32]
   size_t img_bytes = 0;
   int cin_buf = 0;          // input channels consumed from the dense buffer (multiple of 16)

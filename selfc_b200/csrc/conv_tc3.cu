@@ -63,8 +63,21 @@ struct Params {
   int out_slab, N, h, w, nks, kps;
   int tiles_x, tiles_y, ntiles;
   int nst;
+  int rev;               // walk the tiles last-to-first (see tc::next_direction)
   int* err;
+  long long* dbg;        // SELFC_TC_DBG=1 (+ -DSELFC_TC_TIMING): CTA 0's barrier-wait cycles
 };
+
+// barrier wait; with -DSELFC_TC_TIMING the cycles spent waiting are accumulated for the debug counters
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, int* err, int code, long long& acc) {
+#ifdef SELFC_TC_TIMING
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err, code);
+  acc += clock64() - t0;
+#else
+  mbar_wait(bar, parity, err, code);
+#endif
+}
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -78,12 +91,35 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Tile order: band-major -- (tile row, frame, tile column) from slowest to fastest -- so that a launch sweeps the image top to
+// bottom across all frames, the order the (3,1,1) conv5 kernel also walks the pixels in; p.rev walks it bottom to top.
+// Consecutive launches of a dense block alternate direction (tc::next_direction): a launch starts on the rows the previous
+// one touched last, which are still in L2 (the dense buffer of a GOP is 2-4x the L2, so a same-direction sweep always misses).
+__device__ __forceinline__ void decode_tile(const Params& p, int tile, int& tx, int& ty, int& n) {
+  if (tile >= p.ntiles) { tx = 0; ty = 0; n = p.N; return; }
+  const int t = p.rev ? p.ntiles - 1 - tile : tile;
+  tx = t % p.tiles_x;
+  n = (t / p.tiles_x) % p.N;
+  ty = t / (p.tiles_x * p.N);
+}
+
+// PAIR: the kernel runs as CTA pairs (cluster of 2, cta_group::2).  Each CTA of a pair works on its own tile with its own
+// activation pipeline, accumulators and epilogue; the pair's leader issues ONE M = 256 MMA for both (128 halo positions from
+// each CTA), and each CTA keeps only half of the weight rows (48 of the 96 (kx, n) rows), so an MMA reads 4 + 1.5 KB of each
+// SM's shared memory instead of 4 + 3 KB -- the operand feed, not the tensor pipe, is what bounds the one-CTA form.
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                   const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int prob = p.nprob == 2 ? (int)(blockIdx.x & 1u) : 0;
-  const int rank = p.nprob == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // this CTA walks tiles rank, rank + nctas, ...
-  const int nctas = p.nprob == 2 ? (int)((gridDim.x + 1 - prob) >> 1) : (int)gridDim.x;
+  constexpr int NBH = PAIR ? NB / 2 : NB;                 // weight rows held by this CTA
+  constexpr int WT_BYTES = NBH * 16 * 2;                  // one (ky, K-step) B tile of this CTA
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // scheduling unit: a CTA or a CTA pair
+  const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int prob = p.nprob == 2 ? (unit & 1) : 0;
+  const int rank = p.nprob == 2 ? (unit >> 1) : unit;                        // this unit walks steps rank, rank + nwalk, ...
+  const int nwalk = p.nprob == 2 ? ((nunits + 1 - prob) >> 1) : nunits;
+  const int nsteps = PAIR ? (p.ntiles + 1) >> 1 : p.ntiles;                  // a pair takes tiles 2*step, 2*step + 1
   const CUtensorMap* tmap = prob ? &tmap_b : &tmap_a;
   const void* wimg = prob ? p.wimg2 : p.wimg;
   const float* biasp = prob ? p.bias2 : p.bias;
@@ -104,6 +140,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE_MAX + 1 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE_MAX + 3 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE_MAX + 5);
+  const uint32_t wpeer_bar = bar_base + 8u * (2 * NSTAGE_MAX + 6);           // leader: the peer's weights have landed
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + bar_off + 8 * (2 * NSTAGE_MAX + 5));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -115,16 +152,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(w_bar, 1);
+    mbar_init(wpeer_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), PAIR ? 8 : 4);       // the epilogue warps of both CTAs release the leader's accumulator stage
     }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc2(tmem_slot, (uint32_t)TMEM_COLS);
+    else tmem_alloc(tmem_slot, (uint32_t)TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_launch_dependents();
@@ -133,69 +175,100 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t wbytes = 3u * nks * WTILE_BYTES;
+      const uint32_t wbytes = 3u * nks * WT_BYTES;
+      const uint8_t* wsrc = (const uint8_t*)wimg + (PAIR ? (size_t)crank * wbytes : 0);
       mbar_expect_tx(w_bar, wbytes);
       for (int ky = 0; ky < 3; ++ky)
-        bulk_g2s(w_base + ky * nks * WTILE_BYTES, (const uint8_t*)wimg + (size_t)ky * nks * WTILE_BYTES, (uint32_t)nks * WTILE_BYTES,
-                 w_bar);
+        bulk_g2s(w_base + ky * nks * WT_BYTES, wsrc + (size_t)ky * nks * WT_BYTES, (uint32_t)nks * WT_BYTES, w_bar);
+#ifdef SELFC_TC_TIMING
+      const long long t_pdl0 = clock64();
+#endif
       pdl_wait();      // weights are static; activations come from the previous kernel in the stream
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = rank; tile < p.ntiles; tile += nctas) {
-        const int tx = tile % p.tiles_x;
-        const int ty = (tile / p.tiles_x) % p.tiles_y;
-        const int n = tile / (p.tiles_x * p.tiles_y);
+      long long w_empty = 0;
+      const long long t_start = clock64();
+#ifdef SELFC_TC_TIMING
+      if (p.dbg) {
+        atomicMax((unsigned long long*)&p.dbg[10], (unsigned long long)(t_start - t_pdl0));
+        atomicAdd((unsigned long long*)&p.dbg[11], (unsigned long long)(t_start - t_pdl0));
+      }
+#endif
+      for (int step = rank; step < nsteps; step += nwalk) {
+        const int tile = PAIR ? 2 * step + (int)crank : step;
+        int tx, ty, n;
+        decode_tile(p, tile, tx, ty, n);                   // n == N for the odd tile out of a pair: the box is zero-filled
         const int x0 = tx * VALID_W - 1, y0 = ty * ROWS - 1;
         for (int c0 = 0; c0 < nks; c0 += KPS) {
-          mbar_wait(empty_bar(s), ph ^ 1u, p.err, 31);
-          mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
-          tma_load_5d(a_base + s * STAGE, tmap, full_bar(s), 0, x0, y0, n, c0);
+          timed_wait(empty_bar(s), ph ^ 1u, p.err, 31, w_empty);
+          if (PAIR) {
+            // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
+            if (crank == 0) mbar_expect_tx(full_bar(s), 2u * (uint32_t)STAGE);
+            tma_load_5d_pair(a_base + s * STAGE, tmap, mapa_u32(full_bar(s), 0), 0, x0, y0, n, c0);
+          } else {
+            mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
+            tma_load_5d(a_base + s * STAGE, tmap, full_bar(s), 0, x0, y0, n, c0);
+          }
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = w_empty; p.dbg[1] = clock64() - t_start; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
-    mbar_wait(w_bar, 0, p.err, 32);
-    int s = 0;
-    uint32_t ph = 0;
-    int it = 0;
-    const uint32_t hi_a = desc_hi(256, 6);            // activations: SWIZZLE_32B rows, 8-row atoms of 256 bytes
-    const uint32_t hi_b = desc_hi(128, 0);            // weights: no-swizzle core matrices, 8-row groups 128 bytes apart
-    const uint32_t b_ky = (uint32_t)nks * (WTILE_BYTES >> 4);
-    for (int tile = rank; tile < p.ntiles; tile += nctas, ++it) {
-      const int acc = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u, p.err, 33);
-      tc_fence_after();
-      for (int c0 = 0; c0 < nks; c0 += KPS) {
-        const int nk = nks - c0 < KPS ? nks - c0 : KPS;
-        mbar_wait(full_bar(s), ph, p.err, 34);
+    if (PAIR && crank != 0) {
+      // the peer issues no MMAs; it only tells the leader that its half of the weights is in place
+      mbar_wait(w_bar, 0, p.err, 32);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(wpeer_bar, 0));
+    } else {
+      // ===================== MMA issuer: whole warp runs the loop, one elected lane issues =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, NB);
+      mbar_wait(w_bar, 0, p.err, 32);
+      if (PAIR) mbar_wait(wpeer_bar, 0, p.err, 36);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      const uint32_t hi_a = desc_hi(256, 6);            // activations: SWIZZLE_32B rows, 8-row atoms of 256 bytes
+      const uint32_t hi_b = desc_hi(128, 0);            // weights: no-swizzle core matrices, 8-row groups 128 bytes apart
+      const uint32_t b_ky = (uint32_t)nks * (WT_BYTES >> 4);
+      long long w_full = 0, w_tempty = 0;
+      const long long t_start = clock64();
+      for (int step = rank; step < nsteps; step += nwalk, ++it) {
+        const int acc = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        timed_wait(tempty_bar(acc), (use & 1u) ^ 1u, p.err, 33, w_tempty);
         tc_fence_after();
-        const uint32_t a_stage = a_base + s * STAGE;
-        for (int ks = 0; ks < nk; ++ks) {
-          const uint32_t a_lo = desc_lo(a_stage + (uint32_t)ks * SUB_BYTES, 16);
-          // B (weights): (ky, K-step) tiles of 3 KB; the two 8-element K core matrices are 12 row-groups apart
-          const uint32_t b_lo = desc_lo(w_base + (uint32_t)(c0 + ks) * WTILE_BYTES, (NB / 8) * 128);
-          // consecutive MMAs alternate between the two M-blocks' accumulators: back-to-back accumulation into ONE
-          // accumulator is a dependent chain (measured ~145 cycles per small MMA), independent accumulators pipeline
+        for (int c0 = 0; c0 < nks; c0 += KPS) {
+          const int nk = nks - c0 < KPS ? nks - c0 : KPS;
+          timed_wait(full_bar(s), ph, p.err, 34, w_full);
+          tc_fence_after();
+          const uint32_t a_stage = a_base + s * STAGE;
+          for (int ks = 0; ks < nk; ++ks) {
+            const uint32_t a_lo = desc_lo(a_stage + (uint32_t)ks * SUB_BYTES, 16);
+            // B (weights): (ky, K-step) tiles; the two 8-element K core matrices are NBH/8 row-groups apart
+            const uint32_t b_lo = desc_lo(w_base + (uint32_t)(c0 + ks) * WT_BYTES, (NBH / 8) * 128);
+            // consecutive MMAs alternate between the two M-blocks' accumulators: back-to-back accumulation into ONE
+            // accumulator is a dependent chain (measured ~145 cycles per small MMA), independent accumulators pipeline
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
+            for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-            for (int mb = 0; mb < MBLK; ++mb) {
-              const uint32_t d = tmem_base + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
-              // A rows = flattened halo positions: M-block mb starts at tile row 4*mb, the ky tap one tile row further
-              const uint64_t ad = desc_join(a_lo + (uint32_t)((mb * 128 + ky * WT) * 2), hi_a);
-              const uint64_t bd = desc_join(b_lo + (uint32_t)ky * b_ky, hi_b);
-              umma_bf16_elect(d, ad, bd, idesc, ((c0 + ks) > 0 || ky > 0) ? 1u : 0u);
+              for (int mb = 0; mb < MBLK; ++mb) {
+                const uint32_t d = tmem_base + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
+                // A rows = flattened halo positions: M-block mb starts at tile row 4*mb, the ky tap one tile row further
+                const uint64_t ad = desc_join(a_lo + (uint32_t)((mb * 128 + ky * WT) * 2), hi_a);
+                const uint64_t bd = desc_join(b_lo + (uint32_t)ky * b_ky, hi_b);
+                if (PAIR) umma2_bf16_elect(d, ad, bd, idesc, ((c0 + ks) > 0 || ky > 0) ? 1u : 0u);
+                else umma_bf16_elect(d, ad, bd, idesc, ((c0 + ks) > 0 || ky > 0) ? 1u : 0u);
+              }
             }
           }
+          if (PAIR) umma2_commit_elect(empty_bar(s));
+          else umma_commit_elect(empty_bar(s));
+          if (++s == NST) { s = 0; ph ^= 1u; }
         }
-        umma_commit_elect(empty_bar(s));
-        if (++s == NST) { s = 0; ph ^= 1u; }
+        if (PAIR) umma2_commit_elect(tfull_bar(acc));
+        else umma_commit_elect(tfull_bar(acc));
       }
-      umma_commit_elect(tfull_bar(acc));
+      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - t_start; }
     }
   } else {
     // ===================== epilogue warps 2..5 =====================
@@ -205,22 +278,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) bias[j] = __ldg(biasp + j);
     const size_t slab_elems = (size_t)p.slabM * 16;
+    const uint32_t tempty_leader0 = PAIR ? mapa_u32(tempty_bar(0), 0) : 0u;
     int it = 0;
-    for (int tile = rank; tile < p.ntiles; tile += nctas, ++it) {
+    long long w_tfull = 0;
+    const long long t_start = clock64();
+    for (int step = rank; step < nsteps; step += nwalk, ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int tx = tile % p.tiles_x;
-      const int ty = (tile / p.tiles_x) % p.tiles_y;
-      const int n = tile / (p.tiles_x * p.tiles_y);
+      const int tile = PAIR ? 2 * step + (int)crank : step;
+      const bool tile_ok = tile < p.ntiles;
+      int tx, ty, n;
+      decode_tile(p, tile, tx, ty, n);
       const int x = tx * VALID_W + lane;
-      mbar_wait(tfull_bar(acc), use & 1u, p.err, 35);
+      timed_wait(tfull_bar(acc), use & 1u, p.err, 35, w_tfull);
       tc_fence_after();
 #pragma unroll
       for (int mb = 0; mb < MBLK; ++mb) {
         const int y = ty * ROWS + mb * 4 + q;
-        const bool ok = lane < VALID_W && x < p.w && y < p.h;
+        const bool ok = tile_ok && lane < VALID_W && x < p.w && y < p.h;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
-        __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)n * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
+        __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)(ok ? n : 0) * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
 #pragma unroll
         for (int n0 = 0; n0 < NOUT; n0 += 16) {
           uint32_t r0[16], r1[16], r2[16];
@@ -232,7 +309,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
             // both accumulators of this tile are in registers: the next-but-one tile's MMAs may start
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(tempty_leader0 + 8u * (uint32_t)acc);
+              else mbar_arrive(tempty_bar(acc));
+            }
           }
           float v[16];
 #pragma unroll
@@ -252,19 +332,32 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
         }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[6] = w_tfull; p.dbg[8] = clock64() - t_start; p.dbg[9] = it; }
+#ifdef SELFC_TC_TIMING
+    if (p.dbg && threadIdx.x == 64) {      // busy time of every CTA's epilogue (first accumulator ready -> last store), max / sum
+      const long long busy = clock64() - t_start - w_tfull;
+      atomicMax((unsigned long long*)&p.dbg[12], (unsigned long long)busy);
+      atomicAdd((unsigned long long*)&p.dbg[13], (unsigned long long)busy);
+      atomicMax((unsigned long long*)&p.dbg[14], (unsigned long long)(clock64() - t_start));
+      atomicAdd((unsigned long long*)&p.dbg[15], (unsigned long long)(clock64() - t_start));
+    }
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // neither CTA leaves (or frees tensor memory) while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)TMEM_COLS);
+    else tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
   }
 }
 
-// wref [32][cin_ref][3][3] fp32 -> bf16 B-operand image [ky][kstep][kcore(2)][ngroup(12)][r%8][k%8], row r = kx*32 + n
-__global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* __restrict__ img, int cin_ref, int cin_buf, int xreal,
-                                int xpad) {
+// wref [32][cin_ref][3][3] fp32 -> bf16 B-operand image [ky][kstep][kcore(2)][ngroup(12)][r%8][k%8], row r = kx*32 + n;
+// img_pair: the same rows split between the CTAs of a pair, [half(2)][ky][kstep][kcore(2)][ngroup(6)][r%8][k%8], half = r / 48
+__global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ img_pair,
+                                int cin_ref, int cin_buf, int xreal, int xpad) {
   const int nks = cin_buf / 16;
   const int total = 3 * cin_buf * NB;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,6 +372,11 @@ __global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* _
   const int ks = c / 16, kk = c % 16;
   const size_t off = (size_t)(ky * nks + ks) * (WTILE_BYTES / 2) + (size_t)((kk / 8) * (NB / 8) + r / 8) * 64 + (r % 8) * 8 + (kk % 8);
   img[off] = __float2bfloat16_rn(v);
+  const int half = r / (NB / 2), rh = r % (NB / 2);
+  const size_t half_elems = (size_t)3 * nks * (WTILE_BYTES / 4);
+  const size_t offp = half * half_elems + (size_t)(ky * nks + ks) * (WTILE_BYTES / 4) + (size_t)((kk / 8) * (NB / 16) + rh / 8) * 64 +
+                      (rh % 8) * 8 + (kk % 8);
+  img_pair[offp] = __float2bfloat16_rn(v);
 }
 
 }  // namespace tc3
@@ -338,7 +436,21 @@ int debug_read(long long* out, int cap) {
     cudaMemcpy(out + 17 * i + 1, g_dbg_dev + 16 * i, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
   }
   g_dbg_n = 0;
+  if (g_dbg_dev) cudaMemset(g_dbg_dev, 0, 4096 * 16 * sizeof(long long));
   return n;
+}
+
+// sweep direction of the next tcgen05 conv launch: alternates per launch (SELFC_ZIGZAG=0: always forward)
+int next_direction() {
+  static int on = -1;
+  static int dir = 0;
+  if (on < 0) {
+    const char* e = getenv("SELFC_ZIGZAG");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!on) return 0;
+  dir ^= 1;
+  return dir;
 }
 
 bool pdl_enabled() {
@@ -368,12 +480,14 @@ int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_re
   if (w.img == nullptr || w.img_bytes != bytes) {
     free_tc_weights(w);
     SELFC_CUDA(cudaMalloc(&w.img, bytes));
+    SELFC_CUDA(cudaMalloc(&w.img_pair, bytes));
     SELFC_CUDA(cudaMalloc(&w.bias, tc3::NOUT * sizeof(float)));
     w.img_bytes = bytes;
   }
   w.cin_buf = cin_buf;
   const int total = 3 * cin_buf * tc3::NB;
-  tc3::pack_tc3_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, reinterpret_cast<__nv_bfloat16*>(w.img), cin_ref, cin_buf, xreal, xpad);
+  tc3::pack_tc3_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, reinterpret_cast<__nv_bfloat16*>(w.img),
+                                                         reinterpret_cast<__nv_bfloat16*>(w.img_pair), cin_ref, cin_buf, xreal, xpad);
   SELFC_LAUNCH_CHECK("pack_tc3_kernel");
   SELFC_CUDA(cudaMemcpyAsync(w.bias, bref, tc3::NOUT * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -381,8 +495,10 @@ int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_re
 
 void free_tc_weights(TcConvW& w) {
   if (w.img) cudaFree(w.img);
+  if (w.img_pair) cudaFree(w.img_pair);
   if (w.bias) cudaFree(w.bias);
   w.img = nullptr;
+  w.img_pair = nullptr;
   w.bias = nullptr;
   w.img_bytes = 0;
 }
@@ -405,9 +521,18 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
     kps_pref = e ? atoi(e) : 2;
     if (kps_pref < 1 || kps_pref > 4) kps_pref = 2;
   }
+  // SELFC_TC3_PAIR=1: CTA-pair kernel (cta_group::2).  Parity-green and its MMA issue is cheaper (40 vs 67 cycles per MMA slot),
+  // but the launch as a whole is bound by the dense buffer's DRAM traffic either way (profiles/r2_conv3x3_waits.md), so the
+  // simpler one-CTA kernel stays the default.
+  static int pair_pref = -1;
+  if (pair_pref < 0) {
+    const char* e = getenv("SELFC_TC3_PAIR");
+    pair_pref = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  const bool pair = pair_pref == 1 && w.img_pair != nullptr && (!dual || w2->img_pair != nullptr);
   const int nks = cin / 16;
   int kps = kps_pref < nks ? kps_pref : nks;
-  const int fixed = tc3::BAR_BYTES + (int)w.img_bytes + 1024;      // both problems' weights have the same size
+  const int fixed = tc3::BAR_BYTES + (int)(pair ? w.img_bytes / 2 : w.img_bytes) + 1024;      // both problems' weights have the same size
   while (kps > 1 && (227 * 1024 - fixed) / (kps * tc3::SUB_BYTES) < 3) --kps;
   CUtensorMap tmap, tmap2;
   const cuuint64_t gdim[5] = {16, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
@@ -425,11 +550,11 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   }
   tc3::Params p;
   memset(&p, 0, sizeof(p));
-  p.wimg = w.img;
+  p.wimg = pair ? w.img_pair : w.img;
   p.bias = w.bias;
   p.buf = buf;
   p.nprob = dual ? 2 : 1;
-  p.wimg2 = dual ? w2->img : w.img;
+  p.wimg2 = dual ? (pair ? w2->img_pair : w2->img) : p.wimg;
   p.bias2 = dual ? w2->bias : w.bias;
   p.buf2 = dual ? buf2 : buf;
   p.slabM = slabM;
@@ -444,6 +569,8 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   p.ntiles = p.tiles_x * p.tiles_y * N;
   p.err = tc::err_flag_for_device();
   if (p.ntiles == 0) return 0;
+  p.rev = tc::next_direction();
+  if (tc::debug_slots()) p.dbg = tc::debug_next_slot(9000000 + (dual ? 100000 : 0) + nks);
   const int stage = kps * tc3::SUB_BYTES;
   int nst = (227 * 1024 - fixed) / stage;
   if (nst > tc3::NSTAGE_MAX) nst = tc3::NSTAGE_MAX;
@@ -452,13 +579,22 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   const int smem = fixed + nst * stage;
   static bool attr_set = false;
   if (!attr_set) {
-    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int nsm = tc::num_sms();
-  int grid = p.nprob * p.ntiles < nsm ? p.nprob * p.ntiles : nsm;
-  if (dual && (grid & 1)) --grid;                   // CTA parity selects the problem: both halves get the same CTA count
-  SELFC_CUDA(tc::launch_pdl(tc3::conv3x3_tc3_kernel, grid, tc3::THREADS, smem, st, tmap, tmap2, p));
+  if (pair) {
+    // scheduling units are CTA pairs, each taking two tiles per step; dual launches give every problem the same number of pairs
+    const int nsteps = (p.ntiles + 1) / 2;
+    int npairs = p.nprob * nsteps < nsm / 2 ? p.nprob * nsteps : nsm / 2;
+    if (dual && (npairs & 1)) --npairs;
+    SELFC_CUDA(tc::launch_pdl_pairs(tc3::conv3x3_tc3_kernel<true>, 2 * npairs, tc3::THREADS, smem, st, tmap, tmap2, p));
+  } else {
+    int grid = p.nprob * p.ntiles < nsm ? p.nprob * p.ntiles : nsm;
+    if (dual && (grid & 1)) --grid;                   // CTA parity selects the problem: both halves get the same CTA count
+    SELFC_CUDA(tc::launch_pdl(tc3::conv3x3_tc3_kernel<false>, grid, tc3::THREADS, smem, st, tmap, tmap2, p));
+  }
   SELFC_LAUNCH_CHECK("conv3x3_tc3_kernel");
   return 0;
 }

@@ -47,6 +47,7 @@ struct Params {
   int kps, nchunk, nacc;                      // K steps per stage, stages per frame, rolling accumulators
   int epi_quads;                              // 16-byte quads of epilogue operands staged per pixel-frame (Y2: 24, Y1: 1)
   int tiles_p, ntiles, tmem_cols;
+  int zrev;         // walk the pixel strips last-to-first (tc::next_direction)
   long long m_limit;   // rows (pixels) that really exist in the buffer
   int epi, rev, act;
   int in_slab;                                // input is a slab-planar dense buffer (common.cuh): 4-D TMA, SWIZZLE_32B sub-tiles
@@ -83,6 +84,7 @@ __device__ __forceinline__ void stage_epilogue_operands(const Params& p, int til
   int t2 = t + ahead, tile2 = tile;
   while (t2 >= p.T) { t2 -= p.T; tile2 += (int)gridDim.x; }
   if (tile2 < p.ntiles) {
+    if (p.zrev) tile2 = p.ntiles - 1 - tile2;
     const int b = tile2 / p.tiles_p;
     const int pix = (tile2 - b * p.tiles_p) * MT + row;
     if (pix < p.hw) {
@@ -239,7 +241,8 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       uint32_t ph = 0;
       long long w_prod = 0;
       const long long t_start = clock64();
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int tile_i = blockIdx.x; tile_i < p.ntiles; tile_i += gridDim.x) {
+        const int tile = p.zrev ? p.ntiles - 1 - tile_i : tile_i;
         const int b = tile / p.tiles_p;
         const int p0 = (tile - b * p.tiles_p) * MT;
         for (int f = 0; f < T; ++f) {
@@ -346,7 +349,8 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       stage_epilogue_operands(p, (int)blockIdx.x, 0, 1, row, Mtot, epi_base + (uint32_t)(p.epi_quads * MT + row) * 16u);
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile_i = blockIdx.x; tile_i < p.ntiles; tile_i += gridDim.x, ++it) {
+      const int tile = p.zrev ? p.ntiles - 1 - tile_i : tile_i;
       const int b = tile / p.tiles_p;
       const int pix = (tile - b * p.tiles_p) * MT + row;
       const bool valid = pix < p.hw;
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(aslot));
-        if (p.epi_quads) stage_epilogue_operands(p, tile, t, 2, row, Mtot, ebuf);
+        if (p.epi_quads) stage_epilogue_operands(p, tile_i, t, 2, row, Mtot, ebuf);
       }
     }
     if (p.epi_quads) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -733,6 +737,7 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
     p.dbg = slot;
   }
   if (p.ntiles == 0) return 0;
+  p.zrev = tc::next_direction();
   p.epi_quads = a.epi == EPI_COUPLE_Y2 ? 2 * kSQuads : (a.epi == EPI_COUPLE_HG ? kSQuads : (a.epi == EPI_COUPLE_Y1 ? 1 : 0));
   const int fixed = tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes * (hg ? 2 : 1) + 2 * p.epi_quads * tc5::MT * 16 + 1024;
   const int stage_bytes = kps * tc5::MT * 32;
