@@ -92,6 +92,13 @@ int selfc_frames_to_u8(const float* x, uint8_t* img, int N, int H, int W, void* 
 /* a1 FrequencyAnalyzer.forward(rev=False) :62-78 -> [N,51,h,w]; a10 rev=True :79-82 -> [N,3,H,W] */
 int selfc_fa_fwd(const float* x, float* out51, int N, int H, int W, void* stream);
 int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream);
+/* f3: the 2x operators of the sibling configurations.  FrequencyAnalyzer(k=2) of the compression model's rescaler half
+ * (SelfC_Codec_arch_inv.py:78-98): x [N,3,H,W] <-> [N,15,H/2,W/2].  HaarDownsampling of `model: SelfC` / IRN
+ * (SelfC_arch_inv.py:44-84, Inv_arch.py:44-84): x [N,C,H,W] <-> [N,4C,H/2,W/2], output channel k*C+c. */
+int selfc_fa2_fwd(const float* x, float* out15, int N, int H, int W, void* stream);
+int selfc_fa2_rev(const float* z15, float* y, int N, int h, int w, void* stream);
+int selfc_haar_fwd(const float* x, float* out, int N, int C, int H, int W, void* stream);
+int selfc_haar_rev(const float* z, float* y, int N, int C, int h, int w, void* stream);
 /* a4 Quantization.py:4-17 on [n] floats */
 int selfc_quantize(const float* x, uint8_t* q_u8, float* q_f32, size_t n, void* stream);
 /* caller-side neighbour of the path: LR_ref of `distortion: sr_bd`, models/Guassian.py:7-52 as called at

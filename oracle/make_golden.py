@@ -146,6 +146,24 @@ def case_u8(ref):
     np.savez_compressed(os.path.join(OUT, "u8.npz"), img=img, from_ref=from_ref.numpy(), y=y.numpy(), to_ref=to_ref)
 
 
+def case_2x(ref):
+    """f3: the 2x operators of the sibling configurations, from the reference's own modules."""
+    import models.modules.SelfC_arch_inv as haar_mod              # reference modules
+    import models.modules.SelfC_Codec_arch_inv as codec_mod
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(2, 3, 12, 20, generator=g)
+    z15 = torch.randn(2, 15, 6, 10, generator=g)
+    xh = torch.rand(2, 5, 8, 12, generator=g)
+    zh = torch.randn(2, 12, 4, 6, generator=g)
+    fa = codec_mod.FrequencyAnalyzer(3)                            # k defaults to 2
+    h3, h5 = haar_mod.HaarDownsampling(3), haar_mod.HaarDownsampling(5)
+    with torch.no_grad():
+        np.savez_compressed(os.path.join(OUT, "ops2x.npz"), x=x.numpy(), fa2_fwd=fa(x).numpy(), z15=z15.numpy(),
+                            fa2_rev=fa(z15, rev=True).numpy(), xh=xh.numpy(), haar5_fwd=h5(xh).numpy(),
+                            haar3_fwd=h3(x).numpy(), zh=zh.numpy(), haar3_rev=h3(zh, rev=True).numpy(),
+                            haar_state_keys=np.array(sorted(h3.state_dict().keys())))
+
+
 def case_train(ref, name, b, t, hh, ww, wseed, xseed):
     """One training step's losses and gradients from the reference's own modules (SelfC_model.py:148-170 restated with
     netG, Quantization, ReconstructionLoss and Guassian_downsample imported from the reference; SelfCModel itself needs
@@ -189,6 +207,7 @@ def main():
     case_fa(ref)
     case_metrics(ref)
     case_u8(ref)
+    case_2x(ref)
     case_net(ref, "net_t3", b=2, t=3, hh=32, ww=48, wseed=0, xseed=11)
     case_net(ref, "net_t7", b=1, t=7, hh=32, ww=40, wseed=1, xseed=12)
     # partial 8x16 output tiles, non-integral 32x32 pooling windows (h=10, w=18), larger weights

@@ -122,10 +122,11 @@ def make_eps(b: int, t: int, h: int, w: int, seed: int) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # A.1 FrequencyAnalyzer  (models/modules/SelfC_GMM_arch_inv.py:46-82)
 # --------------------------------------------------------------------------------------
-def fa_forward(x: torch.Tensor) -> torch.Tensor:
+def fa_forward(x: torch.Tensor, SCALE: int = SCALE) -> torch.Tensor:
     """``[N,3,H,W] -> [N,51,H/4,W/4]``: 4x4 box mean + unshuffled residual.
 
     HF channel = (sy*4+sx)*3 + c  (local PixelUnshuffle, :46-60, used at :75-78).
+    SCALE=2 is the compression model's analyzer (SelfC_Codec_arch_inv.py:78-94): ``-> [N,15,H/2,W/2]``.
     """
     n, c, hh, ww = x.shape
     h, w = hh // SCALE, ww // SCALE
@@ -142,16 +143,43 @@ def fa_forward(x: torch.Tensor) -> torch.Tensor:
     return torch.cat([lf, hf], dim=1)
 
 
-def fa_reverse(z: torch.Tensor) -> torch.Tensor:
+def fa_reverse(z: torch.Tensor, SCALE: int = SCALE) -> torch.Tensor:
     """``[N,51,h,w] -> [N,3,4h,4w]``; HF channel = c*16 + sy*4 + sx (nn.PixelShuffle, :70,:79-82).
 
     NOT the inverse of fa_forward's channel order - replicated on purpose.
+    SCALE=2: ``[N,15,h,w] -> [N,3,2h,2w]`` (SelfC_Codec_arch_inv.py:95-98).
     """
     n, _, h, w = z.shape
     lf = z[:, :3]
     hf = z[:, 3:].reshape(n, 3, SCALE, SCALE, h, w)
     out = lf[:, :, :, None, :, None] + hf.permute(0, 1, 4, 2, 5, 3)
     return out.reshape(n, 3, h * SCALE, w * SCALE)
+
+
+# --------------------------------------------------------------------------------------
+# F.3 HaarDownsampling  (models/modules/SelfC_arch_inv.py:44-84; Inv_arch.py:44-84 is the same class)
+# --------------------------------------------------------------------------------------
+_HAAR_SIGNS = ((1, 1, 1, 1), (1, -1, 1, -1), (1, 1, -1, -1), (1, -1, -1, 1))   # w_k over (a, b, c, d) = x[0,0], x[0,1], x[1,0], x[1,1]
+
+
+def haar_forward(x: torch.Tensor) -> torch.Tensor:
+    """``[N,C,H,W] -> [N,4C,H/2,W/2]``: grouped 2x2 stride-2 conv with the +-1 Haar weights (:50-60), ``/ 4.0``, then the
+    ``reshape [N,C,4,..] -> transpose(1,2)`` of :70-73, i.e. output channel ``k*C + c``."""
+    a, b, c, d = x[:, :, 0::2, 0::2], x[:, :, 0::2, 1::2], x[:, :, 1::2, 0::2], x[:, :, 1::2, 1::2]
+    outs = [(((sa * a + sb * b) + sc * c) + sd * d) / 4.0 for sa, sb, sc, sd in _HAAR_SIGNS]
+    return torch.cat(outs, dim=1)
+
+
+def haar_reverse(z: torch.Tensor) -> torch.Tensor:
+    """``[N,4C,h,w] -> [N,C,2h,2w]``: conv_transpose2d with the same weights, no scaling (:79-82)."""
+    n, c4, h, w = z.shape
+    cch = c4 // 4
+    zk = [z[:, k * cch:(k + 1) * cch] for k in range(4)]
+    y = torch.empty(n, cch, 2 * h, 2 * w, dtype=z.dtype)
+    for pos, (dy, dx) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        s = [_HAAR_SIGNS[k][pos] for k in range(4)]
+        y[:, :, dy::2, dx::2] = ((s[0] * zk[0] + s[1] * zk[1]) + s[2] * zk[2]) + s[3] * zk[3]
+    return y
 
 
 # --------------------------------------------------------------------------------------

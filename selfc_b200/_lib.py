@@ -31,6 +31,10 @@ SIGNATURES = {
     "selfc_frames_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa_rev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "selfc_fa2_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "selfc_fa2_rev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "selfc_haar_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "selfc_haar_rev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "selfc_quantize": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "selfc_gaussian_down": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "selfc_d2dt": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),

@@ -61,13 +61,47 @@ class InvBlockExp(nn.Module):
 
 
 class FrequencyAnalyzer(nn.Module):
-    """4x4 box-mean LF + pixel-unshuffled residual HF (:62-82); usable on its own."""
+    """k x k box-mean LF + pixel-unshuffled residual HF; usable on its own.  k=4: the rescaler's
+    (SelfC_GMM_arch_inv.py:62-82); k=2: the compression model's (SelfC_Codec_arch_inv.py:78-98, its default)."""
 
-    def __init__(self, channel_in=3):
+    def __init__(self, channel_in=3, k=4):
         super().__init__()
+        if channel_in != 3 or k not in (2, 4):
+            raise NotImplementedError("FrequencyAnalyzer is built for 3 channels and k in {2, 4}")
+        self.k = k
 
     def forward(self, x, rev=False):
-        return _engine.fa_reverse(x) if rev else _engine.fa_forward(x)
+        return _engine.fa_reverse(x, self.k) if rev else _engine.fa_forward(x, self.k)
+
+
+class HaarDownsampling(nn.Module):
+    """Orthogonal 2x2 Haar split of `model: SelfC` / IRN (SelfC_arch_inv.py:44-84, Inv_arch.py:44-84).  `haar_weights` is kept
+    as the reference's frozen parameter so that state_dicts stay interchangeable; the kernels hard-code its +-1 pattern."""
+
+    def __init__(self, channel_in):
+        super().__init__()
+        self.channel_in = channel_in
+        w = torch.ones(4, 1, 2, 2)
+        w[1, 0, 0, 1] = -1
+        w[1, 0, 1, 1] = -1
+        w[2, 0, 1, 0] = -1
+        w[2, 0, 1, 1] = -1
+        w[3, 0, 1, 0] = -1
+        w[3, 0, 0, 1] = -1
+        self.haar_weights = nn.Parameter(torch.cat([w] * channel_in, 0), requires_grad=False)
+        self.last_jac = 0.0
+
+    def forward(self, x, rev=False):
+        import math
+        elements = x.shape[1] * x.shape[2] * x.shape[3]
+        if not rev:
+            self.last_jac = elements / 4 * math.log(1 / 16.)
+            return _engine.haar_forward(x)
+        self.last_jac = elements / 4 * math.log(16.)
+        return _engine.haar_reverse(x)
+
+    def jacobian(self, x, rev=False):
+        return self.last_jac
 
 
 class GlobalAgg(nn.Module):

@@ -184,6 +184,105 @@ __global__ void __launch_bounds__(256) frames_to_u8_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------------
+// 2x variants.  FrequencyAnalyzer(k=2) of the compression model's rescaler half
+// (SelfC_Codec_arch_inv.py:78-98): [N,3,H,W] <-> [N,15,H/2,W/2], same structure as the 4x one (2x2 box mean + residual;
+// forward HF channel = (sy*2+sx)*3+c, reverse = c*4+sy*2+sx).  HaarDownsampling of `model: SelfC` / IRN
+// (SelfC_arch_inv.py:44-84): grouped 2x2 stride-2 conv with +-1 weights, /4, channel k*C+c; the reverse is the transposed
+// conv with the same weights and no scaling.  One thread per output LR pixel (x channel for Haar).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fa2_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int h, int w) {
+  const long long M = (long long)N * h * w;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int j = (int)(m % w), i = (int)((m / w) % h), n = (int)(m / ((long long)w * h));
+  const int W = 2 * w, H = 2 * h;
+  const long long hw = (long long)h * w;
+  float* o = out + (long long)n * 15 * hw + (long long)i * w + j;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* src = x + (((long long)n * 3 + c) * H + 2 * i) * W + 2 * j;
+    const float2 r0 = __ldg(reinterpret_cast<const float2*>(src));
+    const float2 r1 = __ldg(reinterpret_cast<const float2*>(src + W));
+    const float lf = (((r0.x + r0.y) + r1.x) + r1.y) / 4.0f;       // row-major accumulation, as adaptive_avg_pool2d
+    o[c * hw] = lf;
+    o[(3 + 0 * 3 + c) * hw] = r0.x - lf;
+    o[(3 + 1 * 3 + c) * hw] = r0.y - lf;
+    o[(3 + 2 * 3 + c) * hw] = r1.x - lf;
+    o[(3 + 3 * 3 + c) * hw] = r1.y - lf;
+  }
+}
+
+__global__ void __launch_bounds__(256) fa2_rev_kernel(const float* __restrict__ z, float* __restrict__ y, int N, int h, int w) {
+  const long long M = (long long)N * h * w;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int j = (int)(m % w), i = (int)((m / w) % h), n = (int)(m / ((long long)w * h));
+  const int W = 2 * w, H = 2 * h;
+  const long long hw = (long long)h * w;
+  const float* src = z + (long long)n * 15 * hw + (long long)i * w + j;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float lf = __ldg(src + c * hw);
+    float* dst = y + (((long long)n * 3 + c) * H + 2 * i) * W + 2 * j;
+    *reinterpret_cast<float2*>(dst) = make_float2(lf + __ldg(src + (3 + c * 4 + 0) * hw), lf + __ldg(src + (3 + c * 4 + 1) * hw));
+    *reinterpret_cast<float2*>(dst + W) = make_float2(lf + __ldg(src + (3 + c * 4 + 2) * hw), lf + __ldg(src + (3 + c * 4 + 3) * hw));
+  }
+}
+
+// Haar weights w_k[dy][dx]: k=0 all +1; k=1 -1 on dx=1; k=2 -1 on dy=1; k=3 -1 on the anti-diagonal
+__global__ void __launch_bounds__(256) haar_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C, int h, int w) {
+  const long long M = (long long)N * C * h * w;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int j = (int)(m % w), i = (int)((m / w) % h);
+  const int c = (int)((m / ((long long)w * h)) % C), n = (int)(m / ((long long)w * h * C));
+  const int W = 2 * w;
+  const long long hw = (long long)h * w;
+  const float* src = x + (((long long)n * C + c) * 2 * h + 2 * i) * W + 2 * j;
+  const float2 r0 = __ldg(reinterpret_cast<const float2*>(src));
+  const float2 r1 = __ldg(reinterpret_cast<const float2*>(src + W));
+  const float a = r0.x, b = r0.y, cc = r1.x, d = r1.y;
+  float* o = out + ((long long)n * 4 * C + c) * hw + (long long)i * w + j;
+  o[0] = (((a + b) + cc) + d) / 4.0f;
+  o[(long long)C * hw] = (((a - b) + cc) - d) / 4.0f;
+  o[2LL * C * hw] = (((a + b) - cc) - d) / 4.0f;
+  o[3LL * C * hw] = (((a - b) - cc) + d) / 4.0f;
+}
+
+__global__ void __launch_bounds__(256) haar_rev_kernel(const float* __restrict__ z, float* __restrict__ y, int N, int C, int h, int w) {
+  const long long M = (long long)N * C * h * w;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int j = (int)(m % w), i = (int)((m / w) % h);
+  const int c = (int)((m / ((long long)w * h)) % C), n = (int)(m / ((long long)w * h * C));
+  const int W = 2 * w;
+  const long long hw = (long long)h * w;
+  const float* src = z + ((long long)n * 4 * C + c) * hw + (long long)i * w + j;
+  const float z0 = __ldg(src), z1 = __ldg(src + (long long)C * hw), z2 = __ldg(src + 2LL * C * hw), z3 = __ldg(src + 3LL * C * hw);
+  float* dst = y + (((long long)n * C + c) * 2 * h + 2 * i) * W + 2 * j;
+  *reinterpret_cast<float2*>(dst) = make_float2(((z0 + z1) + z2) + z3, ((z0 - z1) + z2) - z3);
+  *reinterpret_cast<float2*>(dst + W) = make_float2(((z0 + z1) - z2) - z3, ((z0 - z1) - z2) + z3);
+}
+
+int launch_fa2(const float* in, float* out, bool rev, int N, int h, int w, cudaStream_t st) {
+  const long long M = (long long)N * h * w;
+  if (M == 0) return 0;
+  if (rev) fa2_rev_kernel<<<cdiv(M, 256), 256, 0, st>>>(in, out, N, h, w);
+  else fa2_fwd_kernel<<<cdiv(M, 256), 256, 0, st>>>(in, out, N, h, w);
+  SELFC_LAUNCH_CHECK("fa2_kernel");
+  return 0;
+}
+
+int launch_haar(const float* in, float* out, bool rev, int N, int C, int h, int w, cudaStream_t st) {
+  const long long M = (long long)N * C * h * w;
+  if (M == 0) return 0;
+  if (rev) haar_rev_kernel<<<cdiv(M, 256), 256, 0, st>>>(in, out, N, C, h, w);
+  else haar_fwd_kernel<<<cdiv(M, 256), 256, 0, st>>>(in, out, N, C, h, w);
+  SELFC_LAUNCH_CHECK("haar_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Quantisation (Quantization.py:9-12): round-half-even of clamp(x,0,1)*255.
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float quant_code(float v) {

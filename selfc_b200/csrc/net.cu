@@ -811,6 +811,34 @@ int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream) 
   return launch_fa_rev(z51, true, y, N, h, w, (cudaStream_t)stream);
 }
 
+int selfc_fa2_fwd(const float* x, float* out15, int N, int H, int W, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "fa2_fwd: N=%d H=%d W=%d", N, H, W);
+  if (N == 0) return 0;
+  SELFC_CHECK_ARG(x && out15 && ((uintptr_t)x & 7) == 0, "fa2_fwd: null or misaligned pointer");
+  return launch_fa2(x, out15, false, N, H / 2, W / 2, (cudaStream_t)stream);
+}
+
+int selfc_fa2_rev(const float* z15, float* y, int N, int h, int w, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && h >= 1 && w >= 1, "fa2_rev: N=%d h=%d w=%d", N, h, w);
+  if (N == 0) return 0;
+  SELFC_CHECK_ARG(z15 && y && ((uintptr_t)y & 7) == 0, "fa2_rev: null or misaligned pointer");
+  return launch_fa2(z15, y, true, N, h, w, (cudaStream_t)stream);
+}
+
+int selfc_haar_fwd(const float* x, float* out, int N, int C, int H, int W, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && C >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "haar_fwd: N=%d C=%d H=%d W=%d", N, C, H, W);
+  if (N == 0) return 0;
+  SELFC_CHECK_ARG(x && out && ((uintptr_t)x & 7) == 0, "haar_fwd: null or misaligned pointer");
+  return launch_haar(x, out, false, N, C, H / 2, W / 2, (cudaStream_t)stream);
+}
+
+int selfc_haar_rev(const float* z, float* y, int N, int C, int h, int w, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && C >= 1 && h >= 1 && w >= 1, "haar_rev: N=%d C=%d h=%d w=%d", N, C, h, w);
+  if (N == 0) return 0;
+  SELFC_CHECK_ARG(z && y && ((uintptr_t)y & 7) == 0, "haar_rev: null or misaligned pointer");
+  return launch_haar(z, y, true, N, C, h, w, (cudaStream_t)stream);
+}
+
 int selfc_gaussian_down(const float* x, const float* k13, float* y, int N, int C, int H, int W, void* stream) {
   SELFC_CHECK_ARG(x && k13 && y, "gaussian_down: null pointer");
   SELFC_CHECK_ARG(N >= 0 && C >= 1 && H >= 16 && W >= 16 && H % 4 == 0 && W % 4 == 0, "gaussian_down: N=%d C=%d H=%d W=%d", N, C, H, W);

@@ -504,23 +504,65 @@ def _dev_check(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.float32).contiguous()
 
 
-def fa_forward(x: torch.Tensor) -> torch.Tensor:
+def fa_forward(x: torch.Tensor, k: int = 4) -> torch.Tensor:
+    """FrequencyAnalyzer.forward(rev=False): k=4 the rescaler's (SelfC_GMM_arch_inv.py:62-78), k=2 the codec model's
+    (SelfC_Codec_arch_inv.py:78-94)."""
     x = _dev_check(x)
     n, c, hh, ww = x.shape
+    if k == 2:
+        if c != 3 or hh % 2 or ww % 2:
+            raise ValueError(f"fa_forward(k=2) expects [N,3,H,W] with even H,W, got {tuple(x.shape)}")
+        out = torch.empty((n, 15, hh // 2, ww // 2), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().selfc_fa2_fwd(_ptr(x), _ptr(out), n, hh, ww, _stream(x.device)), "fa2_fwd")
+        return out
+    if k != 4:
+        raise ValueError("FrequencyAnalyzer is built for k=4 and k=2")
     out = torch.empty((n, 51, hh // 4, ww // 4), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().selfc_fa_fwd(_ptr(x), _ptr(out), n, hh, ww, _stream(x.device)), "fa_fwd")
     return out
 
 
-def fa_reverse(z: torch.Tensor) -> torch.Tensor:
+def fa_reverse(z: torch.Tensor, k: int = 4) -> torch.Tensor:
     z = _dev_check(z)
     n, c, h, w = z.shape
+    if k == 2:
+        if c != 15:
+            raise ValueError("fa_reverse(k=2) expects 15 channels")
+        y = torch.empty((n, 3, 2 * h, 2 * w), dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            _lib.check(_lib.lib().selfc_fa2_rev(_ptr(z), _ptr(y), n, h, w, _stream(z.device)), "fa2_rev")
+        return y
     if c != 51:
         raise ValueError("fa_reverse expects 51 channels")
     y = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=z.device)
     with torch.cuda.device(z.device):
         _lib.check(_lib.lib().selfc_fa_rev(_ptr(z), _ptr(y), n, h, w, _stream(z.device)), "fa_rev")
+    return y
+
+
+def haar_forward(x: torch.Tensor) -> torch.Tensor:
+    """HaarDownsampling.forward(rev=False) (SelfC_arch_inv.py:66-74): [N,C,H,W] -> [N,4C,H/2,W/2]."""
+    x = _dev_check(x)
+    n, c, hh, ww = x.shape
+    if hh % 2 or ww % 2:
+        raise ValueError(f"haar_forward expects even H,W, got {tuple(x.shape)}")
+    out = torch.empty((n, 4 * c, hh // 2, ww // 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().selfc_haar_fwd(_ptr(x), _ptr(out), n, c, hh, ww, _stream(x.device)), "haar_fwd")
+    return out
+
+
+def haar_reverse(z: torch.Tensor) -> torch.Tensor:
+    """HaarDownsampling.forward(rev=True) (:75-82): [N,4C,h,w] -> [N,C,2h,2w]."""
+    z = _dev_check(z)
+    n, c4, h, w = z.shape
+    if c4 % 4:
+        raise ValueError("haar_reverse expects a multiple of 4 channels")
+    y = torch.empty((n, c4 // 4, 2 * h, 2 * w), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().selfc_haar_rev(_ptr(z), _ptr(y), n, c4 // 4, h, w, _stream(z.device)), "haar_rev")
     return y
 
 

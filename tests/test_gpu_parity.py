@@ -512,6 +512,35 @@ def test_u8_errors_are_loud(dev):
         eng.down_u8(torch.zeros(3, 32, 48, 3, dtype=torch.uint8), 3)                  # host tensor: no CPU path
 
 
+# ------------------------------------------------------------------------------------------------ f3: 2x operators
+def test_2x_operators_bit_exact(dev, golden_dir):
+    """FrequencyAnalyzer(k=2) and HaarDownsampling kernels against the reference's modules (fixture) and the oracle."""
+    from selfc_b200 import engine
+    from selfc_b200.arch import FrequencyAnalyzer, HaarDownsampling
+    g = np.load(os.path.join(golden_dir, "ops2x.npz"))
+    fa2 = FrequencyAnalyzer(3, k=2)
+    assert np.array_equal(fa2(_t(g["x"]).to(dev)).cpu().numpy(), g["fa2_fwd"])
+    assert np.array_equal(fa2(_t(g["z15"]).to(dev), rev=True).cpu().numpy(), g["fa2_rev"])
+    h3, h5 = HaarDownsampling(3).to(dev), HaarDownsampling(5).to(dev)
+    assert sorted(h3.state_dict().keys()) == [str(k) for k in g["haar_state_keys"]]
+    assert np.array_equal(h3(_t(g["x"]).to(dev)).cpu().numpy(), g["haar3_fwd"])
+    assert np.array_equal(h5(_t(g["xh"]).to(dev)).cpu().numpy(), g["haar5_fwd"])
+    assert np.array_equal(h3(_t(g["zh"]).to(dev), rev=True).cpu().numpy(), g["haar3_rev"])
+    gen = torch.Generator().manual_seed(41)
+    x = torch.rand(3, 3, 270, 482, generator=gen)
+    assert torch.equal(engine.fa_forward(x.to(dev), 2).cpu(), so.fa_forward(x, 2))
+    assert torch.equal(engine.haar_forward(x.to(dev)).cpu(), so.haar_forward(x))
+    z = torch.randn(2, 15, 33, 47, generator=gen)
+    assert torch.equal(engine.fa_reverse(z.to(dev), 2).cpu(), so.fa_reverse(z, 2))
+    zh = torch.randn(2, 28, 33, 47, generator=gen)
+    assert torch.equal(engine.haar_reverse(zh.to(dev)).cpu(), so.haar_reverse(zh))
+    assert engine.haar_forward(torch.zeros(0, 3, 4, 4, device=dev)).shape == (0, 12, 2, 2)
+    with pytest.raises(ValueError):
+        engine.haar_forward(torch.zeros(1, 3, 5, 4, device=dev))
+    with pytest.raises(ValueError):
+        engine.fa_forward(torch.zeros(1, 3, 6, 6, device=dev), 3)
+
+
 # ------------------------------------------------------------------------------------------------ a13 building blocks (training step)
 @pytest.mark.parametrize("prefix,cin,cout", [("operations.2.F", 48, 3), ("operations.6.G", 3, 48), ("stp_net.local_m2", 64, 64)])
 def test_d2dt_backward_vs_autograd(dev, prefix, cin, cout):
