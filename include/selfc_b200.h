@@ -92,6 +92,14 @@ int selfc_frames_to_u8(const float* x, uint8_t* img, int N, int H, int W, void* 
 /* a1 FrequencyAnalyzer.forward(rev=False) :62-78 -> [N,51,h,w]; a10 rev=True :79-82 -> [N,3,H,W] */
 int selfc_fa_fwd(const float* x, float* out51, int N, int H, int W, void* stream);
 int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream);
+/* f1: validation metrics (train.py:28-86 cal_metric).  rgb_to_ycbcr (data/util.py:239-245): x [N,3,H,W] -> y [N,1,H,W].
+ * frame_metrics: per frame n, sse[n] = sum (a-b)^2 and ssim_sum[n] = sum of the SSIM map (utils/util.py:361-488: 11-tap
+ * window win11, valid convolution, K1 .01, K2 .03, data_range 1) over C channels, or over the BT.601 luma when to_y != 0
+ * (C must be 3).  Outputs are fp64 device arrays of N; ssim_sum may be NULL.  PSNR = 20 log10(1/sqrt(sse / count)),
+ * SSIM = ssim_sum / (Ceff (H-10) (W-10)) are left to the caller (utils/util.py:198-221, :596-603). */
+int selfc_rgb_to_y(const float* x, float* y, int N, int H, int W, void* stream);
+int selfc_frame_metrics(const float* a, const float* b, int N, int C, int H, int W, int to_y, const float* win11,
+                        double* sse, double* ssim_sum, void* stream);
 /* f3: the 2x operators of the sibling configurations.  FrequencyAnalyzer(k=2) of the compression model's rescaler half
  * (SelfC_Codec_arch_inv.py:78-98): x [N,3,H,W] <-> [N,15,H/2,W/2].  HaarDownsampling of `model: SelfC` / IRN
  * (SelfC_arch_inv.py:44-84, Inv_arch.py:44-84): x [N,C,H,W] <-> [N,4C,H/2,W/2], output channel k*C+c. */

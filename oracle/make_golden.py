@@ -164,6 +164,21 @@ def case_2x(ref):
                             haar_state_keys=np.array(sorted(h3.state_dict().keys())))
 
 
+def case_sampler(ref):
+    """f4: index streams of the reference's DistIterSampler (data/data_sampler.py) for a few (size, world, ratio, epoch)."""
+    from data.data_sampler import DistIterSampler              # reference module
+    out = {}
+    for size, world, ratio in ((37, 3, 4), (64, 2, 200), (5, 4, 1)):
+        ds = list(range(size))
+        for rank in range(world):
+            smp = DistIterSampler(ds, world, rank, ratio)
+            for epoch in (0, 3):
+                smp.set_epoch(epoch)
+                out[f"s{size}_w{world}_r{ratio}_k{rank}_e{epoch}"] = np.array(list(iter(smp)), dtype=np.int32)
+                out[f"s{size}_w{world}_r{ratio}_k{rank}_len"] = np.int64(len(smp))
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), torch_version=np.array(torch.__version__), **out)
+
+
 def case_train(ref, name, b, t, hh, ww, wseed, xseed):
     """One training step's losses and gradients from the reference's own modules (SelfC_model.py:148-170 restated with
     netG, Quantization, ReconstructionLoss and Guassian_downsample imported from the reference; SelfCModel itself needs
@@ -208,6 +223,7 @@ def main():
     case_metrics(ref)
     case_u8(ref)
     case_2x(ref)
+    case_sampler(ref)
     case_net(ref, "net_t3", b=2, t=3, hh=32, ww=48, wseed=0, xseed=11)
     case_net(ref, "net_t7", b=1, t=7, hh=32, ww=40, wseed=1, xseed=12)
     # partial 8x16 output tiles, non-integral 32x32 pooling windows (h=10, w=18), larger weights

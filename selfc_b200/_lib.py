@@ -31,6 +31,8 @@ SIGNATURES = {
     "selfc_frames_to_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa_rev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "selfc_rgb_to_y": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "selfc_frame_metrics": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "selfc_fa2_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_fa2_rev": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "selfc_haar_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -14,6 +14,11 @@ int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w,
 // 2x variants (f3): FrequencyAnalyzer(k=2) [N,3,2h,2w] <-> [N,15,h,w]; HaarDownsampling [N,C,2h,2w] <-> [N,4C,h,w]
 int launch_fa2(const float* in, float* out, bool rev, int N, int h, int w, cudaStream_t st);
 int launch_haar(const float* in, float* out, bool rev, int N, int C, int h, int w, cudaStream_t st);
+// validation metrics (metrics.cu): BT.601 luma; per-frame sum of squared errors and sum of the SSIM map (fp64), to_y = convert
+// the 3-channel inputs to luma on load
+int launch_rgb_to_y(const float* x, float* y, long long N, long long HW, cudaStream_t st);
+int launch_frame_metrics(const float* a, const float* b, int N, int C, int H, int W, int to_y, const float* win11, double* sse,
+                         double* ssim_sum, cudaStream_t st);
 // 8-bit frames in cv2 layout [N][H][W][3] (B,G,R): fused into the FrequencyAnalyzer kernels (HR side) and stand-alone
 template <typename T>
 int launch_fa_fwd_z_u8(const uint8_t* x, float* z, T* fbuf, int fpitch, long long fslabM, int N, int h, int w, cudaStream_t st);

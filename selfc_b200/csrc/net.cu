@@ -811,6 +811,21 @@ int selfc_fa_rev(const float* z51, float* y, int N, int h, int w, void* stream) 
   return launch_fa_rev(z51, true, y, N, h, w, (cudaStream_t)stream);
 }
 
+int selfc_rgb_to_y(const float* x, float* y, int N, int H, int W, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && (N == 0 || (x && y)), "rgb_to_y: null pointer or N=%d H=%d W=%d", N, H, W);
+  return launch_rgb_to_y(x, y, N, (long long)H * W, (cudaStream_t)stream);
+}
+
+int selfc_frame_metrics(const float* a, const float* b, int N, int C, int H, int W, int to_y, const float* win11, double* sse,
+                        double* ssim_sum, void* stream) {
+  SELFC_CHECK_ARG(N >= 0 && C >= 1 && H >= 1 && W >= 1, "frame_metrics: N=%d C=%d H=%d W=%d", N, C, H, W);
+  if (N == 0) return 0;
+  SELFC_CHECK_ARG(a && b && sse, "frame_metrics: null pointer");
+  SELFC_CHECK_ARG(!to_y || C == 3, "frame_metrics: luma conversion needs 3 channels, got %d", C);
+  SELFC_CHECK_ARG(ssim_sum == nullptr || (win11 != nullptr && H >= 11 && W >= 11), "frame_metrics: SSIM needs an 11-tap window and H,W >= 11");
+  return launch_frame_metrics(a, b, N, C, H, W, to_y, win11, sse, ssim_sum, (cudaStream_t)stream);
+}
+
 int selfc_fa2_fwd(const float* x, float* out15, int N, int H, int W, void* stream) {
   SELFC_CHECK_ARG(N >= 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "fa2_fwd: N=%d H=%d W=%d", N, H, W);
   if (N == 0) return 0;

@@ -82,6 +82,59 @@ class SelfCModel:
         sd = OrderedDict((k, v.detach().cpu()) for k, v in self.netG.module.state_dict().items())
         torch.save(sd, save_path)
 
+    def save(self, iter_label):
+        """SelfC_model.py:318-319 / base_model.py:77-85: `<models>/<iter>_G.pth`."""
+        import os
+        os.makedirs(self.opt["path"]["models"], exist_ok=True)
+        path = os.path.join(self.opt["path"]["models"], "{}_{}.pth".format(iter_label, "G"))
+        self.save_network(path)
+        return path
+
+    # ---- training state: base_model.py:109-133 -----------------------------------------------------------------
+    def training_state(self, epoch, iter_step):
+        """The dict the reference saves: epoch, iter, one scheduler and one optimizer state.  The optimizer entry has
+        torch.optim.Adam's state_dict layout (per-parameter step / exp_avg / exp_avg_sq in named_parameters order), so the
+        file loads into the reference's own optimizer as well."""
+        tr = self.trainer
+        offs = tr._offsets.tolist()
+        state = {}
+        for i, p in enumerate(tr.params):
+            state[i] = {"step": torch.tensor(float(tr.step_count)),
+                        "exp_avg": tr.m[offs[i]:offs[i + 1]].view(p.shape).detach().cpu().clone(),
+                        "exp_avg_sq": tr.v[offs[i]:offs[i + 1]].view(p.shape).detach().cpu().clone()}
+        group = {"lr": self.cur_lr, "betas": tuple(tr.betas), "eps": tr.eps, "weight_decay": tr.weight_decay, "amsgrad": False,
+                 "initial_lr": float(self.train_opt["lr_G"]), "params": list(range(len(tr.params)))}
+        sched = {"last_epoch": int(iter_step), "milestones": list(self.train_opt["lr_steps"] or []),
+                 "gamma": float(self.train_opt["lr_gamma"] or 1.0)}
+        return {"epoch": epoch, "iter": iter_step, "schedulers": [sched], "optimizers": [{"state": state, "param_groups": [group]}]}
+
+    def save_training_state(self, epoch, iter_step):
+        import os
+        os.makedirs(self.opt["path"]["training_state"], exist_ok=True)
+        path = os.path.join(self.opt["path"]["training_state"], "{}.state".format(iter_step))
+        torch.save(self.training_state(epoch, iter_step), path)
+        return path
+
+    def resume_training(self, resume_state):
+        """Restore the Adam moments, step count and learning rate.  (The reference's body is commented out,
+        base_model.py:122-133, so its resume silently restarts the optimiser; the network weights come from
+        path.pretrain_model_G in both.)"""
+        tr = self.trainer
+        opt_state = resume_state["optimizers"][0]
+        offs = tr._offsets.tolist()
+        if len(opt_state["state"]) != len(tr.params):
+            raise ValueError("Wrong lengths of optimizers")
+        steps = set()
+        for i, p in enumerate(tr.params):
+            st = opt_state["state"][i]
+            tr.m[offs[i]:offs[i + 1]].view(p.shape).copy_(st["exp_avg"])
+            tr.v[offs[i]:offs[i + 1]].view(p.shape).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) != 1:
+            raise ValueError("per-parameter Adam step counts differ")
+        tr.step_count = steps.pop()
+        self.cur_lr = float(opt_state["param_groups"][0]["lr"])
+
     # ---- feed_data: SelfC_model.py:93-132 -----------------------------------------------------------------
     def feed_data(self, data):
         real = data["GT"]                                   # [B,3,t,H,W]

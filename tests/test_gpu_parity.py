@@ -512,6 +512,87 @@ def test_u8_errors_are_loud(dev):
         eng.down_u8(torch.zeros(3, 32, 48, 3, dtype=torch.uint8), 3)                  # host tensor: no CPU path
 
 
+# ------------------------------------------------------------------------------------------------ f1: metrics kernels
+def test_metrics_kernels_vs_reference_fixture_and_oracle(dev, golden_dir):
+    """rgb_to_ycbcr bit-exact; PSNR within 1e-3 dB and SSIM within 1e-5 of the reference's own functions (fixture) and of the
+    oracle on a larger odd-sized clip, RGB and fused-luma variants (north star: 0.01 dB / 1e-4)."""
+    from selfc_b200 import metrics
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    a, b = _t(g["a"]), _t(g["b"])
+    ya = metrics.rgb_to_ycbcr(a.to(dev))
+    assert torch.equal(ya.cpu(), so.rgb_to_y(a))
+    np.testing.assert_allclose(ya.cpu().numpy(), g["ya"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(metrics.calculate_psnr(a.to(dev), b.to(dev), to_y=True), g["psnr"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(metrics.calculate_ssim(a.to(dev), b.to(dev), to_y=True), g["ssim"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(metrics.calculate_ssim(ya, metrics.rgb_to_ycbcr(b.to(dev))), g["ssim"], rtol=0, atol=1e-5)
+    assert metrics.calculate_psnr(a.to(dev), a.to(dev)) == float("inf")
+    gen = torch.Generator().manual_seed(77)
+    x = torch.rand(3, 3, 75, 133, generator=gen)
+    y = (x + 0.03 * torch.randn(x.shape, generator=gen)).clamp(0, 1)
+    np.testing.assert_allclose(metrics.calculate_psnr(x.to(dev), y.to(dev)), so.psnr_frames(x, y), rtol=0, atol=1e-3)
+    ref_rgb = [float(np.mean([so.ssim_frames(x[i:i + 1, c:c + 1], y[i:i + 1, c:c + 1])[0] for c in range(3)])) for i in range(3)]
+    np.testing.assert_allclose(metrics.calculate_ssim(x.to(dev), y.to(dev)), ref_rgb, rtol=0, atol=1e-5)
+    cm = metrics.clip_metrics(x.to(dev), y.to(dev), x[:, :, :32, :40].to(dev), y[:, :, :32, :40].to(dev))
+    assert sorted(cm) == ["lr_psnr", "lr_psnr_y", "lr_ssim", "lr_ssim_y", "psnr", "psnr_y", "ssim", "ssim_y"]
+    np.testing.assert_allclose(cm["psnr_y"], so.psnr_frames(so.rgb_to_y(x), so.rgb_to_y(y)), rtol=0, atol=1e-3)
+    np.testing.assert_allclose(cm["ssim_y"], so.ssim_frames(so.rgb_to_y(x), so.rgb_to_y(y)), rtol=0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ f4: checkpoint / resume
+def test_training_state_roundtrip_and_resume(dev, tmp_path):
+    """train 2 steps -> save model + .state -> fresh model resumes -> step 3 equals the uninterrupted run's step 3 (losses and
+    weights to float-atomics noise); the .state optimizer entry loads into torch.optim.Adam (the reference's optimizer)."""
+    from selfc_b200 import options, train_loop
+    from selfc_b200.model import create_model
+    from selfc_b200.global_var import GlobalVar
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    yml = os.path.join(here, "selfc_b200", "configs", "selfc_large_train_synthetic.yml")
+
+    def make(pretrain=None):
+        opt = options.parse(yml, is_train=True)
+        opt["path"]["models"] = str(tmp_path / "models")
+        opt["path"]["training_state"] = str(tmp_path / "training_state")
+        opt["path"]["pretrain_model_G"] = pretrain
+        opt["logger"] = {"print_freq": 1, "save_checkpoint_freq": 2}
+        opt["train"]["niter"] = 3
+        opt = options.dict_to_nonedict(opt)
+        torch.manual_seed(5)
+        m = create_model(opt)
+        m.netG.module.set_noise(11, 0)
+        return opt, m
+
+    t = 3
+    GlobalVar.set_Temporal_LEN(t)
+    ds = train_loop.SyntheticClips(n=3, t=t, size=32, seed=2)
+    loader = [{"GT": ds[i]["GT"][None]} for i in range(3)]
+    opt, m_full = make()
+    sd0 = {k: v.detach().clone() for k, v in m_full.netG.module.state_dict().items()}
+    assert train_loop.train(opt, m_full, loader, total_epochs=0, rank=0) == 3
+    log_full = dict(m_full.get_current_log())
+    assert os.path.exists(tmp_path / "models" / "2_G.pth") and os.path.exists(tmp_path / "training_state" / "2.state")
+    state = torch.load(tmp_path / "training_state" / "2.state", weights_only=False)
+    assert state["iter"] == 2 and state["epoch"] == 0 and len(state["optimizers"][0]["state"]) == len(m_full.trainer.params) == 354
+    # the optimizer entry is a valid torch.optim.Adam state_dict for the same parameter list
+    ref_params = [torch.nn.Parameter(p.detach().cpu().clone()) for p in m_full.trainer.params]
+    adam = torch.optim.Adam(ref_params, lr=1e-4)
+    adam.load_state_dict(state["optimizers"][0])
+    assert float(adam.state[ref_params[0]]["step"]) == 2.0
+    # resume: fresh model from the step-2 weights + state, then the third step only
+    opt2, m_res = make(pretrain=str(tmp_path / "models" / "2_G.pth"))
+    m_res.netG.module.set_noise(11, 2)
+    last = train_loop.train(opt2, m_res, loader[2:], resume_state=state, total_epochs=0, rank=0)
+    assert last == 3
+    log_res = m_res.get_current_log()
+    for k in ("l_forw_fit", "l_back_rec", "loss"):
+        assert abs(log_res[k] - log_full[k]) <= 1e-5 * max(1.0, abs(log_full[k])), (k, log_res[k], log_full[k])
+    a, b = m_full.netG.module.state_dict(), m_res.netG.module.state_dict()
+    moved = max(float((a[k] - sd0[k]).abs().max()) for k in a)
+    n_all = sum(v.numel() for v in a.values())
+    n_off = sum(int(((a[k] - b[k]).abs() > 1e-6).sum()) for k in a)       # Adam steps of +-lr: only sign flips of noise-level
+    worst = max(float((a[k] - b[k]).abs().max()) for k in a)              # gradients (float atomics in wgrad) can differ
+    assert moved > 1e-5 and n_off <= 0.005 * n_all and worst <= 2.1e-4, (moved, n_off, n_all, worst)
+
+
 # ------------------------------------------------------------------------------------------------ f3: 2x operators
 def test_2x_operators_bit_exact(dev, golden_dir):
     """FrequencyAnalyzer(k=2) and HaarDownsampling kernels against the reference's modules (fixture) and the oracle."""

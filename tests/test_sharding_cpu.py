@@ -94,3 +94,48 @@ def test_multistep_lr_and_single_process_allreduce():
     assert train.multistep_lr(1e-4, 350000, [100000, 200000, 300000], 0.5) == 1.25e-5
     g = torch.ones(4)
     assert train.all_reduce_sum(g) == 1.0 and torch.equal(g, torch.ones(4))
+
+
+# ------------------------------------------------------------------------------------------------ f4: training driver (host logic)
+def test_dist_iter_sampler_matches_reference(golden_dir):
+    """Index streams identical to the reference's DistIterSampler (fixture from data/data_sampler.py) when the torch version that
+    generated the fixture is the one running; always: every rank gets num_samples indices and the ranks partition the epoch."""
+    import os
+    import numpy as np
+    import torch
+    from selfc_b200.data_sampler import DistIterSampler
+    g = np.load(os.path.join(golden_dir, "sampler.npz"))
+    same_torch = str(g["torch_version"]) == torch.__version__
+    for size, world, ratio in ((37, 3, 4), (64, 2, 200), (5, 4, 1)):
+        ds = list(range(size))
+        for epoch in (0, 3):
+            streams = []
+            for rank in range(world):
+                smp = DistIterSampler(ds, world, rank, ratio)
+                smp.set_epoch(epoch)
+                idx = list(iter(smp))
+                assert len(idx) == len(smp) == int(g[f"s{size}_w{world}_r{ratio}_k{rank}_len"])
+                if same_torch:
+                    assert idx == g[f"s{size}_w{world}_r{ratio}_k{rank}_e{epoch}"].tolist()
+                streams.append(idx)
+            # interleaving the ranks gives the (seeded) permutation of the enlarged epoch folded onto the dataset
+            gen = torch.Generator().manual_seed(epoch)
+            total = len(streams[0]) * world
+            full = (torch.randperm(total, generator=gen) % size).tolist()
+            inter = [streams[i % world][i // world] for i in range(total)]
+            assert inter == full
+    with __import__("pytest").raises(RuntimeError):
+        DistIterSampler(list(range(4)))          # no process group, no explicit world/rank
+
+
+def test_training_driver_helpers():
+    from selfc_b200 import train_loop
+    # train.py:146-152
+    assert train_loop.epochs_needed(64, 16, 400000, distributed=False) == 100000
+    assert train_loop.epochs_needed(64, 16, 400000, distributed=True) == 500
+    msg = train_loop.log_message(3, 12000, 5e-5, {"l_forw_fit": 1.25e-3, "loss": 0.5})
+    assert msg == "<epoch:  3, iter:  12,000, lr:5.000e-05> l_forw_fit: 1.2500e-03 loss: 5.0000e-01 "
+    ds = train_loop.SyntheticClips(n=4, t=3, size=32, seed=1)
+    a, b = ds[2]["GT"], ds[2]["GT"]
+    assert a.shape == (3, 3, 32, 32) and bool((a == b).all()) and float(a.min()) >= 0 and float(a.max()) <= 1
+    assert not bool((ds[1]["GT"] == a).all())
