@@ -19,7 +19,7 @@ constexpr int SM_KC = 16;
 constexpr int SM_APITCH = SM_TILE_M + 4;
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs<T> a) {
+__global__ void __launch_bounds__(256, 3) conv_simt_kernel(const ConvArgs<T> a) {
   __shared__ __align__(16) float As[2][SM_KC][SM_APITCH];
   __shared__ __align__(16) float Bs[2][SM_KC][SM_TILE_N];
 

@@ -47,73 +47,134 @@ __global__ void lrelu_bwd_kernel(float* __restrict__ g, const float* __restrict_
 }
 
 // wgrad: dw[tap][c][n] += sum_m in[m + shift(tap)][c] * g[m][n]  (+ the bias gradient in pseudo-tap `taps`: db[n] += sum_m g[m][n]).
-// grid (taps + 1, ceil(cin/32), splits); block 256 = 32 (c) x 8 (n groups of 4); each CTA reduces its share of the pixels through
-// shared-memory tiles of 32 pixels and adds its partial 32x32 block with atomics (fp32 scratch in buffer-channel order).
-__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ in, int in_pitch, int cin, const float* __restrict__ g,
+// grid ((taps + 1) * ceil(cout/32), ceil(cin/64), splits); block 256 = 64 input channels x 4 pixel groups.  A CTA reduces its
+// share of the pixels through shared-memory tiles of 32 pixels; a thread owns ONE input channel and all 32 output channels of
+// the tile (32 accumulators): per pixel one conflict-free LDS of its activation and eight broadcast LDS.128 of the gradient row
+// feed 32 FMAs (the first version's 1 x 4 register tile issued 5 LDS per 4 FMAs and ran at a fifth of the FMA rate).  The four
+// pixel groups are summed through shared memory, then one atomic per element adds the CTA's partial 64 x 32 block (fp32
+// scratch in buffer-channel order).
+constexpr int WG_C = 64;
+__global__ void __launch_bounds__(256, 3) wgrad_kernel(const float* __restrict__ in, int in_pitch, int cin, const float* __restrict__ g,
                                                     int g_pitch, int g_off, int cout, float* __restrict__ dw, int np, int taps,
                                                     int tap_mode, int BT, int Tn, int h, int w_) {
-  __shared__ float As[32][33];     // [pixel][c]
-  __shared__ float Gs[32][33];     // [pixel][n]
+  __shared__ __align__(16) float As[32][WG_C + 4];     // [pixel][c]
+  __shared__ __align__(16) float Gs[32][32];           // [pixel][n]
+  __shared__ float Red[WG_C][33];                      // cross-group reduction
   const int tap = blockIdx.x % (taps + 1);
   const int n0 = (blockIdx.x / (taps + 1)) * 32;          // output-channel tile
-  const int c0 = blockIdx.y * 32;
+  const int c0 = blockIdx.y * WG_C;
   const bool bias_pass = tap == taps;
   if (bias_pass && blockIdx.y != 0) return;
   const long long hw = (long long)h * w_;
   const long long M = (long long)BT * hw;
   const int tid = threadIdx.x;
-  const int tc = tid & 31, tn = (tid >> 5) * 4;
+  const int tc = tid & (WG_C - 1), pg = tid >> 6;
   int dy = 0, dx = 0, dt = 0;
   if (!bias_pass) {
     if (tap_mode == TAP_SPATIAL) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
     else if (tap_mode == TAP_TEMPORAL) dt = tap - 1;
   }
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
   const long long per = (M + gridDim.z - 1) / gridDim.z;
   const long long m_begin = (long long)blockIdx.z * per;
   const long long m_end = m_begin + per < M ? m_begin + per : M;
-  for (long long mb = m_begin; mb < m_end; mb += 32) {
-    // stage 32 pixels: thread (p = tid/8, q = tid%8) loads 4 channels of A and 4 of G
-    const int p = tid >> 3, q4 = (tid & 7) * 4;
-    const long long m = mb + p;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), gv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < m_end) {
-      if (n0 + q4 < cout) {
+  // global -> registers for the tile starting at mb (the loads of tile i+1 are in flight while tile i is being reduced)
+  float4 rg, ra[2];
+  auto fetch = [&](long long mb) {
+    {   // gradient rows: thread (p = tid/8, q = tid%8) loads 4 output channels
+      const int p = tid >> 3, q4 = (tid & 7) * 4;
+      const long long m = mb + p;
+      rg = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < m_end && n0 + q4 < cout) {
         const float* gp = g + m * g_pitch + g_off + n0 + q4;
-        gv.x = gp[0];
-        if (n0 + q4 + 1 < cout) gv.y = gp[1];
-        if (n0 + q4 + 2 < cout) gv.z = gp[2];
-        if (n0 + q4 + 3 < cout) gv.w = gp[3];
-      }
-      if (bias_pass) {
-        av = make_float4(1.f, 1.f, 1.f, 1.f);
-      } else if (c0 + q4 < cin) {
-        const long long n = m / hw, pix = m - n * hw;
-        const int y = (int)(pix / w_), x = (int)(pix - (long long)y * w_);
-        const int t = (int)(n % Tn);
-        const bool ok = (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w_ && (unsigned)(t + dt) < (unsigned)Tn;
-        if (ok) av = load4(in + (m + (long long)dt * hw + dy * w_ + dx) * in_pitch + c0 + q4);
+        rg.x = gp[0];
+        if (n0 + q4 + 1 < cout) rg.y = gp[1];
+        if (n0 + q4 + 2 < cout) rg.z = gp[2];
+        if (n0 + q4 + 3 < cout) rg.w = gp[3];
       }
     }
-    As[p][q4] = av.x; As[p][q4 + 1] = av.y; As[p][q4 + 2] = av.z; As[p][q4 + 3] = av.w;
-    Gs[p][q4] = gv.x; Gs[p][q4 + 1] = gv.y; Gs[p][q4 + 2] = gv.z; Gs[p][q4 + 3] = gv.w;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {   // (shifted) activations: 32 pixels x 16 float4
+      const int idx = tid + i * 256;
+      const int p = idx >> 4, q4 = (idx & 15) * 4;
+      const long long m = mb + p;
+      ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < m_end) {
+        if (bias_pass) {
+          ra[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        } else if (c0 + q4 < cin) {
+          const long long n = m / hw, pix = m - n * hw;
+          const int y = (int)(pix / w_), x = (int)(pix - (long long)y * w_);
+          const int t = (int)(n % Tn);
+          const bool ok = (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w_ && (unsigned)(t + dt) < (unsigned)Tn;
+          if (ok) ra[i] = load4(in + (m + (long long)dt * hw + dy * w_ + dx) * in_pitch + c0 + q4);
+        }
+      }
+    }
+  };
+  if (m_begin < m_end) fetch(m_begin);
+  for (long long mb = m_begin; mb < m_end; mb += 32) {
+    *reinterpret_cast<float4*>(&Gs[tid >> 3][(tid & 7) * 4]) = rg;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256;
+      *reinterpret_cast<float4*>(&As[idx >> 4][(idx & 15) * 4]) = ra[i];
+    }
     __syncthreads();
-#pragma unroll 8
-    for (int pp = 0; pp < 32; ++pp) {
+    if (mb + 32 < m_end) fetch(mb + 32);
+#pragma unroll 2
+    for (int pp = pg; pp < 32; pp += 4) {
       const float a = As[pp][tc];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, Gs[pp][tn + j], acc[j]);
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 gv = *reinterpret_cast<const float4*>(&Gs[pp][j4 * 4]);
+        acc[4 * j4 + 0] = fmaf(a, gv.x, acc[4 * j4 + 0]);
+        acc[4 * j4 + 1] = fmaf(a, gv.y, acc[4 * j4 + 1]);
+        acc[4 * j4 + 2] = fmaf(a, gv.z, acc[4 * j4 + 2]);
+        acc[4 * j4 + 3] = fmaf(a, gv.w, acc[4 * j4 + 3]);
+      }
     }
     __syncthreads();
   }
+  // sum the four pixel groups into group 0
+  for (int gsrc = 1; gsrc < 4; ++gsrc) {
+    if (pg == gsrc) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Red[tc][j] = acc[j];
+    }
+    __syncthreads();
+    if (pg == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += Red[tc][j];
+    }
+    __syncthreads();
+  }
+  if (pg != 0) return;
   if (bias_pass) {
     if (tc == 0)
-      for (int j = 0; j < 4; ++j)
-        if (n0 + tn + j < cout) atomicAdd(dw + (long long)taps * cin * np + n0 + tn + j, acc[j]);
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < cout) atomicAdd(dw + (long long)taps * cin * np + n0 + j, acc[j]);
   } else if (c0 + tc < cin) {
-    for (int j = 0; j < 4; ++j)
-      if (n0 + tn + j < cout) atomicAdd(dw + ((long long)tap * cin + c0 + tc) * np + n0 + tn + j, acc[j]);
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < cout) atomicAdd(dw + ((long long)tap * cin + c0 + tc) * np + n0 + j, acc[j]);
   }
+}
+
+// pixel splits of a wgrad launch: the grid should fill the resident slots (3 CTAs per SM) once or twice, not 1.1 times
+static int wgrad_splits(long long M, int base_ctas) {
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int slots = 3 * nsm;
+  int waves = M >= 400000 ? 4 : (M >= 100000 ? 2 : 1);
+  int splits = waves * slots / (base_ctas > 0 ? base_ctas : 1);
+  const long long max_splits = M / 256 > 0 ? M / 256 : 1;      // at least 8 tiles of 32 pixels per CTA
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits > 1024) splits = 1024;
+  if (splits < 1) splits = 1;
+  return splits;
 }
 
 // scratch [taps][cin_buf][np] (+ [np] bias) in buffer-channel order -> reference layouts dW [cout][cin_ref][taps], db [cout] (accumulating)
@@ -193,10 +254,8 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const float* buf
     if (gparams != nullptr && gparams[2 * k] != nullptr) {
       const size_t dw_floats = (size_t)(taps * cin + 1) * W.np[k];
       SELFC_CUDA(cudaMemsetAsync(dw, 0, dw_floats * sizeof(float), st));
-      int splits = (int)(M / 2048);
-      if (splits < 1) splits = 1;
-      if (splits > 64) splits = 64;
-      dim3 grid((taps + 1) * cdiv(cout, 32), cdiv(cin, 32), splits);
+      const int splits = wgrad_splits(M, (taps + 1) * cdiv(cout, 32) * cdiv(cin, WG_C));
+      dim3 grid((taps + 1) * cdiv(cout, 32), cdiv(cin, WG_C), splits);
       wgrad_kernel<<<grid, 256, 0, st>>>(buf, pitch, cin, g, g_pitch, g_off, cout, dw, W.np[k], taps, tap_mode, d.B * d.T, d.T, d.h, d.w);
       SELFC_LAUNCH_CHECK("wgrad_kernel");
       const int cin_ref = W.cin + kGrowth * k;
@@ -471,10 +530,8 @@ static int pointwise_backward(const float* wf, int cin, int np, int cout, const 
   float* dw = scratch + (size_t)cout4 * npd;
   if (gw != nullptr) {
     SELFC_CUDA(cudaMemsetAsync(dw, 0, (size_t)(cin + 1) * np * sizeof(float), st));
-    int splits = (int)(M / 2048);
-    if (splits < 1) splits = 1;
-    if (splits > 64) splits = 64;
-    dim3 grid(2 * cdiv(cout, 32), cdiv(cin, 32), splits);
+    const int splits = wgrad_splits(M, 2 * cdiv(cout, 32) * cdiv(cin, WG_C));
+    dim3 grid(2 * cdiv(cout, 32), cdiv(cin, WG_C), splits);
     wgrad_kernel<<<grid, 256, 0, st>>>(in, in_pitch, cin, g, g_pitch, 0, cout, dw, np, 1, TAP_POINT, d.B * d.T, d.T, d.h, d.w);
     SELFC_LAUNCH_CHECK("wgrad_kernel");
     const long long total = (long long)cout * cin;
