@@ -512,6 +512,41 @@ def test_u8_errors_are_loud(dev):
         eng.down_u8(torch.zeros(3, 32, 48, 3, dtype=torch.uint8), 3)                  # host tensor: no CPU path
 
 
+# ------------------------------------------------------------------------------------------------ opt-in kernel variants
+_VARIANT_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import selfc_oracle as so
+from selfc_b200.engine import Engine
+dev = torch.device("cuda", 0)
+eng = Engine(dev, "bf16"); eng.load_state(so.make_state_dict(0))
+x = so.make_frames(1, 3, 72, 136, 5).to(dev)          # 3 x 5 tiles per frame: odd tile counts, partial tiles
+lr, rec = eng.rescale(x, 3, seed=7, offset=1)
+torch.save({"lr": lr.cpu(), "rec": rec.cpu()}, sys.argv[1])
+"""
+
+
+@pytest.mark.parametrize("env", [{"SELFC_TC3_PAIR": "1"}, {"SELFC_ZIGZAG": "0"}, {"SELFC_TC3_PAIR": "1", "SELFC_ZIGZAG": "0"}])
+def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
+    """The CTA-pair conv3x3 kernel (cta_group::2) and the tile-sweep direction change scheduling only: the bf16 path must give
+    bit-identical LR codes and HR frames with and without them (each variant in its own process: the knobs are read once)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for i, extra in enumerate(({}, env)):
+        out = str(tmp_path / f"v{i}.pt")
+        e = dict(os.environ)
+        for k in ("SELFC_TC3_PAIR", "SELFC_ZIGZAG"):
+            e.pop(k, None)
+        e.update(extra)
+        r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET % here, out], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(out))
+    assert torch.equal(outs[0]["lr"], outs[1]["lr"])
+    assert torch.equal(outs[0]["rec"], outs[1]["rec"])
+
+
 # ------------------------------------------------------------------------------------------------ f1: metrics kernels
 def test_metrics_kernels_vs_reference_fixture_and_oracle(dev, golden_dir):
     """rgb_to_ycbcr bit-exact; PSNR within 1e-3 dB and SSIM within 1e-5 of the reference's own functions (fixture) and of the
