@@ -107,7 +107,16 @@ __device__ __forceinline__ void decode_tile(const Params& p, int tile, int& tx, 
 // activation pipeline, accumulators and epilogue; the pair's leader issues ONE M = 256 MMA for both (128 halo positions from
 // each CTA), and each CTA keeps only half of the weight rows (48 of the 96 (kx, n) rows), so an MMA reads 4 + 1.5 KB of each
 // SM's shared memory instead of 4 + 3 KB -- the operand feed, not the tensor pipe, is what bounds the one-CTA form.
-template <bool PAIR>
+// P2: the activation tile is fetched as rows of TWO adjacent positions (64-byte rows, SWIZZLE_64B) instead of one: the TMA unit
+// delivers about one box row per clock whatever its width (scripts/ubench/tma_rate.cu), so this halves the TMA time per K-step
+// (320 -> 160 rows for six MMAs), which is what bounds the mainloop of the one-position form.  An M-row of the MMA is then a
+// position PAIR g and the K-step of the first / second position of the pair is selected by a +0 / +32 byte start address inside
+// the 64-byte row, exactly like a K advance inside a swizzle atom: accumulator i (0/1) row g <-> position 2g+i, one MMA covers all
+// 8 tile rows (128 pairs), the ky tap is a 16-pair (1 KB = two atoms) start offset.  Pairs are (x odd, x+1) so that the halo
+// origin 30*tx-1 is pair aligned: the tensor map is based one position BEFORE the buffer, row pitch W positions, W/2+1 pairs per
+// row.  The two positions this makes readable that are not padding zeros -- x = -1 (previous row's last pixel) and x = W (next
+// row's first) -- only ever feed the kx=0 term of x = 0 and the kx=2 term of x = W-1, which the epilogue drops.
+template <bool PAIR, bool P2>
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                   const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -201,13 +210,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
         const int x0 = tx * VALID_W - 1, y0 = ty * ROWS - 1;
         for (int c0 = 0; c0 < nks; c0 += KPS) {
           timed_wait(empty_bar(s), ph ^ 1u, p.err, 31, w_empty);
+          const int xc = P2 ? tx * (VALID_W / 2) : x0;        // P2: pair index of the halo origin (pairs start at odd x)
           if (PAIR) {
             // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both
             if (crank == 0) mbar_expect_tx(full_bar(s), 2u * (uint32_t)STAGE);
-            tma_load_5d_pair(a_base + s * STAGE, tmap, mapa_u32(full_bar(s), 0), 0, x0, y0, n, c0);
+            tma_load_5d_pair(a_base + s * STAGE, tmap, mapa_u32(full_bar(s), 0), 0, xc, y0, n, c0);
           } else {
             mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
-            tma_load_5d(a_base + s * STAGE, tmap, full_bar(s), 0, x0, y0, n, c0);
+            tma_load_5d(a_base + s * STAGE, tmap, full_bar(s), 0, xc, y0, n, c0);
           }
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
@@ -227,7 +237,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      const uint32_t hi_a = desc_hi(256, 6);            // activations: SWIZZLE_32B rows, 8-row atoms of 256 bytes
+      // activations: SWIZZLE_32B rows of one position (8-row atoms of 256 bytes) / P2: SWIZZLE_64B rows of a position pair (512)
+      const uint32_t hi_a = P2 ? desc_hi(512, 4) : desc_hi(256, 6);
       const uint32_t hi_b = desc_hi(128, 0);            // weights: no-swizzle core matrices, 8-row groups 128 bytes apart
       const uint32_t b_ky = (uint32_t)nks * (WT_BYTES >> 4);
       long long w_full = 0, w_tempty = 0;
@@ -254,7 +265,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
               for (int mb = 0; mb < MBLK; ++mb) {
                 const uint32_t d = tmem_base + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
                 // A rows = flattened halo positions: M-block mb starts at tile row 4*mb, the ky tap one tile row further
-                const uint64_t ad = desc_join(a_lo + (uint32_t)((mb * 128 + ky * WT) * 2), hi_a);
+                // (P2: rows = position pairs, `mb` = which position of the pair (+32 bytes), the ky tap 16 pairs further)
+                const uint64_t ad = desc_join(a_lo + (uint32_t)(P2 ? (mb * 32 + ky * (WT / 2) * 64) >> 4 : (mb * 128 + ky * WT) * 2), hi_a);
                 const uint64_t bd = desc_join(b_lo + (uint32_t)ky * b_ky, hi_b);
                 if (PAIR) umma2_bf16_elect(d, ad, bd, idesc, ((c0 + ks) > 0 || ky > 0) ? 1u : 0u);
                 else umma_bf16_elect(d, ad, bd, idesc, ((c0 + ks) > 0 || ky > 0) ? 1u : 0u);
@@ -292,21 +304,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
       const int x = tx * VALID_W + lane;
       timed_wait(tfull_bar(acc), use & 1u, p.err, 35, w_tfull);
       tc_fence_after();
-#pragma unroll
-      for (int mb = 0; mb < MBLK; ++mb) {
-        const int y = ty * ROWS + mb * 4 + q;
-        const bool ok = tile_ok && lane < VALID_W && x < p.w && y < p.h;
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
-        __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)(ok ? n : 0) * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
+      if constexpr (P2) {
+        // lane quarter q holds pairs g = 32q + lane: tile row r = g / 16, pair c = g % 16 <-> halo columns 2c, 2c+1 (global x =
+        // 30 tx - 1 + column).  Output column o uses halo columns o, o+1, o+2 (kx = 0, 1, 2): this thread produces o = 2c, 2c+1.
+        const int g = q * 32 + lane;
+        const int r = g >> 4, c = g & 15;
+        const int y = ty * ROWS + r;
+        const int xo = tx * VALID_W + 2 * c;                 // global x of output 2c
+        const bool row_ok = tile_ok && y < p.h && c < VALID_W / 2;
+        const bool ok0 = row_ok && xo < p.w, ok1 = row_ok && xo + 1 < p.w;
+        const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + 0) * ACC_STRIDE);
+        const uint32_t trow1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + 1) * ACC_STRIDE);
+        __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)(ok0 ? n : 0) * p.h + (ok0 ? y : 0)) * p.w + (ok0 ? xo : 0)) * 16;
+        const bool drop_left = xo == 0;                      // kx = 0 term of x = 0 reads x = -1 (not a padding zero in this layout)
+        const bool drop_right0 = xo == p.w - 1, drop_right1 = xo + 1 == p.w - 1;      // kx = 2 term of x = W-1 reads x = W
 #pragma unroll
         for (int n0 = 0; n0 < NOUT; n0 += 16) {
-          uint32_t r0[16], r1[16], r2[16];
-          tmem_ld16(trow + (uint32_t)n0, r0);
-          tmem_ld16(trow + (uint32_t)(NOUT + n0), r1);
-          tmem_ld16(trow + (uint32_t)(2 * NOUT + n0), r2);
+          uint32_t a0[3][16], a1[3][16];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            tmem_ld16(trow0 + (uint32_t)(kx * NOUT + n0), a0[kx]);
+            tmem_ld16(trow1 + (uint32_t)(kx * NOUT + n0), a1[kx]);
+          }
           tmem_ld_wait();
-          if (mb == MBLK - 1 && n0 == NOUT - 16) {
-            // both accumulators of this tile are in registers: the next-but-one tile's MMAs may start
+          if (n0 == NOUT - 16) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -314,20 +335,71 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
               else mbar_arrive(tempty_bar(acc));
             }
           }
-          float v[16];
+          float v0[16], v1[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[j]), 1);
-            const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 2);
-            v[j] = lrelu02(__uint_as_float(r0[j]) + a1 + a2 + bias[n0 + j]);
+            // neighbours in the next pair (lane + 1; c = 15 wraps into the next row only for columns that are not outputs)
+            const float nx0_k2 = __shfl_down_sync(0xffffffffu, __uint_as_float(a0[2][j]), 1);
+            const float nx0_k1 = __shfl_down_sync(0xffffffffu, __uint_as_float(a0[1][j]), 1);
+            const float nx1_k2 = __shfl_down_sync(0xffffffffu, __uint_as_float(a1[2][j]), 1);
+            const float t0 = drop_left ? 0.f : __uint_as_float(a0[0][j]);
+            v0[j] = lrelu02(t0 + __uint_as_float(a1[1][j]) + (drop_right0 ? 0.f : nx0_k2) + bias[n0 + j]);
+            v1[j] = lrelu02(__uint_as_float(a1[0][j]) + nx0_k1 + (drop_right1 ? 0.f : nx1_k2) + bias[n0 + j]);
           }
-          if (ok) {
+          __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems;
+          if (ok0) {
             uint4 lo, hi;
-            lo.x = pack_bf2(v[0], v[1]); lo.y = pack_bf2(v[2], v[3]); lo.z = pack_bf2(v[4], v[5]); lo.w = pack_bf2(v[6], v[7]);
-            hi.x = pack_bf2(v[8], v[9]); hi.y = pack_bf2(v[10], v[11]); hi.z = pack_bf2(v[12], v[13]); hi.w = pack_bf2(v[14], v[15]);
-            __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems;
+            lo.x = pack_bf2(v0[0], v0[1]); lo.y = pack_bf2(v0[2], v0[3]); lo.z = pack_bf2(v0[4], v0[5]); lo.w = pack_bf2(v0[6], v0[7]);
+            hi.x = pack_bf2(v0[8], v0[9]); hi.y = pack_bf2(v0[10], v0[11]); hi.z = pack_bf2(v0[12], v0[13]); hi.w = pack_bf2(v0[14], v0[15]);
             *reinterpret_cast<uint4*>(os) = lo;
             *reinterpret_cast<uint4*>(os + 8) = hi;
+          }
+          if (ok1) {
+            uint4 lo, hi;
+            lo.x = pack_bf2(v1[0], v1[1]); lo.y = pack_bf2(v1[2], v1[3]); lo.z = pack_bf2(v1[4], v1[5]); lo.w = pack_bf2(v1[6], v1[7]);
+            hi.x = pack_bf2(v1[8], v1[9]); hi.y = pack_bf2(v1[10], v1[11]); hi.z = pack_bf2(v1[12], v1[13]); hi.w = pack_bf2(v1[14], v1[15]);
+            *reinterpret_cast<uint4*>(os + 16) = lo;
+            *reinterpret_cast<uint4*>(os + 24) = hi;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int mb = 0; mb < MBLK; ++mb) {
+          const int y = ty * ROWS + mb * 4 + q;
+          const bool ok = tile_ok && lane < VALID_W && x < p.w && y < p.h;
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
+          __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)(ok ? n : 0) * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
+  #pragma unroll
+          for (int n0 = 0; n0 < NOUT; n0 += 16) {
+            uint32_t r0[16], r1[16], r2[16];
+            tmem_ld16(trow + (uint32_t)n0, r0);
+            tmem_ld16(trow + (uint32_t)(NOUT + n0), r1);
+            tmem_ld16(trow + (uint32_t)(2 * NOUT + n0), r2);
+            tmem_ld_wait();
+            if (mb == MBLK - 1 && n0 == NOUT - 16) {
+              // both accumulators of this tile are in registers: the next-but-one tile's MMAs may start
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(tempty_leader0 + 8u * (uint32_t)acc);
+                else mbar_arrive(tempty_bar(acc));
+              }
+            }
+            float v[16];
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[j]), 1);
+              const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 2);
+              v[j] = lrelu02(__uint_as_float(r0[j]) + a1 + a2 + bias[n0 + j]);
+            }
+            if (ok) {
+              uint4 lo, hi;
+              lo.x = pack_bf2(v[0], v[1]); lo.y = pack_bf2(v[2], v[3]); lo.z = pack_bf2(v[4], v[5]); lo.w = pack_bf2(v[6], v[7]);
+              hi.x = pack_bf2(v[8], v[9]); hi.y = pack_bf2(v[10], v[11]); hi.z = pack_bf2(v[12], v[13]); hi.w = pack_bf2(v[14], v[15]);
+              __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems;
+              *reinterpret_cast<uint4*>(os) = lo;
+              *reinterpret_cast<uint4*>(os + 8) = hi;
+            }
           }
         }
       }
@@ -521,29 +593,49 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
     kps_pref = e ? atoi(e) : 2;
     if (kps_pref < 1 || kps_pref > 4) kps_pref = 2;
   }
-  // SELFC_TC3_PAIR=1: CTA-pair kernel (cta_group::2).  Parity-green and its MMA issue is cheaper (40 vs 67 cycles per MMA slot),
-  // but the launch as a whole is bound by the dense buffer's DRAM traffic either way (profiles/r2_conv3x3_waits.md), so the
-  // simpler one-CTA kernel stays the default.
+  // SELFC_TC3_PAIR=0: one-CTA kernel (cta_group::1) instead of CTA pairs.  The pair kernel's cheaper MMA issue only pays together
+  // with the position-pair TMA rows (SELFC_TC3_P2): each alone leaves the other limit in place (profiles/r2_conv3x3_waits.md).
   static int pair_pref = -1;
   if (pair_pref < 0) {
     const char* e = getenv("SELFC_TC3_PAIR");
-    pair_pref = (e && atoi(e) != 0) ? 1 : 0;
+    pair_pref = (e && atoi(e) == 0) ? 0 : 1;
   }
   const bool pair = pair_pref == 1 && w.img_pair != nullptr && (!dual || w2->img_pair != nullptr);
   const int nks = cin / 16;
   int kps = kps_pref < nks ? kps_pref : nks;
   const int fixed = tc3::BAR_BYTES + (int)(pair ? w.img_bytes / 2 : w.img_bytes) + 1024;      // both problems' weights have the same size
   while (kps > 1 && (227 * 1024 - fixed) / (kps * tc3::SUB_BYTES) < 3) --kps;
+  // SELFC_TC3_P2=0: one position per TMA row (SWIZZLE_32B) instead of position pairs.  Pairs need an even width.
+  static int p2_pref = -1;
+  if (p2_pref < 0) {
+    const char* e = getenv("SELFC_TC3_P2");
+    p2_pref = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const bool p2 = p2_pref == 1 && (wd % 2) == 0;
   CUtensorMap tmap, tmap2;
-  const cuuint64_t gdim[5] = {16, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
-  const cuuint64_t gstr[4] = {32, (cuuint64_t)wd * 32, (cuuint64_t)h * wd * 32, (cuuint64_t)slabM * 32};
-  const cuuint32_t box[5] = {16, (cuuint32_t)tc3::WT, (cuuint32_t)tc3::HT, 1, (cuuint32_t)kps};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r == CUDA_SUCCESS)
-    r = encode(&tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dual ? buf2 : buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r;
+  if (p2) {
+    // rows = pairs of positions (x odd, x + 1): based one position before the buffer, W/2 + 1 pairs per image row
+    const cuuint64_t gdim[5] = {32, (cuuint64_t)wd / 2 + 1, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
+    const cuuint64_t gstr[4] = {64, (cuuint64_t)wd * 32, (cuuint64_t)h * wd * 32, (cuuint64_t)slabM * 32};
+    const cuuint32_t box[5] = {32, (cuuint32_t)tc3::WT / 2, (cuuint32_t)tc3::HT, 1, (cuuint32_t)kps};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf - 16, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+      r = encode(&tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (dual ? buf2 : buf) - 16, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t gdim[5] = {16, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
+    const cuuint64_t gstr[4] = {32, (cuuint64_t)wd * 32, (cuuint64_t)h * wd * 32, (cuuint64_t)slabM * 32};
+    const cuuint32_t box[5] = {16, (cuuint32_t)tc3::WT, (cuuint32_t)tc3::HT, 1, (cuuint32_t)kps};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+      r = encode(&tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dual ? buf2 : buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (%dx%dx%d, %d slabs)", (int)r, N, h, wd, nks);
     return SELFC_E_CUDA;
@@ -579,8 +671,10 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   const int smem = fixed + nst * stage;
   static bool attr_set = false;
   if (!attr_set) {
-    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int nsm = tc::num_sms();
@@ -589,11 +683,13 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
     const int nsteps = (p.ntiles + 1) / 2;
     int npairs = p.nprob * nsteps < nsm / 2 ? p.nprob * nsteps : nsm / 2;
     if (dual && (npairs & 1)) --npairs;
-    SELFC_CUDA(tc::launch_pdl_pairs(tc3::conv3x3_tc3_kernel<true>, 2 * npairs, tc3::THREADS, smem, st, tmap, tmap2, p));
+    SELFC_CUDA(tc::launch_pdl_pairs(p2 ? tc3::conv3x3_tc3_kernel<true, true> : tc3::conv3x3_tc3_kernel<true, false>, 2 * npairs,
+                                    tc3::THREADS, smem, st, tmap, tmap2, p));
   } else {
     int grid = p.nprob * p.ntiles < nsm ? p.nprob * p.ntiles : nsm;
     if (dual && (grid & 1)) --grid;                   // CTA parity selects the problem: both halves get the same CTA count
-    SELFC_CUDA(tc::launch_pdl(tc3::conv3x3_tc3_kernel<false>, grid, tc3::THREADS, smem, st, tmap, tmap2, p));
+    SELFC_CUDA(tc::launch_pdl(p2 ? tc3::conv3x3_tc3_kernel<false, true> : tc3::conv3x3_tc3_kernel<false, false>, grid, tc3::THREADS,
+                              smem, st, tmap, tmap2, p));
   }
   SELFC_LAUNCH_CHECK("conv3x3_tc3_kernel");
   return 0;

@@ -526,10 +526,12 @@ torch.save({"lr": lr.cpu(), "rec": rec.cpu()}, sys.argv[1])
 """
 
 
-@pytest.mark.parametrize("env", [{"SELFC_TC3_PAIR": "1"}, {"SELFC_ZIGZAG": "0"}, {"SELFC_TC3_PAIR": "1", "SELFC_ZIGZAG": "0"}])
+@pytest.mark.parametrize("env", [{"SELFC_TC3_PAIR": "0"}, {"SELFC_TC3_P2": "0"}, {"SELFC_TC3_PAIR": "0", "SELFC_TC3_P2": "0"},
+                                 {"SELFC_ZIGZAG": "0"}])
 def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
-    """The CTA-pair conv3x3 kernel (cta_group::2) and the tile-sweep direction change scheduling only: the bf16 path must give
-    bit-identical LR codes and HR frames with and without them (each variant in its own process: the knobs are read once)."""
+    """CTA pairs (cta_group::2), position-pair TMA rows and the tile-sweep direction change how conv3x3 is scheduled and fed, not
+    what it computes: the bf16 path must give bit-identical LR codes and HR frames with each of them switched off (every variant
+    in its own process: the knobs are read once)."""
     import subprocess
     import sys
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -537,7 +539,7 @@ def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
     for i, extra in enumerate(({}, env)):
         out = str(tmp_path / f"v{i}.pt")
         e = dict(os.environ)
-        for k in ("SELFC_TC3_PAIR", "SELFC_ZIGZAG"):
+        for k in ("SELFC_TC3_PAIR", "SELFC_TC3_P2", "SELFC_ZIGZAG"):
             e.pop(k, None)
         e.update(extra)
         r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET % here, out], env=e, capture_output=True, text=True, timeout=600)
