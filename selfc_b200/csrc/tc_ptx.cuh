@@ -8,7 +8,13 @@
 namespace selfc {
 namespace tc {
 
+#ifdef SELFC_TC_NO_WAIT_HINT
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
+#else
+// try_wait carries a suspend-time hint: the hardware parks the waiting warp (up to ~20 us per attempt) instead of letting it
+// re-issue the poll, which matters in a power-capped run where five of a CTA's six warps wait most of the time
+constexpr uint32_t SPIN_LIMIT = 1u << 19;
+#endif
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -26,7 +32,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#ifdef SELFC_TC_NO_WAIT_HINT
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 20000;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
