@@ -20,7 +20,9 @@ int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_re
 void free_tc_weights(TcConvW& w);
 // conv_k of a dense block, in place on the slab-planar buffer (slabM = N*h*wd pixels per 16-channel slab): reads
 // channels [0,cin), writes lrelu(conv+bias) to [out_off,out_off+32)   (conv_tc3.cu)
-// (w2, buf2): optional second problem of the same shape run by the other half of the grid in the same launch (G and H)
+// (w2, buf2): optional second problem of the same shape run by the other half of the grid in the same launch (G and H).
+// The buffers must have 32 readable bytes before their first and after their last slab (the position-pair tensor map reads one
+// position either side; the values never reach an output).  Workspace regions satisfy this: none is first, all carry a guard.
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
                       const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr);
 

@@ -65,7 +65,9 @@ Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w) {
   Workspace ws;
   const size_t M = (size_t)B * T * h * w;
   const size_t es = ctx->mode == SELFC_MODE_BF16 ? 2 : 4;
-  const size_t guard = 4096;   // conv_tc halo boxes may touch a few rows past a buffer's end only through TMA (bounds-checked); keep slack anyway
+  // slack after every region: conv3x3's position-pair tensor map reads one position (32 bytes) before and after a dense buffer
+  // (never used in an output); `z` comes first, so no dense buffer starts the workspace
+  const size_t guard = 4096;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
