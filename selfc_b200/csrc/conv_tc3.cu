@@ -10,15 +10,17 @@
 // So one activation tile load feeds all nine taps, the tile is read from shared memory once per ky (3x, not 9x), and an
 // MMA moves 4 KB (A) + 3 KB (B) of shared memory for 48 cycles of math (the N = 32 formulation moved 5 KB for 16).
 //
-// Data movement: a pipeline stage is `kps` K-steps; ONE 5-D TMA box {16 ch, 32 x, 10 y, 1 frame, kps slabs} brings the
-// (8+2) x 32 halo of an 8 x 30 output tile, every tile row of a K-step being one contiguous 1 KB run of the slab
-// (SWIZZLE_32B rows of 32 bytes; out-of-image rows / columns / slabs are zero-filled by the TMA = the conv padding).
-// DRAM traffic is algorithmic: the conv reads exactly the cin/16 slabs it consumes.
+// Data movement: a pipeline stage is `kps` K-steps; ONE 5-D TMA box brings the (8+2) x 32 halo of an 8 x 30 output tile, every
+// tile row of a K-step being one contiguous 1 KB run of the slab (out-of-image rows / columns / slabs are zero-filled by the
+// TMA = the conv padding).  DRAM traffic is algorithmic: the conv reads exactly the cin/16 slabs it consumes.  Two forms of the
+// box (template P2): {16 ch, 32 x, 10 y} rows of one position (SWIZZLE_32B), or -- default for even widths -- rows of two
+// adjacent positions {32, 16 pairs, 10 y} (SWIZZLE_64B), which halves the number of rows the TMA unit has to move.
 //
 // Per CTA (persistent, 192 threads): warp 0 TMA producer, warp 1 MMA issuer (whole warp, elected lane), warps 2..5
-// epilogue (TMEM lane quarter q = tile row q of the M-block, lane = x): tcgen05.ld -> shuffle-add the kx partials ->
-// + bias -> LeakyReLU(0.2) -> bf16 -> two 32-byte stores into the output slabs.  Accumulators are double-buffered across
-// tiles (2 tiles x 2 M-blocks x 128 columns), the whole conv's weights stay resident in shared memory.
+// epilogue: tcgen05.ld -> shuffle-add the kx partials -> + bias -> LeakyReLU(0.2) -> bf16 -> 32-byte stores into the output
+// slabs.  Accumulators are double-buffered across tiles (2 tiles x 2 accumulators x 128 columns), the whole conv's weights stay
+// resident in shared memory.  By default CTAs run as pairs (template PAIR, cta_group::2): one M = 256 MMA covers the tiles of
+// both CTAs and each CTA keeps only half of the weight rows.  What each form buys and why: profiles/r2_conv3x3_waits.md.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
