@@ -299,7 +299,9 @@ def run_ours(args):
         ach = c["work"] / (c["ms"] / 1e3) / 1e12 if c["ms"] > 0 else 0.0
         # DRAM bytes per launch of the same kernel class from the committed `ncu` capture (profiles/; null when absent)
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_conv3x3_ncu_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_conv3x3_ncu_traffic.json")
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "r1_conv3x3_ncu_traffic.json")
         if os.path.exists(tp) and (hh, ww) == (HR_H, HR_W):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         roofline = {"kernel": "conv3x3_tc3_kernel: (1,3,3) dense-block convolution, tcgen05 implicit GEMM "
