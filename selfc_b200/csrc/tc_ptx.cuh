@@ -13,7 +13,7 @@ constexpr uint32_t SPIN_LIMIT = 1u << 26;
 #else
 // try_wait carries a suspend-time hint: the hardware parks the waiting warp (up to ~20 us per attempt) instead of letting it
 // re-issue the poll, which matters in a power-capped run where five of a CTA's six warps wait most of the time
-constexpr uint32_t SPIN_LIMIT = 1u << 19;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 #endif
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
