@@ -169,6 +169,12 @@ int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, 
 /* a7 sampler (:383-394): params [B*T,720,h,w] (channel hf*15+k*3+j), eps as in selfc_up -> v [B*T,48,h,w] */
 int selfc_gmm_sample(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* v,
                      int B, int T, int h, int w, void* stream);
+/* the same draw on the bf16 mode's internal layout (the sampler selfc_up launches after the tcgen05 head): params_planar
+ * [180][M][4] fp32, quad j*60 + k*12 + i = channels hf 4i..4i+3 of kind j (0 logit, 1 log-sigma, 2 mu), component k, with
+ * M = B*T*h*w pixels m = (b*T + t)*h*w + pix; z_planar [13][M][4]: quads 1..12 receive the 48 HF channels (quad 0, the LR
+ * frame, is not touched).  form: 0 thread-per-pixel kernel, 1 warp-split kernel, -1 the default (SELFC_GMM_SPLIT). */
+int selfc_gmm_sample_planar(const float* params_planar, const float* eps, uint64_t seed, uint64_t offset, float* z_planar,
+                            int B, int T, int h, int w, int form, void* stream);
 /* the noise selfc_up would draw for (seed, offset), in the reference layout [B,48,5,T,h,w] */
 int selfc_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, int h, int w, void* stream);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "selfc_conv3x3": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_global_agg": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "selfc_gmm_sample": (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _vp]),
+    "selfc_gmm_sample_planar": (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _vp]),
     "selfc_export_eps": (_i, [_vp, _u64, _u64, _i, _i, _i, _i, _vp]),
     "selfc_launch_count": (_u64, []),
     "selfc_prof_enable": (_i, [_vp, _i]),

@@ -913,6 +913,13 @@ int selfc_gmm_sample(const float* params, const float* eps, uint64_t seed, uint6
   return launch_gmm_sample(params, true, eps, seed, offset, v, true, 0, 0, B, T, h, w, (cudaStream_t)stream);
 }
 
+int selfc_gmm_sample_planar(const float* params_planar, const float* eps, uint64_t seed, uint64_t offset, float* z_planar, int B,
+                            int T, int h, int w, int form, void* stream) {
+  SELFC_CHECK_ARG(params_planar && z_planar, "gmm_sample_planar: null pointer");
+  SELFC_CHECK_ARG(B >= 0 && T >= 1 && h >= 1 && w >= 1 && form >= -1 && form <= 1, "gmm_sample_planar: bad shape / form");
+  return launch_gmm_sample_planar(params_planar, eps, seed, offset, z_planar, B, T, h, w, (cudaStream_t)stream, form);
+}
+
 int selfc_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, int h, int w, void* stream) {
   SELFC_CHECK_ARG(eps, "export_eps: null pointer");
   SELFC_CHECK_ARG(B >= 0 && T >= 1 && h >= 1 && w >= 1, "export_eps: bad shape");

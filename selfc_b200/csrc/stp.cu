@@ -3,6 +3,8 @@
 //
 // Reference behaviour restated (not copied): models/modules/SelfC_GMM_arch_inv.py:257-285 (GlobalAgg),
 // :383-394 + :412-417 (sampler / reparametrize).
+#include <cstdlib>
+#include <cuda_pipeline.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -56,8 +58,102 @@ __global__ void __launch_bounds__(256) ga_stat_kernel(const T* __restrict__ x, i
   }
 }
 
-// one CTA per clip, one warp-pair (64 threads) per frame: d -> q,k -> A = q k^T / 64 -> row softmax -> W [T][T], column sums
+// one CTA of 1024 threads per clip: d (sum of the ga_stat partials) -> q,k -> A = q k^T / 64 -> row softmax -> W [T][T], column sums.
+// A latency chain on one SM, so every stage is laid out for few, wide steps: proj2/proj3 weights are staged into shared memory
+// with coalesced loads (row-per-thread __ldg reads cost 32 L1 wavefronts per instruction: 30 of the 43 us this kernel used to
+// take) while the partial sums are in flight; each frame's partials are summed by S = 16/T thread groups (fixed order).
+constexpr int kGaWPitch = 65;         // padded rows: thread c walks row c, the 32 lanes of a warp hit 32 different banks
 __global__ void __launch_bounds__(1024) ga_weights_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ fcb,
+                                                          const float* __restrict__ p2w, const float* __restrict__ p2b,
+                                                          const float* __restrict__ p3w, const float* __restrict__ p3b,
+                                                          float* __restrict__ wmat, float* __restrict__ wsum, int T) {
+  constexpr int MAXT = 32;
+  extern __shared__ float sm[];
+  float* d = sm;                      // [T][64]
+  float* q = d + T * 64;              // [T][65]  (padded: the q.k products read rows with stride 65)
+  float* k = q + T * 65;              // [T][65]
+  float* A = k + T * 65;              // [T][MAXT]
+  float* dpart = A + T * MAXT;        // [16][64]   per-group partial sums of stage 1
+  float* w2s = dpart + 16 * 64;       // [64][65]
+  float* w3s = w2s + 64 * kGaWPitch;  // [64][65]
+  const int b = blockIdx.x;
+  const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;     // 16 groups of 64 threads
+  // stage 0: weights -> shared memory (4096 + 4096 coalesced 4-byte cp.async, in flight while stage 1 waits for its partials)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = u * 1024 + threadIdx.x;       // element (row e / 64, column e % 64)
+    __pipeline_memcpy_async(w2s + (e >> 6) * kGaWPitch + (e & 63), p2w + e, 4);
+    __pipeline_memcpy_async(w3s + (e >> 6) * kGaWPitch + (e & 63), p3w + e, 4);
+  }
+  __pipeline_commit();
+  // stage 1: d[t][c] = fcb + sum over the nsplit partials, S groups per frame
+  const int S = T <= 8 ? 16 / T : 1;
+  const int per = (nsplit + S - 1) / S;
+  for (int t0 = 0; t0 < T; t0 += 16 / S) {
+    const int t = t0 + grp / S, sub = grp % S;
+    float s = 0.f;
+    if (t < T && grp < (16 / S) * S) {
+      const int sp1 = min(nsplit, (sub + 1) * per);
+      int sp = sub * per;
+      const float* pp = partial + (((long long)b * T + t) * nsplit) * 64 + c;
+      for (; sp + 16 <= sp1; sp += 16) {        // 16 independent loads in flight, summed in a fixed order (deterministic)
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldg(pp + (long long)(sp + u) * 64);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += v[u];
+      }
+      for (; sp < sp1; ++sp) s += __ldg(pp + (long long)sp * 64);
+    }
+    dpart[grp * 64 + c] = s;
+    __syncthreads();
+    if (sub == 0 && t < T && grp < (16 / S) * S) {
+      float tot = dpart[grp * 64 + c];
+      for (int u = 1; u < S; ++u) tot += dpart[(grp + u) * 64 + c];
+      d[t * 64 + c] = tot + fcb[0];
+    }
+    __syncthreads();
+  }
+  __pipeline_wait_prior(0);
+  __syncthreads();
+  // stage 2: q = proj2(d), k = proj3(d): one thread per (q|k, frame, channel)
+  for (int item = threadIdx.x; item < 2 * T * 64; item += blockDim.x) {
+    const int which = item / (T * 64), t = (item / 64) % T;
+    const float* wrow = (which ? w3s : w2s) + c * kGaWPitch;
+    float acc = which ? p3b[c] : p2b[c];
+#pragma unroll 16
+    for (int i = 0; i < 64; ++i) acc += wrow[i] * d[t * 64 + i];
+    (which ? k : q)[t * 65 + c] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    const int t = e / T, u = e % T;
+    float s = 0.f;
+    for (int i = 0; i < 64; ++i) s += q[t * 65 + i] * k[u * 65 + i];
+    A[t * MAXT + u] = s / 64.0f;
+  }
+  __syncthreads();
+  if (threadIdx.x < T) {
+    const int t = threadIdx.x;
+    float mx = -INFINITY;
+    for (int u = 0; u < T; ++u) mx = fmaxf(mx, A[t * MAXT + u]);
+    float sum = 0.f;
+    for (int u = 0; u < T; ++u) { A[t * MAXT + u] = expf(A[t * MAXT + u] - mx); sum += A[t * MAXT + u]; }
+    for (int u = 0; u < T; ++u) {
+      A[t * MAXT + u] = A[t * MAXT + u] / sum;
+      wmat[((long long)b * T + t) * T + u] = A[t * MAXT + u];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < T) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += A[t * MAXT + threadIdx.x];
+    wsum[(long long)b * T + threadIdx.x] = s;
+  }
+}
+
+// Earlier form (SELFC_GA_WEIGHTS_V1=1), kept for A/B: one CTA per clip, one warp-pair (64 threads) per frame: d -> q,k -> A = q k^T / 64 -> row softmax -> W [T][T], column sums
+__global__ void __launch_bounds__(1024) ga_weights_v1_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ fcb,
                                                           const float* __restrict__ p2w, const float* __restrict__ p2b,
                                                           const float* __restrict__ p3w, const float* __restrict__ p3b,
                                                           float* __restrict__ wmat, float* __restrict__ wsum, int T) {
@@ -381,6 +477,83 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
   }
 }
 
+// Warp-split form of the planar sampler (default): a CTA of four warps owns 32 pixels and warp w owns HF quads 3w .. 3w+2 of
+// all five components, so every thread keeps its 60 logits in registers and the 720 parameters of a pixel are read from
+// DRAM exactly once (the thread-per-pixel form above walks the 240 logits three times and its third walk misses the L1/L2:
+// 4.1 GB read per 1080p GOP for 2.6 GB of parameters).  The per-component max and exp-sum over the 48 HF channels are
+// combined across the four warps through 2 x 2.5 KB of shared memory, in a fixed order (deterministic).
+__global__ void __launch_bounds__(128) gmm_sample_planar_split_kernel(const float* __restrict__ params, const float* __restrict__ eps,
+                                                                      uint64_t seed, uint64_t offset, float* __restrict__ z, int T,
+                                                                      long long hw, long long M) {
+  __shared__ float red_max[kGmmK][4][32];
+  __shared__ float red_sum[kGmmK][4][32];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const long long m_raw = (long long)blockIdx.x * 32 + lane;
+  const bool live = m_raw < M;
+  const long long m = live ? m_raw : M - 1;          // out-of-range lanes shadow the last pixel (they must reach the barriers)
+  const long long n = m / hw, pix = m - n * hw;
+  const int t = (int)(n % T);
+  const long long b = n / T;
+  float e[kGmmK][3][4];
+#pragma unroll
+  for (int k = 0; k < kGmmK; ++k)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float4 l = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + wq * 3 + q, (size_t)m)));
+      e[k][q][0] = l.x; e[k][q][1] = l.y; e[k][q][2] = l.z; e[k][q][3] = l.w;
+    }
+#pragma unroll
+  for (int k = 0; k < kGmmK; ++k) {
+    float mk = e[k][0][0];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mk = fmaxf(mk, e[k][q][c]);
+    red_max[k][wq][lane] = mk;
+  }
+  __syncthreads();
+  float inv[kGmmK];
+#pragma unroll
+  for (int k = 0; k < kGmmK; ++k) {
+    const float mk = fmaxf(fmaxf(red_max[k][0][lane], red_max[k][1][lane]), fmaxf(red_max[k][2][lane], red_max[k][3][lane]));
+    float sk = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        e[k][q][c] = __expf(e[k][q][c] - mk);        // ex2.approx based exp: relative error ~2^-21 on (-inf, 0]
+        sk += e[k][q][c];
+      }
+    red_sum[k][wq][lane] = sk;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kGmmK; ++k)
+    inv[k] = 1.0f / (((red_sum[k][0][lane] + red_sum[k][1][lane]) + red_sum[k][2][lane]) + red_sum[k][3][lane]);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int i = wq * 3 + q;
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kGmmK; ++k) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 60 + k * 12 + i, (size_t)m)));
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 120 + k * 12 + i, (size_t)m)));
+      const float ls[4] = {s4.x, s4.y, s4.z, s4.w}, mu[4] = {m4.x, m4.y, m4.z, m4.w};
+      float ep4[4];
+      if (eps) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ep4[c] = __ldg(eps + (uint64_t)(((((b * kHF + 4 * i + c) * kGmmK + k) * T + t) * hw) + pix));
+      } else {
+        philox_normal4(eps_group(b, i, k, t, pix, T, hw), seed, offset, ep4);   // one Philox call per (k, hf quad)
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        out[c] += (e[k][q][c] * inv[k]) * (ep4[c] * __expf(fminf(fmaxf(ls[c], -7.f), 7.f)) + mu[c]);
+    }
+    if (live) store4(z + quad_off((size_t)M, 1 + i, (size_t)m), make_float4(out[0], out[1], out[2], out[3]));
+  }
+}
+
 // tail_gmm.5 rows hf*15+k*3+j  ->  j*240 + k*48 + hf  (so each tcgen05 pass emits one parameter kind, hf contiguous)
 __global__ void permute_gmm_rows_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wp,
                                         float* __restrict__ bp, int by_component) {
@@ -426,9 +599,22 @@ template int launch_ga_stat<__nv_bfloat16>(const __nv_bfloat16*, int, const floa
 int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const float* p2w, const float* p2b, const float* p3w,
                       const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st) {
   SELFC_CHECK_ARG(T >= 1 && T <= 32, "GlobalAgg: temporal length %d outside [1,32]", T);
-  const int threads = 64 * (T < 16 ? T : 16);
-  const size_t smem = (size_t)(T * 64 + 2 * T * 65 + T * 32) * sizeof(float);
-  ga_weights_kernel<<<B, threads, smem, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
+  const size_t smem = (size_t)(T * 64 + 2 * T * 65 + T * 32 + 16 * 64 + 2 * 64 * kGaWPitch) * sizeof(float);   // 41 KB at T = 7, 64 KB at T = 32
+  static bool attr_set = false;
+  if (!attr_set) {
+    SELFC_CUDA(cudaFuncSetAttribute(ga_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    attr_set = true;
+  }
+  static int v1 = -1;
+  if (v1 < 0) {
+    const char* e = getenv("SELFC_GA_WEIGHTS_V1");
+    v1 = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  if (v1)
+    ga_weights_v1_kernel<<<B, 64 * (T < 16 ? T : 16), (size_t)(T * 64 + 2 * T * 65 + T * 32) * sizeof(float), st>>>(
+        partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
+  else
+    ga_weights_kernel<<<B, 1024, smem, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
   SELFC_LAUNCH_CHECK("ga_weights_kernel");
   return 0;
 }
@@ -451,10 +637,18 @@ int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, u
 }
 
 int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* z, int B, int T, int h,
-                             int w, cudaStream_t st) {
+                             int w, cudaStream_t st, int form) {
   const long long M = (long long)B * T * h * w;
   if (M == 0) return 0;
-  gmm_sample_planar_kernel<<<cdiv(M, 128), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
+  static int split = -1;                  // SELFC_GMM_SPLIT=0: the thread-per-pixel form
+  if (split < 0) {
+    const char* e = getenv("SELFC_GMM_SPLIT");
+    split = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (form < 0 ? split == 1 : form == 1)
+    gmm_sample_planar_split_kernel<<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
+  else
+    gmm_sample_planar_kernel<<<cdiv(M, 128), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
   SELFC_LAUNCH_CHECK("gmm_sample_planar_kernel");
   return 0;
 }

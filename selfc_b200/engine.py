@@ -616,6 +616,27 @@ def gmm_sample(params: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None,
     return v
 
 
+def gmm_sample_planar(params: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
+                      form: int = -1):
+    """The sampler the bf16 mode launches, driven from reference-layout tensors: params [B*T,720,h,w] (channel hf*15+k*3+j,
+    SelfC_GMM_arch_inv.py:383-388) are permuted into the planar quads the tcgen05 head writes, the planar latent comes back
+    as v [B*T,48,h,w].  form 0 / 1 selects the thread-per-pixel / warp-split kernel, -1 the default."""
+    params = _dev_check(params)
+    bt, c, h, w = params.shape
+    if c != 720 or bt % T:
+        raise ValueError("gmm_sample_planar expects [B*T,720,h,w]")
+    if eps is not None:
+        eps = _dev_check(eps)
+    m = bt * h * w
+    # [M, hf, k, j] -> [j, k, i, M, 4]
+    planar = params.permute(0, 2, 3, 1).reshape(m, HF_DIM // 4, 4, GMM_K, 3).permute(4, 3, 1, 0, 2).contiguous()
+    z = torch.zeros((1 + HF_DIM // 4, m, 4), dtype=torch.float32, device=params.device)
+    with torch.cuda.device(params.device):
+        _lib.check(_lib.lib().selfc_gmm_sample_planar(_ptr(planar), _ptr(eps), seed, offset, _ptr(z), bt // T, T, h, w, form,
+                                                      _stream(params.device)), "gmm_sample_planar")
+    return z[1:].permute(1, 0, 2).reshape(bt, h, w, HF_DIM).permute(0, 3, 1, 2).contiguous()
+
+
 def export_eps(B: int, T: int, h: int, w: int, seed: int, offset: int, device) -> torch.Tensor:
     eps = torch.empty((B, HF_DIM, GMM_K, T, h, w), dtype=torch.float32, device=device)
     with torch.cuda.device(eps.device):

@@ -80,7 +80,7 @@ def test_dense_block_vs_oracle(dev, prefix, cin):
     torch.testing.assert_close(got, ref, rtol=0, atol=2e-5)
 
 
-@pytest.mark.parametrize("h,w,t", [(10, 18, 2), (32, 32, 3), (45, 67, 7)])
+@pytest.mark.parametrize("h,w,t", [(10, 18, 2), (32, 32, 3), (45, 67, 7), (40, 52, 12), (64, 96, 5)])
 def test_global_agg_vs_oracle(dev, h, w, t):
     sd = so.make_state_dict(6, gain=2.0)
     eng = _engine(dev, sd)
@@ -113,6 +113,26 @@ def test_gmm_sample_vs_oracle(dev):
     eps2 = engine.export_eps(b, t, h, w, seed=42, offset=3, device=dev)
     got2 = engine.gmm_sample(params.to(dev), t, seed=42, offset=3).cpu()
     torch.testing.assert_close(got2, so.gmm_sample(params, eps2.cpu(), t), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("form", [0, 1, -1])
+def test_gmm_sample_planar_vs_oracle(dev, form):
+    """The bf16 mode's sampler (planar parameter quads written by the tcgen05 head) through its own entry point, both kernel
+    forms (thread-per-pixel, warp-split) and the default: injected eps and the counter-based stream; ragged pixel counts
+    (M % 32 != 0 and M % 128 != 0) exercise the shadow lanes of the warp-split form."""
+    from selfc_b200 import engine
+    for (b, t, h, w) in [(2, 3, 5, 9), (1, 7, 6, 11), (1, 2, 8, 8)]:
+        gen = torch.Generator().manual_seed(5 + h)
+        params = torch.randn(b * t, 720, h, w, generator=gen) * 3.0      # exercises the +-7 clamp
+        eps = so.make_eps(b, t, h, w, 23)
+        ref = so.gmm_sample(params, eps, t)
+        got = engine.gmm_sample_planar(params.to(dev), t, eps=eps.to(dev), form=form).cpu()
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-4)
+        eps2 = engine.export_eps(b, t, h, w, seed=42, offset=3, device=dev)
+        got2 = engine.gmm_sample_planar(params.to(dev), t, seed=42, offset=3, form=form).cpu()
+        torch.testing.assert_close(got2, so.gmm_sample(params, eps2.cpu(), t), rtol=1e-5, atol=1e-4)
+        # the NCHW kernel of the fp32 mode draws the same numbers
+        torch.testing.assert_close(got2, engine.gmm_sample(params.to(dev), t, seed=42, offset=3).cpu(), rtol=1e-5, atol=1e-5)
 
 
 def test_philox_stream(dev):
