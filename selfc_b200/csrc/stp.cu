@@ -4,6 +4,7 @@
 // Reference behaviour restated (not copied): models/modules/SelfC_GMM_arch_inv.py:257-285 (GlobalAgg),
 // :383-394 + :412-417 (sampler / reparametrize).
 #include <cstdlib>
+#include <type_traits>
 #include <cuda_pipeline.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -36,12 +37,50 @@ __global__ void ga_wmap_kernel(const float* __restrict__ fcw, float* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) ga_stat_kernel(const T* __restrict__ x, int pitch, const float* __restrict__ wmap,
                                                       float* __restrict__ partial, int nsplit, int hw) {
-  __shared__ float red[16][64 + 4];
   const int split = blockIdx.x, n = blockIdx.y;
-  const int ch = (threadIdx.x & 15) * 4;
-  const int lane = threadIdx.x >> 4;
   const int per = (hw + nsplit - 1) / nsplit;
   const int p0 = split * per, p1 = min(hw, p0 + per);
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // bf16 features: 8 threads x 16 bytes per pixel, 32 pixels per pass, four passes (64 bytes per thread) in flight
+    __shared__ float red[32][64 + 4];
+    const int ch = (threadIdx.x & 7) * 8;
+    const int lane = threadIdx.x >> 3;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const T* xb = x + (long long)n * hw * pitch + ch;
+    for (int p = p0 + lane; p < p1; p += 128) {
+      uint4 r[4];
+      float wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p + 32 * u;
+        const bool ok = pp < p1;
+        wv[u] = ok ? __ldg(wmap + pp) : 0.f;
+        r[u] = ok ? __ldg(reinterpret_cast<const uint4*>(xb + (long long)pp * pitch)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w32[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] = fmaf(wv[u], __uint_as_float(w32[j] << 16), acc[2 * j]);             // bf16 -> fp32 is a 16-bit shift
+          acc[2 * j + 1] = fmaf(wv[u], __uint_as_float(w32[j] & 0xffff0000u), acc[2 * j + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[lane][ch + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float s = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) s += red[l][threadIdx.x];
+      partial[((long long)n * nsplit + split) * 64 + threadIdx.x] = s;
+    }
+    return;
+  } else {
+  __shared__ float red[16][64 + 4];
+  const int ch = (threadIdx.x & 15) * 4;
+  const int lane = threadIdx.x >> 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = p0 + lane; p < p1; p += 16) {
     const float wv = __ldg(wmap + p);
@@ -55,6 +94,7 @@ __global__ void __launch_bounds__(256) ga_stat_kernel(const T* __restrict__ x, i
 #pragma unroll
     for (int l = 0; l < 16; ++l) s += red[l][threadIdx.x];
     partial[((long long)n * nsplit + split) * 64 + threadIdx.x] = s;
+  }
   }
 }
 
@@ -124,75 +164,6 @@ __global__ void __launch_bounds__(1024) ga_weights_kernel(const float* __restric
 #pragma unroll 16
     for (int i = 0; i < 64; ++i) acc += wrow[i] * d[t * 64 + i];
     (which ? k : q)[t * 65 + c] = acc;
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
-    const int t = e / T, u = e % T;
-    float s = 0.f;
-    for (int i = 0; i < 64; ++i) s += q[t * 65 + i] * k[u * 65 + i];
-    A[t * MAXT + u] = s / 64.0f;
-  }
-  __syncthreads();
-  if (threadIdx.x < T) {
-    const int t = threadIdx.x;
-    float mx = -INFINITY;
-    for (int u = 0; u < T; ++u) mx = fmaxf(mx, A[t * MAXT + u]);
-    float sum = 0.f;
-    for (int u = 0; u < T; ++u) { A[t * MAXT + u] = expf(A[t * MAXT + u] - mx); sum += A[t * MAXT + u]; }
-    for (int u = 0; u < T; ++u) {
-      A[t * MAXT + u] = A[t * MAXT + u] / sum;
-      wmat[((long long)b * T + t) * T + u] = A[t * MAXT + u];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < T) {
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) s += A[t * MAXT + threadIdx.x];
-    wsum[(long long)b * T + threadIdx.x] = s;
-  }
-}
-
-// Earlier form (SELFC_GA_WEIGHTS_V1=1), kept for A/B: one CTA per clip, one warp-pair (64 threads) per frame: d -> q,k -> A = q k^T / 64 -> row softmax -> W [T][T], column sums
-__global__ void __launch_bounds__(1024) ga_weights_v1_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ fcb,
-                                                          const float* __restrict__ p2w, const float* __restrict__ p2b,
-                                                          const float* __restrict__ p3w, const float* __restrict__ p3b,
-                                                          float* __restrict__ wmat, float* __restrict__ wsum, int T) {
-  constexpr int MAXT = 32;
-  extern __shared__ float sm[];
-  float* d = sm;                      // [T][64]
-  float* q = d + T * 64;              // [T][65]  (padded: the q.k products read rows with stride 65)
-  float* k = q + T * 65;              // [T][65]
-  float* A = k + T * 65;              // [T][MAXT]
-  const int b = blockIdx.x;
-  const int nfr = blockDim.x / 64;    // frames handled concurrently
-  const int c = threadIdx.x & 63, f0 = threadIdx.x >> 6;
-  for (int t = f0; t < T; t += nfr) {
-    float s = 0.f;
-    const float* pp = partial + (((long long)b * T + t) * nsplit) * 64 + c;
-    int sp = 0;
-    for (; sp + 16 <= nsplit; sp += 16) {        // 16 independent loads in flight, summed in a fixed order (deterministic)
-      float v[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = __ldg(pp + (long long)(sp + u) * 64);
-#pragma unroll
-      for (int u = 0; u < 16; ++u) s += v[u];
-    }
-    for (; sp < nsplit; ++sp) s += __ldg(pp + (long long)sp * 64);
-    d[t * 64 + c] = s + fcb[0];
-  }
-  __syncthreads();
-  for (int t = f0; t < T; t += nfr) {
-    float sq = p2b[c], sk = p3b[c];
-    const float* w2 = p2w + c * 64;
-    const float* w3 = p3w + c * 64;
-#pragma unroll 8
-    for (int i = 0; i < 64; ++i) {
-      const float dv = d[t * 64 + i];
-      sq += __ldg(w2 + i) * dv;
-      sk += __ldg(w3 + i) * dv;
-    }
-    q[t * 65 + c] = sq;
-    k[t * 65 + c] = sk;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
@@ -477,16 +448,20 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
   }
 }
 
-// Warp-split form of the planar sampler (default): a CTA of four warps owns 32 pixels and warp w owns HF quads 3w .. 3w+2 of
-// all five components, so every thread keeps its 60 logits in registers and the 720 parameters of a pixel are read from
-// DRAM exactly once (the thread-per-pixel form above walks the 240 logits three times and its third walk misses the L1/L2:
-// 4.1 GB read per 1080p GOP for 2.6 GB of parameters).  The per-component max and exp-sum over the 48 HF channels are
-// combined across the four warps through 2 x 2.5 KB of shared memory, in a fixed order (deterministic).
-__global__ void __launch_bounds__(128) gmm_sample_planar_split_kernel(const float* __restrict__ params, const float* __restrict__ eps,
-                                                                      uint64_t seed, uint64_t offset, float* __restrict__ z, int T,
-                                                                      long long hw, long long M) {
-  __shared__ float red_max[kGmmK][4][32];
-  __shared__ float red_sum[kGmmK][4][32];
+// Warp-split form of the planar sampler (default): a CTA of four warps owns 32 pixels and warp w owns HF quads 3w .. 3w+2, so
+// the 720 parameters of a pixel are read from DRAM exactly once (the thread-per-pixel form above walks the 240 logits three
+// times and its third walk misses L1/L2: 4.1 GB read per 1080p GOP for 2.6 GB of parameters).  The softmax over the 48 HF
+// channels is independent per mixture component, so the CTA walks k = 0..4 and a thread only holds the 12 logits of (its three
+// quads, this k) plus 12 accumulators: 64 registers, 32 resident warps per SM -- the kernel is issue-bound (60 Philox calls,
+// 120 Box-Muller pairs and 480 exp per pixel), so occupancy is what the form with all 60 logits in registers (113 registers,
+// 16 warps per SM: slower than thread-per-pixel in the stream) lacked.  The per-component max and exp-sum are combined across
+// the four warps through shared memory in a fixed order (deterministic).
+template <bool kEps>
+__global__ void __launch_bounds__(128, 8) gmm_sample_planar_perk_kernel(const float* __restrict__ params, const float* __restrict__ eps,
+                                                                        uint64_t seed, uint64_t offset, float* __restrict__ z, int T,
+                                                                        long long hw, long long M) {
+  __shared__ float red_max[4][32];
+  __shared__ float red_sum[4][32];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const long long m_raw = (long long)blockIdx.x * 32 + lane;
   const bool live = m_raw < M;
@@ -494,53 +469,48 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_split_kernel(const floa
   const long long n = m / hw, pix = m - n * hw;
   const int t = (int)(n % T);
   const long long b = n / T;
-  float e[kGmmK][3][4];
+  float out[3][4];
 #pragma unroll
-  for (int k = 0; k < kGmmK; ++k)
+  for (int q = 0; q < 3; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[q][c] = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < kGmmK; ++k) {
+    float e[3][4];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      const float4 l = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + wq * 3 + q, (size_t)m)));
-      e[k][q][0] = l.x; e[k][q][1] = l.y; e[k][q][2] = l.z; e[k][q][3] = l.w;
+      const int i = wq * 3 + q;
+      const float4 l = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + i, (size_t)m)));
+      e[q][0] = l.x; e[q][1] = l.y; e[q][2] = l.z; e[q][3] = l.w;
     }
-#pragma unroll
-  for (int k = 0; k < kGmmK; ++k) {
-    float mk = e[k][0][0];
+    float mk = e[0][0];
 #pragma unroll
     for (int q = 0; q < 3; ++q)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) mk = fmaxf(mk, e[k][q][c]);
-    red_max[k][wq][lane] = mk;
-  }
-  __syncthreads();
-  float inv[kGmmK];
-#pragma unroll
-  for (int k = 0; k < kGmmK; ++k) {
-    const float mk = fmaxf(fmaxf(red_max[k][0][lane], red_max[k][1][lane]), fmaxf(red_max[k][2][lane], red_max[k][3][lane]));
+      for (int c = 0; c < 4; ++c) mk = fmaxf(mk, e[q][c]);
+    red_max[wq][lane] = mk;
+    __syncthreads();
+    mk = fmaxf(fmaxf(red_max[0][lane], red_max[1][lane]), fmaxf(red_max[2][lane], red_max[3][lane]));
     float sk = 0.f;
 #pragma unroll
     for (int q = 0; q < 3; ++q)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        e[k][q][c] = __expf(e[k][q][c] - mk);        // ex2.approx based exp: relative error ~2^-21 on (-inf, 0]
-        sk += e[k][q][c];
+        e[q][c] = __expf(e[q][c] - mk);              // ex2.approx based exp: relative error ~2^-21 on (-inf, 0]
+        sk += e[q][c];
       }
-    red_sum[k][wq][lane] = sk;
-  }
-  __syncthreads();
+    red_sum[wq][lane] = sk;
+    __syncthreads();
+    const float inv = 1.0f / (((red_sum[0][lane] + red_sum[1][lane]) + red_sum[2][lane]) + red_sum[3][lane]);
 #pragma unroll
-  for (int k = 0; k < kGmmK; ++k)
-    inv[k] = 1.0f / (((red_sum[k][0][lane] + red_sum[k][1][lane]) + red_sum[k][2][lane]) + red_sum[k][3][lane]);
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const int i = wq * 3 + q;
-    float out[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < kGmmK; ++k) {
+    for (int q = 0; q < 3; ++q) {
+      const int i = wq * 3 + q;
+      // issued before the Philox rounds, which cover most of their latency
       const float4 s4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 60 + k * 12 + i, (size_t)m)));
       const float4 m4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 120 + k * 12 + i, (size_t)m)));
       const float ls[4] = {s4.x, s4.y, s4.z, s4.w}, mu[4] = {m4.x, m4.y, m4.z, m4.w};
       float ep4[4];
-      if (eps) {
+      if constexpr (kEps) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) ep4[c] = __ldg(eps + (uint64_t)(((((b * kHF + 4 * i + c) * kGmmK + k) * T + t) * hw) + pix));
       } else {
@@ -548,9 +518,13 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_split_kernel(const floa
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        out[c] += (e[k][q][c] * inv[k]) * (ep4[c] * __expf(fminf(fmaxf(ls[c], -7.f), 7.f)) + mu[c]);
+        out[q][c] += (e[q][c] * inv) * (ep4[c] * __expf(fminf(fmaxf(ls[c], -7.f), 7.f)) + mu[c]);
     }
-    if (live) store4(z + quad_off((size_t)M, 1 + i, (size_t)m), make_float4(out[0], out[1], out[2], out[3]));
+  }
+  if (live) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      store4(z + quad_off((size_t)M, 1 + wq * 3 + q, (size_t)m), make_float4(out[q][0], out[q][1], out[q][2], out[q][3]));
   }
 }
 
@@ -605,16 +579,7 @@ int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const 
     SELFC_CUDA(cudaFuncSetAttribute(ga_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     attr_set = true;
   }
-  static int v1 = -1;
-  if (v1 < 0) {
-    const char* e = getenv("SELFC_GA_WEIGHTS_V1");
-    v1 = (e && atoi(e) == 1) ? 1 : 0;
-  }
-  if (v1)
-    ga_weights_v1_kernel<<<B, 64 * (T < 16 ? T : 16), (size_t)(T * 64 + 2 * T * 65 + T * 32) * sizeof(float), st>>>(
-        partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
-  else
-    ga_weights_kernel<<<B, 1024, smem, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
+  ga_weights_kernel<<<B, 1024, smem, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
   SELFC_LAUNCH_CHECK("ga_weights_kernel");
   return 0;
 }
@@ -645,8 +610,11 @@ int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t see
     const char* e = getenv("SELFC_GMM_SPLIT");
     split = (e && atoi(e) == 0) ? 0 : 1;
   }
-  if (form < 0 ? split == 1 : form == 1)
-    gmm_sample_planar_split_kernel<<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
+  const int f = form < 0 ? split : form;
+  if (f == 1 && eps != nullptr)
+    gmm_sample_planar_perk_kernel<true><<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
+  else if (f == 1)
+    gmm_sample_planar_perk_kernel<false><<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
   else
     gmm_sample_planar_kernel<<<cdiv(M, 128), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
   SELFC_LAUNCH_CHECK("gmm_sample_planar_kernel");
