@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
 
 // Warp-split form of the planar sampler (default): a CTA of four warps owns 32 pixels and warp w owns HF quads 3w .. 3w+2, so
 // the 720 parameters of a pixel are read from DRAM exactly once (the thread-per-pixel form above walks the 240 logits three
-// times and its third walk misses L1/L2: 4.1 GB read per 1080p GOP for 2.6 GB of parameters).  The softmax over the 48 HF
+// times and its third walk misses L1/L2: 3.2 GB read per 1080p GOP for 2.6 GB of parameters).  The softmax over the 48 HF
 // channels is independent per mixture component, so the CTA walks k = 0..4 and a thread only holds the 12 logits of (its three
 // quads, this k) plus 12 accumulators: 64 registers, 32 resident warps per SM -- the kernel is issue-bound (60 Philox calls,
 // 120 Box-Muller pairs and 480 exp per pixel), so occupancy is what the form with all 60 logits in registers (113 registers,
