@@ -671,13 +671,15 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   SELFC_CHECK_ARG(nst >= 2, "conv3x3_tc: no room for the activation pipeline (cin %d)", cin);
   p.nst = nst;
   const int smem = fixed + nst * stage;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool smem_set[64] = {};           // per device: function attributes belong to the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !smem_set[dev]) {
     SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    smem_set[dev] = true;
   }
   const int nsm = tc::num_sms();
   if (pair) {

@@ -574,10 +574,12 @@ int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const 
                       const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st) {
   SELFC_CHECK_ARG(T >= 1 && T <= 32, "GlobalAgg: temporal length %d outside [1,32]", T);
   const size_t smem = (size_t)(T * 64 + 2 * T * 65 + T * 32 + 16 * 64 + 2 * 64 * kGaWPitch) * sizeof(float);   // 41 KB at T = 7, 64 KB at T = 32
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool smem_set[64] = {};           // per device: function attributes belong to the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !smem_set[dev]) {
     SELFC_CUDA(cudaFuncSetAttribute(ga_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    attr_set = true;
+    smem_set[dev] = true;
   }
   ga_weights_kernel<<<B, 1024, smem, st>>>(partial, nsplit, fcb, p2w, p2b, p3w, p3b, wmat, wsum, T);
   SELFC_LAUNCH_CHECK("ga_weights_kernel");

@@ -616,6 +616,20 @@ def gmm_sample(params: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None,
     return v
 
 
+def gmm_params_to_planar(params: torch.Tensor) -> torch.Tensor:
+    """[B*T,720,h,w] in the reference's channel order hf*15 + k*3 + j (SelfC_GMM_arch_inv.py:383-388) -> the planar quads the
+    tcgen05 head writes: [180][M][4] with quad = j*60 + k*12 + i holding hf = 4i..4i+3 (j: 0 logit, 1 log-sigma, 2 mu)."""
+    bt, c, h, w = params.shape
+    m = bt * h * w
+    # [M, i, e, k, j] -> [j, k, i, M, e]
+    return params.permute(0, 2, 3, 1).reshape(m, HF_DIM // 4, 4, GMM_K, 3).permute(4, 3, 1, 0, 2).reshape(180, m, 4).contiguous()
+
+
+def gmm_latent_from_planar(z: torch.Tensor, bt: int, h: int, w: int) -> torch.Tensor:
+    """planar latent state [13][M][4] (quad 0 = LR frame, quads 1..12 = HF) -> v [B*T,48,h,w]"""
+    return z[1:].permute(1, 0, 2).reshape(bt, h, w, HF_DIM).permute(0, 3, 1, 2).contiguous()
+
+
 def gmm_sample_planar(params: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
                       form: int = -1):
     """The sampler the bf16 mode launches, driven from reference-layout tensors: params [B*T,720,h,w] (channel hf*15+k*3+j,
@@ -628,13 +642,12 @@ def gmm_sample_planar(params: torch.Tensor, T: int, eps: Optional[torch.Tensor] 
     if eps is not None:
         eps = _dev_check(eps)
     m = bt * h * w
-    # [M, hf, k, j] -> [j, k, i, M, 4]
-    planar = params.permute(0, 2, 3, 1).reshape(m, HF_DIM // 4, 4, GMM_K, 3).permute(4, 3, 1, 0, 2).contiguous()
+    planar = gmm_params_to_planar(params)
     z = torch.zeros((1 + HF_DIM // 4, m, 4), dtype=torch.float32, device=params.device)
     with torch.cuda.device(params.device):
         _lib.check(_lib.lib().selfc_gmm_sample_planar(_ptr(planar), _ptr(eps), seed, offset, _ptr(z), bt // T, T, h, w, form,
                                                       _stream(params.device)), "gmm_sample_planar")
-    return z[1:].permute(1, 0, 2).reshape(bt, h, w, HF_DIM).permute(0, 3, 1, 2).contiguous()
+    return gmm_latent_from_planar(z, bt, h, w)
 
 
 def export_eps(B: int, T: int, h: int, w: int, seed: int, offset: int, device) -> torch.Tensor:

@@ -107,3 +107,30 @@ def test_packaged_seeded_weights_equal_the_oracle_recipe():
     a, b = seeded_state_dict(net, 0), so.make_state_dict(0)
     assert list(a.keys()) == list(b.keys())
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_planar_gmm_layout_helpers_match_the_oracle_sampler():
+    """Host logic of selfc_gmm_sample_planar's Python wrapper: the permutation from the reference's parameter order
+    (hf*15 + k*3 + j, SelfC_GMM_arch_inv.py:383-388) to the planar quads [j*60 + k*12 + i][M][4] and back from the planar
+    latent.  A plain-torch evaluation of the sampler ON the planar layout must reproduce the oracle's draw."""
+    from selfc_b200 import engine
+    b, t, h, w = 2, 3, 4, 5
+    gen = torch.Generator().manual_seed(11)
+    params = torch.randn(b * t, 720, h, w, generator=gen)
+    eps = so.make_eps(b, t, h, w, 3)
+    ref = so.gmm_sample(params, eps, t)
+    m = b * t * h * w
+    planar = engine.gmm_params_to_planar(params)
+    assert planar.shape == (180, m, 4) and planar.is_contiguous()
+    # spot check of the index map: quad j*60 + k*12 + i, element e  <-  channel (4i+e)*15 + k*3 + j of pixel m
+    for (j, k, i, e, mm) in [(0, 0, 0, 0, 0), (1, 3, 7, 2, 17), (2, 4, 11, 3, m - 1)]:
+        n, pix = divmod(mm, h * w)
+        assert planar[j * 60 + k * 12 + i, mm, e] == params[n, (4 * i + e) * 15 + k * 3 + j, pix // w, pix % w]
+    lg, ls, mu = (planar[j * 60:(j + 1) * 60].reshape(5, 12, m, 4).permute(0, 2, 1, 3).reshape(5, m, 48) for j in range(3))
+    pi = torch.softmax(lg, dim=2)                                    # over the 48 HF channels, per component (F3)
+    e = eps.permute(2, 0, 3, 4, 5, 1).reshape(5, m, 48)             # [B,48,5,T,h,w] -> [k, m, hf]
+    v = (pi * (e * torch.exp(ls.clamp(-7, 7)) + mu)).sum(0)          # [m, 48]
+    z = torch.zeros(13, m, 4)
+    z[1:] = v.reshape(m, 12, 4).permute(1, 0, 2)
+    got = engine.gmm_latent_from_planar(z, b * t, h, w)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
