@@ -33,7 +33,14 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 HR_H, HR_W, GOP = 1080, 1920, 7
-METRIC = "1080p 4x rescale frames/s (down+up)"
+METRIC = "1080p 4x rescale frames/s (down+up)"           # BASELINE.json's metric; other --height/--width get their own name
+
+
+def metric_name(hh: int, ww: int) -> str:
+    return METRIC if (hh, ww) == (HR_H, HR_W) else f"{hh}x{ww} 4x rescale frames/s (down+up)"
+
+
+REF_CROP = (272, 480)                                     # --impl reference / cpu_baseline: crop of the clip the CPU arm runs
 FLOP_PER_LR_PX = 10_885_760          # algorithmic conv/linear FLOPs per LR pixel-frame, down + up
 
 
@@ -78,14 +85,25 @@ def gop_slices(frames: int):
     return gop_indices(frames, GOP)
 
 
-def workload_config(args, mode: str):
+def workload_config(args, mode: str, weights: str = "seeded random, reference state_dict layout"):
     hh, ww, frames = args.height, args.width, args.frames
     n_gops = (frames + GOP - 1) // GOP
     return {"workload": f"SelfC-large 4x rescaling (down + 8-bit quantise + up), synthetic UVG-shape {hh}x{ww} "
                         f"{frames}-frame group per GPU per step = {n_gops} GOPs of {GOP} (tail padded), {mode} mode",
             "frames_per_step_per_gpu": frames, "gops_per_launch": max(1, args.gops_per_launch),
-            "weights": "seeded random, reference state_dict layout",
+            "weights": weights,
             "l2": "inputs larger than L2 (one group = %.2f GB fp32)" % (frames * 3 * hh * ww * 4 / 1e9)}
+
+
+def reference_config(args):
+    """What the CPU arm actually runs: a bounded fp32 crop of the same clip, scaled by area to frame equivalents."""
+    hh, ww = args.height, args.width
+    ch, cw = min(REF_CROP[0], hh), min(REF_CROP[1], ww)
+    return {"workload": f"SelfC-large 4x rescaling (down + 8-bit quantise + up) on the host CPU: {GOP} frames of a {ch}x{cw} crop of the "
+                        f"synthetic {hh}x{ww} clip per step, fp32 (the reference's own precision), reported in {hh}x{ww}-frame "
+                        f"equivalents (x {ch * cw / float(hh * ww):.4f} by area); the GPU arm runs the full {args.frames}-frame group",
+            "crop": [ch, cw], "frames_per_step": GOP, "area_scale": ch * cw / float(hh * ww),
+            "weights": "seeded random, reference state_dict layout"}
 
 
 class ClockSampler(threading.Thread):
@@ -129,7 +147,7 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_fps(hh: int, ww: int, steps: int, warmup: int, crop=(272, 480)):
+def cpu_reference_fps(hh: int, ww: int, steps: int, warmup: int, crop=REF_CROP):
     """The reference's CPU path (oracle port, all host threads) on a bounded crop of the 1080p workload: 7 frames of
     crop[0] x crop[1] per step; frames/s in 1080p-frame equivalents = 7 * crop_area / frame_area / seconds."""
     from oracle import selfc_oracle as so
@@ -158,9 +176,9 @@ def run_reference(args):
     if rank != 0:
         return
     fps, ms, cores, sample = cpu_reference_fps(args.height, args.width, max(1, args.steps), max(0, args.warmup))
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric_name(args.height, args.width), "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.mode),
+            "dtype": "f32", "data": "synthetic", "config": reference_config(args),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -171,7 +189,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from selfc_b200.engine import Engine, launch_count
-    from selfc_b200.synthetic import seeded_state_dict, synthetic_net
+    from selfc_b200.synthetic import bench_state_dict, synthetic_net
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,7 +203,9 @@ def run_ours(args):
     hh, ww, frames = args.height, args.width, args.frames
     h, w = hh // 4, ww // 4
     eng = Engine(dev, args.mode)
-    eng.load_state(seeded_state_dict(synthetic_net()[0], 0))
+    # the real SelfC-large checkpoint when $SELFC_CKPT (or pretrained_models/selfc_large_pretrain.pth) exists on this box
+    state, weights_desc = bench_state_dict(synthetic_net()[0], 0)
+    eng.load_state(state)
     group = make_group(frames, hh, ww, 1234 + rank, dev)
     gops = gop_slices(frames)
     gpl = max(1, args.gops_per_launch)
@@ -249,7 +269,7 @@ def run_ours(args):
             # the public host-buffer call: pinned H2D per GOP, rescale, D2H of LR codes + HR frames, copies on side streams
             eng.rescale_host(host_in, host_lr, host_hr, GOP, seed=42, offset0=step_idx * len(gops))
 
-        e_steps = max(1, min(args.steps, 3))
+        e_steps = max(1, args.steps)
         step_e2e(0)
         barrier()
         t0 = time.perf_counter()
@@ -329,10 +349,10 @@ def run_ours(args):
         cpu_baseline = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
 
     whole_tflops = value * (h * w) * FLOP_PER_LR_PX / 1e12
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": metric_name(hh, ww), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(args, args.mode),
+            "config": workload_config(args, args.mode, weights_desc),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "algorithmic_tflops": whole_tflops}
     print(json.dumps(line), flush=True)

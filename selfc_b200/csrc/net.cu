@@ -103,6 +103,27 @@ template <typename T>
 static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pitch, const Dims& d, cudaStream_t st, int k_first = 0,
                            int k_last = 3, const DenseW* W2 = nullptr, T* buf2 = nullptr) {
   const long long slabM = dense_slab(ctx, d);
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // the whole block's conv1..conv4 (conv1..conv3 for cin = 64) as ONE launch with the growth channels kept on chip
+    // (dense_fused.cu); SELFC_DB_FUSED=0 selects the layer-by-layer launches (bit-identical results, A/B and parity tests)
+    static int fused_on = -1;
+    if (fused_on < 0) {
+      const char* e = getenv("SELFC_DB_FUSED");
+      fused_on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const bool dual = W2 != nullptr && W2->tc[0].img_pair != nullptr;
+    if (fused_on && ctx->mode == SELFC_MODE_BF16 && k_first == 0 && k_last == 3 && W.tc[0].img_pair != nullptr && (W2 == nullptr || dual)) {
+      const int L = dense_fused_supported(W.xpad, 4) ? 4 : (dense_fused_supported(W.xpad, 3) ? 3 : 0);
+      if (L > 0) {
+        double flops = 0.0;
+        for (int k = 0; k < L; ++k) flops += 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;
+        PROF(ctx, st, 0, (dual ? 2.0 : 1.0) * flops,
+             launch_dense_fused(W.tc, L, reinterpret_cast<__nv_bfloat16*>(buf), slabM, W.xpad, d.B * d.T, d.h, d.w, st, dual ? W2->tc : nullptr,
+                                dual ? reinterpret_cast<__nv_bfloat16*>(buf2) : nullptr));
+        k_first = L;
+      }
+    }
+  }
   for (int k = k_first; k <= k_last; ++k) {
     const int cin = W.xpad + kGrowth * k;
     const double flops = 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;   // algorithmic (unpadded) FLOPs

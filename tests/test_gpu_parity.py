@@ -16,6 +16,11 @@ pytestmark = pytest.mark.gpu
 
 HR_TOL_FP32 = 1e-3
 HR_TOL_BF16 = 2e-2
+# bf16 mode, LR codes: the north star's gate is "within 1 LSB on >= 99.99 %".  The eight F blocks' bf16 rounding (~5e-4 on a
+# 3.9e-3 code step) moves ~10 % of the codes across a rounding boundary (measured 89.4 % exact); what must NOT happen is a
+# systematic offset, so the exact-match fraction and the mean signed difference are bounded too (and printed).
+LR_EXACT_BF16 = 0.80
+LR_BIAS_BF16 = 0.05
 
 
 @pytest.fixture(scope="module")
@@ -212,8 +217,8 @@ def test_bf16_mode_vs_oracle(dev, b, t, hh, ww):
         lr = so.quantize(z[:, :3])
         hr_ref, hf_ref = so.net_up(sd, lr, eps, t)
     out51, lr_u8, _ = eng.down(x.to(dev), t)
-    diff = (lr_u8.cpu().int() - so.quantize_u8(z[:, :3]).int()).abs()
-    assert diff.max().item() <= 1 and (diff <= 1).float().mean().item() >= 0.9999
+    exact, within1, mx = _report_lr(f"bf16 {b}x{t}x{hh}x{ww}", lr_u8.cpu(), so.quantize_u8(z[:, :3]))
+    assert mx <= 1 and within1 >= 0.9999 and exact >= LR_EXACT_BF16      # a systematic 1-LSB offset would fail here
     hr, hf = eng.up(lr.to(dev), t, eps=eps.to(dev))
     assert (hr.cpu() - hr_ref).abs().max().item() <= HR_TOL_BF16
 
@@ -304,6 +309,110 @@ def test_full_size_bf16_mode_agrees_with_fp32_mode(dev, hh, ww):
     hr16b, _ = e16.up(lr32_q, t, seed=5, offset=2, want_hf=False)
     assert torch.equal(hr16, hr16b) and torch.isfinite(hr16).all()
     assert (hr16 - hr32).abs().max().item() <= 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ benchmark size vs the ORACLE
+def _clip_metrics(hr, ref_frames):
+    ya, y0 = so.rgb_to_y(hr), so.rgb_to_y(ref_frames)
+    return float(np.mean(so.psnr_frames(ya, y0))), float(np.mean(so.ssim_frames(ya, y0)))
+
+
+@pytest.fixture(scope="module")
+def oracle_1080p():
+    """The oracle on TWO different 7-frame 1080p GOPs (BASELINE.json configs[2] size; ~20 s of host time each): latent, LR
+    codes, HR and the per-clip Y-PSNR / Y-SSIM of test_rescaling.py:109-123.  Weights: the real checkpoint when present."""
+    from conftest import test_weights
+    t, hh, ww = 7, 1080, 1920
+    sd, desc = test_weights(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    clips = []
+    for c in range(2):
+        x = so.make_frames(1, t, hh, ww, 4321 + c)
+        eps = so.make_eps(1, t, hh // 4, ww // 4, 17 + c)
+        with torch.no_grad():
+            z = so.net_down(sd, x, t)
+            lr = so.quantize(z[:, :3])
+            hr, _ = so.net_up(sd, lr, eps, t)
+        clips.append({"x": x, "eps": eps, "lr_u8": so.quantize_u8(z[:, :3]), "lr": lr, "hr": hr, "metrics": _clip_metrics(hr, x)})
+        del z
+    print(f"[oracle_1080p] weights: {desc}")
+    return {"sd": sd, "t": t, "clips": clips}
+
+
+def _report_lr(tag, got_u8, ref_u8):
+    d = (got_u8.int() - ref_u8.int()).abs()
+    exact, within1 = (d == 0).float().mean().item(), (d <= 1).float().mean().item()
+    print(f"[{tag}] LR codes: exact match {exact * 100:.4f} %, within 1 LSB {within1 * 100:.4f} %, max |diff| {d.max().item()}, "
+          f"mean signed diff {(got_u8.float() - ref_u8.float()).mean().item():+.2e} LSB")
+    return exact, within1, int(d.max().item())
+
+
+def test_1080p_gop_fp32_mode_vs_oracle(dev, oracle_1080p):
+    """fp32 mode at the benchmark's own size, directly against the oracle: LR exact on >= 99.99 %, HR <= 1e-3, clip metrics."""
+    o, c = oracle_1080p, oracle_1080p["clips"][0]
+    eng = _engine(dev, o["sd"], "fp32")
+    _, lr_u8, _ = eng.down(c["x"].to(dev), o["t"], want_out51=False)
+    exact, within1, mx = _report_lr("1080p fp32", lr_u8.cpu(), c["lr_u8"])
+    assert mx <= 1 and exact >= 0.9999
+    hr, _ = eng.up(c["lr"].to(dev), o["t"], eps=c["eps"].to(dev), want_hf=False)
+    err = (hr.cpu() - c["hr"]).abs().max().item()
+    p, s = _clip_metrics(hr.cpu(), c["x"])
+    print(f"[1080p fp32] HR max |diff| {err:.3e}; Y-PSNR {p:.4f} dB (oracle {c['metrics'][0]:.4f}), Y-SSIM {s:.6f} (oracle {c['metrics'][1]:.6f})")
+    assert err <= HR_TOL_FP32
+    assert abs(p - c["metrics"][0]) <= 0.01 and abs(s - c["metrics"][1]) <= 1e-4
+
+
+def test_1080p_two_gops_bf16_mode_vs_oracle(dev, oracle_1080p):
+    """bf16 mode (the mode the headline number is quoted in) at the benchmark's size with B = 2, directly against the oracle:
+    LR within 1 LSB on >= 99.99 % of the pixels (exact-match fraction and signed bias reported and bounded), HR <= 2e-2, and the
+    north star's per-clip gate (Y-PSNR within 0.01 dB, Y-SSIM within 1e-4) for each clip."""
+    o = oracle_1080p
+    t = o["t"]
+    eng = _engine(dev, o["sd"], "bf16")
+    x = torch.cat([c["x"] for c in o["clips"]], 0).to(dev)
+    ref_u8 = torch.cat([c["lr_u8"] for c in o["clips"]], 0)
+    _, lr_u8, _ = eng.down(x, t, want_out51=False)
+    exact, within1, mx = _report_lr("1080p bf16 B=2", lr_u8.cpu(), ref_u8)
+    assert mx <= 1 and within1 >= 0.9999
+    assert exact >= LR_EXACT_BF16, "a systematic 1-LSB offset would show up as a low exact-match fraction"
+    bias = (lr_u8.cpu().float() - ref_u8.float()).mean().item()
+    assert abs(bias) <= LR_BIAS_BF16, f"LR codes are biased by {bias} LSB against the oracle"
+    lr = torch.cat([c["lr"] for c in o["clips"]], 0).to(dev)
+    eps = torch.cat([c["eps"] for c in o["clips"]], 0).to(dev)
+    hr, _ = eng.up(lr, t, eps=eps, want_hf=False)
+    hr = hr.cpu()
+    for i, c in enumerate(o["clips"]):
+        got = hr[i * t:(i + 1) * t]
+        err = (got - c["hr"]).abs().max().item()
+        p, s = _clip_metrics(got, c["x"])
+        print(f"[1080p bf16 clip {i}] HR max |diff| {err:.3e}; Y-PSNR {p:.4f} dB (oracle {c['metrics'][0]:.4f}), "
+              f"Y-SSIM {s:.6f} (oracle {c['metrics'][1]:.6f})")
+        assert err <= HR_TOL_BF16
+        assert abs(p - c["metrics"][0]) <= 0.01 and abs(s - c["metrics"][1]) <= 1e-4
+
+
+def test_vid4_shape_bf16_mode_metrics_gate(dev):
+    """configs[1] shape (7 x 576 x 704) in bf16 mode: the per-clip Y-PSNR / Y-SSIM gate of the north star, plus LR / HR gates."""
+    from conftest import test_weights
+    b, t, hh, ww = 1, 7, 576, 704
+    sd, _ = test_weights(0)
+    eng = _engine(dev, sd, "bf16")
+    x = so.make_frames(b, t, hh, ww, 1234)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 99)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        z = so.net_down(sd, x, t)
+        lr = so.quantize(z[:, :3])
+        hr_ref, _ = so.net_up(sd, lr, eps, t)
+    _, lr_u8, _ = eng.down(x.to(dev), t, want_out51=False)
+    exact, within1, mx = _report_lr("vid4 bf16", lr_u8.cpu(), so.quantize_u8(z[:, :3]))
+    assert mx <= 1 and within1 >= 0.9999 and exact >= LR_EXACT_BF16
+    hr, _ = eng.up(lr.to(dev), t, eps=eps.to(dev), want_hf=False)
+    assert (hr.cpu() - hr_ref).abs().max().item() <= HR_TOL_BF16
+    p_got, s_got = _clip_metrics(hr.cpu(), x)
+    p_ref, s_ref = _clip_metrics(hr_ref, x)
+    print(f"[vid4 bf16] Y-PSNR {p_got:.4f} dB (oracle {p_ref:.4f}), Y-SSIM {s_got:.6f} (oracle {s_ref:.6f})")
+    assert abs(p_got - p_ref) <= 0.01 and abs(s_got - s_ref) <= 1e-4
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 conv (bf16 mode)
@@ -547,7 +656,8 @@ torch.save({"lr": lr.cpu(), "rec": rec.cpu()}, sys.argv[1])
 
 
 @pytest.mark.parametrize("env", [{"SELFC_TC3_PAIR": "0"}, {"SELFC_TC3_P2": "0"}, {"SELFC_TC3_PAIR": "0", "SELFC_TC3_P2": "0"},
-                                 {"SELFC_ZIGZAG": "0"}])
+                                 {"SELFC_ZIGZAG": "0"}, {"SELFC_DB_FUSED": "0"},
+                                 {"SELFC_DB_FUSED": "0", "SELFC_TC3_PAIR": "0", "SELFC_TC3_P2": "0"}])
 def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
     """CTA pairs (cta_group::2), position-pair TMA rows and the tile-sweep direction change how conv3x3 is scheduled and fed, not
     what it computes: the bf16 path must give bit-identical LR codes and HR frames with each of them switched off (every variant
@@ -559,7 +669,7 @@ def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
     for i, extra in enumerate(({}, env)):
         out = str(tmp_path / f"v{i}.pt")
         e = dict(os.environ)
-        for k in ("SELFC_TC3_PAIR", "SELFC_TC3_P2", "SELFC_ZIGZAG"):
+        for k in ("SELFC_TC3_PAIR", "SELFC_TC3_P2", "SELFC_ZIGZAG", "SELFC_DB_FUSED"):
             e.pop(k, None)
         e.update(extra)
         r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET % here, out], env=e, capture_output=True, text=True, timeout=600)
@@ -567,6 +677,55 @@ def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
         outs.append(torch.load(out))
     assert torch.equal(outs[0]["lr"], outs[1]["lr"])
     assert torch.equal(outs[0]["rec"], outs[1]["rec"])
+
+
+_FUSED_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import selfc_oracle as so
+from selfc_b200.engine import Engine
+dev = torch.device("cuda", 0)
+b, t, h, w = [int(v) for v in sys.argv[2:6]]
+eng = Engine(dev, "bf16"); eng.load_state(so.make_state_dict(3))
+out = {}
+for prefix, cin in (("operations.4.F", 48), ("operations.7.G", 3), ("stp_net.local_m1", 3), ("stp_net.local_m2", 64)):
+    x = (torch.randn(b * t, cin, h, w, generator=torch.Generator().manual_seed(cin + h)) * 0.5).to(dev)
+    out[prefix] = eng.d2dt(prefix, x, t).cpu()                              # conv1..4 (+ conv5) of one dense block
+    xc = (torch.randn(b * t, cin + 96, h, w, generator=torch.Generator().manual_seed(cin + w)) * 0.5).to(dev)
+    out[prefix + ".conv4"] = eng.conv3x3(prefix, 3, xc, t).cpu()            # single layer: always the layer-by-layer kernel
+frames = so.make_frames(b, t, 4 * h, 4 * w, 5).to(dev)
+lr, rec = eng.rescale(frames, t, seed=7, offset=1)                          # the whole path: dual G+H launches, both directions
+out["lr"], out["rec"] = lr.cpu(), rec.cpu()
+torch.save(out, sys.argv[1])
+"""
+
+
+@pytest.mark.parametrize("b,t,h,w", [(1, 2, 9, 14), (1, 3, 37, 121), (2, 7, 64, 112), (1, 7, 135, 250), (1, 1, 270, 480)])
+def test_fused_dense_block_is_bit_identical_to_layer_by_layer(dev, tmp_path, b, t, h, w):
+    """dense_fused_kernel (conv1..4 of a block in one launch, growth channels in tensor memory, strips of 120 columns walked row
+    by row) against four conv3x3_tc3_kernel launches: same MMAs in the same K order and the same epilogue arithmetic, so the
+    dense blocks' outputs, the LR codes and the HR frames must be IDENTICAL.  Shapes: one partial strip; a strip boundary one
+    column wide (121); Vimeo LR shape with B = 2; several strips, odd strip-column count and row ranges that cross column
+    boundaries; one full 1080p LR frame (4 exact strips, an odd number of strip columns per pair walk)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for i, extra in enumerate(({}, {"SELFC_DB_FUSED": "0"})):
+        out = str(tmp_path / f"f{i}.pt")
+        e = dict(os.environ)
+        e.pop("SELFC_DB_FUSED", None)
+        e.update(extra)
+        r = subprocess.run([sys.executable, "-c", _FUSED_SNIPPET % here, out, str(b), str(t), str(h), str(w)], env=e, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(out))
+    for k in outs[0]:
+        same = torch.equal(outs[0][k], outs[1][k])
+        if not same:
+            d = (outs[0][k].float() - outs[1][k].float()).abs()
+            print(f"[fused vs layer-by-layer] {k}: max |diff| {d.max().item():.3e}, differing {100.0 * (d > 0).float().mean().item():.3f} %")
+        assert same, f"{k} differs between the fused and the layer-by-layer dense block"
 
 
 # ------------------------------------------------------------------------------------------------ f1: metrics kernels
