@@ -27,10 +27,10 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
                       const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr);
 
 // ---- dense_fused.cu: conv1..convL of a dense block in ONE launch, growth channels kept in tensor memory ----------------
-// w[0..L-1] = the block's conv_k weights (TcConvW::img_pair is what the kernel reads), L = 4 (or 3 when the fourth layer's
-// weights do not fit shared memory next to the X ring: cin = 64).  Reads channels [0,cin) of the slab-planar buffer, writes
+// w[0..L-1] = the block's conv_k weights (TcConvW::img_pair is what the kernel reads), L = dense_fused_layers(cin): 4, or 3 when the fourth layer's
+// weights do not fit shared memory next to the X ring (cin = 64).  Reads channels [0,cin) of the slab-planar buffer, writes
 // x1..xL to [cin, cin + 32 L); bit-identical to L launches of launch_conv3x3_tc.  (w2, buf2): second problem of the same shape.
-bool dense_fused_supported(int cin, int L);
+int dense_fused_layers(int cin);      // how many layers (4, 3 or 0 = unsupported) one launch fuses for this X width
 int launch_dense_fused(const TcConvW* w, int L, __nv_bfloat16* buf, long long slabM, int cin, int N, int h, int wd, cudaStream_t st,
                        const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr);
 

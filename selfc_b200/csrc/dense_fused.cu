@@ -49,27 +49,34 @@ constexpr int NB = 3 * NOUT;                  // 96
 constexpr int NBH = NB / 2;                   // weight rows per CTA of the pair
 constexpr int WT_BYTES = NBH * 16 * 2;        // one (ky, K-step) B tile of one CTA: 1536
 constexpr int SLAB_ROW = MPOS * 32;           // one 16-channel slab of one strip row: 4 KB
-constexpr int NXR = 8;                        // X ring slots (rows)
-constexpr int NACC = 3;                       // accumulators in rotation
+constexpr int NACC = 2;                       // accumulators: group g uses g & 1, and is drained by epilogue team g & 1
 constexpr int MAXL = 4;
-constexpr int THREADS = 320;
+constexpr int EPI_WARPS = 16;                 // two teams x two channel halves x four lane quarters
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
-constexpr int RING_COL0 = NACC * NB;          // 288
+constexpr int RING_COL0 = NACC * NB;          // 192
 constexpr int BAR_BYTES = 512;
-constexpr int NRING_MAX = 14;                 // growth-ring slots of all layers (6 + 5 + 3 for L = 4)
-constexpr int XBUF_BYTES = 2 * 2 * 4 * 2 * 16 * 4;      // [warpgroup][parity][quarter][side][16] floats
+constexpr int NXR_MAX = 16;
+constexpr int NRING_MAX = 18;                 // growth-ring slots of all layers (8 + 6 + 4)
+constexpr int XBUF_BYTES = 2 * 2 * 2 * 4 * 2 * 16 * 4;      // [team][channel half][parity][quarter][side][16] floats
 constexpr int BIAS_BYTES = MAXL * NOUT * 4;
 
-// schedule tables (see the header comment); L = number of fused layers
-__host__ __device__ constexpr int lag_of(int L, int j) { return L == 4 ? (j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 3 : 4) : (j == 0 ? 0 : j == 1 ? 1 : 3); }
-__host__ __device__ constexpr int order_of(int L, int oi) { return L == 4 ? (oi == 0 ? 0 : oi == 1 ? 2 : oi == 2 ? 1 : 3) : (oi == 0 ? 0 : oi == 1 ? 2 : 1); }
-__host__ __device__ constexpr int ring_of(int L, int j) { return L == 4 ? (j == 0 ? 6 : j == 1 ? 5 : 3) : (j == 0 ? 5 : 3); }
-__host__ __device__ constexpr int ringcol_of(int L, int j) {
-  return RING_COL0 + (j == 0 ? 0 : j == 1 ? 16 * ring_of(L, 0) : 16 * (ring_of(L, 0) + ring_of(L, 1)));
-}
-__host__ __device__ constexpr int ringslot0_of(int L, int j) { return (ringcol_of(L, j) - RING_COL0) / 16; }      // first global slot index
-static_assert(ringcol_of(4, 2) + 16 * ring_of(4, 2) <= TMEM_COLS, "TMEM budget");
-static_assert(ringslot0_of(4, 2) + ring_of(4, 2) <= 14, "ring slot barriers");
+// Row schedules (SCH): which row of which layer a step issues, in which order, and the ring sizes that follow from it (a ring slot
+// may be overwritten once every reader of its row has been ISSUED before the overwriting row's own MMAs; verified by simulation).
+//   SCH 0  L = 4, lags 0,2,4,6, order conv1,conv2,conv3,conv4: every consumer reads rows stored a whole step earlier.  Rings
+//          8 + 6 + 4 rows, 9 live X rows (16-slot ring): X of 1 slab (G, H, local_m1).
+//   SCH 1  L = 4, lags 0,2,4,5, order conv3,conv1,conv2,conv4: conv4 reads the x3 row conv3 stored two groups earlier in the same
+//          step.  Rings 7 + 5 + 3, 8 live X rows (9-slot ring): what fits next to 108 KB of weights when X has 3 slabs (F).
+//   SCH 2  L = 3, lags 0,2,4: rings 6 + 4, 7 live X rows (8-slot ring): X of 4 slabs (STP 64 -> 64; conv4 runs layer-by-layer).
+__host__ __device__ constexpr int nlayers_of(int SCH) { return SCH == 2 ? 3 : 4; }
+__host__ __device__ constexpr int lag_of(int SCH, int j) { return SCH == 1 ? (j == 3 ? 5 : 2 * j) : 2 * j; }
+__host__ __device__ constexpr int order_of(int SCH, int oi) { return SCH == 1 ? (oi == 0 ? 2 : oi == 1 ? 0 : oi == 2 ? 1 : 3) : oi; }
+__host__ __device__ constexpr int ring_of(int SCH, int j) { return SCH == 0 ? 8 - 2 * j : SCH == 1 ? 7 - 2 * j : 6 - 2 * j; }
+__host__ __device__ constexpr int nxr_of(int SCH) { return SCH == 0 ? 16 : SCH == 1 ? 9 : 8; }
+__host__ __device__ constexpr int ringslot0_of(int SCH, int j) { return j == 0 ? 0 : j == 1 ? ring_of(SCH, 0) : ring_of(SCH, 0) + ring_of(SCH, 1); }
+__host__ __device__ constexpr int ringcol_of(int SCH, int j) { return RING_COL0 + 16 * ringslot0_of(SCH, j); }
+static_assert(ringcol_of(0, 2) + 16 * ring_of(0, 2) <= TMEM_COLS, "TMEM budget");
+static_assert(ringslot0_of(0, 2) + ring_of(0, 2) <= NRING_MAX, "ring slot barriers");
 
 struct Params {
   const void* wimg[2][MAXL];     // per problem, per layer: TcConvW::img_pair (two halves of the B image)
@@ -80,6 +87,7 @@ struct Params {
   int N, h, w, S, ncol;          // S strips per image row, ncol = N * S strip columns
   int piece_len, total_pr;       // a CTA pair owns piece_len consecutive rows of the (column pair, row) sequence
   int* err;
+  long long* dbg;                // SELFC_TC_DBG=1: CTA 0's barrier-wait cycles per role (tc::debug_next_slot)
 };
 
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -88,14 +96,32 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// A operand in tensor memory (lane = row, 8 columns = 16 bf16 of K)
-__device__ __forceinline__ void umma2_ts_bf16_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// Pair MMAs issued by one elected lane when `valid` (a warp-uniform flag): skipping an out-of-image tap must not put a branch
+// around the instruction -- with one basic block per MMA the compiler re-materialises every descriptor through R2UR moves
+// (~90 cycles per issue instead of a handful of uniform-datapath instructions).
+__device__ __forceinline__ void umma2_ss_bf16_elect_if(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                                       uint32_t valid) {
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
+      "{\n\t.reg .pred p, q, v;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 v, %5, 0;\n\t"
+      "and.pred q, q, v;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(valid)
+      : "memory");
+}
+// A operand in tensor memory (lane = row, 8 columns = 16 bf16 of K)
+__device__ __forceinline__ void umma2_ts_bf16_elect_if(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                                       uint32_t valid) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, v;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 v, %5, 0;\n\t"
+      "and.pred q, q, v;\n\t"
       "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(valid)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
@@ -108,6 +134,40 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Barrier waits of this kernel are on the critical path of every row (producer -> epilogue -> consumer), unlike the tile kernels
+// whose waits mostly find the phase complete: poll without a suspend-time hint (the hinted form parks the warp and wakes late).
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_nohint(bar, parity)) {
+    if (++spins > (1u << 26)) {       // a protocol bug traps (launch error) instead of hanging the GPU
+      if (err) atomicExch(err, code);
+      __trap();
+    }
+  }
+}
+
+// the same, accumulating the cycles spent waiting when the debug counters are on
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int* err, int code, bool timed, long long& acc) {
+  if (timed) {
+    const long long t0 = clock64();
+    mbar_wait_fast(bar, parity, err, code);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait_fast(bar, parity, err, code);
+  }
 }
 
 template <int V> using IC = std::integral_constant<int, V>;
@@ -128,9 +188,12 @@ __device__ __forceinline__ bool next_seg(int& cur, int pr_end, int h, uint32_t c
   return true;
 }
 
-template <int L>
+template <int SCH, int NX, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                   const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  constexpr int L = nlayers_of(SCH);
+  constexpr int NXR = nxr_of(SCH);
+  constexpr int DMAX = lag_of(SCH, L - 1);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t crank = cluster_ctarank();               // 0 = leader
   const int unit = (int)(blockIdx.x >> 1);
@@ -138,27 +201,29 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
   const int piece = p.nprob == 2 ? (unit >> 1) : unit;
   const CUtensorMap* tmap = prob ? &tmap_b : &tmap_a;
   __nv_bfloat16* obuf = p.buf[prob];
-  const int nx = p.nx, h = p.h;
-  const int xrow_bytes = nx * SLAB_ROW;
+  constexpr int nx = NX;                                  // 16-channel slabs of X: compile-time, so every descriptor offset folds
+  const int h = p.h;
+  constexpr int xrow_bytes = nx * SLAB_ROW;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   // [X ring][weights of the L layers][barriers][exchange][bias]
   const uint32_t x_base = base;
   const uint32_t w_base = base + NXR * xrow_bytes;
-  const int wtotal = 3 * WT_BYTES * (L * nx + L * (L - 1));          // sum_j 3 * (nx + 2j) tiles
+  constexpr int wtotal = 3 * WT_BYTES * (L * nx + L * (L - 1));      // sum_j 3 * (nx + 2j) tiles
   const uint32_t bar_base = w_base + wtotal;
   float* xbuf = reinterpret_cast<float*>(gen_base + (bar_base - base) + BAR_BYTES);
   float* sbias = reinterpret_cast<float*>(gen_base + (bar_base - base) + BAR_BYTES + XBUF_BYTES);
   auto xfull = [&](int s) { return bar_base + 8u * s; };
-  auto xempty = [&](int s) { return bar_base + 8u * (NXR + s); };
-  const uint32_t w_bar = bar_base + 8u * (2 * NXR);
-  const uint32_t wpeer_bar = bar_base + 8u * (2 * NXR + 1);
-  auto tfull = [&](int a) { return bar_base + 8u * (2 * NXR + 2 + a); };
-  auto tempty = [&](int a) { return bar_base + 8u * (2 * NXR + 2 + NACC + a); };
+  auto xempty = [&](int s) { return bar_base + 8u * (NXR_MAX + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * NXR_MAX);
+  const uint32_t wpeer_bar = bar_base + 8u * (2 * NXR_MAX + 1);
+  auto tfull = [&](int a) { return bar_base + 8u * (2 * NXR_MAX + 2 + a); };
+  auto tempty = [&](int a) { return bar_base + 8u * (2 * NXR_MAX + 2 + NACC + a); };
   // one "row stored" barrier per growth-ring slot (a single barrier per layer could be lapped: at the start of a row range a
   // layer produces several rows before its consumer's first wait, and an mbarrier only tells the last two phases apart)
-  auto gready = [&](int slot_global) { return bar_base + 8u * (2 * NXR + 2 + 2 * NACC + slot_global); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * NXR + 2 + 2 * NACC + NRING_MAX);
+  auto gready = [&](int slot_global) { return bar_base + 8u * (2 * NXR_MAX + 2 + 2 * NACC + slot_global); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NXR_MAX + 2 + 2 * NACC + NRING_MAX);
+  static_assert(8 * (2 * NXR_MAX + 2 + 2 * NACC + NRING_MAX + 1) <= BAR_BYTES, "barrier block");
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -173,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
     mbar_init(wpeer_bar, 1);
     for (int a = 0; a < NACC; ++a) {
       mbar_init(tfull(a), 1);
-      mbar_init(tempty(a), 16);          // 8 epilogue warps of each CTA release the leader's accumulator
+      mbar_init(tempty(a), 16);          // the 8 warps of one epilogue team in each CTA release the leader's accumulator
     }
     for (int j = 0; j < NRING_MAX; ++j) mbar_init(gready(j), 16);
     fence_barrier_init();
@@ -192,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
 
   const int pr_begin = piece * p.piece_len;
   const int pr_end = pr_begin + p.piece_len < p.total_pr ? pr_begin + p.piece_len : p.total_pr;
-  constexpr int DMAX = lag_of(L, L - 1);
+  const bool timed = DBG && p.dbg != nullptr && blockIdx.x == 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -205,20 +270,24 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
         off += bytes;
       }
       pdl_wait();      // weights are static; activations come from the previous kernel in the stream
-      int q = 0;
+      int slot = 0;
+      uint32_t ph = 0;
       int cur = pr_begin;
       Seg sg;
+      long long w_xempty = 0;
+      const long long t_start = DBG ? clock64() : 0;
       while (next_seg(cur, pr_end, h, crank, sg)) {
         const int n = sg.col < p.ncol ? sg.col / p.S : p.N;              // dummy column of an odd pair: rows past the tensor -> zeros
         const int xs = (sg.col < p.ncol ? (sg.col % p.S) : 0) * VALID - HALO;
         const int rho0 = sg.r0 - L > 0 ? sg.r0 - L : 0, rho1 = sg.r1 + L < h ? sg.r1 + L : h;
-        for (int rho = rho0; rho < rho1; ++rho, ++q) {
-          const int slot = q & (NXR - 1);
-          mbar_wait(xempty(slot), (((uint32_t)q / NXR) & 1u) ^ 1u, p.err, 41);
+        for (int rho = rho0; rho < rho1; ++rho) {
+          mbar_wait_t(xempty(slot), ph ^ 1u, p.err, 41, timed, w_xempty);
           if (crank == 0) mbar_expect_tx(xfull(slot), 2u * (uint32_t)xrow_bytes);     // both CTAs' boxes land on the leader's barrier
           tma_load_4d_pair(x_base + slot * xrow_bytes, tmap, mapa_u32(xfull(slot), 0), 0, xs, n * h + rho, 0);
+          if (++slot == NXR) { slot = 0; ph ^= 1u; }
         }
       }
+      if (timed) { p.dbg[0] = w_xempty; p.dbg[1] = clock64() - t_start; }
     }
   } else if (warp == 1) {
     if (crank != 0) {
@@ -231,11 +300,16 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
       const uint32_t hi_b = desc_hi(128, 0);             // weights: no-swizzle core matrices, 8-row groups 128 bytes apart
       mbar_wait(w_bar, 0, p.err, 42);
       mbar_wait(wpeer_bar, 0, p.err, 43);
-      int q_base = 0, xw = 0, gcnt = 0;
+      const uint32_t xlo_base = desc_lo(x_base, 16);                    // descriptor low words: + (byte offset >> 4)
+      const uint32_t wlo_base = desc_lo(w_base, (NBH / 8) * 128);
+      int q_base = 0, xw = 0, gcnt = 0;   // q_base / xw: X rows loaded before this segment / observed (running counts)
       int ev[MAXL] = {0, 0, 0, 0};        // rows of layer j whose "stored" barrier has been observed (running count)
       int prod[MAXL] = {0, 0, 0, 0};      // rows of layer j issued so far (running count): row's ring slot = count % ring
       int cur = pr_begin;
       Seg sg;
+      long long w_tempty = 0, w_xfull = 0, w_gready[MAXL] = {0, 0, 0, 0};
+      int nsteps = 0;
+      const long long t_start = DBG ? clock64() : 0;
       while (next_seg(cur, pr_end, h, crank, sg)) {
         const int r0 = sg.r0, r1 = sg.r1;
         const int rho0 = r0 - L > 0 ? r0 - L : 0, rho1 = r1 + L < h ? r1 + L : h;
@@ -243,20 +317,21 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < MAXL; ++j) cb[j] = prod[j];
         const int s_first = r0 - (L - 1) > 0 ? r0 - (L - 1) : 0, s_last = r1 - 1 + DMAX;
+        nsteps += s_last - s_first + 1;
         for (int s = s_first; s <= s_last; ++s) {
           auto group = [&](auto OI) {
-            constexpr int J = order_of(L, decltype(OI)::value);
-            const int r = s - lag_of(L, J);
+            constexpr int J = order_of(SCH, decltype(OI)::value);
+            const int r = s - lag_of(SCH, J);
             const int lo = r0 - (L - 1 - J) > 0 ? r0 - (L - 1 - J) : 0, hi = r1 + (L - 1 - J) < h ? r1 + (L - 1 - J) : h;
             if (r < lo || r >= hi) return;
-            const int acc = gcnt % NACC;
-            const uint32_t use = (uint32_t)(gcnt / NACC);
-            mbar_wait(tempty(acc), (use & 1u) ^ 1u, p.err, 44);
+            const int acc = gcnt & 1;
+            const uint32_t use = (uint32_t)(gcnt >> 1);
+            mbar_wait_t(tempty(acc), (use & 1u) ^ 1u, p.err, 44, timed, w_tempty);
             if constexpr (J == 0) {
               const int last = r + 1 < rho1 - 1 ? r + 1 : rho1 - 1;
               const int need = q_base + (last - rho0) + 1;
               while (xw < need) {
-                mbar_wait(xfull(xw & (NXR - 1)), ((uint32_t)xw / NXR) & 1u, p.err, 45);
+                mbar_wait_t(xfull(xw % NXR), ((uint32_t)xw / NXR) & 1u, p.err, 45, timed, w_xfull);
                 ++xw;
               }
             } else {
@@ -264,57 +339,52 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
               const int last = r + 1 < hi_p - 1 ? r + 1 : hi_p - 1;
               const int target = cb[J - 1] + (last - lo_p) + 1;
               while (ev[J - 1] < target) {
-                constexpr int RG = ring_of(L, J - 1);
+                constexpr int RG = ring_of(SCH, J - 1);
                 const int c = ev[J - 1];
-                mbar_wait(gready(ringslot0_of(L, J - 1) + c % RG), (uint32_t)(c / RG) & 1u, p.err, 46);
+                mbar_wait_t(gready(ringslot0_of(SCH, J - 1) + c % RG), (uint32_t)(c / RG) & 1u, p.err, 46, timed, w_gready[J - 1]);
                 ++ev[J - 1];
               }
             }
             tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)(acc * NB);
-            const int nks = nx + 2 * J;
-            const uint32_t wj = w_base + (uint32_t)(3 * WT_BYTES * (J * nx + J * (J - 1)));
-            const uint32_t b_ky = (uint32_t)nks * (WT_BYTES >> 4);
-            uint32_t accum = 0;
-            bool ok[3];
+            constexpr int nks = nx + 2 * J;
+            constexpr uint32_t wj_off = (uint32_t)(3 * WT_BYTES * (J * nx + J * (J - 1)));      // this layer's B image inside the weights
+            constexpr uint32_t b_ky = (uint32_t)nks * (WT_BYTES >> 4);
+            uint32_t ok[3];
             uint32_t xa[3];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
               const int rr = r + ky - 1;
-              ok[ky] = rr >= 0 && rr < h;
-              xa[ky] = x_base + (uint32_t)(((q_base + rr - rho0) & (NXR - 1)) * xrow_bytes);
+              ok[ky] = (rr >= 0 && rr < h) ? 1u : 0u;
+              xa[ky] = xlo_base + (uint32_t)(((q_base + (ok[ky] ? rr - rho0 : 0)) % NXR) * (xrow_bytes >> 4));
             }
+            // the accumulator is overwritten by the first tap issued: (K-step 0, ky = 0), or ky = 1 when row r - 1 is outside the image
+            const uint32_t acc_k0[3] = {0u, ok[0], 1u};
             // K order = the dense buffer's channel order [X | x1 | x2 | x3], ky inner: the order of the unfused kernel
+#pragma unroll
             for (int ks = 0; ks < nx; ++ks) {
-              const uint32_t b_lo = desc_lo(wj + (uint32_t)ks * WT_BYTES, (NBH / 8) * 128);
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
-                if (!ok[ky]) continue;
-                const uint64_t ad = desc_join(desc_lo(xa[ky] + (uint32_t)ks * SLAB_ROW, 16), hi_a);
-                const uint64_t bd = desc_join(b_lo + (uint32_t)ky * b_ky, hi_b);
-                umma2_bf16_elect(d, ad, bd, idesc, accum);
-                accum = 1;
+                const uint64_t ad = desc_join(xa[ky] + (uint32_t)(ks * (SLAB_ROW >> 4)), hi_a);
+                const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)ks * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
+                umma2_ss_bf16_elect_if(d, ad, bd, idesc, ks == 0 ? acc_k0[ky] : 1u, ok[ky]);
               }
             }
 #pragma unroll
             for (int g = 0; g < J; ++g) {
               uint32_t ga[3];
-#pragma unroll
               const int lo_g = r0 - (L - 1 - g) > 0 ? r0 - (L - 1 - g) : 0;
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
                 const int cnt = ok[ky] ? cb[g] + (r + ky - 1 - lo_g) : 0;
-                ga[ky] = tmem_base + (uint32_t)(ringcol_of(L, g) + (cnt % ring_of(L, g)) * 16);
+                ga[ky] = tmem_base + (uint32_t)(ringcol_of(SCH, g) + (cnt % ring_of(SCH, g)) * 16);
               }
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
-                const uint32_t b_lo = desc_lo(wj + (uint32_t)(nx + 2 * g + half) * WT_BYTES, (NBH / 8) * 128);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
-                  if (!ok[ky]) continue;
-                  const uint64_t bd = desc_join(b_lo + (uint32_t)ky * b_ky, hi_b);
-                  umma2_ts_bf16_elect(d, ga[ky] + (uint32_t)(half * 8), bd, idesc, accum);
-                  accum = 1;
+                  const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)(nx + 2 * g + half) * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
+                  umma2_ts_bf16_elect_if(d, ga[ky] + (uint32_t)(half * 8), bd, idesc, 1u, ok[ky]);
                 }
               }
             }
@@ -328,26 +398,41 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
           if constexpr (L > 3) group(IC<3>{});
           // X row s - DMAX - 1 has no reader left
           const int f = s - DMAX - 1;
-          if (f >= rho0 && f < rho1) umma2_commit_elect(xempty((q_base + f - rho0) & (NXR - 1)));
+          if (f >= rho0 && f < rho1) umma2_commit_elect(xempty((q_base + f - rho0) % NXR));
         }
-        for (int f = (r1 - 1 > rho0 ? r1 - 1 : rho0); f < rho1; ++f) umma2_commit_elect(xempty((q_base + f - rho0) & (NXR - 1)));
+        for (int f = (s_last - DMAX > rho0 ? s_last - DMAX : rho0); f < rho1; ++f) umma2_commit_elect(xempty((q_base + f - rho0) % NXR));
         q_base += rho1 - rho0;
+      }
+      if (timed && lane == 0) {
+        p.dbg[2] = w_tempty; p.dbg[3] = w_xfull; p.dbg[4] = w_gready[0]; p.dbg[5] = w_gready[1]; p.dbg[6] = w_gready[2];
+        p.dbg[7] = clock64() - t_start; p.dbg[8] = nsteps; p.dbg[9] = gcnt;
       }
     }
   } else {
-    // ===================== epilogue warps 2..9: two warpgroups x four lane quarters =====================
-    const int wg = (warp - 2) >> 2;              // output channels 16 wg .. 16 wg + 15
+    // ===================== epilogue warps 2..17: two teams x two channel halves x four lane quarters =====================
+    // Team t drains the groups with (running group count & 1) == t, i.e. accumulator t: two rows' epilogues are in flight at a time.
+    const int ew = warp - 2;
+    const int team = ew >> 3;
+    const int wg = (ew >> 2) & 1;                // output channels 16 wg .. 16 wg + 15
     const int q = warp & 3;                      // TMEM lane quarter = positions 32 q .. 32 q + 31 of the strip row
     const int i = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t tempty_leader0 = mapa_u32(tempty(0), 0);
+    const uint32_t tempty_leader = mapa_u32(tempty(team), 0);
     const uint32_t gready_leader0 = mapa_u32(gready(0), 0);
+    const uint32_t tfull_bar = tfull(team);
+    const uint32_t trow = lane_addr + (uint32_t)(team * NB + wg * 16);
+    const int bar_id = 1 + team * 2 + wg;
     const size_t slab_elems = (size_t)p.slabM * 16;
+    const bool edge_l = lane == 0, edge_r = lane == 31;
+    const bool has_l = q > 0, has_r = q < 3;     // the strip's first / last position has no neighbour
     pdl_wait();
     int gcnt = 0;
     int cnt[MAXL] = {0, 0, 0, 0};         // rows of layer j stored so far: ring slot = count % ring (the MMA warp counts the same)
     int cur = pr_begin;
     Seg sg;
+    long long w_tfull = 0;
+    int mine = 0;
+    const long long t_start = DBG ? clock64() : 0;
     while (next_seg(cur, pr_end, h, crank, sg)) {
       const int r0 = sg.r0, r1 = sg.r1;
       const bool col_ok = sg.col < p.ncol;
@@ -355,71 +440,88 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
       const int x = (col_ok ? (sg.col % p.S) : 0) * VALID - HALO + i;
       const bool inimg = col_ok && x >= 0 && x < p.w;
       const bool store_col = inimg && i >= HALO && i < MPOS - HALO;
+      const uint32_t keep = inimg ? 0xffffffffu : 0u;       // columns outside the image are the next layer's zero padding
+      __nv_bfloat16* ocol = obuf + (size_t)(nx + wg) * slab_elems + ((size_t)n * h * p.w + x) * 16;
       const int s_first = r0 - (L - 1) > 0 ? r0 - (L - 1) : 0, s_last = r1 - 1 + DMAX;
       for (int s = s_first; s <= s_last; ++s) {
         auto group = [&](auto OI) {
-          constexpr int J = order_of(L, decltype(OI)::value);
-          const int r = s - lag_of(L, J);
+          constexpr int J = order_of(SCH, decltype(OI)::value);
+          const int r = s - lag_of(SCH, J);
           const int lo = r0 - (L - 1 - J) > 0 ? r0 - (L - 1 - J) : 0, hi = r1 + (L - 1 - J) < h ? r1 + (L - 1 - J) : h;
           if (r < lo || r >= hi) return;
-          const int acc = gcnt % NACC;
-          const uint32_t use = (uint32_t)(gcnt / NACC);
-          mbar_wait(tfull(acc), use & 1u, p.err, 47);
+          const int g = gcnt++;
+          int slot = 0;
+          if constexpr (J < L - 1) slot = cnt[J]++ % ring_of(SCH, J);
+          if ((g & 1) != team) return;
+          const uint32_t use = (uint32_t)(g >> 1);
+          mbar_wait_t(tfull_bar, use & 1u, p.err, 47, timed, w_tfull);
           tc_fence_after();
           uint32_t a0[16], a1[16], a2[16];
-          const uint32_t trow = lane_addr + (uint32_t)(acc * NB + wg * 16);
           tmem_ld16(trow, a0);
           tmem_ld16(trow + NOUT, a1);
           tmem_ld16(trow + 2 * NOUT, a2);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8u * (uint32_t)acc);
-          // neighbours across the quarter boundaries: lane 31's kx=0 partials go right, lane 0's kx=2 partials go left
-          float* xb = xbuf + (size_t)((wg * 2 + (gcnt & 1)) * 4) * 32;
-          if (lane == 31) {
+          if (lane == 0) mbar_arrive_cluster(tempty_leader);
+          // neighbours across the quarter boundaries: lane 31's kx=0 partials go right, lane 0's kx=2 partials go left.
+          // Branch-free on purpose: a divergent region costs ~70 cycles here and this is the per-row critical path.
+          float* xb = xbuf + (size_t)(((team * 2 + wg) * 2 + (use & 1)) * 4) * 32;
+          if (edge_l || edge_r) {
+            float4* dst = reinterpret_cast<float4*>(xb + (q * 2 + (edge_l ? 1 : 0)) * 16);
 #pragma unroll
-            for (int t = 0; t < 16; ++t) xb[(q * 2 + 0) * 16 + t] = __uint_as_float(a0[t]);
+            for (int t = 0; t < 16; t += 4)
+              dst[t / 4] = edge_l ? make_float4(__uint_as_float(a2[t]), __uint_as_float(a2[t + 1]), __uint_as_float(a2[t + 2]), __uint_as_float(a2[t + 3]))
+                                  : make_float4(__uint_as_float(a0[t]), __uint_as_float(a0[t + 1]), __uint_as_float(a0[t + 2]), __uint_as_float(a0[t + 3]));
           }
-          if (lane == 0) {
+          named_bar_sync(bar_id, 128);
+          // every lane reads both edge vectors of its quarter's neighbours (broadcast loads), lanes 0 / 31 select them
+          float el[16], er[16];
+          {
+            const float4* pl = reinterpret_cast<const float4*>(xb + ((has_l ? q - 1 : 0) * 2 + 0) * 16);
+            const float4* pr = reinterpret_cast<const float4*>(xb + ((has_r ? q + 1 : 3) * 2 + 1) * 16);
 #pragma unroll
-            for (int t = 0; t < 16; ++t) xb[(q * 2 + 1) * 16 + t] = __uint_as_float(a2[t]);
+            for (int t = 0; t < 16; t += 4) {
+              const float4 a = pl[t / 4], b = pr[t / 4];
+              el[t] = a.x; el[t + 1] = a.y; el[t + 2] = a.z; el[t + 3] = a.w;
+              er[t] = b.x; er[t + 1] = b.y; er[t + 2] = b.z; er[t + 3] = b.w;
+            }
           }
-          named_bar_sync(1 + wg, 128);
           float v[16];
 #pragma unroll
           for (int t = 0; t < 16; ++t) {
-            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(a0[t]), 1);
-            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(a2[t]), 1);
-            if (lane == 0) left = q > 0 ? xb[((q - 1) * 2 + 0) * 16 + t] : 0.f;
-            if (lane == 31) right = q < 3 ? xb[((q + 1) * 2 + 1) * 16 + t] : 0.f;
-            const float o = lrelu02(left + __uint_as_float(a1[t]) + right + sbias[J * NOUT + wg * 16 + t]);
-            v[t] = inimg ? o : 0.f;            // columns outside the image are the next layer's zero padding
+            const float sl = __shfl_up_sync(0xffffffffu, __uint_as_float(a0[t]), 1);
+            const float sr = __shfl_down_sync(0xffffffffu, __uint_as_float(a2[t]), 1);
+            const float left = edge_l ? (has_l ? el[t] : 0.f) : sl;
+            const float right = edge_r ? (has_r ? er[t] : 0.f) : sr;
+            v[t] = lrelu02(left + __uint_as_float(a1[t]) + right + sbias[J * NOUT + wg * 16 + t]);
           }
           uint32_t pk[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) pk[t] = pack_bf2(v[2 * t], v[2 * t + 1]);
+          for (int t = 0; t < 8; ++t) pk[t] = pack_bf2(v[2 * t], v[2 * t + 1]) & keep;
           if constexpr (J < L - 1) {
-            const int slot = cnt[J] % ring_of(L, J);
-            tmem_st8(lane_addr + (uint32_t)(ringcol_of(L, J) + slot * 16 + wg * 8), pk);
+            tmem_st8(lane_addr + (uint32_t)(ringcol_of(SCH, J) + slot * 16 + wg * 8), pk);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(gready_leader0 + 8u * (uint32_t)(ringslot0_of(L, J) + slot));
-            ++cnt[J];
+            if (lane == 0) mbar_arrive_cluster(gready_leader0 + 8u * (uint32_t)(ringslot0_of(SCH, J) + slot));
           }
           if (store_col && r >= r0 && r < r1) {
-            __nv_bfloat16* o = obuf + (size_t)(nx + 2 * J + wg) * slab_elems + ((size_t)((size_t)n * h + r) * p.w + x) * 16;
+            __nv_bfloat16* o = ocol + (size_t)(2 * J) * slab_elems + (size_t)r * p.w * 16;
             *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          ++gcnt;
+          ++mine;
         };
         group(IC<0>{});
         group(IC<1>{});
         group(IC<2>{});
         if constexpr (L > 3) group(IC<3>{});
       }
+    }
+    if (timed && (threadIdx.x == 64 || threadIdx.x == 64 + 256)) {
+      long long* d = p.dbg + 10 + 3 * team;
+      d[0] = w_tfull; d[1] = clock64() - t_start; d[2] = mine;
     }
   }
 
@@ -432,24 +534,35 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
   }
 }
 
-static int smem_bytes(int L, int nx) {
-  return 1024 + NXR * nx * SLAB_ROW + 3 * WT_BYTES * (L * nx + L * (L - 1)) + BAR_BYTES + XBUF_BYTES + BIAS_BYTES;
+static int smem_bytes(int sch, int nx) {
+  const int L = nlayers_of(sch);
+  return 1024 + nxr_of(sch) * nx * SLAB_ROW + 3 * WT_BYTES * (L * nx + L * (L - 1)) + BAR_BYTES + XBUF_BYTES + BIAS_BYTES;
+}
+// One instantiation per X width the network has -- 1 slab (G, H, local_m1), 3 (F), 4 (the STP 64 -> 64 blocks) -- each with the
+// deepest schedule whose X ring and weights fit shared memory; -1: not built for this width (the caller runs layer by layer).
+static int pick_schedule(int nx, int max_layers) {
+  const int sch = nx == 1 ? 0 : nx == 3 ? 1 : nx == 4 ? 2 : -1;
+  if (sch < 0 || nlayers_of(sch) > max_layers || smem_bytes(sch, nx) > 227 * 1024) return -1;
+  return sch;
 }
 
 }  // namespace dbf
 
-bool dense_fused_supported(int cin, int L) {
-  if (cin % 16 != 0 || (L != 3 && L != 4)) return false;
-  return dbf::smem_bytes(L, cin / 16) <= 227 * 1024;
+int dense_fused_layers(int cin) {
+  if (cin % 16 != 0 || cin <= 0) return 0;
+  const int sch = dbf::pick_schedule(cin / 16, 4);
+  return sch < 0 ? 0 : dbf::nlayers_of(sch);
 }
 
 int launch_dense_fused(const TcConvW* w, int L, __nv_bfloat16* buf, long long slabM, int cin, int N, int h, int wd, cudaStream_t st,
                        const TcConvW* w2, __nv_bfloat16* buf2) {
-  SELFC_CHECK_ARG(dense_fused_supported(cin, L), "dense_fused: cin=%d with %d fused layers does not fit shared memory", cin, L);
+  SELFC_CHECK_ARG(cin % 16 == 0 && cin > 0, "dense_fused: cin=%d must be a positive multiple of 16", cin);
+  const int nx = cin / 16;
+  const int sch = dbf::pick_schedule(nx, L);
+  SELFC_CHECK_ARG(sch >= 0 && dbf::nlayers_of(sch) == L, "dense_fused: cin=%d with %d fused layers does not fit shared memory", cin, L);
   SELFC_CHECK_ARG(aligned16(buf) && slabM == (long long)N * h * wd, "dense_fused: slab layout / alignment");
   const bool dual = w2 != nullptr;
   SELFC_CHECK_ARG(!dual || (buf2 != nullptr && aligned16(buf2) && buf2 != buf), "dense_fused: the second problem needs its own buffer");
-  const int nx = cin / 16;
   for (int j = 0; j < L; ++j) {
     SELFC_CHECK_ARG(w[j].img_pair != nullptr && w[j].cin_buf == cin + 32 * j, "dense_fused: layer %d weights not packed for cin=%d", j, cin + 32 * j);
     SELFC_CHECK_ARG(!dual || (w2[j].img_pair != nullptr && w2[j].cin_buf == cin + 32 * j), "dense_fused: second problem's layer %d", j);
@@ -502,18 +615,26 @@ int launch_dense_fused(const TcConvW* w, int L, __nv_bfloat16* buf, long long sl
   p.piece_len = piece_len;
   const int pieces = cdiv(p.total_pr, piece_len);
   p.err = tc::err_flag_for_device();
-  const int smem = dbf::smem_bytes(L, nx);
+  const bool dbg = tc::debug_slots();
+  if (dbg) p.dbg = tc::debug_next_slot(8000000 + (dual ? 100000 : 0) + sch * 1000 + nx);
+  const int smem = dbf::smem_bytes(sch, nx);
   static bool smem_set[64] = {};           // per device: function attributes belong to the device's context
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !smem_set[dev]) {
-    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<1, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<2, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
   }
   const int grid = 2 * pieces * p.nprob;
-  if (L == 4) SELFC_CUDA(tc::launch_pdl_pairs(dbf::dense_fused_kernel<4>, grid, dbf::THREADS, smem, st, tmap, tmap2, p));
-  else SELFC_CUDA(tc::launch_pdl_pairs(dbf::dense_fused_kernel<3>, grid, dbf::THREADS, smem, st, tmap, tmap2, p));
+  auto kern = sch == 0 ? (dbg ? dbf::dense_fused_kernel<0, 1, true> : dbf::dense_fused_kernel<0, 1, false>)
+            : sch == 1 ? (dbg ? dbf::dense_fused_kernel<1, 3, true> : dbf::dense_fused_kernel<1, 3, false>)
+                       : (dbg ? dbf::dense_fused_kernel<2, 4, true> : dbf::dense_fused_kernel<2, 4, false>);
+  SELFC_CUDA(tc::launch_pdl_pairs(kern, grid, dbf::THREADS, smem, st, tmap, tmap2, p));
   SELFC_LAUNCH_CHECK("dense_fused_kernel");
   return 0;
 }

@@ -113,7 +113,7 @@ static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pi
     }
     const bool dual = W2 != nullptr && W2->tc[0].img_pair != nullptr;
     if (fused_on && ctx->mode == SELFC_MODE_BF16 && k_first == 0 && k_last == 3 && W.tc[0].img_pair != nullptr && (W2 == nullptr || dual)) {
-      const int L = dense_fused_supported(W.xpad, 4) ? 4 : (dense_fused_supported(W.xpad, 3) ? 3 : 0);
+      const int L = dense_fused_layers(W.xpad);
       if (L > 0) {
         double flops = 0.0;
         for (int k = 0; k < L; ++k) flops += 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;
