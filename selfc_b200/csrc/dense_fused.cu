@@ -112,6 +112,15 @@ __device__ __forceinline__ void umma2_ss_bf16_elect_if(uint32_t tmem_d, uint64_t
       : "memory");
 }
 // A operand in tensor memory (lane = row, 8 columns = 16 bf16 of K)
+__device__ __forceinline__ void umma2_ts_bf16_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_ts_bf16_elect_if(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
                                                        uint32_t valid) {
   asm volatile(
@@ -150,6 +159,10 @@ __device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t bar, uint32_t pari
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity, int* err, int code) {
+#ifdef SELFC_DBF_HINT_WAIT
+  mbar_wait(bar, parity, err, code);
+  return;
+#endif
   uint32_t spins = 0;
   while (!mbar_try_wait_nohint(bar, parity)) {
     if (++spins > (1u << 26)) {       // a protocol bug traps (launch error) instead of hanging the GPU
@@ -350,41 +363,74 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
             constexpr int nks = nx + 2 * J;
             constexpr uint32_t wj_off = (uint32_t)(3 * WT_BYTES * (J * nx + J * (J - 1)));      // this layer's B image inside the weights
             constexpr uint32_t b_ky = (uint32_t)nks * (WT_BYTES >> 4);
-            uint32_t ok[3];
+            // slots of rows r-1, r, r+1 in the X ring / the growth rings: one modulo for the middle row, wrap for its neighbours
+            const bool ok_up = r > 0, ok_dn = r + 1 < h;                  // out-of-image rows are skipped taps (zero padding)
             uint32_t xa[3];
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const int rr = r + ky - 1;
-              ok[ky] = (rr >= 0 && rr < h) ? 1u : 0u;
-              xa[ky] = xlo_base + (uint32_t)(((q_base + (ok[ky] ? rr - rho0 : 0)) % NXR) * (xrow_bytes >> 4));
+            {
+              const int sm = (q_base + r - rho0) % NXR;
+              const int su = sm == 0 ? NXR - 1 : sm - 1, sd = sm == NXR - 1 ? 0 : sm + 1;
+              xa[0] = xlo_base + (uint32_t)(su * (xrow_bytes >> 4));
+              xa[1] = xlo_base + (uint32_t)(sm * (xrow_bytes >> 4));
+              xa[2] = xlo_base + (uint32_t)(sd * (xrow_bytes >> 4));
             }
-            // the accumulator is overwritten by the first tap issued: (K-step 0, ky = 0), or ky = 1 when row r - 1 is outside the image
-            const uint32_t acc_k0[3] = {0u, ok[0], 1u};
-            // K order = the dense buffer's channel order [X | x1 | x2 | x3], ky inner: the order of the unfused kernel
-#pragma unroll
-            for (int ks = 0; ks < nx; ++ks) {
-#pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {
-                const uint64_t ad = desc_join(xa[ky] + (uint32_t)(ks * (SLAB_ROW >> 4)), hi_a);
-                const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)ks * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
-                umma2_ss_bf16_elect_if(d, ad, bd, idesc, ks == 0 ? acc_k0[ky] : 1u, ok[ky]);
-              }
-            }
+            uint32_t ga[J > 0 ? J : 1][3];
 #pragma unroll
             for (int g = 0; g < J; ++g) {
-              uint32_t ga[3];
+              const int RGg = ring_of(SCH, g);
               const int lo_g = r0 - (L - 1 - g) > 0 ? r0 - (L - 1 - g) : 0;
+              const int sm = (cb[g] + (r - lo_g)) % RGg;
+              const int su = sm == 0 ? RGg - 1 : sm - 1, sd = sm == RGg - 1 ? 0 : sm + 1;
+              const uint32_t gb = tmem_base + (uint32_t)ringcol_of(SCH, g);
+              ga[g][0] = gb + (uint32_t)(su * 16);
+              ga[g][1] = gb + (uint32_t)(sm * 16);
+              ga[g][2] = gb + (uint32_t)(sd * 16);
+            }
+            // K order = the dense buffer's channel order [X | x1 | x2 | x3], ky inner: the order of the unfused kernel
+            if (ok_up && ok_dn) {
+              // interior row (all but the first / last image row): unpredicated issue, a few uniform-datapath instructions per MMA
 #pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {
-                const int cnt = ok[ky] ? cb[g] + (r + ky - 1 - lo_g) : 0;
-                ga[ky] = tmem_base + (uint32_t)(ringcol_of(SCH, g) + (cnt % ring_of(SCH, g)) * 16);
-              }
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
+              for (int ks = 0; ks < nx; ++ks) {
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
-                  const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)(nx + 2 * g + half) * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
-                  umma2_ts_bf16_elect_if(d, ga[ky] + (uint32_t)(half * 8), bd, idesc, 1u, ok[ky]);
+                  const uint64_t ad = desc_join(xa[ky] + (uint32_t)(ks * (SLAB_ROW >> 4)), hi_a);
+                  const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)ks * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
+                  umma2_bf16_elect(d, ad, bd, idesc, (ks > 0 || ky > 0) ? 1u : 0u);
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < J; ++g) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky) {
+                    const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)(nx + 2 * g + half) * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
+                    umma2_ts_bf16_elect(d, ga[g][ky] + (uint32_t)(half * 8), bd, idesc, 1u);
+                  }
+                }
+              }
+            } else {
+              // first / last image row: the missing tap is predicated off (never a branch around an MMA: see umma2_*_elect_if);
+              // the accumulator is overwritten by the first tap issued -- (K-step 0, ky = 0), or ky = 1 when row r - 1 does not exist
+              const uint32_t ok[3] = {ok_up ? 1u : 0u, 1u, ok_dn ? 1u : 0u};
+              const uint32_t acc_k0[3] = {0u, ok[0], 1u};
+#pragma unroll
+              for (int ks = 0; ks < nx; ++ks) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                  const uint64_t ad = desc_join(xa[ky] + (uint32_t)(ks * (SLAB_ROW >> 4)), hi_a);
+                  const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)ks * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
+                  umma2_ss_bf16_elect_if(d, ad, bd, idesc, ks == 0 ? acc_k0[ky] : 1u, ok[ky]);
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < J; ++g) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky) {
+                    const uint64_t bd = desc_join(wlo_base + ((wj_off + (uint32_t)(nx + 2 * g + half) * WT_BYTES) >> 4) + (uint32_t)ky * b_ky, hi_b);
+                    umma2_ts_bf16_elect_if(d, ga[g][ky] + (uint32_t)(half * 8), bd, idesc, 1u, ok[ky]);
+                  }
                 }
               }
             }
