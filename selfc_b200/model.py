@@ -106,7 +106,10 @@ class SelfCModel:
                  "initial_lr": float(self.train_opt["lr_G"]), "params": list(range(len(tr.params)))}
         sched = {"last_epoch": int(iter_step), "milestones": list(self.train_opt["lr_steps"] or []),
                  "gamma": float(self.train_opt["lr_gamma"] or 1.0)}
-        return {"epoch": epoch, "iter": iter_step, "schedulers": [sched], "optimizers": [{"state": state, "param_groups": [group]}]}
+        net = self.netG.module
+        return {"epoch": epoch, "iter": iter_step, "schedulers": [sched], "optimizers": [{"state": state, "param_groups": [group]}],
+                # the counter-based noise stream of the sampler (not in the reference, whose noise is the unseeded CUDA generator)
+                "noise": {"seed": int(net.noise_seed), "offset": int(net.noise_offset)}}
 
     def save_training_state(self, epoch, iter_step):
         import os
@@ -134,6 +137,9 @@ class SelfCModel:
             raise ValueError("per-parameter Adam step counts differ")
         tr.step_count = steps.pop()
         self.cur_lr = float(opt_state["param_groups"][0]["lr"])
+        noise = resume_state.get("noise")
+        if noise is not None:                  # continue the eps stream where the saved run stopped
+            self.netG.module.set_noise(int(noise["seed"]), int(noise["offset"]))
 
     # ---- feed_data: SelfC_model.py:93-132 -----------------------------------------------------------------
     def feed_data(self, data):

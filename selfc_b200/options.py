@@ -100,3 +100,21 @@ def dict2str(opt, indent_l=1):
         else:
             msg += " " * (indent_l * 2) + k + ": " + str(v) + "\n"
     return msg
+
+
+def check_resume(opt, resume_iter):
+    """options.py:105-120 of the reference (called at train.py:122): when resuming, the network weights are those saved next to
+    the training state -- path.pretrain_model_G is pointed at <models>/<iter>_G.pth (a configured pretrain path is ignored,
+    with a warning).  Unlike the reference this fails at once when that file is missing instead of training on from freshly
+    initialised weights with stale Adam moments."""
+    import logging
+    import os.path as osp
+    logger = logging.getLogger("base")
+    if opt["path"].get("resume_state"):
+        if opt["path"].get("pretrain_model_G") is not None:
+            logger.warning("pretrain_model path will be ignored when resuming training.")
+        path = osp.join(opt["path"]["models"], "{}_G.pth".format(resume_iter))
+        if not osp.isfile(path):
+            raise FileNotFoundError(f"resume_state is set but the matching weights {path} do not exist")
+        opt["path"]["pretrain_model_G"] = path
+        logger.info("Set [pretrain_model_G] to " + path)

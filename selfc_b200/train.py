@@ -32,6 +32,19 @@ def all_reduce_sum(flat: torch.Tensor) -> float:
     return 1.0
 
 
+def broadcast_parameters(params: Sequence[torch.Tensor], src: int = 0) -> bool:
+    """DistributedDataParallel broadcasts rank `src`'s parameters when it wraps the module (train.py:94-100 of the reference);
+    the flat-gradient all-reduce only keeps the replicas identical if they START identical, so the trainer does the same.
+    Returns True when a broadcast happened (a process group with more than one rank exists)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    with torch.no_grad():
+        for p in params:
+            dist.broadcast(p.data, src=src)
+    return True
+
+
 def shard_batch(n_clips: int, world: int, rank: int) -> range:
     """Per-rank slice of a global batch of clips (data/__init__.py:13-14: batch_size // world per rank)."""
     per = n_clips // world
@@ -64,10 +77,31 @@ class Trainer:
         self._sq = torch.zeros(1, dtype=torch.float32, device=device)
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.step_count = 0
+        self._ptr_key = None
+        self.broadcast_parameters()
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        if broadcast_parameters(self.params, src):
+            self._bump_versions()
+
+    def _bump_versions(self) -> None:
+        """The optimiser kernel (and the broadcast above) write the parameters behind autograd's back: bump the version counters
+        so that EVERY engine caching packed weights (keyed on (data_ptr, _version)) re-packs, not only this trainer's."""
+        with torch.no_grad():
+            for p in self.params:
+                p.add_(0)
 
     def _refresh_ptrs(self):
         cur = [p.data_ptr() for p in self.params]
-        self._ptrs = torch.tensor(cur, dtype=torch.int64, device=self.device)
+        if cur != self._ptr_key:
+            # selfc_adam_step writes through raw pointers: every parameter must be a contiguous fp32 tensor on this device
+            for name, p in zip(PARAM_NAMES, self.params):
+                same_dev = p.device.type == "cuda" and (self.device.index is None or p.device.index == self.device.index)
+                if p.dtype != torch.float32 or not p.is_contiguous() or not same_dev:
+                    raise RuntimeError(f"parameter {name} must be a contiguous float32 tensor on {self.device} for the optimiser "
+                                       f"kernel (got {p.dtype}, contiguous={p.is_contiguous()}, {p.device})")
+            self._ptrs = torch.tensor(cur, dtype=torch.int64, device=self.device)
+            self._ptr_key = cur
 
     def grads_and_losses(self, real_h: torch.Tensor, ref_l: torch.Tensor, t: int, eps: Optional[torch.Tensor] = None, seed: int = 0,
                          offset: int = 0):
@@ -91,7 +125,8 @@ class Trainer:
                                          _ptr(self.v), _ptr(self._sq), float(gscale), float(self.max_norm or 0.0),
                                          float(self.lr if lr is None else lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                                          float(self.weight_decay), int(self.step_count), _stream(self.device)), "adam_step")
-        self.engine.invalidate()       # parameters were written through raw pointers: re-pack before the next forward
+        self._bump_versions()          # parameters were written through raw pointers: every cached engine re-packs
+        self.engine.invalidate()
 
     def step(self, real_h, ref_l, t, eps=None, seed=0, offset=0, lr=None):
         losses = self.grads_and_losses(real_h, ref_l, t, eps=eps, seed=seed, offset=offset)

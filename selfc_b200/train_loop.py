@@ -153,6 +153,7 @@ def main(argv=None):
     resume_state = None
     if opt["path"].get("resume_state"):
         resume_state = torch.load(opt["path"]["resume_state"], map_location="cpu", weights_only=False)
+        option.check_resume(opt, resume_state["iter"])          # weights = <models>/<iter>_G.pth (train.py:122)
     if rank <= 0:
         for key in ("models", "training_state"):
             os.makedirs(opt["path"][key], exist_ok=True)
@@ -164,6 +165,11 @@ def main(argv=None):
     seed = opt["train"]["manual_seed"]
     if seed is None:
         seed = random.randint(1, 10000)
+        if opt["dist"]:
+            # every rank must build the same initial weights and draw the same synthetic clips: rank 0's draw wins
+            box = [seed]
+            dist.broadcast_object_list(box, src=0)
+            seed = box[0]
     set_random_seed(int(seed))
     ds_opt = opt["datasets"]["train"]
     t = int(ds_opt["video_len"] or 7)

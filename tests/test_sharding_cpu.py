@@ -87,6 +87,59 @@ def test_gradient_allreduce_world2_gloo():
         assert clips == list(range(4 * rank, 4 * rank + 4))
 
 
+def _bcast_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from selfc_b200 import train
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                                        # every rank starts from DIFFERENT weights
+    params = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7))]
+    before = [p.detach().clone() for p in params]
+    did = train.broadcast_parameters(params, src=0)
+    q.put((rank, did, [p.detach().tolist() for p in params], [b.tolist() for b in before]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_initial_parameter_broadcast_world2_gloo():
+    """DDP's construction-time broadcast (train.py:94-100): after Trainer.broadcast_parameters every rank holds rank 0's weights."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, did0, after0, before0), (r1, did1, after1, before1) = res
+    assert did0 and did1
+    assert before0 != before1                                            # they really started apart
+    assert after0 == before0 and after1 == before0                       # and both ended on rank 0's values
+    from selfc_b200 import train
+    assert train.broadcast_parameters([torch.nn.Parameter(torch.zeros(2))]) is False      # no process group: nothing to do
+
+
+def test_check_resume_points_at_saved_weights(tmp_path):
+    """options.check_resume (reference options.py:105-120, train.py:122): resuming loads <models>/<iter>_G.pth, warns when a
+    pretrain path was configured, and fails when the weights that belong to the training state are missing."""
+    import pytest
+    from selfc_b200 import options
+    models = tmp_path / "models"
+    models.mkdir()
+    opt = {"path": {"resume_state": str(tmp_path / "training_state" / "200.state"), "models": str(models), "pretrain_model_G": "/somewhere/else.pth"}}
+    with pytest.raises(FileNotFoundError):
+        options.check_resume(opt, 200)
+    (models / "200_G.pth").write_bytes(b"x")
+    options.check_resume(opt, 200)
+    assert opt["path"]["pretrain_model_G"] == str(models / "200_G.pth")
+    opt2 = {"path": {"resume_state": None, "models": str(models), "pretrain_model_G": "keep.pth"}}
+    options.check_resume(opt2, 200)
+    assert opt2["path"]["pretrain_model_G"] == "keep.pth"               # not resuming: untouched
+
+
 def test_multistep_lr_and_single_process_allreduce():
     from selfc_b200 import train
     assert train.multistep_lr(1e-4, 0, [100000, 200000, 300000], 0.5) == 1e-4
