@@ -230,11 +230,11 @@ class SelfCInvNet(nn.Module):
         t = GlobalVar.get_Temporal_LEN()
         if t is None:
             raise RuntimeError("GlobalVar.set_Temporal_LEN(T) must be called before forward (the reference's dataset does it)")
+        eng = self._engine_for(x.device)            # raises for CPU tensors: there is no fallback
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise RuntimeError("selfc_b200.SelfCInvNet.forward builds no autograd graph: loss.backward() through it cannot work. "
                                "Train through SelfCModel.optimize_parameters / selfc_b200.train.Trainer (the CUDA training "
                                "step), or call forward under torch.no_grad() / in eval() mode.")
-        eng = self._engine_for(x.device)
         if not rev:
             out, _, _ = eng.down(x, t, want_out51=True, want_u8=False, want_q=False)
             return out, out.new_zeros(())          # loss_c = out.mean() * 0  (:468)
