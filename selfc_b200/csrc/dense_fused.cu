@@ -60,6 +60,12 @@ constexpr int NXR_MAX = 16;
 constexpr int NRING_MAX = 18;                 // growth-ring slots of all layers (8 + 6 + 4)
 constexpr int XBUF_BYTES = 2 * 2 * 2 * 4 * 2 * 16 * 4;      // [team][channel half][parity][quarter][side][16] floats
 constexpr int BIAS_BYTES = MAXL * NOUT * 4;
+// SCH 0 (X of one slab) has shared memory to spare: there the kx partial sums of ALL lanes travel through shared memory (8 STS.128
+// + 8 LDS.128 per thread and row) instead of 32 shuffles + 32 edge selects -- the epilogue is instruction-issue bound.  Rows of
+// 20 floats (16 + 4 pad: conflict-free 16-byte accesses), row 0 of L / row 128 of R stay zero (the strip's ends have no neighbour).
+constexpr int XS_ROW = 20;
+constexpr int XS_BYTES_PER = 2 * (MPOS + 1) * XS_ROW * 4;       // L and R planes of one (team, channel half)
+__host__ __device__ constexpr bool xs_of(int SCH) { return SCH == 0; }
 
 // Row schedules (SCH): which row of which layer a step issues, in which order, and the ring sizes that follow from it (a ring slot
 // may be overwritten once every reader of its row has been ISSUED before the overwriting row's own MMAs; verified by simulation).
@@ -226,6 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
   const uint32_t bar_base = w_base + wtotal;
   float* xbuf = reinterpret_cast<float*>(gen_base + (bar_base - base) + BAR_BYTES);
   float* sbias = reinterpret_cast<float*>(gen_base + (bar_base - base) + BAR_BYTES + XBUF_BYTES);
+  float* xsbuf = reinterpret_cast<float*>(gen_base + (bar_base - base) + BAR_BYTES + XBUF_BYTES + BIAS_BYTES);     // xs_of(SCH) only
   auto xfull = [&](int s) { return bar_base + 8u * s; };
   auto xempty = [&](int s) { return bar_base + 8u * (NXR_MAX + s); };
   const uint32_t w_bar = bar_base + 8u * (2 * NXR_MAX);
@@ -260,6 +267,9 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
   if (warp == 1) tmem_alloc2(tmem_slot, (uint32_t)TMEM_COLS);
   if (warp >= 2) {
     for (int i = (int)threadIdx.x - 64; i < L * NOUT; i += THREADS - 64) sbias[i] = __ldg(p.bias[prob][i / NOUT] + (i % NOUT));
+    if constexpr (xs_of(SCH)) {
+      for (int i = (int)threadIdx.x - 64; i < 4 * XS_BYTES_PER / 4; i += THREADS - 64) xsbuf[i] = 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -510,6 +520,28 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_leader);
+          float v[16];
+          if constexpr (xs_of(SCH)) {
+            // every lane's kx = 0 / kx = 2 partial sums through shared memory: thread i reads L of i - 1 and R of i + 1
+            float4* lpl = reinterpret_cast<float4*>(xsbuf + (size_t)(team * 2 + wg) * (XS_BYTES_PER / 4));
+            float4* rpl = lpl + (MPOS + 1) * (XS_ROW / 4);
+            named_bar_sync(bar_id, 128);             // the previous row's values have been read by everyone
+#pragma unroll
+            for (int t = 0; t < 16; t += 4) {
+              lpl[(i + 1) * (XS_ROW / 4) + t / 4] = make_float4(__uint_as_float(a0[t]), __uint_as_float(a0[t + 1]), __uint_as_float(a0[t + 2]), __uint_as_float(a0[t + 3]));
+              rpl[i * (XS_ROW / 4) + t / 4] = make_float4(__uint_as_float(a2[t]), __uint_as_float(a2[t + 1]), __uint_as_float(a2[t + 2]), __uint_as_float(a2[t + 3]));
+            }
+            named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int t = 0; t < 16; t += 4) {
+              const float4 l = lpl[i * (XS_ROW / 4) + t / 4], rr = rpl[(i + 1) * (XS_ROW / 4) + t / 4];
+              const float4 b = *reinterpret_cast<const float4*>(sbias + J * NOUT + wg * 16 + t);
+              v[t] = lrelu02(l.x + __uint_as_float(a1[t]) + rr.x + b.x);
+              v[t + 1] = lrelu02(l.y + __uint_as_float(a1[t + 1]) + rr.y + b.y);
+              v[t + 2] = lrelu02(l.z + __uint_as_float(a1[t + 2]) + rr.z + b.z);
+              v[t + 3] = lrelu02(l.w + __uint_as_float(a1[t + 3]) + rr.w + b.w);
+            }
+          } else {
           // neighbours across the quarter boundaries: lane 31's kx=0 partials go right, lane 0's kx=2 partials go left.
           // Branch-free on purpose: a divergent region costs ~70 cycles here and this is the per-row critical path.
           float* xb = xbuf + (size_t)(((team * 2 + wg) * 2 + (use & 1)) * 4) * 32;
@@ -533,7 +565,6 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
               er[t] = b.x; er[t + 1] = b.y; er[t + 2] = b.z; er[t + 3] = b.w;
             }
           }
-          float v[16];
 #pragma unroll
           for (int t = 0; t < 16; ++t) {
             const float sl = __shfl_up_sync(0xffffffffu, __uint_as_float(a0[t]), 1);
@@ -541,6 +572,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
             const float left = edge_l ? (has_l ? el[t] : 0.f) : sl;
             const float right = edge_r ? (has_r ? er[t] : 0.f) : sr;
             v[t] = lrelu02(left + __uint_as_float(a1[t]) + right + sbias[J * NOUT + wg * 16 + t]);
+          }
           }
           uint32_t pk[8];
 #pragma unroll
@@ -582,7 +614,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
 
 static int smem_bytes(int sch, int nx) {
   const int L = nlayers_of(sch);
-  return 1024 + nxr_of(sch) * nx * SLAB_ROW + 3 * WT_BYTES * (L * nx + L * (L - 1)) + BAR_BYTES + XBUF_BYTES + BIAS_BYTES;
+  return 1024 + nxr_of(sch) * nx * SLAB_ROW + 3 * WT_BYTES * (L * nx + L * (L - 1)) + BAR_BYTES + XBUF_BYTES + BIAS_BYTES +
+         (xs_of(sch) ? 4 * XS_BYTES_PER : 0);
 }
 // One instantiation per X width the network has -- 1 slab (G, H, local_m1), 3 (F), 4 (the STP 64 -> 64 blocks) -- each with the
 // deepest schedule whose X ring and weights fit shared memory; -1: not built for this width (the caller runs layer by layer).
