@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=HR_W)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the 'train' block (configs[3]: a few training steps + gradient all-reduce)")
     ap.add_argument("--workload", default="rescale", choices=["rescale", "train"],
                     help="rescale: the headline metric (default); train: BASELINE.json configs[3], one training step on synthetic "
                          "Vimeo90K-shape septuplets per rank with the flat-gradient NCCL all-reduce")
@@ -319,24 +320,36 @@ def run_ours(args):
         ach = c["work"] / (c["ms"] / 1e3) / 1e12 if c["ms"] > 0 else 0.0
         # DRAM bytes per launch of the same kernel class from the committed `ncu` capture (profiles/; null when absent)
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r2_conv3x3_ncu_traffic.json")
-        if not os.path.exists(tp):
-            tp = os.path.join(ROOT, "profiles", "r1_conv3x3_ncu_traffic.json")
+        for name in ("r2b_conv3x3_ncu_traffic.json", "r2_conv3x3_ncu_traffic.json", "r1_conv3x3_ncu_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tp):
+                break
         if os.path.exists(tp) and (hh, ww) == (HR_H, HR_W):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "conv3x3_tc3_kernel: (1,3,3) dense-block convolution, tcgen05 implicit GEMM "
-                              "(all 216 launches of one 7-frame GOP, down+up)",
+        fused = os.environ.get("SELFC_DB_FUSED", "1") != "0"
+        roofline = {"kernel": ("dense_fused_kernel: conv1..4 of a D2DTInput dense block in ONE launch (tcgen05 implicit GEMM, growth channels "
+                               "kept in tensor memory; + conv3x3_tc3_kernel for conv4 of the five 64->64 STP blocks) -- all (1,3,3) "
+                               "convolutions of one 7-frame GOP, down+up" if fused else
+                               "conv3x3_tc3_kernel: (1,3,3) dense-block convolution, tcgen05 implicit GEMM (all 216 launches of one 7-frame GOP, down+up)"),
                     "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
                     "traffic": traffic,
                     "hbm_view": ({"achieved_gbs": traffic / (c["ms"] / max(1, c["launches"]) / 1e3) / 1e9, "peak_gbs": hbm,
                                   "frac": traffic / (c["ms"] / max(1, c["launches"]) / 1e3) / 1e9 / hbm,
                                   "note": "the same launches against the HBM roof: cold-cache DRAM bytes per launch (ncu) / in-stream launch time; "
-                                          "the class sits at about the same fraction of both roofs"} if traffic and c["ms"] > 0 else None),
+                                          "fused, the class moves 0.39 of round 1's bytes and is tensor-bound"} if traffic and c["ms"] > 0 else None),
                     "peak_source": f"of {src} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "algorithmic_flops_per_launch": c["work"] / max(1, c["launches"]),
                     "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches": c["launches"],
                     "share_of_step": c["ms"] / tot_ms if tot_ms else None,
                     "classes": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                                     "share": round(v["ms"] / tot_ms, 4) if tot_ms else None} for k, v in prof.items()}}
+
+    # ---- BASELINE.json configs[3] beside the headline: a few training steps per rank with the gradient all-reduce ----------------
+    train_block = None
+    if not args.no_train:
+        del group, lr_out, hr_out
+        torch.cuda.empty_cache()
+        train_block = measure_train(dev, world, rank, steps=3, warmup=2, b=1)
 
     if rank != 0:
         if world > 1:
@@ -354,36 +367,28 @@ def run_ours(args):
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args, args.mode, weights_desc),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "algorithmic_tflops": whole_tflops}
+            "algorithmic_tflops": whole_tflops, "train": train_block}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_train(args):
-    """BASELINE.json configs[3]: SelfC-large training step (forward, backward, gradient all-reduce, clip, Adam) on synthetic
-    Vimeo90K-shape septuplets, fp32 mode (fp32-FMA kernels; the tensor-core backward is the next round's work)."""
+def measure_train(dev, world: int, rank: int, steps: int, warmup: int, b: int):
+    """BASELINE.json configs[3] on this rank's GPU: `steps` training steps (forward, backward, flat-gradient all-reduce, clip, Adam)
+    on b synthetic Vimeo90K-shape septuplets; device-timed, max over ranks; the all-reduce alone is timed separately."""
     import torch.distributed as dist
     from selfc_b200 import engine as _eng
     from selfc_b200.global_var import GlobalVar
     from selfc_b200.synthetic import seeded_state_dict, synthetic_net
     from selfc_b200.train import Trainer
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    t, hh, ww, b = GOP, 256, 448, max(1, args.septuplets)
+    t, hh, ww = GOP, 256, 448
     net, _ = synthetic_net(train=True)
     net.load_state_dict(seeded_state_dict(net, 0), strict=True)
     net = net.to(dev)
+    prev_t = GlobalVar.get_Temporal_LEN()
     GlobalVar.set_Temporal_LEN(t)
     tr = Trainer(net, dev, lr=1e-4, weight_decay=1e-14, max_norm=10.0)
-    x = make_group(b * t, hh, ww, 1234 + rank, dev)
+    x = make_group(b * t, hh, ww, 4321 + rank, dev)
     ref_l = _eng.gaussian_downsample(x)
 
     def barrier():
@@ -393,34 +398,63 @@ def run_train(args):
             torch.cuda.synchronize()
 
     losses = None
-    for i in range(args.warmup):
+    for i in range(warmup):
         losses = tr.step(x, ref_l, t, seed=42, offset=i)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     n0 = _eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     ev0.record()
-    for i in range(args.steps):
-        losses = tr.step(x, ref_l, t, seed=42, offset=args.warmup + i)
+    for i in range(steps):
+        losses = tr.grads_and_losses(x, ref_l, t, seed=42, offset=warmup + i)
+        ar[i][0].record()
+        gscale = tr.all_reduce()
+        ar[i][1].record()
+        tr.apply(gscale)
     ev1.record()
     barrier()
     launches = _eng.launch_count() - n0
-    clocks = sampler.stop()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    ms = torch.tensor([ev0.elapsed_time(ev1), sum(a.elapsed_time(b_) for a, b_ in ar)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total, ms_ar = float(ms[0].item()), float(ms[1].item())
+    if prev_t is not None:
+        GlobalVar.set_Temporal_LEN(prev_t)
+    flop = 3.0 * FLOP_PER_LR_PX * (hh // 4) * (ww // 4) * t * b * world      # training ~ 3x forward
+    return {"septuplets_per_s": world * b * steps / (ms_total / 1e3), "ms_per_step": ms_total / steps, "allreduce_ms": ms_ar / steps,
+            "allreduce_bytes": int(tr.total * 4), "n_gpus": world, "steps": steps, "warmup": warmup, "septuplets_per_step_per_gpu": b,
+            "dtype": "f32", "gpu_launches": int(launches), "loss": float(losses[0].item()),
+            "algorithmic_tflops": flop * steps / (ms_total / 1e3) / 1e12,
+            "what": "SelfC-large training step on synthetic 7x256x448 septuplets (BASELINE.json configs[3]): forward + recompute-based "
+                    "backward on fp32-FMA kernels, ONE NCCL all-reduce of the flat 3.37M-element gradient, clip, Adam; device-timed, "
+                    "max over ranks"}
+
+
+def run_train(args):
+    """`--workload train`: BASELINE.json configs[3] as its own line (the default line carries the same measurement as "train")."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    b = max(1, args.septuplets)
+    sampler = ClockSampler(local)
+    sampler.start()
+    m = measure_train(dev, world, rank, steps=args.steps, warmup=args.warmup, b=b)
+    clocks = sampler.stop()
     if rank == 0:
-        flop = 3.0 * FLOP_PER_LR_PX * (hh // 4) * (ww // 4) * t * b * world      # training ~ 3x forward
-        line = {"metric": "training step septuplets/s (7x256x448 HR, fwd+bwd+allreduce+Adam)", "value": world * b * args.steps / (ms_total / 1e3),
-                "unit": "septuplets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        line = {"metric": "training step septuplets/s (7x256x448 HR, fwd+bwd+allreduce+Adam)", "value": m["septuplets_per_s"],
+                "unit": "septuplets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"SelfC-large training step, {b} synthetic Vimeo90K-shape septuplet(s) per GPU per step, fp32 mode "
                                        "(fp32-FMA kernels, recompute-based backward), one NCCL all-reduce of the flat 3.37M-element gradient",
                            "septuplets_per_step_per_gpu": b, "weights": "seeded random, reference state_dict layout"},
-                "clocks": clocks, "gpu_launches": int(launches), "loss": float(losses[0].item()),
-                "algorithmic_tflops": flop * args.steps / (ms_total / 1e3) / 1e12}
+                "clocks": clocks, "gpu_launches": m["gpu_launches"], "loss": m["loss"], "allreduce_ms": m["allreduce_ms"],
+                "algorithmic_tflops": m["algorithmic_tflops"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -260,7 +260,26 @@ static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* 
   float* wmat = reinterpret_cast<float*>(wsp + ws.wmat);
   float* wsum = reinterpret_cast<float*>(wsp + ws.wsum);
   const double px_bytes = (double)d.M() * kStpC * sizeof(T);
-  PROF(ctx, st, 2, 0.0, launch_ga_wmap(g.fcw, wmap, d.h, d.w, st));
+  {
+    // the pooling weight map: cached per (weights, h, w, stream) in the context instead of one launch per call
+    GaW& gm = const_cast<GaW&>(g);
+    const size_t need = (size_t)d.h * d.w * sizeof(float);
+    if (gm.wmap_cache == nullptr || gm.wmap_cap < need) {
+      if (gm.wmap_cache) cudaFree(gm.wmap_cache);
+      gm.wmap_cache = nullptr;
+      gm.wmap_cap = 0;
+      gm.wmap_h = gm.wmap_w = 0;
+      SELFC_CUDA(cudaMalloc(&gm.wmap_cache, need));
+      gm.wmap_cap = need;
+    }
+    if (gm.wmap_h != d.h || gm.wmap_w != d.w || gm.wmap_stream != st) {
+      PROF(ctx, st, 2, 0.0, launch_ga_wmap(g.fcw, gm.wmap_cache, d.h, d.w, st));
+      gm.wmap_h = d.h;
+      gm.wmap_w = d.w;
+      gm.wmap_stream = st;
+    }
+    wmap = gm.wmap_cache;
+  }
   PROF(ctx, st, 2, px_bytes, launch_ga_stat<T>(feat, kStpC, wmap, partial, ws.nsplit, d.B * d.T, (int)d.hw(), st));
   PROF(ctx, st, 2, 0.0, launch_ga_weights(partial, ws.nsplit, g.fcb, g.p2w, g.p2b, g.p3w, g.p3b, wmat, wsum, d.B, d.T, st));
   if (wmat_copy) SELFC_CUDA(cudaMemcpyAsync(wmat_copy, wmat, (size_t)d.B * d.T * d.T * 4, cudaMemcpyDeviceToDevice, st));
@@ -588,6 +607,7 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
     for (int k = 0; k < 5; ++k) free_tc_weights(ctx->stp[i].tc[k]);
     free_temporal_weights(ctx->stp[i].t5);
     free_temporal_weights(ctx->ga[i].tp);
+    if (ctx->ga[i].wmap_cache) cudaFree(ctx->ga[i].wmap_cache);
   }
   for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.t[j]);
   for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.g[j]);
@@ -695,6 +715,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
   // GlobalAgg
   for (int g = 0; g < 6; ++g) {
     GaW& G = ctx->ga[g];
+    G.wmap_h = G.wmap_w = 0;          // fc.weight changes: the cached pooling weight map is stale
     const int f = ga_first[g];
     float* dst[8];
     for (int j = 0; j < 8; ++j) dst[j] = fp(ga_off[g][j]);

@@ -32,6 +32,12 @@ struct GaW {
   float *fcw = nullptr, *fcb = nullptr, *p2w = nullptr, *p2b = nullptr, *p3w = nullptr, *p3b = nullptr;
   float *p1w = nullptr, *p1b = nullptr;   // packed [64][64] (k-major rows), bias [64]
   TcTempW tp;                             // proj1 image (BF16 mode)
+  // fc(adaptive_avg_pool2d(.)) as a per-pixel weight map [h*w]: depends only on fc.weight and (h, w), so it is built once per
+  // (weights, frame size, stream) and kept by the context (invalidated by selfc_ctx_load_weights, freed by selfc_ctx_destroy)
+  float* wmap_cache = nullptr;
+  size_t wmap_cap = 0;
+  int wmap_h = 0, wmap_w = 0;
+  cudaStream_t wmap_stream = nullptr;
 };
 struct ProfRec {
   cudaEvent_t a = nullptr, b = nullptr;

@@ -1031,9 +1031,12 @@ def test_model_optimize_parameters_matches_oracle_step(dev):
     assert abs(log["l_forw_fit"] - l_forw.item()) <= 1e-5 and abs(log["l_back_rec"] - l_back.item()) <= 1e-5
     moved = max(float((p.detach().cpu() - sd[k]).abs().max()) for k, p in net.named_parameters())
     assert 0.5e-4 <= moved <= 1.05e-4                           # Adam's first step: |update| <= lr
+    # forward builds no autograd graph: in train mode with grad enabled it must say so instead of returning graph-less tensors
+    with pytest.raises(RuntimeError, match="no autograd graph"):
+        net(x=x.to(dev))
     # the next forward uses the updated weights (packed images were invalidated)
-    out, _ = net(x=x.to(dev))
     with torch.no_grad():
+        out, _ = net(x=x.to(dev))
         ref_out = so.net_down({k: p.detach().cpu() for k, p in net.named_parameters()}, x, t)
     torch.testing.assert_close(out.cpu(), ref_out, rtol=0, atol=2e-4)
     m.update_learning_rate(100000)
