@@ -31,8 +31,14 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
 // weights do not fit shared memory next to the X ring (cin = 64).  Reads channels [0,cin) of the slab-planar buffer, writes
 // x1..xL to [cin, cin + 32 L); bit-identical to L launches of launch_conv3x3_tc.  (w2, buf2): second problem of the same shape.
 int dense_fused_layers(int cin);      // how many layers (4, 3 or 0 = unsupported) one launch fuses for this X width
+// (f5img, f5part): for a block with 3 outputs (F of a coupling; cin 48) the launch also applies conv5's three temporal taps to
+// every row while [X | x1..x4] is on chip and writes 9 fp32 partial products per pixel to f5part [3 taps][M][4]; x1..x4 are then
+// NOT written to HBM and launch_f5_combine finishes conv5 + the additive coupling (replaces the temporal kernel's EPI_COUPLE_Y1).
 int launch_dense_fused(const TcConvW* w, int L, __nv_bfloat16* buf, long long slabM, int cin, int N, int h, int wd, cudaStream_t st,
-                       const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr);
+                       const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr, const void* f5img = nullptr, float* f5part = nullptr);
+int pack_f5_weights(void** img, const float* wref, int cin, cudaStream_t st);      // conv5.weight [3][cin][3] -> *img (allocated on first use)
+int launch_f5_combine(const float* part, const float* bias, float* z, __nv_bfloat16* copyA, __nv_bfloat16* copyB, int T, long long hw,
+                      long long M, int rev, cudaStream_t st);
 
 // ---- temporal_tc.cu: (3,1,1) conv5 + coupling epilogues, GlobalAgg apply ---------------------------------------
 struct TcTempW {

@@ -74,15 +74,29 @@ __host__ __device__ constexpr bool xs_of(int SCH) { return SCH == 0; }
 //   SCH 1  L = 4, lags 0,2,4,5, order conv3,conv1,conv2,conv4: conv4 reads the x3 row conv3 stored two groups earlier in the same
 //          step.  Rings 7 + 5 + 3, 8 live X rows (9-slot ring): what fits next to 108 KB of weights when X has 3 slabs (F).
 //   SCH 2  L = 3, lags 0,2,4: rings 6 + 4, 7 live X rows (8-slot ring): X of 4 slabs (STP 64 -> 64; conv4 runs layer-by-layer).
+//   SCH 3  SCH 1 plus a FIFTH group per step: the three temporal taps of conv5 applied to row s-6 of [X | x1..x4] (a pointwise
+//          GEMM, N = 16 = 3 taps x 3 outputs padded), order conv3, conv1, conv5-taps, conv2, conv4; x4 gets a 2-row ring.  Only
+//          for cout = 3 (the F block of a coupling): 9 fp32 partial products per pixel replace conv5's re-read of 176 channels,
+//          and x1..x4 need not be written to HBM at all.
+__host__ __device__ constexpr bool f5_of(int SCH) { return SCH == 3; }
 __host__ __device__ constexpr int nlayers_of(int SCH) { return SCH == 2 ? 3 : 4; }
-__host__ __device__ constexpr int lag_of(int SCH, int j) { return SCH == 1 ? (j == 3 ? 5 : 2 * j) : 2 * j; }
-__host__ __device__ constexpr int order_of(int SCH, int oi) { return SCH == 1 ? (oi == 0 ? 2 : oi == 1 ? 0 : oi == 2 ? 1 : 3) : oi; }
-__host__ __device__ constexpr int ring_of(int SCH, int j) { return SCH == 0 ? 8 - 2 * j : SCH == 1 ? 7 - 2 * j : 6 - 2 * j; }
-__host__ __device__ constexpr int nxr_of(int SCH) { return SCH == 0 ? 16 : SCH == 1 ? 9 : 8; }
-__host__ __device__ constexpr int ringslot0_of(int SCH, int j) { return j == 0 ? 0 : j == 1 ? ring_of(SCH, 0) : ring_of(SCH, 0) + ring_of(SCH, 1); }
+__host__ __device__ constexpr int lag_of(int SCH, int j) { return (SCH == 1 || SCH == 3) ? (j == 4 ? 6 : j == 3 ? 5 : 2 * j) : 2 * j; }
+__host__ __device__ constexpr int order_of(int SCH, int oi) {
+  return SCH == 1 ? (oi == 0 ? 2 : oi == 1 ? 0 : oi == 2 ? 1 : 3) : SCH == 3 ? (oi == 0 ? 2 : oi == 1 ? 0 : oi == 2 ? 4 : oi == 3 ? 1 : 3) : oi;
+}
+__host__ __device__ constexpr int ngroups_of(int SCH) { return nlayers_of(SCH) + (f5_of(SCH) ? 1 : 0); }
+__host__ __device__ constexpr int ring_of(int SCH, int j) { return SCH == 0 ? 8 - 2 * j : (SCH == 1 || SCH == 3) ? (j == 3 ? 2 : 7 - 2 * j) : 6 - 2 * j; }
+__host__ __device__ constexpr int nxr_of(int SCH) { return SCH == 0 ? 16 : (SCH == 1 || SCH == 3) ? 9 : 8; }
+__host__ __device__ constexpr int ringslot0_of(int SCH, int j) {
+  return j == 0 ? 0 : j == 1 ? ring_of(SCH, 0) : j == 2 ? ring_of(SCH, 0) + ring_of(SCH, 1) : ring_of(SCH, 0) + ring_of(SCH, 1) + ring_of(SCH, 2);
+}
+constexpr int F5_N = 16;                                  // conv5-taps GEMM: rows tap * 3 + co (9 of 16)
+constexpr int F5_KSTEPS = 11;                             // 48 + 128 channels
+constexpr int F5_TILE = (F5_N / 2) * 16 * 2;              // one K-step of one CTA's half of the B image: 256 bytes
 __host__ __device__ constexpr int ringcol_of(int SCH, int j) { return RING_COL0 + 16 * ringslot0_of(SCH, j); }
 static_assert(ringcol_of(0, 2) + 16 * ring_of(0, 2) <= TMEM_COLS, "TMEM budget");
 static_assert(ringslot0_of(0, 2) + ring_of(0, 2) <= NRING_MAX, "ring slot barriers");
+static_assert(ringcol_of(3, 3) + 16 * ring_of(3, 3) <= TMEM_COLS && ringslot0_of(3, 3) + ring_of(3, 3) <= NRING_MAX, "SCH 3 budget");
 
 struct Params {
   const void* wimg[2][MAXL];     // per problem, per layer: TcConvW::img_pair (two halves of the B image)
@@ -92,6 +106,9 @@ struct Params {
   long long slabM;
   int N, h, w, S, ncol;          // S strips per image row, ncol = N * S strip columns
   int piece_len, total_pr;       // a CTA pair owns piece_len consecutive rows of the (column pair, row) sequence
+  const void* w5img;             // SCH 3: conv5-taps B image (pack_f5_kernel), two halves
+  float* part;                   // SCH 3: partial products [3 taps][M][4] fp32 (M = N*h*w)
+  int store_growth;              // write x1..xL to the dense buffer (0: nobody reads them -- SCH 3)
   int* err;
   long long* dbg;                // SELFC_TC_DBG=1: CTA 0's barrier-wait cycles per role (tc::debug_next_slot)
 };
@@ -212,7 +229,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
                                                                   const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   constexpr int L = nlayers_of(SCH);
   constexpr int NXR = nxr_of(SCH);
-  constexpr int DMAX = lag_of(SCH, L - 1);
+  constexpr bool F5 = f5_of(SCH);
+  constexpr int DMAX = lag_of(SCH, F5 ? 4 : L - 1);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t crank = cluster_ctarank();               // 0 = leader
   const int unit = (int)(blockIdx.x >> 1);
@@ -228,7 +246,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
   // [X ring][weights of the L layers][barriers][exchange][bias]
   const uint32_t x_base = base;
   const uint32_t w_base = base + NXR * xrow_bytes;
-  constexpr int wtotal = 3 * WT_BYTES * (L * nx + L * (L - 1));      // sum_j 3 * (nx + 2j) tiles
+  constexpr int wconv = 3 * WT_BYTES * (L * nx + L * (L - 1));       // sum_j 3 * (nx + 2j) tiles
+  constexpr int wtotal = wconv + (F5 ? F5_KSTEPS * F5_TILE : 0);
   const uint32_t bar_base = w_base + wtotal;
   float* xbuf = reinterpret_cast<float*>(gen_base + (bar_base - base) + BAR_BYTES);
   float* sbias = reinterpret_cast<float*>(gen_base + (bar_base - base) + BAR_BYTES + XBUF_BYTES);
@@ -292,6 +311,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
         bulk_g2s(w_base + off, (const uint8_t*)p.wimg[prob][j] + (size_t)crank * bytes, (uint32_t)bytes, w_bar);
         off += bytes;
       }
+      if constexpr (F5)
+        bulk_g2s(w_base + wconv, (const uint8_t*)p.w5img + (size_t)crank * (F5_KSTEPS * F5_TILE), (uint32_t)(F5_KSTEPS * F5_TILE), w_bar);
       pdl_wait();      // weights are static; activations come from the previous kernel in the stream
       int slot = 0;
       uint32_t ph = 0;
@@ -342,8 +363,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
         const int s_first = r0 - (L - 1) > 0 ? r0 - (L - 1) : 0, s_last = r1 - 1 + DMAX;
         nsteps += s_last - s_first + 1;
         for (int s = s_first; s <= s_last; ++s) {
-          auto group = [&](auto OI) {
-            constexpr int J = order_of(SCH, decltype(OI)::value);
+          auto group = [&](auto JC) {
+            constexpr int J = decltype(JC)::value;
             const int r = s - lag_of(SCH, J);
             const int lo = r0 - (L - 1 - J) > 0 ? r0 - (L - 1 - J) : 0, hi = r1 + (L - 1 - J) < h ? r1 + (L - 1 - J) : h;
             if (r < lo || r >= hi) return;
@@ -448,10 +469,56 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
             ++gcnt;
             ++prod[J];
           };
-          group(IC<0>{});
-          group(IC<1>{});
-          group(IC<2>{});
-          if constexpr (L > 3) group(IC<3>{});
+          // SCH 3: the three temporal taps of conv5 on row r of [X | x1 | x2 | x3 | x4] -- a pointwise GEMM, N = 16, 11 K-steps
+          auto group5 = [&]() {
+            const int r = s - lag_of(SCH, 4);
+            if (r < r0 || r >= r1) return;
+            const int acc = gcnt & 1;
+            const uint32_t use = (uint32_t)(gcnt >> 1);
+            mbar_wait_t(tempty(acc), (use & 1u) ^ 1u, p.err, 44, timed, w_tempty);
+            {
+              // x4 row r stored?  (X and x1..x3 of row r were waited for by conv4's row r - 1 at the latest)
+              constexpr int RG = ring_of(SCH, 3);
+              const int target = cb[3] + (r - r0) + 1;
+              while (ev[3] < target) {
+                const int c = ev[3];
+                mbar_wait_t(gready(ringslot0_of(SCH, 3) + c % RG), (uint32_t)(c / RG) & 1u, p.err, 46, timed, w_gready[2]);
+                ++ev[3];
+              }
+            }
+            tc_fence_after();
+            constexpr uint32_t idesc5 = umma_idesc_bf16(256, F5_N);
+            const uint32_t d = tmem_base + (uint32_t)(acc * NB);
+            const uint32_t hi_b5 = desc_hi(128, 0);
+            const uint32_t w5lo = desc_lo(w_base + wconv, 128);        // one 8-row group per CTA: K core matrices 128 bytes apart
+            const uint32_t xa = xlo_base + (uint32_t)(((q_base + r - rho0) % NXR) * (xrow_bytes >> 4));
+#pragma unroll
+            for (int ks = 0; ks < nx; ++ks)
+              umma2_bf16_elect(d, desc_join(xa + (uint32_t)(ks * (SLAB_ROW >> 4)), hi_a), desc_join(w5lo + (uint32_t)(ks * (F5_TILE >> 4)), hi_b5),
+                               idesc5, ks > 0 ? 1u : 0u);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int lo_g = r0 - (L - 1 - g) > 0 ? r0 - (L - 1 - g) : 0;
+              const uint32_t ga = tmem_base + (uint32_t)(ringcol_of(SCH, g) + ((cb[g] + (r - lo_g)) % ring_of(SCH, g)) * 16);
+#pragma unroll
+              for (int half = 0; half < 2; ++half)
+                umma2_ts_bf16_elect(d, ga + (uint32_t)(half * 8), desc_join(w5lo + (uint32_t)((nx + 2 * g + half) * (F5_TILE >> 4)), hi_b5), idesc5, 1u);
+            }
+            umma2_commit_elect(tfull(acc));
+            ++gcnt;
+          };
+          if constexpr (F5) {
+            group(IC<2>{});
+            group(IC<0>{});
+            group5();
+            group(IC<1>{});
+            group(IC<3>{});
+          } else {
+            group(IC<order_of(SCH, 0)>{});
+            group(IC<order_of(SCH, 1)>{});
+            group(IC<order_of(SCH, 2)>{});
+            if constexpr (L > 3) group(IC<order_of(SCH, 3)>{});
+          }
           // X row s - DMAX - 1 has no reader left
           const int f = s - DMAX - 1;
           if (f >= rho0 && f < rho1) umma2_commit_elect(xempty((q_base + f - rho0) % NXR));
@@ -500,14 +567,15 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
       __nv_bfloat16* ocol = obuf + (size_t)(nx + wg) * slab_elems + ((size_t)n * h * p.w + x) * 16;
       const int s_first = r0 - (L - 1) > 0 ? r0 - (L - 1) : 0, s_last = r1 - 1 + DMAX;
       for (int s = s_first; s <= s_last; ++s) {
-        auto group = [&](auto OI) {
-          constexpr int J = order_of(SCH, decltype(OI)::value);
+        auto group = [&](auto JC) {
+          constexpr int J = decltype(JC)::value;
+          constexpr bool TO_RING = J < L - 1 || F5;                 // this layer's rows are A operands of later groups
           const int r = s - lag_of(SCH, J);
           const int lo = r0 - (L - 1 - J) > 0 ? r0 - (L - 1 - J) : 0, hi = r1 + (L - 1 - J) < h ? r1 + (L - 1 - J) : h;
           if (r < lo || r >= hi) return;
           const int g = gcnt++;
           int slot = 0;
-          if constexpr (J < L - 1) slot = cnt[J]++ % ring_of(SCH, J);
+          if constexpr (TO_RING) slot = cnt[J]++ % ring_of(SCH, J);
           if ((g & 1) != team) return;
           const uint32_t use = (uint32_t)(g >> 1);
           mbar_wait_t(tfull_bar, use & 1u, p.err, 47, timed, w_tfull);
@@ -577,24 +645,58 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
           uint32_t pk[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) pk[t] = pack_bf2(v[2 * t], v[2 * t + 1]) & keep;
-          if constexpr (J < L - 1) {
+          if constexpr (TO_RING) {
             tmem_st8(lane_addr + (uint32_t)(ringcol_of(SCH, J) + slot * 16 + wg * 8), pk);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(gready_leader0 + 8u * (uint32_t)(ringslot0_of(SCH, J) + slot));
           }
-          if (store_col && r >= r0 && r < r1) {
+          if (store_col && r >= r0 && r < r1 && (!F5 || p.store_growth)) {
             __nv_bfloat16* o = ocol + (size_t)(2 * J) * slab_elems + (size_t)r * p.w * 16;
             *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
           ++mine;
         };
-        group(IC<0>{});
-        group(IC<1>{});
-        group(IC<2>{});
-        if constexpr (L > 3) group(IC<3>{});
+        // SCH 3: the conv5-taps group -- 9 partial products per pixel (columns tap * 3 + co) -> part[tap][m] as (co0, co1, co2, 0)
+        auto group5 = [&]() {
+          const int r = s - lag_of(SCH, 4);
+          if (r < r0 || r >= r1) return;
+          const int g = gcnt++;
+          if ((g & 1) != team) return;
+          const uint32_t use = (uint32_t)(g >> 1);
+          mbar_wait_t(tfull_bar, use & 1u, p.err, 47, timed, w_tfull);
+          tc_fence_after();
+          uint32_t a[16];
+          if (wg == 0) {                       // warp-uniform: the second channel half has nothing to read, it only releases
+            tmem_ld16(lane_addr + (uint32_t)(team * NB), a);
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader);
+          if (wg == 0 && store_col) {
+            const size_t Mtot = (size_t)p.slabM;
+            float* o = p.part + (((size_t)n * h + r) * p.w + x) * 4;
+            store4(o, make_float4(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]), 0.f));
+            store4(o + Mtot * 4, make_float4(__uint_as_float(a[3]), __uint_as_float(a[4]), __uint_as_float(a[5]), 0.f));
+            store4(o + Mtot * 8, make_float4(__uint_as_float(a[6]), __uint_as_float(a[7]), __uint_as_float(a[8]), 0.f));
+          }
+          ++mine;
+        };
+        if constexpr (F5) {
+          group(IC<2>{});
+          group(IC<0>{});
+          group5();
+          group(IC<1>{});
+          group(IC<3>{});
+        } else {
+          group(IC<order_of(SCH, 0)>{});
+          group(IC<order_of(SCH, 1)>{});
+          group(IC<order_of(SCH, 2)>{});
+          if constexpr (L > 3) group(IC<order_of(SCH, 3)>{});
+        }
       }
     }
     if (timed && (threadIdx.x == 64 || threadIdx.x == 64 + 256)) {
@@ -612,10 +714,58 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
   }
 }
 
+// conv5 weight [3][cin_ref = 176][3 taps] fp32 -> bf16 B image of the conv5-taps GEMM, rows n' = tap * 3 + co (9 of 16), split in two
+// halves of 8 rows for the CTA pair: [half(2)][kstep(11)][kcore(2)][row % 8][k % 8]
+__global__ void pack_f5_kernel(const float* __restrict__ wref, __nv_bfloat16* __restrict__ img, int cin) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= F5_N * cin) return;
+  const int n = idx % F5_N, c = idx / F5_N;
+  const int tap = n / 3, co = n % 3;
+  const float v = n < 9 ? wref[((size_t)co * cin + c) * 3 + tap] : 0.f;
+  const int ks = c / 16, kk = c % 16;
+  img[(size_t)(n / 8) * (F5_KSTEPS * 128) + (size_t)ks * 128 + (kk / 8) * 64 + (n % 8) * 8 + (kk % 8)] = __float2bfloat16_rn(v);
+}
+
+// F(x2)[t] = sum_tap W[tap] . in[t + tap - 1] from the per-frame partial products, then the additive half of the coupling
+// (SelfC_GMM_arch_inv.py:24,31): y1 = x1 +/- (F + bias) on the fp32 latent state, with bf16 copies of y1 into the X slabs of the
+// coupling's G and H dense buffers (channels 3..15 zero) -- what EPI_COUPLE_Y1 of the temporal kernel does for the layer-by-layer path
+__global__ void __launch_bounds__(256) f5_combine_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ z,
+                                                         __nv_bfloat16* __restrict__ copyA, __nv_bfloat16* __restrict__ copyB, int T, long long hw,
+                                                         long long M, int rev) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int t = (int)((m / hw) % T);
+  float4 f = *reinterpret_cast<const float4*>(part + ((size_t)M + m) * 4);                    // tap 1: this frame
+  if (t > 0) {
+    const float4 q = *reinterpret_cast<const float4*>(part + (size_t)(m - hw) * 4);           // tap 0 applied to frame t - 1
+    f.x += q.x; f.y += q.y; f.z += q.z;
+  }
+  if (t + 1 < T) {
+    const float4 q = *reinterpret_cast<const float4*>(part + ((size_t)2 * M + m + hw) * 4);    // tap 2 applied to frame t + 1
+    f.x += q.x; f.y += q.y; f.z += q.z;
+  }
+  f.x += __ldg(bias); f.y += __ldg(bias + 1); f.z += __ldg(bias + 2);
+  float* zp = z + quad_off((size_t)M, 0, (size_t)m);
+  const float4 x1 = *reinterpret_cast<const float4*>(zp);
+  const float y0 = rev ? x1.x - f.x : x1.x + f.x, y1 = rev ? x1.y - f.y : x1.y + f.y, y2 = rev ? x1.z - f.z : x1.z + f.z;
+  *reinterpret_cast<float4*>(zp) = make_float4(y0, y1, y2, 0.f);
+  const uint4 lo = make_uint4(pack_bf2(y0, y1), pack_bf2(y2, 0.f), 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+  if (copyA) {
+    uint4* o = reinterpret_cast<uint4*>(copyA + (size_t)m * 16);
+    o[0] = lo;
+    o[1] = zero;
+  }
+  if (copyB) {
+    uint4* o = reinterpret_cast<uint4*>(copyB + (size_t)m * 16);
+    o[0] = lo;
+    o[1] = zero;
+  }
+}
+
 static int smem_bytes(int sch, int nx) {
   const int L = nlayers_of(sch);
   return 1024 + nxr_of(sch) * nx * SLAB_ROW + 3 * WT_BYTES * (L * nx + L * (L - 1)) + BAR_BYTES + XBUF_BYTES + BIAS_BYTES +
-         (xs_of(sch) ? 4 * XS_BYTES_PER : 0);
+         (xs_of(sch) ? 4 * XS_BYTES_PER : 0) + (f5_of(sch) ? F5_KSTEPS * F5_TILE : 0);
 }
 // One instantiation per X width the network has -- 1 slab (G, H, local_m1), 3 (F), 4 (the STP 64 -> 64 blocks) -- each with the
 // deepest schedule whose X ring and weights fit shared memory; -1: not built for this width (the caller runs layer by layer).
@@ -633,11 +783,33 @@ int dense_fused_layers(int cin) {
   return sch < 0 ? 0 : dbf::nlayers_of(sch);
 }
 
+int pack_f5_weights(void** img, const float* wref, int cin, cudaStream_t st) {
+  SELFC_CHECK_ARG(cin == 16 * dbf::F5_KSTEPS, "pack_f5_weights: built for %d input channels, got %d", 16 * dbf::F5_KSTEPS, cin);
+  const size_t bytes = (size_t)2 * dbf::F5_KSTEPS * dbf::F5_TILE;
+  if (*img == nullptr) SELFC_CUDA(cudaMalloc(img, bytes));
+  dbf::pack_f5_kernel<<<cdiv(dbf::F5_N * cin, 256), 256, 0, st>>>(wref, reinterpret_cast<__nv_bfloat16*>(*img), cin);
+  SELFC_LAUNCH_CHECK("pack_f5_kernel");
+  return 0;
+}
+
+int launch_f5_combine(const float* part, const float* bias, float* z, __nv_bfloat16* copyA, __nv_bfloat16* copyB, int T, long long hw,
+                      long long M, int rev, cudaStream_t st) {
+  if (M == 0) return 0;
+  SELFC_CHECK_ARG(part && bias && z && aligned16(part) && aligned16(z), "f5_combine: null or misaligned buffer");
+  dbf::f5_combine_kernel<<<cdiv(M, 256), 256, 0, st>>>(part, bias, z, copyA, copyB, T, hw, M, rev);
+  SELFC_LAUNCH_CHECK("f5_combine_kernel");
+  return 0;
+}
+
 int launch_dense_fused(const TcConvW* w, int L, __nv_bfloat16* buf, long long slabM, int cin, int N, int h, int wd, cudaStream_t st,
-                       const TcConvW* w2, __nv_bfloat16* buf2) {
+                       const TcConvW* w2, __nv_bfloat16* buf2, const void* f5img, float* f5part) {
   SELFC_CHECK_ARG(cin % 16 == 0 && cin > 0, "dense_fused: cin=%d must be a positive multiple of 16", cin);
   const int nx = cin / 16;
-  const int sch = dbf::pick_schedule(nx, L);
+  const bool f5 = f5img != nullptr;
+  SELFC_CHECK_ARG(!f5 || (nx == 3 && L == 4 && w2 == nullptr && f5part != nullptr && aligned16(f5part)),
+                  "dense_fused: the conv5-taps group is built for the F block (cin 48, 4 layers, single problem)");
+  const int sch = f5 ? 3 : dbf::pick_schedule(nx, L);
+  SELFC_CHECK_ARG(!f5 || dbf::smem_bytes(3, nx) <= 227 * 1024, "dense_fused: the conv5-taps schedule does not fit shared memory");
   SELFC_CHECK_ARG(sch >= 0 && dbf::nlayers_of(sch) == L, "dense_fused: cin=%d with %d fused layers does not fit shared memory", cin, L);
   SELFC_CHECK_ARG(aligned16(buf) && slabM == (long long)N * h * wd, "dense_fused: slab layout / alignment");
   const bool dual = w2 != nullptr;
@@ -693,6 +865,9 @@ int launch_dense_fused(const TcConvW* w, int L, __nv_bfloat16* buf, long long sl
   if (piece_len < 8) piece_len = 8;
   p.piece_len = piece_len;
   const int pieces = cdiv(p.total_pr, piece_len);
+  p.w5img = f5img;
+  p.part = f5part;
+  p.store_growth = f5 ? 0 : 1;
   p.err = tc::err_flag_for_device();
   const bool dbg = tc::debug_slots();
   if (dbg) p.dbg = tc::debug_next_slot(8000000 + (dual ? 100000 : 0) + sch * 1000 + nx);
@@ -707,11 +882,14 @@ int launch_dense_fused(const TcConvW* w, int L, __nv_bfloat16* buf, long long sl
     SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<3, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(dbf::dense_fused_kernel<3, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
   }
   const int grid = 2 * pieces * p.nprob;
   auto kern = sch == 0 ? (dbg ? dbf::dense_fused_kernel<0, 1, true> : dbf::dense_fused_kernel<0, 1, false>)
             : sch == 1 ? (dbg ? dbf::dense_fused_kernel<1, 3, true> : dbf::dense_fused_kernel<1, 3, false>)
+            : sch == 3 ? (dbg ? dbf::dense_fused_kernel<3, 3, true> : dbf::dense_fused_kernel<3, 3, false>)
                        : (dbg ? dbf::dense_fused_kernel<2, 4, true> : dbf::dense_fused_kernel<2, 4, false>);
   SELFC_CUDA(tc::launch_pdl_pairs(kern, grid, dbf::THREADS, smem, st, tmap, tmap2, p));
   SELFC_LAUNCH_CHECK("dense_fused_kernel");

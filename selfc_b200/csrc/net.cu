@@ -194,6 +194,29 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
   const DenseW& G = ctx->inv[blk][1];
   const DenseW& H = ctx->inv[blk][2];
   auto do_F = [&]() -> int {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      // F has 3 outputs: conv5's temporal taps are applied inside the fused conv1..4 launch while the block's activations are on
+      // chip (9 partial products per pixel), x1..x4 never go to HBM, and a small kernel finishes conv5 + the additive coupling.
+      // SELFC_F5=0: conv1..4 launch + the temporal kernel (what G / H / the STP blocks use).
+      static int f5_on = -1;
+      if (f5_on < 0) {
+        const char* e = getenv("SELFC_F5");
+        const char* e2 = getenv("SELFC_DB_FUSED");
+        f5_on = ((e && atoi(e) == 0) || (e2 && atoi(e2) == 0)) ? 0 : 1;
+      }
+      if (f5_on && ctx->mode == SELFC_MODE_BF16 && F.f5img != nullptr && F.tc[0].img_pair != nullptr && F.xpad == 48 &&
+          dense_fused_layers(F.xpad) == 4) {
+        double flops = conv5_flops(F, d);
+        for (int k = 0; k < 4; ++k) flops += 2.0 * (double)d.M() * 9.0 * (F.cin + kGrowth * k) * kGrowth;
+        PROF(ctx, st, 0, flops,
+             launch_dense_fused(F.tc, 4, reinterpret_cast<__nv_bfloat16*>(fbuf), dense_slab(ctx, d), F.xpad, d.B * d.T, d.h, d.w, st, nullptr, nullptr,
+                                F.f5img, sbuf));
+        PROF(ctx, st, 1, 0.0,
+             launch_f5_combine(sbuf, F.t5.bias, z, reinterpret_cast<__nv_bfloat16*>(gbuf), reinterpret_cast<__nv_bfloat16*>(hbuf), d.T, d.hw(), d.M(),
+                               rev ? 1 : 0, st));
+        return 0;
+      }
+    }
     SELFC_TRY(run_dense_convs<T>(ctx, F, fbuf, ws.fpitch, d, st));
     ConvArgs<T> a = conv5_args<T>(ctx, F, fbuf, ws.fpitch, d);
     a.epi = EPI_COUPLE_Y1; a.rev = rev ? 1 : 0; a.z = z;
@@ -602,6 +625,7 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
     {
       for (int k = 0; k < 5; ++k) free_tc_weights(ctx->inv[b][j].tc[k]);
       free_temporal_weights(ctx->inv[b][j].t5);
+      if (ctx->inv[b][j].f5img) cudaFree(ctx->inv[b][j].f5img);
     }
   for (int i = 0; i < 6; ++i) {
     for (int k = 0; k < 5; ++k) free_tc_weights(ctx->stp[i].tc[k]);
@@ -708,8 +732,10 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
       if (ctx->mode == SELFC_MODE_BF16 && k < 4) {
         SELFC_TRY(pack_tc_weights(W->tc[k], p[d.first + 2 * k], p[d.first + 2 * k + 1], cin_ref, cin_buf, d.cin, d.xpad, st));
       }
-      if (ctx->mode == SELFC_MODE_BF16 && k == 4)
+      if (ctx->mode == SELFC_MODE_BF16 && k == 4) {
         SELFC_TRY(pack_temporal_weights(W->t5, p[d.first + 8], p[d.first + 9], d.cout, cin_ref, 3, cin_buf, d.cin, d.xpad, st));
+        if (d.cout == 3 && d.cin == d.xpad && cin_buf == 176) SELFC_TRY(pack_f5_weights(&W->f5img, p[d.first + 8], cin_buf, st));
+      }
     }
   }
   // GlobalAgg

@@ -27,6 +27,7 @@ struct DenseW {            // one D2DTInput in kernel layout
   int np[5] = {};
   TcConvW tc[5];           // tcgen05 bf16 images (BF16 mode)
   TcTempW t5;              // conv5 image (BF16 mode)
+  void* f5img = nullptr;   // BF16 mode, cout == 3 (F blocks): conv5's taps as a pointwise GEMM inside the fused dense-block kernel
 };
 struct GaW {
   float *fcw = nullptr, *fcb = nullptr, *p2w = nullptr, *p2b = nullptr, *p3w = nullptr, *p3b = nullptr;

@@ -673,6 +673,7 @@ def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
         e = dict(os.environ)
         for k in ("SELFC_TC3_PAIR", "SELFC_TC3_P2", "SELFC_ZIGZAG", "SELFC_DB_FUSED"):
             e.pop(k, None)
+        e["SELFC_F5"] = "0"      # conv5's taps inside the fused launch re-associate an fp32 sum: compared with a tolerance elsewhere
         e.update(extra)
         r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET % here, out], env=e, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
@@ -713,21 +714,36 @@ def test_fused_dense_block_is_bit_identical_to_layer_by_layer(dev, tmp_path, b, 
     import sys
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for i, extra in enumerate(({}, {"SELFC_DB_FUSED": "0"})):
+    # default (fused blocks + conv5's taps of the F blocks inside the fused launch), SELFC_F5=0 (fused blocks, temporal kernel for
+    # every conv5), SELFC_DB_FUSED=0 (layer by layer)
+    for i, extra in enumerate(({}, {"SELFC_F5": "0"}, {"SELFC_DB_FUSED": "0"})):
         out = str(tmp_path / f"f{i}.pt")
         e = dict(os.environ)
-        e.pop("SELFC_DB_FUSED", None)
+        for k in ("SELFC_DB_FUSED", "SELFC_F5"):
+            e.pop(k, None)
         e.update(extra)
         r = subprocess.run([sys.executable, "-c", _FUSED_SNIPPET % here, out, str(b), str(t), str(h), str(w)], env=e, capture_output=True,
                            text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(torch.load(out))
-    for k in outs[0]:
-        same = torch.equal(outs[0][k], outs[1][k])
+    for k in outs[1]:
+        same = torch.equal(outs[1][k], outs[2][k])
         if not same:
-            d = (outs[0][k].float() - outs[1][k].float()).abs()
+            d = (outs[1][k].float() - outs[2][k].float()).abs()
             print(f"[fused vs layer-by-layer] {k}: max |diff| {d.max().item():.3e}, differing {100.0 * (d > 0).float().mean().item():.3f} %")
         assert same, f"{k} differs between the fused and the layer-by-layer dense block"
+    # The conv5-taps path sums the three taps' fp32 partial products outside the accumulator: the same numbers up to fp32 summation
+    # order (1e-7; bit-identical when T = 1).  In bf16 mode such a perturbation occasionally flips the bf16 rounding of a y1 / y2
+    # copy (2^-9 relative), which the following blocks amplify locally to ~1e-3 -- the mode's own noise floor against the oracle
+    # (LR codes 89 % exact, HR 5e-3..9e-3) -- so the two paths are compared with that floor, not bit for bit.
+    for k in outs[0]:
+        if k in ("lr", "rec"):
+            continue
+        assert torch.equal(outs[0][k], outs[1][k]), f"{k}: the dense-block entry points do not use the conv5-taps path"
+    dl = (outs[0]["lr"].int() - outs[1]["lr"].int()).abs()
+    dr = (outs[0]["rec"] - outs[1]["rec"]).abs().max().item()
+    print(f"[conv5 taps in the fused launch vs temporal kernel] LR codes equal {100.0 * (dl == 0).float().mean().item():.4f} %, HR max |diff| {dr:.3e}")
+    assert dl.max().item() <= 1 and (dl == 0).float().mean().item() >= 0.95 and dr <= 1e-2
 
 
 # ------------------------------------------------------------------------------------------------ f1: metrics kernels
