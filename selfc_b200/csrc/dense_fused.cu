@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
     int cur = pr_begin;
     Seg sg;
     long long w_tfull = 0;
-    int mine = 0;
+    int mine = 0, xrows = 0;              // groups / exchanging rows this team has drained
     const long long t_start = DBG ? clock64() : 0;
     while (next_seg(cur, pr_end, h, crank, sg)) {
       const int r0 = sg.r0, r1 = sg.r1;
@@ -612,7 +612,9 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
           } else {
           // neighbours across the quarter boundaries: lane 31's kx=0 partials go right, lane 0's kx=2 partials go left.
           // Branch-free on purpose: a divergent region costs ~70 cycles here and this is the per-row critical path.
-          float* xb = xbuf + (size_t)(((team * 2 + wg) * 2 + (use & 1)) * 4) * 32;
+          // double buffered by the count of rows THIS team exchanged (not by the group count: the conv5-taps group of SCH 3 takes
+          // part in the group sequence without a barrier, so two exchanging rows of a team can be 2 groups apart with equal parity)
+          float* xb = xbuf + (size_t)(((team * 2 + wg) * 2 + (xrows & 1)) * 4) * 32;
           if (edge_l || edge_r) {
             float4* dst = reinterpret_cast<float4*>(xb + (q * 2 + (edge_l ? 1 : 0)) * 16);
 #pragma unroll
@@ -658,6 +660,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
             *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
           ++mine;
+          ++xrows;
         };
         // SCH 3: the conv5-taps group -- 9 partial products per pixel (columns tap * 3 + co) -> part[tap][m] as (co0, co1, co2, 0)
         auto group5 = [&]() {
