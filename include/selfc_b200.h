@@ -186,6 +186,13 @@ int selfc_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, i
 int selfc_prof_enable(selfc_ctx* ctx, int on);
 int selfc_prof_read(selfc_ctx* ctx, int ncls, double* ms, double* work, uint64_t* launches);
 
+/* The row schedule of dense_fused_kernel (csrc/dense_fused.cu) for schedule id `sch` (0: one-slab X, 1: F, 2: 64->64 STP, 3: F with
+ * conv5's taps), for tests that verify the ring sizes by simulating the issue order (host only, no device needed):
+ * out[0] = conv layers L, out[1] = groups per step, out[2] = X-ring slots, out[3..7] = lag of group j (rows behind conv1),
+ * out[8..12] = issue order, out[13..16] = tensor-memory ring rows of x1..x4 (0 = not kept on chip), out[17] = tensor-memory
+ * columns in use.  Returns 0, or SELFC_E_ARG for an unknown id. */
+int selfc_dense_fused_schedule(int sch, int* out18);
+
 /* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
 uint64_t selfc_launch_count(void);
 

@@ -30,6 +30,7 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
 // w[0..L-1] = the block's conv_k weights (TcConvW::img_pair is what the kernel reads), L = dense_fused_layers(cin): 4, or 3 when the fourth layer's
 // weights do not fit shared memory next to the X ring (cin = 64).  Reads channels [0,cin) of the slab-planar buffer, writes
 // x1..xL to [cin, cin + 32 L); bit-identical to L launches of launch_conv3x3_tc.  (w2, buf2): second problem of the same shape.
+int dense_fused_schedule(int sch, int* out18);       // the compiled schedule tables (C-ABI selfc_dense_fused_schedule)
 int dense_fused_layers(int cin);      // how many layers (4, 3 or 0 = unsupported) one launch fuses for this X width
 // (f5img, f5part): for a block with 3 outputs (F of a coupling; cin 48) the launch also applies conv5's three temporal taps to
 // every row while [X | x1..x4] is on chip and writes 9 fp32 partial products per pixel to f5part [3 taps][M][4]; x1..x4 are then

@@ -780,6 +780,25 @@ static int pick_schedule(int nx, int max_layers) {
 
 }  // namespace dbf
 
+int dense_fused_schedule(int sch, int* out) {
+  if (sch < 0 || sch > 3 || out == nullptr) return SELFC_E_ARG;
+  const int L = dbf::nlayers_of(sch), ng = dbf::ngroups_of(sch);
+  for (int i = 0; i < 18; ++i) out[i] = 0;
+  out[0] = L;
+  out[1] = ng;
+  out[2] = dbf::nxr_of(sch);
+  for (int j = 0; j < ng; ++j) out[3 + j] = dbf::lag_of(sch, j);
+  for (int oi = 0; oi < ng; ++oi) out[8 + oi] = dbf::order_of(sch, oi);
+  const int kept = dbf::f5_of(sch) ? L : L - 1;          // layers whose rows are A operands of later groups
+  int cols = dbf::RING_COL0;
+  for (int j = 0; j < kept; ++j) {
+    out[13 + j] = dbf::ring_of(sch, j);
+    cols += 16 * dbf::ring_of(sch, j);
+  }
+  out[17] = cols;
+  return 0;
+}
+
 int dense_fused_layers(int cin) {
   if (cin % 16 != 0 || cin <= 0) return 0;
   const int sch = dbf::pick_schedule(cin / 16, 4);

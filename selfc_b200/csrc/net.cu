@@ -591,6 +591,7 @@ int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch
 extern "C" {
 
 int selfc_version(void) { return 100; }
+int selfc_dense_fused_schedule(int sch, int* out18) { return selfc::dense_fused_schedule(sch, out18); }
 /* debug only (SELFC_TC_DBG=1): barrier-wait cycle counters of the tcgen05 temporal kernel, 17 int64 per launch */
 int selfc_debug_read(long long* out, int cap) { return selfc::tc::debug_read(out, cap); }
 const char* selfc_last_error(void) { return g_err; }

@@ -134,3 +134,46 @@ def test_planar_gmm_layout_helpers_match_the_oracle_sampler():
     z[1:] = v.reshape(m, 12, 4).permute(1, 0, 2)
     got = engine.gmm_latent_from_planar(z, b * t, h, w)
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_dense_fused_schedules_keep_every_row_alive_until_its_last_reader():
+    """The fused dense-block kernel (csrc/dense_fused.cu) keeps rows of x1..x4 in tensor-memory rings and rows of X in a
+    shared-memory ring while four (five) layers walk down a strip, one row per step, `lag` rows apart and in a fixed issue
+    `order`.  A ring slot may be overwritten once every reader of its row has been ISSUED before the overwriting row's own MMAs
+    (tcgen05.commit covers everything issued earlier), a consumer must be issued after its producer, and everything has to fit 512
+    tensor-memory columns.  Simulate the issue order of the COMPILED tables (host-only C-ABI call) and check all three."""
+    import ctypes as C
+    from selfc_b200 import _lib, build
+    build.build()
+    L_ = _lib.lib()
+    out = (C.c_int * 18)()
+    assert L_.selfc_dense_fused_schedule(7, out) != 0
+    for sch in range(4):
+        assert L_.selfc_dense_fused_schedule(sch, out) == 0
+        v = list(out)
+        nl, ng, nxr = v[0], v[1], v[2]
+        lag, order, ring, cols = v[3:3 + ng], v[8:8 + ng], v[13:17], v[17]
+        assert sorted(order) == list(range(ng)) and cols <= 512 and lag[0] == 0
+        f5 = ng > nl
+
+        def reads(j, r):          # (source, row): source -1 = X, 0.. = x1..
+            if j < nl:            # conv layer j: rows r-1, r, r+1 of X and of every earlier layer
+                return [(g, rr) for g in range(-1, j) for rr in (r - 1, r, r + 1) if rr >= 0]
+            return [(g, r) for g in range(-1, nl)]      # conv5 taps: row r of everything
+        issued = [(s, j, s - lag[j]) for s in range(80) for j in order if s - lag[j] >= 0]
+        idx = {(j, r): k for k, (s, j, r) in enumerate(issued)}
+        kept = nl if f5 else nl - 1
+        for k, (s, j, r) in enumerate(issued):
+            for g, rr in reads(j, r):
+                if g < 0 or (g, rr) not in idx:
+                    continue
+                assert g < kept and ring[g] > 0, (sch, "a layer reads rows that are not kept on chip", j, g)
+                assert idx[(g, rr)] < k, (sch, "consumer issued before its producer", (j, r), (g, rr))
+                over = (g, rr + ring[g])            # the row that re-uses this slot
+                assert over not in idx or idx[over] > k, (sch, "ring too small", g, rr, (j, r))
+        # X rows alive at once (+1 in flight) must fit the ring
+        live = 0
+        for s in range(30, 80):
+            rows = [rr for j in order for g, rr in reads(j, s - lag[j]) if g == -1]
+            live = max(live, max(rows) - min(rows) + 1)
+        assert live + 1 <= nxr, (sch, live, nxr)
