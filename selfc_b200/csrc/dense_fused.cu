@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
   constexpr int NXR = nxr_of(SCH);
   constexpr bool F5 = f5_of(SCH);
   constexpr int DMAX = lag_of(SCH, F5 ? 4 : L - 1);
+  // oldest X row a step reads = s - XOLD: a conv layer at lag d reads rows down to s - d - 1, the conv5-taps group only row s - 6
+  constexpr int XOLD = F5 ? (lag_of(SCH, L - 1) + 1 > lag_of(SCH, 4) ? lag_of(SCH, L - 1) + 1 : lag_of(SCH, 4)) : lag_of(SCH, L - 1) + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t crank = cluster_ctarank();               // 0 = leader
   const int unit = (int)(blockIdx.x >> 1);
@@ -519,11 +521,11 @@ __global__ void __launch_bounds__(THREADS, 1) dense_fused_kernel(const __grid_co
             group(IC<order_of(SCH, 2)>{});
             if constexpr (L > 3) group(IC<order_of(SCH, 3)>{});
           }
-          // X row s - DMAX - 1 has no reader left
-          const int f = s - DMAX - 1;
+          // X row s - XOLD has no reader left (the next step's oldest row is s + 1 - XOLD)
+          const int f = s - XOLD;
           if (f >= rho0 && f < rho1) umma2_commit_elect(xempty((q_base + f - rho0) % NXR));
         }
-        for (int f = (s_last - DMAX > rho0 ? s_last - DMAX : rho0); f < rho1; ++f) umma2_commit_elect(xempty((q_base + f - rho0) % NXR));
+        for (int f = (s_last - XOLD + 1 > rho0 ? s_last - XOLD + 1 : rho0); f < rho1; ++f) umma2_commit_elect(xempty((q_base + f - rho0) % NXR));
         q_base += rho1 - rho0;
       }
       if (timed && lane == 0) {
