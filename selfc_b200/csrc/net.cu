@@ -621,6 +621,8 @@ int selfc_ctx_create(selfc_ctx** out, int device, int mode) {
 int selfc_ctx_destroy(selfc_ctx* ctx) {
   if (!ctx) return 0;
   if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->train_scratch) cudaFree(ctx->train_scratch);
+  if (ctx->train_zero_bias) cudaFree(ctx->train_zero_bias);
   for (int b = 0; b < 8; ++b)
     for (int j = 0; j < 3; ++j)
     {
@@ -710,6 +712,8 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
   const size_t head_perm_b = pl.take(720 * 4);
   if (ctx->arena_bytes < pl.off) {
     if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->train_scratch) cudaFree(ctx->train_scratch);
+  if (ctx->train_zero_bias) cudaFree(ctx->train_zero_bias);
     ctx->arena = nullptr;
     SELFC_CUDA(cudaMalloc(&ctx->arena, pl.off));
     ctx->arena_bytes = pl.off;

@@ -71,6 +71,10 @@ struct selfc_ctx {
   char* arena = nullptr;
   size_t arena_bytes = 0;
   std::mutex mu;
+  // training-step scratch owned by the context (dgrad weights + weight-gradient scratch, a zero bias vector): allocated on first
+  // use under `mu`, freed by selfc_ctx_destroy -- two contexts (or two trainers) on one device do not share it
+  float* train_scratch = nullptr;
+  float* train_zero_bias = nullptr;
   // optional per-launch timing (bench.py's roofline leg): CUDA events around every launch, by kernel class
   bool prof_on = false;
   std::vector<ProfRec> prof;

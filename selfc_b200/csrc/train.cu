@@ -17,6 +17,27 @@ namespace selfc {
 
 constexpr size_t kTrainScratchFloats = 768 * 1024;   // dgrad weights (<= 720 x 256) + weight-gradient scratch (<= 257 x 736), per device
 
+// Training scratch lives in the context (allocated once under its mutex, freed by selfc_ctx_destroy): two contexts, or two
+// trainers, on one device never share it.  The context's device is current when these run (check_run).
+static float* train_scratch(const selfc_ctx* cctx) {        // dgrad weights + weight-gradient scratch of dense_block_backward
+  selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (!ctx->train_scratch && cudaMalloc(&ctx->train_scratch, kTrainScratchFloats * sizeof(float)) != cudaSuccess) ctx->train_scratch = nullptr;
+  return ctx->train_scratch;
+}
+static float* train_zero_bias(const selfc_ctx* cctx) {      // dgrad has no bias term: 1024 zeros
+  selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (!ctx->train_zero_bias) {
+    if (cudaMalloc(&ctx->train_zero_bias, 1024 * sizeof(float)) != cudaSuccess) {
+      ctx->train_zero_bias = nullptr;
+      return nullptr;
+    }
+    cudaMemset(ctx->train_zero_bias, 0, 1024 * sizeof(float));
+  }
+  return ctx->train_zero_bias;
+}
+
 // ---- dgrad weights: wd[(tap' * cout4 + n)][c] = w[((taps-1-tap') * cin_buf + c)][n]   (w = forward pack [taps*cin_buf][np]) ----
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, int taps, int cin_buf, int np, int cout,
                                   int cout4, int npd) {
@@ -224,15 +245,8 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const float* buf
   const long long M = d.M();
   if (M == 0) return 0;
   SELFC_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)M * pitch * sizeof(float), st));
-  static float* zero_bias_dev[64] = {};       // dgrad has no bias term
-  int dev = 0;
-  cudaGetDevice(&dev);
-  SELFC_CHECK_ARG(dev >= 0 && dev < 64, "device index");
-  if (!zero_bias_dev[dev]) {
-    SELFC_CUDA(cudaMalloc(&zero_bias_dev[dev], 256 * sizeof(float)));
-    SELFC_CUDA(cudaMemset(zero_bias_dev[dev], 0, 256 * sizeof(float)));
-  }
-  float* zero_bias = zero_bias_dev[dev];
+  float* zero_bias = train_zero_bias(ctx);     // dgrad has no bias term
+  SELFC_CHECK_ARG(zero_bias != nullptr, "out of device memory (training scratch)");
   for (int k = 4; k >= 0; --k) {
     const int taps = k < 4 ? 9 : 3;
     const int tap_mode = k < 4 ? TAP_SPATIAL : TAP_TEMPORAL;
@@ -380,15 +394,6 @@ __global__ void cpl_rev_pre_kernel(float* __restrict__ gz, const float* __restri
   store4(gz + quad_off((size_t)M, 1 + q, (size_t)m), make_float4(oX[0], oX[1], oX[2], oX[3]));
 }
 
-static float* train_scratch() {              // dgrad weights + weight-gradient scratch of dense_block_backward (per device)
-  static float* scratch_dev[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return nullptr;
-  if (!scratch_dev[dev] && cudaMalloc(&scratch_dev[dev], kTrainScratchFloats * sizeof(float)) != cudaSuccess)
-    return nullptr;
-  return scratch_dev[dev];
-}
 
 // zin: the block's saved input state (planar); gz: gradient w.r.t. the block's OUTPUT state on entry, w.r.t. its INPUT state
 // on return; gparams: 30 gradients (F, G, H x conv1..5 weight/bias), accumulated into.  Scratch inside the workspace: the STP
@@ -406,7 +411,7 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
   float* gyH = gyG + (size_t)M * kHF;                                        // [M][48]
   float* gyF = reinterpret_cast<float*>(wsp + ws.h1);                        // [M][4]
   float* acc = gyF + (size_t)M * 4;                                          // [M][4]
-  float* scratch = train_scratch();
+  float* scratch = train_scratch(ctx);
   SELFC_CHECK_ARG(scratch != nullptr, "out of device memory (training scratch)");
   const DenseW& F = ctx->inv[blk][0];
   const DenseW& G = ctx->inv[blk][1];
@@ -617,17 +622,6 @@ __global__ void __launch_bounds__(128) gmm_sample_bwd_kernel(float* __restrict__
   for (int c = lane; c < 180; c += 32) dst[c] = reinterpret_cast<float4*>(P)[c];
 }
 
-static float* train_zero_bias() {
-  static float* zb[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return nullptr;
-  if (!zb[dev]) {
-    if (cudaMalloc(&zb[dev], 1024 * sizeof(float)) != cudaSuccess) return nullptr;
-    cudaMemset(zb[dev], 0, 1024 * sizeof(float));
-  }
-  return zb[dev];
-}
 
 // GMM head + sampler backward.  feat [M][64]: the STP feature (before the head's first LeakyReLU); gz: gradient state whose HF
 // quads hold g_v; gfeat [M][64] receives the feature gradient (overwritten); gparams[6]: tail_gmm.{1,3,5}.{weight,bias}.
@@ -641,8 +635,8 @@ int head_sampler_backward(const selfc_ctx* ctx, const float* feat, const float* 
   float* fact = reinterpret_cast<float*>(tp + tape.sc);           // [M][64]
   float* gh2 = reinterpret_cast<float*>(tp + tape.sa);            // [M][256]
   float* gh1 = reinterpret_cast<float*>(tp + tape.sb);            // [M][128]
-  float* scratch = train_scratch();
-  float* zb = train_zero_bias();
+  float* scratch = train_scratch(ctx);
+  float* zb = train_zero_bias(ctx);
   SELFC_CHECK_ARG(scratch && zb, "out of device memory (training scratch)");
   const HeadW& hd = ctx->head;
   // recompute the head: fact = lrelu(feat); h1 = lrelu(W1 fact + b1); h2 = lrelu(W2 h1 + b2); params = W3 h2 + b3
@@ -886,8 +880,8 @@ int ga_backward(const selfc_ctx* ctx, const GaW& g, const float* x, const float*
   float* gd = R + up64((size_t)d.B * T * T);         // [BT][64]
   float* gwmap = gd + (size_t)BT * 64;               // [hw]
   float* gb1w = gwmap + up64((size_t)hw);            // [64] scratch for the wsum-weighted bias gradient
-  float* scratch = train_scratch();
-  float* zb = train_zero_bias();
+  float* scratch = train_scratch(ctx);
+  float* zb = train_zero_bias(ctx);
   SELFC_CHECK_ARG(scratch && zb, "out of device memory (training scratch)");
   // recompute the forward's small quantities
   SELFC_TRY(launch_ga_wmap(g.fcw, wmap, d.h, d.w, st));
@@ -1034,7 +1028,7 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
   float* lrq = reinterpret_cast<float*>(tp + tape.lrq);
   float* glr = reinterpret_cast<float*>(tp + tape.glr);
   float* lacc = reinterpret_cast<float*>(tp + tape.loss);
-  float* scratch = train_scratch();
+  float* scratch = train_scratch(ctx);
   SELFC_CHECK_ARG(scratch != nullptr, "out of device memory (training scratch)");
   const float kScale = 144.0f * 144.0f * 3.0f;
   const float n_lr = (float)((double)M * 3.0), n_hr = (float)((double)M * 48.0);
@@ -1165,7 +1159,7 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
   float* buf = reinterpret_cast<float*>(wsp + ws.stpbuf);
   float* gbuf = reinterpret_cast<float*>(wsp + ws.params);           // M * 720 floats >= M * pitch
   float* gyd = reinterpret_cast<float*>(wsp + ws.h2);                // M * 256 floats
-  float* scratch = train_scratch();                                  // dgrad weights + weight-gradient scratch (<= 0.9 MB)
+  float* scratch = train_scratch(ctx);                                  // dgrad weights + weight-gradient scratch (<= 0.9 MB)
   SELFC_CHECK_ARG(scratch != nullptr, "out of device memory (training scratch)");
   const int pitch = W->xpad + 4 * kGrowth;
   SELFC_CHECK_ARG(dense_bwd_scratch_floats(*W) <= kTrainScratchFloats, "d2dt_backward: scratch size");
