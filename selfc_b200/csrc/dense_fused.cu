@@ -1,32 +1,33 @@
 // conv1..convL of a D2DTInput dense block (Subnet_constructor.py:102-105,126-129) as ONE launch: the growth channels
 // x1..x_{L-1} never leave the SM between the layers.  BF16 mode, tcgen05 / TMEM / TMA, CTA pairs (cta_group::2).
 //
-// Unfused (conv_tc3.cu) every layer re-reads [X | x1 | ...] from HBM: (cin + 32(k-1)) channels in, 32 out, per layer.  Here a
-// CTA owns a vertical STRIP of the image -- 128 positions wide, 120 of them outputs of the last layer -- and slides down it one
-// row per step with the four layers software-pipelined one behind the other ("line buffers"):
+// Layer by layer (conv_tc3.cu) every layer re-reads [X | x1 | ...] from HBM: (cin + 32(k-1)) channels in, 32 out, per layer.  Here
+// a CTA owns a vertical STRIP of the image -- 128 positions wide, 120 of them outputs of the last layer -- and slides down it one
+// row per step with the layers software-pipelined one behind the other ("line buffers"); e.g. for the one-slab-X blocks
 //
-//     step s issues, in this order:   conv1 row s,   conv3 row s-3,   conv2 row s-1,   conv4 row s-4          (L = 4)
+//     step s issues   conv1 row s,   conv2 row s-2,   conv3 row s-4,   conv4 row s-6
 //
-// A row of a layer is one accumulator: D[p][kx*32+n] += sum_c A[row+ky-1][p][c] * W[ky,kx][n][c] (M = 128 positions of this
-// CTA + 128 of its pair, N = 96 = the three kx taps stacked, K = 16), out[p][n] = D[p-1][kx=0] + D[p][kx=1] + D[p+1][kx=2]
-// -- the same arithmetic, in the same order, as conv3x3_tc3_kernel, so the results are bit-identical to the unfused path.
-// The A operands: X rows come from HBM by TMA (SWIZZLE_32B, one box per row: 128 positions x nx slabs) into an 8-row ring in
-// shared memory; the growth rows x1..x3 are written by the epilogue warps as bf16 straight into TENSOR MEMORY (tcgen05.st) and
-// read from there by the MMAs (A-in-TMEM form: lane = position, 8 columns per 16 channels; issue rate 48 cycles for N = 96,
-// profiles/r2b_ubench_mma_tmem_a.txt) -- rings of 6 / 5 / 3 rows = 224 columns next to three 96-column accumulators.
-// No vertical recompute (only 2 x (L-1) rows where a CTA's row range starts / ends), horizontal recompute 8 of 128 positions
-// (the same 15/16 efficiency as the 30-of-32 tiles of the unfused kernel).  Out-of-image rows are skipped MMAs, out-of-image
-// columns are TMA zero-fill (X) or zeros written by the epilogue (growth rows): exactly the zero padding of the reference.
-// Every layer's 32 outputs are also stored to the dense buffer in HBM once (conv5 reads them): per pixel a block moves
-// (cin + 128) bf16 channels instead of (4 cin + 192 + 128).
+// (the schedules -- lags, issue order, ring sizes -- are the tables below; C-ABI selfc_dense_fused_schedule exposes them to a CPU test
+// that simulates the issue order).  A row of a layer is one accumulator: D[p][kx*32+n] += sum_c A[row+ky-1][p][c] * W[ky,kx][n][c]
+// (M = 128 positions of this CTA + 128 of its pair, N = 96 = the three kx taps stacked, K = 16), out[p][n] = D[p-1][kx=0] +
+// D[p][kx=1] + D[p+1][kx=2] -- the same MMAs in the same K order and the same epilogue arithmetic as conv3x3_tc3_kernel, so the
+// results are bit-identical to the layer-by-layer path.
+// The A operands: X rows come from HBM once, by TMA (SWIZZLE_32B, one box per row: 128 positions x nx slabs), into a ring in shared
+// memory; the growth rows are written by the epilogue warps as bf16 straight into TENSOR MEMORY (tcgen05.st) and read from there by
+// the MMAs (A-in-TMEM form: lane = position, 8 columns per 16 channels; 48 cycles per N = 96 MMA, profiles/r2b_ubench_mma_tmem_a.txt)
+// -- rings of 8 + 6 + 4 rows next to two 96-column accumulators.  No vertical recompute (only 2 (L-1) rows where a CTA's row range
+// starts / ends), horizontal recompute 8 of 128 positions (the 15/16 efficiency of the 30-of-32 tiles of the layer-by-layer kernel).
+// Out-of-image rows are MMAs not issued, out-of-image columns are TMA zero-fill (X) or zeros written by the epilogue (growth rows):
+// exactly the zero padding of the reference.  Every layer's 32 outputs are stored to the dense buffer in HBM once (conv5 reads
+// them): per pixel a block moves (cin + 128) bf16 channels instead of (4 cin + 192 + 128) -- and for the F block (3 outputs) not
+// even that: conv5's three temporal taps are applied to the row while it is on chip (schedule 3) and 9 fp32 partial products per
+// pixel are all that leaves; f5_combine_kernel finishes conv5 and the additive coupling.
 //
-// The order above puts an independent row between a producer and its consumer (conv2 row s-1 needs x1 row s; conv4 row s-4
-// needs x3 row s-3), which hides the epilogue latency; ring sizes follow from it (a slot is overwritten only after every MMA
-// issued before the overwriting row's own MMAs has completed -- tcgen05.commit semantics).
-//
-// Per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warps 2..9 epilogue -- two warpgroups, each
-// taking 16 of a row's 32 output channels (halves the producer->consumer latency).  The lane +-1 neighbours of the kx
-// combination are warp shuffles inside a 32-position quarter and a 512-byte shared-memory exchange across quarters.
+// Per CTA (576 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only; interior rows take an unpredicated issue path
+// that stays in the uniform datapath), warps 2..17 epilogue = two teams x two channel halves x four lane quarters: team t drains the
+// groups with odd / even running index = accumulator t, so two rows' epilogues are in flight.  The lane +-1 neighbours of the kx
+// combination are warp shuffles + a 512-byte exchange across the lane quarters, or -- where shared memory allows (one-slab X) -- all
+// partial sums through shared memory.  A "row stored" mbarrier per ring slot tells the issuer when a growth row may be read.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
