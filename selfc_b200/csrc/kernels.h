@@ -102,8 +102,10 @@ int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const 
 int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, uint64_t seed, uint64_t offset, float* v,
                       bool v_nchw, int vpitch, int voff, int B, int T, int h, int w, cudaStream_t st);
 // params as planar quads [180][M][4] in the permuted channel order n' = j*240 + k*48 + hf (tcgen05 head); v -> planar z
+// params_half: the quads are fp16 (what the tcgen05 head writes by default), read by the warp-split form only
 int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* z, int B, int T, int h,
-                             int w, cudaStream_t st, int form = -1 /* 0 thread-per-pixel, 1 warp-split, -1 default / SELFC_GMM_SPLIT */);
+                             int w, cudaStream_t st, int form = -1 /* 0 thread-per-pixel, 1 warp-split, -1 default / SELFC_GMM_SPLIT */,
+                             bool params_half = false);
 // by_component: rows k*144 + j*48 + hf (fused head + sampler, one GEMM per mixture component); else j*240 + k*48 + hf
 int launch_permute_gmm_rows(const float* w, const float* b, float* wp, float* bp, bool by_component, cudaStream_t st);
 int launch_export_eps(float* eps, uint64_t seed, uint64_t offset, int B, int T, long long hw, cudaStream_t st);

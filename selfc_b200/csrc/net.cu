@@ -390,17 +390,28 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
                                 i == 5 ? fact : nullptr));
   }
   // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
-  bool head_done = false, sampled = false;
+  bool head_done = false, sampled = false, params_are_half = false;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     if (ctx->mode == SELFC_MODE_BF16 && ctx->head.t[0].img != nullptr) {
       // pointwise GEMMs over all M pixels, viewed as 2 pseudo-frames of ceil(M/2) rows (two accumulators in flight)
+      // The 720-channel parameter tensor between the last head GEMM and the sampler is stored as fp16 quads: the GEMM's inputs are
+      // bf16 (2^-9), fp16 (2^-11) adds nothing measurable, and its write + read halve.  SELFC_GMM_FP16=0: fp32 quads (also taken when
+      // the thread-per-pixel sampler form is selected, which reads fp32 only).
+      static int half_on = -1;
+      if (half_on < 0) {
+        const char* e = getenv("SELFC_GMM_FP16");
+        const char* e2 = getenv("SELFC_GMM_SPLIT");
+        half_on = ((e && atoi(e) == 0) || (e2 && atoi(e2) == 0)) ? 0 : 1;
+      }
+      const bool params_half = half_on == 1;
+      params_are_half = params_half;
       auto pointwise = [&](const TcTempW& w, const __nv_bfloat16* in, int in_pitch, __nv_bfloat16* outT, int outT_pitch, float* outF,
                            int outF_pitch, int outF_off, int act) -> int {
         TcTempArgs t;
         t.in = in; t.in_pitch = in_pitch; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
         t.epi = EPI_STORE; t.act = act;
         t.outT = outT; t.outT_pitch = outT_pitch; t.outF = outF; t.outF_pitch = outF_pitch; t.outF_off = outF_off;
-        t.outF_planar = outF != nullptr ? 1 : 0;     // GMM parameters as planar quads for the thread-per-pixel sampler
+        t.outF_planar = outF != nullptr ? (params_half ? 2 : 1) : 0;     // GMM parameters as planar quads (fp16 by default) for the sampler
         return launch_temporal_tc(w, t, st);
       };
       PROF(ctx, st, 3, 2.0 * M * 64 * 128, pointwise(ctx->head.t[0], fact, kStpC, h1, 128, nullptr, 0, 0, 1));
@@ -450,7 +461,8 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   }
   if (sampled) {
   } else if (head_done)
-    PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample_planar(params, eps, seed, offset, z, d.B, d.T, d.h, d.w, st));
+    PROF(ctx, st, 4, (double)M * (720 * (params_are_half ? 2 : 4) + 48 * 4),
+         launch_gmm_sample_planar(params, eps, seed, offset, z, d.B, d.T, d.h, d.w, st, -1, params_are_half));
   else
     PROF(ctx, st, 4, (double)M * (720 + 48) * 4, launch_gmm_sample(params, false, eps, seed, offset, z, false, /*planar z*/ -1, 0, d.B, d.T, d.h, d.w, st));
   if (hf) PROF(ctx, st, 5, (double)M * 48 * 8, launch_export_hf(z, hf, M, hw, st));

@@ -5,6 +5,7 @@
 // :383-394 + :412-417 (sampler / reparametrize).
 #include <cstdlib>
 #include <type_traits>
+#include <cuda_fp16.h>
 #include <cuda_pipeline.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -466,8 +467,22 @@ __global__ void __launch_bounds__(128) gmm_sample_planar_kernel(const float* __r
 // 120 Box-Muller pairs and 480 exp per pixel), so occupancy is what the form with all 60 logits in registers (113 registers,
 // 16 warps per SM: slower than thread-per-pixel in the stream) lacked.  The per-component max and exp-sum are combined across
 // the four warps through shared memory in a fixed order (deterministic).
-template <bool kEps>
-__global__ void __launch_bounds__(128, 8) gmm_sample_planar_perk_kernel(const float* __restrict__ params, const float* __restrict__ eps,
+// PT = float, or __half: the tcgen05 head stores the parameters as fp16 quads (8 bytes) -- its inputs are bf16 (2^-9), so fp16's
+// 2^-11 adds nothing measurable, and the 720-channel tensor's write + read halve (2.6 -> 1.3 GB each per 1080p GOP)
+template <typename PT>
+__device__ __forceinline__ float4 load_quad(const PT* params, size_t quad_index) {
+  if constexpr (std::is_same<PT, __half>::value) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(params + quad_index));
+    const __half2 a = *reinterpret_cast<const __half2*>(&r.x), b = *reinterpret_cast<const __half2*>(&r.y);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  } else {
+    return __ldg(reinterpret_cast<const float4*>(params + quad_index));
+  }
+}
+
+template <bool kEps, typename PT>
+__global__ void __launch_bounds__(128, 8) gmm_sample_planar_perk_kernel(const PT* __restrict__ params, const float* __restrict__ eps,
                                                                         uint64_t seed, uint64_t offset, float* __restrict__ z, int T,
                                                                         long long hw, long long M) {
   __shared__ float red_max[4][32];
@@ -490,7 +505,7 @@ __global__ void __launch_bounds__(128, 8) gmm_sample_planar_perk_kernel(const fl
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const int i = wq * 3 + q;
-      const float4 l = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, k * 12 + i, (size_t)m)));
+      const float4 l = load_quad<PT>(params, quad_off((size_t)M, k * 12 + i, (size_t)m));
       e[q][0] = l.x; e[q][1] = l.y; e[q][2] = l.z; e[q][3] = l.w;
     }
     float mk = e[0][0];
@@ -516,8 +531,8 @@ __global__ void __launch_bounds__(128, 8) gmm_sample_planar_perk_kernel(const fl
     for (int q = 0; q < 3; ++q) {
       const int i = wq * 3 + q;
       // issued before the Philox rounds, which cover most of their latency
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 60 + k * 12 + i, (size_t)m)));
-      const float4 m4 = __ldg(reinterpret_cast<const float4*>(params + quad_off((size_t)M, 120 + k * 12 + i, (size_t)m)));
+      const float4 s4 = load_quad<PT>(params, quad_off((size_t)M, 60 + k * 12 + i, (size_t)m));
+      const float4 m4 = load_quad<PT>(params, quad_off((size_t)M, 120 + k * 12 + i, (size_t)m));
       const float ls[4] = {s4.x, s4.y, s4.z, s4.w}, mu[4] = {m4.x, m4.y, m4.z, m4.w};
       float ep4[4];
       if constexpr (kEps) {
@@ -614,7 +629,7 @@ int launch_gmm_sample(const float* params, bool params_nchw, const float* eps, u
 }
 
 int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t seed, uint64_t offset, float* z, int B, int T, int h,
-                             int w, cudaStream_t st, int form) {
+                             int w, cudaStream_t st, int form, bool params_half) {
   const long long M = (long long)B * T * h * w;
   if (M == 0) return 0;
   static int split = -1;                  // SELFC_GMM_SPLIT=0: the thread-per-pixel form
@@ -623,10 +638,15 @@ int launch_gmm_sample_planar(const float* params, const float* eps, uint64_t see
     split = (e && atoi(e) == 0) ? 0 : 1;
   }
   const int f = form < 0 ? split : form;
-  if (f == 1 && eps != nullptr)
-    gmm_sample_planar_perk_kernel<true><<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
+  if (params_half) {
+    SELFC_CHECK_ARG(f == 1, "gmm_sample_planar: fp16 parameters are read by the per-component kernel only");
+    const __half* ph = reinterpret_cast<const __half*>(params);
+    if (eps != nullptr) gmm_sample_planar_perk_kernel<true, __half><<<cdiv(M, 32), 128, 0, st>>>(ph, eps, seed, offset, z, T, (long long)h * w, M);
+    else gmm_sample_planar_perk_kernel<false, __half><<<cdiv(M, 32), 128, 0, st>>>(ph, eps, seed, offset, z, T, (long long)h * w, M);
+  } else if (f == 1 && eps != nullptr)
+    gmm_sample_planar_perk_kernel<true, float><<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
   else if (f == 1)
-    gmm_sample_planar_perk_kernel<false><<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
+    gmm_sample_planar_perk_kernel<false, float><<<cdiv(M, 32), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
   else
     gmm_sample_planar_kernel<<<cdiv(M, 128), 128, 0, st>>>(params, eps, seed, offset, z, T, (long long)h * w, M);
   SELFC_LAUNCH_CHECK("gmm_sample_planar_kernel");

@@ -17,6 +17,7 @@
 // Epilogue warps read the accumulator of the finished pass (tcgen05.ld), apply bias and the fused coupling arithmetic on
 // the fp32 latent state, and release the accumulator.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -55,7 +56,7 @@ struct Params {
   int outT_pitch, outT_off;
   long long outT_slabM, copy_slabM;           // layouts of outT and of copyA / copyB (0 = pixel-major)
   float* outF;
-  int outF_pitch, outF_off, outF_planar;   // outF_planar: write quads [C/4][m_limit][4] instead of [M][pitch]
+  int outF_pitch, outF_off, outF_planar;   // outF_planar: write quads [C/4][m_limit][4] instead of [M][pitch]; 2: the quads are fp16
   float* z;
   float* sbuf;
   __nv_bfloat16* copyA;
@@ -476,7 +477,17 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                     if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
                 }
               }
-              if (p.outF && p.outF_planar) {
+              if (p.outF && p.outF_planar == 2) {
+                __half* oh = reinterpret_cast<__half*>(p.outF);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const __half2 a = __floats2half2_rn(v[j], v[j + 1]), b = __floats2half2_rn(v[j + 2], v[j + 3]);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<const uint32_t*>(&a);
+                  pk.y = *reinterpret_cast<const uint32_t*>(&b);
+                  *reinterpret_cast<uint2*>(oh + quad_off((size_t)p.m_limit, (p.outF_off + n0 + j) / 4, m)) = pk;
+                }
+              } else if (p.outF && p.outF_planar) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
                   store4(p.outF + quad_off((size_t)p.m_limit, (p.outF_off + n0 + j) / 4, m), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
