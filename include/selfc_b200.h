@@ -35,6 +35,9 @@ extern "C" {
 /* precision modes (new knob, supplied out of band; SURVEY 8b "Config") */
 #define SELFC_MODE_FP32 0      /* fp32 storage, fp32 FMA convolutions: the <=1e-3 numerics gate */
 #define SELFC_MODE_BF16 1      /* bf16 activations, tcgen05 kind::f16 implicit-GEMM, fp32 accumulate/state */
+#define SELFC_MODE_BF16X3 2    /* the numerics-gate mode ON TENSOR CORES (BASELINE configs[1]): activations and weights as (hi, lo) bf16
+                                  pairs (16 mantissa bits), every product as three tcgen05 MMAs (hi.hi + hi.lo + lo.hi) with fp32
+                                  accumulation, fp32 latent state -- HR within 1e-3 of the fp32 reference at ~1/3 of the BF16 rate */
 
 #define SELFC_NUM_PARAMS 354   /* state_dict tensors of SelfCInvNet (vid4 YAML) */
 

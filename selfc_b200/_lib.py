@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(HERE, "libselfc_b200.so")
 
 MODE_FP32 = 0
 MODE_BF16 = 1
+MODE_BF16X3 = 2      # (hi, lo) bf16 pairs, three tcgen05 MMAs per product: the <=1e-3 numerics gate on tensor cores
 NUM_PARAMS = 354
 
 _lib = None

@@ -101,6 +101,81 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+// ---- BF16X3 mode: activations as (hi, lo) bf16 pairs ------------------------------------------------------------
+// The fp32-gate mode on tensor cores (BASELINE configs[1]) keeps every activation as hi = bf16(v), lo = bf16(v - hi) (16 mantissa
+// bits) and every weight the same way, and forms A.W = A_hi.W_hi + A_hi.W_lo + A_lo.W_hi with three bf16 MMAs into one fp32
+// accumulator (the dropped A_lo.W_lo term is 2^-18 relative).  Storage: the buffers keep the layouts of common.cuh's dense
+// buffers with a 4-byte element, but the two halves of an element are NOT adjacent: every run of 16 consecutive elements (one
+// 64-byte row: 16 channels of one pixel, in the slab-planar and in the pixel-major layout alike) is stored as [16 x hi | 16 x lo],
+// i.e. as two K = 16 operand rows of 32 bytes that the MMA descriptors address directly (+0 / +32 bytes inside a SWIZZLE_64B or
+// SWIZZLE_128B row).  `bfx2*` is therefore a HANDLE: pointer arithmetic counts logical elements, and the helpers below turn
+// the handle into the addresses of the two halves (buffers are 64-byte aligned; rows never straddle).
+struct bfx2 { uint32_t opaque; };
+__host__ __device__ __forceinline__ size_t x2_hi_index(size_t logical) { return ((logical >> 4) << 5) + (logical & 15); }   // in bf16 units; lo = +16
+__device__ __forceinline__ __nv_bfloat16* x2_hi_ptr(const bfx2* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  return reinterpret_cast<__nv_bfloat16*>((a & ~(uintptr_t)63) + ((a & 63) >> 1));
+}
+__device__ __forceinline__ void x2_split(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t x2_pack_hi(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t x2_pack_lo(float a, float b, uint32_t hi) {      // residuals of the two values packed in `hi`
+  return x2_pack_hi(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+// 8 consecutive channels (multiple of 8 inside a 16-row) -> 16 bytes of hi + 16 bytes of lo at +32 bytes
+__device__ __forceinline__ void x2_store8(__nv_bfloat16* hi_ptr, const float* v) {
+  uint4 h, l;
+  h.x = x2_pack_hi(v[0], v[1]); h.y = x2_pack_hi(v[2], v[3]); h.z = x2_pack_hi(v[4], v[5]); h.w = x2_pack_hi(v[6], v[7]);
+  l.x = x2_pack_lo(v[0], v[1], h.x); l.y = x2_pack_lo(v[2], v[3], h.y); l.z = x2_pack_lo(v[4], v[5], h.z); l.w = x2_pack_lo(v[6], v[7], h.w);
+  *reinterpret_cast<uint4*>(hi_ptr) = h;
+  *reinterpret_cast<uint4*>(hi_ptr + 16) = l;
+}
+__device__ __forceinline__ void x2_load8(const __nv_bfloat16* hi_ptr, float* v) {
+  const uint4 h = *reinterpret_cast<const uint4*>(hi_ptr);
+  const uint4 l = *reinterpret_cast<const uint4*>(hi_ptr + 16);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ float4 load4(const bfx2* p) {
+  const __nv_bfloat16* h = x2_hi_ptr(p);
+  const uint2 a = *reinterpret_cast<const uint2*>(h);
+  const uint2 b = *reinterpret_cast<const uint2*>(h + 16);
+  return make_float4(__uint_as_float(a.x << 16) + __uint_as_float(b.x << 16),
+                     __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u),
+                     __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16),
+                     __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u));
+}
+__device__ __forceinline__ void store4(bfx2* p, float4 v) {
+  __nv_bfloat16* h = x2_hi_ptr(p);
+  uint2 a, b;
+  a.x = x2_pack_hi(v.x, v.y); a.y = x2_pack_hi(v.z, v.w);
+  b.x = x2_pack_lo(v.x, v.y, a.x); b.y = x2_pack_lo(v.z, v.w, a.y);
+  *reinterpret_cast<uint2*>(h) = a;
+  *reinterpret_cast<uint2*>(h + 16) = b;
+}
+// single elements (the layout kernels of the component entry points)
+__device__ __forceinline__ float load1(const float* p) { return *p; }
+__device__ __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float load1(const bfx2* p) {
+  const __nv_bfloat16* h = x2_hi_ptr(p);
+  return __bfloat162float(h[0]) + __bfloat162float(h[16]);
+}
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store1(bfx2* p, float v) {
+  __nv_bfloat16* h = x2_hi_ptr(p);
+  x2_split(v, h[0], h[16]);
+}
+
 // ---- Philox4x32-10 counter RNG (keyed on the reference's eps linear index; SURVEY 7.2 "RNG") ---------
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                        uint32_t k0, uint32_t k1, uint32_t out[4]) {

@@ -248,6 +248,12 @@ int launch_conv_simt(const ConvArgs<T>& a, cudaStream_t st) {
 }
 template int launch_conv_simt<float>(const ConvArgs<float>&, cudaStream_t);
 template int launch_conv_simt<__nv_bfloat16>(const ConvArgs<__nv_bfloat16>&, cudaStream_t);
+// BF16X3 mode runs on the tcgen05 kernels only: there is no FMA fallback for (hi, lo) buffers, and asking for one is an error
+template <>
+int launch_conv_simt<bfx2>(const ConvArgs<bfx2>&, cudaStream_t) {
+  set_error("BF16X3 mode: this convolution has no tcgen05 path for the requested shape (no fp32-FMA fallback for (hi, lo) buffers)");
+  return SELFC_E_UNSUPPORTED;
+}
 
 // ---- weight packing ---------------------------------------------------------------------------------------
 __global__ void pack_conv_simt_kernel(const float* __restrict__ wref, const float* __restrict__ bref, float* __restrict__ wpk,

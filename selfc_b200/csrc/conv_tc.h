@@ -11,20 +11,23 @@ namespace selfc {
 struct TcConvW {
   void* img = nullptr;      // device, bf16
   void* img_pair = nullptr; // device, bf16: the same rows split in two halves for the CTA-pair kernel
+  void* img_x2 = nullptr;   // device, bf16 (BF16X3 mode): the pair image with a hi and a lo tile per (ky, K-step), 2 x img_bytes
   float* bias = nullptr;    // device, [32]
   size_t img_bytes = 0;
   int cin_buf = 0;          // input channels consumed from the dense buffer (multiple of 16)
 };
 
-int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st);
+int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st,
+                    bool x2 = false);
 void free_tc_weights(TcConvW& w);
 // conv_k of a dense block, in place on the slab-planar buffer (slabM = N*h*wd pixels per 16-channel slab): reads
 // channels [0,cin), writes lrelu(conv+bias) to [out_off,out_off+32)   (conv_tc3.cu)
 // (w2, buf2): optional second problem of the same shape run by the other half of the grid in the same launch (G and H).
 // The buffers must have 32 readable bytes before their first and after their last slab (the position-pair tensor map reads one
 // position either side; the values never reach an output).  Workspace regions satisfy this: none is first, all carry a guard.
+// x2 (BF16X3 mode, common.cuh): the buffers hold (hi, lo) bf16 pairs -- 64-byte rows per position and slab -- and every tap is three MMAs
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
-                      const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr);
+                      const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr, bool x2 = false);
 
 // ---- dense_fused.cu: conv1..convL of a dense block in ONE launch, growth channels kept in tensor memory ----------------
 // w[0..L-1] = the block's conv_k weights (TcConvW::img_pair is what the kernel reads), L = dense_fused_layers(cin): 4, or 3 when the fourth layer's
@@ -47,6 +50,7 @@ struct TcTempW {
   float* bias = nullptr;    // device, [64]
   size_t img_bytes = 0;
   int cin_buf = 0, npad = 0, taps = 0, cout = 0;
+  bool x2 = false;          // BF16X3 mode: a hi and a lo tile per (tap, K-step); the launch then reads (hi, lo) activations
 };
 
 struct TcTempArgs {
@@ -62,6 +66,7 @@ struct TcTempArgs {
   long long outT_slabM = 0, copy_slabM = 0;
   float* outF = nullptr;
   int outF_pitch = 0, outF_off = 0, outF_planar = 0;
+  int outF_blk = 0, outF_blk_stride = 0;   // planar outF: column n -> channel outF_off + (n / blk) * stride + n % blk
   long long m_limit = 0;             // > 0: rows >= m_limit do not exist (pointwise mode over pseudo-frames)
   float* z = nullptr;
   float* sbuf = nullptr;
@@ -87,7 +92,7 @@ struct TcTempArgs {
 };
 
 int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int cout, int cin_ref, int taps, int cin_buf, int xreal,
-                          int xpad, cudaStream_t st);
+                          int xpad, cudaStream_t st, bool x2 = false);
 void free_temporal_weights(TcTempW& w);
 bool temporal_tc_supported(const TcTempW& w, int T);
 // w2: weights of the second conv of an EPI_COUPLE_HG launch (G), same shape as w (H)

@@ -118,12 +118,19 @@ __device__ __forceinline__ void decode_tile(const Params& p, int tile, int& tx, 
 // origin 30*tx-1 is pair aligned: the tensor map is based one position BEFORE the buffer, row pitch W positions, W/2+1 pairs per
 // row.  The two positions this makes readable that are not padding zeros -- x = -1 (previous row's last pixel) and x = W (next
 // row's first) -- only ever feed the kx=0 term of x = 0 and the kx=2 term of x = W-1, which the epilogue drops.
-template <bool PAIR, bool P2>
+// X2 (BF16X3 mode, common.cuh; PAIR only, one position per TMA row): activations and weights are (hi, lo) bf16 pairs.  A position's
+// 16 channels are one 64-byte row [16 x hi | 16 x lo] (SWIZZLE_64B), i.e. two K = 16 operand rows 32 bytes apart, every (ky, K-step)
+// has a hi and a lo weight tile, and a tap issues THREE MMAs into the same accumulator -- hi.hi, hi.lo, lo.hi -- so the product
+// carries 16 mantissa bits per operand with fp32 accumulation; the epilogue splits its fp32 results the same way.
+template <bool PAIR, bool P2, bool X2 = false>
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                   const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  static_assert(!X2 || (PAIR && !P2), "the (hi, lo) form exists for CTA pairs with one position per TMA row");
   constexpr int NBH = PAIR ? NB / 2 : NB;                 // weight rows held by this CTA
   constexpr int WT_BYTES = NBH * 16 * 2;                  // one (ky, K-step) B tile of this CTA
+  constexpr int WSTEP = X2 ? 2 * WT_BYTES : WT_BYTES;     // X2: a K-step's hi tile followed by its lo tile
+  constexpr int SUBB = X2 ? 2 * SUB_BYTES : SUB_BYTES;    // one K-step sub-tile of activations
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // scheduling unit: a CTA or a CTA pair
   const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
   __nv_bfloat16* obuf = prob ? p.buf2 : p.buf;
   const int NST = p.nst;
   const int KPS = p.kps;
-  const int STAGE = KPS * SUB_BYTES;
+  const int STAGE = KPS * SUBB;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   // [activation stages][barriers][weights]
@@ -186,11 +193,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t wbytes = 3u * nks * WT_BYTES;
+      const uint32_t wbytes = 3u * nks * WSTEP;
       const uint8_t* wsrc = (const uint8_t*)wimg + (PAIR ? (size_t)crank * wbytes : 0);
       mbar_expect_tx(w_bar, wbytes);
       for (int ky = 0; ky < 3; ++ky)
-        bulk_g2s(w_base + ky * nks * WT_BYTES, wsrc + (size_t)ky * nks * WT_BYTES, (uint32_t)nks * WT_BYTES, w_bar);
+        bulk_g2s(w_base + ky * nks * WSTEP, wsrc + (size_t)ky * nks * WSTEP, (uint32_t)nks * WSTEP, w_bar);
 #ifdef SELFC_TC_TIMING
       const long long t_pdl0 = clock64();
 #endif
@@ -240,9 +247,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
       uint32_t ph = 0;
       int it = 0;
       // activations: SWIZZLE_32B rows of one position (8-row atoms of 256 bytes) / P2: SWIZZLE_64B rows of a position pair (512)
-      const uint32_t hi_a = P2 ? desc_hi(512, 4) : desc_hi(256, 6);
+      const uint32_t hi_a = (P2 || X2) ? desc_hi(512, 4) : desc_hi(256, 6);
       const uint32_t hi_b = desc_hi(128, 0);            // weights: no-swizzle core matrices, 8-row groups 128 bytes apart
-      const uint32_t b_ky = (uint32_t)nks * (WT_BYTES >> 4);
+      const uint32_t b_ky = (uint32_t)nks * (WSTEP >> 4);
       long long w_full = 0, w_tempty = 0;
       const long long t_start = clock64();
       for (int step = rank; step < nsteps; step += nwalk, ++it) {
@@ -256,11 +263,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
           tc_fence_after();
           const uint32_t a_stage = a_base + s * STAGE;
           for (int ks = 0; ks < nk; ++ks) {
-            const uint32_t a_lo = desc_lo(a_stage + (uint32_t)ks * SUB_BYTES, 16);
+            const uint32_t a_lo = desc_lo(a_stage + (uint32_t)ks * SUBB, 16);
             // B (weights): (ky, K-step) tiles; the two 8-element K core matrices are NBH/8 row-groups apart
-            const uint32_t b_lo = desc_lo(w_base + (uint32_t)(c0 + ks) * WT_BYTES, (NBH / 8) * 128);
+            const uint32_t b_lo = desc_lo(w_base + (uint32_t)(c0 + ks) * WSTEP, (NBH / 8) * 128);
             // consecutive MMAs alternate between the two M-blocks' accumulators: back-to-back accumulation into ONE
             // accumulator is a dependent chain (measured ~145 cycles per small MMA), independent accumulators pipeline
+            if constexpr (X2) {
+              // rows of 64 bytes: M-block mb starts 128 rows in, the ky tap one tile row (32 rows) further; the lo half of a row
+              // is its second K = 16 operand (+32 bytes); the lo weight tile follows the hi tile
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+#pragma unroll
+                  for (int mb = 0; mb < MBLK; ++mb) {
+                    const uint32_t d = tmem_base + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
+                    const uint64_t ad = desc_join(a_lo + (uint32_t)(((mb * 128 + ky * WT) * 64 + (term == 2 ? 32 : 0)) >> 4), hi_a);
+                    const uint64_t bd = desc_join(b_lo + (uint32_t)ky * b_ky + (term == 1 ? (uint32_t)(WT_BYTES >> 4) : 0u), hi_b);
+                    umma2_bf16_elect(d, ad, bd, idesc, ((c0 + ks) > 0 || ky > 0 || term > 0) ? 1u : 0u);
+                  }
+                }
+              }
+              continue;
+            }
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -370,7 +395,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
           const int y = ty * ROWS + mb * 4 + q;
           const bool ok = tile_ok && lane < VALID_W && x < p.w && y < p.h;
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MBLK + mb) * ACC_STRIDE);
-          __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems + ((size_t)((size_t)(ok ? n : 0) * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * 16;
+          constexpr int ROWE = X2 ? 32 : 16;       // bf16 elements per (position, slab) row
+          __nv_bfloat16* o = obuf + (size_t)p.out_slab * slab_elems * (ROWE / 16) +
+                             ((size_t)((size_t)(ok ? n : 0) * p.h + (ok ? y : 0)) * p.w + (ok ? x : 0)) * ROWE;
   #pragma unroll
           for (int n0 = 0; n0 < NOUT; n0 += 16) {
             uint32_t r0[16], r1[16], r2[16];
@@ -395,12 +422,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
               v[j] = lrelu02(__uint_as_float(r0[j]) + a1 + a2 + bias[n0 + j]);
             }
             if (ok) {
-              uint4 lo, hi;
-              lo.x = pack_bf2(v[0], v[1]); lo.y = pack_bf2(v[2], v[3]); lo.z = pack_bf2(v[4], v[5]); lo.w = pack_bf2(v[6], v[7]);
-              hi.x = pack_bf2(v[8], v[9]); hi.y = pack_bf2(v[10], v[11]); hi.z = pack_bf2(v[12], v[13]); hi.w = pack_bf2(v[14], v[15]);
-              __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems;
-              *reinterpret_cast<uint4*>(os) = lo;
-              *reinterpret_cast<uint4*>(os + 8) = hi;
+              if constexpr (X2) {
+                __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems * 2;
+                x2_store8(os, v);              // channels 0..7: hi at +0, lo at +16 elements
+                x2_store8(os + 8, v + 8);      // channels 8..15
+              } else {
+                uint4 lo, hi;
+                lo.x = pack_bf2(v[0], v[1]); lo.y = pack_bf2(v[2], v[3]); lo.z = pack_bf2(v[4], v[5]); lo.w = pack_bf2(v[6], v[7]);
+                hi.x = pack_bf2(v[8], v[9]); hi.y = pack_bf2(v[10], v[11]); hi.z = pack_bf2(v[12], v[13]); hi.w = pack_bf2(v[14], v[15]);
+                __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems;
+                *reinterpret_cast<uint4*>(os) = lo;
+                *reinterpret_cast<uint4*>(os + 8) = hi;
+              }
             }
           }
         }
@@ -430,8 +463,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
 
 // wref [32][cin_ref][3][3] fp32 -> bf16 B-operand image [ky][kstep][kcore(2)][ngroup(12)][r%8][k%8], row r = kx*32 + n;
 // img_pair: the same rows split between the CTAs of a pair, [half(2)][ky][kstep][kcore(2)][ngroup(6)][r%8][k%8], half = r / 48
+// img_x2 (BF16X3 mode): the pair image with a hi and a lo tile per (ky, K-step), [half(2)][ky][kstep][hi|lo][kcore(2)][ngroup(6)][r%8][k%8],
+// hi = bf16(w), lo = bf16(w - hi)
 __global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ img_pair,
-                                int cin_ref, int cin_buf, int xreal, int xpad) {
+                                __nv_bfloat16* __restrict__ img_x2, int cin_ref, int cin_buf, int xreal, int xpad) {
   const int nks = cin_buf / 16;
   const int total = 3 * cin_buf * NB;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,6 +486,15 @@ __global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* _
   const size_t offp = half * half_elems + (size_t)(ky * nks + ks) * (WTILE_BYTES / 4) + (size_t)((kk / 8) * (NB / 16) + rh / 8) * 64 +
                       (rh % 8) * 8 + (kk % 8);
   img_pair[offp] = __float2bfloat16_rn(v);
+  if (img_x2 != nullptr) {
+    const size_t tile = (size_t)(WTILE_BYTES / 4);
+    const size_t inner = (size_t)((kk / 8) * (NB / 16) + rh / 8) * 64 + (rh % 8) * 8 + (kk % 8);
+    const size_t offx = half * (2 * half_elems) + (size_t)((ky * nks + ks) * 2) * tile + inner;
+    __nv_bfloat16 hi, lo;
+    x2_split(v, hi, lo);
+    img_x2[offx] = hi;
+    img_x2[offx + tile] = lo;
+  }
 }
 
 }  // namespace tc3
@@ -547,7 +591,8 @@ int num_sms() {
 }
 }  // namespace tc
 
-int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st) {
+int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_ref, int cin_buf, int xreal, int xpad, cudaStream_t st,
+                    bool x2) {
   SELFC_CHECK_ARG(cin_buf % 16 == 0 && cin_buf <= tc3::MAX_CIN, "conv3x3_tc: cin %d must be a multiple of 16 and <= %d", cin_buf,
                   tc3::MAX_CIN);
   const size_t bytes = (size_t)3 * (cin_buf / 16) * tc3::WTILE_BYTES;
@@ -558,10 +603,12 @@ int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_re
     SELFC_CUDA(cudaMalloc(&w.bias, tc3::NOUT * sizeof(float)));
     w.img_bytes = bytes;
   }
+  if (x2 && w.img_x2 == nullptr) SELFC_CUDA(cudaMalloc(&w.img_x2, 2 * bytes));
   w.cin_buf = cin_buf;
   const int total = 3 * cin_buf * tc3::NB;
   tc3::pack_tc3_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, reinterpret_cast<__nv_bfloat16*>(w.img),
-                                                         reinterpret_cast<__nv_bfloat16*>(w.img_pair), cin_ref, cin_buf, xreal, xpad);
+                                                         reinterpret_cast<__nv_bfloat16*>(w.img_pair),
+                                                         x2 ? reinterpret_cast<__nv_bfloat16*>(w.img_x2) : nullptr, cin_ref, cin_buf, xreal, xpad);
   SELFC_LAUNCH_CHECK("pack_tc3_kernel");
   SELFC_CUDA(cudaMemcpyAsync(w.bias, bref, tc3::NOUT * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -570,16 +617,21 @@ int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_re
 void free_tc_weights(TcConvW& w) {
   if (w.img) cudaFree(w.img);
   if (w.img_pair) cudaFree(w.img_pair);
+  if (w.img_x2) cudaFree(w.img_x2);
   if (w.bias) cudaFree(w.bias);
   w.img = nullptr;
   w.img_pair = nullptr;
+  w.img_x2 = nullptr;
   w.bias = nullptr;
   w.img_bytes = 0;
 }
 
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
-                      const TcConvW* w2, __nv_bfloat16* buf2) {
+                      const TcConvW* w2, __nv_bfloat16* buf2, bool x2) {
   SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
+  SELFC_CHECK_ARG(!x2 || (w.img_x2 != nullptr && (w2 == nullptr || w2->img_x2 != nullptr) && ((uintptr_t)buf & 63) == 0 &&
+                          (buf2 == nullptr || ((uintptr_t)buf2 & 63) == 0)),
+                  "conv3x3_tc: the (hi, lo) form needs its weight image and 64-byte aligned buffers");
   SELFC_CHECK_ARG(out_off % 16 == 0 && aligned16(buf) && slabM == (long long)N * h * wd, "conv3x3_tc: slab layout / alignment");
   const bool dual = w2 != nullptr;
   SELFC_CHECK_ARG(!dual || (w2->img != nullptr && w2->cin_buf == cin && buf2 != nullptr && aligned16(buf2) && buf2 != buf),
@@ -602,21 +654,34 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
     const char* e = getenv("SELFC_TC3_PAIR");
     pair_pref = (e && atoi(e) == 0) ? 0 : 1;
   }
-  const bool pair = pair_pref == 1 && w.img_pair != nullptr && (!dual || w2->img_pair != nullptr);
+  const bool pair = x2 || (pair_pref == 1 && w.img_pair != nullptr && (!dual || w2->img_pair != nullptr));
   const int nks = cin / 16;
   int kps = kps_pref < nks ? kps_pref : nks;
-  const int fixed = tc3::BAR_BYTES + (int)(pair ? w.img_bytes / 2 : w.img_bytes) + 1024;      // both problems' weights have the same size
-  while (kps > 1 && (227 * 1024 - fixed) / (kps * tc3::SUB_BYTES) < 3) --kps;
+  const int sub_bytes = x2 ? 2 * tc3::SUB_BYTES : tc3::SUB_BYTES;
+  // both problems' weights have the same size; x2: hi + lo images, half of each per CTA
+  const int fixed = tc3::BAR_BYTES + (int)(x2 ? w.img_bytes : (pair ? w.img_bytes / 2 : w.img_bytes)) + 1024;
+  while (kps > 1 && (227 * 1024 - fixed) / (kps * sub_bytes) < 3) --kps;
   // SELFC_TC3_P2=0: one position per TMA row (SWIZZLE_32B) instead of position pairs.  Pairs need an even width.
   static int p2_pref = -1;
   if (p2_pref < 0) {
     const char* e = getenv("SELFC_TC3_P2");
     p2_pref = (e && atoi(e) == 0) ? 0 : 1;
   }
-  const bool p2 = p2_pref == 1 && (wd % 2) == 0;
+  const bool p2 = !x2 && p2_pref == 1 && (wd % 2) == 0;
   CUtensorMap tmap, tmap2;
   CUresult r;
-  if (p2) {
+  if (x2) {
+    // rows = one position's 16 channels as [16 x hi | 16 x lo] (64 bytes)
+    const cuuint64_t gdim[5] = {32, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
+    const cuuint64_t gstr[4] = {64, (cuuint64_t)wd * 64, (cuuint64_t)h * wd * 64, (cuuint64_t)slabM * 64};
+    const cuuint32_t box[5] = {32, (cuuint32_t)tc3::WT, (cuuint32_t)tc3::HT, 1, (cuuint32_t)kps};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+      r = encode(&tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dual ? buf2 : buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (p2) {
     // rows = pairs of positions (x odd, x + 1): based one position before the buffer, W/2 + 1 pairs per image row
     const cuuint64_t gdim[5] = {32, (cuuint64_t)wd / 2 + 1, (cuuint64_t)h, (cuuint64_t)N, (cuuint64_t)nks};
     const cuuint64_t gstr[4] = {64, (cuuint64_t)wd * 32, (cuuint64_t)h * wd * 32, (cuuint64_t)slabM * 32};
@@ -644,11 +709,11 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   }
   tc3::Params p;
   memset(&p, 0, sizeof(p));
-  p.wimg = pair ? w.img_pair : w.img;
+  p.wimg = x2 ? w.img_x2 : (pair ? w.img_pair : w.img);
   p.bias = w.bias;
   p.buf = buf;
   p.nprob = dual ? 2 : 1;
-  p.wimg2 = dual ? (pair ? w2->img_pair : w2->img) : p.wimg;
+  p.wimg2 = dual ? (x2 ? w2->img_x2 : (pair ? w2->img_pair : w2->img)) : p.wimg;
   p.bias2 = dual ? w2->bias : w.bias;
   p.buf2 = dual ? buf2 : buf;
   p.slabM = slabM;
@@ -665,7 +730,7 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   if (p.ntiles == 0) return 0;
   p.rev = tc::next_direction();
   if (tc::debug_slots()) p.dbg = tc::debug_next_slot(9000000 + (dual ? 100000 : 0) + nks);
-  const int stage = kps * tc3::SUB_BYTES;
+  const int stage = kps * sub_bytes;
   int nst = (227 * 1024 - fixed) / stage;
   if (nst > tc3::NSTAGE_MAX) nst = tc3::NSTAGE_MAX;
   SELFC_CHECK_ARG(nst >= 2, "conv3x3_tc: no room for the activation pipeline (cin %d)", cin);
@@ -679,6 +744,7 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
     SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc3::conv3x3_tc3_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
   }
   const int nsm = tc::num_sms();
@@ -687,8 +753,11 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
     const int nsteps = (p.ntiles + 1) / 2;
     int npairs = p.nprob * nsteps < nsm / 2 ? p.nprob * nsteps : nsm / 2;
     if (dual && (npairs & 1)) --npairs;
-    SELFC_CUDA(tc::launch_pdl_pairs(p2 ? tc3::conv3x3_tc3_kernel<true, true> : tc3::conv3x3_tc3_kernel<true, false>, 2 * npairs,
-                                    tc3::THREADS, smem, st, tmap, tmap2, p));
+    if (x2)
+      SELFC_CUDA(tc::launch_pdl_pairs(tc3::conv3x3_tc3_kernel<true, false, true>, 2 * npairs, tc3::THREADS, smem, st, tmap, tmap2, p));
+    else
+      SELFC_CUDA(tc::launch_pdl_pairs(p2 ? tc3::conv3x3_tc3_kernel<true, true> : tc3::conv3x3_tc3_kernel<true, false>, 2 * npairs,
+                                      tc3::THREADS, smem, st, tmap, tmap2, p));
   } else {
     int grid = p.nprob * p.ntiles < nsm ? p.nprob * p.ntiles : nsm;
     if (dual && (grid & 1)) --grid;                   // CTA parity selects the problem: both halves get the same CTA count

@@ -30,8 +30,9 @@ int launch_export_down(const float* z, float* out51, uint8_t* lr_u8, float* lr_q
 int launch_export_hf(const float* z, float* hf, long long M, long long hw, cudaStream_t st);
 int launch_gaussian_down(const float* x, const float* k13, float* y, int NC, int H, int W, cudaStream_t st);
 // BF16 mode: lr [N,3,h,w] -> quad 0 of z + the X slab (16 channels) of up to three slab-planar dense buffers, one pass
+// x2: the buffers hold (hi, lo) bf16 pairs (BF16X3 mode, common.cuh): 64-byte rows [16 x hi | 16 x lo]
 int launch_lr_ingest_slab(const float* lr, float* z, __nv_bfloat16* d0, __nv_bfloat16* d1, __nv_bfloat16* d2, long long M, long long hw,
-                          cudaStream_t st);
+                          cudaStream_t st, bool x2 = false);
 template <typename T>
 int launch_nchw_to_dense(const float* x, T* dst, int pitch, long long slabM, int off, int C, int cpad, long long M, long long hw,
                          cudaStream_t st);
@@ -95,7 +96,8 @@ template <typename T>
 int launch_ga_stat(const T* x, int pitch, const float* wmap, float* partial, int nsplit, int BT, int hw, cudaStream_t st);
 // BF16 mode GlobalAgg apply: out = x + sum_t W[b,t,t'] * P[t], P = proj1(x) + bias (pixel-major [M][64] bf16)
 int launch_ga_mix(const __nv_bfloat16* P, const __nv_bfloat16* x, const float* wmat, __nv_bfloat16* outT, int outT_pitch,
-                  long long outT_slabM, float* outF, int outF_pitch, __nv_bfloat16* outAct, int B, int T, long long hw, cudaStream_t st);
+                  long long outT_slabM, float* outF, int outF_pitch, __nv_bfloat16* outAct, int B, int T, long long hw, cudaStream_t st,
+                  bool x2 = false /* BF16X3 mode: P, x, outT, outAct hold (hi, lo) pairs */);
 int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const float* p2w, const float* p2b, const float* p3w,
                       const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st);
 // params: pixel-major [M][720] fp32 (ppitch floats per pixel) or NCHW [BT,720,h,w] (params_nchw)

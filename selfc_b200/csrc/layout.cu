@@ -353,12 +353,14 @@ __global__ void nchw_to_dense_kernel(const float* __restrict__ x, int ctot, int 
   if (m >= M) return;
   const long long n = m / hw, pix = m % hw;
   for (int c = 0; c < cpad; ++c)
-    dst[dense_off(m, off + c, pitch, slabM)] = from_f<T>(c < C ? __ldg(x + (n * ctot + c0 + c) * hw + pix) : 0.f);
+    store1(dst + dense_off(m, off + c, pitch, slabM), c < C ? __ldg(x + (n * ctot + c0 + c) * hw + pix) : 0.f);
 }
 
 // LR ingest of the reverse pass in ONE coalesced pass: lr [N,3,h,w] fp32 -> quad 0 of the latent state (x1 of the
 // reversed block 8) and the 16-channel X slab (3 values + 13 zeros, two 16-byte stores) of up to three slab-planar dense
 // buffers (G, H, local_m1).  The generic per-channel kernel above took 82 us per buffer at 1080p.
+// X2 (BF16X3 mode, common.cuh): the slab row of a pixel is 64 bytes, [16 x hi | 16 x lo]
+template <bool X2>
 __global__ void __launch_bounds__(256) lr_ingest_slab_kernel(const float* __restrict__ lr, float* __restrict__ z, __nv_bfloat16* __restrict__ d0,
                                                              __nv_bfloat16* __restrict__ d1, __nv_bfloat16* __restrict__ d2, long long M,
                                                              long long hw) {
@@ -374,16 +376,25 @@ __global__ void __launch_bounds__(256) lr_ingest_slab_kernel(const float* __rest
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (dst[i] == nullptr) continue;
-    uint4* o = reinterpret_cast<uint4*>(dst[i] + m * 16);       // slab 0 of a slab-planar buffer: [M][16]
-    o[0] = lo;
-    o[1] = zero;
+    if (X2) {
+      uint4* o = reinterpret_cast<uint4*>(dst[i] + m * 32);     // slab 0: [M][16 hi | 16 lo]
+      o[0] = lo;
+      o[1] = zero;
+      o[2] = make_uint4(x2_pack_lo(a, b, lo.x), x2_pack_lo(c, 0.f, lo.y), 0u, 0u);
+      o[3] = zero;
+    } else {
+      uint4* o = reinterpret_cast<uint4*>(dst[i] + m * 16);       // slab 0 of a slab-planar buffer: [M][16]
+      o[0] = lo;
+      o[1] = zero;
+    }
   }
 }
 
 int launch_lr_ingest_slab(const float* lr, float* z, __nv_bfloat16* d0, __nv_bfloat16* d1, __nv_bfloat16* d2, long long M, long long hw,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool x2) {
   if (M == 0) return 0;
-  lr_ingest_slab_kernel<<<cdiv(M, 256), 256, 0, st>>>(lr, z, d0, d1, d2, M, hw);
+  if (x2) lr_ingest_slab_kernel<true><<<cdiv(M, 256), 256, 0, st>>>(lr, z, d0, d1, d2, M, hw);
+  else lr_ingest_slab_kernel<false><<<cdiv(M, 256), 256, 0, st>>>(lr, z, d0, d1, d2, M, hw);
   SELFC_LAUNCH_CHECK("lr_ingest_slab_kernel");
   return 0;
 }
@@ -394,7 +405,7 @@ __global__ void dense_to_nchw_kernel(const T* __restrict__ src, int pitch, long 
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const long long n = m / hw, pix = m % hw;
-  for (int c = 0; c < C; ++c) y[(n * C + c) * hw + pix] = to_f(src[dense_off(m, off + c, pitch, slabM)]);
+  for (int c = 0; c < C; ++c) y[(n * C + c) * hw + pix] = load1(src + dense_off(m, off + c, pitch, slabM));
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -458,6 +469,7 @@ int launch_fa_fwd_z_u8(const uint8_t* x, float* z, T* fbuf, int fpitch, long lon
 }
 template int launch_fa_fwd_z_u8<float>(const uint8_t*, float*, float*, int, long long, int, int, int, cudaStream_t);
 template int launch_fa_fwd_z_u8<__nv_bfloat16>(const uint8_t*, float*, __nv_bfloat16*, int, long long, int, int, int, cudaStream_t);
+template int launch_fa_fwd_z_u8<bfx2>(const uint8_t*, float*, bfx2*, int, long long, int, int, int, cudaStream_t);
 
 int launch_fa_rev_u8(const float* z, uint8_t* y, int N, int h, int w, cudaStream_t st) {
   long long M = (long long)N * h * w;
@@ -481,6 +493,7 @@ int launch_frames_to_u8(const float* x, uint8_t* img, long long N, long long HW,
 }
 template int launch_fa_fwd_z<float>(const float*, float*, float*, int, long long, int, int, int, cudaStream_t);
 template int launch_fa_fwd_z<__nv_bfloat16>(const float*, float*, __nv_bfloat16*, int, long long, int, int, int, cudaStream_t);
+template int launch_fa_fwd_z<bfx2>(const float*, float*, bfx2*, int, long long, int, int, int, cudaStream_t);
 
 int launch_fa_rev(const float* z, bool z_is_nchw, float* y, int N, int h, int w, cudaStream_t st) {
   long long M = (long long)N * h * w;
@@ -527,6 +540,8 @@ template int launch_nchw_slice_to_dense<float>(const float*, int, int, float*, i
                                                cudaStream_t);
 template int launch_nchw_slice_to_dense<__nv_bfloat16>(const float*, int, int, __nv_bfloat16*, int, long long, int, int, int, long long,
                                                        long long, cudaStream_t);
+template int launch_nchw_slice_to_dense<bfx2>(const float*, int, int, bfx2*, int, long long, int, int, int, long long, long long, cudaStream_t);
+template int launch_nchw_to_dense<bfx2>(const float*, bfx2*, int, long long, int, int, int, long long, long long, cudaStream_t);
 template int launch_nchw_to_dense<float>(const float*, float*, int, long long, int, int, int, long long, long long, cudaStream_t);
 template int launch_nchw_to_dense<__nv_bfloat16>(const float*, __nv_bfloat16*, int, long long, int, int, int, long long, long long,
                                                  cudaStream_t);
@@ -539,5 +554,6 @@ int launch_dense_to_nchw(const T* src, int pitch, long long slabM, int off, floa
 }
 template int launch_dense_to_nchw<float>(const float*, int, long long, int, float*, int, long long, long long, cudaStream_t);
 template int launch_dense_to_nchw<__nv_bfloat16>(const __nv_bfloat16*, int, long long, int, float*, int, long long, long long, cudaStream_t);
+template int launch_dense_to_nchw<bfx2>(const bfx2*, int, long long, int, float*, int, long long, long long, cudaStream_t);
 
 }  // namespace selfc

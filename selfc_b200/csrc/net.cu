@@ -61,6 +61,13 @@ static void prof_end(const selfc_ctx* cctx, cudaStream_t st) {
     if (rc_p != 0) return rc_p;        \
   } while (0)
 
+// element types of the tensor-core modes: bf16 (BF16 mode) and (hi, lo) bf16 pairs (BF16X3 mode, common.cuh)
+template <typename T> constexpr bool kTc = std::is_same<T, __nv_bfloat16>::value || std::is_same<T, bfx2>::value;
+template <typename T> constexpr bool kX2 = std::is_same<T, bfx2>::value;
+template <typename T> static __nv_bfloat16* as_bf(T* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
+template <typename T> static const __nv_bfloat16* as_bf(const T* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
+static bool mode_tc(const selfc_ctx* ctx) { return ctx->mode == SELFC_MODE_BF16 || ctx->mode == SELFC_MODE_BF16X3; }
+
 Workspace make_workspace(const selfc_ctx* ctx, int B, int T, int h, int w) {
   Workspace ws;
   const size_t M = (size_t)B * T * h * w;
@@ -127,14 +134,15 @@ static int run_dense_convs(const selfc_ctx* ctx, const DenseW& W, T* buf, int pi
   for (int k = k_first; k <= k_last; ++k) {
     const int cin = W.xpad + kGrowth * k;
     const double flops = 2.0 * (double)d.M() * 9.0 * (W.cin + kGrowth * k) * kGrowth;   // algorithmic (unpadded) FLOPs
-    if (ctx->mode == SELFC_MODE_BF16 && W.tc[k].img != nullptr) {
+    if (kTc<T> && mode_tc(ctx) && W.tc[k].img != nullptr) {
       if (W2 != nullptr && W2->tc[k].img != nullptr) {
         // two dense blocks of the same shape (G and H of a coupling) side by side: one launch per layer for both
         PROF(ctx, st, 0, 2.0 * flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), slabM, cin, /*out_off=*/cin, d.B * d.T,
-                                                        d.h, d.w, st, &W2->tc[k], reinterpret_cast<__nv_bfloat16*>(buf2)));
+                                                        d.h, d.w, st, &W2->tc[k], reinterpret_cast<__nv_bfloat16*>(buf2), kX2<T>));
         continue;
       }
-      PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), slabM, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st));
+      PROF(ctx, st, 0, flops, launch_conv3x3_tc(W.tc[k], reinterpret_cast<__nv_bfloat16*>(buf), slabM, cin, /*out_off=*/cin, d.B * d.T, d.h, d.w, st,
+                                                nullptr, nullptr, kX2<T>));
       continue;
     }
     ConvArgs<T> a;
@@ -164,17 +172,17 @@ static double conv5_flops(const DenseW& W, const Dims& d) { return 2.0 * (double
 // conv5 / GlobalAgg-apply dispatch: tcgen05 kernel in BF16 mode when T accumulators fit TMEM, fp32-FMA kernel otherwise
 template <typename T>
 static int launch_temporal(const selfc_ctx* ctx, const TcTempW& tw, const ConvArgs<T>& a, const Dims& d, cudaStream_t st) {
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (ctx->mode == SELFC_MODE_BF16 && temporal_tc_supported(tw, d.T)) {
+  if constexpr (kTc<T>) {
+    if (mode_tc(ctx) && temporal_tc_supported(tw, d.T)) {
       TcTempArgs t;
-      t.in = a.in; t.in_pitch = a.in_pitch; t.B = d.B; t.T = d.T; t.hw = (int)d.hw(); t.in_slabM = a.in_slabM;
+      t.in = as_bf(a.in); t.in_pitch = a.in_pitch; t.B = d.B; t.T = d.T; t.hw = (int)d.hw(); t.in_slabM = a.in_slabM;
       t.epi = a.epi; t.rev = a.rev; t.act = a.act;
-      t.outT = a.outT; t.outT_pitch = a.outT_pitch; t.outT_off = a.outT_off; t.outT_slabM = a.outT_slabM; t.copy_slabM = a.copy_slabM;
+      t.outT = as_bf(a.outT); t.outT_pitch = a.outT_pitch; t.outT_off = a.outT_off; t.outT_slabM = a.outT_slabM; t.copy_slabM = a.copy_slabM;
       t.outF = a.outF; t.outF_pitch = a.outF_pitch;
       t.z = a.z; t.sbuf = a.sbuf;
-      t.copyA = a.copyA; t.copyA_pitch = a.copyA_pitch; t.copyB = a.copyB; t.copyB_pitch = a.copyB_pitch; t.copy_pad = a.copy_pad;
-      t.wmat = a.wmat; t.wsum = a.wsum; t.resid = a.resid; t.resid_pitch = a.resid_pitch;
-      t.outAct = a.outAct; t.outAct_pitch = a.outAct_pitch;
+      t.copyA = as_bf(a.copyA); t.copyA_pitch = a.copyA_pitch; t.copyB = as_bf(a.copyB); t.copyB_pitch = a.copyB_pitch; t.copy_pad = a.copy_pad;
+      t.wmat = a.wmat; t.wsum = a.wsum; t.resid = as_bf(a.resid); t.resid_pitch = a.resid_pitch;
+      t.outAct = as_bf(a.outAct); t.outAct_pitch = a.outAct_pitch;
       const int rc = launch_temporal_tc(tw, t, st);
       if (rc != SELFC_E_UNSUPPORTED) return rc;      // shared memory cannot hold the frame ring: fp32-FMA kernel below
     }
@@ -232,7 +240,7 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
       const char* e = getenv("SELFC_DUAL_GH");
       dual_on = (e && atoi(e) == 0) ? 0 : 1;
     }
-    const bool dual = dual_on && ctx->mode == SELFC_MODE_BF16 && H.tc[0].img != nullptr && G.tc[0].img != nullptr;
+    const bool dual = dual_on && kTc<T> && mode_tc(ctx) && H.tc[0].img != nullptr && G.tc[0].img != nullptr;
     if (dual) SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st, 0, 3, &G, gbuf));
     else SELFC_TRY(run_dense_convs<T>(ctx, H, hbuf, ws.gpitch, d, st));
     if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -306,15 +314,16 @@ static int run_global_agg(const selfc_ctx* ctx, const GaW& g, const T* feat, T* 
   PROF(ctx, st, 2, px_bytes, launch_ga_stat<T>(feat, kStpC, wmap, partial, ws.nsplit, d.B * d.T, (int)d.hw(), st));
   PROF(ctx, st, 2, 0.0, launch_ga_weights(partial, ws.nsplit, g.fcb, g.p2w, g.p2b, g.p3w, g.p3b, wmat, wsum, d.B, d.T, st));
   if (wmat_copy) SELFC_CUDA(cudaMemcpyAsync(wmat_copy, wmat, (size_t)d.B * d.T * d.T * 4, cudaMemcpyDeviceToDevice, st));
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (ctx->mode == SELFC_MODE_BF16 && g.tp.img != nullptr) {
+  if constexpr (kTc<T>) {
+    if (mode_tc(ctx) && g.tp.img != nullptr) {
       // P = proj1(x) + bias as a tcgen05 pointwise GEMM over all M pixels (two pseudo-frames), then the T x T mix at full occupancy
       __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(wsp + ws.h1);
       TcTempArgs t;
-      t.in = feat; t.in_pitch = kStpC; t.B = 1; t.T = 2; t.hw = (int)((d.M() + 1) / 2); t.m_limit = d.M();
+      t.in = as_bf(feat); t.in_pitch = kStpC; t.B = 1; t.T = 2; t.hw = (int)((d.M() + 1) / 2); t.m_limit = d.M();
       t.epi = EPI_STORE; t.act = 0; t.outT = P; t.outT_pitch = kStpC;
       PROF(ctx, st, 2, 2.0 * px_bytes, launch_temporal_tc(g.tp, t, st));
-      PROF(ctx, st, 2, 3.0 * px_bytes, launch_ga_mix(P, feat, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch, outAct, d.B, d.T, d.hw(), st));
+      PROF(ctx, st, 2, 3.0 * px_bytes, launch_ga_mix(P, as_bf(feat), wmat, as_bf(outT), outT_pitch, outT_slabM, outF, outF_pitch, as_bf(outAct), d.B,
+                                                     d.T, d.hw(), st, kX2<T>));
       return 0;
     }
   }
@@ -364,9 +373,9 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   const long long slabM = dense_slab(ctx, d);
   // LR ingest: x1 of the reversed block 8, and the X slot of local_m1
   bool ingested = false;
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+  if constexpr (kTc<T>) {
     if (slabM != 0 && xp == 16) {
-      PROF(ctx, st, 5, (double)M * (12 + 16 + 3 * 32), launch_lr_ingest_slab(lr, z, gbuf, hbuf, stpbuf, M, hw, st));
+      PROF(ctx, st, 5, (double)M * (12 + 16 + 3 * 16 * sizeof(T)), launch_lr_ingest_slab(lr, z, as_bf(gbuf), as_bf(hbuf), as_bf(stpbuf), M, hw, st, kX2<T>));
       ingested = true;
     }
   }
@@ -391,8 +400,8 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   }
   // tail_gmm (:336-344,:379): lrelu -> 64->128 -> lrelu -> 128->256 -> lrelu -> 256->720
   bool head_done = false, sampled = false, params_are_half = false;
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (ctx->mode == SELFC_MODE_BF16 && ctx->head.t[0].img != nullptr) {
+  if constexpr (kTc<T>) {
+    if (mode_tc(ctx) && ctx->head.t[0].img != nullptr) {
       // pointwise GEMMs over all M pixels, viewed as 2 pseudo-frames of ceil(M/2) rows (two accumulators in flight)
       // The 720-channel parameter tensor between the last head GEMM and the sampler is stored as fp16 quads: the GEMM's inputs are
       // bf16 (2^-9), fp16 (2^-11) adds nothing measurable, and its write + read halve.  SELFC_GMM_FP16=0: fp32 quads (also taken when
@@ -403,7 +412,7 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
         const char* e2 = getenv("SELFC_GMM_SPLIT");
         half_on = ((e && atoi(e) == 0) || (e2 && atoi(e2) == 0)) ? 0 : 1;
       }
-      const bool params_half = half_on == 1;
+      const bool params_half = half_on == 1 && !kX2<T>;      // BF16X3 mode keeps fp32 parameters
       params_are_half = params_half;
       auto pointwise = [&](const TcTempW& w, const __nv_bfloat16* in, int in_pitch, __nv_bfloat16* outT, int outT_pitch, float* outF,
                            int outF_pitch, int outF_off, int act) -> int {
@@ -414,8 +423,8 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
         t.outF_planar = outF != nullptr ? (params_half ? 2 : 1) : 0;     // GMM parameters as planar quads (fp16 by default) for the sampler
         return launch_temporal_tc(w, t, st);
       };
-      PROF(ctx, st, 3, 2.0 * M * 64 * 128, pointwise(ctx->head.t[0], fact, kStpC, h1, 128, nullptr, 0, 0, 1));
-      PROF(ctx, st, 3, 2.0 * M * 128 * 256, pointwise(ctx->head.t[1], h1, 128, h2, 256, nullptr, 0, 0, 1));
+      PROF(ctx, st, 3, 2.0 * M * 64 * 128, pointwise(ctx->head.t[0], as_bf(fact), kStpC, as_bf(h1), 128, nullptr, 0, 0, 1));
+      PROF(ctx, st, 3, 2.0 * M * 128 * 256, pointwise(ctx->head.t[1], as_bf(h1), 128, as_bf(h2), 256, nullptr, 0, 0, 1));
       // SELFC_GMM_FUSED=1: head GEMM with the sampler fused into its epilogue, one launch per mixture component (the
       // 720-channel tensor never exists: 2.6 GB less workspace traffic at 1080p).  Parity-tested, but OFF by default: the
       // Philox / Box-Muller / exp work then runs on the GEMM's four epilogue warps per SM and is latency-bound there
@@ -425,11 +434,21 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
         const char* e = getenv("SELFC_GMM_FUSED");
         fused = (e && atoi(e) != 0) ? 1 : 0;
       }
-      if (fused && ctx->head.g[0].img != nullptr) {
+      if (kX2<T>) {
+        // (hi, lo) weights of a 256 -> 240 GEMM do not fit shared memory: one 256 -> 144 launch per mixture component (rows
+        // [logit | log-scale | mean] x 48 of component k), written into the planar parameter tensor at channels j*240 + k*48 + hf
+        for (int k = 0; k < kGmmK; ++k) {
+          TcTempArgs t;
+          t.in = as_bf(h2); t.in_pitch = 256; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
+          t.epi = EPI_STORE; t.act = 0;
+          t.outF = params; t.outF_pitch = 720; t.outF_off = kHF * k; t.outF_planar = 1; t.outF_blk = kHF; t.outF_blk_stride = 240;
+          PROF(ctx, st, 3, 2.0 * M * 256 * 144, launch_temporal_tc(ctx->head.g[k], t, st));
+        }
+      } else if (fused && ctx->head.g[0].img != nullptr) {
         // 256 -> 720 and the soft-GMM draw, one launch per mixture component: the 720-channel tensor never exists
         for (int k = 0; k < kGmmK; ++k) {
           TcTempArgs t;
-          t.in = h2; t.in_pitch = 256; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
+          t.in = as_bf(h2); t.in_pitch = 256; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
           t.epi = EPI_GMM; t.z = z;
           t.gmm_k = k; t.gmm_T = d.T; t.gmm_hw = hw; t.eps = eps; t.seed = seed; t.offset = offset;
           PROF(ctx, st, k == 0 ? 3 : 4, k == 0 ? 2.0 * M * 256 * 720 : (double)M * (720 + 48) * 4, launch_temporal_tc(ctx->head.g[k], t, st));
@@ -437,7 +456,7 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
         sampled = true;
       } else {
         for (int j = 0; j < 3; ++j)
-          PROF(ctx, st, 3, 2.0 * M * 256 * 240, pointwise(ctx->head.t[2 + j], h2, 256, nullptr, 0, params, 720, 240 * j, 0));
+          PROF(ctx, st, 3, 2.0 * M * 256 * 240, pointwise(ctx->head.t[2 + j], as_bf(h2), 256, nullptr, 0, params, 720, 240 * j, 0));
       }
       head_done = true;
     }
@@ -611,7 +630,7 @@ uint64_t selfc_launch_count(void) { return g_launches; }
 
 int selfc_ctx_create(selfc_ctx** out, int device, int mode) {
   SELFC_CHECK_ARG(out != nullptr, "selfc_ctx_create: null out");
-  SELFC_CHECK_ARG(mode == SELFC_MODE_FP32 || mode == SELFC_MODE_BF16, "selfc_ctx_create: unknown mode %d", mode);
+  SELFC_CHECK_ARG(mode == SELFC_MODE_FP32 || mode == SELFC_MODE_BF16 || mode == SELFC_MODE_BF16X3, "selfc_ctx_create: unknown mode %d", mode);
   int ndev = 0;
   SELFC_CUDA(cudaGetDeviceCount(&ndev));
   SELFC_CHECK_ARG(device >= 0 && device < ndev, "selfc_ctx_create: device %d of %d", device, ndev);
@@ -625,7 +644,7 @@ int selfc_ctx_create(selfc_ctx** out, int device, int mode) {
   SELFC_CHECK_ARG(c != nullptr, "out of host memory");
   c->device = device;
   c->mode = mode;
-  c->xpad3 = mode == SELFC_MODE_BF16 ? 16 : 4;
+  c->xpad3 = mode == SELFC_MODE_FP32 ? 4 : 16;
   *out = c;
   return 0;
 }
@@ -690,6 +709,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
   std::lock_guard<std::mutex> lock(ctx->mu);
   SELFC_CUDA(cudaSetDevice(ctx->device));
   const int xp3 = ctx->xpad3;
+  const bool x2 = ctx->mode == SELFC_MODE_BF16X3;
 
   // plan the arena
   ArenaPlan pl;
@@ -746,12 +766,12 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
       W->w[k] = fp(d.w[k]); W->b[k] = fp(d.b[k]); W->np[k] = d.np[k];
       SELFC_TRY(launch_pack_conv_simt(p[d.first + 2 * k], p[d.first + 2 * k + 1], W->w[k], W->b[k], cout, cin_ref, taps, cin_buf,
                                       d.cin, d.xpad, d.np[k], st));
-      if (ctx->mode == SELFC_MODE_BF16 && k < 4) {
-        SELFC_TRY(pack_tc_weights(W->tc[k], p[d.first + 2 * k], p[d.first + 2 * k + 1], cin_ref, cin_buf, d.cin, d.xpad, st));
+      if (mode_tc(ctx) && k < 4) {
+        SELFC_TRY(pack_tc_weights(W->tc[k], p[d.first + 2 * k], p[d.first + 2 * k + 1], cin_ref, cin_buf, d.cin, d.xpad, st, x2));
       }
-      if (ctx->mode == SELFC_MODE_BF16 && k == 4) {
-        SELFC_TRY(pack_temporal_weights(W->t5, p[d.first + 8], p[d.first + 9], d.cout, cin_ref, 3, cin_buf, d.cin, d.xpad, st));
-        if (d.cout == 3 && d.cin == d.xpad && cin_buf == 176) SELFC_TRY(pack_f5_weights(&W->f5img, p[d.first + 8], cin_buf, st));
+      if (mode_tc(ctx) && k == 4) {
+        SELFC_TRY(pack_temporal_weights(W->t5, p[d.first + 8], p[d.first + 9], d.cout, cin_ref, 3, cin_buf, d.cin, d.xpad, st, x2));
+        if (!x2 && d.cout == 3 && d.cin == d.xpad && cin_buf == 176) SELFC_TRY(pack_f5_weights(&W->f5img, p[d.first + 8], cin_buf, st));
       }
     }
   }
@@ -766,7 +786,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     SELFC_CUDA(cudaMemcpyAsync(G.fcw, p[f + 0], 1024 * 4, cudaMemcpyDeviceToDevice, st));
     SELFC_CUDA(cudaMemcpyAsync(G.fcb, p[f + 1], 4, cudaMemcpyDeviceToDevice, st));
     SELFC_TRY(launch_pack_conv_simt(p[f + 2], p[f + 3], G.p1w, G.p1b, 64, 64, 1, 64, 64, 64, 64, st));
-    if (ctx->mode == SELFC_MODE_BF16) SELFC_TRY(pack_temporal_weights(G.tp, p[f + 2], p[f + 3], 64, 64, 1, 64, 64, 64, st));
+    if (mode_tc(ctx)) SELFC_TRY(pack_temporal_weights(G.tp, p[f + 2], p[f + 3], 64, 64, 1, 64, 64, 64, st, x2));
     SELFC_CUDA(cudaMemcpyAsync(G.p2w, p[f + 4], 64 * 64 * 4, cudaMemcpyDeviceToDevice, st));
     SELFC_CUDA(cudaMemcpyAsync(G.p2b, p[f + 5], 64 * 4, cudaMemcpyDeviceToDevice, st));
     SELFC_CUDA(cudaMemcpyAsync(G.p3w, p[f + 6], 64 * 64 * 4, cudaMemcpyDeviceToDevice, st));
@@ -780,17 +800,19 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     SELFC_TRY(launch_pack_conv_simt(p[P_TAIL + 2 * j], p[P_TAIL + 2 * j + 1], ctx->head.w[j], ctx->head.b[j], cout, cin, 1, cin, cin,
                                     cin, ctx->head.np[j], st));
   }
-  if (ctx->mode == SELFC_MODE_BF16) {
-    SELFC_TRY(pack_temporal_weights(ctx->head.t[0], p[P_TAIL + 0], p[P_TAIL + 1], 128, 64, 1, 64, 64, 64, st));
-    SELFC_TRY(pack_temporal_weights(ctx->head.t[1], p[P_TAIL + 2], p[P_TAIL + 3], 256, 128, 1, 128, 128, 128, st));
+  if (mode_tc(ctx)) {
+    SELFC_TRY(pack_temporal_weights(ctx->head.t[0], p[P_TAIL + 0], p[P_TAIL + 1], 128, 64, 1, 64, 64, 64, st, x2));
+    SELFC_TRY(pack_temporal_weights(ctx->head.t[1], p[P_TAIL + 2], p[P_TAIL + 3], 256, 128, 1, 128, 128, 128, st, x2));
     float* wperm = fp(head_perm_w);
     float* bperm = fp(head_perm_b);
-    SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, false, st));
-    for (int j = 0; j < 3; ++j)
-      SELFC_TRY(pack_temporal_weights(ctx->head.t[2 + j], wperm + (size_t)240 * j * 256, bperm + 240 * j, 240, 256, 1, 256, 256, 256, st));
+    if (!x2) {      // (hi, lo) images of a 256 -> 240 GEMM would not fit shared memory: BF16X3 mode uses the per-component images
+      SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, false, st));
+      for (int j = 0; j < 3; ++j)
+        SELFC_TRY(pack_temporal_weights(ctx->head.t[2 + j], wperm + (size_t)240 * j * 256, bperm + 240 * j, 240, 256, 1, 256, 256, 256, st));
+    }
     SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, true, st));
     for (int k = 0; k < kGmmK; ++k)
-      SELFC_TRY(pack_temporal_weights(ctx->head.g[k], wperm + (size_t)144 * k * 256, bperm + 144 * k, 144, 256, 1, 256, 256, 256, st));
+      SELFC_TRY(pack_temporal_weights(ctx->head.g[k], wperm + (size_t)144 * k * 256, bperm + 144 * k, 144, 256, 1, 256, 256, 256, st, x2));
   }
   ctx->loaded = true;
   return 0;
@@ -810,6 +832,7 @@ int selfc_down(selfc_ctx* ctx, const float* hr, float* out51, uint8_t* lr_u8, fl
   cudaStream_t st = (cudaStream_t)stream;
   if (ctx->mode == SELFC_MODE_BF16)
     return down_impl<__nv_bfloat16>(ctx, hr, out51, lr_u8, lr_q, d, (char*)workspace, ws, st);
+  if (ctx->mode == SELFC_MODE_BF16X3) return down_impl<bfx2>(ctx, hr, out51, lr_u8, lr_q, d, (char*)workspace, ws, st);
   return down_impl<float>(ctx, hr, out51, lr_u8, lr_q, d, (char*)workspace, ws, st);
 }
 
@@ -822,6 +845,7 @@ int selfc_up(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, u
   cudaStream_t st = (cudaStream_t)stream;
   if (ctx->mode == SELFC_MODE_BF16)
     return up_impl<__nv_bfloat16>(ctx, lr, eps, seed, offset, hr, hf, d, (char*)workspace, ws, st);
+  if (ctx->mode == SELFC_MODE_BF16X3) return up_impl<bfx2>(ctx, lr, eps, seed, offset, hr, hf, d, (char*)workspace, ws, st);
   return up_impl<float>(ctx, lr, eps, seed, offset, hr, hf, d, (char*)workspace, ws, st);
 }
 
@@ -836,6 +860,8 @@ int selfc_down_u8(selfc_ctx* ctx, const uint8_t* hr_img, uint8_t* lr_img, float*
   float* q = lr_q ? lr_q : reinterpret_cast<float*>((char*)workspace + ws.lrq);
   if (ctx->mode == SELFC_MODE_BF16)
     SELFC_TRY(down_impl<__nv_bfloat16>(ctx, nullptr, nullptr, nullptr, q, d, (char*)workspace, ws, st, hr_img));
+  else if (ctx->mode == SELFC_MODE_BF16X3)
+    SELFC_TRY(down_impl<bfx2>(ctx, nullptr, nullptr, nullptr, q, d, (char*)workspace, ws, st, hr_img));
   else
     SELFC_TRY(down_impl<float>(ctx, nullptr, nullptr, nullptr, q, d, (char*)workspace, ws, st, hr_img));
   if (lr_img) SELFC_TRY(launch_frames_to_u8(q, lr_img, (long long)B * T, d.hw(), st));
@@ -853,6 +879,7 @@ int selfc_up_u8(selfc_ctx* ctx, const uint8_t* lr_img, const float* eps, uint64_
   SELFC_TRY(launch_frames_from_u8(lr_img, q, (long long)B * T, d.hw(), st));
   if (ctx->mode == SELFC_MODE_BF16)
     return up_impl<__nv_bfloat16>(ctx, q, eps, seed, offset, nullptr, nullptr, d, (char*)workspace, ws, st, nullptr, hr_img);
+  if (ctx->mode == SELFC_MODE_BF16X3) return up_impl<bfx2>(ctx, q, eps, seed, offset, nullptr, nullptr, d, (char*)workspace, ws, st, nullptr, hr_img);
   return up_impl<float>(ctx, q, eps, seed, offset, nullptr, nullptr, d, (char*)workspace, ws, st, nullptr, hr_img);
 }
 
@@ -866,12 +893,14 @@ int selfc_rescale_u8(selfc_ctx* ctx, const uint8_t* hr_img, const float* eps, ui
   cudaStream_t st = (cudaStream_t)stream;
   char* wsp = (char*)workspace;
   float* q = reinterpret_cast<float*>(wsp + ws.lrq);
-  const bool bf = ctx->mode == SELFC_MODE_BF16;
+  const bool bf = ctx->mode == SELFC_MODE_BF16, x3 = ctx->mode == SELFC_MODE_BF16X3;
   SELFC_TRY(bf ? down_impl<__nv_bfloat16>(ctx, nullptr, nullptr, nullptr, q, d, wsp, ws, st, hr_img)
-               : down_impl<float>(ctx, nullptr, nullptr, nullptr, q, d, wsp, ws, st, hr_img));
+               : x3 ? down_impl<bfx2>(ctx, nullptr, nullptr, nullptr, q, d, wsp, ws, st, hr_img)
+                    : down_impl<float>(ctx, nullptr, nullptr, nullptr, q, d, wsp, ws, st, hr_img));
   if (lr_img) SELFC_TRY(launch_frames_to_u8(q, lr_img, (long long)B * T, d.hw(), st));
   return bf ? up_impl<__nv_bfloat16>(ctx, q, eps, seed, offset, nullptr, nullptr, d, wsp, ws, st, nullptr, hr_out_img)
-            : up_impl<float>(ctx, q, eps, seed, offset, nullptr, nullptr, d, wsp, ws, st, nullptr, hr_out_img);
+            : x3 ? up_impl<bfx2>(ctx, q, eps, seed, offset, nullptr, nullptr, d, wsp, ws, st, nullptr, hr_out_img)
+                 : up_impl<float>(ctx, q, eps, seed, offset, nullptr, nullptr, d, wsp, ws, st, nullptr, hr_out_img);
 }
 
 int selfc_frames_from_u8(const uint8_t* img, float* x, int N, int H, int W, void* stream) {
@@ -961,6 +990,7 @@ int selfc_conv3x3(selfc_ctx* ctx, int first_param, int k, const float* x, float*
   SELFC_CHECK_ARG(W != nullptr, "conv3x3: parameter index %d is not the conv1.weight of a dense block", first_param);
   Dims d{B, T, h, w};
   if (ctx->mode == SELFC_MODE_BF16) return conv3x3_impl<__nv_bfloat16>(ctx, *W, k, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
+  if (ctx->mode == SELFC_MODE_BF16X3) return conv3x3_impl<bfx2>(ctx, *W, k, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
   return conv3x3_impl<float>(ctx, *W, k, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
 }
 
@@ -973,6 +1003,7 @@ int selfc_d2dt(selfc_ctx* ctx, int first_param, const float* x, float* y, int B,
   SELFC_CHECK_ARG(W != nullptr, "d2dt: parameter index %d is not the conv1.weight of a dense block", first_param);
   Dims d{B, T, h, w};
   if (ctx->mode == SELFC_MODE_BF16) return d2dt_impl<__nv_bfloat16>(ctx, *W, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
+  if (ctx->mode == SELFC_MODE_BF16X3) return d2dt_impl<bfx2>(ctx, *W, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
   return d2dt_impl<float>(ctx, *W, x, y, d, (char*)workspace, ws, (cudaStream_t)stream);
 }
 
@@ -988,6 +1019,7 @@ int selfc_global_agg(selfc_ctx* ctx, int first_param, const float* x, float* y, 
   SELFC_CHECK_ARG(g != nullptr, "global_agg: parameter index %d is not the fc.weight of a GlobalAgg", first_param);
   Dims d{B, T, h, w};
   if (ctx->mode == SELFC_MODE_BF16) return ga_impl<__nv_bfloat16>(ctx, *g, x, y, wmat_out, d, (char*)workspace, ws, (cudaStream_t)stream);
+  if (ctx->mode == SELFC_MODE_BF16X3) return ga_impl<bfx2>(ctx, *g, x, y, wmat_out, d, (char*)workspace, ws, (cudaStream_t)stream);
   return ga_impl<float>(ctx, *g, x, y, wmat_out, d, (char*)workspace, ws, (cudaStream_t)stream);
 }
 

@@ -98,8 +98,8 @@ struct Dims {
   long long hw() const { return (long long)h * w; }
 };
 
-// layout of the dense-block buffers (common.cuh): slab-planar in BF16 mode, pixel-major in FP32 mode
-inline long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->mode == SELFC_MODE_BF16 ? d.M() : 0; }
+// layout of the dense-block buffers (common.cuh): slab-planar in the BF16 / BF16X3 modes, pixel-major in FP32 mode
+inline long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->mode != SELFC_MODE_FP32 ? d.M() : 0; }
 
 
 // what the training step asks the reverse pass to keep (fp32, device): ga_save = 7 x [M][64] (slot i+1 <- output of

@@ -199,6 +199,37 @@ __global__ void __launch_bounds__(1024) ga_weights_kernel(const float* __restric
 // as a whole but were 205 us when done by the four epilogue warps per SM of the GEMM kernel; here they run at full
 // occupancy: one thread per (pixel, 8-channel group), 16-byte loads / stores, consecutive lanes on consecutive addresses.
 // ------------------------------------------------------------------------------------------------------
+// 8 consecutive channels of a bf16 buffer at logical element offset `off` (a multiple of 8); X2: the buffer holds (hi, lo) pairs
+// as 64-byte rows [16 x hi | 16 x lo] (BF16X3 mode, common.cuh) and the value is hi + lo
+template <bool X2>
+__device__ __forceinline__ void mix_load8(const __nv_bfloat16* base, size_t off, float* v) {
+  if constexpr (X2) {
+    x2_load8(base + x2_hi_index(off), v);
+  } else {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(base + off));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+template <bool X2>
+__device__ __forceinline__ void mix_store8(__nv_bfloat16* base, size_t off, const float* v) {
+  if constexpr (X2) {
+    x2_store8(base + x2_hi_index(off), v);
+  } else {
+    uint4 r;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(base + off) = r;
+  }
+}
+
+template <bool X2>
 __global__ void __launch_bounds__(256) ga_mix_kernel(const __nv_bfloat16* __restrict__ P, const __nv_bfloat16* __restrict__ x,
                                                      const float* __restrict__ wmat, __nv_bfloat16* __restrict__ outT, int outT_pitch,
                                                      long long outT_slabM, float* __restrict__ outF, int outF_pitch,
@@ -210,34 +241,17 @@ __global__ void __launch_bounds__(256) ga_mix_kernel(const __nv_bfloat16* __rest
   const long long n = m / hw, pix = m - n * hw;
   const int tq = (int)(n % T);
   const long long b = n / T;
-  auto unpack = [](const uint4 r, float* v) {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-      v[2 * i] = __low2float(h);
-      v[2 * i + 1] = __high2float(h);
-    }
-  };
-  auto pack = [](const float* v) {
-    uint4 r;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
-    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
-    return r;
-  };
   float acc[8];
-  unpack(__ldg(reinterpret_cast<const uint4*>(x + m * kStpC + c0)), acc);
+  mix_load8<X2>(x, (size_t)m * kStpC + c0, acc);
   const float* wm = wmat + b * T * T + tq;          // W[b][t][t' = tq]
   for (int t = 0; t < T; ++t) {
     const float wv = __ldg(wm + t * T);
     float pv[8];
-    unpack(__ldg(reinterpret_cast<const uint4*>(P + ((b * T + t) * hw + pix) * kStpC + c0)), pv);
+    mix_load8<X2>(P, (size_t)((b * T + t) * hw + pix) * kStpC + c0, pv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv, pv[j], acc[j]);
   }
-  if (outT) *reinterpret_cast<uint4*>(outT + dense_off(m, c0, outT_pitch, outT_slabM)) = pack(acc);
+  if (outT) mix_store8<X2>(outT, dense_off(m, c0, outT_pitch, outT_slabM), acc);
   if (outF) {
     float* o = outF + m * outF_pitch + c0;
     store4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(256) ga_mix_kernel(const __nv_bfloat16* __rest
   if (outAct) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = lrelu02(acc[j]);
-    *reinterpret_cast<uint4*>(outAct + m * kStpC + c0) = pack(acc);
+    mix_store8<X2>(outAct, (size_t)m * kStpC + c0, acc);
   }
 }
 
@@ -255,6 +269,7 @@ __global__ void __launch_bounds__(256) ga_mix_kernel(const __nv_bfloat16* __rest
 // 8 channels = 16-byte accesses: a warp reads 4 pixels x 128 bytes contiguously and writes 128-byte runs into each 16-channel
 // slab of the dense buffer (the 4-channel form wrote 64-byte runs: 3.7 TB/s); 2 CTAs of 256 threads per SM keep 2 x T x 16 bytes
 // per thread in flight.
+template <bool X2>
 __global__ void __launch_bounds__(256, 2) ga_mix_allframes_kernel(const __nv_bfloat16* __restrict__ P, const __nv_bfloat16* __restrict__ x,
                                                                   const float* __restrict__ wmat, __nv_bfloat16* __restrict__ outT,
                                                                   int outT_pitch, long long outT_slabM, float* __restrict__ outF,
@@ -266,50 +281,54 @@ __global__ void __launch_bounds__(256, 2) ga_mix_allframes_kernel(const __nv_bfl
   const int c0 = (int)(idx & 7) * 8;
   if (bp >= Bhw) return;
   const long long b = bp / hw, pix = bp - b * hw;
-  auto unpack = [](const uint4 r, float* v) {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-      v[2 * i] = __low2float(h);
-      v[2 * i + 1] = __high2float(h);
-    }
-  };
-  auto pack = [](const float* v) {
-    uint4 r;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
-    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
-    return r;
-  };
+  // raw 16-byte loads are kept packed until they are used (64 registers for P and x of all frames); X2 keeps P as fp32 sums of the
+  // two halves and reads x when its output frame is produced
   uint4 pr[TM], xr[TM];
+  float pf[X2 ? TM : 1][8];
 #pragma unroll
   for (int t = 0; t < TM; ++t) {
     if (t < T) {
       const long long m = (b * T + t) * hw + pix;
-      pr[t] = __ldg(reinterpret_cast<const uint4*>(P + m * kStpC + c0));
-      xr[t] = __ldg(reinterpret_cast<const uint4*>(x + m * kStpC + c0));
+      if constexpr (X2) {
+        mix_load8<true>(P, (size_t)m * kStpC + c0, pf[t]);
+      } else {
+        pr[t] = __ldg(reinterpret_cast<const uint4*>(P + m * kStpC + c0));
+        xr[t] = __ldg(reinterpret_cast<const uint4*>(x + m * kStpC + c0));
+      }
     }
   }
+  auto unpack = [](const uint4 r, float* v) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  };
   const float* wm = wmat + b * T * T;               // W[b][t][t']
 #pragma unroll
   for (int tq = 0; tq < TM; ++tq) {
     if (tq >= T) continue;
     const long long m = (b * T + tq) * hw + pix;
     float acc[8];
-    unpack(xr[tq], acc);
+    if constexpr (X2) mix_load8<true>(x, (size_t)m * kStpC + c0, acc);
+    else unpack(xr[tq], acc);
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
       if (t < T) {
         const float wv = __ldg(wm + t * T + tq);
         float pv[8];
-        unpack(pr[t], pv);
+        if constexpr (X2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pv[j] = pf[t][j];
+        } else {
+          unpack(pr[t], pv);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv, pv[j], acc[j]);
       }
     }
-    if (outT) *reinterpret_cast<uint4*>(outT + dense_off(m, c0, outT_pitch, outT_slabM)) = pack(acc);
+    if (outT) mix_store8<X2>(outT, dense_off(m, c0, outT_pitch, outT_slabM), acc);
     if (outF) {
       store4(outF + m * outF_pitch + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
       store4(outF + m * outF_pitch + c0 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
@@ -317,23 +336,29 @@ __global__ void __launch_bounds__(256, 2) ga_mix_allframes_kernel(const __nv_bfl
     if (outAct) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = lrelu02(acc[j]);
-      *reinterpret_cast<uint4*>(outAct + m * kStpC + c0) = pack(acc);
+      mix_store8<X2>(outAct, (size_t)m * kStpC + c0, acc);
     }
   }
 }
 
 int launch_ga_mix(const __nv_bfloat16* P, const __nv_bfloat16* x, const float* wmat, __nv_bfloat16* outT, int outT_pitch,
-                  long long outT_slabM, float* outF, int outF_pitch, __nv_bfloat16* outAct, int B, int T, long long hw, cudaStream_t st) {
+                  long long outT_slabM, float* outF, int outF_pitch, __nv_bfloat16* outAct, int B, int T, long long hw, cudaStream_t st,
+                  bool x2) {
   const long long M = (long long)B * T * hw;
   if (M == 0) return 0;
   SELFC_CHECK_ARG(outF == nullptr || outF_pitch % 4 == 0, "ga_mix: outF pitch");
   if (T <= 8) {
-    ga_mix_allframes_kernel<<<cdiv((long long)B * hw * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch,
-                                                                             outAct, T, hw, (long long)B * hw);
+    if (x2)
+      ga_mix_allframes_kernel<true><<<cdiv((long long)B * hw * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF,
+                                                                                     outF_pitch, outAct, T, hw, (long long)B * hw);
+    else
+      ga_mix_allframes_kernel<false><<<cdiv((long long)B * hw * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF,
+                                                                                      outF_pitch, outAct, T, hw, (long long)B * hw);
     SELFC_LAUNCH_CHECK("ga_mix_allframes_kernel");
     return 0;
   }
-  ga_mix_kernel<<<cdiv(M * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch, outAct, T, hw, M);
+  if (x2) ga_mix_kernel<true><<<cdiv(M * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch, outAct, T, hw, M);
+  else ga_mix_kernel<false><<<cdiv(M * 8, 256), 256, 0, st>>>(P, x, wmat, outT, outT_pitch, outT_slabM, outF, outF_pitch, outAct, T, hw, M);
   SELFC_LAUNCH_CHECK("ga_mix_kernel");
   return 0;
 }
@@ -594,6 +619,7 @@ int launch_ga_stat(const T* x, int pitch, const float* wmap, float* partial, int
 }
 template int launch_ga_stat<float>(const float*, int, const float*, float*, int, int, int, cudaStream_t);
 template int launch_ga_stat<__nv_bfloat16>(const __nv_bfloat16*, int, const float*, float*, int, int, int, cudaStream_t);
+template int launch_ga_stat<bfx2>(const bfx2*, int, const float*, float*, int, int, int, cudaStream_t);
 
 int launch_ga_weights(const float* partial, int nsplit, const float* fcb, const float* p2w, const float* p2b, const float* p3w,
                       const float* p3b, float* wmat, float* wsum, int B, int T, cudaStream_t st) {

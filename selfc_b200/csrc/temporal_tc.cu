@@ -57,6 +57,7 @@ struct Params {
   long long outT_slabM, copy_slabM;           // layouts of outT and of copyA / copyB (0 = pixel-major)
   float* outF;
   int outF_pitch, outF_off, outF_planar;   // outF_planar: write quads [C/4][m_limit][4] instead of [M][pitch]; 2: the quads are fp16
+  int outF_blk, outF_blk_stride;           // planar: column n -> channel outF_off + (n / blk) * stride + n % blk (blk = 0: outF_off + n)
   float* z;
   float* sbuf;
   __nv_bfloat16* copyA;
@@ -170,7 +171,10 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 
-template <int TAPS, bool GMM>
+// X2 (BF16X3 mode, common.cuh): activations and weights are (hi, lo) bf16 pairs.  16 channels of a pixel are one 64-byte row
+// [16 x hi | 16 x lo] -- a SWIZZLE_64B sub-tile row of a slab, or a quarter of a SWIZZLE_128B row of a pixel-major buffer --
+// every (tap, K-step) has a hi and a lo weight tile, and a K-step issues three MMAs per tap (hi.hi, hi.lo, lo.hi).
+template <int TAPS, bool GMM, bool X2 = false>
 __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                   const __grid_constant__ CUtensorMap tmap2, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -181,13 +185,13 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   const int KPS = p.kps;
   const int NC = p.nchunk;
   const int NACC = p.nacc;
-  const int STAGE_BYTES = KPS * MT * 32;            // KPS K-steps of [128 px][16 ch]
+  const int STAGE_BYTES = KPS * MT * (X2 ? 64 : 32);   // KPS K-steps of [128 px][16 ch]
   const uint32_t a_base = base;
   const uint32_t bar_base = base + NST * STAGE_BYTES;
   const uint32_t bias_off = NST * STAGE_BYTES + BAR_BYTES;
   const uint32_t w_base = base + bias_off + BIAS_BYTES;
   // epilogue operand staging (double buffered, each thread owns its 16-byte slots): [2][epi_quads][128 px][16 B]
-  const uint32_t epi_base = w_base + (uint32_t)p.taps * p.nks * p.nhalf * 32u * (p.nc_split < p.nchunk ? 2u : 1u);
+  const uint32_t epi_base = w_base + (uint32_t)p.taps * p.nks * p.nhalf * 32u * (p.nc_split < p.nchunk ? 2u : 1u) * (X2 ? 2u : 1u);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NST_MAX + s); };
   const uint32_t w_bar = bar_base + 8u * (2 * NST_MAX);
@@ -225,17 +229,18 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
   constexpr int taps = TAPS;
   const int nconv = p.nhalf;                          // N of one MMA (== npad unless two convs share the accumulator)
   const uint32_t wtile = (uint32_t)nconv * 32u;
+  const uint32_t wkstep = X2 ? 2u * wtile : wtile;   // bytes of weights per K-step (X2: hi tile, then lo tile)
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer: stages in (tile, frame, chunk) order =====================
-      const uint32_t wbytes = (uint32_t)taps * nks * wtile;
+      const uint32_t wbytes = (uint32_t)taps * nks * wkstep;
       const bool two = p.nc_split < NC;
       mbar_expect_tx(w_bar, two ? 2u * wbytes : wbytes);
       for (int tap = 0; tap < taps; ++tap) {
-        bulk_g2s(w_base + tap * nks * wtile, (const uint8_t*)p.wimg + (size_t)tap * nks * wtile, (uint32_t)nks * wtile, w_bar);
+        bulk_g2s(w_base + tap * nks * wkstep, (const uint8_t*)p.wimg + (size_t)tap * nks * wkstep, (uint32_t)nks * wkstep, w_bar);
         if (two)
-          bulk_g2s(w_base + wbytes + tap * nks * wtile, (const uint8_t*)p.wimg2 + (size_t)tap * nks * wtile, (uint32_t)nks * wtile, w_bar);
+          bulk_g2s(w_base + wbytes + tap * nks * wkstep, (const uint8_t*)p.wimg2 + (size_t)tap * nks * wkstep, (uint32_t)nks * wkstep, w_bar);
       }
       pdl_wait();      // weights are static; activations come from the previous kernel in the stream
       int s = 0;
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
             mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);
             if (c >= p.nc_split) tma_load_4d(a_base + s * STAGE_BYTES, &tmap2, full_bar(s), 0, p0, b * T + f, (c - p.nc_split) * KPS);
             else if (p.in_slab) tma_load_4d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), 0, p0, b * T + f, c * KPS);
-            else tma_load_3d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), c * KPS * 16, p0, b * T + f);
+            else tma_load_3d(a_base + s * STAGE_BYTES, &tmap, full_bar(s), c * KPS * (X2 ? 32 : 16), p0, b * T + f);
             if (++s == NST) { s = 0; ph ^= 1u; }
           }
         }
@@ -265,8 +270,9 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       const uint32_t idesc = umma_idesc_bf16(128, nconv);
       // pixel-major input: one SWIZZLE_128B row of 64 channels per pixel, a K step advances 32 bytes inside the row;
       // slab input: KPS sub-tiles of [128 px][16 ch] (SWIZZLE_32B, 4 KB each), a K step advances one sub-tile
-      const uint32_t hi_a = p.in_slab ? desc_hi(256, 6) : desc_hi(1024, 2);
-      const uint32_t a_kinc = p.in_slab ? (uint32_t)(MT * 32 >> 4) : 2u;
+      // X2: SWIZZLE_64B sub-tiles of 8 KB / 64 bytes per K-step inside the SWIZZLE_128B row; the lo operand is 32 bytes after the hi one
+      const uint32_t hi_a = p.in_slab ? (X2 ? desc_hi(512, 4) : desc_hi(256, 6)) : desc_hi(1024, 2);
+      const uint32_t a_kinc = p.in_slab ? (uint32_t)(MT * (X2 ? 64 : 32) >> 4) : (X2 ? 4u : 2u);
       long long w_full = 0, w_tempty = 0;
       const long long t_start = clock64();
       mbar_wait(w_bar, 0, p.err, 12);
@@ -277,8 +283,8 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
       const uint32_t amask = (uint32_t)(NACC - 1);          // NACC is 2 or 4
       const uint32_t hi_b = desc_hi(128, 0);
       const uint32_t b_lbo = ((uint32_t)nconv * 16u >> 4) << 16;
-      const uint32_t wconv = (uint32_t)taps * nks * wtile;    // bytes of one conv's weight image
-      const uint32_t wstep = wtile >> 4;                    // descriptor units per 16-channel weight tile
+      const uint32_t wconv = (uint32_t)taps * nks * wkstep;   // bytes of one conv's weight image
+      const uint32_t wstep = wkstep >> 4;                   // descriptor units per 16-channel K-step of weights
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, gbase += T) {
         // INPUT-frame-major: the tile of input frame fi feeds the outputs fi-1, fi, fi+1 (taps 2, 1, 0) back to back with
         // the same A descriptor, then is released.  Output fi-1 is complete once frame fi has been consumed.
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
             const int o = TAPS == 3 ? fi - tap + 1 : fi;                   // out[o] += W[tap] . in[o + tap - 1]
             valid[j] = o >= 0 && o < T;
             dcol[j] = tmem_base + (((uint32_t)(gbase + o)) & amask) * (uint32_t)npad;
-            bdesc0[j] = (((w_base + (uint32_t)(tap * nks) * wtile) & 0x3FFFFu) >> 4) | b_lbo;
+            bdesc0[j] = (((w_base + (uint32_t)(tap * nks) * wkstep) & 0x3FFFFu) >> 4) | b_lbo;
             // first contribution to out[o] comes from frame max(o-1, 0) (frame o for a pointwise conv)
             started[j] = TAPS == 3 ? (fi != (o > 0 ? o - 1 : 0) ? 1u : 0u) : 0u;
             if (valid[j] && !started[j]) {
@@ -314,6 +320,20 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
             const uint32_t a_lo = desc_lo(a_base + s * STAGE_BYTES, 16);
             for (int ks = 0; ks < ksn; ++ks, ++kk) {
               const uint64_t ad = desc_join(a_lo + a_kinc * (uint32_t)ks, hi_a);
+              if constexpr (X2) {
+                const uint64_t ad_lo = desc_join(a_lo + a_kinc * (uint32_t)ks + 2u, hi_a);
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+#pragma unroll
+                  for (int j = 0; j < TAPS; ++j) {
+                    if (!valid[j]) continue;
+                    umma_bf16_elect(dcol[j] + cvoff_d, term == 2 ? ad_lo : ad,
+                                    desc_join(bdesc0[j] + cvoff_b + kk * wstep + (term == 1 ? (wtile >> 4) : 0u), hi_b), idesc,
+                                    started[j] | ((kk > 0 || term > 0) ? 1u : 0u));
+                  }
+                }
+                continue;
+              }
 #pragma unroll
               for (int j = 0; j < TAPS; ++j) {
                 if (!valid[j]) continue;
@@ -467,7 +487,11 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = lrelu02(v[j]);
               }
-              if (p.outT) {
+              if (X2 && p.outT) {       // cout % 16 == 0 (checked by the launcher)
+                __nv_bfloat16* o = p.outT + x2_hi_index(dense_off((long long)m, p.outT_off + n0, p.outT_pitch, p.outT_slabM));
+                x2_store8(o, v);
+                x2_store8(o + 8, v + 8);
+              } else if (p.outT) {
                 __nv_bfloat16* o = p.outT + dense_off((long long)m, p.outT_off + n0, p.outT_pitch, p.outT_slabM);
                 if (n0 + 16 <= p.cout) {
                   store_bf16x8(o, v);
@@ -477,6 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                     if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
                 }
               }
+              const int ncol = p.outF_blk ? p.outF_off + (n0 / p.outF_blk) * p.outF_blk_stride + n0 % p.outF_blk : p.outF_off + n0;
               if (p.outF && p.outF_planar == 2) {
                 __half* oh = reinterpret_cast<__half*>(p.outF);
 #pragma unroll
@@ -485,12 +510,12 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                   uint2 pk;
                   pk.x = *reinterpret_cast<const uint32_t*>(&a);
                   pk.y = *reinterpret_cast<const uint32_t*>(&b);
-                  *reinterpret_cast<uint2*>(oh + quad_off((size_t)p.m_limit, (p.outF_off + n0 + j) / 4, m)) = pk;
+                  *reinterpret_cast<uint2*>(oh + quad_off((size_t)p.m_limit, (ncol + j) / 4, m)) = pk;
                 }
               } else if (p.outF && p.outF_planar) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
-                  store4(p.outF + quad_off((size_t)p.m_limit, (p.outF_off + n0 + j) / 4, m), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                  store4(p.outF + quad_off((size_t)p.m_limit, (ncol + j) / 4, m), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
               } else if (p.outF) {
                 float* o = p.outF + m * p.outF_pitch + p.outF_off + n0;
                 if (n0 + 16 <= p.cout && ((p.outF_pitch | p.outF_off) & 3) == 0) {
@@ -512,6 +537,19 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
               y[1] = p.rev ? x1.y - v[1] : x1.y + v[1];
               y[2] = p.rev ? x1.z - v[2] : x1.z + v[2];
               store4(zp, make_float4(y[0], y[1], y[2], 0.f));
+              if (X2) {
+                if (p.copyA) {
+                  __nv_bfloat16* o = p.copyA + x2_hi_index(dense_off((long long)m, 0, p.copyA_pitch, p.copy_slabM));
+                  x2_store8(o, y);
+                  x2_store8(o + 8, y + 8);
+                }
+                if (p.copyB) {
+                  __nv_bfloat16* o = p.copyB + x2_hi_index(dense_off((long long)m, 0, p.copyB_pitch, p.copy_slabM));
+                  x2_store8(o, y);
+                  x2_store8(o + 8, y + 8);
+                }
+                break;
+              }
               if (p.copyA) {
                 __nv_bfloat16* o = p.copyA + dense_off((long long)m, 0, p.copyA_pitch, p.copy_slabM);
                 store_bf16x8(o, y);
@@ -570,7 +608,11 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                 }
                 store4(zp + j, make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]));
               }
-              if (p.copyA) {
+              if (X2 && p.copyA) {
+                __nv_bfloat16* o = p.copyA + x2_hi_index(dense_off((long long)m, n0, p.copyA_pitch, p.copy_slabM));
+                x2_store8(o, y);
+                x2_store8(o + 8, y + 8);
+              } else if (p.copyA) {
                 __nv_bfloat16* o = p.copyA + dense_off((long long)m, n0, p.copyA_pitch, p.copy_slabM);
                 store_bf16x8(o, y);
                 store_bf16x8(o + 8, y + 8);
@@ -598,9 +640,10 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
 }
 
 // wref [cout][cin_ref][taps] fp32 -> bf16 image [tap][kstep][kcore(2)][ngroup(npad/8)][n%8][k%8]
+// x2 (BF16X3 mode): [tap][kstep][hi|lo][kcore(2)][ngroup(npad/8)][n%8][k%8], hi = bf16(w), lo = bf16(w - hi)
 __global__ void pack_temporal_kernel(const float* __restrict__ wref, const float* __restrict__ bref, __nv_bfloat16* __restrict__ img,
                                      float* __restrict__ bias, int cout, int cin_ref, int taps, int cin_buf, int xreal, int xpad,
-                                     int npad) {
+                                     int npad, int x2) {
   const int nchunk = cin_buf / 16;
   const int total = taps * cin_buf * npad;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,27 +656,36 @@ __global__ void pack_temporal_kernel(const float* __restrict__ wref, const float
   float v = 0.f;
   if (n < cout && cref >= 0 && cref < cin_ref) v = wref[((size_t)n * cin_ref + cref) * taps + tap];
   const int ks = c / 16, kk = c % 16;
-  const size_t off = (size_t)(tap * nchunk + ks) * (npad * 16) + (size_t)((kk / 8) * (npad / 8) + n / 8) * 64 + (n % 8) * 8 + (kk % 8);
+  const size_t inner = (size_t)((kk / 8) * (npad / 8) + n / 8) * 64 + (n % 8) * 8 + (kk % 8);
+  if (x2) {
+    const size_t off = (size_t)(tap * nchunk + ks) * 2 * (npad * 16) + inner;
+    __nv_bfloat16 hi, lo;
+    x2_split(v, hi, lo);
+    img[off] = hi;
+    img[off + (size_t)npad * 16] = lo;
+    return;
+  }
+  const size_t off = (size_t)(tap * nchunk + ks) * (npad * 16) + inner;
   img[off] = __float2bfloat16_rn(v);
 }
 
 }  // namespace tc5
 
 int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int cout, int cin_ref, int taps, int cin_buf, int xreal,
-                          int xpad, cudaStream_t st) {
+                          int xpad, cudaStream_t st, bool x2) {
   SELFC_CHECK_ARG(cin_buf % 16 == 0 && cout >= 1 && cout <= 256, "temporal_tc: cin %d / cout %d unsupported", cin_buf, cout);
   const int npad = (cout + 15) & ~15;
-  const size_t bytes = (size_t)taps * (cin_buf / 16) * npad * 32;
+  const size_t bytes = (size_t)taps * (cin_buf / 16) * npad * 32 * (x2 ? 2 : 1);
   if (w.img == nullptr || w.img_bytes != bytes) {
     free_temporal_weights(w);
     SELFC_CUDA(cudaMalloc(&w.img, bytes));
     SELFC_CUDA(cudaMalloc(&w.bias, 256 * sizeof(float)));
     w.img_bytes = bytes;
   }
-  w.cin_buf = cin_buf; w.npad = npad; w.taps = taps; w.cout = cout;
+  w.cin_buf = cin_buf; w.npad = npad; w.taps = taps; w.cout = cout; w.x2 = x2;
   const int total = taps * cin_buf * npad;
   tc5::pack_temporal_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, bref, reinterpret_cast<__nv_bfloat16*>(w.img), w.bias, cout, cin_ref,
-                                                              taps, cin_buf, xreal, xpad, npad);
+                                                              taps, cin_buf, xreal, xpad, npad, x2 ? 1 : 0);
   SELFC_LAUNCH_CHECK("pack_temporal_kernel");
   return 0;
 }
@@ -654,6 +706,10 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
   SELFC_CHECK_ARG(!hg || (w2 != nullptr && w2->img != nullptr && w2->cin_buf == w.cin_buf && w2->npad == w.npad && w.npad == kHF &&
                           w.taps == 3 && a.in2 != nullptr && a.in_slabM != 0 && aligned16(a.in2)),
                   "temporal_tc: the fused H+G epilogue needs two 48-output temporal convs over slab-planar buffers of the same shape");
+  const bool x2 = w.x2;
+  SELFC_CHECK_ARG(!x2 || (!hg && a.epi != EPI_GMM && a.epi != EPI_COUPLE_HG && ((uintptr_t)a.in & 63) == 0 && a.in_pitch % 16 == 0 &&
+                          (a.outT == nullptr || (w.cout % 16 == 0 && a.outT_off % 16 == 0 && a.outT_pitch % 16 == 0))),
+                  "temporal_tc: the (hi, lo) form has no fused H+G / GMM epilogue and needs 64-byte aligned rows");
   const int npad_acc = hg ? 2 * w.npad : w.npad;       // accumulator columns per output frame
   SELFC_CHECK_ARG(a.in_pitch % 8 == 0 && aligned16(a.in), "temporal_tc: input pitch/alignment");
   SELFC_CHECK_ARG(a.epi != EPI_GA, "temporal_tc: the GlobalAgg mix is a separate kernel (stp.cu: ga_mix)");
@@ -666,7 +722,7 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
   const int nks = w.cin_buf / 16;
   // K steps per ring stage: slab input -> the split of nks with the least padding (a stage is kps sub-tiles of 4 KB);
   // pixel-major input -> one SWIZZLE_128B row of 64 channels per pixel
-  int kps = 4;
+  int kps = x2 ? 2 : 4;
   if (a.in_slabM) {
     int best_waste = 1 << 30;
     for (int k = 4; k >= 2; --k) {
@@ -674,6 +730,12 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
       if (waste < best_waste) { best_waste = waste; kps = k; }
     }
     if (nks < kps) kps = nks;
+    if (x2) {
+      // (hi, lo) stages are twice as large and the weights twice as many: keep at least three ring slots
+      const int epi_q = a.epi == EPI_COUPLE_Y2 ? 2 * kSQuads : (a.epi == EPI_COUPLE_Y1 ? 1 : 0);
+      const int fixed0 = tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes + 2 * epi_q * tc5::MT * 16 + 1024;
+      while (kps > 1 && (227 * 1024 - fixed0) / (kps * tc5::MT * 64) < 3) --kps;
+    }
   }
   if (hg && nks % kps != 0) return SELFC_E_UNSUPPORTED;      // the second conv's chunks must start on a stage boundary
   const int nchunk1 = cdiv(nks, kps);
@@ -683,20 +745,24 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
   if (a.in_slabM) {
     // slab-planar dense buffer [cin/16][M][16]: box = 128 pixels of one frame x kps slabs, each slab's rows one 4 KB run
     SELFC_CHECK_ARG(a.in_slabM == (long long)BT * a.hw, "temporal_tc: slab stride %lld != B*T*hw", a.in_slabM);
-    const cuuint64_t gdim[4] = {16, (cuuint64_t)a.hw, (cuuint64_t)BT, (cuuint64_t)nks};
-    const cuuint64_t gstr[3] = {32, (cuuint64_t)a.hw * 32, (cuuint64_t)a.in_slabM * 32};
-    const cuuint32_t box[4] = {16, (cuuint32_t)tc5::MT, 1, (cuuint32_t)kps};
+    const cuuint64_t rowb = x2 ? 64 : 32;      // bytes per (pixel, slab) row; x2: [16 x hi | 16 x lo]
+    const cuuint64_t gdim[4] = {rowb / 2, (cuuint64_t)a.hw, (cuuint64_t)BT, (cuuint64_t)nks};
+    const cuuint64_t gstr[3] = {rowb, (cuuint64_t)a.hw * rowb, (cuuint64_t)a.in_slabM * rowb};
+    const cuuint32_t box[4] = {(cuuint32_t)(rowb / 2), (cuuint32_t)tc5::MT, 1, (cuuint32_t)kps};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle swz = x2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS)
       r = encode(&tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(hg ? a.in2 : a.in), gdim, gstr, box, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    const cuuint64_t gdim[3] = {(cuuint64_t)a.in_pitch, (cuuint64_t)a.hw, (cuuint64_t)BT};
-    const cuuint64_t gstr[2] = {(cuuint64_t)a.in_pitch * 2, (cuuint64_t)a.hw * a.in_pitch * 2};
+    // x2: a pixel's row is in_pitch (hi, lo) pairs = 2 * in_pitch bf16; a stage still takes 64 bf16 = 2 K-steps of [16 hi | 16 lo]
+    const int epp = x2 ? 2 * a.in_pitch : a.in_pitch;
+    const cuuint64_t gdim[3] = {(cuuint64_t)epp, (cuuint64_t)a.hw, (cuuint64_t)BT};
+    const cuuint64_t gstr[2] = {(cuuint64_t)epp * 2, (cuuint64_t)a.hw * epp * 2};
     const cuuint32_t box[3] = {64, (cuuint32_t)tc5::MT, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(a.in), gdim, gstr, box, estr,
@@ -733,6 +799,7 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
   p.outT = a.outT; p.outT_pitch = a.outT_pitch; p.outT_off = a.outT_off;
   p.outT_slabM = a.outT_slabM; p.copy_slabM = a.copy_slabM;
   p.outF = a.outF; p.outF_pitch = a.outF_pitch; p.outF_off = a.outF_off; p.outF_planar = a.outF_planar;
+  p.outF_blk = a.outF_blk; p.outF_blk_stride = a.outF_blk_stride;
   p.m_limit = a.m_limit > 0 ? a.m_limit : (long long)BT * a.hw;
   p.z = a.z; p.sbuf = a.sbuf;
   p.copyA = a.copyA; p.copyA_pitch = a.copyA_pitch; p.copyB = a.copyB; p.copyB_pitch = a.copyB_pitch; p.copy_pad = a.copy_pad;
@@ -751,7 +818,7 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
   p.zrev = tc::next_direction();
   p.epi_quads = a.epi == EPI_COUPLE_Y2 ? 2 * kSQuads : (a.epi == EPI_COUPLE_HG ? kSQuads : (a.epi == EPI_COUPLE_Y1 ? 1 : 0));
   const int fixed = tc5::BAR_BYTES + tc5::BIAS_BYTES + (int)w.img_bytes * (hg ? 2 : 1) + 2 * p.epi_quads * tc5::MT * 16 + 1024;
-  const int stage_bytes = kps * tc5::MT * 32;
+  const int stage_bytes = kps * tc5::MT * (x2 ? 64 : 32);
   int nst = (227 * 1024 - fixed) / stage_bytes;
   if (nst > tc5::NST_MAX) nst = tc5::NST_MAX;
   if (nst < 2) {
@@ -767,12 +834,16 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
     SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(tc5::temporal_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
   }
   const int nsm = tc::num_sms();
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
   SELFC_CHECK_ARG(a.epi != EPI_GMM || w.taps == 1, "temporal_tc: the GMM epilogue belongs to a pointwise conv");
-  if (w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3, false>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
+  if (x2 && w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3, false, true>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
+  else if (x2) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1, false, true>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
+  else if (w.taps == 3) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<3, false>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
   else if (a.epi == EPI_GMM) SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1, true>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
   else SELFC_CUDA(tc::launch_pdl(tc5::temporal_tc_kernel<1, false>, grid, tc5::THREADS, smem, st, tmap, tmap2, p));
   SELFC_LAUNCH_CHECK("temporal_tc_kernel");

@@ -11,7 +11,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import MODE_BF16, MODE_FP32, NUM_PARAMS
+from ._lib import MODE_BF16, MODE_BF16X3, MODE_FP32, NUM_PARAMS
 
 HF_DIM = 48
 GMM_K = 5
@@ -65,7 +65,9 @@ def parse_mode(mode) -> int:
         return MODE_FP32
     if mode in (MODE_BF16, "bf16", "bfloat16"):
         return MODE_BF16
-    raise ValueError(f"unknown selfc_b200 precision mode {mode!r} (use 'fp32' or 'bf16')")
+    if mode in (MODE_BF16X3, "bf16x3", "fp32_tc"):
+        return MODE_BF16X3
+    raise ValueError(f"unknown selfc_b200 precision mode {mode!r} (use 'fp32', 'bf16x3' or 'bf16')")
 
 
 class Engine:
