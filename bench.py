@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the SelfC-large 4x rescaling hot path (BASELINE.json: "1080p 4x rescale frames/s (down+up)").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32] [--frames F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|bf16x3|fp32] [--frames F]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One step = one synthetic UVG-shape 1080p group of F frames (default 100 = 15 GOPs of 7, the last one padded with
@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("SELFC_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default=os.environ.get("SELFC_B200_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--frames", type=int, default=100, help="frames per 1080p group (one step = one group per GPU)")
     ap.add_argument("--gops-per-launch", type=int, default=1)
     ap.add_argument("--height", type=int, default=HR_H)
@@ -326,9 +326,9 @@ def run_ours(args):
             tp = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tp):
                 break
-        if os.path.exists(tp) and (hh, ww) == (HR_H, HR_W):
+        if os.path.exists(tp) and (hh, ww) == (HR_H, HR_W) and args.mode == "bf16":
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        fused = os.environ.get("SELFC_DB_FUSED", "1") != "0"
+        fused = os.environ.get("SELFC_DB_FUSED", "1") != "0" and args.mode == "bf16"
         roofline = {"kernel": ("dense_fused_kernel: conv1..4 of a D2DTInput dense block in ONE launch (tcgen05 implicit GEMM, growth channels "
                                "kept in tensor memory; + conv3x3_tc3_kernel for conv4 of the five 64->64 STP blocks) -- all (1,3,3) "
                                "convolutions of one 7-frame GOP, down+up" if fused else
@@ -339,7 +339,10 @@ def run_ours(args):
                                   "frac": traffic / (c["ms"] / max(1, c["launches"]) / 1e3) / 1e9 / hbm,
                                   "note": "the same launches against the HBM roof: cold-cache DRAM bytes per launch (ncu) / in-stream launch time; "
                                           "fused, the class moves 0.39 of round 1's bytes and is tensor-bound"} if traffic and c["ms"] > 0 else None),
-                    "peak_source": f"of {src} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "peak_source": f"of {src} bf16_tflops_sustained (kernel timed inside a long step)" +
+                                   ("; bf16x3 mode issues three bf16 MMAs per algorithmic product, so frac <= 1/3 by construction "
+                                    "(mma_frac = 3 x frac is the tensor-pipe view)" if args.mode == "bf16x3" else ""),
+                    "mma_frac": (3.0 * ach / tf_sust) if args.mode == "bf16x3" else ach / tf_sust,
                     "algorithmic_flops_per_launch": c["work"] / max(1, c["launches"]),
                     "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches": c["launches"],
                     "share_of_step": c["ms"] / tot_ms if tot_ms else None,
@@ -366,8 +369,8 @@ def run_ours(args):
     whole_tflops = value * (h * w) * FLOP_PER_LR_PX / 1e12
     line = {"metric": metric_name(hh, ww), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(args, args.mode, weights_desc),
+            "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 ((hi, lo) bf16 pairs, three tensor-core MMAs per product, fp32 accumulate)"}.get(args.mode, "f32"),
+            "data": "synthetic", "config": workload_config(args, args.mode, weights_desc),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "algorithmic_tflops": whole_tflops, "train": train_block}
     print(json.dumps(line), flush=True)

@@ -421,6 +421,129 @@ def test_vid4_shape_bf16_mode_metrics_gate(dev):
     assert abs(p_got - p_ref) <= 0.01 and abs(s_got - s_ref) <= 1e-4
 
 
+# ------------------------------------------------------------------------------------------------ BF16X3 mode (x1: configs[1] on tensor cores)
+# The numerics-gate configuration on the tcgen05 kernels: (hi, lo) bf16 pairs, three MMAs per product, fp32 accumulation.  The
+# north star's fp32 gate applies -- HR <= 1e-3, LR exact on >= 99.99 %, clip metrics within 0.01 dB / 1e-4 -- and the tests hold it
+# to a tighter bound (measured 2.3e-5 at Vid4 size) so that a lost partial product (2^-9 ~ 2e-3 relative) cannot hide.
+HR_TOL_X3 = 2e-4
+
+
+@pytest.mark.parametrize("prefix,cin,k", [("operations.5.G", 3, 0), ("operations.2.F", 48, 0), ("operations.2.F", 48, 3),
+                                          ("operations.5.H", 3, 1), ("stp_net.local_m2", 64, 3), ("stp_net.local_m1", 3, 2)])
+@pytest.mark.parametrize("shape", [(1, 2, 13, 21), (2, 3, 40, 70), (1, 1, 1, 1), (1, 1, 9, 61)])
+def test_x3_conv3x3_vs_fp64(dev, prefix, cin, k, shape):
+    """One (1,3,3) conv through the (hi, lo) form of the tcgen05 kernel against the same conv in fp64 on the UNROUNDED operands."""
+    import torch.nn.functional as F
+    sd = so.make_state_dict(9)
+    eng = _engine(dev, sd, "bf16x3")
+    b, t, h, w = shape
+    x = torch.randn(b * t, cin + 32 * k, h, w, generator=torch.Generator().manual_seed(cin + k)) * 0.7
+    wgt, bias = sd[f"{prefix}.conv{k + 1}.weight"], sd[f"{prefix}.conv{k + 1}.bias"]
+    ref = F.leaky_relu(F.conv2d(x.double(), wgt[:, :, 0].double(), bias.double(), padding=1), 0.2).float()
+    got = eng.conv3x3(prefix, k, x.to(dev), t).cpu()
+    torch.testing.assert_close(got, ref, rtol=2e-5, atol=5e-5)
+
+
+@pytest.mark.parametrize("prefix,cin", [("operations.1.F", 48), ("operations.3.G", 3), ("stp_net.local_m2", 64), ("stp_net.local_m1", 3)])
+@pytest.mark.parametrize("t,h,w", [(1, 9, 14), (3, 13, 21), (7, 24, 40), (9, 8, 8), (16, 5, 7)])
+def test_x3_dense_block_vs_oracle(dev, prefix, cin, t, h, w):
+    sd = so.make_state_dict(5)
+    eng = _engine(dev, sd, "bf16x3")
+    b = 2
+    x = torch.randn(b * t, cin, h, w, generator=torch.Generator().manual_seed(7)) * 0.5
+    with torch.no_grad():
+        ref = so.d2dt(sd, prefix, x, t)
+    got = eng.d2dt(prefix, x.to(dev), t).cpu()
+    torch.testing.assert_close(got, ref, rtol=2e-5, atol=3e-5)
+
+
+@pytest.mark.parametrize("h,w,t", [(10, 18, 2), (45, 67, 7), (40, 52, 12)])
+def test_x3_global_agg_vs_oracle(dev, h, w, t):
+    sd = so.make_state_dict(6, gain=2.0)
+    eng = _engine(dev, sd, "bf16x3")
+    b = 2
+    x = torch.randn(b * t, 64, h, w, generator=torch.Generator().manual_seed(h))
+    with torch.no_grad():
+        ref = so.global_agg(sd, "stp_net.global_m2", x, t)
+        wref = so.global_agg_weights(sd, "stp_net.global_m2", x, t)
+    got, wmat = eng.global_agg("stp_net.global_m2", x.to(dev), t)
+    torch.testing.assert_close(wmat.cpu(), wref, rtol=0, atol=1e-5)
+    torch.testing.assert_close(got.cpu(), ref, rtol=5e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("b,t,hh,ww", [(2, 7, 96, 160), (1, 1, 20, 28), (1, 3, 36, 44), (1, 9, 16, 16), (1, 1, 4, 4), (3, 5, 8, 12), (1, 2, 484, 16),
+                                       (1, 1, 16, 1940), (1, 12, 24, 36)])
+def test_x3_mode_vs_oracle(dev, b, t, hh, ww):
+    """Whole network in BF16X3 mode on the shapes the bf16 mode is tested on (odd pixel counts, a single LR pixel, T up to 12, tall
+    and wide clips): latent and HR far inside the fp32 gate, LR codes exact but for rounding-boundary cases."""
+    sd = so.make_state_dict(0)
+    eng = _engine(dev, sd, "bf16x3")
+    x = so.make_frames(b, t, hh, ww, 77)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 5)
+    with torch.no_grad():
+        z = so.net_down(sd, x, t)
+        lr = so.quantize(z[:, :3])
+        hr_ref, hf_ref = so.net_up(sd, lr, eps, t)
+    out51, lr_u8, _ = eng.down(x.to(dev), t)
+    assert (out51.cpu() - z).abs().max().item() <= HR_TOL_X3
+    exact, within1, mx = _report_lr(f"bf16x3 {b}x{t}x{hh}x{ww}", lr_u8.cpu(), so.quantize_u8(z[:, :3]))
+    # codes that differ sit on a rounding boundary (latent within 2e-4 of it): a handful per clip, whatever its size
+    assert mx <= 1 and (exact >= 0.999 or round((1.0 - exact) * lr_u8.numel()) <= 3)
+    hr, hf = eng.up(lr.to(dev), t, eps=eps.to(dev))
+    torch.testing.assert_close(hf.cpu(), hf_ref, rtol=0, atol=5e-4)
+    assert (hr.cpu() - hr_ref).abs().max().item() <= HR_TOL_X3
+    # the Philox stream and the 8-bit interface go through the same kernels as in the other modes
+    hr_a, _ = eng.up(lr.to(dev), t, seed=3, offset=1, want_hf=False)
+    hr_b, _ = eng.up(lr.to(dev), t, seed=3, offset=1, want_hf=False)
+    assert torch.equal(hr_a, hr_b) and torch.isfinite(hr_a).all()
+
+
+def test_x3_vid4_shape_batch_vs_oracle(dev):
+    """BASELINE.json configs[1]: batched 7-frame 576x704 clips (B = 2 here, two different clips) on tensor cores against the oracle at
+    full size -- the fp32 gate (HR <= 1e-3; held to 2e-4), LR exact on >= 99.9 % and within 1 LSB everywhere, per-clip Y-PSNR /
+    Y-SSIM within 0.01 dB / 1e-4."""
+    from conftest import test_weights
+    b, t, hh, ww = 2, 7, 576, 704
+    sd, _ = test_weights(0)
+    eng = _engine(dev, sd, "bf16x3")
+    x = torch.cat([so.make_frames(1, t, hh, ww, 1234), so.make_frames(1, t, hh, ww, 4321)], 0)
+    eps = so.make_eps(b, t, hh // 4, ww // 4, 99)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        z = so.net_down(sd, x, t)
+        lr = so.quantize(z[:, :3])
+        hr_ref, _ = so.net_up(sd, lr, eps, t)
+    _, lr_u8, _ = eng.down(x.to(dev), t, want_out51=False)
+    exact, within1, mx = _report_lr("vid4 bf16x3 B=2", lr_u8.cpu(), so.quantize_u8(z[:, :3]))
+    assert mx <= 1 and exact >= 0.999
+    hr, _ = eng.up(lr.to(dev), t, eps=eps.to(dev), want_hf=False)
+    hr = hr.cpu()
+    err = (hr - hr_ref).abs().max().item()
+    print(f"[vid4 bf16x3 B=2] HR max |diff| {err:.3e}")
+    assert err <= HR_TOL_X3
+    for i in range(b):
+        sl = slice(i * t, (i + 1) * t)
+        p_got, s_got = _clip_metrics(hr[sl], x[sl])
+        p_ref, s_ref = _clip_metrics(hr_ref[sl], x[sl])
+        print(f"[vid4 bf16x3 clip {i}] Y-PSNR {p_got:.4f} dB (oracle {p_ref:.4f}), Y-SSIM {s_got:.6f} (oracle {s_ref:.6f})")
+        assert abs(p_got - p_ref) <= 0.01 and abs(s_got - s_ref) <= 1e-4
+
+
+def test_x3_1080p_gop_vs_oracle(dev, oracle_1080p):
+    """BF16X3 mode at the benchmark's size against the oracle: the fp32 gate on tensor cores."""
+    o, c = oracle_1080p, oracle_1080p["clips"][1]
+    eng = _engine(dev, o["sd"], "bf16x3")
+    _, lr_u8, _ = eng.down(c["x"].to(dev), o["t"], want_out51=False)
+    exact, within1, mx = _report_lr("1080p bf16x3", lr_u8.cpu(), c["lr_u8"])
+    assert mx <= 1 and exact >= 0.999
+    hr, _ = eng.up(c["lr"].to(dev), o["t"], eps=c["eps"].to(dev), want_hf=False)
+    err = (hr.cpu() - c["hr"]).abs().max().item()
+    p, s = _clip_metrics(hr.cpu(), c["x"])
+    print(f"[1080p bf16x3] HR max |diff| {err:.3e}; Y-PSNR {p:.4f} dB (oracle {c['metrics'][0]:.4f}), Y-SSIM {s:.6f} (oracle {c['metrics'][1]:.6f})")
+    assert err <= HR_TOL_X3
+    assert abs(p - c["metrics"][0]) <= 0.01 and abs(s - c["metrics"][1]) <= 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 conv (bf16 mode)
 def _bf16r(t):
     return t.to(torch.bfloat16).to(torch.float32)
@@ -548,7 +671,7 @@ def test_u8_frame_conversions_bit_exact(dev, golden_dir):
     assert eng.frames_to_u8(torch.zeros(0, 3, 8, 8, device=dev)).shape == (0, 8, 8, 3)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16x3"])
 def test_u8_path_equals_fp32_interface_on_converted_frames(dev, mode):
     """The fused 8-bit entry points are the fp32 entry points composed with the CPU conversions, bit for bit:
     down_u8(img) == to_u8(down(from_u8(img))), up_u8(lr_img) == to_u8(up(from_u8(lr_img))), and the one-call rescale_u8."""
