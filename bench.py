@@ -378,7 +378,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_train(dev, world: int, rank: int, steps: int, warmup: int, b: int):
+def measure_train(dev, world: int, rank: int, steps: int, warmup: int, b: int, train_mode: str = None):
     """BASELINE.json configs[3] on this rank's GPU: `steps` training steps (forward, backward, flat-gradient all-reduce, clip, Adam)
     on b synthetic Vimeo90K-shape septuplets; device-timed, max over ranks; the all-reduce alone is timed separately."""
     import torch.distributed as dist
@@ -387,9 +387,11 @@ def measure_train(dev, world: int, rank: int, steps: int, warmup: int, b: int):
     from selfc_b200.synthetic import seeded_state_dict, synthetic_net
     from selfc_b200.train import Trainer
     t, hh, ww = GOP, 256, 448
+    train_mode = train_mode or os.environ.get("SELFC_TRAIN_MODE", "bf16x3")
     net, _ = synthetic_net(train=True)
     net.load_state_dict(seeded_state_dict(net, 0), strict=True)
     net = net.to(dev)
+    net.set_precision(train_mode)
     prev_t = GlobalVar.get_Temporal_LEN()
     GlobalVar.set_Temporal_LEN(t)
     tr = Trainer(net, dev, lr=1e-4, weight_decay=1e-14, max_norm=10.0)
@@ -428,11 +430,18 @@ def measure_train(dev, world: int, rank: int, steps: int, warmup: int, b: int):
     flop = 3.0 * FLOP_PER_LR_PX * (hh // 4) * (ww // 4) * t * b * world      # training ~ 3x forward
     return {"septuplets_per_s": world * b * steps / (ms_total / 1e3), "ms_per_step": ms_total / steps, "allreduce_ms": ms_ar / steps,
             "allreduce_bytes": int(tr.total * 4), "n_gpus": world, "steps": steps, "warmup": warmup, "septuplets_per_step_per_gpu": b,
-            "dtype": "f32", "gpu_launches": int(launches), "loss": float(losses[0].item()),
+            "dtype": "f32" if train_mode == "fp32" else "bf16x3 (fp32 master weights, gradients and state)", "mode": train_mode,
+            "gpu_launches": int(launches), "loss": float(losses[0].item()),
             "algorithmic_tflops": flop * steps / (ms_total / 1e3) / 1e12,
             "what": "SelfC-large training step on synthetic 7x256x448 septuplets (BASELINE.json configs[3]): forward + recompute-based "
-                    "backward on fp32-FMA kernels, ONE NCCL all-reduce of the flat 3.37M-element gradient, clip, Adam; device-timed, "
-                    "max over ranks"}
+                    "backward (" + TRAIN_MODE_WHAT[train_mode] + "), ONE NCCL all-reduce of the flat 3.37M-element gradient, clip, Adam; "
+                    "device-timed, max over ranks"}
+
+
+TRAIN_MODE_WHAT = {
+    "fp32": "fp32-FMA kernels",
+    "bf16x3": "forward and recomputed forward on the tcgen05 kernels with (hi, lo) bf16 operands, gradients fp32",
+}
 
 
 def run_train(args):
@@ -454,9 +463,9 @@ def run_train(args):
     if rank == 0:
         line = {"metric": "training step septuplets/s (7x256x448 HR, fwd+bwd+allreduce+Adam)", "value": m["septuplets_per_s"],
                 "unit": "septuplets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"SelfC-large training step, {b} synthetic Vimeo90K-shape septuplet(s) per GPU per step, fp32 mode "
-                                       "(fp32-FMA kernels, recompute-based backward), one NCCL all-reduce of the flat 3.37M-element gradient",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": m["dtype"], "data": "synthetic",
+                "config": {"workload": f"SelfC-large training step, {b} synthetic Vimeo90K-shape septuplet(s) per GPU per step, {m['mode']} mode "
+                                       f"({TRAIN_MODE_WHAT[m['mode']]}, recompute-based backward), one NCCL all-reduce of the flat 3.37M-element gradient",
                            "septuplets_per_step_per_gpu": b, "weights": "seeded random, reference state_dict layout"},
                 "clocks": clocks, "gpu_launches": m["gpu_launches"], "loss": m["loss"], "allreduce_ms": m["allreduce_ms"],
                 "algorithmic_tflops": m["algorithmic_tflops"]}

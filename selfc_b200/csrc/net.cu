@@ -590,29 +590,42 @@ const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
   return nullptr;
 }
 
-int invblock_f32(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
-  return run_invblock<float>(ctx, blk, rev, wsp, ws, d, st);
+template <typename E>
+int invblock_fwd(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
+  return run_invblock<E>(ctx, blk, rev, wsp, ws, d, st);
 }
-int up_f32_hooked(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, const Dims& d, char* wsp,
-                  const Workspace& ws, cudaStream_t st, const TrainHooks* hooks) {
-  return up_impl<float>(ctx, lr, eps, seed, offset, hr, nullptr, d, wsp, ws, st, hooks);
+template <typename E>
+int up_hooked(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, const Dims& d, char* wsp,
+              const Workspace& ws, cudaStream_t st, const TrainHooks* hooks) {
+  return up_impl<E>(ctx, lr, eps, seed, offset, hr, nullptr, d, wsp, ws, st, hooks);
 }
-// one STP stage's dense block in FP32 mode: conv1..4 + conv5 on the buffer whose X slot is already filled -> feat [M][64]
-int stp_dense_f32(const selfc_ctx* ctx, int i, float* stpbuf, int pitch, float* feat, const Dims& d, cudaStream_t st) {
+template <typename E>
+int stp_dense(const selfc_ctx* ctx, int i, E* stpbuf, int pitch, float* feat, const Dims& d, cudaStream_t st) {
   const DenseW& W = ctx->stp[i];
-  SELFC_TRY(run_dense_convs<float>(ctx, W, stpbuf, pitch, d, st));
-  ConvArgs<float> a = conv5_args<float>(ctx, W, stpbuf, pitch, d);
+  SELFC_TRY(run_dense_convs<E>(ctx, W, stpbuf, pitch, d, st));
+  ConvArgs<E> a = conv5_args<E>(ctx, W, stpbuf, pitch, d);
   a.epi = EPI_STORE; a.act = 0; a.outF = feat; a.outF_pitch = kStpC; a.outF_off = 0;
-  return launch_conv_simt<float>(a, st);
+  return launch_temporal<E>(ctx, W.t5, a, d, st);
 }
+template <typename E>
+int dense_convs(const selfc_ctx* ctx, const DenseW& W, E* buf, int pitch, const Dims& d, cudaStream_t st) {
+  return run_dense_convs<E>(ctx, W, buf, pitch, d, st);
+}
+template int invblock_fwd<float>(const selfc_ctx*, int, bool, char*, const Workspace&, const Dims&, cudaStream_t);
+template int invblock_fwd<bfx2>(const selfc_ctx*, int, bool, char*, const Workspace&, const Dims&, cudaStream_t);
+template int up_hooked<float>(selfc_ctx*, const float*, const float*, uint64_t, uint64_t, float*, const Dims&, char*, const Workspace&, cudaStream_t,
+                              const TrainHooks*);
+template int up_hooked<bfx2>(selfc_ctx*, const float*, const float*, uint64_t, uint64_t, float*, const Dims&, char*, const Workspace&, cudaStream_t,
+                             const TrainHooks*);
+template int stp_dense<float>(const selfc_ctx*, int, float*, int, float*, const Dims&, cudaStream_t);
+template int stp_dense<bfx2>(const selfc_ctx*, int, bfx2*, int, float*, const Dims&, cudaStream_t);
+template int dense_convs<float>(const selfc_ctx*, const DenseW&, float*, int, const Dims&, cudaStream_t);
+template int dense_convs<bfx2>(const selfc_ctx*, const DenseW&, bfx2*, int, const Dims&, cudaStream_t);
 const GaW* find_ga(selfc_ctx* ctx, int first_param) {
   const int ga_first[6] = {P_GLOBAL1, P_GLOBAL2, P_OTHER + 10, P_OTHER + 28, P_OTHER + 46, P_OTHER + 64};
   for (int i = 0; i < 6; ++i)
     if (first_param == ga_first[i]) return &ctx->ga[i];
   return nullptr;
-}
-int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st) {
-  return run_dense_convs<float>(ctx, W, buf, pitch, d, st);
 }
 }  // namespace selfc
 

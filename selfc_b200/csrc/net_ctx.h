@@ -108,16 +108,21 @@ struct TrainHooks {
   float* ga_save = nullptr;
   float* z_save = nullptr;
 };
-int up_f32_hooked(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, const Dims& d, char* wsp,
-                  const Workspace& ws, cudaStream_t st, const TrainHooks* hooks);
-int stp_dense_f32(const selfc_ctx* ctx, int i, float* stpbuf, int pitch, float* feat, const Dims& d, cudaStream_t st);
-
-// fp32-mode forward pieces re-used by the training step (net.cu)
-int dense_convs_f32(const selfc_ctx* ctx, const DenseW& W, float* buf, int pitch, const Dims& d, cudaStream_t st);
+// forward pieces re-used by the training step (net.cu); E = float (FP32 mode) or bfx2 (BF16X3 mode: the same launches on the tcgen05
+// kernels, dense buffers slab-planar (hi, lo) pairs)
+template <typename E>
+int up_hooked(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, const Dims& d, char* wsp,
+              const Workspace& ws, cudaStream_t st, const TrainHooks* hooks);
+// one STP stage's dense block: conv1..4 + conv5 on the buffer whose X slot is already filled -> feat [M][64] fp32
+template <typename E>
+int stp_dense(const selfc_ctx* ctx, int i, E* stpbuf, int pitch, float* feat, const Dims& d, cudaStream_t st);
+template <typename E>
+int dense_convs(const selfc_ctx* ctx, const DenseW& W, E* buf, int pitch, const Dims& d, cudaStream_t st);
 // InvBlockExp forward / reverse on the latent state in the workspace (ws.z), leaving the F / G / H dense buffers and the
 // log-scale (ws.sbuf) behind; the X slot of the first dense block must already hold its input (x2 for F when !rev, x1 for
 // G and H when rev)
-int invblock_f32(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st);
+template <typename E>
+int invblock_fwd(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st);
 int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws);
 const DenseW* find_dense(selfc_ctx* ctx, int first_param);
 const GaW* find_ga(selfc_ctx* ctx, int first_param);

@@ -53,13 +53,15 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict
 }
 
 // g[m][off + n] *= (y[m][off + n] > 0 ? 1 : 0.2)   for n < 32  (LeakyReLU backward through the stored activation)
-__global__ void lrelu_bwd_kernel(float* __restrict__ g, const float* __restrict__ y, int pitch, int off, long long M) {
+// E: element type of the forward dense buffer y (float: pixel-major, FP32 mode; bfx2: slab-planar (hi, lo) pairs, BF16X3 mode)
+template <typename E>
+__global__ void lrelu_bwd_kernel(float* __restrict__ g, const E* __restrict__ y, int pitch, long long slabM, int off, long long M) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long m = idx >> 3;
   const int c = (int)(idx & 7) * 4;
   if (m >= M) return;
   float4 gv = load4(g + m * pitch + off + c);
-  const float4 yv = load4(y + m * pitch + off + c);
+  const float4 yv = load4(y + dense_off(m, off + c, pitch, slabM));
   gv.x *= yv.x > 0.f ? 1.f : 0.2f;
   gv.y *= yv.y > 0.f ? 1.f : 0.2f;
   gv.z *= yv.z > 0.f ? 1.f : 0.2f;
@@ -75,7 +77,8 @@ __global__ void lrelu_bwd_kernel(float* __restrict__ g, const float* __restrict_
 // pixel groups are summed through shared memory, then one atomic per element adds the CTA's partial 64 x 32 block (fp32
 // scratch in buffer-channel order).
 constexpr int WG_C = 64;
-__global__ void __launch_bounds__(256, 3) wgrad_kernel(const float* __restrict__ in, int in_pitch, int cin, const float* __restrict__ g,
+template <typename E>
+__global__ void __launch_bounds__(256, 3) wgrad_kernel(const E* __restrict__ in, int in_pitch, long long in_slabM, int cin, const float* __restrict__ g,
                                                     int g_pitch, int g_off, int cout, float* __restrict__ dw, int np, int taps,
                                                     int tap_mode, int BT, int Tn, int h, int w_) {
   __shared__ __align__(16) float As[32][WG_C + 4];     // [pixel][c]
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256, 3) wgrad_kernel(const float* __restrict__
           const int y = (int)(pix / w_), x = (int)(pix - (long long)y * w_);
           const int t = (int)(n % Tn);
           const bool ok = (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w_ && (unsigned)(t + dt) < (unsigned)Tn;
-          if (ok) ra[i] = load4(in + (m + (long long)dt * hw + dy * w_ + dx) * in_pitch + c0 + q4);
+          if (ok) ra[i] = load4(in + dense_off(m + (long long)dt * hw + dy * w_ + dx, c0 + q4, in_pitch, in_slabM));
         }
       }
     }
@@ -239,10 +242,11 @@ size_t dense_bwd_scratch_floats(const DenseW& W) {
   return wd + dw + 256;
 }
 
-int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const float* buf, int pitch, const float* gy, int gy_pitch, float* gbuf,
+template <typename E>
+int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, int pitch, const float* gy, int gy_pitch, float* gbuf,
                          float* scratch, float* const* gparams, const Dims& d, cudaStream_t st) {
-  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32, "the training step runs in FP32 mode");
   const long long M = d.M();
+  const long long slabM = dense_slab(ctx, d);         // layout of the forward buffer; gradient buffers are fp32 pixel-major
   if (M == 0) return 0;
   SELFC_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)M * pitch * sizeof(float), st));
   float* zero_bias = train_zero_bias(ctx);     // dgrad has no bias term
@@ -259,7 +263,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const float* buf
     const int g_pitch = k < 4 ? pitch : gy_pitch;
     const int g_off = k < 4 ? slot : 0;
     if (k < 4) {
-      lrelu_bwd_kernel<<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, buf, pitch, slot, M);
+      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, buf, pitch, slabM, slot, M);
       SELFC_LAUNCH_CHECK("lrelu_bwd_kernel");
     }
     float* wd = scratch;
@@ -270,7 +274,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const float* buf
       SELFC_CUDA(cudaMemsetAsync(dw, 0, dw_floats * sizeof(float), st));
       const int splits = wgrad_splits(M, (taps + 1) * cdiv(cout, 32) * cdiv(cin, WG_C));
       dim3 grid((taps + 1) * cdiv(cout, 32), cdiv(cin, WG_C), splits);
-      wgrad_kernel<<<grid, 256, 0, st>>>(buf, pitch, cin, g, g_pitch, g_off, cout, dw, W.np[k], taps, tap_mode, d.B * d.T, d.T, d.h, d.w);
+      wgrad_kernel<E><<<grid, 256, 0, st>>>(buf, pitch, slabM, cin, g, g_pitch, g_off, cout, dw, W.np[k], taps, tap_mode, d.B * d.T, d.T, d.h, d.w);
       SELFC_LAUNCH_CHECK("wgrad_kernel");
       const int cin_ref = W.cin + kGrowth * k;
       const long long total = (long long)cout * cin_ref * taps;
@@ -296,17 +300,23 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const float* buf
 
 // ====================================================================================================================
 // InvBlockExp backward (SelfC_GMM_arch_inv.py:21-33), both directions.  State and its gradient are planar quads
-// [13][M][4] (common.cuh); the block's forward is RECOMPUTED from its saved input state (invblock_f32), which leaves the
+// [13][M][4] (common.cuh); the block's forward is RECOMPUTED from its saved input state (invblock_fwd), which leaves the
 // three dense buffers and the log-scale s in the workspace.
 //   forward dir:  y1 = x1 + F(x2);  s = 2*sigmoid(H(y1))-1;  y2 = x2*e^s + G(y1)
 //   reverse dir:  s = 2*sigmoid(H(x1))-1;  y2 = (x2 - G(x1))*e^-s;  y1 = x1 - F(y2)
 // ====================================================================================================================
-__global__ void quads_to_dense_kernel(const float* __restrict__ z, int q0, int nq, float* __restrict__ dst, int pitch, int off, long long M) {
+// quads [q0, q0 + nq) of the planar state -> channels [off, off + 4 nq) of a dense buffer; channels up to off + cpad are zero-filled
+// (the 16-channel X slot of the 3-input blocks in the tensor-core modes)
+template <typename E>
+__global__ void quads_to_dense_kernel(const float* __restrict__ z, int q0, int nq, E* __restrict__ dst, int pitch, long long slabM, int off,
+                                      int cpad, long long M) {
+  const int per = cpad / 4 > nq ? cpad / 4 : nq;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * nq) return;
-  const long long m = idx / nq;
-  const int j = (int)(idx - m * nq);
-  store4(dst + m * pitch + off + 4 * j, load4(z + quad_off((size_t)M, q0 + j, (size_t)m)));
+  if (idx >= M * per) return;
+  const long long m = idx / per;
+  const int j = (int)(idx - m * per);
+  const float4 v = j < nq ? load4(z + quad_off((size_t)M, q0 + j, (size_t)m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  store4(dst + dense_off(m, off + 4 * j, pitch, slabM), v);
 }
 
 // forward dir, step 1: gyG = gy2, gyH = gy2*x2*e^s*(1-s^2)/2, gz[x2 part] = gy2*e^s
@@ -398,14 +408,17 @@ __global__ void cpl_rev_pre_kernel(float* __restrict__ gz, const float* __restri
 // zin: the block's saved input state (planar); gz: gradient w.r.t. the block's OUTPUT state on entry, w.r.t. its INPUT state
 // on return; gparams: 30 gradients (F, G, H x conv1..5 weight/bias), accumulated into.  Scratch inside the workspace: the STP
 // regions (params, h1, h2), which are idle while a coupling block runs.
+template <typename E>
 int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin, float* gz, float* const* gparams, char* wsp,
                       const Workspace& ws, const Dims& d, cudaStream_t st) {
   const long long M = d.M();
+  const long long slabM = dense_slab(ctx, d);
+  const int xp3 = ctx->xpad3;
   float* z = reinterpret_cast<float*>(wsp + ws.z);
   float* sbuf = reinterpret_cast<float*>(wsp + ws.sbuf);
-  float* fbuf = reinterpret_cast<float*>(wsp + ws.fbuf);
-  float* gbuf = reinterpret_cast<float*>(wsp + ws.gbuf);
-  float* hbuf = reinterpret_cast<float*>(wsp + ws.hbuf);
+  E* fbuf = reinterpret_cast<E*>(wsp + ws.fbuf);
+  E* gbuf = reinterpret_cast<E*>(wsp + ws.gbuf);
+  E* hbuf = reinterpret_cast<E*>(wsp + ws.hbuf);
   float* gdense = reinterpret_cast<float*>(wsp + ws.params);                 // [M][<=192] gradient of a dense buffer
   float* gyG = reinterpret_cast<float*>(wsp + ws.h2);                        // [M][48]
   float* gyH = gyG + (size_t)M * kHF;                                        // [M][48]
@@ -419,48 +432,48 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
   float* const* gF = gparams ? gparams : nullptr;
   float* const* gG = gparams ? gparams + 10 : nullptr;
   float* const* gH = gparams ? gparams + 20 : nullptr;
-  const int nb = cdiv(M, 256), nbq = cdiv(M * kSQuads, 256);
+  const int nb = cdiv(M, 256), nbq = cdiv(M * kSQuads, 256), nbx = cdiv(M * (xp3 / 4), 256);
   // recompute the block's forward from its input state
   SELFC_CUDA(cudaMemcpyAsync(z, zin, (size_t)M * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
   if (!rev) {
-    quads_to_dense_kernel<<<nbq, 256, 0, st>>>(zin, 1, kSQuads, fbuf, ws.fpitch, 0, M);
+    quads_to_dense_kernel<E><<<nbq, 256, 0, st>>>(zin, 1, kSQuads, fbuf, ws.fpitch, slabM, 0, 0, M);
     SELFC_LAUNCH_CHECK("quads_to_dense_kernel");
   } else {
-    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, gbuf, ws.gpitch, 0, M);
-    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, hbuf, ws.gpitch, 0, M);
+    quads_to_dense_kernel<E><<<nbx, 256, 0, st>>>(zin, 0, 1, gbuf, ws.gpitch, slabM, 0, xp3, M);
+    quads_to_dense_kernel<E><<<nbx, 256, 0, st>>>(zin, 0, 1, hbuf, ws.gpitch, slabM, 0, xp3, M);
     SELFC_LAUNCH_CHECK("quads_to_dense_kernel");
   }
-  SELFC_TRY(invblock_f32(ctx, blk, rev, wsp, ws, d, st));
+  SELFC_TRY(invblock_fwd<E>(ctx, blk, rev, wsp, ws, d, st));
   // the block's last epilogue has already put the NEXT block's input into an X slot (y2 into F's, or y1 into G's and H's):
   // restore this block's own inputs, which the weight gradients need
   if (!rev) {
-    quads_to_dense_kernel<<<nbq, 256, 0, st>>>(zin, 1, kSQuads, fbuf, ws.fpitch, 0, M);
+    quads_to_dense_kernel<E><<<nbq, 256, 0, st>>>(zin, 1, kSQuads, fbuf, ws.fpitch, slabM, 0, 0, M);
   } else {
-    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, gbuf, ws.gpitch, 0, M);
-    quads_to_dense_kernel<<<nb, 256, 0, st>>>(zin, 0, 1, hbuf, ws.gpitch, 0, M);
+    quads_to_dense_kernel<E><<<nbx, 256, 0, st>>>(zin, 0, 1, gbuf, ws.gpitch, slabM, 0, xp3, M);
+    quads_to_dense_kernel<E><<<nbx, 256, 0, st>>>(zin, 0, 1, hbuf, ws.gpitch, slabM, 0, xp3, M);
   }
   SELFC_LAUNCH_CHECK("quads_to_dense_kernel");
   if (!rev) {
     cpl_fwd_pre_kernel<<<nbq, 256, 0, st>>>(gz, zin, sbuf, gyG, gyH, M);
     SELFC_LAUNCH_CHECK("cpl_fwd_pre_kernel");
-    SELFC_TRY(dense_block_backward(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
+    SELFC_TRY(dense_block_backward<E>(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
     take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 1, 1.0f, M);
-    SELFC_TRY(dense_block_backward(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
+    SELFC_TRY(dense_block_backward<E>(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
     take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 0, 1.0f, M);
     cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, acc, gyF, 1.0f, M);             // gx1 = gy1 + G^T + H^T; F's output gradient = the same
     SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
-    SELFC_TRY(dense_block_backward(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
+    SELFC_TRY(dense_block_backward<E>(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
     cpl_add_hf_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, M);
     SELFC_LAUNCH_CHECK("cpl_add_hf_kernel");
   } else {
     cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, nullptr, gyF, -1.0f, M);        // y1 = x1 - F(y2): F's output gradient = -gy1
     SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
-    SELFC_TRY(dense_block_backward(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
+    SELFC_TRY(dense_block_backward<E>(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
     cpl_rev_pre_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, z, sbuf, gyG, gyH, M);
     SELFC_LAUNCH_CHECK("cpl_rev_pre_kernel");
-    SELFC_TRY(dense_block_backward(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
+    SELFC_TRY(dense_block_backward<E>(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
     take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 1, 1.0f, M);
-    SELFC_TRY(dense_block_backward(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
+    SELFC_TRY(dense_block_backward<E>(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
     take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 0, 1.0f, M);
     cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, acc, nullptr, 1.0f, M);
     SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
@@ -537,7 +550,7 @@ static int pointwise_backward(const float* wf, int cin, int np, int cout, const 
     SELFC_CUDA(cudaMemsetAsync(dw, 0, (size_t)(cin + 1) * np * sizeof(float), st));
     const int splits = wgrad_splits(M, 2 * cdiv(cout, 32) * cdiv(cin, WG_C));
     dim3 grid(2 * cdiv(cout, 32), cdiv(cin, WG_C), splits);
-    wgrad_kernel<<<grid, 256, 0, st>>>(in, in_pitch, cin, g, g_pitch, 0, cout, dw, np, 1, TAP_POINT, d.B * d.T, d.T, d.h, d.w);
+    wgrad_kernel<float><<<grid, 256, 0, st>>>(in, in_pitch, 0, cin, g, g_pitch, 0, cout, dw, np, 1, TAP_POINT, d.B * d.T, d.T, d.h, d.w);
     SELFC_LAUNCH_CHECK("wgrad_kernel");
     const long long total = (long long)cout * cin;
     wgrad_unpack_kernel<<<cdiv(total, 256), 256, 0, st>>>(dw, gw, gb, cout, cin, 1, cin, cin, cin, np);
@@ -1000,6 +1013,18 @@ __global__ void copy_cols_kernel(float* __restrict__ dst, int dpitch, int doff, 
   store4(dst + m * dpitch + doff + c, load4(src + m * spitch + soff + c));
 }
 
+// X slot of a dense buffer (either layout) <- fp32 pixel-major [M][spitch] columns [0, ncol)
+template <typename E>
+__global__ void cols_to_dense_kernel(E* __restrict__ dst, int dpitch, long long slabM, const float* __restrict__ src, int spitch, int ncol,
+                                     long long M) {
+  const int per = ncol / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * per) return;
+  const long long m = idx / per;
+  const int c = (int)(idx - m * per) * 4;
+  store4(dst + dense_off(m, c, dpitch, slabM), load4(src + m * spitch + c));
+}
+
 // losses[0..2] = (total, l_forw_fit, l_back_rec) from the accumulated sums
 __global__ void loss_finish_kernel(const float* __restrict__ acc, float* __restrict__ out, float n_lr, float n_hr) {
   const float lf = acc[0] / n_lr, lb = acc[1] / n_hr;
@@ -1008,14 +1033,16 @@ __global__ void loss_finish_kernel(const float* __restrict__ acc, float* __restr
   out[2] = lb;
 }
 
+template <typename E>
 int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset, float* const* grads,
                 float* losses, const Dims& d, char* wsp, const Workspace& ws, char* tp, const Tape& tape, cudaStream_t st) {
   const long long M = d.M(), hw = d.hw();
+  const long long slabM = dense_slab(ctx, d);
   const int BT = d.B * d.T;
   const size_t state_f = (size_t)M * kZQuads * 4;       // floats per planar state
   float* z = reinterpret_cast<float*>(wsp + ws.z);
-  float* fbuf = reinterpret_cast<float*>(wsp + ws.fbuf);
-  float* stpbuf = reinterpret_cast<float*>(wsp + ws.stpbuf);
+  E* fbuf = reinterpret_cast<E*>(wsp + ws.fbuf);
+  E* stpbuf = reinterpret_cast<E*>(wsp + ws.stpbuf);
   float* gdense = reinterpret_cast<float*>(wsp + ws.params);
   float* gz = reinterpret_cast<float*>(tp + tape.gz);
   float* zs_dn = reinterpret_cast<float*>(tp + tape.zsave);             // slots 0..7: input of forward block blk; slot 8: the output
@@ -1035,23 +1062,23 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
   SELFC_CUDA(cudaMemsetAsync(lacc, 0, 64, st));
 
   // ---- forward: downscale (states kept), quantise, upscale (states and STP stage outputs kept) ----
-  SELFC_TRY(launch_fa_fwd_z<float>(hr, z, fbuf, ws.fpitch, 0, BT, d.h, d.w, st));
+  SELFC_TRY(launch_fa_fwd_z<E>(hr, z, fbuf, ws.fpitch, slabM, BT, d.h, d.w, st));
   for (int blk = 0; blk < 8; ++blk) {
     SELFC_CUDA(cudaMemcpyAsync(zs_dn + blk * state_f, z, state_f * 4, cudaMemcpyDeviceToDevice, st));
-    SELFC_TRY(invblock_f32(ctx, blk, false, wsp, ws, d, st));
+    SELFC_TRY(invblock_fwd<E>(ctx, blk, false, wsp, ws, d, st));
   }
   SELFC_CUDA(cudaMemcpyAsync(zs_dn + 8 * state_f, z, state_f * 4, cudaMemcpyDeviceToDevice, st));
   SELFC_TRY(launch_export_down(z, nullptr, nullptr, lrq, M, hw, st));            // Quantization.forward
   TrainHooks hooks;
   hooks.ga_save = ga_save;
   hooks.z_save = zs_up;
-  SELFC_TRY(up_f32_hooked(ctx, lrq, eps, seed, offset, rec, d, wsp, ws, st, &hooks));
+  SELFC_TRY(up_hooked<E>(ctx, lrq, eps, seed, offset, rec, d, wsp, ws, st, &hooks));
 
   // ---- backward ----
   loss_back_fa_bwd_kernel<<<cdiv(M, 128), 128, 0, st>>>(hr, rec, gz, lacc, kScale / n_hr, BT, d.h, d.w);
   SELFC_LAUNCH_CHECK("loss_back_fa_bwd_kernel");
   for (int blk = 0; blk < 8; ++blk)            // the reverse pass ran blocks 7..0, so their backward runs 0..7
-    SELFC_TRY(invblock_backward(ctx, blk, true, zs_up + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
+    SELFC_TRY(invblock_backward<E>(ctx, blk, true, zs_up + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
   // gz now holds d loss / d [LR_q | v]; the HF part goes through the sampler and the GMM head into the STP
   SELFC_TRY(head_sampler_backward(ctx, ga_save + (size_t)6 * M * kStpC, eps, seed, offset, gz, gcur, grads ? grads + P_TAIL : nullptr, wsp, ws,
                                   tp, tape, d, st));
@@ -1061,14 +1088,14 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
     const DenseW& W = ctx->stp[i];
     const int pitch = W.xpad + 4 * kGrowth;
     // recompute stage i: X slot <- its input (LR for the first stage), dense block -> feat
-    if (i == 0) SELFC_TRY(launch_nchw_to_dense<float>(lrq, stpbuf, pitch, 0, 0, 3, W.xpad, M, hw, st));
+    if (i == 0) SELFC_TRY(launch_nchw_to_dense<E>(lrq, stpbuf, pitch, slabM, 0, 3, W.xpad, M, hw, st));
     else {
-      copy_cols_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(stpbuf, pitch, 0, ga_save + (size_t)i * M * kStpC, kStpC, 0, kStpC, M);
-      SELFC_LAUNCH_CHECK("copy_cols_kernel");
+      cols_to_dense_kernel<E><<<cdiv(M * 16, 256), 256, 0, st>>>(stpbuf, pitch, slabM, ga_save + (size_t)i * M * kStpC, kStpC, kStpC, M);
+      SELFC_LAUNCH_CHECK("cols_to_dense_kernel");
     }
-    SELFC_TRY(stp_dense_f32(ctx, i, stpbuf, pitch, feat, d, st));
+    SELFC_TRY(stp_dense<E>(ctx, i, stpbuf, pitch, feat, d, st));
     SELFC_TRY(ga_backward(ctx, ctx->ga[i], feat, gcur, gnext, grads ? grads + ga_first[i] : nullptr, wsp, ws, tp, tape, d, st));
-    SELFC_TRY(dense_block_backward(ctx, W, stpbuf, pitch, gnext, kStpC, gdense, scratch, grads ? grads + stp_first[i] : nullptr, d, st));
+    SELFC_TRY(dense_block_backward<E>(ctx, W, stpbuf, pitch, gnext, kStpC, gdense, scratch, grads ? grads + stp_first[i] : nullptr, d, st));
     if (i > 0) {
       copy_cols_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(gcur, kStpC, 0, gdense, pitch, 0, kStpC, M);
     } else {
@@ -1080,7 +1107,7 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
   loss_forw_kernel<<<cdiv(M, 128), 128, 0, st>>>(zs_dn + 8 * state_f, ref_l, glr, gz, lacc, kScale / n_lr, hw, M);
   SELFC_LAUNCH_CHECK("loss_forw_kernel");
   for (int blk = 7; blk >= 0; --blk)
-    SELFC_TRY(invblock_backward(ctx, blk, false, zs_dn + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
+    SELFC_TRY(invblock_backward<E>(ctx, blk, false, zs_dn + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
   if (losses) {
     loss_finish_kernel<<<1, 1, 0, st>>>(lacc, losses, n_lr, n_hr);
     SELFC_LAUNCH_CHECK("loss_finish_kernel");
@@ -1150,13 +1177,12 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
   Workspace ws;
   SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
   SELFC_CHECK_ARG(x && gy && gx, "d2dt_backward: null pointer");
-  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32, "d2dt_backward: the training step runs in FP32 mode");
+  SELFC_CHECK_ARG(ctx->mode != SELFC_MODE_BF16, "d2dt_backward: the training step runs in FP32 or BF16X3 mode");
   const DenseW* W = find_dense(ctx, first_param);
   SELFC_CHECK_ARG(W != nullptr, "d2dt_backward: parameter index %d is not the conv1.weight of a dense block", first_param);
   Dims d{B, T, h, w};
   cudaStream_t st = (cudaStream_t)stream;
   char* wsp = (char*)workspace;
-  float* buf = reinterpret_cast<float*>(wsp + ws.stpbuf);
   float* gbuf = reinterpret_cast<float*>(wsp + ws.params);           // M * 720 floats >= M * pitch
   float* gyd = reinterpret_cast<float*>(wsp + ws.h2);                // M * 256 floats
   float* scratch = train_scratch(ctx);                                  // dgrad weights + weight-gradient scratch (<= 0.9 MB)
@@ -1165,10 +1191,18 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
   SELFC_CHECK_ARG(dense_bwd_scratch_floats(*W) <= kTrainScratchFloats, "d2dt_backward: scratch size");
   const int cout4 = (W->cout + 3) & ~3;
   // recompute the forward activations, then walk the block backwards
-  SELFC_TRY(to_dense(x, buf, pitch, W->cin, W->xpad, d, st));
-  SELFC_TRY(dense_convs_f32(ctx, *W, buf, pitch, d, st));
   SELFC_TRY(to_dense(gy, gyd, cout4, W->cout, cout4, d, st));
-  SELFC_TRY(dense_block_backward(ctx, *W, buf, pitch, gyd, cout4, gbuf, scratch, gparams, d, st));
+  if (ctx->mode == SELFC_MODE_BF16X3) {
+    bfx2* buf = reinterpret_cast<bfx2*>(wsp + ws.stpbuf);
+    SELFC_TRY(launch_nchw_to_dense<bfx2>(x, buf, pitch, dense_slab(ctx, d), 0, W->cin, W->xpad, d.M(), d.hw(), st));
+    SELFC_TRY(dense_convs<bfx2>(ctx, *W, buf, pitch, d, st));
+    SELFC_TRY(dense_block_backward<bfx2>(ctx, *W, buf, pitch, gyd, cout4, gbuf, scratch, gparams, d, st));
+  } else {
+    float* buf = reinterpret_cast<float*>(wsp + ws.stpbuf);
+    SELFC_TRY(to_dense(x, buf, pitch, W->cin, W->xpad, d, st));
+    SELFC_TRY(dense_convs<float>(ctx, *W, buf, pitch, d, st));
+    SELFC_TRY(dense_block_backward<float>(ctx, *W, buf, pitch, gyd, cout4, gbuf, scratch, gparams, d, st));
+  }
   return launch_dense_to_nchw<float>(gbuf, pitch, 0, 0, gx, W->cin, d.M(), d.hw(), st);
 }
 
@@ -1181,7 +1215,7 @@ int selfc_invblock_backward(selfc_ctx* ctx, int blk, int rev, const float* z_in,
   Workspace ws;
   SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
   SELFC_CHECK_ARG(z_in && gz && blk >= 0 && blk < 8, "invblock_backward: null pointer or block index");
-  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32, "invblock_backward: the training step runs in FP32 mode");
+  SELFC_CHECK_ARG(ctx->mode != SELFC_MODE_BF16, "invblock_backward: the training step runs in FP32 or BF16X3 mode");
   Dims d{B, T, h, w};
   cudaStream_t st = (cudaStream_t)stream;
   char* wsp = (char*)workspace;
@@ -1190,7 +1224,8 @@ int selfc_invblock_backward(selfc_ctx* ctx, int blk, int rev, const float* z_in,
   float* gz_p = zin_p + (size_t)d.M() * 4 * kZQuads;
   SELFC_TRY(nchw51_to_quads(z_in, zin_p, d, st));
   SELFC_TRY(nchw51_to_quads(gz, gz_p, d, st));
-  SELFC_TRY(invblock_backward(ctx, blk, rev != 0, zin_p, gz_p, gparams, wsp, ws, d, st));
+  if (ctx->mode == SELFC_MODE_BF16X3) SELFC_TRY(invblock_backward<bfx2>(ctx, blk, rev != 0, zin_p, gz_p, gparams, wsp, ws, d, st));
+  else SELFC_TRY(invblock_backward<float>(ctx, blk, rev != 0, zin_p, gz_p, gparams, wsp, ws, d, st));
   return launch_export_down(gz_p, gz, nullptr, nullptr, d.M(), d.hw(), st);
 }
 
@@ -1208,7 +1243,7 @@ int selfc_head_sampler_backward(selfc_ctx* ctx, const float* feat, const float* 
   Workspace ws;
   SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
   SELFC_CHECK_ARG(feat && gv && gfeat && tape, "head_sampler_backward: null pointer");
-  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32, "head_sampler_backward: the training step runs in FP32 mode");
+  SELFC_CHECK_ARG(ctx->mode != SELFC_MODE_BF16, "head_sampler_backward: the training step runs in FP32 or BF16X3 mode");
   const Tape tl = make_tape(B, T, h, w);
   SELFC_CHECK_ARG(tape_bytes >= tl.total && aligned16(tape), "head_sampler_backward: tape too small (%zu < %zu)", tape_bytes, tl.total);
   Dims d{B, T, h, w};
@@ -1231,7 +1266,7 @@ int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, c
   Workspace ws;
   SELFC_TRY(check_run(ctx, B, T, 4 * h, 4 * w, workspace, workspace_bytes, &ws));
   SELFC_CHECK_ARG(x && gout && gx && tape, "global_agg_backward: null pointer");
-  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32 && T <= 16, "global_agg_backward: FP32 mode and T <= 16 only");
+  SELFC_CHECK_ARG(ctx->mode != SELFC_MODE_BF16 && T <= 16, "global_agg_backward: FP32 / BF16X3 mode and T <= 16 only");
   const GaW* g = find_ga(ctx, first_param);
   SELFC_CHECK_ARG(g != nullptr, "global_agg_backward: parameter index %d is not the fc.weight of a GlobalAgg", first_param);
   const Tape tl = make_tape(B, T, h, w);
@@ -1259,11 +1294,13 @@ int selfc_train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const
   SELFC_TRY(check_run(ctx, B, T, H, W, workspace, workspace_bytes, &ws));
   SELFC_CHECK_ARG(hr && ref_l && tape && aligned16(hr), "train_grads: null or misaligned pointer");
   SELFC_CHECK_ARG(grads == nullptr || n_grads == SELFC_NUM_PARAMS, "train_grads: expected %d gradient buffers", SELFC_NUM_PARAMS);
-  SELFC_CHECK_ARG(ctx->mode == SELFC_MODE_FP32 && T <= 16, "train_grads: FP32 mode and T <= 16 only");
+  SELFC_CHECK_ARG(ctx->mode != SELFC_MODE_BF16 && T <= 16, "train_grads: FP32 / BF16X3 mode and T <= 16 only");
   const Tape tl = make_tape(B, T, H / 4, W / 4);
   SELFC_CHECK_ARG(tape_bytes >= tl.total && aligned16(tape), "train_grads: tape too small (%zu < %zu)", tape_bytes, tl.total);
   Dims d{B, T, H / 4, W / 4};
-  return train_grads(ctx, hr, ref_l, eps, seed, offset, grads, losses, d, (char*)workspace, ws, (char*)tape, tl, (cudaStream_t)stream);
+  if (ctx->mode == SELFC_MODE_BF16X3)
+    return train_grads<bfx2>(ctx, hr, ref_l, eps, seed, offset, grads, losses, d, (char*)workspace, ws, (char*)tape, tl, (cudaStream_t)stream);
+  return train_grads<float>(ctx, hr, ref_l, eps, seed, offset, grads, losses, d, (char*)workspace, ws, (char*)tape, tl, (cudaStream_t)stream);
 }
 
 /* a13 optimiser step (SelfC_model.py:66-68,172-176): gradient clipping by global norm + Adam, on a flat gradient buffer.

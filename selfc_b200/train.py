@@ -57,8 +57,9 @@ class Trainer:
 
     def __init__(self, net, device: torch.device, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  max_norm: Optional[float] = 10.0):
-        if net.precision not in ("fp32", None):
-            raise RuntimeError("the training step runs in fp32 mode (set precision fp32)")
+        if net.precision not in ("fp32", "bf16x3", "fp32_tc", None):
+            raise RuntimeError("the training step runs in fp32 mode (fp32-FMA kernels) or in bf16x3 mode (the same arithmetic to 16 "
+                               "mantissa bits per operand on the tensor cores); plain bf16 has no backward")
         self.net, self.device = net, device
         self.engine: Engine = net._engine_for(device)
         own = dict(net.named_parameters())
