@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libselfc_b200.so")
 STAMP = os.path.join(HERE, ".libselfc_b200.stamp")
-SOURCES = ["layout.cu", "conv_simt.cu", "conv_tc3.cu", "dense_fused.cu", "temporal_tc.cu", "stp.cu", "net.cu", "train.cu", "metrics.cu"]
+SOURCES = ["layout.cu", "conv_simt.cu", "conv_tc3.cu", "dense_fused.cu", "temporal_tc.cu", "stp.cu", "net.cu", "train.cu", "wgrad_tc.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 # debugging builds only (e.g. SELFC_B200_NVCC_EXTRA="-DSELFC_TC_TIMING"); part of the digest, so switching it rebuilds

@@ -667,6 +667,7 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->train_scratch) cudaFree(ctx->train_scratch);
   if (ctx->train_zero_bias) cudaFree(ctx->train_zero_bias);
+  if (ctx->wg_planes) cudaFree(ctx->wg_planes);
   for (int b = 0; b < 8; ++b)
     for (int j = 0; j < 3; ++j)
     {

@@ -75,6 +75,11 @@ struct selfc_ctx {
   // use under `mu`, freed by selfc_ctx_destroy -- two contexts (or two trainers) on one device do not share it
   float* train_scratch = nullptr;
   float* train_zero_bias = nullptr;
+  // BF16X3 training: zero-padded pixel planes of the tensor-core weight-gradient kernel (wgrad_tc.cu), zeroed whenever the clip
+  // geometry (B, T, h, w) changes; same ownership as the scratch above
+  void* wg_planes = nullptr;
+  size_t wg_bytes = 0;
+  int wg_key[4] = {0, 0, 0, 0};
   // optional per-launch timing (bench.py's roofline leg): CUDA events around every launch, by kernel class
   bool prof_on = false;
   std::vector<ProfRec> prof;

@@ -11,7 +11,11 @@
 //   weights, accumulating into gbuf (EPI_ACCUM); wgrad is a pixel reduction (wgrad_kernel below).
 #include <string.h>
 
+#include <stdlib.h>
+#include <type_traits>
+
 #include "net_ctx.h"
+#include "wgrad_tc.h"
 
 namespace selfc {
 
@@ -24,6 +28,24 @@ static float* train_scratch(const selfc_ctx* cctx) {        // dgrad weights + w
   std::lock_guard<std::mutex> lock(ctx->mu);
   if (!ctx->train_scratch && cudaMalloc(&ctx->train_scratch, kTrainScratchFloats * sizeof(float)) != cudaSuccess) ctx->train_scratch = nullptr;
   return ctx->train_scratch;
+}
+// planes of the tensor-core weight-gradient kernel for this clip geometry (zeroed when it changes: the padding must read as zero)
+static void* train_wg_planes(const selfc_ctx* cctx, const Dims& d, const WgGeom& g, cudaStream_t st) {
+  selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t need = wg_plane_bytes(g);
+  const bool same = ctx->wg_planes != nullptr && ctx->wg_key[0] == d.B && ctx->wg_key[1] == d.T && ctx->wg_key[2] == d.h && ctx->wg_key[3] == d.w;
+  if (same) return ctx->wg_planes;
+  if (ctx->wg_bytes < need) {
+    if (ctx->wg_planes) cudaFree(ctx->wg_planes);
+    ctx->wg_planes = nullptr;
+    ctx->wg_bytes = 0;
+    if (cudaMalloc(&ctx->wg_planes, need) != cudaSuccess) return nullptr;
+    ctx->wg_bytes = need;
+  }
+  if (cudaMemsetAsync(ctx->wg_planes, 0, need, st) != cudaSuccess) return nullptr;
+  ctx->wg_key[0] = d.B; ctx->wg_key[1] = d.T; ctx->wg_key[2] = d.h; ctx->wg_key[3] = d.w;
+  return ctx->wg_planes;
 }
 static float* train_zero_bias(const selfc_ctx* cctx) {      // dgrad has no bias term: 1024 zeros
   selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
@@ -248,6 +270,25 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
   const long long M = d.M();
   const long long slabM = dense_slab(ctx, d);         // layout of the forward buffer; gradient buffers are fp32 pixel-major
   if (M == 0) return 0;
+  // BF16X3 mode: weight gradients on the tensor cores (wgrad_tc.cu) from transposed, zero-padded planes of the block's activations,
+  // built once for all five convolutions.  SELFC_WGRAD_TC=0: the fp32-FMA pixel reduction below (A/B, parity).
+  bool wg_tc = false;
+  WgGeom geom{};
+  void* planes = nullptr;
+  if constexpr (std::is_same<E, bfx2>::value) {
+    static int tc_on = -1;
+    if (tc_on < 0) {
+      const char* e = getenv("SELFC_WGRAD_TC");
+      tc_on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (tc_on && gparams != nullptr) {
+      geom = wg_geometry(d);
+      planes = train_wg_planes(ctx, d, geom, st);
+      SELFC_CHECK_ARG(planes != nullptr, "out of device memory (weight-gradient planes, %zu bytes)", wg_plane_bytes(geom));
+      SELFC_TRY(launch_wg_planes_act(buf, pitch, d, geom, planes, st));
+      wg_tc = true;
+    }
+  }
   SELFC_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)M * pitch * sizeof(float), st));
   float* zero_bias = train_zero_bias(ctx);     // dgrad has no bias term
   SELFC_CHECK_ARG(zero_bias != nullptr, "out of device memory (training scratch)");
@@ -272,10 +313,16 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
     if (gparams != nullptr && gparams[2 * k] != nullptr) {
       const size_t dw_floats = (size_t)(taps * cin + 1) * W.np[k];
       SELFC_CUDA(cudaMemsetAsync(dw, 0, dw_floats * sizeof(float), st));
-      const int splits = wgrad_splits(M, (taps + 1) * cdiv(cout, 32) * cdiv(cin, WG_C));
-      dim3 grid((taps + 1) * cdiv(cout, 32), cdiv(cin, WG_C), splits);
-      wgrad_kernel<E><<<grid, 256, 0, st>>>(buf, pitch, slabM, cin, g, g_pitch, g_off, cout, dw, W.np[k], taps, tap_mode, d.B * d.T, d.T, d.h, d.w);
-      SELFC_LAUNCH_CHECK("wgrad_kernel");
+      if (wg_tc) {
+        const int nb = k < 4 ? kGrowth : (cout + 15) & ~15;
+        SELFC_TRY(launch_wg_planes_grad(g, g_pitch, g_off, cout, nb, k == 4, d, geom, planes, st));
+        SELFC_TRY(launch_wgrad_tc(planes, geom, cin, cout, nb, taps, k == 4, dw, W.np[k], st));
+      } else {
+        const int splits = wgrad_splits(M, (taps + 1) * cdiv(cout, 32) * cdiv(cin, WG_C));
+        dim3 grid((taps + 1) * cdiv(cout, 32), cdiv(cin, WG_C), splits);
+        wgrad_kernel<E><<<grid, 256, 0, st>>>(buf, pitch, slabM, cin, g, g_pitch, g_off, cout, dw, W.np[k], taps, tap_mode, d.B * d.T, d.T, d.h, d.w);
+        SELFC_LAUNCH_CHECK("wgrad_kernel");
+      }
       const int cin_ref = W.cin + kGrowth * k;
       const long long total = (long long)cout * cin_ref * taps;
       wgrad_unpack_kernel<<<cdiv(total > cout ? total : cout, 256), 256, 0, st>>>(dw, gparams[2 * k], gparams[2 * k + 1], cout, cin_ref, taps, cin,

@@ -1,0 +1,341 @@
+// Weight gradients of the dense-block convolutions on the tensor cores (training step, BF16X3 mode; SURVEY row a13:
+// models/SelfC_model.py:148-183 -- what autograd's conv3d weight-gradient kernels compute for Subnet_constructor.py:102-106).
+//
+//   dW[tap][c][n] = sum over pixels p of  in[p + shift(tap)][c] * g[p][n]        (zero outside the frame / the clip)
+//
+// is a GEMM with the PIXELS as the contraction dimension.  Both operands are first transposed into zero-padded pixel PLANES
+//   AT[row][P]   row 0 = 1 at every real pixel (its products are the bias gradient), row 1 + c = activation channel c
+//   GT[n][P]     the (LeakyReLU-masked) output gradient
+// as (hi, lo) bf16 pairs, P = ((f' * (h+2) + y+1) * Wp + x+1) with one zero row above and below every frame, zero columns up to
+// Wp = roundup(w + 2, 8) and one zero frame before every clip and after the last one.  In these planes EVERY tap is a plain offset
+// of the pixel index -- (ky-1) * Wp + (kx-1) for a spatial tap, (dt-1) * (h+2) * Wp for a temporal one -- and every out-of-frame /
+// out-of-clip neighbour is a stored zero, so a tap's partial sum is one K-major GEMM over a range of P with the A operand loaded
+// at a shifted coordinate (TMA, out-of-range coordinates zero-filled):
+//   D[sh][row][kx * 32 + n] += sum_P AT[row][P + (sh-1) * sh_stride] * GT_kx[n][P],  GT_kx[n][P] = g[n][P - (kx-1)]
+// (spatial: sh = ky, and the three kx taps are stacked in N as three copies of the gradient plane written one pixel apart: a TMA
+// box must start on a 16-byte boundary of its innermost dimension, so the one-pixel shifts cannot be load coordinates; the row
+// shifts are multiples of Wp = 8 k pixels and can).
+// M = 128 rows, N = 96 (3 x 32) / the padded output count of conv5, K = 16 pixels per MMA, three MMAs per product (hi.hi, hi.lo,
+// lo.hi), fp32 accumulation in tensor memory over the CTA's share of the pixels (split-K), then one vector reduction (red.v4.f32)
+// per four weights into the fp32 scratch the existing unpack kernel reads.
+#include <cuda.h>
+#include <string.h>
+
+#include "net_ctx.h"
+#include "tc_ptx.cuh"
+#include "wgrad_tc.h"
+
+namespace selfc {
+namespace wg {
+
+using namespace tc;
+
+constexpr int KT = 32;                  // pixels per pipeline stage: one 64-byte row of bf16 per operand row (SWIZZLE_64B)
+constexpr int ROWS = 128;               // AT rows per CTA (MMA M)
+constexpr int A_TILE = ROWS * KT * 2;   // 8 KB
+constexpr int THREADS = 192;
+constexpr int NST_MAX = 4;
+constexpr int BAR_BYTES = 256;
+
+struct Params {
+  int nsh, nkx, nb, N;                  // A shifts (3), kx blocks stacked in N (3 or 1), rows per block, N = nkx * nb
+  long long sh_stride;                  // P offset between consecutive A shifts (Wp: ky taps; (h+2) * Wp: temporal taps)
+  int ktiles, nsplit, mtiles, nst;
+  int cin, np, taps;                    // scratch layout dw[(tap * cin + c) * np + n], bias at dw[taps * cin * np + n]
+  int ncols;                            // real output channels (n < ncols)
+  int g_row0;                           // first GT row of this launch (0: the three shifted copies; kWgSpatialRows: conv5's rows)
+  float* dw;
+  int tmem_cols;
+  int* err;
+};
+
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                               const __grid_constant__ CUtensorMap tmap_g, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const int NST = p.nst;
+  const int a_bytes = p.nsh * 2 * A_TILE;                 // [shift][hi|lo] tiles of 128 rows x 64 bytes
+  const int b_half = p.N * KT * 2;                        // hi (then lo) block of N rows x 64 bytes
+  const int stage_bytes = a_bytes + 2 * b_half;           // multiple of 1024: N is a multiple of 16
+  const uint32_t bar_base = base + NST * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NST_MAX + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * NST_MAX);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NST_MAX + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + NST * stage_bytes + 8 * (2 * NST_MAX + 1));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int mt = (int)blockIdx.x % p.mtiles;
+  const int split = (int)blockIdx.x / p.mtiles;
+  const int per = (p.ktiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = split * per, k1 = min(p.ktiles, k0 + per);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NST_MAX; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (k0 < k1) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===================== TMA producer =====================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kt = k0; kt < k1; ++kt) {
+          mbar_wait(empty_bar(s), ph ^ 1u, p.err, 41);
+          mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+          const uint32_t st_a = base + s * stage_bytes, st_b = st_a + a_bytes;
+          const int P0 = kt * KT;
+          for (int sh = 0; sh < p.nsh; ++sh)
+            for (int hl = 0; hl < 2; ++hl)
+              tma_load_3d(st_a + (sh * 2 + hl) * A_TILE, &tmap_a, full_bar(s), P0 + (int)((sh - 1) * p.sh_stride), mt * ROWS, hl);
+          for (int hl = 0; hl < 2; ++hl) tma_load_3d(st_b + hl * b_half, &tmap_g, full_bar(s), P0, p.g_row0, hl);
+          if (++s == NST) { s = 0; ph ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+      const uint32_t idesc = umma_idesc_bf16(ROWS, p.N);
+      const uint32_t hi_sw = desc_hi(512, 4);            // K-major SWIZZLE_64B: 8-row groups 512 bytes apart
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kt = k0; kt < k1; ++kt) {
+        mbar_wait(full_bar(s), ph, p.err, 42);
+        tc_fence_after();
+        const uint32_t st_a = base + s * stage_bytes, st_b = st_a + a_bytes;
+        const uint32_t b_hi = desc_lo(st_b, 16), b_lo = desc_lo(st_b + b_half, 16);
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint64_t bd = desc_join((term == 1 ? b_lo : b_hi) + 2u * ks, hi_sw);
+#pragma unroll
+            for (int sh = 0; sh < 3; ++sh) {              // consecutive MMAs go to different accumulators
+              const uint32_t a_lo = desc_lo(st_a + (sh * 2 + (term == 2 ? 1 : 0)) * A_TILE, 16);
+              umma_bf16_elect(tmem_base + (uint32_t)(sh * p.N), desc_join(a_lo + 2u * ks, hi_sw), bd, idesc,
+                              (kt > k0 || ks > 0 || term > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit_elect(empty_bar(s));
+        if (++s == NST) { s = 0; ph ^= 1u; }
+      }
+      umma_commit_elect(done_bar);
+    } else {
+      // ===================== epilogue warps 2..5: accumulator -> fp32 scratch =====================
+      const int q = warp & 3;
+      const int row = mt * ROWS + q * 32 + lane;          // AT row: 0 = the ones row (bias), 1 + c = channel c
+      const int c = row - 1;
+      mbar_wait(done_bar, 0, p.err, 43);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool is_bias = row == 0;
+      const bool is_w = c >= 0 && c < p.cin;
+      for (int sh = 0; sh < p.nsh; ++sh) {
+        for (int n0 = 0; n0 < p.N; n0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + (uint32_t)(sh * p.N + n0), r);      // warp-uniform
+          tmem_ld_wait();
+          const int kx = n0 / p.nb, nn = n0 - kx * p.nb;            // 16-column groups never straddle a kx block (nb % 16 == 0)
+          const int tap = p.nkx == 3 ? sh * 3 + kx : sh;
+          if (is_w) {
+            float* o = p.dw + ((size_t)tap * p.cin + c) * p.np + nn;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (nn + j < p.np)
+                red_add4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else if (is_bias && sh == 1 && (p.nkx == 1 || kx == 1)) {
+            float* o = p.dw + (size_t)p.taps * p.cin * p.np + nn;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (nn + j < p.np)
+                red_add4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---- plane builders ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long plane_index(long long m, const WgGeom& g) {
+  const long long hw = (long long)g.h * g.w;
+  const long long n = m / hw, pix = m - n * hw;
+  const int y = (int)(pix / g.w), x = (int)(pix - (long long)y * g.w);
+  const long long b = n / g.T, t = n - b * g.T;
+  const long long f = b * (g.T + 1) + t + 1;
+  return (f * (g.h + 2) + y + 1) * g.Wp + x + 1;
+}
+
+// activations: slab-planar (hi, lo) dense buffer [pitch/16][M][16 hi | 16 lo] -> AT planes [2][193][Pa]; grid (pixels / 256, slabs)
+__global__ void __launch_bounds__(256) wg_planes_act_kernel(const __nv_bfloat16* __restrict__ buf, long long M, __nv_bfloat16* __restrict__ at,
+                                                            const WgGeom g) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int slab = blockIdx.y;
+  const long long P = plane_index(m, g);
+  const uint4* src = reinterpret_cast<const uint4*>(buf + ((size_t)slab * M + m) * 32);
+  uint4 r[4] = {__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3)};      // 16 hi, 16 lo
+  const uint16_t* e = reinterpret_cast<const uint16_t*>(r);
+  uint16_t* hi = reinterpret_cast<uint16_t*>(at) + (size_t)(1 + slab * 16) * g.Pa + P;
+  uint16_t* lo = hi + (size_t)kWgRows * g.Pa;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    hi[(size_t)j * g.Pa] = e[j];
+    lo[(size_t)j * g.Pa] = e[16 + j];
+  }
+  if (slab == 0) {
+    reinterpret_cast<uint16_t*>(at)[P] = 0x3F80;      // row 0 of the hi plane: 1.0 at real pixels (lo stays 0)
+  }
+}
+
+// gradient: fp32 pixel-major g[m * pitch + off + n], n < ncols -> GT planes [2][160][Pa].  Spatial convs (ncopies = 3): rows
+// kx * 32 + n hold the gradient written at P + (kx - 1), i.e. GT_kx[n][P] = g[n][P - (kx-1)] (the shifted positions are padding
+// columns of the same row, so the three copies never collide with real pixels of a neighbouring row); conv5 (ncopies = 1): rows
+// 96 + n at P, rows >= ncols zero.  The two forms use disjoint rows: each row is always written at the same set of positions.
+__global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __restrict__ gsrc, int pitch, int off, int ncols, int nb, int ncopies,
+                                                             long long M, __nv_bfloat16* __restrict__ gt, const WgGeom g) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long P = plane_index(m, g);
+  const float* src = gsrc + m * pitch + off;
+  const int row0 = ncopies == 3 ? 0 : kWgSpatialRows;
+  for (int n = 0; n < nb; ++n) {
+    const float v = n < ncols ? src[n] : 0.f;
+    __nv_bfloat16 h, l;
+    x2_split(v, h, l);
+    for (int kx = 0; kx < ncopies; ++kx) {
+      __nv_bfloat16* hi = gt + (size_t)(row0 + kx * nb + n) * g.Pa + P + (ncopies == 3 ? kx - 1 : 0);
+      hi[0] = h;
+      hi[(size_t)kWgGradRows * g.Pa] = l;
+    }
+  }
+}
+
+}  // namespace wg
+
+WgGeom wg_geometry(const Dims& d) {
+  WgGeom g;
+  g.B = d.B; g.T = d.T; g.h = d.h; g.w = d.w;
+  g.Wp = (d.w + 2 + 7) & ~7;
+  g.Fp = (long long)(d.h + 2) * g.Wp;
+  g.P = ((long long)d.B * (d.T + 1) + 1) * g.Fp;
+  g.Pa = (g.P + 31) & ~31ll;
+  return g;
+}
+
+size_t wg_plane_bytes(const WgGeom& g) { return (size_t)2 * (kWgRows + kWgGradRows) * g.Pa * sizeof(__nv_bfloat16); }
+
+int launch_wg_planes_act(const bfx2* buf, int pitch, const Dims& d, const WgGeom& g, void* planes, cudaStream_t st) {
+  SELFC_CHECK_ARG(pitch % 16 == 0 && pitch <= kWgRows - 1, "wgrad planes: pitch %d", pitch);
+  const long long M = d.M();
+  dim3 grid(cdiv(M, 256), pitch / 16);
+  wg::wg_planes_act_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(buf), M, reinterpret_cast<__nv_bfloat16*>(planes), g);
+  SELFC_LAUNCH_CHECK("wg_planes_act_kernel");
+  return 0;
+}
+
+int launch_wg_planes_grad(const float* gsrc, int pitch, int off, int ncols, int nb, bool temporal, const Dims& d, const WgGeom& g,
+                          void* planes, cudaStream_t st) {
+  SELFC_CHECK_ARG(nb % 16 == 0 && nb <= kWgGradRows - kWgSpatialRows && ncols <= nb && (temporal || nb == 32),
+                  "wgrad planes: %d gradient columns", ncols);
+  __nv_bfloat16* gt = reinterpret_cast<__nv_bfloat16*>(planes) + (size_t)2 * kWgRows * g.Pa;
+  wg::wg_planes_grad_kernel<<<cdiv(d.M(), 256), 256, 0, st>>>(gsrc, pitch, off, ncols, nb, temporal ? 1 : 3, d.M(), gt, g);
+  SELFC_LAUNCH_CHECK("wg_planes_grad_kernel");
+  return 0;
+}
+
+int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, int taps, bool temporal, float* dw, int np, cudaStream_t st) {
+  SELFC_CHECK_ARG(taps == (temporal ? 3 : 9) && nb % 16 == 0 && nb >= 16 && nb <= kWgGradRows - kWgSpatialRows && cin >= 1 && cin <= kWgRows - 1 && np % 4 == 0 &&
+                      (temporal || nb == 32),
+                  "wgrad_tc: unsupported shape (cin %d, nb %d, taps %d)", cin, nb, taps);
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SELFC_E_CUDA;
+  }
+  __nv_bfloat16* at = reinterpret_cast<__nv_bfloat16*>(planes);
+  __nv_bfloat16* gt = at + (size_t)2 * kWgRows * g.Pa;
+  CUtensorMap tmap_a, tmap_g;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)g.P, (cuuint64_t)kWgRows, 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)g.Pa * 2, (cuuint64_t)kWgRows * g.Pa * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)wg::KT, (cuuint32_t)wg::ROWS, 1};
+    CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, at, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (wgrad activations) failed with CUresult %d", (int)r);
+      return SELFC_E_CUDA;
+    }
+  }
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)g.P, (cuuint64_t)kWgGradRows, 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)g.Pa * 2, (cuuint64_t)kWgGradRows * g.Pa * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)wg::KT, (cuuint32_t)(temporal ? nb : 3 * nb), 1};
+    CUresult r = encode(&tmap_g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gt, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (wgrad gradient) failed with CUresult %d", (int)r);
+      return SELFC_E_CUDA;
+    }
+  }
+  wg::Params p;
+  memset(&p, 0, sizeof(p));
+  p.nsh = 3;
+  p.nkx = temporal ? 1 : 3;
+  p.nb = nb;
+  p.N = p.nkx * nb;
+  p.sh_stride = temporal ? g.Fp : g.Wp;
+  p.g_row0 = temporal ? kWgSpatialRows : 0;
+  p.ktiles = (int)(g.Pa / wg::KT);
+  p.mtiles = cdiv(cin + 1, wg::ROWS);
+  const int nsm = tc::num_sms();
+  int nsplit = 2 * nsm / p.mtiles;                       // two waves of CTAs: ~ a dozen K tiles each at Vimeo shape
+  if (nsplit > p.ktiles / 4) nsplit = p.ktiles / 4;      // at least four K tiles per CTA
+  if (nsplit < 1) nsplit = 1;
+  p.nsplit = nsplit;
+  p.cin = cin; p.np = np; p.taps = taps; p.ncols = ncols; p.dw = dw;
+  int cols = p.nsh * p.N, pw = 32;
+  while (pw < cols) pw <<= 1;
+  p.tmem_cols = pw;
+  p.err = tc::err_flag_for_device();
+  const int stage_bytes = p.nsh * 2 * wg::A_TILE + 2 * p.N * wg::KT * 2;
+  int nst = (227 * 1024 - wg::BAR_BYTES - 1024) / stage_bytes;
+  if (nst > wg::NST_MAX) nst = wg::NST_MAX;
+  p.nst = nst;
+  const int smem = nst * stage_bytes + wg::BAR_BYTES + 1024;
+  static bool smem_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !smem_set[dev]) {
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set[dev] = true;
+  }
+  wg::wgrad_tc_kernel<<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  SELFC_LAUNCH_CHECK("wgrad_tc_kernel");
+  return 0;
+}
+
+}  // namespace selfc

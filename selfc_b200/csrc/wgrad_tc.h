@@ -1,0 +1,30 @@
+// Tensor-core weight gradients of the dense-block convolutions (wgrad_tc.cu) -- host-side interface (BF16X3 training mode).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "net_ctx.h"
+
+namespace selfc {
+
+constexpr int kWgRows = 193;       // AT rows: the ones row + up to 192 channels of a dense buffer
+constexpr int kWgSpatialRows = 96;  // GT rows [0, 96): three one-pixel-shifted copies of a spatial conv's 32 gradient channels
+constexpr int kWgGradRows = 160;    // ... rows [96, 160): conv5's (unshifted) gradient, up to 64 channels
+
+// zero-padded pixel planes of one clip batch: P = ((f' * (h + 2) + y + 1) * Wp + x + 1), f' = b * (T + 1) + t + 1
+struct WgGeom {
+  int B, T, h, w, Wp;
+  long long Fp, P, Pa;             // padded frame size, plane length, allocated plane length (multiple of 32)
+};
+WgGeom wg_geometry(const Dims& d);
+size_t wg_plane_bytes(const WgGeom& g);      // [2][193][Pa] + [2][160][Pa] bf16; must be ZEROED once per geometry (the padding)
+
+// activations of a whole dense buffer (slab-planar (hi, lo) pairs, `pitch` channels) -> AT planes
+int launch_wg_planes_act(const bfx2* buf, int pitch, const Dims& d, const WgGeom& g, void* planes, cudaStream_t st);
+// output gradient g[m * pitch + off + n], n < ncols (fp32, pixel-major) -> GT rows [0, nb), rows >= ncols zero
+int launch_wg_planes_grad(const float* gsrc, int pitch, int off, int ncols, int nb, bool temporal, const Dims& d, const WgGeom& g,
+                          void* planes, cudaStream_t st);
+// dw[(tap * cin + c) * np + n] += sum_p in[p + shift(tap)][c] * g[p][n]; dw[taps * cin * np + n] += sum_p g[p][n]   (dw zeroed by the caller)
+int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, int taps, bool temporal, float* dw, int np, cudaStream_t st);
+
+}  // namespace selfc
