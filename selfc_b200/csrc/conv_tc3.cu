@@ -66,6 +66,10 @@ struct Params {
   int tiles_x, tiles_y, ntiles;
   int nst;
   int rev;               // walk the tiles last-to-first (see tc::next_direction)
+  // X2 input-gradient launches (training, BF16X3 mode): no bias / activation, the 32 results are ADDED to channels
+  // [acc_off, acc_off + acc_n) of an fp32 pixel-major buffer instead of being stored as (hi, lo) pairs
+  float* accF;
+  int acc_pitch, acc_off, acc_n;
   int* err;
   long long* dbg;        // SELFC_TC_DBG=1 (+ -DSELFC_TC_TIMING): CTA 0's barrier-wait cycles
 };
@@ -419,9 +423,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
             for (int j = 0; j < 16; ++j) {
               const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[j]), 1);
               const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 2);
-              v[j] = lrelu02(__uint_as_float(r0[j]) + a1 + a2 + bias[n0 + j]);
+              v[j] = __uint_as_float(r0[j]) + a1 + a2;
+              if (!X2 || p.accF == nullptr) v[j] = lrelu02(v[j] + bias[n0 + j]);
             }
-            if (ok) {
+            if (X2 && p.accF != nullptr) {
+              if (ok) {
+                float* of = p.accF + ((size_t)((size_t)n * p.h + y) * p.w + x) * p.acc_pitch + p.acc_off + n0;
+  #pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  if (n0 + j < p.acc_n) {
+                    float4 t = *reinterpret_cast<const float4*>(of + j);
+                    t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
+                    *reinterpret_cast<float4*>(of + j) = t;
+                  }
+                }
+              }
+            } else if (ok) {
               if constexpr (X2) {
                 __nv_bfloat16* os = o + (size_t)(n0 / 16) * slab_elems * 2;
                 x2_store8(os, v);              // channels 0..7: hi at +0, lo at +16 elements
@@ -497,7 +514,46 @@ __global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* _
   }
 }
 
+// Input-gradient images of one (1,3,3) conv (training, BF16X3 mode).  The gradient w.r.t. the conv's input is the conv of its output
+// gradient (32 channels) with the tap-flipped, transposed weights: gx[c] = sum_{n,ky,kx} Wf[(2-ky)*3 + (2-kx)][c][n] . g[n] at
+// (y + ky - 1, x + kx - 1), Wf = the forward weights in buffer-channel order [tap][cin_buf][32] (conv_simt pack).  The input channels
+// are produced 32 at a time (one launch of the X2 kernel each, K = 32): image j holds rows r = kx * 32 + (c - 32 j) in the pair
+// layout of pack_tc3_kernel's img_x2 with two K-steps; channels >= cin_buf are zero rows.
+__global__ void pack_tc3_dgrad_kernel(const float* __restrict__ wf, __nv_bfloat16* __restrict__ img, int cin_buf, int ngroups) {
+  const int per = 3 * 32 * NB;                       // (ky, n, r) of one group
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * ngroups) return;
+  const int j = idx / per, e = idx - j * per;
+  const int r = e % NB;
+  const int n = (e / NB) % 32;                      // K index: output-gradient channel
+  const int ky = e / (NB * 32);
+  const int kx = r / 32, c = 32 * j + r % 32;
+  float v = 0.f;
+  if (c < cin_buf) v = wf[((size_t)((2 - ky) * 3 + (2 - kx)) * cin_buf + c) * 32 + n];
+  constexpr int nks = 2;
+  const int ks = n / 16, kk = n % 16;
+  const int half = r / (NB / 2), rh = r % (NB / 2);
+  const size_t tile = (size_t)(WTILE_BYTES / 4);
+  const size_t half_elems = (size_t)3 * nks * tile;
+  const size_t inner = (size_t)((kk / 8) * (NB / 16) + rh / 8) * 64 + (rh % 8) * 8 + (kk % 8);
+  const size_t off = (size_t)j * (4 * half_elems) + half * (2 * half_elems) + (size_t)((ky * nks + ks) * 2) * tile + inner;
+  __nv_bfloat16 hi, lo;
+  x2_split(v, hi, lo);
+  img[off] = hi;
+  img[off + tile] = lo;
+}
+
 }  // namespace tc3
+
+size_t tc3_dgrad_image_bytes() { return (size_t)2 * 3 * 2 * tc3::WTILE_BYTES; }      // hi + lo, 3 ky, 2 K-steps
+
+int pack_tc3_dgrad_images(const float* wf, void* img, int cin_buf, cudaStream_t st) {
+  const int ngroups = cdiv(cin_buf, 32);
+  const int total = 3 * 32 * tc3::NB * ngroups;
+  tc3::pack_tc3_dgrad_kernel<<<cdiv(total, 256), 256, 0, st>>>(wf, reinterpret_cast<__nv_bfloat16*>(img), cin_buf, ngroups);
+  SELFC_LAUNCH_CHECK("pack_tc3_dgrad_kernel");
+  return 0;
+}
 
 // ---- host-side helpers shared by the tcgen05 kernels -----------------------------------------------------------
 namespace tc {
@@ -627,7 +683,10 @@ void free_tc_weights(TcConvW& w) {
 }
 
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
-                      const TcConvW* w2, __nv_bfloat16* buf2, bool x2) {
+                      const TcConvW* w2, __nv_bfloat16* buf2, bool x2, const TcAccum* acc) {
+  SELFC_CHECK_ARG(acc == nullptr || (x2 && w2 == nullptr && acc->out != nullptr && acc->pitch % 4 == 0 && acc->off % 4 == 0 && acc->n % 4 == 0 &&
+                                     acc->n >= 4 && acc->n <= 32 && aligned16(acc->out)),
+                  "conv3x3_tc: the accumulate epilogue belongs to a single (hi, lo) problem with 16-byte aligned fp32 rows");
   SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
   SELFC_CHECK_ARG(!x2 || (w.img_x2 != nullptr && (w2 == nullptr || w2->img_x2 != nullptr) && ((uintptr_t)buf & 63) == 0 &&
                           (buf2 == nullptr || ((uintptr_t)buf2 & 63) == 0)),
@@ -727,6 +786,7 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   p.tiles_y = cdiv(h, tc3::ROWS);
   p.ntiles = p.tiles_x * p.tiles_y * N;
   p.err = tc::err_flag_for_device();
+  if (acc != nullptr) { p.accF = acc->out; p.acc_pitch = acc->pitch; p.acc_off = acc->off; p.acc_n = acc->n; }
   if (p.ntiles == 0) return 0;
   p.rev = tc::next_direction();
   if (tc::debug_slots()) p.dbg = tc::debug_next_slot(9000000 + (dual ? 100000 : 0) + nks);

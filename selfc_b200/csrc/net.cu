@@ -668,6 +668,17 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
   if (ctx->train_scratch) cudaFree(ctx->train_scratch);
   if (ctx->train_zero_bias) cudaFree(ctx->train_zero_bias);
   if (ctx->wg_planes) cudaFree(ctx->wg_planes);
+  if (ctx->dg_gslab) cudaFree(ctx->dg_gslab);
+  if (ctx->dg_wtmp) cudaFree(ctx->dg_wtmp);
+  auto free_dg = [](DenseW& W) {
+    for (int k = 0; k < 4; ++k)
+      if (W.dg_img[k]) cudaFree(W.dg_img[k]);
+    free_temporal_weights(W.dg5[0]);
+    free_temporal_weights(W.dg5[1]);
+  };
+  for (int b = 0; b < 8; ++b)
+    for (int j = 0; j < 3; ++j) free_dg(ctx->inv[b][j]);
+  for (int i = 0; i < 6; ++i) free_dg(ctx->stp[i]);
   for (int b = 0; b < 8; ++b)
     for (int j = 0; j < 3; ++j)
     {
@@ -772,6 +783,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     const DensePlan& d = dp[i];
     DenseW* W = i < 24 ? &ctx->inv[i / 3][i % 3] : &ctx->stp[i - 24];
     W->cin = d.cin; W->cout = d.cout; W->xpad = d.xpad;
+    W->dg_valid = false;            // the input-gradient images follow the weights: re-packed by the next backward
     for (int k = 0; k < 5; ++k) {
       const int taps = k < 4 ? 9 : 3;
       const int cin_ref = d.cin + kGrowth * k;

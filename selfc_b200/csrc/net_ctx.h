@@ -28,6 +28,11 @@ struct DenseW {            // one D2DTInput in kernel layout
   TcConvW tc[5];           // tcgen05 bf16 images (BF16 mode)
   TcTempW t5;              // conv5 image (BF16 mode)
   void* f5img = nullptr;   // BF16 mode, cout == 3 (F blocks): conv5's taps as a pointwise GEMM inside the fused dense-block kernel
+  // BF16X3 training: input-gradient images, packed on the first backward after every weight load (dg_valid)
+  void* dg_img[4] = {};    // conv1..4: ceil(cin_k / 32) images of tc3_dgrad_image_bytes()
+  TcTempW dg5[2];          // conv5: the buffer channels in two column groups (<= 96 each)
+  int dg5_c0[2] = {}, dg5_n[2] = {};
+  bool dg_valid = false;
 };
 struct GaW {
   float *fcw = nullptr, *fcb = nullptr, *p2w = nullptr, *p2b = nullptr, *p3w = nullptr, *p3b = nullptr;
@@ -80,6 +85,9 @@ struct selfc_ctx {
   void* wg_planes = nullptr;
   size_t wg_bytes = 0;
   int wg_key[4] = {0, 0, 0, 0};
+  void* dg_gslab = nullptr;      // the output gradient of one conv as (hi, lo) slabs (input of a tensor-core input-gradient launch)
+  size_t dg_gslab_bytes = 0;
+  float* dg_wtmp = nullptr;      // conv5's flipped / transposed weights in reference layout while they are being packed
   // optional per-launch timing (bench.py's roofline leg): CUDA events around every launch, by kernel class
   bool prof_on = false;
   std::vector<ProfRec> prof;

@@ -76,8 +76,10 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict
 
 // g[m][off + n] *= (y[m][off + n] > 0 ? 1 : 0.2)   for n < 32  (LeakyReLU backward through the stored activation)
 // E: element type of the forward dense buffer y (float: pixel-major, FP32 mode; bfx2: slab-planar (hi, lo) pairs, BF16X3 mode)
+// gslab (optional): the masked gradient also as (hi, lo) slabs [2][M][16 | 16] -- the input of the tensor-core input-gradient launches
 template <typename E>
-__global__ void lrelu_bwd_kernel(float* __restrict__ g, const E* __restrict__ y, int pitch, long long slabM, int off, long long M) {
+__global__ void lrelu_bwd_kernel(float* __restrict__ g, const E* __restrict__ y, int pitch, long long slabM, int off, long long M,
+                                 bfx2* __restrict__ gslab = nullptr) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long m = idx >> 3;
   const int c = (int)(idx & 7) * 4;
@@ -89,6 +91,7 @@ __global__ void lrelu_bwd_kernel(float* __restrict__ g, const E* __restrict__ y,
   gv.z *= yv.z > 0.f ? 1.f : 0.2f;
   gv.w *= yv.w > 0.f ? 1.f : 0.2f;
   store4(g + m * pitch + off + c, gv);
+  if (gslab != nullptr) store4(gslab + dense_off(m, c, 32, M), gv);
 }
 
 // wgrad: dw[tap][c][n] += sum_m in[m + shift(tap)][c] * g[m][n]  (+ the bias gradient in pseudo-tap `taps`: db[n] += sum_m g[m][n]).
@@ -264,12 +267,74 @@ size_t dense_bwd_scratch_floats(const DenseW& W) {
   return wd + dw + 256;
 }
 
+// ---- tensor-core input gradients (BF16X3 mode) -------------------------------------------------------------------------
+// conv5: wd5[c][n][dt] = Wf5[((2 - dt) * cin_buf + c) * np + n] (n < cout, else 0): the flipped / transposed temporal weights in the
+// reference layout [cout' = buffer channel][cin' = nb][3] that pack_temporal_weights takes
+__global__ void dgrad5_ref_kernel(const float* __restrict__ wf, float* __restrict__ wd5, int cin_buf, int np, int cout, int nb) {
+  const int total = cin_buf * nb * 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int dt = idx % 3, n = (idx / 3) % nb, c = idx / (3 * nb);
+  wd5[idx] = n < cout ? wf[((size_t)(2 - dt) * cin_buf + c) * np + n] : 0.f;
+}
+// fp32 pixel-major [M][spitch] columns [0, ncol) -> (hi, lo) slabs [nb / 16][M], columns >= ncol zero
+__global__ void cols_to_slab_kernel(bfx2* __restrict__ dst, int nb, const float* __restrict__ src, int spitch, int ncol, long long M) {
+  const int per = nb / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * per) return;
+  const long long m = idx / per;
+  const int c = (int)(idx - m * per) * 4;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = c + e < ncol ? src[m * spitch + c + e] : 0.f;
+  store4(dst + dense_off(m, c, nb, M), make_float4(v[0], v[1], v[2], v[3]));
+}
+
+static int ensure_dgrad_images(const selfc_ctx* cctx, const DenseW& cW, float* zero_bias, cudaStream_t st) {
+  DenseW& W = const_cast<DenseW&>(cW);
+  if (W.dg_valid) return 0;
+  selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t ib = tc3_dgrad_image_bytes();
+  for (int k = 0; k < 4; ++k) {
+    const int cin = W.xpad + kGrowth * k;
+    if (W.dg_img[k] == nullptr) SELFC_CUDA(cudaMalloc(&W.dg_img[k], ib * cdiv(cin, 32)));
+    SELFC_TRY(pack_tc3_dgrad_images(W.w[k], W.dg_img[k], cin, st));
+  }
+  const int cin5 = W.xpad + 4 * kGrowth, nb = (W.cout + 15) & ~15;
+  if (ctx->dg_wtmp == nullptr) SELFC_CUDA(cudaMalloc(&ctx->dg_wtmp, (size_t)192 * 64 * 3 * sizeof(float)));
+  dgrad5_ref_kernel<<<cdiv(cin5 * nb * 3, 256), 256, 0, st>>>(W.w[4], ctx->dg_wtmp, cin5, W.np[4], W.cout, nb);
+  SELFC_LAUNCH_CHECK("dgrad5_ref_kernel");
+  W.dg5_c0[0] = 0; W.dg5_n[0] = cin5 > 96 ? 96 : cin5;
+  W.dg5_c0[1] = W.dg5_n[0]; W.dg5_n[1] = cin5 - W.dg5_n[0];
+  for (int gI = 0; gI < 2; ++gI)
+    if (W.dg5_n[gI] > 0)
+      SELFC_TRY(pack_temporal_weights(W.dg5[gI], ctx->dg_wtmp + (size_t)W.dg5_c0[gI] * nb * 3, zero_bias, W.dg5_n[gI], nb, 3, nb, nb, nb, st, true));
+  W.dg_valid = true;
+  return 0;
+}
+static bfx2* train_gslab(const selfc_ctx* cctx, long long M) {
+  selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t need = (size_t)M * 64 * sizeof(bfx2) + 4096;
+  if (ctx->dg_gslab_bytes < need) {
+    if (ctx->dg_gslab) cudaFree(ctx->dg_gslab);
+    ctx->dg_gslab = nullptr;
+    ctx->dg_gslab_bytes = 0;
+    if (cudaMalloc(&ctx->dg_gslab, need) != cudaSuccess) return nullptr;
+    ctx->dg_gslab_bytes = need;
+  }
+  return reinterpret_cast<bfx2*>(ctx->dg_gslab);
+}
+
 template <typename E>
 int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, int pitch, const float* gy, int gy_pitch, float* gbuf,
                          float* scratch, float* const* gparams, const Dims& d, cudaStream_t st) {
   const long long M = d.M();
   const long long slabM = dense_slab(ctx, d);         // layout of the forward buffer; gradient buffers are fp32 pixel-major
   if (M == 0) return 0;
+  float* zero_bias = train_zero_bias(ctx);     // dgrad has no bias term
+  SELFC_CHECK_ARG(zero_bias != nullptr, "out of device memory (training scratch)");
   // BF16X3 mode: weight gradients on the tensor cores (wgrad_tc.cu) from transposed, zero-padded planes of the block's activations,
   // built once for all five convolutions.  SELFC_WGRAD_TC=0: the fp32-FMA pixel reduction below (A/B, parity).
   bool wg_tc = false;
@@ -289,9 +354,24 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       wg_tc = true;
     }
   }
+  // ... and the input gradients: the tcgen05 forward kernels on the flipped / transposed (hi, lo) weight images, the output gradient
+  // of each conv converted to (hi, lo) slabs on the way.  SELFC_DGRAD_TC=0: the fp32-FMA kernel.
+  bool dg_tc = false;
+  bfx2* gslab = nullptr;
+  if constexpr (std::is_same<E, bfx2>::value) {
+    static int dg_on = -1;
+    if (dg_on < 0) {
+      const char* e = getenv("SELFC_DGRAD_TC");
+      dg_on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (dg_on) {
+      SELFC_TRY(ensure_dgrad_images(ctx, W, zero_bias, st));
+      gslab = train_gslab(ctx, M);
+      SELFC_CHECK_ARG(gslab != nullptr, "out of device memory (gradient slabs)");
+      dg_tc = true;
+    }
+  }
   SELFC_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)M * pitch * sizeof(float), st));
-  float* zero_bias = train_zero_bias(ctx);     // dgrad has no bias term
-  SELFC_CHECK_ARG(zero_bias != nullptr, "out of device memory (training scratch)");
   for (int k = 4; k >= 0; --k) {
     const int taps = k < 4 ? 9 : 3;
     const int tap_mode = k < 4 ? TAP_SPATIAL : TAP_TEMPORAL;
@@ -304,7 +384,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
     const int g_pitch = k < 4 ? pitch : gy_pitch;
     const int g_off = k < 4 ? slot : 0;
     if (k < 4) {
-      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, buf, pitch, slabM, slot, M);
+      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, buf, pitch, slabM, slot, M, dg_tc ? gslab : nullptr);
       SELFC_LAUNCH_CHECK("lrelu_bwd_kernel");
     }
     float* wd = scratch;
@@ -330,6 +410,35 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       SELFC_LAUNCH_CHECK("wgrad_unpack_kernel");
     }
     // input gradient: the forward kernel on the flipped / transposed weights, accumulated into gbuf[0:cin)
+    if (dg_tc && k == 4) {
+      // conv5: gy -> (hi, lo) slabs, then the temporal kernel per column group, STORING into the still-zero gradient buffer
+      const int nb = (cout + 15) & ~15;
+      cols_to_slab_kernel<<<cdiv(M * (nb / 4), 256), 256, 0, st>>>(gslab, nb, gy, gy_pitch, cout, M);
+      SELFC_LAUNCH_CHECK("cols_to_slab_kernel");
+      for (int gI = 0; gI < 2; ++gI) {
+        if (W.dg5_n[gI] <= 0) continue;
+        TcTempArgs t;
+        t.in = reinterpret_cast<const __nv_bfloat16*>(gslab); t.in_pitch = nb; t.B = d.B; t.T = d.T; t.hw = (int)d.hw(); t.in_slabM = M;
+        t.epi = EPI_STORE; t.act = 0;
+        t.outF = gbuf; t.outF_pitch = pitch; t.outF_off = W.dg5_c0[gI];
+        SELFC_TRY(launch_temporal_tc(W.dg5[gI], t, st));
+      }
+      continue;
+    }
+    if (dg_tc) {
+      for (int j = 0; 32 * j < cin; ++j) {
+        TcConvW tw;
+        tw.img = W.dg_img[k];                 // presence only: the (hi, lo) form reads img_x2
+        tw.img_x2 = static_cast<char*>(W.dg_img[k]) + (size_t)j * tc3_dgrad_image_bytes();
+        tw.img_bytes = tc3_dgrad_image_bytes() / 2;
+        tw.cin_buf = 32;
+        tw.bias = zero_bias;
+        TcAccum acc;
+        acc.out = gbuf; acc.pitch = pitch; acc.off = 32 * j; acc.n = cin - 32 * j < 32 ? cin - 32 * j : 32;
+        SELFC_TRY(launch_conv3x3_tc(tw, reinterpret_cast<__nv_bfloat16*>(gslab), M, 32, 0, d.B * d.T, d.h, d.w, st, nullptr, nullptr, true, &acc));
+      }
+      continue;
+    }
     const long long wtot = (long long)taps * cout4 * npd;
     pack_dgrad_kernel<<<cdiv(wtot, 256), 256, 0, st>>>(W.w[k], wd, taps, cin, W.np[k], cout, cout4, npd);
     SELFC_LAUNCH_CHECK("pack_dgrad_kernel");
