@@ -30,7 +30,8 @@ void free_tc_weights(TcConvW& w);
 // pixel-major buffer -- an input-gradient launch: buf holds the output gradient, w.img_x2 one of pack_tc3_dgrad_images' images
 struct TcAccum {
   float* out = nullptr;
-  int pitch = 0, off = 0, n = 0;
+  int pitch = 0, off = 0, n = 0;      // n channels in ngroups groups of 32 (w.img_x2 = the first of ngroups consecutive images)
+  int ngroups = 1;
 };
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
                       const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr, bool x2 = false, const TcAccum* acc = nullptr);

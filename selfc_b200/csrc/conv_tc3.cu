@@ -68,8 +68,9 @@ struct Params {
   int rev;               // walk the tiles last-to-first (see tc::next_direction)
   // X2 input-gradient launches (training, BF16X3 mode): no bias / activation, the 32 results are ADDED to channels
   // [acc_off, acc_off + acc_n) of an fp32 pixel-major buffer instead of being stored as (hi, lo) pairs
+  // Such a launch produces acc_n channels in groups of 32: `ngroups` weight images resident, every tile visited once per group.
   float* accF;
-  int acc_pitch, acc_off, acc_n;
+  int acc_pitch, acc_off, acc_n, ngroups;
   int* err;
   long long* dbg;        // SELFC_TC_DBG=1 (+ -DSELFC_TC_TIMING): CTA 0's barrier-wait cycles
 };
@@ -198,10 +199,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t wbytes = 3u * nks * WSTEP;
-      const uint8_t* wsrc = (const uint8_t*)wimg + (PAIR ? (size_t)crank * wbytes : 0);
-      mbar_expect_tx(w_bar, wbytes);
-      for (int ky = 0; ky < 3; ++ky)
-        bulk_g2s(w_base + ky * nks * WSTEP, wsrc + (size_t)ky * nks * WSTEP, (uint32_t)nks * WSTEP, w_bar);
+      mbar_expect_tx(w_bar, wbytes * (uint32_t)p.ngroups);
+      for (int grp = 0; grp < p.ngroups; ++grp) {       // group images follow each other: [group][half of the pair][ky][K-step]
+        const uint8_t* wsrc = (const uint8_t*)wimg + (size_t)grp * (PAIR ? 2u : 1u) * wbytes + (PAIR ? (size_t)crank * wbytes : 0);
+        for (int ky = 0; ky < 3; ++ky)
+          bulk_g2s(w_base + grp * wbytes + ky * nks * WSTEP, wsrc + (size_t)ky * nks * WSTEP, (uint32_t)nks * WSTEP, w_bar);
+      }
 #ifdef SELFC_TC_TIMING
       const long long t_pdl0 = clock64();
 #endif
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
         int tx, ty, n;
         decode_tile(p, tile, tx, ty, n);                   // n == N for the odd tile out of a pair: the box is zero-filled
         const int x0 = tx * VALID_W - 1, y0 = ty * ROWS - 1;
+        for (int grp = 0; grp < p.ngroups; ++grp)
         for (int c0 = 0; c0 < nks; c0 += KPS) {
           timed_wait(empty_bar(s), ph ^ 1u, p.err, 31, w_empty);
           const int xc = P2 ? tx * (VALID_W / 2) : x0;        // P2: pair index of the halo origin (pairs start at odd x)
@@ -256,9 +260,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
       const uint32_t b_ky = (uint32_t)nks * (WSTEP >> 4);
       long long w_full = 0, w_tempty = 0;
       const long long t_start = clock64();
-      for (int step = rank; step < nsteps; step += nwalk, ++it) {
+      for (int step = rank; step < nsteps; step += nwalk)
+      for (int grp = 0; grp < p.ngroups; ++grp, ++it) {
         const int acc = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
+        const uint32_t w_grp = w_base + (uint32_t)grp * 3u * (uint32_t)nks * WSTEP;
         timed_wait(tempty_bar(acc), (use & 1u) ^ 1u, p.err, 33, w_tempty);
         tc_fence_after();
         for (int c0 = 0; c0 < nks; c0 += KPS) {
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
           for (int ks = 0; ks < nk; ++ks) {
             const uint32_t a_lo = desc_lo(a_stage + (uint32_t)ks * SUBB, 16);
             // B (weights): (ky, K-step) tiles; the two 8-element K core matrices are NBH/8 row-groups apart
-            const uint32_t b_lo = desc_lo(w_base + (uint32_t)(c0 + ks) * WSTEP, (NBH / 8) * 128);
+            const uint32_t b_lo = desc_lo(w_grp + (uint32_t)(c0 + ks) * WSTEP, (NBH / 8) * 128);
             // consecutive MMAs alternate between the two M-blocks' accumulators: back-to-back accumulation into ONE
             // accumulator is a dependent chain (measured ~145 cycles per small MMA), independent accumulators pipeline
             if constexpr (X2) {
@@ -325,7 +331,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
     int it = 0;
     long long w_tfull = 0;
     const long long t_start = clock64();
-    for (int step = rank; step < nsteps; step += nwalk, ++it) {
+    for (int step = rank; step < nsteps; step += nwalk)
+    for (int grp = 0; grp < p.ngroups; ++grp, ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       const int tile = PAIR ? 2 * step + (int)crank : step;
@@ -428,10 +435,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
             }
             if (X2 && p.accF != nullptr) {
               if (ok) {
-                float* of = p.accF + ((size_t)((size_t)n * p.h + y) * p.w + x) * p.acc_pitch + p.acc_off + n0;
+                float* of = p.accF + ((size_t)((size_t)n * p.h + y) * p.w + x) * p.acc_pitch + p.acc_off + 32 * grp + n0;
   #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                  if (n0 + j < p.acc_n) {
+                  if (32 * grp + n0 + j < p.acc_n) {
                     float4 t = *reinterpret_cast<const float4*>(of + j);
                     t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
                     *reinterpret_cast<float4*>(of + j) = t;
@@ -685,7 +692,7 @@ void free_tc_weights(TcConvW& w) {
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
                       const TcConvW* w2, __nv_bfloat16* buf2, bool x2, const TcAccum* acc) {
   SELFC_CHECK_ARG(acc == nullptr || (x2 && w2 == nullptr && acc->out != nullptr && acc->pitch % 4 == 0 && acc->off % 4 == 0 && acc->n % 4 == 0 &&
-                                     acc->n >= 4 && acc->n <= 32 && aligned16(acc->out)),
+                                     acc->n >= 4 && acc->ngroups >= 1 && acc->ngroups <= 6 && acc->n <= 32 * acc->ngroups && aligned16(acc->out)),
                   "conv3x3_tc: the accumulate epilogue belongs to a single (hi, lo) problem with 16-byte aligned fp32 rows");
   SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
   SELFC_CHECK_ARG(!x2 || (w.img_x2 != nullptr && (w2 == nullptr || w2->img_x2 != nullptr) && ((uintptr_t)buf & 63) == 0 &&
@@ -718,7 +725,8 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   int kps = kps_pref < nks ? kps_pref : nks;
   const int sub_bytes = x2 ? 2 * tc3::SUB_BYTES : tc3::SUB_BYTES;
   // both problems' weights have the same size; x2: hi + lo images, half of each per CTA
-  const int fixed = tc3::BAR_BYTES + (int)(x2 ? w.img_bytes : (pair ? w.img_bytes / 2 : w.img_bytes)) + 1024;
+  const int ngroups = acc != nullptr ? acc->ngroups : 1;
+  const int fixed = tc3::BAR_BYTES + (int)(x2 ? w.img_bytes * ngroups : (pair ? w.img_bytes / 2 : w.img_bytes)) + 1024;
   while (kps > 1 && (227 * 1024 - fixed) / (kps * sub_bytes) < 3) --kps;
   // SELFC_TC3_P2=0: one position per TMA row (SWIZZLE_32B) instead of position pairs.  Pairs need an even width.
   static int p2_pref = -1;
@@ -786,6 +794,7 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   p.tiles_y = cdiv(h, tc3::ROWS);
   p.ntiles = p.tiles_x * p.tiles_y * N;
   p.err = tc::err_flag_for_device();
+  p.ngroups = ngroups;
   if (acc != nullptr) { p.accF = acc->out; p.acc_pitch = acc->pitch; p.acc_off = acc->off; p.acc_n = acc->n; }
   if (p.ntiles == 0) return 0;
   p.rev = tc::next_direction();

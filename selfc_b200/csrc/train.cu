@@ -426,17 +426,16 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       continue;
     }
     if (dg_tc) {
-      for (int j = 0; 32 * j < cin; ++j) {
-        TcConvW tw;
-        tw.img = W.dg_img[k];                 // presence only: the (hi, lo) form reads img_x2
-        tw.img_x2 = static_cast<char*>(W.dg_img[k]) + (size_t)j * tc3_dgrad_image_bytes();
-        tw.img_bytes = tc3_dgrad_image_bytes() / 2;
-        tw.cin_buf = 32;
-        tw.bias = zero_bias;
-        TcAccum acc;
-        acc.out = gbuf; acc.pitch = pitch; acc.off = 32 * j; acc.n = cin - 32 * j < 32 ? cin - 32 * j : 32;
-        SELFC_TRY(launch_conv3x3_tc(tw, reinterpret_cast<__nv_bfloat16*>(gslab), M, 32, 0, d.B * d.T, d.h, d.w, st, nullptr, nullptr, true, &acc));
-      }
+      // one launch per conv: all ceil(cin / 32) weight images resident, every tile visited once per 32-channel group
+      TcConvW tw;
+      tw.img = W.dg_img[k];                   // presence only: the (hi, lo) form reads img_x2
+      tw.img_x2 = W.dg_img[k];
+      tw.img_bytes = tc3_dgrad_image_bytes() / 2;
+      tw.cin_buf = 32;
+      tw.bias = zero_bias;
+      TcAccum acc;
+      acc.out = gbuf; acc.pitch = pitch; acc.off = 0; acc.n = cin; acc.ngroups = cdiv(cin, 32);
+      SELFC_TRY(launch_conv3x3_tc(tw, reinterpret_cast<__nv_bfloat16*>(gslab), M, 32, 0, d.B * d.T, d.h, d.w, st, nullptr, nullptr, true, &acc));
       continue;
     }
     const long long wtot = (long long)taps * cout4 * npd;

@@ -19,6 +19,7 @@
 // lo.hi), fp32 accumulation in tensor memory over the CTA's share of the pixels (split-K), then one vector reduction (red.v4.f32)
 // per four weights into the fp32 scratch the existing unpack kernel reads.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "net_ctx.h"
@@ -221,14 +222,25 @@ __global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __rest
   const long long P = plane_index(m, g);
   const float* src = gsrc + m * pitch + off;
   const int row0 = ncopies == 3 ? 0 : kWgSpatialRows;
-  for (int n = 0; n < nb; ++n) {
-    const float v = n < ncols ? src[n] : 0.f;
-    __nv_bfloat16 h, l;
-    x2_split(v, h, l);
-    for (int kx = 0; kx < ncopies; ++kx) {
-      __nv_bfloat16* hi = gt + (size_t)(row0 + kx * nb + n) * g.Pa + P + (ncopies == 3 ? kx - 1 : 0);
-      hi[0] = h;
-      hi[(size_t)kWgGradRows * g.Pa] = l;
+  const bool vec = ((pitch | off) & 3) == 0;
+  for (int n0 = 0; n0 < nb; n0 += 4) {
+    float v4[4];
+    if (vec && n0 + 4 <= ncols) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + n0));
+      v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v4[e] = n0 + e < ncols ? __ldg(src + n0 + e) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat16 h, l;
+      x2_split(v4[e], h, l);
+      for (int kx = 0; kx < ncopies; ++kx) {
+        __nv_bfloat16* hi = gt + (size_t)(row0 + kx * nb + n0 + e) * g.Pa + P + (ncopies == 3 ? kx - 1 : 0);
+        hi[0] = h;
+        hi[(size_t)kWgGradRows * g.Pa] = l;
+      }
     }
   }
 }
@@ -312,7 +324,15 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
   p.ktiles = (int)(g.Pa / wg::KT);
   p.mtiles = cdiv(cin + 1, wg::ROWS);
   const int nsm = tc::num_sms();
-  int nsplit = 2 * nsm / p.mtiles;                       // two waves of CTAs: ~ a dozen K tiles each at Vimeo shape
+  // one wave of CTAs: the per-CTA cost that does not shrink with the split is the reduction of its 128 x 288 accumulator into the
+  // scratch (SELFC_WGRAD_WAVES=2 doubles the split)
+  static int waves = 0;
+  if (!waves) {
+    const char* e = getenv("SELFC_WGRAD_WAVES");
+    waves = e ? atoi(e) : 1;
+    if (waves < 1 || waves > 8) waves = 1;
+  }
+  int nsplit = waves * nsm / p.mtiles;
   if (nsplit > p.ktiles / 4) nsplit = p.ktiles / 4;      // at least four K tiles per CTA
   if (nsplit < 1) nsplit = 1;
   p.nsplit = nsplit;
