@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the 'train' block (configs[3]: a few training steps + gradient all-reduce)")
+    ap.add_argument("--no-gate-mode", action="store_true", help="skip the short BF16X3 (configs[1]) measurement beside the bf16 headline")
     ap.add_argument("--workload", default="rescale", choices=["rescale", "train"],
                     help="rescale: the headline metric (default); train: BASELINE.json configs[3], one training step on synthetic "
                          "Vimeo90K-shape septuplets per rank with the flat-gradient NCCL all-reduce")
@@ -349,6 +350,37 @@ def run_ours(args):
                     "classes": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                                     "share": round(v["ms"] / tot_ms, 4) if tot_ms else None} for k, v in prof.items()}}
 
+    # ---- BASELINE.json configs[1] beside the headline: the numerics-gate mode on the tensor cores (BF16X3), a short device-resident run
+    gate_block = None
+    if args.mode == "bf16" and not args.no_gate_mode and rank == 0:
+        try:
+            del eng
+            torch.cuda.empty_cache()
+            eng3 = Engine(dev, "bf16x3")
+            eng3.load_state(state)
+            n_g = min(4, max(1, frames // GOP))
+            xs = group[:n_g * GOP]
+            for i in range(2):
+                for g0 in range(n_g):
+                    eng3.rescale(xs[g0 * GOP:(g0 + 1) * GOP], GOP, seed=42, offset=g0)
+            torch.cuda.synchronize()
+            g0e, g1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            g0e.record()
+            for i in range(reps):
+                for g0 in range(n_g):
+                    eng3.rescale(xs[g0 * GOP:(g0 + 1) * GOP], GOP, seed=42, offset=g0)
+            g1e.record()
+            torch.cuda.synchronize()
+            gms = g0e.elapsed_time(g1e)
+            gate_block = {"mode": "bf16x3", "value": n_g * GOP * reps / (gms / 1e3), "unit": "frames/s", "frames_timed": n_g * GOP * reps,
+                          "ms_per_gop": gms / (n_g * reps),
+                          "what": "BASELINE.json configs[1] arithmetic (HR within 1e-3 of the fp32 reference; tests hold 2e-4) on the tcgen05 kernels: "
+                                  "(hi, lo) bf16 operands, three MMAs per product, fp32 accumulation; same frames, device-resident, one GPU"}
+            del eng3
+        except Exception as exc:      # never lose the headline line to the side measurement
+            gate_block = {"mode": "bf16x3", "error": str(exc)[:200]}
+
     # ---- BASELINE.json configs[3] beside the headline: a few training steps per rank with the gradient all-reduce ----------------
     train_block = None
     if not args.no_train:
@@ -372,7 +404,7 @@ def run_ours(args):
             "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 ((hi, lo) bf16 pairs, three tensor-core MMAs per product, fp32 accumulate)"}.get(args.mode, "f32"),
             "data": "synthetic", "config": workload_config(args, args.mode, weights_desc),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "algorithmic_tflops": whole_tflops, "train": train_block}
+            "algorithmic_tflops": whole_tflops, "fp32_gate_mode": gate_block, "train": train_block}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

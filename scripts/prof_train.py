@@ -15,6 +15,7 @@ from selfc_b200.synthetic import seeded_state_dict, synthetic_net  # noqa: E402
 from selfc_b200.train import Trainer  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+nb = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 dev = torch.device("cuda", 0)
 t, hh, ww = 7, 256, 448
 net, _ = synthetic_net(train=True)
@@ -23,7 +24,7 @@ net = net.to(dev)
 net.set_precision(mode)
 GlobalVar.set_Temporal_LEN(t)
 tr = Trainer(net, dev, lr=1e-4, weight_decay=1e-14, max_norm=10.0)
-x = bench.make_group(t, hh, ww, 4321, dev)
+x = bench.make_group(nb * t, hh, ww, 4321, dev)
 ref_l = _eng.gaussian_downsample(x)
 for i in range(2):
     tr.step(x, ref_l, t, seed=42, offset=i)
@@ -38,6 +39,6 @@ for e in prof.events():
         a[0] += 1
         a[1] += e.device_time / 1e3 if hasattr(e, "device_time") else e.cuda_time / 1e3
 tot = sum(a[1] for a in agg.values())
-print(f"mode {mode}: {sum(a[0] for a in agg.values())} kernels, {tot:.2f} ms of kernel time")
+print(f"mode {mode}, {nb} septuplet(s): {sum(a[0] for a in agg.values())} kernels, {tot:.2f} ms of kernel time")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
     print(f"{k:72s} {a[0]:5d} {a[1]:9.3f} ms {a[1] / tot:.3f}")

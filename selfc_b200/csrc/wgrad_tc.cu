@@ -44,6 +44,8 @@ struct Params {
   int ktiles, nsplit, mtiles, nst;
   int cin, np, taps;                    // scratch layout dw[(tap * cin + c) * np + n], bias at dw[taps * cin * np + n]
   int ncols;                            // real output channels (n < ncols)
+  int arows;                            // AT rows the TMA box brings (the rows that matter: 1 + cin, rounded up to 8; <= 128).  The MMA
+                                        // still reads 128 rows of the tile: the others hold stale data whose products are never stored
   int g_row0;                           // first GT row of this launch (0: the three shifted copies; kWgSpatialRows: conv5's rows)
   float* dw;
   int tmem_cols;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
         uint32_t ph = 0;
         for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(empty_bar(s), ph ^ 1u, p.err, 41);
-          mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+          mbar_expect_tx(full_bar(s), (uint32_t)(p.nsh * 2 * p.arows * KT * 2 + 2 * b_half));
           const uint32_t st_a = base + s * stage_bytes, st_b = st_a + a_bytes;
           const int P0 = kt * KT;
           for (int sh = 0; sh < p.nsh; ++sh)
@@ -291,10 +293,12 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
   __nv_bfloat16* gt = at + (size_t)2 * kWgRows * g.Pa;
   CUtensorMap tmap_a, tmap_g;
   const cuuint32_t estr[3] = {1, 1, 1};
+  // one M tile: only the rows that exist are fetched (cin = 16 -> 24 of 128); two M tiles: full boxes (the second is zero-filled past row 192)
+  const int arows = cin + 1 <= wg::ROWS ? ((cin + 1 + 7) & ~7) : wg::ROWS;
   {
     const cuuint64_t gdim[3] = {(cuuint64_t)g.P, (cuuint64_t)kWgRows, 2};
     const cuuint64_t gstr[2] = {(cuuint64_t)g.Pa * 2, (cuuint64_t)kWgRows * g.Pa * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)wg::KT, (cuuint32_t)wg::ROWS, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)wg::KT, (cuuint32_t)arows, 1};
     CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, at, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -321,6 +325,7 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
   p.N = p.nkx * nb;
   p.sh_stride = temporal ? g.Fp : g.Wp;
   p.g_row0 = temporal ? kWgSpatialRows : 0;
+  p.arows = arows;
   p.ktiles = (int)(g.Pa / wg::KT);
   p.mtiles = cdiv(cin + 1, wg::ROWS);
   const int nsm = tc::num_sms();
