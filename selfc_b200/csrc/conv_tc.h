@@ -32,6 +32,7 @@ struct TcAccum {
   float* out = nullptr;
   int pitch = 0, off = 0, n = 0;      // n channels in ngroups groups of 32 (w.img_x2 = the first of ngroups consecutive images)
   int ngroups = 1;
+  long long slabM = 0;                // layout of `out`: pixel-major [M][pitch], or 16-channel fp32 slabs [pitch / 16][slabM][16]
 };
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
                       const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr, bool x2 = false, const TcAccum* acc = nullptr);
@@ -78,6 +79,7 @@ struct TcTempArgs {
   float* outF = nullptr;
   int outF_pitch = 0, outF_off = 0, outF_planar = 0;
   int outF_blk = 0, outF_blk_stride = 0;   // planar outF: column n -> channel outF_off + (n / blk) * stride + n % blk
+  long long outF_slabM = 0;                // non-planar outF: 16-channel fp32 slabs instead of pixel-major rows
   long long m_limit = 0;             // > 0: rows >= m_limit do not exist (pointwise mode over pseudo-frames)
   float* z = nullptr;
   float* sbuf = nullptr;

@@ -71,6 +71,7 @@ struct Params {
   // Such a launch produces acc_n channels in groups of 32: `ngroups` weight images resident, every tile visited once per group.
   float* accF;
   int acc_pitch, acc_off, acc_n, ngroups;
+  long long acc_slabM;   // layout of accF: 0 pixel-major, else 16-channel fp32 slabs of acc_slabM pixels
   int* err;
   long long* dbg;        // SELFC_TC_DBG=1 (+ -DSELFC_TC_TIMING): CTA 0's barrier-wait cycles
 };
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
             }
             if (X2 && p.accF != nullptr) {
               if (ok) {
-                float* of = p.accF + ((size_t)((size_t)n * p.h + y) * p.w + x) * p.acc_pitch + p.acc_off + 32 * grp + n0;
+                float* of = p.accF + dense_off((long long)((size_t)((size_t)n * p.h + y) * p.w + x), p.acc_off + 32 * grp + n0, p.acc_pitch, p.acc_slabM);
   #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
                   if (32 * grp + n0 + j < p.acc_n) {
@@ -694,6 +695,7 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   SELFC_CHECK_ARG(acc == nullptr || (x2 && w2 == nullptr && acc->out != nullptr && acc->pitch % 4 == 0 && acc->off % 4 == 0 && acc->n % 4 == 0 &&
                                      acc->n >= 4 && acc->ngroups >= 1 && acc->ngroups <= 6 && acc->n <= 32 * acc->ngroups && aligned16(acc->out)),
                   "conv3x3_tc: the accumulate epilogue belongs to a single (hi, lo) problem with 16-byte aligned fp32 rows");
+  SELFC_CHECK_ARG(acc == nullptr || acc->slabM == 0 || (acc->off % 16 == 0 && acc->pitch % 16 == 0), "conv3x3_tc: slab-planar accumulate buffer");
   SELFC_CHECK_ARG(w.img != nullptr && cin == w.cin_buf, "conv3x3_tc: weights not packed for cin=%d", cin);
   SELFC_CHECK_ARG(!x2 || (w.img_x2 != nullptr && (w2 == nullptr || w2->img_x2 != nullptr) && ((uintptr_t)buf & 63) == 0 &&
                           (buf2 == nullptr || ((uintptr_t)buf2 & 63) == 0)),
@@ -795,7 +797,7 @@ int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int
   p.ntiles = p.tiles_x * p.tiles_y * N;
   p.err = tc::err_flag_for_device();
   p.ngroups = ngroups;
-  if (acc != nullptr) { p.accF = acc->out; p.acc_pitch = acc->pitch; p.acc_off = acc->off; p.acc_n = acc->n; }
+  if (acc != nullptr) { p.accF = acc->out; p.acc_pitch = acc->pitch; p.acc_off = acc->off; p.acc_n = acc->n; p.acc_slabM = acc->slabM; }
   if (p.ntiles == 0) return 0;
   p.rev = tc::next_direction();
   if (tc::debug_slots()) p.dbg = tc::debug_next_slot(9000000 + (dual ? 100000 : 0) + nks);

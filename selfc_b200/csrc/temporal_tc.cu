@@ -58,6 +58,7 @@ struct Params {
   float* outF;
   int outF_pitch, outF_off, outF_planar;   // outF_planar: write quads [C/4][m_limit][4] instead of [M][pitch]; 2: the quads are fp16
   int outF_blk, outF_blk_stride;           // planar: column n -> channel outF_off + (n / blk) * stride + n % blk (blk = 0: outF_off + n)
+  long long outF_slabM;                    // non-planar outF as 16-channel fp32 slabs (0: pixel-major)
   float* z;
   float* sbuf;
   __nv_bfloat16* copyA;
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
                 for (int j = 0; j < 16; j += 4)
                   store4(p.outF + quad_off((size_t)p.m_limit, (ncol + j) / 4, m), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
               } else if (p.outF) {
-                float* o = p.outF + m * p.outF_pitch + p.outF_off + n0;
+                float* o = p.outF + dense_off((long long)m, p.outF_off + n0, p.outF_pitch, p.outF_slabM);
                 if (n0 + 16 <= p.cout && ((p.outF_pitch | p.outF_off) & 3) == 0) {
 #pragma unroll
                   for (int j = 0; j < 16; j += 4) store4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
@@ -799,7 +800,8 @@ int launch_temporal_tc(const TcTempW& w, const TcTempArgs& a, cudaStream_t st, c
   p.outT = a.outT; p.outT_pitch = a.outT_pitch; p.outT_off = a.outT_off;
   p.outT_slabM = a.outT_slabM; p.copy_slabM = a.copy_slabM;
   p.outF = a.outF; p.outF_pitch = a.outF_pitch; p.outF_off = a.outF_off; p.outF_planar = a.outF_planar;
-  p.outF_blk = a.outF_blk; p.outF_blk_stride = a.outF_blk_stride;
+  p.outF_blk = a.outF_blk; p.outF_blk_stride = a.outF_blk_stride; p.outF_slabM = a.outF_slabM;
+  SELFC_CHECK_ARG(a.outF_slabM == 0 || (a.outF_off % 16 == 0 && a.outF_pitch % 16 == 0 && w.cout % 16 == 0), "temporal_tc: slab-planar fp32 output");
   p.m_limit = a.m_limit > 0 ? a.m_limit : (long long)BT * a.hw;
   p.z = a.z; p.sbuf = a.sbuf;
   p.copyA = a.copyA; p.copyA_pitch = a.copyA_pitch; p.copyB = a.copyB; p.copyB_pitch = a.copyB_pitch; p.copy_pad = a.copy_pad;

@@ -60,6 +60,23 @@ static float* train_zero_bias(const selfc_ctx* cctx) {      // dgrad has no bias
   return ctx->train_zero_bias;
 }
 
+// BF16X3 training knobs.  When both the weight and the input gradients run on the tensor cores, the gradient of a dense buffer is kept
+// SLAB-PLANAR in fp32 ([pitch / 16][M][16], common.cuh's slab layout with a 4-byte element): the accumulate epilogue of the
+// input-gradient launches (thread = pixel, 16 channels = 64 contiguous bytes, consecutive lanes on consecutive rows) and the plane
+// builder then move 2 KB runs per warp instead of 32 scattered 64-byte pieces.  Otherwise it is pixel-major [M][pitch] as in FP32 mode.
+static bool env_on(const char* name, int& cache) {
+  if (cache < 0) {
+    const char* e = getenv(name);
+    cache = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return cache == 1;
+}
+static bool wgrad_tc_on() { static int c = -1; return env_on("SELFC_WGRAD_TC", c); }
+static bool dgrad_tc_on() { static int c = -1; return env_on("SELFC_DGRAD_TC", c); }
+static long long grad_slab(const selfc_ctx* ctx, const Dims& d) {
+  return ctx->mode == SELFC_MODE_BF16X3 && wgrad_tc_on() && dgrad_tc_on() ? d.M() : 0;
+}
+
 // ---- dgrad weights: wd[(tap' * cout4 + n)][c] = w[((taps-1-tap') * cin_buf + c)][n]   (w = forward pack [taps*cin_buf][np]) ----
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, int taps, int cin_buf, int np, int cout,
                                   int cout4, int npd) {
@@ -78,19 +95,20 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict
 // E: element type of the forward dense buffer y (float: pixel-major, FP32 mode; bfx2: slab-planar (hi, lo) pairs, BF16X3 mode)
 // gslab (optional): the masked gradient also as (hi, lo) slabs [2][M][16 | 16] -- the input of the tensor-core input-gradient launches
 template <typename E>
-__global__ void lrelu_bwd_kernel(float* __restrict__ g, const E* __restrict__ y, int pitch, long long slabM, int off, long long M,
+__global__ void lrelu_bwd_kernel(float* __restrict__ g, long long gslabM, const E* __restrict__ y, int pitch, long long slabM, int off, long long M,
                                  bfx2* __restrict__ gslab = nullptr) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long m = idx >> 3;
   const int c = (int)(idx & 7) * 4;
   if (m >= M) return;
-  float4 gv = load4(g + m * pitch + off + c);
+  float* gp = g + dense_off(m, off + c, pitch, gslabM);
+  float4 gv = load4(gp);
   const float4 yv = load4(y + dense_off(m, off + c, pitch, slabM));
   gv.x *= yv.x > 0.f ? 1.f : 0.2f;
   gv.y *= yv.y > 0.f ? 1.f : 0.2f;
   gv.z *= yv.z > 0.f ? 1.f : 0.2f;
   gv.w *= yv.w > 0.f ? 1.f : 0.2f;
-  store4(g + m * pitch + off + c, gv);
+  store4(gp, gv);
   if (gslab != nullptr) store4(gslab + dense_off(m, c, 32, M), gv);
 }
 
@@ -341,12 +359,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
   WgGeom geom{};
   void* planes = nullptr;
   if constexpr (std::is_same<E, bfx2>::value) {
-    static int tc_on = -1;
-    if (tc_on < 0) {
-      const char* e = getenv("SELFC_WGRAD_TC");
-      tc_on = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    if (tc_on && gparams != nullptr) {
+    if (wgrad_tc_on() && gparams != nullptr) {
       geom = wg_geometry(d);
       planes = train_wg_planes(ctx, d, geom, st);
       SELFC_CHECK_ARG(planes != nullptr, "out of device memory (weight-gradient planes, %zu bytes)", wg_plane_bytes(geom));
@@ -359,18 +372,14 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
   bool dg_tc = false;
   bfx2* gslab = nullptr;
   if constexpr (std::is_same<E, bfx2>::value) {
-    static int dg_on = -1;
-    if (dg_on < 0) {
-      const char* e = getenv("SELFC_DGRAD_TC");
-      dg_on = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    if (dg_on) {
+    if (dgrad_tc_on()) {
       SELFC_TRY(ensure_dgrad_images(ctx, W, zero_bias, st));
       gslab = train_gslab(ctx, M);
       SELFC_CHECK_ARG(gslab != nullptr, "out of device memory (gradient slabs)");
       dg_tc = true;
     }
   }
+  const long long gslabM = grad_slab(ctx, d);         // layout of gbuf (see grad_slab); implies wg_tc || gparams == nullptr, and dg_tc
   SELFC_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)M * pitch * sizeof(float), st));
   for (int k = 4; k >= 0; --k) {
     const int taps = k < 4 ? 9 : 3;
@@ -384,7 +393,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
     const int g_pitch = k < 4 ? pitch : gy_pitch;
     const int g_off = k < 4 ? slot : 0;
     if (k < 4) {
-      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, buf, pitch, slabM, slot, M, dg_tc ? gslab : nullptr);
+      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, gslabM, buf, pitch, slabM, slot, M, dg_tc ? gslab : nullptr);
       SELFC_LAUNCH_CHECK("lrelu_bwd_kernel");
     }
     float* wd = scratch;
@@ -395,9 +404,10 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       SELFC_CUDA(cudaMemsetAsync(dw, 0, dw_floats * sizeof(float), st));
       if (wg_tc) {
         const int nb = k < 4 ? kGrowth : (cout + 15) & ~15;
-        SELFC_TRY(launch_wg_planes_grad(g, g_pitch, g_off, cout, nb, k == 4, d, geom, planes, st));
+        SELFC_TRY(launch_wg_planes_grad(g, g_pitch, g_off, k < 4 ? gslabM : 0, cout, nb, k == 4, d, geom, planes, st));
         SELFC_TRY(launch_wgrad_tc(planes, geom, cin, cout, nb, taps, k == 4, dw, W.np[k], st));
       } else {
+        SELFC_CHECK_ARG(gslabM == 0, "the fp32-FMA weight gradient reads a pixel-major gradient buffer");
         const int splits = wgrad_splits(M, (taps + 1) * cdiv(cout, 32) * cdiv(cin, WG_C));
         dim3 grid((taps + 1) * cdiv(cout, 32), cdiv(cin, WG_C), splits);
         wgrad_kernel<E><<<grid, 256, 0, st>>>(buf, pitch, slabM, cin, g, g_pitch, g_off, cout, dw, W.np[k], taps, tap_mode, d.B * d.T, d.T, d.h, d.w);
@@ -420,7 +430,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
         TcTempArgs t;
         t.in = reinterpret_cast<const __nv_bfloat16*>(gslab); t.in_pitch = nb; t.B = d.B; t.T = d.T; t.hw = (int)d.hw(); t.in_slabM = M;
         t.epi = EPI_STORE; t.act = 0;
-        t.outF = gbuf; t.outF_pitch = pitch; t.outF_off = W.dg5_c0[gI];
+        t.outF = gbuf; t.outF_pitch = pitch; t.outF_off = W.dg5_c0[gI]; t.outF_slabM = gslabM;
         SELFC_TRY(launch_temporal_tc(W.dg5[gI], t, st));
       }
       continue;
@@ -434,7 +444,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       tw.cin_buf = 32;
       tw.bias = zero_bias;
       TcAccum acc;
-      acc.out = gbuf; acc.pitch = pitch; acc.off = 0; acc.n = cin; acc.ngroups = cdiv(cin, 32);
+      acc.out = gbuf; acc.pitch = pitch; acc.off = 0; acc.n = cin; acc.ngroups = cdiv(cin, 32); acc.slabM = gslabM;
       SELFC_TRY(launch_conv3x3_tc(tw, reinterpret_cast<__nv_bfloat16*>(gslab), M, 32, 0, d.B * d.T, d.h, d.w, st, nullptr, nullptr, true, &acc));
       continue;
     }
@@ -499,10 +509,10 @@ __global__ void cpl_fwd_pre_kernel(float* __restrict__ gz, const float* __restri
 }
 
 // acc[m][0:4] (+)= src[m][0:4]  (first channels of a dense-buffer gradient); init: overwrite instead of add
-__global__ void take4_kernel(float* __restrict__ acc, const float* __restrict__ src, int pitch, int init, float sign, long long M) {
+__global__ void take4_kernel(float* __restrict__ acc, const float* __restrict__ src, int pitch, long long sslabM, int init, float sign, long long M) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
-  const float4 v = load4(src + m * pitch);
+  const float4 v = load4(src + dense_off(m, 0, pitch, sslabM));
   float4 a = init ? make_float4(0.f, 0.f, 0.f, 0.f) : load4(acc + m * 4);
   a.x += sign * v.x; a.y += sign * v.y; a.z += sign * v.z; a.w = 0.f;
   store4(acc + m * 4, a);
@@ -523,26 +533,26 @@ __global__ void cpl_quad0_kernel(float* __restrict__ gz, const float* __restrict
 }
 
 // gz[x2 part] += gX[m][0:48]   (forward dir, after F's backward)
-__global__ void cpl_add_hf_kernel(float* __restrict__ gz, const float* __restrict__ gX, int pitch, long long M) {
+__global__ void cpl_add_hf_kernel(float* __restrict__ gz, const float* __restrict__ gX, int pitch, long long xslabM, long long M) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * kSQuads) return;
   const long long m = idx / kSQuads;
   const int q = (int)(idx - m * kSQuads);
   float4 g = load4(gz + quad_off((size_t)M, 1 + q, (size_t)m));
-  const float4 a = load4(gX + m * pitch + 4 * q);
+  const float4 a = load4(gX + dense_off(m, 4 * q, pitch, xslabM));
   g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
   store4(gz + quad_off((size_t)M, 1 + q, (size_t)m), g);
 }
 
 // reverse dir: t = gy2 + gXF;  gz[x2 part] = t*e^-s;  gyG = -t*e^-s;  gyH = -t*y2*(1-s^2)/2
-__global__ void cpl_rev_pre_kernel(float* __restrict__ gz, const float* __restrict__ gXF, int pitchF, const float* __restrict__ zout,
+__global__ void cpl_rev_pre_kernel(float* __restrict__ gz, const float* __restrict__ gXF, int pitchF, long long fslabM, const float* __restrict__ zout,
                                    const float* __restrict__ sbuf, float* __restrict__ gyG, float* __restrict__ gyH, long long M) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * kSQuads) return;
   const long long m = idx / kSQuads;
   const int q = (int)(idx - m * kSQuads);
   const float4 g = load4(gz + quad_off((size_t)M, 1 + q, (size_t)m));
-  const float4 f = load4(gXF + m * pitchF + 4 * q);
+  const float4 f = load4(gXF + dense_off(m, 4 * q, pitchF, fslabM));
   const float4 y = load4(zout + quad_off((size_t)M, 1 + q, (size_t)m));
   const float4 s = load4(sbuf + quad_off((size_t)M, q, (size_t)m));
   const float tt[4] = {g.x + f.x, g.y + f.y, g.z + f.z, g.w + f.w}, yy[4] = {y.x, y.y, y.z, y.w}, ss[4] = {s.x, s.y, s.z, s.w};
@@ -588,6 +598,7 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
   float* const* gG = gparams ? gparams + 10 : nullptr;
   float* const* gH = gparams ? gparams + 20 : nullptr;
   const int nb = cdiv(M, 256), nbq = cdiv(M * kSQuads, 256), nbx = cdiv(M * (xp3 / 4), 256);
+  const long long gsl = grad_slab(ctx, d);           // layout of the dense-buffer gradients dense_block_backward leaves in gdense
   // recompute the block's forward from its input state
   SELFC_CUDA(cudaMemcpyAsync(z, zin, (size_t)M * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
   if (!rev) {
@@ -612,24 +623,24 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
     cpl_fwd_pre_kernel<<<nbq, 256, 0, st>>>(gz, zin, sbuf, gyG, gyH, M);
     SELFC_LAUNCH_CHECK("cpl_fwd_pre_kernel");
     SELFC_TRY(dense_block_backward<E>(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
-    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 1, 1.0f, M);
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, gsl, 1, 1.0f, M);
     SELFC_TRY(dense_block_backward<E>(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
-    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 0, 1.0f, M);
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, gsl, 0, 1.0f, M);
     cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, acc, gyF, 1.0f, M);             // gx1 = gy1 + G^T + H^T; F's output gradient = the same
     SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
     SELFC_TRY(dense_block_backward<E>(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
-    cpl_add_hf_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, M);
+    cpl_add_hf_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, gsl, M);
     SELFC_LAUNCH_CHECK("cpl_add_hf_kernel");
   } else {
     cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, nullptr, gyF, -1.0f, M);        // y1 = x1 - F(y2): F's output gradient = -gy1
     SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
     SELFC_TRY(dense_block_backward<E>(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
-    cpl_rev_pre_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, z, sbuf, gyG, gyH, M);
+    cpl_rev_pre_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, gsl, z, sbuf, gyG, gyH, M);
     SELFC_LAUNCH_CHECK("cpl_rev_pre_kernel");
     SELFC_TRY(dense_block_backward<E>(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
-    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 1, 1.0f, M);
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, gsl, 1, 1.0f, M);
     SELFC_TRY(dense_block_backward<E>(ctx, H, hbuf, ws.gpitch, gyH, kHF, gdense, scratch, gH, d, st));
-    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, 0, 1.0f, M);
+    take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, gsl, 0, 1.0f, M);
     cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, acc, nullptr, 1.0f, M);
     SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
   }
@@ -1159,13 +1170,13 @@ __global__ void loss_back_fa_bwd_kernel(const float* __restrict__ x, const float
 
 // dst[m][doff + c] = src[m][soff + c], c < ncol (ncol % 4 == 0)
 __global__ void copy_cols_kernel(float* __restrict__ dst, int dpitch, int doff, const float* __restrict__ src, int spitch, int soff, int ncol,
-                                 long long M) {
+                                 long long M, long long sslabM = 0) {
   const int per = ncol / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * per) return;
   const long long m = idx / per;
   const int c = (int)(idx - m * per) * 4;
-  store4(dst + m * dpitch + doff + c, load4(src + m * spitch + soff + c));
+  store4(dst + m * dpitch + doff + c, load4(src + dense_off(m, soff + c, spitch, sslabM)));
 }
 
 // X slot of a dense buffer (either layout) <- fp32 pixel-major [M][spitch] columns [0, ncol)
@@ -1252,9 +1263,9 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
     SELFC_TRY(ga_backward(ctx, ctx->ga[i], feat, gcur, gnext, grads ? grads + ga_first[i] : nullptr, wsp, ws, tp, tape, d, st));
     SELFC_TRY(dense_block_backward<E>(ctx, W, stpbuf, pitch, gnext, kStpC, gdense, scratch, grads ? grads + stp_first[i] : nullptr, d, st));
     if (i > 0) {
-      copy_cols_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(gcur, kStpC, 0, gdense, pitch, 0, kStpC, M);
+      copy_cols_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(gcur, kStpC, 0, gdense, pitch, 0, kStpC, M, grad_slab(ctx, d));
     } else {
-      copy_cols_kernel<<<cdiv(M, 256), 256, 0, st>>>(glr, 4, 0, gdense, pitch, 0, 4, M);
+      copy_cols_kernel<<<cdiv(M, 256), 256, 0, st>>>(glr, 4, 0, gdense, pitch, 0, 4, M, grad_slab(ctx, d));
     }
     SELFC_LAUNCH_CHECK("copy_cols_kernel");
   }
@@ -1358,7 +1369,7 @@ int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const f
     SELFC_TRY(dense_convs<float>(ctx, *W, buf, pitch, d, st));
     SELFC_TRY(dense_block_backward<float>(ctx, *W, buf, pitch, gyd, cout4, gbuf, scratch, gparams, d, st));
   }
-  return launch_dense_to_nchw<float>(gbuf, pitch, 0, 0, gx, W->cin, d.M(), d.hw(), st);
+  return launch_dense_to_nchw<float>(gbuf, pitch, grad_slab(ctx, d), 0, gx, W->cin, d.M(), d.hw(), st);
 }
 
 

@@ -217,22 +217,22 @@ __global__ void __launch_bounds__(256) wg_planes_act_kernel(const __nv_bfloat16*
 // kx * 32 + n hold the gradient written at P + (kx - 1), i.e. GT_kx[n][P] = g[n][P - (kx-1)] (the shifted positions are padding
 // columns of the same row, so the three copies never collide with real pixels of a neighbouring row); conv5 (ncopies = 1): rows
 // 96 + n at P, rows >= ncols zero.  The two forms use disjoint rows: each row is always written at the same set of positions.
-__global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __restrict__ gsrc, int pitch, int off, int ncols, int nb, int ncopies,
-                                                             long long M, __nv_bfloat16* __restrict__ gt, const WgGeom g) {
+__global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __restrict__ gsrc, int pitch, int off, long long sslabM, int ncols, int nb,
+                                                             int ncopies, long long M, __nv_bfloat16* __restrict__ gt, const WgGeom g) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const long long P = plane_index(m, g);
-  const float* src = gsrc + m * pitch + off;
   const int row0 = ncopies == 3 ? 0 : kWgSpatialRows;
   const bool vec = ((pitch | off) & 3) == 0;
   for (int n0 = 0; n0 < nb; n0 += 4) {
+    const float* src = gsrc + dense_off(m, off + n0, pitch, sslabM);      // 4-channel groups never straddle a 16-channel slab
     float v4[4];
     if (vec && n0 + 4 <= ncols) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(src + n0));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src));
       v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
     } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v4[e] = n0 + e < ncols ? __ldg(src + n0 + e) : 0.f;
+      for (int e = 0; e < 4; ++e) v4[e] = n0 + e < ncols ? __ldg(src + e) : 0.f;
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -270,12 +270,12 @@ int launch_wg_planes_act(const bfx2* buf, int pitch, const Dims& d, const WgGeom
   return 0;
 }
 
-int launch_wg_planes_grad(const float* gsrc, int pitch, int off, int ncols, int nb, bool temporal, const Dims& d, const WgGeom& g,
-                          void* planes, cudaStream_t st) {
+int launch_wg_planes_grad(const float* gsrc, int pitch, int off, long long sslabM, int ncols, int nb, bool temporal, const Dims& d,
+                          const WgGeom& g, void* planes, cudaStream_t st) {
   SELFC_CHECK_ARG(nb % 16 == 0 && nb <= kWgGradRows - kWgSpatialRows && ncols <= nb && (temporal || nb == 32),
                   "wgrad planes: %d gradient columns", ncols);
   __nv_bfloat16* gt = reinterpret_cast<__nv_bfloat16*>(planes) + (size_t)2 * kWgRows * g.Pa;
-  wg::wg_planes_grad_kernel<<<cdiv(d.M(), 256), 256, 0, st>>>(gsrc, pitch, off, ncols, nb, temporal ? 1 : 3, d.M(), gt, g);
+  wg::wg_planes_grad_kernel<<<cdiv(d.M(), 256), 256, 0, st>>>(gsrc, pitch, off, sslabM, ncols, nb, temporal ? 1 : 3, d.M(), gt, g);
   SELFC_LAUNCH_CHECK("wg_planes_grad_kernel");
   return 0;
 }

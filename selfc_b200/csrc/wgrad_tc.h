@@ -21,9 +21,9 @@ size_t wg_plane_bytes(const WgGeom& g);      // [2][193][Pa] + [2][160][Pa] bf16
 
 // activations of a whole dense buffer (slab-planar (hi, lo) pairs, `pitch` channels) -> AT planes
 int launch_wg_planes_act(const bfx2* buf, int pitch, const Dims& d, const WgGeom& g, void* planes, cudaStream_t st);
-// output gradient g[m * pitch + off + n], n < ncols (fp32, pixel-major) -> GT rows [0, nb), rows >= ncols zero
-int launch_wg_planes_grad(const float* gsrc, int pitch, int off, int ncols, int nb, bool temporal, const Dims& d, const WgGeom& g,
-                          void* planes, cudaStream_t st);
+// output gradient channels [off, off + ncols) of an fp32 buffer (pixel-major, or 16-channel slabs when sslabM != 0) -> GT rows, rows >= ncols zero
+int launch_wg_planes_grad(const float* gsrc, int pitch, int off, long long sslabM, int ncols, int nb, bool temporal, const Dims& d,
+                          const WgGeom& g, void* planes, cudaStream_t st);
 // dw[(tap * cin + c) * np + n] += sum_p in[p + shift(tap)][c] * g[p][n]; dw[taps * cin * np + n] += sum_p g[p][n]   (dw zeroed by the caller)
 int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, int taps, bool temporal, float* dw, int np, cudaStream_t st);
 
