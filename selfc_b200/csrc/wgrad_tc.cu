@@ -219,30 +219,31 @@ __global__ void __launch_bounds__(256) wg_planes_act_kernel(const __nv_bfloat16*
 // 96 + n at P, rows >= ncols zero.  The two forms use disjoint rows: each row is always written at the same set of positions.
 __global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __restrict__ gsrc, int pitch, int off, long long sslabM, int ncols, int nb,
                                                              int ncopies, long long M, __nv_bfloat16* __restrict__ gt, const WgGeom g) {
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
+  // one thread per (4-channel group, pixel), pixels fastest: a warp writes 64 contiguous bytes per plane row and store instruction,
+  // and the launch has nb / 4 times the threads of a thread-per-pixel form (at 50 K pixels that form left the SMs a third full)
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * (nb / 4)) return;
+  const int n0 = (int)(idx / M) * 4;
+  const long long m = idx - (long long)(n0 / 4) * M;
   const long long P = plane_index(m, g);
   const int row0 = ncopies == 3 ? 0 : kWgSpatialRows;
-  const bool vec = ((pitch | off) & 3) == 0;
-  for (int n0 = 0; n0 < nb; n0 += 4) {
-    const float* src = gsrc + dense_off(m, off + n0, pitch, sslabM);      // 4-channel groups never straddle a 16-channel slab
-    float v4[4];
-    if (vec && n0 + 4 <= ncols) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(src));
-      v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
-    } else {
+  const float* src = gsrc + dense_off(m, off + n0, pitch, sslabM);      // 4-channel groups never straddle a 16-channel slab
+  float v4[4];
+  if (((pitch | off) & 3) == 0 && n0 + 4 <= ncols) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+    v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
+  } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v4[e] = n0 + e < ncols ? __ldg(src + e) : 0.f;
-    }
+    for (int e = 0; e < 4; ++e) v4[e] = n0 + e < ncols ? __ldg(src + e) : 0.f;
+  }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __nv_bfloat16 h, l;
-      x2_split(v4[e], h, l);
-      for (int kx = 0; kx < ncopies; ++kx) {
-        __nv_bfloat16* hi = gt + (size_t)(row0 + kx * nb + n0 + e) * g.Pa + P + (ncopies == 3 ? kx - 1 : 0);
-        hi[0] = h;
-        hi[(size_t)kWgGradRows * g.Pa] = l;
-      }
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat16 h, l;
+    x2_split(v4[e], h, l);
+    for (int kx = 0; kx < ncopies; ++kx) {
+      __nv_bfloat16* hi = gt + (size_t)(row0 + kx * nb + n0 + e) * g.Pa + P + (ncopies == 3 ? kx - 1 : 0);
+      hi[0] = h;
+      hi[(size_t)kWgGradRows * g.Pa] = l;
     }
   }
 }
@@ -275,7 +276,7 @@ int launch_wg_planes_grad(const float* gsrc, int pitch, int off, long long sslab
   SELFC_CHECK_ARG(nb % 16 == 0 && nb <= kWgGradRows - kWgSpatialRows && ncols <= nb && (temporal || nb == 32),
                   "wgrad planes: %d gradient columns", ncols);
   __nv_bfloat16* gt = reinterpret_cast<__nv_bfloat16*>(planes) + (size_t)2 * kWgRows * g.Pa;
-  wg::wg_planes_grad_kernel<<<cdiv(d.M(), 256), 256, 0, st>>>(gsrc, pitch, off, sslabM, ncols, nb, temporal ? 1 : 3, d.M(), gt, g);
+  wg::wg_planes_grad_kernel<<<cdiv(d.M() * (nb / 4), 256), 256, 0, st>>>(gsrc, pitch, off, sslabM, ncols, nb, temporal ? 1 : 3, d.M(), gt, g);
   SELFC_LAUNCH_CHECK("wg_planes_grad_kernel");
   return 0;
 }

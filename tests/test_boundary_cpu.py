@@ -177,3 +177,19 @@ def test_dense_fused_schedules_keep_every_row_alive_until_its_last_reader():
             rows = [rr for j in order for g, rr in reads(j, s - lag[j]) if g == -1]
             live = max(live, max(rows) - min(rows) + 1)
         assert live + 1 <= nxr, (sch, live, nxr)
+
+
+def test_precision_modes_match_the_header():
+    """The three precision modes of the C-ABI (include/selfc_b200.h) and the strings the host side accepts for them."""
+    import re
+    from selfc_b200 import _lib
+    from selfc_b200.engine import parse_mode
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(here, "include", "selfc_b200.h")).read()
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (SELFC_MODE_\w+) (\d+)", hdr)}
+    assert consts == {"SELFC_MODE_FP32": _lib.MODE_FP32, "SELFC_MODE_BF16": _lib.MODE_BF16, "SELFC_MODE_BF16X3": _lib.MODE_BF16X3}
+    assert parse_mode("fp32") == parse_mode(None) == _lib.MODE_FP32
+    assert parse_mode("bf16") == _lib.MODE_BF16
+    assert parse_mode("bf16x3") == parse_mode("fp32_tc") == _lib.MODE_BF16X3
+    with pytest.raises(ValueError):
+        parse_mode("tf32")
