@@ -475,7 +475,8 @@ def measure_train(dev, world: int, rank: int, steps: int, warmup: int, b: int, t
 
 TRAIN_MODE_WHAT = {
     "fp32": "fp32-FMA kernels",
-    "bf16x3": "forward and recomputed forward on the tcgen05 kernels with (hi, lo) bf16 operands, gradients fp32",
+    "bf16x3": "forward, recomputed forward, input gradients and weight gradients on the tcgen05 kernels with (hi, lo) bf16 operands; fp32 master "
+              "weights, gradient buffers and optimiser",
 }
 
 
