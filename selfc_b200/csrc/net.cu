@@ -570,6 +570,8 @@ int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_
   SELFC_CHECK_ARG((long long)B * T * (H / 4) * (W / 4) < (1ll << 31) / 8, "clip batch too large for 32-bit tile indices");
   *ws = make_workspace(ctx, B, T, H / 4, W / 4);
   SELFC_CHECK_ARG(workspace != nullptr && aligned16(workspace), "workspace null or misaligned");
+  // BF16X3 mode addresses the two halves of an element from the low bits of its handle (common.cuh: 64-byte rows)
+  SELFC_CHECK_ARG(ctx->mode != SELFC_MODE_BF16X3 || (reinterpret_cast<uintptr_t>(workspace) & 63u) == 0, "BF16X3 mode needs a 64-byte aligned workspace");
   if (workspace_bytes < ws->total) {
     set_error("workspace too small: %zu < %zu bytes", workspace_bytes, ws->total);
     return SELFC_E_STATE;

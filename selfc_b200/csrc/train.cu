@@ -405,7 +405,7 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       if (wg_tc) {
         const int nb = k < 4 ? kGrowth : (cout + 15) & ~15;
         SELFC_TRY(launch_wg_planes_grad(g, g_pitch, g_off, k < 4 ? gslabM : 0, cout, nb, k == 4, d, geom, planes, st));
-        SELFC_TRY(launch_wgrad_tc(planes, geom, cin, cout, nb, taps, k == 4, dw, W.np[k], st));
+        SELFC_TRY(launch_wgrad_tc(planes, geom, cin, cout, nb, k == 4 ? WG_TEMPORAL : WG_SPATIAL, dw, W.np[k], st));
       } else {
         SELFC_CHECK_ARG(gslabM == 0, "the fp32-FMA weight gradient reads a pixel-major gradient buffer");
         const int splits = wgrad_splits(M, (taps + 1) * cdiv(cout, 32) * cdiv(cin, WG_C));
@@ -704,15 +704,32 @@ __global__ void lrelu_fwd_kernel(const float* __restrict__ x, float* __restrict_
 
 // Backward of a pointwise (1x1x1) conv y = W.x + b:  g_in = W^T g (stored or accumulated),  dW += g (x) in,  db += sum g.
 // wf: forward pack [cin][np]; gw / gb: reference layouts [cout][cin] / [cout], accumulated into.
-static int pointwise_backward(const float* wf, int cin, int np, int cout, const float* in, int in_pitch, const float* g, int g_pitch,
-                              float* gin, int gin_pitch, bool accumulate, float* gw, float* gb, float* scratch, float* zero_bias,
+static int pointwise_backward(const selfc_ctx* ctx, const float* wf, int cin, int np, int cout, const float* in, int in_pitch, const float* g,
+                              int g_pitch, float* gin, int gin_pitch, bool accumulate, float* gw, float* gb, float* scratch, float* zero_bias,
                               const Dims& d, cudaStream_t st) {
   const long long M = d.M();
   const int cout4 = (cout + 3) & ~3;
   const int npd = (cin + 31) & ~31;
   float* wd = scratch;
   float* dw = scratch + (size_t)cout4 * npd;
-  if (gw != nullptr) {
+  if (gw != nullptr && ctx->mode == SELFC_MODE_BF16X3 && wgrad_tc_on() && cin % 4 == 0 && in_pitch % 4 == 0 && cin <= kWgRows - 1) {
+    // BF16X3 mode: the pointwise form of the tensor-core weight-gradient kernel (one unshifted tile per stage), 64 output channels per
+    // launch over the same activation planes
+    const WgGeom geom = wg_geometry(d);
+    void* planes = train_wg_planes(ctx, d, geom, st);
+    SELFC_CHECK_ARG(planes != nullptr, "out of device memory (weight-gradient planes, %zu bytes)", wg_plane_bytes(geom));
+    SELFC_CUDA(cudaMemsetAsync(dw, 0, (size_t)(cin + 1) * np * sizeof(float), st));
+    SELFC_TRY(launch_wg_planes_act_f32(in, in_pitch, cin, d, geom, planes, st));
+    for (int n0 = 0; n0 < cout; n0 += 64) {
+      const int ncols = cout - n0 < 64 ? cout - n0 : 64;
+      const int nb = (ncols + 15) & ~15;
+      SELFC_TRY(launch_wg_planes_grad(g, g_pitch, n0, 0, ncols, nb, true, d, geom, planes, st));
+      SELFC_TRY(launch_wgrad_tc(planes, geom, cin, ncols, nb, WG_POINT, dw, np, st, n0));
+    }
+    const long long total = (long long)cout * cin;
+    wgrad_unpack_kernel<<<cdiv(total, 256), 256, 0, st>>>(dw, gw, gb, cout, cin, 1, cin, cin, cin, np);
+    SELFC_LAUNCH_CHECK("wgrad_unpack_kernel");
+  } else if (gw != nullptr) {
     SELFC_CUDA(cudaMemsetAsync(dw, 0, (size_t)(cin + 1) * np * sizeof(float), st));
     const int splits = wgrad_splits(M, 2 * cdiv(cout, 32) * cdiv(cin, WG_C));
     dim3 grid(2 * cdiv(cout, 32), cdiv(cin, WG_C), splits);
@@ -834,15 +851,15 @@ int head_sampler_backward(const selfc_ctx* ctx, const float* feat, const float* 
   gmm_sample_bwd_kernel<<<cdiv(M, 4), 128, 0, st>>>(params, eps, seed, offset, gz, d.T, d.hw(), M);
   SELFC_LAUNCH_CHECK("gmm_sample_bwd_kernel");
   // 256 -> 720
-  SELFC_TRY(pointwise_backward(hd.w[2], 256, hd.np[2], 720, h2, 256, params, 720, gh2, 256, false, gparams ? gparams[4] : nullptr,
+  SELFC_TRY(pointwise_backward(ctx, hd.w[2], 256, hd.np[2], 720, h2, 256, params, 720, gh2, 256, false, gparams ? gparams[4] : nullptr,
                                gparams ? gparams[5] : nullptr, scratch, zb, d, st));
   lrelu_bwd_full_kernel<<<cdiv(M * 64, 256), 256, 0, st>>>(gh2, h2, M * 64);
   // 128 -> 256
-  SELFC_TRY(pointwise_backward(hd.w[1], 128, hd.np[1], 256, h1, 128, gh2, 256, gh1, 128, false, gparams ? gparams[2] : nullptr,
+  SELFC_TRY(pointwise_backward(ctx, hd.w[1], 128, hd.np[1], 256, h1, 128, gh2, 256, gh1, 128, false, gparams ? gparams[2] : nullptr,
                                gparams ? gparams[3] : nullptr, scratch, zb, d, st));
   lrelu_bwd_full_kernel<<<cdiv(M * 32, 256), 256, 0, st>>>(gh1, h1, M * 32);
   // 64 -> 128
-  SELFC_TRY(pointwise_backward(hd.w[0], 64, hd.np[0], 128, fact, 64, gh1, 128, gfeat, 64, false, gparams ? gparams[0] : nullptr,
+  SELFC_TRY(pointwise_backward(ctx, hd.w[0], 64, hd.np[0], 128, fact, 64, gh1, 128, gfeat, 64, false, gparams ? gparams[0] : nullptr,
                                gparams ? gparams[1] : nullptr, scratch, zb, d, st));
   lrelu_bwd_full_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(gfeat, fact, M * 16);
   SELFC_LAUNCH_CHECK("lrelu_bwd_full_kernel");
@@ -1072,7 +1089,7 @@ int ga_backward(const selfc_ctx* ctx, const GaW& g, const float* x, const float*
   // proj1: weight gradient from (Xmix, gout); gXmix = P1^T gout.  Its plain bias gradient is NOT the right one (the bias is
   // scaled by colsum(W) per frame), so it goes to a scratch and the weighted sum is formed from the per-frame sums S below.
   SELFC_CUDA(cudaMemsetAsync(gb1w, 0, 64 * sizeof(float), st));
-  SELFC_TRY(pointwise_backward(g.p1w, 64, 64, 64, xmix, 64, gout, 64, gxmix, 64, false, gparams ? gparams[2] : nullptr, gb1w, scratch, zb, d, st));
+  SELFC_TRY(pointwise_backward(ctx, g.p1w, 64, 64, 64, xmix, 64, gout, 64, gxmix, 64, false, gparams ? gparams[2] : nullptr, gb1w, scratch, zb, d, st));
   frame_channel_sum_kernel<<<BT, 256, 0, st>>>(gout, S, hw);
   SELFC_LAUNCH_CHECK("frame_channel_sum_kernel");
   // gx = gout + sum_t' W[t,t'] gXmix[t']

@@ -44,6 +44,8 @@ struct Params {
   int ktiles, nsplit, mtiles, nst;
   int cin, np, taps;                    // scratch layout dw[(tap * cin + c) * np + n], bias at dw[taps * cin * np + n]
   int ncols;                            // real output channels (n < ncols)
+  int sh_center;                        // index of the unshifted A tile (1 of 3; 0 for a pointwise conv's single tile)
+  int n_off;                            // first output channel of this launch inside the scratch rows (pointwise convs wider than 64)
   int arows;                            // AT rows the TMA box brings (the rows that matter: 1 + cin, rounded up to 8; <= 128).  The MMA
                                         // still reads 128 rows of the tile: the others hold stale data whose products are never stored
   int g_row0;                           // first GT row of this launch (0: the three shifted copies; kWgSpatialRows: conv5's rows)
@@ -56,13 +58,14 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <int NSH>
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                const __grid_constant__ CUtensorMap tmap_g, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int NST = p.nst;
-  const int a_bytes = p.nsh * 2 * A_TILE;                 // [shift][hi|lo] tiles of 128 rows x 64 bytes
+  const int a_bytes = NSH * 2 * A_TILE;                   // [shift][hi|lo] tiles of 128 rows x 64 bytes
   const int b_half = p.N * KT * 2;                        // hi (then lo) block of N rows x 64 bytes
   const int stage_bytes = a_bytes + 2 * b_half;           // multiple of 1024: N is a multiple of 16
   const uint32_t bar_base = base + NST * stage_bytes;
@@ -101,12 +104,12 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
         uint32_t ph = 0;
         for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(empty_bar(s), ph ^ 1u, p.err, 41);
-          mbar_expect_tx(full_bar(s), (uint32_t)(p.nsh * 2 * p.arows * KT * 2 + 2 * b_half));
+          mbar_expect_tx(full_bar(s), (uint32_t)(NSH * 2 * p.arows * KT * 2 + 2 * b_half));
           const uint32_t st_a = base + s * stage_bytes, st_b = st_a + a_bytes;
           const int P0 = kt * KT;
-          for (int sh = 0; sh < p.nsh; ++sh)
+          for (int sh = 0; sh < NSH; ++sh)
             for (int hl = 0; hl < 2; ++hl)
-              tma_load_3d(st_a + (sh * 2 + hl) * A_TILE, &tmap_a, full_bar(s), P0 + (int)((sh - 1) * p.sh_stride), mt * ROWS, hl);
+              tma_load_3d(st_a + (sh * 2 + hl) * A_TILE, &tmap_a, full_bar(s), P0 + (int)((sh - p.sh_center) * p.sh_stride), mt * ROWS, hl);
           for (int hl = 0; hl < 2; ++hl) tma_load_3d(st_b + hl * b_half, &tmap_g, full_bar(s), P0, p.g_row0, hl);
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
           for (int term = 0; term < 3; ++term) {
             const uint64_t bd = desc_join((term == 1 ? b_lo : b_hi) + 2u * ks, hi_sw);
 #pragma unroll
-            for (int sh = 0; sh < 3; ++sh) {              // consecutive MMAs go to different accumulators
+            for (int sh = 0; sh < NSH; ++sh) {            // consecutive MMAs go to different accumulators
               const uint32_t a_lo = desc_lo(st_a + (sh * 2 + (term == 2 ? 1 : 0)) * A_TILE, 16);
               umma_bf16_elect(tmem_base + (uint32_t)(sh * p.N), desc_join(a_lo + 2u * ks, hi_sw), bd, idesc,
                               (kt > k0 || ks > 0 || term > 0) ? 1u : 0u);
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       const bool is_bias = row == 0;
       const bool is_w = c >= 0 && c < p.cin;
-      for (int sh = 0; sh < p.nsh; ++sh) {
+      for (int sh = 0; sh < NSH; ++sh) {
         for (int n0 = 0; n0 < p.N; n0 += 16) {
           uint32_t r[16];
           tmem_ld16(lane_addr + (uint32_t)(sh * p.N + n0), r);      // warp-uniform
@@ -157,16 +160,16 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
           const int kx = n0 / p.nb, nn = n0 - kx * p.nb;            // 16-column groups never straddle a kx block (nb % 16 == 0)
           const int tap = p.nkx == 3 ? sh * 3 + kx : sh;
           if (is_w) {
-            float* o = p.dw + ((size_t)tap * p.cin + c) * p.np + nn;
+            float* o = p.dw + ((size_t)tap * p.cin + c) * p.np + p.n_off + nn;
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
-              if (nn + j < p.np)
+              if (p.n_off + nn + j < p.np)
                 red_add4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          } else if (is_bias && sh == 1 && (p.nkx == 1 || kx == 1)) {
-            float* o = p.dw + (size_t)p.taps * p.cin * p.np + nn;
+          } else if (is_bias && sh == p.sh_center && (p.nkx == 1 || kx == 1)) {
+            float* o = p.dw + (size_t)p.taps * p.cin * p.np + p.n_off + nn;
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
-              if (nn + j < p.np)
+              if (p.n_off + nn + j < p.np)
                 red_add4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           }
         }
@@ -211,6 +214,27 @@ __global__ void __launch_bounds__(256) wg_planes_act_kernel(const __nv_bfloat16*
   if (slab == 0) {
     reinterpret_cast<uint16_t*>(at)[P] = 0x3F80;      // row 0 of the hi plane: 1.0 at real pixels (lo stays 0)
   }
+}
+
+// activations of a pointwise conv: fp32 pixel-major [M][pitch], channels [0, C) -> AT rows 1 + c (one thread per (4 channels, pixel))
+__global__ void __launch_bounds__(256) wg_planes_act_f32_kernel(const float* __restrict__ src, int pitch, int C, long long M,
+                                                                __nv_bfloat16* __restrict__ at, const WgGeom g) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * (C / 4)) return;
+  const int c0 = (int)(idx / M) * 4;
+  const long long m = idx - (long long)(c0 / 4) * M;
+  const long long P = plane_index(m, g);
+  const float4 t = __ldg(reinterpret_cast<const float4*>(src + m * pitch + c0));
+  const float v4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat16 h, l;
+    x2_split(v4[e], h, l);
+    __nv_bfloat16* hi = at + (size_t)(1 + c0 + e) * g.Pa + P;
+    hi[0] = h;
+    hi[(size_t)kWgRows * g.Pa] = l;
+  }
+  if (c0 == 0) reinterpret_cast<uint16_t*>(at)[P] = 0x3F80;      // the ones row
 }
 
 // gradient: fp32 pixel-major g[m * pitch + off + n], n < ncols -> GT planes [2][160][Pa].  Spatial convs (ncopies = 3): rows
@@ -271,6 +295,13 @@ int launch_wg_planes_act(const bfx2* buf, int pitch, const Dims& d, const WgGeom
   return 0;
 }
 
+int launch_wg_planes_act_f32(const float* src, int pitch, int C, const Dims& d, const WgGeom& g, void* planes, cudaStream_t st) {
+  SELFC_CHECK_ARG(C % 4 == 0 && pitch % 4 == 0 && C <= kWgRows - 1 && aligned16(src), "wgrad planes: %d fp32 channels (pitch %d)", C, pitch);
+  wg::wg_planes_act_f32_kernel<<<cdiv(d.M() * (C / 4), 256), 256, 0, st>>>(src, pitch, C, d.M(), reinterpret_cast<__nv_bfloat16*>(planes), g);
+  SELFC_LAUNCH_CHECK("wg_planes_act_f32_kernel");
+  return 0;
+}
+
 int launch_wg_planes_grad(const float* gsrc, int pitch, int off, long long sslabM, int ncols, int nb, bool temporal, const Dims& d,
                           const WgGeom& g, void* planes, cudaStream_t st) {
   SELFC_CHECK_ARG(nb % 16 == 0 && nb <= kWgGradRows - kWgSpatialRows && ncols <= nb && (temporal || nb == 32),
@@ -281,10 +312,12 @@ int launch_wg_planes_grad(const float* gsrc, int pitch, int off, long long sslab
   return 0;
 }
 
-int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, int taps, bool temporal, float* dw, int np, cudaStream_t st) {
-  SELFC_CHECK_ARG(taps == (temporal ? 3 : 9) && nb % 16 == 0 && nb >= 16 && nb <= kWgGradRows - kWgSpatialRows && cin >= 1 && cin <= kWgRows - 1 && np % 4 == 0 &&
-                      (temporal || nb == 32),
-                  "wgrad_tc: unsupported shape (cin %d, nb %d, taps %d)", cin, nb, taps);
+int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, int kind, float* dw, int np, cudaStream_t st, int n_off) {
+  const bool temporal = kind != WG_SPATIAL;        // conv5 and the pointwise convs read the unshifted gradient rows
+  const int taps = kind == WG_SPATIAL ? 9 : (kind == WG_TEMPORAL ? 3 : 1);
+  SELFC_CHECK_ARG(kind >= WG_SPATIAL && kind <= WG_POINT && nb % 16 == 0 && nb >= 16 && nb <= kWgGradRows - kWgSpatialRows && cin >= 1 &&
+                      cin <= kWgRows - 1 && np % 4 == 0 && n_off % 4 == 0 && n_off >= 0 && (temporal || nb == 32),
+                  "wgrad_tc: unsupported shape (cin %d, nb %d, kind %d)", cin, nb, kind);
   tc::EncodeTiledFn encode = tc::get_encode_fn();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -320,11 +353,13 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
   }
   wg::Params p;
   memset(&p, 0, sizeof(p));
-  p.nsh = 3;
+  p.nsh = kind == WG_POINT ? 1 : 3;
+  p.sh_center = kind == WG_POINT ? 0 : 1;
+  p.n_off = n_off;
   p.nkx = temporal ? 1 : 3;
   p.nb = nb;
   p.N = p.nkx * nb;
-  p.sh_stride = temporal ? g.Fp : g.Wp;
+  p.sh_stride = kind == WG_TEMPORAL ? g.Fp : (kind == WG_SPATIAL ? g.Wp : 0);
   p.g_row0 = temporal ? kWgSpatialRows : 0;
   p.arows = arows;
   p.ktiles = (int)(g.Pa / wg::KT);
@@ -356,10 +391,12 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !smem_set[dev]) {
-    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
   }
-  wg::wgrad_tc_kernel<<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  if (p.nsh == 1) wg::wgrad_tc_kernel<1><<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  else wg::wgrad_tc_kernel<3><<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
   SELFC_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;
 }

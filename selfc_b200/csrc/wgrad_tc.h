@@ -7,7 +7,7 @@
 
 namespace selfc {
 
-constexpr int kWgRows = 193;       // AT rows: the ones row + up to 192 channels of a dense buffer
+constexpr int kWgRows = 257;       // AT rows: the ones row + up to 256 channels (dense buffers: 192; the GMM head's 256-channel layer)
 constexpr int kWgSpatialRows = 96;  // GT rows [0, 96): three one-pixel-shifted copies of a spatial conv's 32 gradient channels
 constexpr int kWgGradRows = 160;    // ... rows [96, 160): conv5's (unshifted) gradient, up to 64 channels
 
@@ -17,14 +17,19 @@ struct WgGeom {
   long long Fp, P, Pa;             // padded frame size, plane length, allocated plane length (multiple of 32)
 };
 WgGeom wg_geometry(const Dims& d);
-size_t wg_plane_bytes(const WgGeom& g);      // [2][193][Pa] + [2][160][Pa] bf16; must be ZEROED once per geometry (the padding)
+size_t wg_plane_bytes(const WgGeom& g);      // [2][257][Pa] + [2][160][Pa] bf16; must be ZEROED once per geometry (the padding)
 
 // activations of a whole dense buffer (slab-planar (hi, lo) pairs, `pitch` channels) -> AT planes
 int launch_wg_planes_act(const bfx2* buf, int pitch, const Dims& d, const WgGeom& g, void* planes, cudaStream_t st);
 // output gradient channels [off, off + ncols) of an fp32 buffer (pixel-major, or 16-channel slabs when sslabM != 0) -> GT rows, rows >= ncols zero
 int launch_wg_planes_grad(const float* gsrc, int pitch, int off, long long sslabM, int ncols, int nb, bool temporal, const Dims& d,
                           const WgGeom& g, void* planes, cudaStream_t st);
-// dw[(tap * cin + c) * np + n] += sum_p in[p + shift(tap)][c] * g[p][n]; dw[taps * cin * np + n] += sum_p g[p][n]   (dw zeroed by the caller)
-int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, int taps, bool temporal, float* dw, int np, cudaStream_t st);
+// the same from an fp32 pixel-major tensor [M][pitch], channels [0, C) (the pointwise convs of the GMM head and of GlobalAgg)
+int launch_wg_planes_act_f32(const float* src, int pitch, int C, const Dims& d, const WgGeom& g, void* planes, cudaStream_t st);
+// dw[(tap * cin + c) * np + n_off + n] += sum_p in[p + shift(tap)][c] * g[p][n]; dw[taps * cin * np + n_off + n] += sum_p g[p][n]   (dw zeroed
+// by the caller).  kind: WG_SPATIAL (9 taps, 32 outputs), WG_TEMPORAL (3 taps, <= 64 outputs), WG_POINT (1 tap, <= 64 outputs per launch:
+// a wider layer is a loop over n_off; the gradient planes are built with temporal = true)
+enum WgKind { WG_SPATIAL = 0, WG_TEMPORAL = 1, WG_POINT = 2 };
+int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, int kind, float* dw, int np, cudaStream_t st, int n_off = 0);
 
 }  // namespace selfc

@@ -1051,11 +1051,13 @@ def test_invblock_backward_vs_autograd(dev, rev, mode):
         _assert_grad(gval.cpu(), ref, mode, tol, name)
 
 
-def test_head_sampler_backward_vs_autograd(dev):
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_head_sampler_backward_vs_autograd(dev, mode):
     """Backward of tail_gmm (three 1x1 convs + LeakyReLUs) and the soft-GMM sampler (softmax over hf, clamp, exp, injected
-    eps) against autograd on the oracle."""
+    eps) against autograd on the oracle.  bf16x3: the weight gradients through the pointwise form of the tensor-core kernel (the
+    recomputed forward and the input gradients of the head stay fp32-FMA, so the element-wise tolerance is the same)."""
     sd = so.make_state_dict(12, gain=2.0)
-    eng = _engine(dev, sd)
+    eng = _engine(dev, sd, mode)
     b, t, h, w = 2, 3, 7, 10
     gen = torch.Generator().manual_seed(9)
     feat = torch.randn(b * t, 64, h, w, generator=gen)
@@ -1072,12 +1074,14 @@ def test_head_sampler_backward_vs_autograd(dev):
         torch.testing.assert_close(gval.cpu(), ref, rtol=0, atol=3e-4 * float(ref.abs().max()) + 1e-6)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("h,w,t", [(10, 18, 2), (33, 40, 7)])
-def test_global_agg_backward_vs_autograd(dev, h, w, t):
+def test_global_agg_backward_vs_autograd(dev, h, w, t, mode):
     """Backward of GlobalAgg (pooled descriptor -> T x T softmax mixing -> proj1 mix + residual) against autograd on the
-    oracle: input gradient and the eight parameter gradients (fc through the overlapping adaptive-pool bins)."""
+    oracle: input gradient and the eight parameter gradients (fc through the overlapping adaptive-pool bins); bf16x3: proj1's
+    weight gradient on the tensor cores."""
     sd = so.make_state_dict(6, gain=2.0)
-    eng = _engine(dev, sd)
+    eng = _engine(dev, sd, mode)
     b = 2
     prefix = "stp_net.global_m2"
     gen = torch.Generator().manual_seed(h)
