@@ -891,26 +891,39 @@ __global__ void ga_mix_f32_kernel(const float* __restrict__ in, const float* __r
   store4(out + m * 64 + c, acc);
 }
 
-// S[n][ch] = sum_pix g[n,pix,ch]   (one block per frame, 256 threads = 4 pixel lanes x 64 channels)
-__global__ void __launch_bounds__(256) frame_channel_sum_kernel(const float* __restrict__ g, float* __restrict__ S, long long hw) {
+// Both reductions below run as (output, pixel split) blocks writing partial sums part[output * nsplit + split], summed in a fixed
+// order by sum_splits_kernel (deterministic): one block per output left 7 / 49 CTAs on 148 SMs (58 / 128 us at Vimeo shape).
+constexpr int kGaSplits = 16;
+__global__ void sum_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int n_out, int nsplit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += part[(size_t)i * nsplit + k];
+  out[i] = s;
+}
+// S[n][ch] = sum_pix g[n,pix,ch]   (grid (frames, splits), 256 threads = 4 pixel lanes x 64 channels)
+__global__ void __launch_bounds__(256) frame_channel_sum_kernel(const float* __restrict__ g, float* __restrict__ Spart, long long hw) {
   __shared__ float red[4][64];
-  const int n = blockIdx.x, ch = threadIdx.x & 63, lane = threadIdx.x >> 6;
+  const int n = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y, ch = threadIdx.x & 63, lane = threadIdx.x >> 6;
+  const long long per = (hw + nsplit - 1) / nsplit, p0 = split * per, p1 = p0 + per < hw ? p0 + per : hw;
   float acc = 0.f;
-  for (long long p = lane; p < hw; p += 4) acc += g[((long long)n * hw + p) * 64 + ch];
+  for (long long p = p0 + lane; p < p1; p += 4) acc += g[((long long)n * hw + p) * 64 + ch];
   red[lane][ch] = acc;
   __syncthreads();
-  if (lane == 0) S[n * 64 + ch] = red[0][ch] + red[1][ch] + red[2][ch] + red[3][ch];
+  if (lane == 0) Spart[((size_t)n * 64 + ch) * nsplit + split] = red[0][ch] + red[1][ch] + red[2][ch] + red[3][ch];
 }
 
-// R[b][t][u] = sum_{pix,ch} a[b,t,pix,ch] * c[b,u,pix,ch]   (one block per (b,t,u))
-__global__ void __launch_bounds__(256) pair_dot_kernel(const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ R, int T,
+// R[b][t][u] = sum_{pix,ch} a[b,t,pix,ch] * c[b,u,pix,ch]   (grid ((b,t,u), splits))
+__global__ void __launch_bounds__(256) pair_dot_kernel(const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ Rpart, int T,
                                                        long long hw) {
   __shared__ float red[256];
   const int u = blockIdx.x % T, t = (blockIdx.x / T) % T, b = blockIdx.x / (T * T);
+  const int split = blockIdx.y, nsplit = gridDim.y;
   const float4* pa = reinterpret_cast<const float4*>(a + ((long long)(b * T + t) * hw) * 64);
   const float4* pc = reinterpret_cast<const float4*>(c + ((long long)(b * T + u) * hw) * 64);
+  const long long n4 = hw * 16, per = (n4 + nsplit - 1) / nsplit, i0 = split * per, i1 = i0 + per < n4 ? i0 + per : n4;
   float acc = 0.f;
-  for (long long i = threadIdx.x; i < hw * 16; i += 256) {
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
     const float4 x = pa[i], y = pc[i];
     acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
   }
@@ -920,7 +933,7 @@ __global__ void __launch_bounds__(256) pair_dot_kernel(const float* __restrict__
     if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
     __syncthreads();
   }
-  if (threadIdx.x == 0) R[blockIdx.x] = red[0];
+  if (threadIdx.x == 0) Rpart[(size_t)blockIdx.x * nsplit + split] = red[0];
 }
 
 // per clip: recompute d, q, k, W; gW = R + b1 . S; softmax backward; gq, gk; gd; gradients of proj2 / proj3 / fc.bias
@@ -1090,13 +1103,20 @@ int ga_backward(const selfc_ctx* ctx, const GaW& g, const float* x, const float*
   // scaled by colsum(W) per frame), so it goes to a scratch and the weighted sum is formed from the per-frame sums S below.
   SELFC_CUDA(cudaMemsetAsync(gb1w, 0, 64 * sizeof(float), st));
   SELFC_TRY(pointwise_backward(ctx, g.p1w, 64, 64, 64, xmix, 64, gout, 64, gxmix, 64, false, gparams ? gparams[2] : nullptr, gb1w, scratch, zb, d, st));
-  frame_channel_sum_kernel<<<BT, 256, 0, st>>>(gout, S, hw);
+  // (the training scratch is free again once pointwise_backward's launches are queued: partial sums of the two reductions)
+  float* Spart = scratch;
+  float* Rpart = scratch + (size_t)BT * 64 * kGaSplits;
+  frame_channel_sum_kernel<<<dim3(BT, kGaSplits), 256, 0, st>>>(gout, Spart, hw);
   SELFC_LAUNCH_CHECK("frame_channel_sum_kernel");
+  sum_splits_kernel<<<cdiv(BT * 64, 256), 256, 0, st>>>(Spart, S, BT * 64, kGaSplits);
+  SELFC_LAUNCH_CHECK("sum_splits_kernel");
   // gx = gout + sum_t' W[t,t'] gXmix[t']
   ga_mix_f32_kernel<<<nb16, 256, 0, st>>>(gxmix, wmat, 1, gout, gx, T, hw, M);
   SELFC_LAUNCH_CHECK("ga_mix_f32_kernel");
-  pair_dot_kernel<<<d.B * T * T, 256, 0, st>>>(x, gxmix, R, T, hw);
+  pair_dot_kernel<<<dim3(d.B * T * T, kGaSplits), 256, 0, st>>>(x, gxmix, Rpart, T, hw);
   SELFC_LAUNCH_CHECK("pair_dot_kernel");
+  sum_splits_kernel<<<cdiv(d.B * T * T, 256), 256, 0, st>>>(Rpart, R, d.B * T * T, kGaSplits);
+  SELFC_LAUNCH_CHECK("sum_splits_kernel");
   SELFC_CUDA(cudaMemsetAsync(gwmap, 0, (size_t)hw * sizeof(float), st));
   const size_t smem = (size_t)(5 * T * 64 + 2 * T * 32) * sizeof(float);
   ga_small_bwd_kernel<<<d.B, 64, smem, st>>>(partial, ws.nsplit, g.fcb, g.p2w, g.p2b, g.p3w, g.p3b, g.p1b, R, S, gd,

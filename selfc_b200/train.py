@@ -89,8 +89,7 @@ class Trainer:
         """The optimiser kernel (and the broadcast above) write the parameters behind autograd's back: bump the version counters
         so that EVERY engine caching packed weights (keyed on (data_ptr, _version)) re-packs, not only this trainer's."""
         with torch.no_grad():
-            for p in self.params:
-                p.add_(0)
+            torch._foreach_add_(self.params, 0.0)       # a handful of multi-tensor launches instead of 354 (0.6 ms of a 44 ms step)
 
     def _refresh_ptrs(self):
         cur = [p.data_ptr() for p in self.params]
