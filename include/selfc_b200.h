@@ -195,6 +195,12 @@ int selfc_prof_read(selfc_ctx* ctx, int ncls, double* ms, double* work, uint64_t
  * out[8..12] = issue order, out[13..16] = tensor-memory ring rows of x1..x4 (0 = not kept on chip), out[17] = tensor-memory
  * columns in use.  Returns 0, or SELFC_E_ARG for an unknown id. */
 int selfc_dense_fused_schedule(int sch, int* out18);
+/* Host-side view of the zero-padded pixel planes the tensor-core weight-gradient kernel (BF16X3 training, csrc/wgrad_tc.cu)
+ * contracts over: out4 = {Wp (row pitch, a multiple of 8 >= w + 2), Fp = (h + 2) * Wp, P (plane length), Pa (allocated, multiple of 32)}.
+ * Pixel (b, t, y, x) of a [B][T][h][w] clip batch lives at P = ((b * (T + 1) + t + 1) * (h + 2) + y + 1) * Wp + x + 1; a spatial tap
+ * (ky, kx) is the offset (ky - 1) * Wp + (kx - 1), a temporal tap dt the offset (dt - 1) * Fp, and every such neighbour of a real pixel
+ * is either the real neighbour or padding (tests/test_boundary_cpu.py checks exactly that).  No device work. */
+int selfc_wgrad_geometry(int B, int T, int h, int w, long long* out4);
 
 /* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
 uint64_t selfc_launch_count(void);

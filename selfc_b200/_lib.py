@@ -55,6 +55,7 @@ SIGNATURES = {
     "selfc_gmm_sample_planar": (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _vp]),
     "selfc_export_eps": (_i, [_vp, _u64, _u64, _i, _i, _i, _i, _vp]),
     "selfc_dense_fused_schedule": (_i, [_i, C.POINTER(_i)]),
+    "selfc_wgrad_geometry": (_i, [_i, _i, _i, _i, C.POINTER(C.c_longlong)]),
     "selfc_launch_count": (_u64, []),
     "selfc_prof_enable": (_i, [_vp, _i]),
     "selfc_prof_read": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_u64)]),

@@ -15,6 +15,7 @@
 #include "conv_tc.h"
 #include "tc_ptx.cuh"
 #include "net_ctx.h"
+#include "wgrad_tc.h"
 
 namespace selfc {
 
@@ -638,6 +639,14 @@ extern "C" {
 
 int selfc_version(void) { return 100; }
 int selfc_dense_fused_schedule(int sch, int* out18) { return selfc::dense_fused_schedule(sch, out18); }
+/* the zero-padded pixel planes of the tensor-core weight-gradient kernel (wgrad_tc.cu) for a clip batch: out4 = {Wp, Fp, P, Pa};
+ * pixel (b, t, y, x) lives at P = ((b * (T + 1) + t + 1) * (h + 2) + y + 1) * Wp + x + 1 (host-side check of the padding scheme) */
+int selfc_wgrad_geometry(int B, int T, int h, int w, long long* out4) {
+  SELFC_CHECK_ARG(B >= 1 && T >= 1 && h >= 1 && w >= 1 && out4 != nullptr, "wgrad_geometry: bad argument");
+  const selfc::WgGeom g = selfc::wg_geometry(selfc::Dims{B, T, h, w});
+  out4[0] = g.Wp; out4[1] = g.Fp; out4[2] = g.P; out4[3] = g.Pa;
+  return 0;
+}
 /* debug only (SELFC_TC_DBG=1): barrier-wait cycle counters of the tcgen05 temporal kernel, 17 int64 per launch */
 int selfc_debug_read(long long* out, int cap) { return selfc::tc::debug_read(out, cap); }
 const char* selfc_last_error(void) { return g_err; }

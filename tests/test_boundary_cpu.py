@@ -193,3 +193,63 @@ def test_precision_modes_match_the_header():
     assert parse_mode("bf16x3") == parse_mode("fp32_tc") == _lib.MODE_BF16X3
     with pytest.raises(ValueError):
         parse_mode("tf32")
+
+
+@pytest.mark.parametrize("B,T,h,w", [(1, 1, 1, 1), (2, 3, 5, 7), (1, 7, 9, 14), (3, 2, 4, 30), (1, 2, 3, 6)])
+def test_wgrad_planes_make_every_tap_a_plain_offset(B, T, h, w):
+    """The tensor-core weight-gradient kernel (BF16X3 training) contracts over zero-padded pixel planes in which a tap is a plain
+    offset of the pixel index.  From the geometry the library reports (no device work): all real pixels get distinct indices inside
+    the plane, the row pitch lets TMA boxes start on 16-byte boundaries, and every spatial / temporal neighbour of a real pixel is
+    either the true neighbour (inside the frame / the clip) or a padding position -- never a real pixel of another row, frame or clip
+    -- including the one-pixel-shifted copies of the gradient plane."""
+    import ctypes as C
+    import numpy as np
+    from selfc_b200 import _lib
+    out = (C.c_longlong * 4)()
+    assert _lib.lib().selfc_wgrad_geometry(B, T, h, w, out) == 0
+    Wp, Fp, P, Pa = [int(v) for v in out]
+    assert Wp % 8 == 0 and Wp >= w + 2 and Fp == (h + 2) * Wp and P == (B * (T + 1) + 1) * Fp and Pa % 32 == 0 and Pa >= P
+    b, t, y, x = np.meshgrid(np.arange(B), np.arange(T), np.arange(h), np.arange(w), indexing="ij")
+    idx = ((b * (T + 1) + t + 1) * (h + 2) + y + 1) * Wp + x + 1
+    assert idx.min() >= 0 and idx.max() < P and np.unique(idx).size == idx.size
+    real = np.full(Pa + 2 * Fp, -1, dtype=np.int64)            # plane position -> flat pixel id (or -1: padding), with slack either side
+    flat = np.arange(idx.size).reshape(idx.shape)
+    real[idx + Fp] = flat
+    for ky in range(3):
+        for kx in range(3):
+            got = real[idx + Fp + (ky - 1) * Wp + (kx - 1)]
+            yy, xx = y + ky - 1, x + kx - 1
+            inside = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+            want = np.where(inside, flat[b, t, np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)], -1)
+            assert np.array_equal(got, want), (ky, kx)
+    for dt in range(3):
+        got = real[idx + Fp + (dt - 1) * Fp]
+        tt = t + dt - 1
+        inside = (tt >= 0) & (tt < T)
+        want = np.where(inside, flat[b, np.clip(tt, 0, T - 1), y, x], -1)
+        assert np.array_equal(got, want), dt
+
+
+def test_bf16x3_arithmetic_restated_on_the_host():
+    """What the BF16X3 mode computes, restated with torch CPU ops: hi = bf16(v), lo = bf16(v - hi), A.W ~ A_hi.W_hi + A_hi.W_lo + A_lo.W_hi
+    with fp32 accumulation.  The split carries 16 mantissa bits (|v - hi - lo| <= 2^-17 |v|) and a K = 1440 dot product (the widest
+    (1,3,3) layer: 9 x 160) lands within a few 1e-6 of the fp64 result relative to the operand scale -- three orders of magnitude
+    inside the 1e-3 gate, against ~2e-3 for plain bf16 operands."""
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(4096, 1440, generator=g)
+    w = torch.randn(1440, 32, generator=g) * 0.05
+
+    def split(v):
+        hi = v.to(torch.bfloat16).to(torch.float32)
+        lo = (v - hi).to(torch.bfloat16).to(torch.float32)
+        return hi, lo
+
+    a_hi, a_lo = split(a)
+    w_hi, w_lo = split(w)
+    assert ((a - a_hi - a_lo).abs() <= a.abs() * 2.0 ** -17 + 1e-30).all()
+    ref = a.double() @ w.double()
+    x3 = (a_hi @ w_hi + a_hi @ w_lo + a_lo @ w_hi).double()
+    bf = (a_hi @ w_hi).double()
+    scale = float(ref.abs().max())
+    err_x3, err_bf = float((x3 - ref).abs().max()) / scale, float((bf - ref).abs().max()) / scale
+    assert err_x3 <= 1e-5 and err_bf >= 50 * err_x3, (err_x3, err_bf)
