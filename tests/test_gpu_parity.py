@@ -158,18 +158,22 @@ def test_philox_stream(dev):
 
 
 # ------------------------------------------------------------------------------------------------ a2 / a9 / a11
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("name", ["net_t3", "net_t7", "net_t2_gain"])
-def test_network_vs_golden_and_oracle(dev, golden_dir, name):
+def test_network_vs_golden_and_oracle(dev, golden_dir, name, mode):
+    """Both numerics-gate modes (fp32-FMA kernels; (hi, lo) bf16 operands on the tensor cores) against the outputs of the LIVE REFERENCE
+    (tests/golden/net_*.npz, oracle/make_golden.py): latent, LR codes, HF sample, HR."""
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     b, t, hh, ww, wseed, xseed = [int(v) for v in g["meta"]]
     sd = so.make_state_dict(wseed, float(g["gain"]))
-    eng = _engine(dev, sd)
+    eng = _engine(dev, sd, mode)
     x = _t(g["x"])
     out51, lr_u8, lr_q = eng.down(x.to(dev), t)
-    torch.testing.assert_close(out51.cpu(), _t(g["down_out"]), rtol=0, atol=1e-4)
+    torch.testing.assert_close(out51.cpu(), _t(g["down_out"]), rtol=0, atol=1e-4 if mode == "fp32" else 4e-4)
     ref_u8 = so.quantize_u8(_t(g["down_out"])[:, :3])
     diff = (lr_u8.cpu().int() - ref_u8.int()).abs()
-    assert diff.max().item() <= 1 and (diff == 0).float().mean().item() >= 0.9999
+    exact = (diff == 0).float().mean().item()
+    assert diff.max().item() <= 1 and (exact >= 0.9999 or (mode == "bf16x3" and round((1.0 - exact) * diff.numel()) <= 3))
     assert torch.equal(lr_q.cpu(), lr_u8.cpu().float() / 255.0)
     # up, from the REFERENCE's quantised LR so both sides see identical inputs
     eps = so.make_eps(b, t, hh // 4, ww // 4, int(g["eps_seed"]))
