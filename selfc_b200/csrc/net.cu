@@ -193,12 +193,17 @@ static int launch_temporal(const selfc_ctx* ctx, const TcTempW& tw, const ConvAr
 
 // InvBlockExp (SelfC_GMM_arch_inv.py:21-33) on the latent state z, forward or reverse
 template <typename T>
-static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
+static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st,
+                        const BlockBufsV* bb = nullptr) {
   float* z = reinterpret_cast<float*>(wsp + ws.z);
-  float* sbuf = reinterpret_cast<float*>(wsp + ws.sbuf);
-  T* fbuf = reinterpret_cast<T*>(wsp + ws.fbuf);
-  T* gbuf = reinterpret_cast<T*>(wsp + ws.gbuf);
-  T* hbuf = reinterpret_cast<T*>(wsp + ws.hbuf);
+  float* sbuf = bb ? bb->s : reinterpret_cast<float*>(wsp + ws.sbuf);
+  T* fbuf = bb ? static_cast<T*>(bb->f) : reinterpret_cast<T*>(wsp + ws.fbuf);
+  T* gbuf = bb ? static_cast<T*>(bb->g) : reinterpret_cast<T*>(wsp + ws.gbuf);
+  T* hbuf = bb ? static_cast<T*>(bb->h) : reinterpret_cast<T*>(wsp + ws.hbuf);
+  // where the block's last epilogue leaves the next block's input (training keeps every block's buffers; see BlockBufsV)
+  T* f_out = bb && !rev ? static_cast<T*>(bb->f_next) : fbuf;      // Y2's copy: forward -> the next block's F; reverse -> this block's F
+  T* g_out = bb && rev ? static_cast<T*>(bb->g_next) : gbuf;       // Y1's copies: forward -> this block's G, H; reverse -> the next block's
+  T* h_out = bb && rev ? static_cast<T*>(bb->h_next) : hbuf;
   const DenseW& F = ctx->inv[blk][0];
   const DenseW& G = ctx->inv[blk][1];
   const DenseW& H = ctx->inv[blk][2];
@@ -221,7 +226,7 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
              launch_dense_fused(F.tc, 4, reinterpret_cast<__nv_bfloat16*>(fbuf), dense_slab(ctx, d), F.xpad, d.B * d.T, d.h, d.w, st, nullptr, nullptr,
                                 F.f5img, sbuf));
         PROF(ctx, st, 1, 0.0,
-             launch_f5_combine(sbuf, F.t5.bias, z, reinterpret_cast<__nv_bfloat16*>(gbuf), reinterpret_cast<__nv_bfloat16*>(hbuf), d.T, d.hw(), d.M(),
+             launch_f5_combine(sbuf, F.t5.bias, z, reinterpret_cast<__nv_bfloat16*>(g_out), reinterpret_cast<__nv_bfloat16*>(h_out), d.T, d.hw(), d.M(),
                                rev ? 1 : 0, st));
         return 0;
       }
@@ -229,7 +234,7 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
     SELFC_TRY(run_dense_convs<T>(ctx, F, fbuf, ws.fpitch, d, st));
     ConvArgs<T> a = conv5_args<T>(ctx, F, fbuf, ws.fpitch, d);
     a.epi = EPI_COUPLE_Y1; a.rev = rev ? 1 : 0; a.z = z;
-    a.copyA = gbuf; a.copyA_pitch = ws.gpitch; a.copyB = hbuf; a.copyB_pitch = ws.gpitch; a.copy_pad = ctx->xpad3;
+    a.copyA = g_out; a.copyA_pitch = ws.gpitch; a.copyB = h_out; a.copyB_pitch = ws.gpitch; a.copy_pad = ctx->xpad3;
     a.copy_slabM = dense_slab(ctx, d);
     PROF(ctx, st, 1, conv5_flops(F, d), launch_temporal<T>(ctx, F.t5, a, d, st));
     return 0;
@@ -255,7 +260,7 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
         TcTempArgs t;
         t.in = hbuf; t.in2 = gbuf; t.in_pitch = ws.gpitch; t.B = d.B; t.T = d.T; t.hw = (int)d.hw(); t.in_slabM = dense_slab(ctx, d);
         t.epi = EPI_COUPLE_HG; t.rev = rev ? 1 : 0; t.z = z;
-        t.copyA = fbuf; t.copyA_pitch = ws.fpitch; t.copy_slabM = dense_slab(ctx, d);
+        t.copyA = f_out; t.copyA_pitch = ws.fpitch; t.copy_slabM = dense_slab(ctx, d);
         prof_begin(ctx, st, 1, conv5_flops(H, d) + conv5_flops(G, d));
         const int rc = launch_temporal_tc(H.t5, t, st, &G.t5);
         prof_end(ctx, st);
@@ -269,7 +274,7 @@ static int run_invblock(const selfc_ctx* ctx, int blk, bool rev, char* wsp, cons
     if (!dual) SELFC_TRY(run_dense_convs<T>(ctx, G, gbuf, ws.gpitch, d, st));
     ConvArgs<T> g = conv5_args<T>(ctx, G, gbuf, ws.gpitch, d);
     g.epi = EPI_COUPLE_Y2; g.rev = rev ? 1 : 0; g.z = z; g.sbuf = sbuf;
-    g.copyA = fbuf; g.copyA_pitch = ws.fpitch; g.copy_slabM = dense_slab(ctx, d);
+    g.copyA = f_out; g.copyA_pitch = ws.fpitch; g.copy_slabM = dense_slab(ctx, d);
     PROF(ctx, st, 1, conv5_flops(G, d), launch_temporal<T>(ctx, G.t5, g, d, st));
     return 0;
   };
@@ -361,8 +366,10 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
                    const Dims& d, char* wsp, const Workspace& ws, cudaStream_t st, const TrainHooks* hooks = nullptr,
                    uint8_t* hr_img = nullptr) {
   float* z = reinterpret_cast<float*>(wsp + ws.z);
-  T* gbuf = reinterpret_cast<T*>(wsp + ws.gbuf);
-  T* hbuf = reinterpret_cast<T*>(wsp + ws.hbuf);
+  // the X slots of the first reverse block (block 8): the workspace buffers, or that block's own buffers when training keeps them
+  const BlockBufsV* ub = hooks ? hooks->up_bufs : nullptr;
+  T* gbuf = ub ? static_cast<T*>(ub[7].g) : reinterpret_cast<T*>(wsp + ws.gbuf);
+  T* hbuf = ub ? static_cast<T*>(ub[7].h) : reinterpret_cast<T*>(wsp + ws.hbuf);
   T* stpbuf = reinterpret_cast<T*>(wsp + ws.stpbuf);
   T* feat = reinterpret_cast<T*>(wsp + ws.feat);
   T* fact = reinterpret_cast<T*>(wsp + ws.fact);
@@ -489,8 +496,10 @@ static int up_impl(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t s
   for (int blk = 7; blk >= 0; --blk) {
     if (hooks && hooks->z_save)      // training: the state each reverse block starts from
       SELFC_CUDA(cudaMemcpyAsync(hooks->z_save + (size_t)blk * d.M() * kZQuads * 4, z, (size_t)d.M() * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
-    SELFC_TRY(run_invblock<T>(ctx, blk, true, wsp, ws, d, st));
+    SELFC_TRY(run_invblock<T>(ctx, blk, true, wsp, ws, d, st, ub ? &ub[blk] : nullptr));
   }
+  if (hooks && hooks->z_save)
+    SELFC_CUDA(cudaMemcpyAsync(hooks->z_save + (size_t)8 * d.M() * kZQuads * 4, z, (size_t)d.M() * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
   if (hr_img != nullptr)
     PROF(ctx, st, 5, (double)M * (51 * 4 + 48), launch_fa_rev_u8(z, hr_img, d.B * d.T, d.h, d.w, st));
   else
@@ -594,8 +603,8 @@ const DenseW* find_dense(selfc_ctx* ctx, int first_param) {
 }
 
 template <typename E>
-int invblock_fwd(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st) {
-  return run_invblock<E>(ctx, blk, rev, wsp, ws, d, st);
+int invblock_fwd(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st, const BlockBufsV* bufs) {
+  return run_invblock<E>(ctx, blk, rev, wsp, ws, d, st, bufs);
 }
 template <typename E>
 int up_hooked(selfc_ctx* ctx, const float* lr, const float* eps, uint64_t seed, uint64_t offset, float* hr, const Dims& d, char* wsp,
@@ -614,8 +623,8 @@ template <typename E>
 int dense_convs(const selfc_ctx* ctx, const DenseW& W, E* buf, int pitch, const Dims& d, cudaStream_t st) {
   return run_dense_convs<E>(ctx, W, buf, pitch, d, st);
 }
-template int invblock_fwd<float>(const selfc_ctx*, int, bool, char*, const Workspace&, const Dims&, cudaStream_t);
-template int invblock_fwd<bfx2>(const selfc_ctx*, int, bool, char*, const Workspace&, const Dims&, cudaStream_t);
+template int invblock_fwd<float>(const selfc_ctx*, int, bool, char*, const Workspace&, const Dims&, cudaStream_t, const BlockBufsV*);
+template int invblock_fwd<bfx2>(const selfc_ctx*, int, bool, char*, const Workspace&, const Dims&, cudaStream_t, const BlockBufsV*);
 template int up_hooked<float>(selfc_ctx*, const float*, const float*, uint64_t, uint64_t, float*, const Dims&, char*, const Workspace&, cudaStream_t,
                               const TrainHooks*);
 template int up_hooked<bfx2>(selfc_ctx*, const float*, const float*, uint64_t, uint64_t, float*, const Dims&, char*, const Workspace&, cudaStream_t,

@@ -117,9 +117,17 @@ inline long long dense_slab(const selfc_ctx* ctx, const Dims& d) { return ctx->m
 
 // what the training step asks the reverse pass to keep (fp32, device): ga_save = 7 x [M][64] (slot i+1 <- output of
 // GlobalAgg i), z_save = 8 x planar state (slot blk <- the state reverse block blk starts from)
+// Dense buffers of ONE coupling block kept for its backward (training): its own F / G / H buffers and log-scale, and where the block's
+// last epilogue puts the NEXT block's input (forward direction: y2 -> the next block's F; reverse: y1 -> the next block's G and H).
+// Inference runs every block in the same three workspace buffers (all of these equal the workspace's).
+struct BlockBufsV {
+  void *f = nullptr, *g = nullptr, *h = nullptr, *f_next = nullptr, *g_next = nullptr, *h_next = nullptr;
+  float* s = nullptr;
+};
 struct TrainHooks {
   float* ga_save = nullptr;
-  float* z_save = nullptr;
+  float* z_save = nullptr;              // slot blk <- the state reverse block blk starts from; slot 8 <- the state after the last one
+  const BlockBufsV* up_bufs = nullptr;  // [8]: per-block buffers of the reverse pass (the activations stay for the backward)
 };
 // forward pieces re-used by the training step (net.cu); E = float (FP32 mode) or bfx2 (BF16X3 mode: the same launches on the tcgen05
 // kernels, dense buffers slab-planar (hi, lo) pairs)
@@ -135,7 +143,8 @@ int dense_convs(const selfc_ctx* ctx, const DenseW& W, E* buf, int pitch, const 
 // log-scale (ws.sbuf) behind; the X slot of the first dense block must already hold its input (x2 for F when !rev, x1 for
 // G and H when rev)
 template <typename E>
-int invblock_fwd(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st);
+int invblock_fwd(const selfc_ctx* ctx, int blk, bool rev, char* wsp, const Workspace& ws, const Dims& d, cudaStream_t st,
+                 const BlockBufsV* bufs = nullptr);
 int check_run(selfc_ctx* ctx, int B, int T, int H, int W, void* workspace, size_t workspace_bytes, Workspace* ws);
 const DenseW* find_dense(selfc_ctx* ctx, int first_param);
 const GaW* find_ga(selfc_ctx* ctx, int first_param);

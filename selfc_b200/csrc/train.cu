@@ -573,17 +573,19 @@ __global__ void cpl_rev_pre_kernel(float* __restrict__ gz, const float* __restri
 // zin: the block's saved input state (planar); gz: gradient w.r.t. the block's OUTPUT state on entry, w.r.t. its INPUT state
 // on return; gparams: 30 gradients (F, G, H x conv1..5 weight/bias), accumulated into.  Scratch inside the workspace: the STP
 // regions (params, h1, h2), which are idle while a coupling block runs.
+// kept (optional): the block's buffers as its forward left them + zout = the block's output state; then nothing is recomputed
 template <typename E>
 int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin, float* gz, float* const* gparams, char* wsp,
-                      const Workspace& ws, const Dims& d, cudaStream_t st) {
+                      const Workspace& ws, const Dims& d, cudaStream_t st, const BlockBufsV* kept = nullptr, const float* zout = nullptr) {
   const long long M = d.M();
   const long long slabM = dense_slab(ctx, d);
   const int xp3 = ctx->xpad3;
   float* z = reinterpret_cast<float*>(wsp + ws.z);
-  float* sbuf = reinterpret_cast<float*>(wsp + ws.sbuf);
-  E* fbuf = reinterpret_cast<E*>(wsp + ws.fbuf);
-  E* gbuf = reinterpret_cast<E*>(wsp + ws.gbuf);
-  E* hbuf = reinterpret_cast<E*>(wsp + ws.hbuf);
+  float* sbuf = kept ? kept->s : reinterpret_cast<float*>(wsp + ws.sbuf);
+  E* fbuf = kept ? static_cast<E*>(kept->f) : reinterpret_cast<E*>(wsp + ws.fbuf);
+  E* gbuf = kept ? static_cast<E*>(kept->g) : reinterpret_cast<E*>(wsp + ws.gbuf);
+  E* hbuf = kept ? static_cast<E*>(kept->h) : reinterpret_cast<E*>(wsp + ws.hbuf);
+  const float* zo = kept ? zout : z;                  // the block's output state (the reverse direction's coupling gradient reads y2)
   float* gdense = reinterpret_cast<float*>(wsp + ws.params);                 // [M][<=192] gradient of a dense buffer
   float* gyG = reinterpret_cast<float*>(wsp + ws.h2);                        // [M][48]
   float* gyH = gyG + (size_t)M * kHF;                                        // [M][48]
@@ -599,7 +601,8 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
   float* const* gH = gparams ? gparams + 20 : nullptr;
   const int nb = cdiv(M, 256), nbq = cdiv(M * kSQuads, 256), nbx = cdiv(M * (xp3 / 4), 256);
   const long long gsl = grad_slab(ctx, d);           // layout of the dense-buffer gradients dense_block_backward leaves in gdense
-  // recompute the block's forward from its input state
+  // recompute the block's forward from its input state (unless its buffers were kept)
+  if (kept == nullptr) {
   SELFC_CUDA(cudaMemcpyAsync(z, zin, (size_t)M * kZQuads * 16, cudaMemcpyDeviceToDevice, st));
   if (!rev) {
     quads_to_dense_kernel<E><<<nbq, 256, 0, st>>>(zin, 1, kSQuads, fbuf, ws.fpitch, slabM, 0, 0, M);
@@ -619,6 +622,7 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
     quads_to_dense_kernel<E><<<nbx, 256, 0, st>>>(zin, 0, 1, hbuf, ws.gpitch, slabM, 0, xp3, M);
   }
   SELFC_LAUNCH_CHECK("quads_to_dense_kernel");
+  }
   if (!rev) {
     cpl_fwd_pre_kernel<<<nbq, 256, 0, st>>>(gz, zin, sbuf, gyG, gyH, M);
     SELFC_LAUNCH_CHECK("cpl_fwd_pre_kernel");
@@ -635,7 +639,7 @@ int invblock_backward(const selfc_ctx* ctx, int blk, bool rev, const float* zin,
     cpl_quad0_kernel<<<nb, 256, 0, st>>>(gz, nullptr, gyF, -1.0f, M);        // y1 = x1 - F(y2): F's output gradient = -gy1
     SELFC_LAUNCH_CHECK("cpl_quad0_kernel");
     SELFC_TRY(dense_block_backward<E>(ctx, F, fbuf, ws.fpitch, gyF, 4, gdense, scratch, gF, d, st));
-    cpl_rev_pre_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, gsl, z, sbuf, gyG, gyH, M);
+    cpl_rev_pre_kernel<<<nbq, 256, 0, st>>>(gz, gdense, ws.fpitch, gsl, zo, sbuf, gyG, gyH, M);
     SELFC_LAUNCH_CHECK("cpl_rev_pre_kernel");
     SELFC_TRY(dense_block_backward<E>(ctx, G, gbuf, ws.gpitch, gyG, kHF, gdense, scratch, gG, d, st));
     take4_kernel<<<nb, 256, 0, st>>>(acc, gdense, ws.gpitch, gsl, 1, 1.0f, M);
@@ -662,6 +666,10 @@ struct Tape {
   size_t lrq, glr;
   size_t loss;          // 4 floats: sum of squared LR errors, sum of Charbonnier terms
   size_t small;         // per-clip scratch of the GlobalAgg backward
+  // the coupling blocks' dense buffers and log-scales, kept by the forward passes so that the backward does not recompute them
+  // (16 x (176 + 144 + 144 + 48) x 4 bytes = 32 KB per LR pixel: 1.6 GB per 7x256x448 septuplet -- 180 GB of HBM make the trade easy)
+  size_t acts;
+  size_t act_f, act_g, act_s, act_block;      // byte sizes of one F buffer, one G / H buffer, one log-scale, one block's set
 };
 static Tape make_tape(int B, int T, int h, int w) {
   Tape t;
@@ -682,6 +690,11 @@ static Tape make_tape(int B, int T, int h, int w) {
   t.glr = take(M * 4 * 4);
   t.loss = take(64);
   t.small = take(((size_t)B * T * 128 + (size_t)B * T * T + (size_t)h * w + 1024) * 4);
+  t.act_f = align_up(M * 176 * 4 + 4096, 1024);
+  t.act_g = align_up(M * 144 * 4 + 4096, 1024);
+  t.act_s = align_up(M * kHF * 4 + 256, 1024);
+  t.act_block = t.act_f + 2 * t.act_g + t.act_s;
+  t.acts = take(16 * t.act_block);
   t.total = off;
   return t;
 }
@@ -1236,6 +1249,24 @@ __global__ void loss_finish_kernel(const float* __restrict__ acc, float* __restr
   out[2] = lb;
 }
 
+// per-block buffers inside the tape: dir 0 = the downscaling pass (blocks run 0..7), dir 1 = the upscaling pass (7..0); the last
+// block of a pass has no successor: its "next" targets are the workspace's own buffers (never read)
+static void make_block_bufs(BlockBufsV out[8], int dir, char* tp, const Tape& tape, char* wsp, const Workspace& ws) {
+  auto blockp = [&](int blk) { return tp + tape.acts + (size_t)(dir * 8 + blk) * tape.act_block; };
+  for (int blk = 0; blk < 8; ++blk) {
+    char* b = blockp(blk);
+    out[blk].f = b;
+    out[blk].g = b + tape.act_f;
+    out[blk].h = b + tape.act_f + tape.act_g;
+    out[blk].s = reinterpret_cast<float*>(b + tape.act_f + 2 * tape.act_g);
+    const int nxt = dir == 0 ? blk + 1 : blk - 1;
+    const bool has = nxt >= 0 && nxt < 8;
+    out[blk].f_next = has ? (void*)blockp(nxt) : (void*)(wsp + ws.fbuf);
+    out[blk].g_next = has ? (void*)(blockp(nxt) + tape.act_f) : (void*)(wsp + ws.gbuf);
+    out[blk].h_next = has ? (void*)(blockp(nxt) + tape.act_f + tape.act_g) : (void*)(wsp + ws.hbuf);
+  }
+}
+
 template <typename E>
 int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset, float* const* grads,
                 float* losses, const Dims& d, char* wsp, const Workspace& ws, char* tp, const Tape& tape, cudaStream_t st) {
@@ -1265,23 +1296,32 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
   SELFC_CUDA(cudaMemsetAsync(lacc, 0, 64, st));
 
   // ---- forward: downscale (states kept), quantise, upscale (states and STP stage outputs kept) ----
-  SELFC_TRY(launch_fa_fwd_z<E>(hr, z, fbuf, ws.fpitch, slabM, BT, d.h, d.w, st));
+  // every coupling block of both passes runs in its own buffers inside the tape and leaves them for its backward (SELFC_TRAIN_KEEP=0:
+  // the three workspace buffers, every block's forward recomputed from its saved input state)
+  static int keep_on = -1;
+  const bool keep = env_on("SELFC_TRAIN_KEEP", keep_on);
+  BlockBufsV bufs_dn[8], bufs_up[8];
+  make_block_bufs(bufs_dn, 0, tp, tape, wsp, ws);
+  make_block_bufs(bufs_up, 1, tp, tape, wsp, ws);
+  SELFC_TRY(launch_fa_fwd_z<E>(hr, z, keep ? static_cast<E*>(bufs_dn[0].f) : fbuf, ws.fpitch, slabM, BT, d.h, d.w, st));
   for (int blk = 0; blk < 8; ++blk) {
     SELFC_CUDA(cudaMemcpyAsync(zs_dn + blk * state_f, z, state_f * 4, cudaMemcpyDeviceToDevice, st));
-    SELFC_TRY(invblock_fwd<E>(ctx, blk, false, wsp, ws, d, st));
+    SELFC_TRY(invblock_fwd<E>(ctx, blk, false, wsp, ws, d, st, keep ? &bufs_dn[blk] : nullptr));
   }
   SELFC_CUDA(cudaMemcpyAsync(zs_dn + 8 * state_f, z, state_f * 4, cudaMemcpyDeviceToDevice, st));
   SELFC_TRY(launch_export_down(z, nullptr, nullptr, lrq, M, hw, st));            // Quantization.forward
   TrainHooks hooks;
   hooks.ga_save = ga_save;
   hooks.z_save = zs_up;
+  hooks.up_bufs = keep ? bufs_up : nullptr;
   SELFC_TRY(up_hooked<E>(ctx, lrq, eps, seed, offset, rec, d, wsp, ws, st, &hooks));
 
   // ---- backward ----
   loss_back_fa_bwd_kernel<<<cdiv(M, 128), 128, 0, st>>>(hr, rec, gz, lacc, kScale / n_hr, BT, d.h, d.w);
   SELFC_LAUNCH_CHECK("loss_back_fa_bwd_kernel");
   for (int blk = 0; blk < 8; ++blk)            // the reverse pass ran blocks 7..0, so their backward runs 0..7
-    SELFC_TRY(invblock_backward<E>(ctx, blk, true, zs_up + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
+    SELFC_TRY(invblock_backward<E>(ctx, blk, true, zs_up + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st,
+                                   keep ? &bufs_up[blk] : nullptr, zs_up + (blk == 0 ? 8 : blk - 1) * state_f));
   // gz now holds d loss / d [LR_q | v]; the HF part goes through the sampler and the GMM head into the STP
   SELFC_TRY(head_sampler_backward(ctx, ga_save + (size_t)6 * M * kStpC, eps, seed, offset, gz, gcur, grads ? grads + P_TAIL : nullptr, wsp, ws,
                                   tp, tape, d, st));
@@ -1310,7 +1350,8 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
   loss_forw_kernel<<<cdiv(M, 128), 128, 0, st>>>(zs_dn + 8 * state_f, ref_l, glr, gz, lacc, kScale / n_lr, hw, M);
   SELFC_LAUNCH_CHECK("loss_forw_kernel");
   for (int blk = 7; blk >= 0; --blk)
-    SELFC_TRY(invblock_backward<E>(ctx, blk, false, zs_dn + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st));
+    SELFC_TRY(invblock_backward<E>(ctx, blk, false, zs_dn + blk * state_f, gz, grads ? grads + P_INV0 + 30 * blk : nullptr, wsp, ws, d, st,
+                                   keep ? &bufs_dn[blk] : nullptr, zs_dn + (blk + 1) * state_f));
   if (losses) {
     loss_finish_kernel<<<1, 1, 0, st>>>(lacc, losses, n_lr, n_hr);
     SELFC_LAUNCH_CHECK("loss_finish_kernel");
