@@ -714,6 +714,10 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
   }
   for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.t[j]);
   for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.g[j]);
+  for (int j = 0; j < 5; ++j) free_temporal_weights(ctx->head.r[j]);
+  for (int j = 0; j < 4; ++j) free_temporal_weights(ctx->head.dg3[j]);
+  free_temporal_weights(ctx->head.dg2);
+  free_temporal_weights(ctx->head.dg1);
   delete ctx;
   return 0;
 }
@@ -787,6 +791,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
   }
   const size_t head_perm_w = pl.take((size_t)720 * 256 * 4);
   const size_t head_perm_b = pl.take(720 * 4);
+  const size_t head_zero = pl.take(256 * 4);
   if (ctx->arena_bytes < pl.off) {
     if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->train_scratch) cudaFree(ctx->train_scratch);
@@ -859,6 +864,19 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
     SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, true, st));
     for (int k = 0; k < kGmmK; ++k)
       SELFC_TRY(pack_temporal_weights(ctx->head.g[k], wperm + (size_t)144 * k * 256, bperm + 144 * k, 144, 256, 1, 256, 256, 256, st, x2));
+    if (x2) {
+      // training (BF16X3): the head's last layer in reference channel order, and the three layers' input-gradient images.  The latter
+      // come straight from the fp32-FMA packs [cin][np] (row = input channel = an input-gradient OUTPUT, column = output channel = its K)
+      for (int i = 0; i < 5; ++i)
+        SELFC_TRY(pack_temporal_weights(ctx->head.r[i], p[P_TAIL + 4] + (size_t)144 * i * 256, p[P_TAIL + 5] + 144 * i, 144, 256, 1, 256, 256, 256, st, true));
+      // zero bias: the first 256 floats of the permuted-bias scratch are overwritten below, so use a dedicated zero vector in the arena
+      float* zero = fp(head_zero);
+      SELFC_CUDA(cudaMemsetAsync(zero, 0, 256 * sizeof(float), st));
+      for (int j = 0; j < 4; ++j)
+        SELFC_TRY(pack_temporal_weights(ctx->head.dg3[j], ctx->head.w[2] + (size_t)64 * j * ctx->head.np[2], zero, 64, ctx->head.np[2], 1, 720, 720, 720, st, true));
+      SELFC_TRY(pack_temporal_weights(ctx->head.dg2, ctx->head.w[1], zero, 128, ctx->head.np[1], 1, 256, 256, 256, st, true));
+      SELFC_TRY(pack_temporal_weights(ctx->head.dg1, ctx->head.w[0], zero, 64, ctx->head.np[0], 1, 128, 128, 128, st, true));
+    }
   }
   ctx->loaded = true;
   return 0;

@@ -56,6 +56,10 @@ struct HeadW {
   int cin[3] = {64, 128, 256}, cout[3] = {128, 256, 720}, np[3] = {128, 256, 736};
   TcTempW t[5];            // BF16 mode: 64->128, 128->256, 256->240 x3 as tcgen05 pointwise GEMMs
   TcTempW g[5];            // BF16 mode: 256->144 per mixture component (fused head + sampler)
+  // BF16X3 training: 256 -> 720 in five 144-row groups in REFERENCE channel order (the sampler's backward reads pixel-major [M][720]),
+  // and the input-gradient images of the three layers (transposed weights; 256 -> 720 in four 64-column groups)
+  TcTempW r[5];
+  TcTempW dg3[4], dg2, dg1;
 };
 
 }  // namespace selfc

@@ -334,7 +334,8 @@ static int ensure_dgrad_images(const selfc_ctx* cctx, const DenseW& cW, float* z
 static bfx2* train_gslab(const selfc_ctx* cctx, long long M) {
   selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
   std::lock_guard<std::mutex> lock(ctx->mu);
-  const size_t need = (size_t)M * 64 * sizeof(bfx2) + 4096;
+  // 64 channels for a dense-block conv's output gradient; 64 + 128 + 256 + 720 + 256 + 128 for the GMM head's tensors (head_sampler_backward)
+  const size_t need = (size_t)M * 1600 * sizeof(bfx2) + 4096;
   if (ctx->dg_gslab_bytes < need) {
     if (ctx->dg_gslab) cudaFree(ctx->dg_gslab);
     ctx->dg_gslab = nullptr;
@@ -834,6 +835,28 @@ __global__ void __launch_bounds__(128) gmm_sample_bwd_kernel(float* __restrict__
 
 // GMM head + sampler backward.  feat [M][64]: the STP feature (before the head's first LeakyReLU); gz: gradient state whose HF
 // quads hold g_v; gfeat [M][64] receives the feature gradient (overwritten); gparams[6]: tail_gmm.{1,3,5}.{weight,bias}.
+// fp32 pixel-major [M][C] -> (hi, lo) pixel-major [M][C] (C % 16 == 0): the input of a tensor-core pointwise conv
+__global__ void f32_to_x2_kernel(const float* __restrict__ src, bfx2* __restrict__ dst, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) store4(dst + 4 * i, load4(src + 4 * i));
+}
+static int to_x2(const float* src, bfx2* dst, long long M, int C, cudaStream_t st) {
+  f32_to_x2_kernel<<<cdiv(M * (C / 4), 256), 256, 0, st>>>(src, dst, M * (C / 4));
+  SELFC_LAUNCH_CHECK("f32_to_x2_kernel");
+  return 0;
+}
+// one tensor-core pointwise conv over all M pixels (two pseudo-frames): (hi, lo) input, optional (hi, lo) and / or fp32 outputs
+static int pointwise_tc(const TcTempW& w, const bfx2* in, int in_pitch, bfx2* outT, int outT_pitch, float* outF, int outF_pitch, int outF_off,
+                        int act, long long M, cudaStream_t st) {
+  TcTempArgs t;
+  t.in = reinterpret_cast<const __nv_bfloat16*>(in); t.in_pitch = in_pitch; t.B = 1; t.T = 2; t.hw = (int)((M + 1) / 2); t.m_limit = M;
+  t.epi = EPI_STORE; t.act = act;
+  t.outT = reinterpret_cast<__nv_bfloat16*>(outT); t.outT_pitch = outT_pitch;
+  t.outF = outF; t.outF_pitch = outF_pitch; t.outF_off = outF_off;
+  return launch_temporal_tc(w, t, st);
+}
+static bool head_tc_on() { static int c = -1; return env_on("SELFC_HEAD_TC", c); }
+
 int head_sampler_backward(const selfc_ctx* ctx, const float* feat, const float* eps, uint64_t seed, uint64_t offset, const float* gz,
                           float* gfeat, float* const* gparams, char* wsp, const Workspace& ws, char* tp, const Tape& tape, const Dims& d,
                           cudaStream_t st) {
@@ -848,9 +871,46 @@ int head_sampler_backward(const selfc_ctx* ctx, const float* feat, const float* 
   float* zb = train_zero_bias(ctx);
   SELFC_CHECK_ARG(scratch && zb, "out of device memory (training scratch)");
   const HeadW& hd = ctx->head;
+  // BF16X3 mode: the head's recomputed forward and its input gradients as tensor-core pointwise convs ((hi, lo) copies of the fp32
+  // tensors in a scratch; fp32 outputs for the masks, the sampler's backward and the weight gradients).  SELFC_HEAD_TC=0: fp32-FMA.
+  const bool tc = ctx->mode == SELFC_MODE_BF16X3 && head_tc_on() && hd.r[0].img != nullptr && hd.dg1.img != nullptr;
+  bfx2* xs = tc ? train_gslab(ctx, M) : nullptr;
+  SELFC_CHECK_ARG(!tc || xs != nullptr, "out of device memory (head scratch)");
+  bfx2* fact_x = xs;                                   // [M][64]
+  bfx2* h1_x = tc ? fact_x + (size_t)M * 64 : nullptr;   // [M][128]
+  bfx2* h2_x = tc ? h1_x + (size_t)M * 128 : nullptr;    // [M][256]
+  bfx2* g_x = tc ? h2_x + (size_t)M * 256 : nullptr;     // [M][720]   gradient of the parameters
+  bfx2* gh2_x = tc ? g_x + (size_t)M * 720 : nullptr;    // [M][256]
+  bfx2* gh1_x = tc ? gh2_x + (size_t)M * 256 : nullptr;  // [M][128]
   // recompute the head: fact = lrelu(feat); h1 = lrelu(W1 fact + b1); h2 = lrelu(W2 h1 + b2); params = W3 h2 + b3
   lrelu_fwd_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(feat, fact, M * 16);
   SELFC_LAUNCH_CHECK("lrelu_fwd_kernel");
+  if (tc) {
+    SELFC_TRY(to_x2(fact, fact_x, M, 64, st));
+    SELFC_TRY(pointwise_tc(hd.t[0], fact_x, 64, h1_x, 128, h1, 128, 0, 1, M, st));
+    SELFC_TRY(pointwise_tc(hd.t[1], h1_x, 128, h2_x, 256, h2, 256, 0, 1, M, st));
+    for (int i = 0; i < 5; ++i) SELFC_TRY(pointwise_tc(hd.r[i], h2_x, 256, nullptr, 0, params, 720, 144 * i, 0, M, st));
+    gmm_sample_bwd_kernel<<<cdiv(M, 4), 128, 0, st>>>(params, eps, seed, offset, gz, d.T, d.hw(), M);
+    SELFC_LAUNCH_CHECK("gmm_sample_bwd_kernel");
+    // weight gradients through pointwise_backward (tensor-core form, no input gradient: gin = null), input gradients here
+    SELFC_TRY(pointwise_backward(ctx, hd.w[2], 256, hd.np[2], 720, h2, 256, params, 720, nullptr, 256, false, gparams ? gparams[4] : nullptr,
+                                 gparams ? gparams[5] : nullptr, scratch, zb, d, st));
+    SELFC_TRY(to_x2(params, g_x, M, 720, st));
+    for (int j = 0; j < 4; ++j) SELFC_TRY(pointwise_tc(hd.dg3[j], g_x, 720, nullptr, 0, gh2, 256, 64 * j, 0, M, st));
+    lrelu_bwd_full_kernel<<<cdiv(M * 64, 256), 256, 0, st>>>(gh2, h2, M * 64);
+    SELFC_TRY(pointwise_backward(ctx, hd.w[1], 128, hd.np[1], 256, h1, 128, gh2, 256, nullptr, 128, false, gparams ? gparams[2] : nullptr,
+                                 gparams ? gparams[3] : nullptr, scratch, zb, d, st));
+    SELFC_TRY(to_x2(gh2, gh2_x, M, 256, st));
+    SELFC_TRY(pointwise_tc(hd.dg2, gh2_x, 256, nullptr, 0, gh1, 128, 0, 0, M, st));
+    lrelu_bwd_full_kernel<<<cdiv(M * 32, 256), 256, 0, st>>>(gh1, h1, M * 32);
+    SELFC_TRY(pointwise_backward(ctx, hd.w[0], 64, hd.np[0], 128, fact, 64, gh1, 128, nullptr, 64, false, gparams ? gparams[0] : nullptr,
+                                 gparams ? gparams[1] : nullptr, scratch, zb, d, st));
+    SELFC_TRY(to_x2(gh1, gh1_x, M, 128, st));
+    SELFC_TRY(pointwise_tc(hd.dg1, gh1_x, 128, nullptr, 0, gfeat, 64, 0, 0, M, st));
+    lrelu_bwd_full_kernel<<<cdiv(M * 16, 256), 256, 0, st>>>(gfeat, fact, M * 16);
+    SELFC_LAUNCH_CHECK("lrelu_bwd_full_kernel");
+    return 0;
+  }
   ConvArgs<float> a;
   a.BT = d.B * d.T; a.Tn = d.T; a.h = d.h; a.w_ = d.w;
   a.taps = 1; a.tap_mode = TAP_POINT; a.epi = EPI_STORE;
