@@ -126,13 +126,13 @@ int selfc_conv3x3(selfc_ctx* ctx, int first_param, int k, const float* x, float*
 /* a13 (training step, models/SelfC_model.py:148-183) building block: backward of D2DTInput (Subnet_constructor.py:115-133)
  * for the dense block at `first_param`.  x [B*T,Cin,h,w], gy [B*T,Cout,h,w] -> gx [B*T,Cin,h,w]; gparams[10] (conv1.weight,
  * conv1.bias, ..., conv5.bias in the reference layouts, device fp32) are ACCUMULATED into; a NULL weight entry skips that
- * conv's weight and bias gradient.  FP32 mode only.  The forward activations are recomputed, not stored. */
+ * conv's weight and bias gradient.  FP32 or BF16X3 mode (BF16X3: forward, input and weight gradients on the tcgen05 kernels).  The forward activations are recomputed here. */
 int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gy, float* gx, float* const* gparams,
                         int B, int T, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
 /* a13 building block: backward of InvBlockExp (SelfC_GMM_arch_inv.py:21-33) number blk (0..7) in the forward (rev = 0) or
  * reverse (rev = 1) direction.  z_in [B*T,51,h,w]: the block's input (its forward is recomputed); gz [B*T,51,h,w]: gradient
  * w.r.t. the block's output on entry, overwritten with the gradient w.r.t. its input; gparams[30] (F, G, H x conv1..5 weight,
- * bias; reference layouts) are accumulated into.  FP32 mode only. */
+ * bias; reference layouts) are accumulated into.  FP32 or BF16X3 mode. */
 int selfc_invblock_backward(selfc_ctx* ctx, int blk, int rev, const float* z_in, float* gz, float* const* gparams,
                             int B, int T, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
 /* extra device memory ("tape": gradient state, saved block inputs, scratch) the training-step entry points need */
@@ -145,7 +145,7 @@ int selfc_head_sampler_backward(selfc_ctx* ctx, const float* feat, const float* 
                                 void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes, void* stream);
 /* a13 building block: backward of GlobalAgg (SelfC_GMM_arch_inv.py:265-285) whose fc.weight is parameter `first_param`.
  * x, gout [B*T,64,h,w] -> gx; gparams[8] (fc.weight, fc.bias, proj1.weight, proj1.bias, proj2.weight, proj2.bias,
- * proj3.weight, proj3.bias; reference layouts) are accumulated into.  FP32 mode, T <= 16. */
+ * proj3.weight, proj3.bias; reference layouts) are accumulated into.  FP32 or BF16X3 mode, T <= 16. */
 int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gout, float* gx,
                               float* const* gparams, int B, int T, int h, int w, void* workspace, size_t workspace_bytes,
                               void* tape, size_t tape_bytes, void* stream);
@@ -154,7 +154,8 @@ int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, c
  * ref_l, Charbonnier reconstruction, total x 144*144*3).  hr [B*T,3,H,W], ref_l [B*T,3,H/4,W/4], eps as in selfc_up.
  * grads[354]: device fp32 buffers in the reference parameter layouts (state_dict order), ACCUMULATED into -- zero them for a
  * plain step; losses: 3 device floats (total, l_forw_fit, l_back_rec).  Block inputs are kept on the tape and every block's
- * forward is recomputed in the backward pass.  FP32 mode (fp32-FMA kernels), T <= 16. */
+ * coupling block keeps its activations inside the tape for its backward (the STP blocks are recomputed).  FP32 mode (fp32-FMA kernels) or
+ * BF16X3 mode (every convolution pass on the tcgen05 kernels with (hi, lo) bf16 operands; fp32 gradients), T <= 16. */
 int selfc_train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset,
                       float* const* grads, int n_grads, float* losses, int B, int T, int H, int W, void* workspace,
                       size_t workspace_bytes, void* tape, size_t tape_bytes, void* stream);

@@ -1,5 +1,7 @@
-// Backward kernels of the training step (models/SelfC_model.py:148-183) -- FP32 mode, pixel-major dense
-// buffers, fp32-FMA arithmetic.  First building block: the backward pass of one D2DTInput dense block
+// Backward of the training step (models/SelfC_model.py:148-183), templated on the element type of the forward's dense
+// buffers: float = FP32 mode (pixel-major buffers, every convolution pass on the fp32-FMA kernel) and bfx2 = BF16X3 mode (slab-planar
+// (hi, lo) buffers; forward, input gradients and weight gradients on the tcgen05 kernels: conv_tc3.cu / temporal_tc.cu / wgrad_tc.cu;
+// gradients, masks and the optimiser stay fp32).  First building block: the backward pass of one D2DTInput dense block
 // (Subnet_constructor.py:115-133), parity-tested against autograd of the oracle.
 //
 //   forward   x_k = lrelu(conv_k([X, x_1..x_{k-1}])), k = 1..4 (1,3,3);   y = conv5([X, x_1..x_4]) (3,1,1), no activation
@@ -7,8 +9,8 @@
 //     conv5:  dW5 += g_y (x) in5,   gbuf[0:cin5) += conv5^T(g_y)
 //     k=4..1: g_k = gbuf[slot_k] * lrelu'(x_k);   dW_k += g_k (x) in_k;   gbuf[0:cin_k) += conv_k^T(g_k)
 //     g_X = gbuf[0:cin)
-//   conv^T (dgrad) is the SAME implicit-GEMM kernel as the forward conv (conv_simt.cu) on the tap-flipped, transposed
-//   weights, accumulating into gbuf (EPI_ACCUM); wgrad is a pixel reduction (wgrad_kernel below).
+//   conv^T (dgrad) is the SAME implicit-GEMM kernel as the forward conv on the tap-flipped, transposed weights, accumulating into
+//   gbuf (conv_simt.cu's EPI_ACCUM / conv_tc3.cu's accumulate epilogue); wgrad is a pixel reduction (wgrad_kernel below / wgrad_tc.cu).
 #include <string.h>
 
 #include <stdlib.h>
@@ -1475,7 +1477,7 @@ extern "C" {
 
 /* a13 building block: backward of D2DTInput (Subnet_constructor.py:115-133) for the dense block at `first_param`.
  * x [B*T,Cin,h,w], gy [B*T,Cout,h,w] -> gx [B*T,Cin,h,w]; gparams[10] (conv1.weight, conv1.bias, ... conv5.bias, reference
- * layouts, device, fp32) are ACCUMULATED into; any of them may be NULL.  FP32 mode only. */
+ * layouts, device, fp32) are ACCUMULATED into; any of them may be NULL.  FP32 or BF16X3 mode. */
 int selfc_d2dt_backward(selfc_ctx* ctx, int first_param, const float* x, const float* gy, float* gx, float* const* gparams, int B, int T,
                         int h, int w, void* workspace, size_t workspace_bytes, void* stream) {
   Workspace ws;
@@ -1590,7 +1592,7 @@ int selfc_global_agg_backward(selfc_ctx* ctx, int first_param, const float* x, c
 /* a13: forward + backward of one training step (models/SelfC_model.py:148-170 with the training YAML's losses: l2 forward fit
  * against ref_l, Charbonnier reconstruction, x 144*144*3; Quantization with its straight-through gradient).  hr [B*T,3,H,W],
  * ref_l [B*T,3,H/4,W/4]; eps as in selfc_up.  grads[354]: device fp32 buffers in the reference parameter layouts, ACCUMULATED
- * into (zero them for a plain step); losses: 3 device floats (total, l_forw_fit, l_back_rec).  FP32 mode, T <= 16. */
+ * into (zero them for a plain step); losses: 3 device floats (total, l_forw_fit, l_back_rec).  FP32 or BF16X3 mode, T <= 16. */
 int selfc_train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float* eps, uint64_t seed, uint64_t offset,
                       float* const* grads, int n_grads, float* losses, int B, int T, int H, int W, void* workspace, size_t workspace_bytes,
                       void* tape, size_t tape_bytes, void* stream) {

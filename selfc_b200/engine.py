@@ -374,7 +374,7 @@ class Engine:
         return y
 
     def d2dt_backward(self, prefix: str, x: torch.Tensor, gy: torch.Tensor, T: int):
-        """Backward of the dense block `prefix` (training step building block, fp32 mode): x [B*T,Cin,h,w], gy [B*T,Cout,h,w]
+        """Backward of the dense block `prefix` (training step building block; fp32 or bf16x3 mode): x [B*T,Cin,h,w], gy [B*T,Cout,h,w]
         -> (gx, {parameter name: gradient}) with the gradients in the reference's parameter layouts."""
         first = PARAM_INDEX[prefix + ".conv1.weight"]
         x = self._check_in(x, "x")
@@ -391,7 +391,7 @@ class Engine:
         return gx, dict(zip(names, grads))
 
     def invblock_backward(self, blk: int, rev: bool, z_in: torch.Tensor, gz: torch.Tensor, T: int):
-        """Backward of InvBlockExp `operations.{blk+1}` in the forward / reverse direction (fp32 mode): z_in, gz [B*T,51,h,w]
+        """Backward of InvBlockExp `operations.{blk+1}` in the forward / reverse direction (fp32 or bf16x3 mode): z_in, gz [B*T,51,h,w]
         -> (gradient w.r.t. z_in, {parameter name: gradient})."""
         z_in = self._check_in(z_in, "z_in")
         gz = self._check_in(gz, "gz").clone()
@@ -416,7 +416,7 @@ class Engine:
 
     def head_sampler_backward(self, feat: torch.Tensor, gv: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0,
                               offset: int = 0):
-        """Backward of tail_gmm + the soft-GMM sampler (fp32 mode): feat [B*T,64,h,w], gv [B*T,48,h,w] -> (gfeat, grads)."""
+        """Backward of tail_gmm + the soft-GMM sampler (fp32 or bf16x3 mode): feat [B*T,64,h,w], gv [B*T,48,h,w] -> (gfeat, grads)."""
         feat = self._check_in(feat, "feat")
         gv = self._check_in(gv, "gv")
         if eps is not None:
@@ -436,7 +436,7 @@ class Engine:
         return gfeat, dict(zip(names, grads))
 
     def global_agg_backward(self, prefix: str, x: torch.Tensor, gout: torch.Tensor, T: int):
-        """Backward of GlobalAgg `prefix` (fp32 mode): x, gout [B*T,64,h,w] -> (gx, grads of its eight parameters)."""
+        """Backward of GlobalAgg `prefix` (fp32 or bf16x3 mode): x, gout [B*T,64,h,w] -> (gx, grads of its eight parameters)."""
         x = self._check_in(x, "x")
         gout = self._check_in(gout, "gout")
         B, h, w = self._clip_dims(x, T)
@@ -454,7 +454,7 @@ class Engine:
 
     def train_grads(self, hr: torch.Tensor, ref_l: torch.Tensor, T: int, eps: Optional[torch.Tensor] = None, seed: int = 0,
                     offset: int = 0, grads: Optional[Sequence[torch.Tensor]] = None):
-        """Forward + backward of one training step (SelfC_model.py:148-170; fp32 mode): hr [B*T,3,H,W], ref_l [B*T,3,H/4,W/4]
+        """Forward + backward of one training step (SelfC_model.py:148-170; fp32 or bf16x3 mode): hr [B*T,3,H,W], ref_l [B*T,3,H/4,W/4]
         -> ({parameter name: gradient}, losses tensor [total, l_forw_fit, l_back_rec]).  `grads` (354 fp32 device tensors in
         PARAM_NAMES order) are accumulated into when given, otherwise fresh zero tensors are used."""
         hr = self._check_in(hr, "hr")

@@ -7,7 +7,7 @@ checkpoint handling (state_dict file, optional 'module.' prefix, strict load).  
     (SelfC_model.py:203-243, SURVEY F7) is not reproduced;
   * no DataParallel wrapper: one process per GPU (the wrapper's `.module` attribute is provided for compatibility);
   * training: optimize_parameters (SelfC_model.py:148-183) runs forward + backward + clip + Adam through the C-ABI
-    (selfc_b200/train.py), fp32 mode; the gradient all-reduce replaces DistributedDataParallel.
+    (selfc_b200/train.py), fp32 or bf16x3 mode (`precision`); the gradient all-reduce replaces DistributedDataParallel.
 """
 from __future__ import annotations
 
