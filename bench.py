@@ -347,6 +347,13 @@ def run_ours(args):
                     "algorithmic_flops_per_launch": c["work"] / max(1, c["launches"]),
                     "avg_launch_ms": c["ms"] / max(1, c["launches"]), "launches": c["launches"],
                     "share_of_step": c["ms"] / tot_ms if tot_ms else None,
+                    # the instrumented GOPs record an event pair around EVERY launch, which serialises them: the programmatic-dependent-launch
+                    # overlap of the real stream (prologue of launch i+1 under the tail of launch i) is lost, so the per-launch times above
+                    # are slightly pessimistic.  The same class share applied to the timed region's own per-GOP time:
+                    "in_stream": ({"gop_ms_timed_region": ms_total / args.steps / len(gops), "gop_ms_instrumented": tot_ms,
+                                   "class_ms": c["ms"] / tot_ms * (ms_total / args.steps / len(gops)),
+                                   "frac": (c["work"] / (c["ms"] / tot_ms * (ms_total / args.steps / len(gops)) / 1e3) / 1e12) / tf_sust}
+                                  if tot_ms and frames >= GOP and gpl == 1 else None),
                     "classes": {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                                     "share": round(v["ms"] / tot_ms, 4) if tot_ms else None} for k, v in prof.items()}}
 
