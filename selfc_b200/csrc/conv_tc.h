@@ -27,7 +27,7 @@ void free_tc_weights(TcConvW& w);
 // position either side; the values never reach an output).  Workspace regions satisfy this: none is first, all carry a guard.
 // x2 (BF16X3 mode, common.cuh): the buffers hold (hi, lo) bf16 pairs -- 64-byte rows per position and slab -- and every tap is three MMAs
 // acc (x2 only; training): instead of bias + LeakyReLU + a (hi, lo) store, ADD the 32 results to channels [off, off + n) of an fp32
-// pixel-major buffer -- an input-gradient launch: buf holds the output gradient, w.img_x2 one of pack_tc3_dgrad_images' images
+// pixel-major buffer -- an input-gradient launch: buf holds the concatenated output gradients, w.img_x2 pack_tc3_dgrad_slot_images' images
 struct TcAccum {
   float* out = nullptr;
   int pitch = 0, off = 0, n = 0;      // n channels in ngroups groups of 32 (w.img_x2 = the first of ngroups consecutive images)
@@ -36,10 +36,11 @@ struct TcAccum {
 };
 int launch_conv3x3_tc(const TcConvW& w, __nv_bfloat16* buf, long long slabM, int cin, int out_off, int N, int h, int wd, cudaStream_t st,
                       const TcConvW* w2 = nullptr, __nv_bfloat16* buf2 = nullptr, bool x2 = false, const TcAccum* acc = nullptr);
-// input-gradient images of a (1,3,3) conv from its forward weights in buffer-channel order [9][cin_buf][32] (fp32): ceil(cin_buf/32)
-// images of tc3_dgrad_image_bytes() each, image j = input channels [32 j, 32 j + 32)
-size_t tc3_dgrad_image_bytes();
-int pack_tc3_dgrad_images(const float* wf, void* img, int cin_buf, cudaStream_t st);
+// input-gradient images of one 32-channel-group SLOT [c0, c0 + ncover) of a dense buffer: the later convs' transposed, tap-flipped
+// weights stacked in K in the order [conv4 | conv3 | ...] (nconv of them; wf / cin = the forward packs [9][cin_k][32] of conv1..4);
+// ceil(ncover / 32) images of tc3_dgrad_slot_image_bytes(nconv) each
+size_t tc3_dgrad_slot_image_bytes(int nconv);
+int pack_tc3_dgrad_slot_images(const float* const wf[4], const int cin[4], void* img, int c0, int ncover, int nconv, cudaStream_t st);
 
 // ---- dense_fused.cu: conv1..convL of a dense block in ONE launch, growth channels kept in tensor memory ----------------
 // w[0..L-1] = the block's conv_k weights (TcConvW::img_pair is what the kernel reads), L = dense_fused_layers(cin): 4, or 3 when the fourth layer's

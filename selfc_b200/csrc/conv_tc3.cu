@@ -522,28 +522,36 @@ __global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* _
   }
 }
 
-// Input-gradient images of one (1,3,3) conv (training, BF16X3 mode).  The gradient w.r.t. the conv's input is the conv of its output
-// gradient (32 channels) with the tap-flipped, transposed weights: gx[c] = sum_{n,ky,kx} Wf[(2-ky)*3 + (2-kx)][c][n] . g[n] at
-// (y + ky - 1, x + kx - 1), Wf = the forward weights in buffer-channel order [tap][cin_buf][32] (conv_simt pack).  The input channels
-// are produced 32 at a time (one launch of the X2 kernel each, K = 32): image j holds rows r = kx * 32 + (c - 32 j) in the pair
-// layout of pack_tc3_kernel's img_x2 with two K-steps; channels >= cin_buf are zero rows.
-__global__ void pack_tc3_dgrad_kernel(const float* __restrict__ wf, __nv_bfloat16* __restrict__ img, int cin_buf, int ngroups) {
-  const int per = 3 * 32 * NB;                       // (ky, n, r) of one group
+// Input-gradient images of a dense block (training, BF16X3 mode), one per 32-channel SLOT of its buffer.  The gradient w.r.t. the
+// buffer channels c of a slot is the sum over the later convs k of conv_k^T(g_k): gx[c] = sum_k sum_{n,ky,kx} Wf_k[(2-ky)*3 + (2-kx)][c][n]
+// . g_k[n] at (y + ky - 1, x + kx - 1), Wf_k = conv k's forward weights in buffer-channel order [tap][cin_k][32] (conv_simt pack).  With the
+// output gradients of the contributing convs CONCATENATED in K -- [g_4 | g_3 | ...], 32 channels each, the order the backward produces
+// them in -- that is ONE conv with K = 32 * nconv per slot, so every gradient channel is written once instead of once per later conv.
+// Image j of a slot holds rows r = kx * 32 + (c - c0 - 32 j) in the pair layout of pack_tc3_kernel's img_x2 with 2 * nconv K-steps;
+// channels beyond the slot are zero rows.
+struct DgradSlotSrc {
+  const float* wf[4];      // forward packs of conv1..conv4
+  int cin[4];              // their buffer-channel counts
+};
+__global__ void pack_tc3_dgrad_slot_kernel(const DgradSlotSrc src, __nv_bfloat16* __restrict__ img, int c0, int ncover, int nconv, int ngroups) {
+  const int K = 32 * nconv;
+  const int per = 3 * K * NB;                        // (ky, kk, r) of one group
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= per * ngroups) return;
   const int j = idx / per, e = idx - j * per;
   const int r = e % NB;
-  const int n = (e / NB) % 32;                      // K index: output-gradient channel
-  const int ky = e / (NB * 32);
-  const int kx = r / 32, c = 32 * j + r % 32;
+  const int kk = (e / NB) % K;                       // K index: conv 4 - kk / 32 (conv4's gradient first), its output channel kk % 32
+  const int ky = e / (NB * K);
+  const int kc = 3 - kk / 32, n = kk % 32;
+  const int kx = r / 32, cl = 32 * j + r % 32;
   float v = 0.f;
-  if (c < cin_buf) v = wf[((size_t)((2 - ky) * 3 + (2 - kx)) * cin_buf + c) * 32 + n];
-  constexpr int nks = 2;
-  const int ks = n / 16, kk = n % 16;
+  if (cl < ncover) v = src.wf[kc][((size_t)((2 - ky) * 3 + (2 - kx)) * src.cin[kc] + c0 + cl) * 32 + n];
+  const int nks = 2 * nconv;
+  const int ks = kk / 16, k16 = kk % 16;
   const int half = r / (NB / 2), rh = r % (NB / 2);
   const size_t tile = (size_t)(WTILE_BYTES / 4);
   const size_t half_elems = (size_t)3 * nks * tile;
-  const size_t inner = (size_t)((kk / 8) * (NB / 16) + rh / 8) * 64 + (rh % 8) * 8 + (kk % 8);
+  const size_t inner = (size_t)((k16 / 8) * (NB / 16) + rh / 8) * 64 + (rh % 8) * 8 + (k16 % 8);
   const size_t off = (size_t)j * (4 * half_elems) + half * (2 * half_elems) + (size_t)((ky * nks + ks) * 2) * tile + inner;
   __nv_bfloat16 hi, lo;
   x2_split(v, hi, lo);
@@ -553,13 +561,16 @@ __global__ void pack_tc3_dgrad_kernel(const float* __restrict__ wf, __nv_bfloat1
 
 }  // namespace tc3
 
-size_t tc3_dgrad_image_bytes() { return (size_t)2 * 3 * 2 * tc3::WTILE_BYTES; }      // hi + lo, 3 ky, 2 K-steps
+size_t tc3_dgrad_slot_image_bytes(int nconv) { return (size_t)2 * 3 * (2 * nconv) * tc3::WTILE_BYTES; }      // per 32-channel group: hi + lo, 3 ky
 
-int pack_tc3_dgrad_images(const float* wf, void* img, int cin_buf, cudaStream_t st) {
-  const int ngroups = cdiv(cin_buf, 32);
-  const int total = 3 * 32 * tc3::NB * ngroups;
-  tc3::pack_tc3_dgrad_kernel<<<cdiv(total, 256), 256, 0, st>>>(wf, reinterpret_cast<__nv_bfloat16*>(img), cin_buf, ngroups);
-  SELFC_LAUNCH_CHECK("pack_tc3_dgrad_kernel");
+int pack_tc3_dgrad_slot_images(const float* const wf[4], const int cin[4], void* img, int c0, int ncover, int nconv, cudaStream_t st) {
+  SELFC_CHECK_ARG(nconv >= 1 && nconv <= 4 && ncover >= 1 && c0 >= 0, "dgrad slot images: bad slot");
+  tc3::DgradSlotSrc src;
+  for (int k = 0; k < 4; ++k) { src.wf[k] = wf[k]; src.cin[k] = cin[k]; }
+  const int ngroups = cdiv(ncover, 32);
+  const int total = 3 * 32 * nconv * tc3::NB * ngroups;
+  tc3::pack_tc3_dgrad_slot_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(img), c0, ncover, nconv, ngroups);
+  SELFC_LAUNCH_CHECK("pack_tc3_dgrad_slot_kernel");
   return 0;
 }
 

@@ -29,7 +29,7 @@ struct DenseW {            // one D2DTInput in kernel layout
   TcTempW t5;              // conv5 image (BF16 mode)
   void* f5img = nullptr;   // BF16 mode, cout == 3 (F blocks): conv5's taps as a pointwise GEMM inside the fused dense-block kernel
   // BF16X3 training: input-gradient images, packed on the first backward after every weight load (dg_valid)
-  void* dg_img[4] = {};    // conv1..4: ceil(cin_k / 32) images of tc3_dgrad_image_bytes()
+  void* dg_img[4] = {};    // slots X, x1, x2, x3 of the buffer: pack_tc3_dgrad_slot_images (4, 3, 2, 1 contributing convs)
   TcTempW dg5[2];          // conv5: the buffer channels in two column groups (<= 96 each)
   int dg5_c0[2] = {}, dg5_n[2] = {};
   bool dg_valid = false;

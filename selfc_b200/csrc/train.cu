@@ -315,11 +315,13 @@ static int ensure_dgrad_images(const selfc_ctx* cctx, const DenseW& cW, float* z
   if (W.dg_valid) return 0;
   selfc_ctx* ctx = const_cast<selfc_ctx*>(cctx);
   std::lock_guard<std::mutex> lock(ctx->mu);
-  const size_t ib = tc3_dgrad_image_bytes();
-  for (int k = 0; k < 4; ++k) {
-    const int cin = W.xpad + kGrowth * k;
-    if (W.dg_img[k] == nullptr) SELFC_CUDA(cudaMalloc(&W.dg_img[k], ib * cdiv(cin, 32)));
-    SELFC_TRY(pack_tc3_dgrad_images(W.w[k], W.dg_img[k], cin, st));
+  // slot s of the dense buffer (s = 0: X, s >= 1: x_s) receives conv_{s+1..4}^T: 4 - s contributing convs
+  const float* wf[4] = {W.w[0], W.w[1], W.w[2], W.w[3]};
+  const int cins[4] = {W.xpad, W.xpad + kGrowth, W.xpad + 2 * kGrowth, W.xpad + 3 * kGrowth};
+  for (int sl = 0; sl < 4; ++sl) {
+    const int c0 = sl == 0 ? 0 : W.xpad + kGrowth * (sl - 1), ncover = sl == 0 ? W.xpad : kGrowth, nconv = 4 - sl;
+    if (W.dg_img[sl] == nullptr) SELFC_CUDA(cudaMalloc(&W.dg_img[sl], tc3_dgrad_slot_image_bytes(nconv) * cdiv(ncover, 32)));
+    SELFC_TRY(pack_tc3_dgrad_slot_images(wf, cins, W.dg_img[sl], c0, ncover, nconv, st));
   }
   const int cin5 = W.xpad + 4 * kGrowth, nb = (W.cout + 15) & ~15;
   if (ctx->dg_wtmp == nullptr) SELFC_CUDA(cudaMalloc(&ctx->dg_wtmp, (size_t)192 * 64 * 3 * sizeof(float)));
@@ -396,7 +398,9 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
     const int g_pitch = k < 4 ? pitch : gy_pitch;
     const int g_off = k < 4 ? slot : 0;
     if (k < 4) {
-      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, gslabM, buf, pitch, slabM, slot, M, dg_tc ? gslab : nullptr);
+      // (the masked gradients of conv4, conv3, ... are kept side by side as (hi, lo) slabs: the K operand of the input-gradient launches)
+      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, gslabM, buf, pitch, slabM, slot, M,
+                                                            dg_tc ? gslab + (size_t)(2 * (3 - k)) * M * 16 : nullptr);
       SELFC_LAUNCH_CHECK("lrelu_bwd_kernel");
     }
     float* wd = scratch;
@@ -439,16 +443,20 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       continue;
     }
     if (dg_tc) {
-      // one launch per conv: all ceil(cin / 32) weight images resident, every tile visited once per 32-channel group
+      // slot by slot: with conv_{k+1}'s masked output gradient in place, the buffer slot it reads LAST -- x_k, or X for k = 0 -- has all
+      // its contributions available: conv5's (stored above) + one launch with the gradients of conv4..conv_{k+1} concatenated in K
+      // (K = 32 (4 - k)), accumulated ONCE.  (Conv by conv, a channel was read-modified-written once per later conv.)
+      const int nconv = 4 - k;
+      const int c0 = k == 0 ? 0 : W.xpad + kGrowth * (k - 1), ncover = k == 0 ? W.xpad : kGrowth;
       TcConvW tw;
       tw.img = W.dg_img[k];                   // presence only: the (hi, lo) form reads img_x2
       tw.img_x2 = W.dg_img[k];
-      tw.img_bytes = tc3_dgrad_image_bytes() / 2;
-      tw.cin_buf = 32;
+      tw.img_bytes = tc3_dgrad_slot_image_bytes(nconv) / 2;
+      tw.cin_buf = 32 * nconv;
       tw.bias = zero_bias;
       TcAccum acc;
-      acc.out = gbuf; acc.pitch = pitch; acc.off = 0; acc.n = cin; acc.ngroups = cdiv(cin, 32); acc.slabM = gslabM;
-      SELFC_TRY(launch_conv3x3_tc(tw, reinterpret_cast<__nv_bfloat16*>(gslab), M, 32, 0, d.B * d.T, d.h, d.w, st, nullptr, nullptr, true, &acc));
+      acc.out = gbuf; acc.pitch = pitch; acc.off = c0; acc.n = ncover; acc.ngroups = cdiv(ncover, 32); acc.slabM = gslabM;
+      SELFC_TRY(launch_conv3x3_tc(tw, reinterpret_cast<__nv_bfloat16*>(gslab), M, 32 * nconv, 0, d.B * d.T, d.h, d.w, st, nullptr, nullptr, true, &acc));
       continue;
     }
     const long long wtot = (long long)taps * cout4 * npd;
