@@ -184,6 +184,152 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   }
 }
 
+// ---- spatial convs on narrow frames: sliding window of activation tiles ----------------------------------------------------------
+// The kernel above fetches three row-shifted activation tiles per stage, i.e. every tile three times (from L2: the planes fit, but at
+// four septuplets per step the launches run at the L2 -> SM bandwidth, 5 TB/s, not at the tensor pipe).  When the row pitch is R <= 4
+// tiles, stage s needs the tiles s - R, s, s + R of the plane: a ring of NA = 11 tiles (hi + lo, 16 KB each) holds the window, every tile
+// is fetched ONCE per CTA (plus 2 R halo tiles per K range) and released after the last stage that reads it (stage index = tile index).
+// The gradient tiles keep their own 3-slot ring.  Same MMAs, same accumulators, same epilogue.
+constexpr int WIN_NA = 11;
+constexpr int WIN_NB = 3;
+constexpr int WIN_A_SLOT = 2 * A_TILE;                  // hi + lo
+constexpr int WIN_B_SLOT = 2 * 96 * KT * 2;             // hi + lo blocks of 96 rows x 64 bytes
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_window_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                      const __grid_constant__ CUtensorMap tmap_g, const Params p, const int R) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t b_base = base + WIN_NA * WIN_A_SLOT;
+  const uint32_t bar_base = b_base + WIN_NB * WIN_B_SLOT;
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (WIN_NA + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * WIN_NA + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * WIN_NA + WIN_NB + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * WIN_NA + 2 * WIN_NB);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WIN_NA + 2 * WIN_NB + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(gen_base + WIN_NA * WIN_A_SLOT + WIN_NB * WIN_B_SLOT + 8 * (2 * WIN_NA + 2 * WIN_NB + 1));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int mt = (int)blockIdx.x % p.mtiles;
+  const int split = (int)blockIdx.x / p.mtiles;
+  const int per = (p.ktiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = split * per, k1 = min(p.ktiles, k0 + per);
+  const int nt = k1 - k0;                                // stages of this CTA; A tiles i = 0 .. nt + 2R - 1 <-> plane tiles k0 - R + i
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < WIN_NA; ++s) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < WIN_NB; ++s) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int b_half = 96 * KT * 2;
+
+  if (nt > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===================== TMA producer: A tile i, then the gradient tile of stage i - 2R =====================
+        for (int i = 0; i < nt + 2 * R; ++i) {
+          const int slot = i % WIN_NA;
+          mbar_wait(aempty(slot), (uint32_t)((i / WIN_NA) & 1) ^ 1u, p.err, 44);
+          mbar_expect_tx(afull(slot), (uint32_t)(2 * p.arows * KT * 2));
+          const int P0 = (k0 - R + i) * KT;
+          for (int hl = 0; hl < 2; ++hl) tma_load_3d(base + slot * WIN_A_SLOT + hl * A_TILE, &tmap_a, afull(slot), P0, mt * ROWS, hl);
+          const int s = i - 2 * R;
+          if (s >= 0) {
+            const int bs = s % WIN_NB;
+            mbar_wait(bempty(bs), (uint32_t)((s / WIN_NB) & 1) ^ 1u, p.err, 45);
+            mbar_expect_tx(bfull(bs), (uint32_t)(2 * b_half));
+            for (int hl = 0; hl < 2; ++hl) tma_load_3d(b_base + bs * WIN_B_SLOT + hl * b_half, &tmap_g, bfull(bs), (k0 + s) * KT, 0, hl);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = umma_idesc_bf16(ROWS, 96);
+      const uint32_t hi_sw = desc_hi(512, 4);
+      for (int s = 0; s < nt; ++s) {
+        // the three tiles of this stage: i = s, s + R, s + 2R (each waited on its own barrier / phase), and its gradient tile
+        uint32_t a_addr[3];
+#pragma unroll
+        for (int sh = 0; sh < 3; ++sh) {
+          const int i = s + sh * R;
+          mbar_wait(afull(i % WIN_NA), (uint32_t)((i / WIN_NA) & 1), p.err, 46);
+          a_addr[sh] = base + (uint32_t)(i % WIN_NA) * WIN_A_SLOT;
+        }
+        const int bs = s % WIN_NB;
+        mbar_wait(bfull(bs), (uint32_t)((s / WIN_NB) & 1), p.err, 47);
+        tc_fence_after();
+        const uint32_t st_b = b_base + (uint32_t)bs * WIN_B_SLOT;
+        const uint32_t b_hi = desc_lo(st_b, 16), b_lo = desc_lo(st_b + b_half, 16);
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint64_t bd = desc_join((term == 1 ? b_lo : b_hi) + 2u * ks, hi_sw);
+#pragma unroll
+            for (int sh = 0; sh < 3; ++sh) {
+              const uint32_t a_lo = desc_lo(a_addr[sh] + (term == 2 ? A_TILE : 0), 16);
+              umma_bf16_elect(tmem_base + (uint32_t)(sh * 96), desc_join(a_lo + 2u * ks, hi_sw), bd, idesc, (s > 0 || ks > 0 || term > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit_elect(aempty(s % WIN_NA));          // tile i = s: this was its last reader
+        umma_commit_elect(bempty(bs));
+      }
+      umma_commit_elect(done_bar);
+    } else {
+      // ===================== epilogue warps 2..5 =====================
+      const int q = warp & 3;
+      const int row = mt * ROWS + q * 32 + lane;
+      const int c = row - 1;
+      mbar_wait(done_bar, 0, p.err, 48);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool is_bias = row == 0;
+      const bool is_w = c >= 0 && c < p.cin;
+      for (int sh = 0; sh < 3; ++sh) {
+        for (int n0 = 0; n0 < 96; n0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + (uint32_t)(sh * 96 + n0), r);
+          tmem_ld_wait();
+          const int kx = n0 / 32, nn = n0 - kx * 32;
+          const int tap = sh * 3 + kx;
+          if (is_w) {
+            float* o = p.dw + ((size_t)tap * p.cin + c) * p.np + nn;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              red_add4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else if (is_bias && sh == 1 && kx == 1) {
+            float* o = p.dw + (size_t)p.taps * p.cin * p.np + nn;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              red_add4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 // ---- plane builders ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long plane_index(long long m, const WgGeom& g) {
   const long long hw = (long long)g.h * g.w;
@@ -274,10 +420,23 @@ __global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __rest
 
 }  // namespace wg
 
+// SELFC_WGRAD_WINDOW: the sliding-window form of the spatial kernel (and the 32-pixel row pitch it needs)
+static bool wg_window_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SELFC_WGRAD_WINDOW");
+    on = e ? (atoi(e) != 0 ? 1 : 0) : kWgWindowDefault;
+  }
+  return on == 1;
+}
+
 WgGeom wg_geometry(const Dims& d) {
   WgGeom g;
   g.B = d.B; g.T = d.T; g.h = d.h; g.w = d.w;
-  g.Wp = (d.w + 2 + 7) & ~7;
+  // row pitch: a multiple of 8 pixels (16-byte TMA coordinates); narrow frames take a multiple of 32 so that a row shift is a whole
+  // number R <= 4 of 32-pixel tiles and the spatial kernel can keep a sliding window of activation tiles (wgrad_tc_window_kernel)
+  const int wp32 = (d.w + 2 + 31) & ~31;
+  g.Wp = wg_window_enabled() && wp32 / 32 <= kWgWindowMaxR ? wp32 : ((d.w + 2 + 7) & ~7);
   g.Fp = (long long)(d.h + 2) * g.Wp;
   g.P = ((long long)d.B * (d.T + 1) + 1) * g.Fp;
   g.Pa = (g.P + 31) & ~31ll;
@@ -394,6 +553,18 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
     SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
+  }
+  // spatial convs on narrow frames: the sliding-window form (SELFC_WGRAD_WINDOW=0 / 1: the three-fetch form / the window form)
+  if (wg_window_enabled() && kind == WG_SPATIAL && g.Wp % 32 == 0 && g.Wp / 32 <= kWgWindowMaxR && np == 32) {
+    const int wsmem = wg::WIN_NA * wg::WIN_A_SLOT + wg::WIN_NB * wg::WIN_B_SLOT + wg::BAR_BYTES + 1024;
+    static bool wset[64] = {};
+    if (dev >= 0 && dev < 64 && !wset[dev]) {
+      SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      wset[dev] = true;
+    }
+    wg::wgrad_tc_window_kernel<<<p.mtiles * p.nsplit, wg::THREADS, wsmem, st>>>(tmap_a, tmap_g, p, g.Wp / 32);
+    SELFC_LAUNCH_CHECK("wgrad_tc_window_kernel");
+    return 0;
   }
   if (p.nsh == 1) wg::wgrad_tc_kernel<1><<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
   else wg::wgrad_tc_kernel<3><<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);

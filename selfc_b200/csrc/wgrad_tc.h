@@ -8,6 +8,8 @@
 namespace selfc {
 
 constexpr int kWgRows = 257;       // AT rows: the ones row + up to 256 channels (dense buffers: 192; the GMM head's 256-channel layer)
+constexpr int kWgWindowDefault = 0;  // default of SELFC_WGRAD_WINDOW (1 once measured faster on the box)
+constexpr int kWgWindowMaxR = 4;    // row pitches up to 4 x 32 pixels take the sliding-window form of the spatial kernel
 constexpr int kWgSpatialRows = 96;  // GT rows [0, 96): three one-pixel-shifted copies of a spatial conv's 32 gradient channels
 constexpr int kWgGradRows = 160;    // ... rows [96, 160): conv5's (unshifted) gradient, up to 64 channels
 
