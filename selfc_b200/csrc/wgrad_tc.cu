@@ -58,15 +58,17 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int NSH>
+// NC: the MMA N as a compile-time constant (instruction descriptor, accumulator columns and the lo-tile offset then cost no registers)
+template <int NSH, int NC>
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                const __grid_constant__ CUtensorMap tmap_g, const Params p) {
+  constexpr int N = NC;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int NST = p.nst;
   const int a_bytes = NSH * 2 * A_TILE;                   // [shift][hi|lo] tiles of 128 rows x 64 bytes
-  const int b_half = p.N * KT * 2;                        // hi (then lo) block of N rows x 64 bytes
+  const int b_half = N * KT * 2;                        // hi (then lo) block of N rows x 64 bytes
   const int stage_bytes = a_bytes + 2 * b_half;           // multiple of 1024: N is a multiple of 16
   const uint32_t bar_base = base + NST * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -116,25 +118,32 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       }
     } else if (warp == 1) {
       // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-      const uint32_t idesc = umma_idesc_bf16(ROWS, p.N);
+      const uint32_t idesc = umma_idesc_bf16(ROWS, N);
       const uint32_t hi_sw = desc_hi(512, 4);            // K-major SWIZZLE_64B: 8-row groups 512 bytes apart
+      // Everything an MMA needs beyond ONE stage-dependent descriptor base per operand is a compile-time offset (tile index, K step) or
+      // hoisted out of the loop: the first version formed 18 independent descriptors per stage, the uniform registers spilled and every
+      // issue paid ~4 R2UR moves (68 for 18 MMAs in the SASS; 2,300 cycles per stage against 870 of tensor time)
+      const uint32_t b_lo_off = (uint32_t)b_half >> 4;
+      uint32_t dcol[NSH];
+#pragma unroll
+      for (int sh = 0; sh < NSH; ++sh) dcol[sh] = tmem_base + (uint32_t)(sh * N);
       int s = 0;
       uint32_t ph = 0;
       for (int kt = k0; kt < k1; ++kt) {
         mbar_wait(full_bar(s), ph, p.err, 42);
         tc_fence_after();
-        const uint32_t st_a = base + s * stage_bytes, st_b = st_a + a_bytes;
-        const uint32_t b_hi = desc_lo(st_b, 16), b_lo = desc_lo(st_b + b_half, 16);
+        const uint32_t st_a = base + s * stage_bytes;
+        const uint32_t a0 = desc_lo(st_a, 16), b0 = desc_lo(st_a + a_bytes, 16);
+        const uint32_t first = kt > k0 ? 1u : 0u;
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
 #pragma unroll
           for (int term = 0; term < 3; ++term) {
-            const uint64_t bd = desc_join((term == 1 ? b_lo : b_hi) + 2u * ks, hi_sw);
+            const uint64_t bd = desc_join(b0 + (term == 1 ? b_lo_off : 0u) + 2u * ks, hi_sw);
 #pragma unroll
             for (int sh = 0; sh < NSH; ++sh) {            // consecutive MMAs go to different accumulators
-              const uint32_t a_lo = desc_lo(st_a + (sh * 2 + (term == 2 ? 1 : 0)) * A_TILE, 16);
-              umma_bf16_elect(tmem_base + (uint32_t)(sh * p.N), desc_join(a_lo + 2u * ks, hi_sw), bd, idesc,
-                              (kt > k0 || ks > 0 || term > 0) ? 1u : 0u);
+              const uint64_t ad = desc_join(a0 + (uint32_t)(((sh * 2 + (term == 2 ? 1 : 0)) * A_TILE) >> 4) + 2u * ks, hi_sw);
+              umma_bf16_elect(dcol[sh], ad, bd, idesc, (ks > 0 || term > 0) ? 1u : first);
             }
           }
         }
@@ -153,9 +162,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       const bool is_bias = row == 0;
       const bool is_w = c >= 0 && c < p.cin;
       for (int sh = 0; sh < NSH; ++sh) {
-        for (int n0 = 0; n0 < p.N; n0 += 16) {
+        for (int n0 = 0; n0 < N; n0 += 16) {
           uint32_t r[16];
-          tmem_ld16(lane_addr + (uint32_t)(sh * p.N + n0), r);      // warp-uniform
+          tmem_ld16(lane_addr + (uint32_t)(sh * N + n0), r);      // warp-uniform
           tmem_ld_wait();
           const int kx = n0 / p.nb, nn = n0 - kx * p.nb;            // 16-column groups never straddle a kx block (nb % 16 == 0)
           const int tap = p.nkx == 3 ? sh * 3 + kx : sh;
@@ -262,27 +271,27 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_window_kernel(const __gri
       const uint32_t hi_sw = desc_hi(512, 4);
       for (int s = 0; s < nt; ++s) {
         // the three tiles of this stage: i = s, s + R, s + 2R (each waited on its own barrier / phase), and its gradient tile
-        uint32_t a_addr[3];
+        uint32_t a0[3];
 #pragma unroll
         for (int sh = 0; sh < 3; ++sh) {
           const int i = s + sh * R;
           mbar_wait(afull(i % WIN_NA), (uint32_t)((i / WIN_NA) & 1), p.err, 46);
-          a_addr[sh] = base + (uint32_t)(i % WIN_NA) * WIN_A_SLOT;
+          a0[sh] = desc_lo(base + (uint32_t)(i % WIN_NA) * WIN_A_SLOT, 16);
         }
         const int bs = s % WIN_NB;
         mbar_wait(bfull(bs), (uint32_t)((s / WIN_NB) & 1), p.err, 47);
         tc_fence_after();
-        const uint32_t st_b = b_base + (uint32_t)bs * WIN_B_SLOT;
-        const uint32_t b_hi = desc_lo(st_b, 16), b_lo = desc_lo(st_b + b_half, 16);
+        const uint32_t b0 = desc_lo(b_base + (uint32_t)bs * WIN_B_SLOT, 16);
+        const uint32_t first = s > 0 ? 1u : 0u;
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
 #pragma unroll
           for (int term = 0; term < 3; ++term) {
-            const uint64_t bd = desc_join((term == 1 ? b_lo : b_hi) + 2u * ks, hi_sw);
+            const uint64_t bd = desc_join(b0 + (term == 1 ? (uint32_t)(96 * KT * 2 >> 4) : 0u) + 2u * ks, hi_sw);
 #pragma unroll
             for (int sh = 0; sh < 3; ++sh) {
-              const uint32_t a_lo = desc_lo(a_addr[sh] + (term == 2 ? A_TILE : 0), 16);
-              umma_bf16_elect(tmem_base + (uint32_t)(sh * 96), desc_join(a_lo + 2u * ks, hi_sw), bd, idesc, (s > 0 || ks > 0 || term > 0) ? 1u : 0u);
+              const uint64_t ad = desc_join(a0[sh] + (term == 2 ? (uint32_t)(A_TILE >> 4) : 0u) + 2u * ks, hi_sw);
+              umma_bf16_elect(tmem_base + (uint32_t)(sh * 96), ad, bd, idesc, (ks > 0 || term > 0) ? 1u : first);
             }
           }
         }
@@ -550,8 +559,12 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !smem_set[dev]) {
-    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<3, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<3, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SELFC_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set[dev] = true;
   }
   // spatial convs on narrow frames: the sliding-window form (SELFC_WGRAD_WINDOW=0 / 1: the three-fetch form / the window form)
@@ -566,8 +579,17 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
     SELFC_LAUNCH_CHECK("wgrad_tc_window_kernel");
     return 0;
   }
-  if (p.nsh == 1) wg::wgrad_tc_kernel<1><<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
-  else wg::wgrad_tc_kernel<3><<<p.mtiles * p.nsplit, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  const int grid = p.mtiles * p.nsplit;
+  if (p.nsh == 3 && p.N == 96) wg::wgrad_tc_kernel<3, 96><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  else if (p.nsh == 3 && p.N == 64) wg::wgrad_tc_kernel<3, 64><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  else if (p.nsh == 3 && p.N == 48) wg::wgrad_tc_kernel<3, 48><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  else if (p.nsh == 3 && p.N == 16) wg::wgrad_tc_kernel<3, 16><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  else if (p.nsh == 1 && p.N == 64) wg::wgrad_tc_kernel<1, 64><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  else if (p.nsh == 1 && p.N == 16) wg::wgrad_tc_kernel<1, 16><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  else {
+    set_error("wgrad_tc: no instantiation for %d shifts x N = %d", p.nsh, p.N);
+    return SELFC_E_UNSUPPORTED;
+  }
   SELFC_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;
 }
