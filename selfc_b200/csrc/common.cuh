@@ -83,6 +83,13 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
+// First statement of a kernel launched through launch_chain() (wgrad_tc.h): let the next kernel of the stream be scheduled, then wait
+// until the previous kernel's results are visible.  Without the launch attribute both instructions do nothing.
+__device__ __forceinline__ void chain_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // 4 consecutive elements -> float4
 __device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {

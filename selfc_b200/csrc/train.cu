@@ -99,6 +99,7 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict
 template <typename E>
 __global__ void lrelu_bwd_kernel(float* __restrict__ g, long long gslabM, const E* __restrict__ y, int pitch, long long slabM, int off, long long M,
                                  bfx2* __restrict__ gslab = nullptr) {
+  chain_entry();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long m = idx >> 3;
   const int c = (int)(idx & 7) * 4;
@@ -249,6 +250,7 @@ static int wgrad_splits(long long M, int base_ctas) {
 // scratch [taps][cin_buf][np] (+ [np] bias) in buffer-channel order -> reference layouts dW [cout][cin_ref][taps], db [cout] (accumulating)
 __global__ void wgrad_unpack_kernel(const float* __restrict__ dw, float* __restrict__ gw, float* __restrict__ gb, int cout, int cin_ref,
                                     int taps, int cin_buf, int xreal, int xpad, int np) {
+  chain_entry();
   const long long total = (long long)cout * cin_ref * taps;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < cout) gb[idx] += dw[(long long)taps * cin_buf * np + idx];
@@ -299,6 +301,7 @@ __global__ void dgrad5_ref_kernel(const float* __restrict__ wf, float* __restric
 }
 // fp32 pixel-major [M][spitch] columns [0, ncol) -> (hi, lo) slabs [nb / 16][M], columns >= ncol zero
 __global__ void cols_to_slab_kernel(bfx2* __restrict__ dst, int nb, const float* __restrict__ src, int spitch, int ncol, long long M) {
+  chain_entry();
   const int per = nb / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * per) return;
@@ -399,8 +402,8 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
     const int g_off = k < 4 ? slot : 0;
     if (k < 4) {
       // (the masked gradients of conv4, conv3, ... are kept side by side as (hi, lo) slabs: the K operand of the input-gradient launches)
-      lrelu_bwd_kernel<E><<<cdiv(M * 8, 256), 256, 0, st>>>(gbuf, gslabM, buf, pitch, slabM, slot, M,
-                                                            dg_tc ? gslab + (size_t)(2 * (3 - k)) * M * 16 : nullptr);
+      SELFC_CUDA(launch_chain(lrelu_bwd_kernel<E>, dim3((unsigned)cdiv(M * 8, 256)), 256, 0, st, gbuf, gslabM, buf, pitch, slabM, slot, M,
+                              dg_tc ? gslab + (size_t)(2 * (3 - k)) * M * 16 : static_cast<bfx2*>(nullptr)));
       SELFC_LAUNCH_CHECK("lrelu_bwd_kernel");
     }
     float* wd = scratch;
@@ -408,12 +411,14 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
     // weight / bias gradients
     if (gparams != nullptr && gparams[2 * k] != nullptr) {
       const size_t dw_floats = (size_t)(taps * cin + 1) * W.np[k];
-      SELFC_CUDA(cudaMemsetAsync(dw, 0, dw_floats * sizeof(float), st));
       if (wg_tc) {
+        // (the plane builder clears the split-K scratch on its way: mask -> planes -> weight gradient -> unpack -> input gradient stays one
+        // chain of kernels, launch_chain)
         const int nb = k < 4 ? kGrowth : (cout + 15) & ~15;
-        SELFC_TRY(launch_wg_planes_grad(g, g_pitch, g_off, k < 4 ? gslabM : 0, cout, nb, k == 4, d, geom, planes, st));
+        SELFC_TRY(launch_wg_planes_grad(g, g_pitch, g_off, k < 4 ? gslabM : 0, cout, nb, k == 4, d, geom, planes, st, dw, (long long)dw_floats));
         SELFC_TRY(launch_wgrad_tc(planes, geom, cin, cout, nb, k == 4 ? WG_TEMPORAL : WG_SPATIAL, dw, W.np[k], st));
       } else {
+        SELFC_CUDA(cudaMemsetAsync(dw, 0, dw_floats * sizeof(float), st));
         SELFC_CHECK_ARG(gslabM == 0, "the fp32-FMA weight gradient reads a pixel-major gradient buffer");
         const int splits = wgrad_splits(M, (taps + 1) * cdiv(cout, 32) * cdiv(cin, WG_C));
         dim3 grid((taps + 1) * cdiv(cout, 32), cdiv(cin, WG_C), splits);
@@ -422,15 +427,15 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
       }
       const int cin_ref = W.cin + kGrowth * k;
       const long long total = (long long)cout * cin_ref * taps;
-      wgrad_unpack_kernel<<<cdiv(total > cout ? total : cout, 256), 256, 0, st>>>(dw, gparams[2 * k], gparams[2 * k + 1], cout, cin_ref, taps, cin,
-                                                                                W.cin, W.xpad, W.np[k]);
+      SELFC_CUDA(launch_chain(wgrad_unpack_kernel, dim3((unsigned)cdiv(total > cout ? total : cout, 256)), 256, 0, st, (const float*)dw, gparams[2 * k],
+                              gparams[2 * k + 1], cout, cin_ref, taps, cin, W.cin, W.xpad, W.np[k]));
       SELFC_LAUNCH_CHECK("wgrad_unpack_kernel");
     }
     // input gradient: the forward kernel on the flipped / transposed weights, accumulated into gbuf[0:cin)
     if (dg_tc && k == 4) {
       // conv5: gy -> (hi, lo) slabs, then the temporal kernel per column group, STORING into the still-zero gradient buffer
       const int nb = (cout + 15) & ~15;
-      cols_to_slab_kernel<<<cdiv(M * (nb / 4), 256), 256, 0, st>>>(gslab, nb, gy, gy_pitch, cout, M);
+      SELFC_CUDA(launch_chain(cols_to_slab_kernel, dim3((unsigned)cdiv(M * (nb / 4), 256)), 256, 0, st, gslab, nb, gy, gy_pitch, cout, M));
       SELFC_LAUNCH_CHECK("cols_to_slab_kernel");
       for (int gI = 0; gI < 2; ++gI) {
         if (W.dg5_n[gI] <= 0) continue;

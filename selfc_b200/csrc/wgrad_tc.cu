@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // launched through launch_chain(): barriers and tensor memory are set up while the plane builder before this kernel drains
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (k0 < k1) {
     if (warp == 0) {
@@ -352,6 +355,7 @@ __device__ __forceinline__ long long plane_index(long long m, const WgGeom& g) {
 // activations: slab-planar (hi, lo) dense buffer [pitch/16][M][16 hi | 16 lo] -> AT planes [2][193][Pa]; grid (pixels / 256, slabs)
 __global__ void __launch_bounds__(256) wg_planes_act_kernel(const __nv_bfloat16* __restrict__ buf, long long M, __nv_bfloat16* __restrict__ at,
                                                             const WgGeom g) {
+  chain_entry();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int slab = blockIdx.y;
@@ -397,10 +401,14 @@ __global__ void __launch_bounds__(256) wg_planes_act_f32_kernel(const float* __r
 // columns of the same row, so the three copies never collide with real pixels of a neighbouring row); conv5 (ncopies = 1): rows
 // 96 + n at P, rows >= ncols zero.  The two forms use disjoint rows: each row is always written at the same set of positions.
 __global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __restrict__ gsrc, int pitch, int off, long long sslabM, int ncols, int nb,
-                                                             int ncopies, long long M, __nv_bfloat16* __restrict__ gt, const WgGeom g) {
+                                                             int ncopies, long long M, __nv_bfloat16* __restrict__ gt, const WgGeom g,
+                                                             float* __restrict__ zero, long long zero_n) {
   // one thread per (4-channel group, pixel), pixels fastest: a warp writes 64 contiguous bytes per plane row and store instruction,
   // and the launch has nb / 4 times the threads of a thread-per-pixel form (at 50 K pixels that form left the SMs a third full)
+  chain_entry();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // the split-K scratch of the weight-gradient launch that follows (one memset node per conv less in the chain)
+  for (long long i = idx; i < zero_n; i += (long long)gridDim.x * blockDim.x) zero[i] = 0.f;
   if (idx >= M * (nb / 4)) return;
   const int n0 = (int)(idx / M) * 4;
   const long long m = idx - (long long)(n0 / 4) * M;
@@ -428,6 +436,15 @@ __global__ void __launch_bounds__(256) wg_planes_grad_kernel(const float* __rest
 }
 
 }  // namespace wg
+
+bool train_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SELFC_TRAIN_PDL");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on == 1;
+}
 
 // SELFC_WGRAD_WINDOW: the sliding-window form of the spatial kernel (and the 32-pixel row pitch it needs)
 static bool wg_window_enabled() {
@@ -458,7 +475,8 @@ int launch_wg_planes_act(const bfx2* buf, int pitch, const Dims& d, const WgGeom
   SELFC_CHECK_ARG(pitch % 16 == 0 && pitch <= kWgRows - 1, "wgrad planes: pitch %d", pitch);
   const long long M = d.M();
   dim3 grid(cdiv(M, 256), pitch / 16);
-  wg::wg_planes_act_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(buf), M, reinterpret_cast<__nv_bfloat16*>(planes), g);
+  SELFC_CUDA(launch_chain(wg::wg_planes_act_kernel, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(buf), M,
+                          reinterpret_cast<__nv_bfloat16*>(planes), g));
   SELFC_LAUNCH_CHECK("wg_planes_act_kernel");
   return 0;
 }
@@ -471,11 +489,12 @@ int launch_wg_planes_act_f32(const float* src, int pitch, int C, const Dims& d, 
 }
 
 int launch_wg_planes_grad(const float* gsrc, int pitch, int off, long long sslabM, int ncols, int nb, bool temporal, const Dims& d,
-                          const WgGeom& g, void* planes, cudaStream_t st) {
+                          const WgGeom& g, void* planes, cudaStream_t st, float* zero, long long zero_n) {
   SELFC_CHECK_ARG(nb % 16 == 0 && nb <= kWgGradRows - kWgSpatialRows && ncols <= nb && (temporal || nb == 32),
                   "wgrad planes: %d gradient columns", ncols);
   __nv_bfloat16* gt = reinterpret_cast<__nv_bfloat16*>(planes) + (size_t)2 * kWgRows * g.Pa;
-  wg::wg_planes_grad_kernel<<<cdiv(d.M() * (nb / 4), 256), 256, 0, st>>>(gsrc, pitch, off, sslabM, ncols, nb, temporal ? 1 : 3, d.M(), gt, g);
+  SELFC_CUDA(launch_chain(wg::wg_planes_grad_kernel, dim3((unsigned)cdiv(d.M() * (nb / 4), 256)), 256, 0, st, gsrc, pitch, off, sslabM, ncols, nb,
+                          temporal ? 1 : 3, d.M(), gt, g, zero, zero_n));
   SELFC_LAUNCH_CHECK("wg_planes_grad_kernel");
   return 0;
 }
@@ -580,12 +599,12 @@ int launch_wgrad_tc(void* planes, const WgGeom& g, int cin, int ncols, int nb, i
     return 0;
   }
   const int grid = p.mtiles * p.nsplit;
-  if (p.nsh == 3 && p.N == 96) wg::wgrad_tc_kernel<3, 96><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
-  else if (p.nsh == 3 && p.N == 64) wg::wgrad_tc_kernel<3, 64><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
-  else if (p.nsh == 3 && p.N == 48) wg::wgrad_tc_kernel<3, 48><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
-  else if (p.nsh == 3 && p.N == 16) wg::wgrad_tc_kernel<3, 16><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
-  else if (p.nsh == 1 && p.N == 64) wg::wgrad_tc_kernel<1, 64><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
-  else if (p.nsh == 1 && p.N == 16) wg::wgrad_tc_kernel<1, 16><<<grid, wg::THREADS, smem, st>>>(tmap_a, tmap_g, p);
+  if (p.nsh == 3 && p.N == 96) SELFC_CUDA(launch_chain(wg::wgrad_tc_kernel<3, 96>, dim3((unsigned)grid), wg::THREADS, smem, st, tmap_a, tmap_g, p));
+  else if (p.nsh == 3 && p.N == 64) SELFC_CUDA(launch_chain(wg::wgrad_tc_kernel<3, 64>, dim3((unsigned)grid), wg::THREADS, smem, st, tmap_a, tmap_g, p));
+  else if (p.nsh == 3 && p.N == 48) SELFC_CUDA(launch_chain(wg::wgrad_tc_kernel<3, 48>, dim3((unsigned)grid), wg::THREADS, smem, st, tmap_a, tmap_g, p));
+  else if (p.nsh == 3 && p.N == 16) SELFC_CUDA(launch_chain(wg::wgrad_tc_kernel<3, 16>, dim3((unsigned)grid), wg::THREADS, smem, st, tmap_a, tmap_g, p));
+  else if (p.nsh == 1 && p.N == 64) SELFC_CUDA(launch_chain(wg::wgrad_tc_kernel<1, 64>, dim3((unsigned)grid), wg::THREADS, smem, st, tmap_a, tmap_g, p));
+  else if (p.nsh == 1 && p.N == 16) SELFC_CUDA(launch_chain(wg::wgrad_tc_kernel<1, 16>, dim3((unsigned)grid), wg::THREADS, smem, st, tmap_a, tmap_g, p));
   else {
     set_error("wgrad_tc: no instantiation for %d shifts x N = %d", p.nsh, p.N);
     return SELFC_E_UNSUPPORTED;
