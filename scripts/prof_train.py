@@ -40,5 +40,5 @@ for e in prof.events():
         a[1] += e.device_time / 1e3 if hasattr(e, "device_time") else e.cuda_time / 1e3
 tot = sum(a[1] for a in agg.values())
 print(f"mode {mode}, {nb} septuplet(s): {sum(a[0] for a in agg.values())} kernels, {tot:.2f} ms of kernel time")
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
     print(f"{k:72s} {a[0]:5d} {a[1]:9.3f} ms {a[1] / tot:.3f}")

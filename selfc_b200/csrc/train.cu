@@ -388,7 +388,8 @@ int dense_block_backward(const selfc_ctx* ctx, const DenseW& W, const E* buf, in
     }
   }
   const long long gslabM = grad_slab(ctx, d);         // layout of gbuf (see grad_slab); implies wg_tc || gparams == nullptr, and dg_tc
-  SELFC_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)M * pitch * sizeof(float), st));
+  // (tensor-core input gradients: conv5's launches STORE all xpad + 128 buffer channels of every pixel first, nothing to clear)
+  if (!dg_tc) SELFC_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)M * pitch * sizeof(float), st));
   for (int k = 4; k >= 0; --k) {
     const int taps = k < 4 ? 9 : 3;
     const int tap_mode = k < 4 ? TAP_SPATIAL : TAP_TEMPORAL;
