@@ -42,3 +42,26 @@ tot = sum(a[1] for a in agg.values())
 print(f"mode {mode}, {nb} septuplet(s): {sum(a[0] for a in agg.values())} kernels, {tot:.2f} ms of kernel time")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
     print(f"{k:72s} {a[0]:5d} {a[1]:9.3f} ms {a[1] / tot:.3f}")
+
+# timeline: busy time (union of kernel intervals) against the span of the step, and which kernels the idle gaps follow
+ev = []
+for e in prof.events():
+    if e.device_type is not None and "cuda" in str(e.device_type).lower():
+        dur = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        ev.append((e.time_range.start, e.time_range.start + dur, e.name.split("(")[0].replace("void ", "").replace("selfc::", "")[:50]))
+ev.sort()
+span = ev[-1][1] - ev[0][0]
+busy, cur_end, gaps = 0.0, ev[0][0], collections.OrderedDict()
+for i, (a, b, name) in enumerate(ev):
+    if a > cur_end:
+        prev = ev[i - 1][2] if i else "-"
+        g = gaps.setdefault(prev + " -> " + name, [0, 0.0])
+        g[0] += 1
+        g[1] += a - cur_end
+        busy += b - a
+    else:
+        busy += max(0.0, b - cur_end)
+    cur_end = max(cur_end, b)
+print(f"span {span / 1e3:.2f} ms, busy {busy / 1e3:.2f} ms, idle {(span - busy) / 1e3:.2f} ms")
+for k, g in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+    print(f"{k:104s} {g[0]:5d} {g[1] / 1e3:8.3f} ms")

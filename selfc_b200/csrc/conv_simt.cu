@@ -10,6 +10,7 @@
 // memory in chunks of 16 with register prefetch (global loads of chunk i+1 overlap the FMAs of chunk i).
 #include "common.cuh"
 #include "kernels.h"
+#include "pack_batch.h"
 
 namespace selfc {
 
@@ -256,28 +257,58 @@ int launch_conv_simt<bfx2>(const ConvArgs<bfx2>&, cudaStream_t) {
 }
 
 // ---- weight packing ---------------------------------------------------------------------------------------
-__global__ void pack_conv_simt_kernel(const float* __restrict__ wref, const float* __restrict__ bref, float* __restrict__ wpk,
-                                      float* __restrict__ bpk, int cout, int cin_ref, int taps, int cin_buf, int xreal, int xpad,
-                                      int np) {
-  const long long total = (long long)taps * cin_buf * np;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < np) bpk[idx] = idx < cout ? bref[idx] : 0.f;
+struct PackSimtJob {
+  const float* wref;
+  const float* bref;
+  float* wpk;
+  float* bpk;
+  int cout, cin_ref, taps, cin_buf, xreal, xpad, np;
+  int pad;                 // (no implicit padding: the job tables are compared bytewise)
+};
+
+__device__ __forceinline__ void pack_conv_simt_body(const PackSimtJob& j, long long idx) {
+  const long long total = (long long)j.taps * j.cin_buf * j.np;
+  if (idx < j.np) j.bpk[idx] = idx < j.cout ? j.bref[idx] : 0.f;
   if (idx >= total) return;
-  const int n = (int)(idx % np);
-  const int c = (int)((idx / np) % cin_buf);
-  const int tap = (int)(idx / ((long long)np * cin_buf));
-  int cref = c < xreal ? c : (c < xpad ? -1 : c - xpad + xreal);
+  const int n = (int)(idx % j.np);
+  const int c = (int)((idx / j.np) % j.cin_buf);
+  const int tap = (int)(idx / ((long long)j.np * j.cin_buf));
+  int cref = c < j.xreal ? c : (c < j.xpad ? -1 : c - j.xpad + j.xreal);
   float v = 0.f;
-  if (n < cout && cref >= 0 && cref < cin_ref) v = wref[((long long)n * cin_ref + cref) * taps + tap];
-  wpk[idx] = v;
+  if (n < j.cout && cref >= 0 && cref < j.cin_ref) v = j.wref[((long long)n * j.cin_ref + cref) * j.taps + tap];
+  j.wpk[idx] = v;
+}
+
+__global__ void pack_conv_simt_kernel(const PackSimtJob j) { pack_conv_simt_body(j, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
+
+// every recorded job in one launch (pack_batch.h)
+__global__ void pack_conv_simt_multi_kernel(const PackSimtJob* __restrict__ jobs, const int* __restrict__ first, int njobs) {
+  const int ji = pack_find_job(first, njobs, blockIdx.x);
+  const PackSimtJob j = jobs[ji];
+  pack_conv_simt_body(j, (long long)(blockIdx.x - __ldg(first + ji)) * blockDim.x + threadIdx.x);
 }
 
 int launch_pack_conv_simt(const float* wref, const float* bref, float* wpk, float* bpk, int cout, int cin_ref, int taps,
                           int cin_buf, int xreal, int xpad, int np, cudaStream_t st) {
   const long long total = (long long)taps * cin_buf * np;
-  pack_conv_simt_kernel<<<cdiv(total > np ? total : np, 256), 256, 0, st>>>(wref, bref, wpk, bpk, cout, cin_ref, taps, cin_buf,
-                                                                           xreal, xpad, np);
+  const PackSimtJob j{wref, bref, wpk, bpk, cout, cin_ref, taps, cin_buf, xreal, xpad, np, 0};
+  const int nblocks = (int)cdiv(total > np ? total : np, 256);
+  if (PackBatch* pb = pack_batch_current()) {
+    pb->simt[pb->point].add(j, nblocks);
+    return 0;
+  }
+  pack_conv_simt_kernel<<<nblocks, 256, 0, st>>>(j);
   SELFC_LAUNCH_CHECK("pack_conv_simt_kernel");
+  return 0;
+}
+
+int flush_pack_conv_simt(JobTable& t, cudaStream_t st) {
+  if (t.njobs() <= 0) return 0;
+  const void* jobs = nullptr;
+  const int* first = nullptr;
+  SELFC_CUDA(t.sync(st, &jobs, &first));
+  pack_conv_simt_multi_kernel<<<t.first.back(), 256, 0, st>>>(static_cast<const PackSimtJob*>(jobs), first, t.njobs());
+  SELFC_LAUNCH_CHECK("pack_conv_simt_multi_kernel");
   return 0;
 }
 

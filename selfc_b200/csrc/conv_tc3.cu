@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "conv_tc.h"
+#include "pack_batch.h"
 #include "tc_ptx.cuh"
 
 namespace selfc {
@@ -490,11 +491,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tc3_kernel(const __grid_co
 // img_pair: the same rows split between the CTAs of a pair, [half(2)][ky][kstep][kcore(2)][ngroup(6)][r%8][k%8], half = r / 48
 // img_x2 (BF16X3 mode): the pair image with a hi and a lo tile per (ky, K-step), [half(2)][ky][kstep][hi|lo][kcore(2)][ngroup(6)][r%8][k%8],
 // hi = bf16(w), lo = bf16(w - hi)
-__global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ img_pair,
-                                __nv_bfloat16* __restrict__ img_x2, int cin_ref, int cin_buf, int xreal, int xpad) {
+struct PackTc3Job {
+  const float* wref;
+  const float* bref;       // conv bias [32] -> bias (the epilogue's copy)
+  __nv_bfloat16* img;
+  __nv_bfloat16* img_pair;
+  __nv_bfloat16* img_x2;
+  float* bias;
+  int cin_ref, cin_buf, xreal, xpad;
+};
+
+__device__ __forceinline__ void pack_tc3_body(const PackTc3Job& j, int idx) {
+  const float* __restrict__ wref = j.wref;
+  __nv_bfloat16* __restrict__ img = j.img;
+  __nv_bfloat16* __restrict__ img_pair = j.img_pair;
+  __nv_bfloat16* __restrict__ img_x2 = j.img_x2;
+  const int cin_ref = j.cin_ref, cin_buf = j.cin_buf, xreal = j.xreal, xpad = j.xpad;
   const int nks = cin_buf / 16;
   const int total = 3 * cin_buf * NB;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < NOUT) j.bias[idx] = j.bref[idx];
   if (idx >= total) return;
   const int r = idx % NB;
   const int c = (idx / NB) % cin_buf;
@@ -522,6 +537,15 @@ __global__ void pack_tc3_kernel(const float* __restrict__ wref, __nv_bfloat16* _
   }
 }
 
+__global__ void pack_tc3_kernel(const PackTc3Job j) { pack_tc3_body(j, blockIdx.x * blockDim.x + threadIdx.x); }
+
+// every recorded job in one launch (pack_batch.h)
+__global__ void pack_tc3_multi_kernel(const PackTc3Job* __restrict__ jobs, const int* __restrict__ first, int njobs) {
+  const int ji = pack_find_job(first, njobs, blockIdx.x);
+  const PackTc3Job j = jobs[ji];
+  pack_tc3_body(j, (blockIdx.x - __ldg(first + ji)) * blockDim.x + threadIdx.x);
+}
+
 // Input-gradient images of a dense block (training, BF16X3 mode), one per 32-channel SLOT of its buffer.  The gradient w.r.t. the
 // buffer channels c of a slot is the sum over the later convs k of conv_k^T(g_k): gx[c] = sum_k sum_{n,ky,kx} Wf_k[(2-ky)*3 + (2-kx)][c][n]
 // . g_k[n] at (y + ky - 1, x + kx - 1), Wf_k = conv k's forward weights in buffer-channel order [tap][cin_k][32] (conv_simt pack).  With the
@@ -533,10 +557,17 @@ struct DgradSlotSrc {
   const float* wf[4];      // forward packs of conv1..conv4
   int cin[4];              // their buffer-channel counts
 };
-__global__ void pack_tc3_dgrad_slot_kernel(const DgradSlotSrc src, __nv_bfloat16* __restrict__ img, int c0, int ncover, int nconv, int ngroups) {
+struct PackSlotJob {
+  DgradSlotSrc src;
+  __nv_bfloat16* img;
+  int c0, ncover, nconv, ngroups;
+};
+__device__ __forceinline__ void pack_tc3_dgrad_slot_body(const PackSlotJob& job, int idx) {
+  const DgradSlotSrc& src = job.src;
+  __nv_bfloat16* __restrict__ img = job.img;
+  const int c0 = job.c0, ncover = job.ncover, nconv = job.nconv, ngroups = job.ngroups;
   const int K = 32 * nconv;
   const int per = 3 * K * NB;                        // (ky, kk, r) of one group
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= per * ngroups) return;
   const int j = idx / per, e = idx - j * per;
   const int r = e % NB;
@@ -559,18 +590,43 @@ __global__ void pack_tc3_dgrad_slot_kernel(const DgradSlotSrc src, __nv_bfloat16
   img[off + tile] = lo;
 }
 
+__global__ void pack_tc3_dgrad_slot_kernel(const PackSlotJob j) { pack_tc3_dgrad_slot_body(j, blockIdx.x * blockDim.x + threadIdx.x); }
+
+// every recorded job in one launch (pack_batch.h)
+__global__ void pack_tc3_dgrad_slot_multi_kernel(const PackSlotJob* __restrict__ jobs, const int* __restrict__ first, int njobs) {
+  const int ji = pack_find_job(first, njobs, blockIdx.x);
+  const PackSlotJob j = jobs[ji];
+  pack_tc3_dgrad_slot_body(j, (blockIdx.x - __ldg(first + ji)) * blockDim.x + threadIdx.x);
+}
+
 }  // namespace tc3
 
 size_t tc3_dgrad_slot_image_bytes(int nconv) { return (size_t)2 * 3 * (2 * nconv) * tc3::WTILE_BYTES; }      // per 32-channel group: hi + lo, 3 ky
 
 int pack_tc3_dgrad_slot_images(const float* const wf[4], const int cin[4], void* img, int c0, int ncover, int nconv, cudaStream_t st) {
   SELFC_CHECK_ARG(nconv >= 1 && nconv <= 4 && ncover >= 1 && c0 >= 0, "dgrad slot images: bad slot");
-  tc3::DgradSlotSrc src;
-  for (int k = 0; k < 4; ++k) { src.wf[k] = wf[k]; src.cin[k] = cin[k]; }
+  tc3::PackSlotJob j;
+  memset(&j, 0, sizeof(j));      // (padding bytes too: the job tables are compared bytewise)
+  for (int k = 0; k < 4; ++k) { j.src.wf[k] = wf[k]; j.src.cin[k] = cin[k]; }
   const int ngroups = cdiv(ncover, 32);
   const int total = 3 * 32 * nconv * tc3::NB * ngroups;
-  tc3::pack_tc3_dgrad_slot_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(img), c0, ncover, nconv, ngroups);
+  j.img = reinterpret_cast<__nv_bfloat16*>(img); j.c0 = c0; j.ncover = ncover; j.nconv = nconv; j.ngroups = ngroups;
+  if (PackBatch* pb = pack_batch_current()) {
+    pb->slot[pb->point].add(j, (int)cdiv(total, 256));
+    return 0;
+  }
+  tc3::pack_tc3_dgrad_slot_kernel<<<cdiv(total, 256), 256, 0, st>>>(j);
   SELFC_LAUNCH_CHECK("pack_tc3_dgrad_slot_kernel");
+  return 0;
+}
+
+int flush_pack_dgrad_slot(JobTable& t, cudaStream_t st) {
+  if (t.njobs() <= 0) return 0;
+  const void* jobs = nullptr;
+  const int* first = nullptr;
+  SELFC_CUDA(t.sync(st, &jobs, &first));
+  tc3::pack_tc3_dgrad_slot_multi_kernel<<<t.first.back(), 256, 0, st>>>(static_cast<const tc3::PackSlotJob*>(jobs), first, t.njobs());
+  SELFC_LAUNCH_CHECK("pack_tc3_dgrad_slot_multi_kernel");
   return 0;
 }
 
@@ -681,11 +737,24 @@ int pack_tc_weights(TcConvW& w, const float* wref, const float* bref, int cin_re
   if (x2 && w.img_x2 == nullptr) SELFC_CUDA(cudaMalloc(&w.img_x2, 2 * bytes));
   w.cin_buf = cin_buf;
   const int total = 3 * cin_buf * tc3::NB;
-  tc3::pack_tc3_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, reinterpret_cast<__nv_bfloat16*>(w.img),
-                                                         reinterpret_cast<__nv_bfloat16*>(w.img_pair),
-                                                         x2 ? reinterpret_cast<__nv_bfloat16*>(w.img_x2) : nullptr, cin_ref, cin_buf, xreal, xpad);
+  const tc3::PackTc3Job j{wref, bref, reinterpret_cast<__nv_bfloat16*>(w.img), reinterpret_cast<__nv_bfloat16*>(w.img_pair),
+                          x2 ? reinterpret_cast<__nv_bfloat16*>(w.img_x2) : nullptr, w.bias, cin_ref, cin_buf, xreal, xpad};
+  if (PackBatch* pb = pack_batch_current()) {
+    pb->tc3[pb->point].add(j, (int)cdiv(total, 256));
+    return 0;
+  }
+  tc3::pack_tc3_kernel<<<cdiv(total, 256), 256, 0, st>>>(j);
   SELFC_LAUNCH_CHECK("pack_tc3_kernel");
-  SELFC_CUDA(cudaMemcpyAsync(w.bias, bref, tc3::NOUT * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int flush_pack_tc3(JobTable& t, cudaStream_t st) {
+  if (t.njobs() <= 0) return 0;
+  const void* jobs = nullptr;
+  const int* first = nullptr;
+  SELFC_CUDA(t.sync(st, &jobs, &first));
+  tc3::pack_tc3_multi_kernel<<<t.first.back(), 256, 0, st>>>(static_cast<const tc3::PackTc3Job*>(jobs), first, t.njobs());
+  SELFC_LAUNCH_CHECK("pack_tc3_multi_kernel");
   return 0;
 }
 

@@ -4,6 +4,7 @@
 // Orchestration restates SelfCInvNet.forward (models/modules/SelfC_GMM_arch_inv.py:450-490), InvBlockExp.forward
 // (:21-33), D2DTInput.forward (Subnet_constructor.py:115-133) and STPNet.forward (:358-394) as a fixed launch
 // sequence over pixel-major buffers; nothing here is a translation of reference code.
+#include <memory>
 #include <mutex>
 #include <new>
 #include <type_traits>
@@ -644,6 +645,27 @@ const GaW* find_ga(selfc_ctx* ctx, int first_param) {
 // =============================================================================================================
 // C-ABI
 // =============================================================================================================
+namespace selfc {
+PackBatch*& pack_batch_current() {
+  static thread_local PackBatch* cur = nullptr;
+  return cur;
+}
+int pack_batch_flush(PackBatch& b, cudaStream_t st) {
+  SELFC_CHECK_ARG(b.point < kPackFlushPoints, "pack batch: more than %d flush points", kPackFlushPoints);
+  SELFC_TRY(flush_pack_conv_simt(b.simt[b.point], st));
+  SELFC_TRY(flush_pack_tc3(b.tc3[b.point], st));
+  SELFC_TRY(flush_pack_dgrad_slot(b.slot[b.point], st));
+  SELFC_TRY(flush_pack_dgrad5_ref(b.ref5[b.point], st));
+  SELFC_TRY(flush_pack_temporal(b.temporal[b.point], st));
+  ++b.point;
+  return 0;
+}
+bool pack_batch_enabled() {
+  const char* e = getenv("SELFC_PACK_BATCH");
+  return !(e && atoi(e) == 0);
+}
+}  // namespace selfc
+
 extern "C" {
 
 int selfc_version(void) { return 100; }
@@ -689,8 +711,10 @@ int selfc_ctx_destroy(selfc_ctx* ctx) {
   if (ctx->train_zero_bias) cudaFree(ctx->train_zero_bias);
   if (ctx->wg_planes) cudaFree(ctx->wg_planes);
   if (ctx->dg_gslab) cudaFree(ctx->dg_gslab);
-  if (ctx->dg_wtmp) cudaFree(ctx->dg_wtmp);
+  ctx->pack.release();
+  ctx->pack_dg.release();
   auto free_dg = [](DenseW& W) {
+    if (W.dg5_tmp) cudaFree(W.dg5_tmp);
     for (int k = 0; k < 4; ++k)
       if (W.dg_img[k]) cudaFree(W.dg_img[k]);
     free_temporal_weights(W.dg5[0]);
@@ -759,6 +783,11 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
   SELFC_CUDA(cudaSetDevice(ctx->device));
   const int xp3 = ctx->xpad3;
   const bool x2 = ctx->mode == SELFC_MODE_BF16X3;
+  // the ~300 pack launches below are recorded and run as three launches per flush point (pack_batch.h).  A flush precedes every launch
+  // that overwrites something a recorded pack reads (the permuted head weights)
+  std::unique_ptr<PackBatchScope> batch_scope;
+  if (pack_batch_enabled()) batch_scope.reset(new PackBatchScope(ctx->pack));
+  auto flush_packs = [&]() -> int { return batch_scope ? pack_batch_flush(ctx->pack, st) : 0; };
 
   // plan the arena
   ArenaPlan pl;
@@ -861,6 +890,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
       for (int j = 0; j < 3; ++j)
         SELFC_TRY(pack_temporal_weights(ctx->head.t[2 + j], wperm + (size_t)240 * j * 256, bperm + 240 * j, 240, 256, 1, 256, 256, 256, st));
     }
+    SELFC_TRY(flush_packs());        // (the packs above read the first permutation)
     SELFC_TRY(launch_permute_gmm_rows(p[P_TAIL + 4], p[P_TAIL + 5], wperm, bperm, true, st));
     for (int k = 0; k < kGmmK; ++k)
       SELFC_TRY(pack_temporal_weights(ctx->head.g[k], wperm + (size_t)144 * k * 256, bperm + 144 * k, 144, 256, 1, 256, 256, 256, st, x2));
@@ -878,6 +908,7 @@ int selfc_ctx_load_weights(selfc_ctx* ctx, const float* const* p, int n_params, 
       SELFC_TRY(pack_temporal_weights(ctx->head.dg1, ctx->head.w[0], zero, 64, ctx->head.np[0], 1, 128, 128, 128, st, true));
     }
   }
+  SELFC_TRY(flush_packs());
   ctx->loaded = true;
   return 0;
 }

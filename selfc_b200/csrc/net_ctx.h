@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "conv_tc.h"
+#include "pack_batch.h"
 
 namespace selfc {
 
@@ -32,6 +33,7 @@ struct DenseW {            // one D2DTInput in kernel layout
   void* dg_img[4] = {};    // slots X, x1, x2, x3 of the buffer: pack_tc3_dgrad_slot_images (4, 3, 2, 1 contributing convs)
   TcTempW dg5[2];          // conv5: the buffer channels in two column groups (<= 96 each)
   int dg5_c0[2] = {}, dg5_n[2] = {};
+  float* dg5_tmp = nullptr; // conv5's flipped / transposed weights in reference layout, the source of dg5's images
   bool dg_valid = false;
 };
 struct GaW {
@@ -91,7 +93,8 @@ struct selfc_ctx {
   int wg_key[4] = {0, 0, 0, 0};
   void* dg_gslab = nullptr;      // the output gradient of one conv as (hi, lo) slabs (input of a tensor-core input-gradient launch)
   size_t dg_gslab_bytes = 0;
-  float* dg_wtmp = nullptr;      // conv5's flipped / transposed weights in reference layout while they are being packed
+  selfc::PackBatch pack;         // job tables of selfc_ctx_load_weights' batched weight packing (pack_batch.h)
+  selfc::PackBatch pack_dg;      // ... and of the training step's input-gradient images (train.cu)
   // optional per-launch timing (bench.py's roofline leg): CUDA events around every launch, by kernel class
   bool prof_on = false;
   std::vector<ProfRec> prof;

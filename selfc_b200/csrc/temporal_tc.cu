@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "conv_tc.h"
 #include "kernels.h"
+#include "pack_batch.h"
 #include "tc_ptx.cuh"
 
 namespace selfc {
@@ -642,12 +643,22 @@ __global__ void __launch_bounds__(THREADS, 1) temporal_tc_kernel(const __grid_co
 
 // wref [cout][cin_ref][taps] fp32 -> bf16 image [tap][kstep][kcore(2)][ngroup(npad/8)][n%8][k%8]
 // x2 (BF16X3 mode): [tap][kstep][hi|lo][kcore(2)][ngroup(npad/8)][n%8][k%8], hi = bf16(w), lo = bf16(w - hi)
-__global__ void pack_temporal_kernel(const float* __restrict__ wref, const float* __restrict__ bref, __nv_bfloat16* __restrict__ img,
-                                     float* __restrict__ bias, int cout, int cin_ref, int taps, int cin_buf, int xreal, int xpad,
-                                     int npad, int x2) {
+struct PackTemporalJob {
+  const float* wref;
+  const float* bref;
+  __nv_bfloat16* img;
+  float* bias;
+  int cout, cin_ref, taps, cin_buf, xreal, xpad, npad, x2;
+};
+
+__device__ __forceinline__ void pack_temporal_body(const PackTemporalJob& j, int idx) {
+  const float* __restrict__ wref = j.wref;
+  const float* __restrict__ bref = j.bref;
+  __nv_bfloat16* __restrict__ img = j.img;
+  float* __restrict__ bias = j.bias;
+  const int cout = j.cout, cin_ref = j.cin_ref, taps = j.taps, cin_buf = j.cin_buf, xreal = j.xreal, xpad = j.xpad, npad = j.npad, x2 = j.x2;
   const int nchunk = cin_buf / 16;
   const int total = taps * cin_buf * npad;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < npad) bias[idx] = idx < cout ? bref[idx] : 0.f;
   if (idx >= total) return;
   const int n = idx % npad;
@@ -670,6 +681,15 @@ __global__ void pack_temporal_kernel(const float* __restrict__ wref, const float
   img[off] = __float2bfloat16_rn(v);
 }
 
+__global__ void pack_temporal_kernel(const PackTemporalJob j) { pack_temporal_body(j, blockIdx.x * blockDim.x + threadIdx.x); }
+
+// every recorded job in one launch (pack_batch.h)
+__global__ void pack_temporal_multi_kernel(const PackTemporalJob* __restrict__ jobs, const int* __restrict__ first, int njobs) {
+  const int ji = pack_find_job(first, njobs, blockIdx.x);
+  const PackTemporalJob j = jobs[ji];
+  pack_temporal_body(j, (blockIdx.x - __ldg(first + ji)) * blockDim.x + threadIdx.x);
+}
+
 }  // namespace tc5
 
 int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int cout, int cin_ref, int taps, int cin_buf, int xreal,
@@ -685,9 +705,23 @@ int pack_temporal_weights(TcTempW& w, const float* wref, const float* bref, int 
   }
   w.cin_buf = cin_buf; w.npad = npad; w.taps = taps; w.cout = cout; w.x2 = x2;
   const int total = taps * cin_buf * npad;
-  tc5::pack_temporal_kernel<<<cdiv(total, 256), 256, 0, st>>>(wref, bref, reinterpret_cast<__nv_bfloat16*>(w.img), w.bias, cout, cin_ref,
-                                                              taps, cin_buf, xreal, xpad, npad, x2 ? 1 : 0);
+  const tc5::PackTemporalJob j{wref, bref, reinterpret_cast<__nv_bfloat16*>(w.img), w.bias, cout, cin_ref, taps, cin_buf, xreal, xpad, npad, x2 ? 1 : 0};
+  if (PackBatch* pb = pack_batch_current()) {
+    pb->temporal[pb->point].add(j, (int)cdiv(total, 256));
+    return 0;
+  }
+  tc5::pack_temporal_kernel<<<cdiv(total, 256), 256, 0, st>>>(j);
   SELFC_LAUNCH_CHECK("pack_temporal_kernel");
+  return 0;
+}
+
+int flush_pack_temporal(JobTable& t, cudaStream_t st) {
+  if (t.njobs() <= 0) return 0;
+  const void* jobs = nullptr;
+  const int* first = nullptr;
+  SELFC_CUDA(t.sync(st, &jobs, &first));
+  tc5::pack_temporal_multi_kernel<<<t.first.back(), 256, 0, st>>>(static_cast<const tc5::PackTemporalJob*>(jobs), first, t.njobs());
+  SELFC_LAUNCH_CHECK("pack_temporal_multi_kernel");
   return 0;
 }
 

@@ -292,12 +292,32 @@ size_t dense_bwd_scratch_floats(const DenseW& W) {
 // ---- tensor-core input gradients (BF16X3 mode) -------------------------------------------------------------------------
 // conv5: wd5[c][n][dt] = Wf5[((2 - dt) * cin_buf + c) * np + n] (n < cout, else 0): the flipped / transposed temporal weights in the
 // reference layout [cout' = buffer channel][cin' = nb][3] that pack_temporal_weights takes
-__global__ void dgrad5_ref_kernel(const float* __restrict__ wf, float* __restrict__ wd5, int cin_buf, int np, int cout, int nb) {
-  const int total = cin_buf * nb * 3;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+struct Dgrad5RefJob {
+  const float* wf;
+  float* wd5;
+  int cin_buf, np, cout, nb;
+};
+__device__ __forceinline__ void dgrad5_ref_body(const Dgrad5RefJob& j, int idx) {
+  const int total = j.cin_buf * j.nb * 3;
   if (idx >= total) return;
-  const int dt = idx % 3, n = (idx / 3) % nb, c = idx / (3 * nb);
-  wd5[idx] = n < cout ? wf[((size_t)(2 - dt) * cin_buf + c) * np + n] : 0.f;
+  const int dt = idx % 3, n = (idx / 3) % j.nb, c = idx / (3 * j.nb);
+  j.wd5[idx] = n < j.cout ? j.wf[((size_t)(2 - dt) * j.cin_buf + c) * j.np + n] : 0.f;
+}
+__global__ void dgrad5_ref_kernel(const Dgrad5RefJob j) { dgrad5_ref_body(j, blockIdx.x * blockDim.x + threadIdx.x); }
+// every recorded job in one launch (pack_batch.h)
+__global__ void dgrad5_ref_multi_kernel(const Dgrad5RefJob* __restrict__ jobs, const int* __restrict__ first, int njobs) {
+  const int ji = pack_find_job(first, njobs, blockIdx.x);
+  const Dgrad5RefJob j = jobs[ji];
+  dgrad5_ref_body(j, (blockIdx.x - __ldg(first + ji)) * blockDim.x + threadIdx.x);
+}
+int flush_pack_dgrad5_ref(JobTable& t, cudaStream_t st) {
+  if (t.njobs() <= 0) return 0;
+  const void* jobs = nullptr;
+  const int* first = nullptr;
+  SELFC_CUDA(t.sync(st, &jobs, &first));
+  dgrad5_ref_multi_kernel<<<t.first.back(), 256, 0, st>>>(static_cast<const Dgrad5RefJob*>(jobs), first, t.njobs());
+  SELFC_LAUNCH_CHECK("dgrad5_ref_multi_kernel");
+  return 0;
 }
 // fp32 pixel-major [M][spitch] columns [0, ncol) -> (hi, lo) slabs [nb / 16][M], columns >= ncol zero
 __global__ void cols_to_slab_kernel(bfx2* __restrict__ dst, int nb, const float* __restrict__ src, int spitch, int ncol, long long M) {
@@ -327,14 +347,20 @@ static int ensure_dgrad_images(const selfc_ctx* cctx, const DenseW& cW, float* z
     SELFC_TRY(pack_tc3_dgrad_slot_images(wf, cins, W.dg_img[sl], c0, ncover, nconv, st));
   }
   const int cin5 = W.xpad + 4 * kGrowth, nb = (W.cout + 15) & ~15;
-  if (ctx->dg_wtmp == nullptr) SELFC_CUDA(cudaMalloc(&ctx->dg_wtmp, (size_t)192 * 64 * 3 * sizeof(float)));
-  dgrad5_ref_kernel<<<cdiv(cin5 * nb * 3, 256), 256, 0, st>>>(W.w[4], ctx->dg_wtmp, cin5, W.np[4], W.cout, nb);
-  SELFC_LAUNCH_CHECK("dgrad5_ref_kernel");
+  // (one scratch per block: with the packs batched (pack_batch.h) every block's flipped weights exist at the same time)
+  if (W.dg5_tmp == nullptr) SELFC_CUDA(cudaMalloc(&W.dg5_tmp, (size_t)192 * 64 * 3 * sizeof(float)));
+  const Dgrad5RefJob rj{W.w[4], W.dg5_tmp, cin5, W.np[4], W.cout, nb};
+  if (PackBatch* pb = pack_batch_current()) {
+    pb->ref5[pb->point].add(rj, (int)cdiv(cin5 * nb * 3, 256));
+  } else {
+    dgrad5_ref_kernel<<<cdiv(cin5 * nb * 3, 256), 256, 0, st>>>(rj);
+    SELFC_LAUNCH_CHECK("dgrad5_ref_kernel");
+  }
   W.dg5_c0[0] = 0; W.dg5_n[0] = cin5 > 96 ? 96 : cin5;
   W.dg5_c0[1] = W.dg5_n[0]; W.dg5_n[1] = cin5 - W.dg5_n[0];
   for (int gI = 0; gI < 2; ++gI)
     if (W.dg5_n[gI] > 0)
-      SELFC_TRY(pack_temporal_weights(W.dg5[gI], ctx->dg_wtmp + (size_t)W.dg5_c0[gI] * nb * 3, zero_bias, W.dg5_n[gI], nb, 3, nb, nb, nb, st, true));
+      SELFC_TRY(pack_temporal_weights(W.dg5[gI], W.dg5_tmp + (size_t)W.dg5_c0[gI] * nb * 3, zero_bias, W.dg5_n[gI], nb, 3, nb, nb, nb, st, true));
   W.dg_valid = true;
   return 0;
 }
@@ -1393,6 +1419,18 @@ int train_grads(selfc_ctx* ctx, const float* hr, const float* ref_l, const float
   SELFC_TRY(up_hooked<E>(ctx, lrq, eps, seed, offset, rec, d, wsp, ws, st, &hooks));
 
   // ---- backward ----
+  // input-gradient images of all 30 dense blocks, stale since the weight load of this step: three launches instead of seven per block
+  if constexpr (std::is_same<E, bfx2>::value) {
+    if (dgrad_tc_on() && pack_batch_enabled()) {
+      float* zb = train_zero_bias(ctx);
+      SELFC_CHECK_ARG(zb != nullptr, "out of device memory (training scratch)");
+      PackBatchScope scope(ctx->pack_dg);
+      for (int blk = 0; blk < 8; ++blk)
+        for (int j = 0; j < 3; ++j) SELFC_TRY(ensure_dgrad_images(ctx, ctx->inv[blk][j], zb, st));
+      for (int i = 0; i < 6; ++i) SELFC_TRY(ensure_dgrad_images(ctx, ctx->stp[i], zb, st));
+      SELFC_TRY(pack_batch_flush(ctx->pack_dg, st));
+    }
+  }
   loss_back_fa_bwd_kernel<<<cdiv(M, 128), 128, 0, st>>>(hr, rec, gz, lacc, kScale / n_hr, BT, d.h, d.w);
   SELFC_LAUNCH_CHECK("loss_back_fa_bwd_kernel");
   for (int blk = 0; blk < 8; ++blk)            // the reverse pass ran blocks 7..0, so their backward runs 0..7
