@@ -475,8 +475,8 @@ def measure_train(dev, world: int, rank: int, steps: int, warmup: int, b: int, t
             "dtype": "f32" if train_mode == "fp32" else "bf16x3 (fp32 master weights, gradients and state)", "mode": train_mode,
             "gpu_launches": int(launches), "loss": float(losses[0].item()),
             "algorithmic_tflops": flop * steps / (ms_total / 1e3) / 1e12,
-            "what": "SelfC-large training step on synthetic 7x256x448 septuplets (BASELINE.json configs[3]): forward + recompute-based "
-                    "backward (" + TRAIN_MODE_WHAT[train_mode] + "), ONE NCCL all-reduce of the flat 3.37M-element gradient, clip, Adam; "
+            "what": "SelfC-large training step on synthetic 7x256x448 septuplets (BASELINE.json configs[3]): forward + backward "
+                    "(the coupling blocks' activations kept, the STP blocks' recomputed; " + TRAIN_MODE_WHAT[train_mode] + "), ONE NCCL all-reduce of the flat 3.37M-element gradient, clip, Adam; "
                     "device-timed, max over ranks"}
 
 
@@ -508,7 +508,7 @@ def run_train(args):
                 "unit": "septuplets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": m["dtype"], "data": "synthetic",
                 "config": {"workload": f"SelfC-large training step, {b} synthetic Vimeo90K-shape septuplet(s) per GPU per step, {m['mode']} mode "
-                                       f"({TRAIN_MODE_WHAT[m['mode']]}, recompute-based backward), one NCCL all-reduce of the flat 3.37M-element gradient",
+                                       f"({TRAIN_MODE_WHAT[m['mode']]}; coupling-block activations kept, STP blocks recomputed in the backward), one NCCL all-reduce of the flat 3.37M-element gradient",
                            "septuplets_per_step_per_gpu": b, "weights": "seeded random, reference state_dict layout"},
                 "clocks": clocks, "gpu_launches": m["gpu_launches"], "loss": m["loss"], "allreduce_ms": m["allreduce_ms"],
                 "algorithmic_tflops": m["algorithmic_tflops"]}
