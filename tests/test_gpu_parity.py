@@ -813,6 +813,46 @@ def test_conv3x3_variants_are_bit_identical(dev, tmp_path, env):
     assert torch.equal(outs[0]["rec"], outs[1]["rec"])
 
 
+_PACK_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import selfc_oracle as so
+from selfc_b200.engine import Engine
+dev = torch.device("cuda", 0)
+x = so.make_frames(1, 3, 40, 72, 5).to(dev)
+out = {}
+for mode in ("bf16", "bf16x3", "fp32"):
+    eng = Engine(dev, mode); eng.load_state(so.make_state_dict(2))
+    lr, rec = eng.rescale(x, 3, seed=7, offset=1)
+    out[mode + ".lr"], out[mode + ".rec"] = lr.cpu(), rec.cpu()
+    eng.load_state(so.make_state_dict(4))          # a second load into the same context: other values through the same job tables
+    lr, rec = eng.rescale(x, 3, seed=7, offset=1)
+    out[mode + ".lr2"], out[mode + ".rec2"] = lr.cpu(), rec.cpu()
+torch.save(out, sys.argv[1])
+"""
+
+
+def test_batched_weight_packing_is_bit_identical(dev, tmp_path):
+    """selfc_ctx_load_weights records its ~300 pack jobs and runs each kind in one launch (csrc/pack_batch.h); SELFC_PACK_BATCH=0 packs
+    tensor by tensor as before.  Same images either way: all three modes must give bit-identical LR codes and HR frames, also after a
+    second load into the same context (the cached job tables are reused; the weights differ)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for i, v in enumerate(("1", "0")):
+        out = str(tmp_path / f"p{i}.pt")
+        e = dict(os.environ)
+        e["SELFC_PACK_BATCH"] = v
+        r = subprocess.run([sys.executable, "-c", _PACK_SNIPPET % here, out], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(out))
+    assert set(outs[0]) == set(outs[1]) and len(outs[0]) == 12
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert not torch.equal(outs[0]["bf16.rec"], outs[0]["bf16.rec2"])      # the second load did change the weights
+
+
 _FUSED_SNIPPET = r"""
 import sys, torch
 sys.path.insert(0, %r)
