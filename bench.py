@@ -394,9 +394,12 @@ def run_ours(args):
         del group, lr_out, hr_out
         torch.cuda.empty_cache()
         train_block = measure_train(dev, world, rank, steps=3, warmup=2, b=1)
-        # the same step with four septuplets per rank: at one septuplet the step is bound by per-launch latencies (3,600 launches over 50 K pixels)
+        # the same step with four septuplets per rank: at one septuplet the step is bound by per-launch latencies (2,100 launches over 50 K
+        # pixels); four per GPU is also what the reference trains with (train_rescaling_selfc_large.yml:12,26: batch_size 8 on gpu_ids [0,1])
         b4 = measure_train(dev, world, rank, steps=2, warmup=1, b=4)
         train_block["four_septuplets_per_step"] = {k: b4[k] for k in ("septuplets_per_s", "ms_per_step", "allreduce_ms", "septuplets_per_step_per_gpu")}
+        train_block["four_septuplets_per_step"]["why"] = ("the reference's per-GPU batch (options/train/train_rescaling_selfc_large.yml: "
+                                                          "batch_size 8 on gpu_ids [0,1])")
 
     if rank != 0:
         if world > 1:
