@@ -1,5 +1,5 @@
 // Weight packing as a handful of launches.  selfc_ctx_load_weights packs ~300 weight tensors into the images the kernels read; a
-// training step does that after every optimiser step, and one tiny launch (+ one 128-byte copy) per tensor was 10 % of the step.  While a
+// training step does that after every optimiser step, and one tiny launch (+ one 128-byte copy) per tensor was 7 % of the step.  While a
 // PackBatch is current (pack_batch_current()), launch_pack_conv_simt / pack_tc_weights / pack_temporal_weights only RECORD a job; the
 // flush runs every job of a kind in ONE launch (a block looks its job up in a table of first-block offsets).  The job tables live in
 // device memory owned by the context and are uploaded only when they differ from what is there (step after step they do not).
