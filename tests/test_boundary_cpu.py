@@ -253,3 +253,30 @@ def test_bf16x3_arithmetic_restated_on_the_host():
     scale = float(ref.abs().max())
     err_x3, err_bf = float((x3 - ref).abs().max()) / scale, float((bf - ref).abs().max()) / scale
     assert err_x3 <= 1e-5 and err_bf >= 50 * err_x3, (err_x3, err_bf)
+
+
+def test_dependent_launch_kernels_wait_for_their_predecessor():
+    """Source lint for the programmatic-dependent-launch discipline (csrc/tc_ptx.cuh `launch_pdl*`, csrc/wgrad_tc.h `launch_chain`): a
+    kernel launched with the stream-serialisation attribute may start before the previous kernel of the stream has finished, so its body
+    must execute `griddepcontrol.wait` (`pdl_wait()` / `chain_entry()`) -- a kernel without it would read its predecessor's output early
+    and no parity test is guaranteed to catch the race."""
+    import glob
+    import re
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = {p: open(p).read() for p in glob.glob(os.path.join(here, "selfc_b200", "csrc", "*.cu"))}
+    launched = set()
+    for text in src.values():
+        for m in re.finditer(r"launch_(?:chain|pdl|pdl_pairs)\(([^;]*?);", text, re.S):
+            launched.update(re.findall(r"(\w+_kernel)\b", m.group(1)))
+    launched.add("dense_fused_kernel")            # launched through a function pointer chosen by template arguments
+    assert {"conv3x3_tc3_kernel", "temporal_tc_kernel", "wgrad_tc_kernel", "wg_planes_grad_kernel", "wg_planes_act_kernel",
+            "lrelu_bwd_kernel", "wgrad_unpack_kernel", "cols_to_slab_kernel"} <= launched, launched
+    for name in sorted(launched):
+        bodies = []
+        for text in src.values():
+            for m in re.finditer(r"__global__[^;{]*?\b" + name + r"\s*\(", text, re.S):
+                end = text.find("\n}\n", m.end())
+                bodies.append(text[m.end():end])
+        assert bodies, f"no definition of {name} found"
+        for body in bodies:
+            assert "pdl_wait()" in body or "chain_entry()" in body, f"{name} is launched as a dependent launch but never waits"
